@@ -1,0 +1,132 @@
+"""ctypes front-end of the C oracle (`oracle/ssd_oracle.c`).
+
+TEST INFRASTRUCTURE (oracle/): used by tests/, bench.py's cpu_baseline / `--impl reference`
+leg and `__graft_entry__.smoke()` only — never by the product path.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libssd_oracle.so")
+_LIB = None
+
+KIND = {"cleanup": 0, "harvest": 1}
+CONTRACT = {None: 0, "none": 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2}
+METRIC_STRIDE = 8 + 6 * 8
+
+
+def build(force=False):
+    """Compile the oracle with the system gcc (the image's $CC has no OpenMP runtime)."""
+    src = os.path.join(_HERE, "ssd_oracle.c")
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(src):
+        return _SO
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    base = [cc, "-O2", "-std=c11", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO, src, "-lm"]
+    try:
+        subprocess.run(base[:4] + ["-fopenmp"] + base[4:], check=True, capture_output=True)
+    except (subprocess.CalledProcessError, FileNotFoundError):
+        subprocess.run(base, check=True)
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        vp, i32, u32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+        L.oracle_create.restype = vp
+        L.oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
+        L.oracle_destroy.argtypes = [vp]
+        L.oracle_reset.argtypes = [vp, vp, vp, vp]
+        L.oracle_step.argtypes = [vp] * 9
+        L.oracle_get_state.argtypes = [vp] * 6
+        L.oracle_set_state.argtypes = [vp] * 6
+        L.oracle_get_metrics.argtypes = [vp, vp]
+        L.oracle_feature_dim.argtypes = [vp]
+        L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32).copy()
+    k = np.asarray(key, dtype=np.uint32).copy()
+    out = np.zeros(4, dtype=np.uint32)
+    lib().oracle_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+class GridOracle:
+    """E independent cleanup_new / harvest_new envs (+ optional subgame contract wrapper)."""
+
+    def __init__(self, kind, num_envs, num_agents, ascii_map, horizon=1000, contract=None,
+                 theta_low=0.0, theta_high=None, null_prob=0.0, seed=73907, first_env_id=0):
+        self.kind = kind
+        self.E, self.n = int(num_envs), int(num_agents)
+        self.H, self.W = len(ascii_map), len(ascii_map[0])
+        if theta_high is None:      # gym Box stores float32 bounds (contract_list.py:20,43)
+            theta_high = float(np.float32(0.2)) if kind == "cleanup" else float(np.float32(10.0))
+        flat = "".join(ascii_map).encode("ascii")
+        self._h = lib().oracle_create(KIND[kind], self.E, self.n, self.H, self.W, flat, int(horizon),
+                                      CONTRACT[contract], float(theta_low), float(theta_high),
+                                      float(null_prob), int(seed) & 0xFFFFFFFF, int(first_env_id))
+        if not self._h:
+            raise ValueError("oracle_create failed (bad sizes / map)")
+        self.F = lib().oracle_feature_dim(self._h)
+        self.episode = np.full(self.E, -1, dtype=np.int64)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        sel = np.ones(self.E, bool) if m is None else m.astype(bool)
+        self.episode[sel] += 1
+        ep = self.episode.astype(np.uint32)
+        obs = np.zeros((self.E, self.n, 15, 15, 3), dtype=np.uint8)
+        lib().oracle_reset(self._h, _p(m), _p(ep), _p(obs))
+        return obs
+
+    def step(self, actions, want_features=True):
+        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.E, self.n)
+        E, n = self.E, self.n
+        out = {
+            "obs": np.zeros((E, n, 15, 15, 3), np.uint8), "rew": np.zeros((E, n)),
+            "base_rew": np.zeros((E, n)), "transfers": np.zeros((E, n)),
+            "info": np.zeros((E, n, 4), np.int32), "done": np.zeros(E, np.uint8),
+            "feature_obs": np.zeros((E, n, self.F)) if want_features else None,
+        }
+        lib().oracle_step(self._h, _p(a), _p(out["obs"]), _p(out["rew"]), _p(out["base_rew"]),
+                          _p(out["transfers"]), _p(out["info"]), _p(out["feature_obs"]), _p(out["done"]))
+        return out
+
+    def get_state(self):
+        E, n = self.E, self.n
+        st = {"map": np.zeros((E, self.H, self.W), np.uint8), "pos": np.zeros((E, n, 2), np.int32),
+              "ori": np.zeros((E, n), np.int32), "t": np.zeros(E, np.int32), "theta": np.zeros(E)}
+        lib().oracle_get_state(self._h, _p(st["map"]), _p(st["pos"]), _p(st["ori"]), _p(st["t"]), _p(st["theta"]))
+        return st
+
+    def set_state(self, map=None, pos=None, ori=None, t=None, theta=None):
+        def prep(x, dt, shape):
+            return None if x is None else np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dt), shape))
+        E, n = self.E, self.n
+        m, p, o = prep(map, np.uint8, (E, self.H, self.W)), prep(pos, np.int32, (E, n, 2)), prep(ori, np.int32, (E, n))
+        tt, th = prep(t, np.int32, (E,)), prep(theta, np.float64, (E,))
+        lib().oracle_set_state(self._h, _p(m), _p(p), _p(o), _p(tt), _p(th))
+
+    def metrics_raw(self):
+        out = np.zeros((self.E, METRIC_STRIDE))
+        lib().oracle_get_metrics(self._h, _p(out))
+        return out

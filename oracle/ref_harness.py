@@ -1,0 +1,316 @@
+"""Run the UNMODIFIED reference env code under counter-based RNG injection.
+
+TEST INFRASTRUCTURE (oracle/), container-only (needs `/root/reference`).  This is the
+ground truth that pins both the C oracle (`oracle/ssd_oracle.c`) and the CUDA path: every
+RNG call site of SURVEY.md §8a table R is monkey-patched (no reference source is edited or
+copied) to read from the Philox stream defined in `oracle/philox.py`.  The golden vectors in
+`tests/golden/` are produced from here by `oracle/make_golden.py`.
+
+Patched names and the reference call sites they serve:
+  np.random.shuffle  <- map_env.py:546 (R1), :685 (R2), :821 (R7); cleanup_new.py:339 (R4)
+  np.random.randint  <- map_env.py:831 (R6); cleanup_features.py:109 / harvest_features.py:122 (R11)
+  np.random.rand / np.random.uniform <- two_stage_train.py:163-164 (R8)
+  environments.cleanup_new.rand / environments.harvest_new.rand <- cleanup_new.py:326, harvest_new.py:294 (R3/R5)
+  random.sample / random.random <- two_stage_train.py:271,276 (R9); self_driving_car_accelerate.py:53,57 (R10);
+                                   cleanup_features.py:115,122 / harvest_features.py:148 (R11)
+  random.shuffle     <- cleanup_features.py:107 / harvest_features.py:118 (R11)
+"""
+import random as _pyrandom
+import sys
+
+import numpy as np
+
+from . import philox as px
+from . import ref_stubs
+
+_CTX = None          # active DrawContext (None -> original RNG functions run)
+_INSTALLED = False
+_ORIG = {}
+
+
+class DrawContext:
+    """Identifies the Philox stream position of the env currently being driven."""
+
+    def __init__(self, seed, env_id):
+        self.seed = int(seed)
+        self.env_id = int(env_id)
+        self.episode = px.EPISODE_CONSTRUCT
+        self.t = 0
+        self.calls = {}
+
+    def begin(self, episode, t):
+        self.episode = int(episode)
+        self.t = int(t)
+        self.calls = {}
+
+    def next_call(self, site):
+        c = self.calls.get(site, 0)
+        self.calls[site] = c + 1
+        return c
+
+    def u32(self, site, call, idx):
+        return px.draws_u32(self.seed, self.env_id, self.episode, self.t, site, call, idx)
+
+    def f64(self, site, call, idx):
+        return px.draws_f64(self.seed, self.env_id, self.episode, self.t, site, call, idx)
+
+
+class active:
+    """`with active(ctx):` routes the patched RNG names to ctx."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def __enter__(self):
+        global _CTX
+        self.prev = _CTX
+        _CTX = self.ctx
+        return self.ctx
+
+    def __exit__(self, *a):
+        global _CTX
+        _CTX = self.prev
+
+
+def _caller_name(depth=2):
+    return sys._getframe(depth).f_code.co_name
+
+
+def _stateless_shuffle(x, site, canonical_sort):
+    ctx = _CTX
+    if canonical_sort:
+        x.sort()
+    call = ctx.next_call(site)
+    keys = ctx.u32(site, call, np.arange(len(x)))
+    order = np.argsort(keys, kind="stable")
+    x[:] = [x[i] for i in order]
+
+
+def _np_shuffle(x):
+    if _CTX is None:
+        return _ORIG["np.shuffle"](x)
+    who = _caller_name()
+    if who == "update_moves":
+        _stateless_shuffle(x, px.SITE_MOVE_ORDER, False)
+    elif who == "update_custom_moves":
+        _stateless_shuffle(x, px.SITE_BEAM_ORDER, False)
+    elif who == "spawn_apples_and_waste":
+        _stateless_shuffle(x, px.SITE_WASTE_ORDER, True)
+    elif who == "spawn_point":
+        _stateless_shuffle(x, px.SITE_SPAWN_POINT, True)
+    else:
+        raise RuntimeError("np.random.shuffle from unexpected site %r" % who)
+
+
+def _np_randint(*args, **kw):
+    if _CTX is None:
+        return _ORIG["np.randint"](*args, **kw)
+    who = _caller_name()
+    if who == "spawn_rotation":          # map_env.py:831  randint(4)
+        site = px.SITE_SPAWN_ROT
+    elif who in ("reset", "initialize_players"):   # feature envs: randint(0, 4)
+        site = px.SITE_FEAT_ROT
+    else:
+        raise RuntimeError("np.random.randint from unexpected site %r" % who)
+    call = _CTX.next_call(site)
+    return int(_CTX.u32(site, call, 0)[0] >> np.uint32(30))
+
+
+def _np_rand(*shape):
+    if _CTX is None:
+        return _ORIG["np.rand"](*shape)
+    if shape:
+        raise RuntimeError("np.random.rand(shape) from unexpected site %r" % _caller_name())
+    return float(_CTX.f64(px.SITE_CONTRACT, 0, 0)[0])       # two_stage_train.py:163
+
+
+def _np_uniform(low=0.0, high=1.0, size=None):
+    if _CTX is None:
+        return _ORIG["np.uniform"](low, high, size)
+    u = _CTX.f64(px.SITE_CONTRACT, 0, 1)[0]                   # two_stage_train.py:164
+    low64 = np.asarray(low, dtype=np.float64)
+    high64 = np.asarray(high, dtype=np.float64)
+    return low64 + (high64 - low64) * u
+
+
+def _spawn_rand(k):
+    """Replacement for the module-level `rand` of cleanup_new / harvest_new (R3/R5)."""
+    if _CTX is None:
+        return _ORIG["np.rand"](k)
+    return _CTX.f64(px.SITE_SPAWN_DRAWS, 0, np.arange(k))
+
+
+def _py_random():
+    if _CTX is None:
+        return _ORIG["py.random"]()
+    who = _caller_name()
+    if who == "step":                      # two_stage_train.py:276 (negotiate)
+        return float(_CTX.f64(px.SITE_NEGOTIATE, 1, 0)[0])
+    if who == "reset":                     # self_driving_car_accelerate.py:53,57: one draw per agent
+        call = _CTX.next_call(px.SITE_SELFDRIVE_RESET)
+        return float(_CTX.f64(px.SITE_SELFDRIVE_RESET, 0, call)[0])
+    if who in ("spawn_apples_and_waste", "spawn_apples"):   # feature envs, sequential draws
+        call = _CTX.next_call(px.SITE_FEAT_SPAWN)
+        return float(_CTX.f64(px.SITE_FEAT_SPAWN, 0, call)[0])
+    raise RuntimeError("random.random from unexpected site %r" % who)
+
+
+def _py_sample(population, k):
+    if _CTX is None:
+        return _ORIG["py.sample"](population, k)
+    pop = list(population)                 # two_stage_train.py:271  random.sample(range(1, n), 2)
+    keys = _CTX.u32(px.SITE_NEGOTIATE, 0, np.arange(len(pop)))
+    order = np.argsort(keys, kind="stable")
+    return [pop[i] for i in order[:k]]
+
+
+def _py_shuffle(x):
+    if _CTX is None:
+        return _ORIG["py.shuffle"](x)
+    _stateless_shuffle(x, px.SITE_FEAT_ORDER, False)
+
+
+def install():
+    """Import the reference under stubs and patch its RNG call sites (idempotent)."""
+    global _INSTALLED
+    if _INSTALLED:
+        return
+    ref_stubs.install()
+    import environments.cleanup_new as cn
+    import environments.harvest_new as hn
+    _ORIG.update({
+        "np.shuffle": np.random.shuffle, "np.randint": np.random.randint,
+        "np.rand": np.random.rand, "np.uniform": np.random.uniform,
+        "py.random": _pyrandom.random, "py.sample": _pyrandom.sample,
+        "py.shuffle": _pyrandom.shuffle,
+    })
+    np.random.shuffle = _np_shuffle
+    np.random.randint = _np_randint
+    np.random.rand = _np_rand
+    np.random.uniform = _np_uniform
+    cn.rand = _spawn_rand
+    hn.rand = _spawn_rand
+    _pyrandom.random = _py_random
+    _pyrandom.sample = _py_sample
+    _pyrandom.shuffle = _py_shuffle
+    _INSTALLED = True
+
+
+ORI_INT = {"UP": 0, "RIGHT": 1, "DOWN": 2, "LEFT": 3}
+
+
+class RefGridEnv:
+    """One reference CleanupEnv / HarvestEnv (+ optional SeparateContractSubgameStage) under injection.
+
+    kind: 'cleanup' | 'harvest'.  contract: None (bare base env) or True (the contract the
+    BASELINE configs pair with the env: CleanupContract / HarvestFeaturemodLocalContract).
+    """
+
+    def __init__(self, kind, num_agents, seed, env_id, contract=True, ascii_map=None,
+                 null_prob=0.0, **env_kwargs):
+        install()
+        from utils.env_creator_functions import env_creator
+        import contract.contract_list as cl
+        self.kind = kind
+        self.n = num_agents
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        cfg = dict(num_agents=num_agents, env_params={}, image_obs=True)
+        if ascii_map is not None:
+            cfg["ascii_map"] = ascii_map
+        cfg.update(env_kwargs)
+        with active(self.ctx):
+            self.ctx.begin(px.EPISODE_CONSTRUCT, 0)
+            self.base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew", cfg)
+            if contract:
+                c = cl.CleanupContract(num_agents) if kind == "cleanup" \
+                    else cl.HarvestFeaturemodLocalContract(num_agents)
+                self.env = env_creator("ContractWrapperSubgame", dict(
+                    num_agents=num_agents, base_env=self.base, contract=c, convolutional=True,
+                    null_prob=null_prob))
+                orig = c.compute_transfer
+
+                def capture(obs, acts, rews, params, infos=None):
+                    self._base_rew = dict(rews)
+                    tr = orig(obs, acts, rews, params, infos)
+                    self._transfers = dict(tr)
+                    return tr
+                c.compute_transfer = capture
+            else:
+                self.env = self.base
+        self.wrapped = bool(contract)
+        self.keys = ["a%d" % i for i in range(num_agents)]
+
+    # -- state snapshot ---------------------------------------------------------------------
+    def _snapshot(self, obs):
+        b = self.base
+        out = {
+            "map": np.frombuffer(b.world_map.tobytes(), dtype=np.uint8).reshape(b.world_map.shape).copy(),
+            "pos": np.array([b.agents[k].pos for k in self.keys], dtype=np.int32),
+            "ori": np.array([ORI_INT[b.agents[k].orientation] for k in self.keys], dtype=np.int32),
+            "obs": np.stack([np.rint(obs[k]["image"] * 255.0).astype(np.uint8) for k in self.keys]),
+            "t": int(b.timesteps),
+        }
+        if self.wrapped:
+            out["theta"] = np.float64(self.env.params["a0"][0])
+            out["contract_obs"] = np.stack([np.asarray(obs[k]["contract"], dtype=np.float64) for k in self.keys])
+        return out
+
+    def reset(self):
+        self.episode += 1
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        return self._snapshot(obs)
+
+    def step(self, actions):
+        acts = {k: int(a) for k, a in zip(self.keys, actions)}
+        with active(self.ctx):
+            self.ctx.begin(self.episode, self.base.timesteps + 1)
+            obs, rew, done, info = self.env.step(acts)
+        out = self._snapshot(obs)
+        out["rew"] = np.array([rew[k] for k in self.keys], dtype=np.float64)
+        out["done"] = bool(done["__all__"])
+        out["eaten_apples"] = np.array([info[k]["eaten_apples"] for k in self.keys], dtype=np.int32)
+        if self.kind == "cleanup":
+            out["cleaned_squares"] = np.array([info[k]["cleaned_squares"] for k in self.keys], dtype=np.int32)
+        else:
+            out["eaten_close_apples"] = np.array([info[k]["eaten_close_apples"] for k in self.keys], dtype=np.int32)
+        out["feature_obs"] = np.stack([np.asarray(info[k]["feature_obs"], dtype=np.float64) for k in self.keys])
+        if self.wrapped:
+            out["base_rew"] = np.array([self._base_rew[k] for k in self.keys], dtype=np.float64)
+            out["transfers"] = np.array([self._transfers[k] for k in self.keys], dtype=np.float64)
+        return out
+
+    def metrics(self):
+        return {k: float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v)
+                for k, v in self.base.metrics.items()}
+
+    # -- state injection (for adversarial scenario tests) -------------------------------------
+    def set_state(self, world_map=None, pos=None, ori=None):
+        """Overwrite grid / agent state in place, keeping world_map_color consistent."""
+        b = self.base
+        inv = {v: k for k, v in ORI_INT.items()}
+        # un-paint agents (map_env.py:238-240 does the same at step start)
+        for a in b.agents.values():
+            b.single_update_world_color_map(a.pos[0], a.pos[1], b.world_map[a.pos[0], a.pos[1]])
+        if world_map is not None:
+            wm = np.asarray(world_map, dtype=np.uint8)
+            for r in range(wm.shape[0]):
+                for c in range(wm.shape[1]):
+                    b.single_update_map(r, c, bytes([wm[r, c]]))
+        if pos is not None:
+            for k, p in zip(self.keys, pos):
+                b.agents[k].set_pos(np.array(p))
+        if ori is not None:
+            for k, o in zip(self.keys, ori):
+                b.agents[k].set_orientation(inv[int(o)])
+        # refresh the caches the next step's infos depend on (same calls custom_reset makes)
+        b.compute_current_apples()
+        if self.kind == "cleanup":
+            b.compute_current_wastes()
+        mwa = b.get_map_with_agents()
+        for a in b.agents.values():
+            a.full_map = mwa
+            if b.world_map[a.pos[0], a.pos[1]] not in [b"F", b"C"]:
+                b.single_update_world_color_map(a.pos[0], a.pos[1], a.get_char_id())
