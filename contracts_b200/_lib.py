@@ -1,0 +1,94 @@
+"""ctypes binding of libssd_b200.so (the C ABI declared in include/ssd_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or no GPU is present every entry
+point raises.  The library is built in-tree by `contracts_b200.build.build()` /
+`__graft_entry__.build()`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
+
+SSD_ABI_VERSION = 1
+ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "selfdrive": 4}
+CONTRACT_KIND = {None: 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2,
+                 "SelfdriveContractDistprop": 3}
+OBS_BYTES_PER_AGENT = 675
+METRIC_STRIDE = 56
+
+
+class SsdError(RuntimeError):
+    pass
+
+
+class ssd_config(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("env_kind", ctypes.c_int32), ("num_envs", ctypes.c_int32),
+        ("num_agents", ctypes.c_int32), ("map_h", ctypes.c_int32), ("map_w", ctypes.c_int32),
+        ("ascii_map", ctypes.c_char_p), ("horizon", ctypes.c_int32), ("contract_kind", ctypes.c_int32),
+        ("theta_low", ctypes.c_double), ("theta_high", ctypes.c_double), ("null_prob", ctypes.c_double),
+        ("seed", ctypes.c_uint32), ("first_env_id", ctypes.c_uint32), ("device", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
+    ]
+
+
+class ssd_step_io(ctypes.Structure):
+    _fields_ = [
+        ("actions_dev", ctypes.c_void_p), ("obs_dev", ctypes.c_void_p), ("obs_env_stride", ctypes.c_int64),
+        ("rew_dev", ctypes.c_void_p), ("base_rew_dev", ctypes.c_void_p), ("transfers_dev", ctypes.c_void_p),
+        ("info_dev", ctypes.c_void_p), ("feature_obs_dev", ctypes.c_void_p), ("done_dev", ctypes.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_last_error", "ssd_reset", "ssd_step",
+    "ssd_set_contract_params", "ssd_negotiate", "ssd_get_state", "ssd_set_state", "ssd_get_metrics",
+    "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
+    "ssd_kernel_launches",
+]
+
+_LIB = None
+
+
+def load():
+    """Load the shared library (raises SsdError with build instructions if it is missing)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise SsdError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
+    L.ssd_abi_version.restype = i32
+    L.ssd_create.argtypes = [ctypes.POINTER(ssd_config), ctypes.POINTER(vp)]
+    L.ssd_destroy.argtypes = [vp]
+    L.ssd_destroy.restype = None
+    L.ssd_last_error.argtypes = [vp]
+    L.ssd_last_error.restype = ctypes.c_char_p
+    L.ssd_reset.argtypes = [vp, vp, vp, i64, vp]
+    L.ssd_step.argtypes = [vp, ctypes.POINTER(ssd_step_io), vp]
+    L.ssd_set_contract_params.argtypes = [vp, vp, vp]
+    L.ssd_negotiate.argtypes = [vp, vp, vp, vp, vp]
+    L.ssd_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ssd_set_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ssd_get_metrics.argtypes = [vp, vp, vp]
+    L.ssd_random_actions.argtypes = [vp, u32, i32, vp, vp]
+    L.ssd_philox4x32_10.argtypes = [vp, vp, vp]
+    L.ssd_philox4x32_10.restype = None
+    L.ssd_feature_dim.argtypes = [vp]
+    L.ssd_state_bytes_per_env.argtypes = [vp]
+    L.ssd_state_bytes_per_env.restype = i64
+    L.ssd_kernel_launches.argtypes = [vp]
+    L.ssd_kernel_launches.restype = i64
+    if L.ssd_abi_version() != SSD_ABI_VERSION:
+        raise SsdError("libssd_b200.so ABI %d != binding ABI %d" % (L.ssd_abi_version(), SSD_ABI_VERSION))
+    _LIB = L
+    return L
+
+
+def check(handle, rc):
+    if rc != 0:
+        msg = load().ssd_last_error(handle)
+        raise SsdError("libssd_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

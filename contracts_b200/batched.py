@@ -1,0 +1,180 @@
+"""Batched device-resident environments: the fast path behind the drop-in API.
+
+`BatchedGridEnv` owns E independent cleanup_new / harvest_new environments (optionally with
+the subgame contract wrapper fused in) on one GPU.  All I/O is torch CUDA tensors; the step
+is one kernel launch through the C ABI (`ssd_step`).  PyTorch is used only for device
+memory and streams.
+
+Reference classes covered (paths relative to the reference root):
+  environments/cleanup_new.py CleanupEnv, environments/harvest_new.py HarvestEnv,
+  environments/two_stage_train.py SeparateContractEnv.step :62-121 and
+  SeparateContractSubgameStage.reset :159-187, contract/contract_list.py.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .maps import CLEANUP_MAP, HARVEST_MAP
+
+_DEFAULT_HIGH = {"CleanupContract": 0.2, "HarvestFeaturemodLocalContract": 10.0}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedGridEnv:
+    """E environments of one kind on one device.
+
+    kind: 'cleanup_new' | 'harvest_new' (the reference's `environment` strings,
+    utils/env_creator_functions.py:47-60).  contract: None or the class name from
+    contract/contract_list.py.  theta_low/high default to the contract's gym Box bounds, which
+    gym stores as float32 (contract_list.py:20,43) — the float32 rounding is part of parity.
+    """
+
+    def __init__(self, kind, num_envs, num_agents, ascii_map=None, horizon=1000, contract=None,
+                 theta_low=0.0, theta_high=None, null_prob=0.0, seed=73907, first_env_id=0,
+                 device=None, padded_obs=False):
+        if kind not in ("cleanup_new", "harvest_new"):
+            raise ValueError("BatchedGridEnv kind must be cleanup_new or harvest_new, got %r" % (kind,))
+        if not torch.cuda.is_available():
+            raise _lib.SsdError("CUDA device required: contracts_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.kind, self.E, self.n = kind, int(num_envs), int(num_agents)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ascii_map = list(ascii_map) if ascii_map is not None else (
+            CLEANUP_MAP if kind == "cleanup_new" else HARVEST_MAP)
+        self.H, self.W = len(self.ascii_map), len(self.ascii_map[0])
+        if any(len(r) != self.W for r in self.ascii_map):
+            raise ValueError("ascii_map rows must have equal length")
+        self.horizon = int(horizon)
+        self.contract = contract
+        if theta_high is None:
+            theta_high = _DEFAULT_HIGH.get(contract, 0.0)
+        self.theta_low = float(np.float32(theta_low))
+        self.theta_high = float(np.float32(theta_high))
+        self.seed, self.first_env_id = int(seed) & 0xFFFFFFFF, int(first_env_id) & 0xFFFFFFFF
+        self._flat = "".join(self.ascii_map).encode("ascii")
+        cfg = _lib.ssd_config(
+            abi_version=_lib.SSD_ABI_VERSION, env_kind=_lib.ENV_KIND[kind], num_envs=self.E, num_agents=self.n,
+            map_h=self.H, map_w=self.W, ascii_map=self._flat, horizon=self.horizon,
+            contract_kind=_lib.CONTRACT_KIND[contract], theta_low=self.theta_low, theta_high=self.theta_high,
+            null_prob=float(null_prob), seed=self.seed, first_env_id=self.first_env_id,
+            device=self.device.index or 0, flags=0)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self.F = self.lib.ssd_feature_dim(self._h)
+        E, n, dev = self.E, self.n, self.device
+        # observation batch tensor: dense [E, n, 15, 15, 3], or env stride padded to 16 B
+        dense = n * _lib.OBS_BYTES_PER_AGENT
+        self.obs_stride = (dense + 15) // 16 * 16 if padded_obs else dense
+        self._obs_buf = torch.zeros((E, self.obs_stride), dtype=torch.uint8, device=dev)
+        self.obs = self._obs_buf[:, :dense].view(E, n, 15, 15, 3) if padded_obs else self._obs_buf.view(E, n, 15, 15, 3)
+        self.rew = torch.zeros((E, n), dtype=torch.float64, device=dev)
+        self.base_rew = torch.zeros((E, n), dtype=torch.float64, device=dev)
+        self.transfers = torch.zeros((E, n), dtype=torch.float64, device=dev)
+        self.info = torch.zeros((E, n, 4), dtype=torch.uint8, device=dev)
+        self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        self.feature_obs = None
+        self._io = _lib.ssd_step_io()
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ssd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, mask=None):
+        """Reset all envs (mask None) or those with mask != 0 (uint8 CUDA tensor [E]).  Returns obs."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self._h, self.lib.ssd_reset(self._h, _ptr(mask), _ptr(self._obs_buf), self.obs_stride, self._stream()))
+        return self.obs
+
+    def step(self, actions, want_features=False, extras=True):
+        """actions: uint8 CUDA tensor [E, n].  Returns (obs, rew, done, info) device tensors.
+
+        The same output tensors are reused every step.  extras=False skips base_rew/transfers.
+        """
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        if want_features and self.feature_obs is None:
+            self.feature_obs = torch.zeros((self.E, self.n, self.F), dtype=torch.float64, device=self.device)
+        io = self._io
+        io.actions_dev = actions.data_ptr()
+        io.obs_dev = self._obs_buf.data_ptr()
+        io.obs_env_stride = self.obs_stride
+        io.rew_dev = self.rew.data_ptr()
+        io.base_rew_dev = self.base_rew.data_ptr() if extras else None
+        io.transfers_dev = self.transfers.data_ptr() if extras else None
+        io.info_dev = self.info.data_ptr()
+        io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
+        io.done_dev = self.done.data_ptr()
+        _lib.check(self._h, self.lib.ssd_step(self._h, ctypes.byref(io), self._stream()))
+        return self.obs, self.rew, self.done, self.info
+
+    def random_actions(self, step_index, num_actions, out=None):
+        if out is None:
+            out = torch.empty((self.E, self.n), dtype=torch.uint8, device=self.device)
+        _lib.check(self._h, self.lib.ssd_random_actions(self._h, int(step_index), int(num_actions), _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def set_contract_params(self, theta):
+        theta = torch.as_tensor(theta, dtype=torch.float64, device=self.device).expand(self.E).contiguous()
+        _lib.check(self._h, self.lib.ssd_set_contract_params(self._h, _ptr(theta), self._stream()))
+
+    def negotiate(self, proposals, accept):
+        """Agreement stage (two_stage_train.py:266-281).  proposals [E], accept [E, n] float64.  Returns uint8 [E]."""
+        proposals = torch.as_tensor(proposals, dtype=torch.float64, device=self.device).expand(self.E).contiguous()
+        accept = torch.as_tensor(accept, dtype=torch.float64, device=self.device).expand(self.E, self.n).contiguous()
+        dec = torch.empty((self.E,), dtype=torch.uint8, device=self.device)
+        _lib.check(self._h, self.lib.ssd_negotiate(self._h, _ptr(proposals), _ptr(accept), _ptr(dec), self._stream()))
+        return dec
+
+    def get_state(self):
+        E, n, dev = self.E, self.n, self.device
+        st = {"map": torch.empty((E, self.H, self.W), dtype=torch.uint8, device=dev),
+              "pos": torch.empty((E, n, 2), dtype=torch.int32, device=dev),
+              "ori": torch.empty((E, n), dtype=torch.int32, device=dev),
+              "t": torch.empty((E,), dtype=torch.int32, device=dev),
+              "theta": torch.empty((E,), dtype=torch.float64, device=dev)}
+        _lib.check(self._h, self.lib.ssd_get_state(self._h, _ptr(st["map"]), _ptr(st["pos"]), _ptr(st["ori"]),
+                                                   _ptr(st["t"]), _ptr(st["theta"]), self._stream()))
+        return st
+
+    def set_state(self, map=None, pos=None, ori=None, t=None, theta=None):
+        def prep(x, dt, shape):
+            if x is None:
+                return None
+            return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=self.device, dtype=dt).expand(shape).contiguous()
+        E, n = self.E, self.n
+        m, p, o = prep(map, torch.uint8, (E, self.H, self.W)), prep(pos, torch.int32, (E, n, 2)), prep(ori, torch.int32, (E, n))
+        tt, th = prep(t, torch.int32, (E,)), prep(theta, torch.float64, (E,))
+        _lib.check(self._h, self.lib.ssd_set_state(self._h, _ptr(m), _ptr(p), _ptr(o), _ptr(tt), _ptr(th), self._stream()))
+
+    def metrics_raw(self):
+        out = torch.empty((self.E, _lib.METRIC_STRIDE), dtype=torch.float64, device=self.device)
+        _lib.check(self._h, self.lib.ssd_get_metrics(self._h, _ptr(out), self._stream()))
+        return out
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.ssd_kernel_launches(self._h))
+
+    @property
+    def state_bytes_per_env(self):
+        return int(self.lib.ssd_state_bytes_per_env(self._h))

@@ -1,0 +1,496 @@
+// ssd_b200.cu — C ABI of libssd_b200.so (see include/ssd_b200.h) and host-side setup.
+//
+// Build (see __graft_entry__.build / contracts_b200/build.py):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
+//        -Xcompiler -fPIC -shared -I include -o contracts_b200/libssd_b200.so contracts_b200/csrc/ssd_b200.cu
+// -fmad=false: reward / transfer arithmetic must round like the reference's float64 ops.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ssd_b200.h"
+#include "ssd_grid.cuh"
+
+static thread_local char g_create_error[512] = "";
+
+struct ssd_handle {
+    ssd_config cfg;
+    std::string ascii;
+    GridParams gp;
+    int grid_blocks;
+    int64_t launches;
+    char err[512];
+    std::vector<void*> dev_allocs;
+};
+
+static int fail(ssd_handle* h, int code, const char* fmt, ...)
+{
+    char* buf = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(h, SSD_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ceil(p * 2^32) clamped: (u32 * 2^-32 < p) <=> (u32 < T)
+static uint32_t prob_threshold(double p)
+{
+    if (!(p > 0.0)) return 0u;
+    double x = ceil(p * 4294967296.0);
+    if (x >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)x;
+}
+
+// DEFAULT_COLOURS (map_env.py:24-42) + CLEANUP_COLORS (cleanup_new.py:42-47), packed r | g << 8 | b << 16
+static uint32_t rgb(int r, int g, int b) { return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16); }
+static void build_palette(uint32_t* pal)
+{
+    const uint32_t cell[16] = { rgb(0, 0, 0), rgb(180, 180, 180), rgb(0, 255, 0), rgb(99, 156, 194),
+                                rgb(113, 75, 24), rgb(113, 75, 24), 0, 0, 0, 0, 0, 0, 0, 0, 0, rgb(0, 0, 0) };
+    const uint32_t agent[9] = { rgb(0, 0, 255), rgb(2, 81, 154), rgb(204, 0, 204), rgb(216, 30, 54), rgb(254, 151, 0),
+                                rgb(100, 255, 255), rgb(99, 99, 255), rgb(250, 204, 255), rgb(238, 223, 16) };
+    for (int b = 0; b < 256; b++) {
+        int hi = b >> 4, lo = b & 15;
+        pal[b] = (hi >= 1 && hi <= 9) ? agent[hi - 1] : cell[lo];
+    }
+}
+
+template <typename T>
+static int upload(ssd_handle* h, const std::vector<T>& v, const T** out)
+{
+    void* d = nullptr;
+    size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&d, bytes));
+    h->dev_allocs.push_back(d);
+    if (v.size()) CUDA_TRY(h, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(d);
+    return SSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int setup_grid(ssd_handle* h)
+{
+    const ssd_config& c = h->cfg;
+    GridParams& p = h->gp;
+    memset(&p, 0, sizeof(p));
+    const int H = c.map_h, W = c.map_w, n = c.num_agents;
+    if (H < 1 || W < 1 || H > 48 || W > 64) return fail(h, SSD_EINVAL, "map size %dx%d out of range (max 48x64)", H, W);
+    if (!c.ascii_map || (int)h->ascii.size() != H * W) return fail(h, SSD_EINVAL, "ascii_map must hold map_h*map_w chars");
+    p.E = c.num_envs; p.n = n; p.H = H; p.W = W;
+    p.Wp = round_up(W, 4); p.S = 8 + p.Wp + 8; p.TH = H + 2 * SSD_VIEW;
+    p.wpw = p.Wp / 4; p.wpw_magic = (65536u + p.wpw - 1) / p.wpw;
+    p.map_bytes = round_up(H * p.Wp, 16);
+    p.rec_stride = p.map_bytes + RO_SIZE;
+    p.kind = c.env_kind; p.contract = c.contract_kind; p.horizon = c.horizon;
+    p.seed = c.seed; p.first_env_id = c.first_env_id;
+    p.theta_low = c.theta_low; p.theta_high = c.theta_high; p.null_prob = c.null_prob;
+    p.F = c.env_kind == SSD_ENV_CLEANUP ? 12 + n : 10 + 2 * n;
+
+    // parse the map like MapEnv.__init__ / CleanupEnv.__init__ / HarvestEnv.__init__
+    std::vector<uint16_t> apple, waste, spawn;
+    std::vector<uint8_t> reset_map(p.map_bytes, (uint8_t)C_OUTSIDE);
+    int n_waste_start = 0, n_spawn_unique = 0;
+    auto off = [&](int r, int col) { return (uint16_t)((r + SSD_VIEW) * p.S + 8 + col); };
+    for (int r = 0; r < H; r++)
+        for (int col = 0; col < W; col++) {
+            char ch = h->ascii[r * W + col];
+            uint8_t code = C_EMPTY;
+            if (ch == '@') code = C_WALL;
+            if (ch == 'P') { spawn.push_back(off(r, col)); n_spawn_unique++; if (c.env_kind == SSD_ENV_CLEANUP) spawn.push_back(off(r, col)); }
+            if (c.env_kind == SSD_ENV_CLEANUP) {
+                if (ch == 'B') apple.push_back(off(r, col));
+                if (ch == 'H') { code = C_WASTE; n_waste_start++; }
+                if (ch == 'R') code = C_RIVER;
+                if (ch == 'S') code = C_STREAM;
+                if (ch == 'H' || ch == 'R') waste.push_back(off(r, col));
+            } else if (ch == 'A') { apple.push_back(off(r, col)); code = C_APPLE; }
+            reset_map[r * p.Wp + col] = code;
+        }
+    // canonical spawn order is the sorted list (row-major offsets are already sorted; duplicates adjacent)
+    if (n_spawn_unique < n) return fail(h, SSD_EINVAL, "map has %d spawn points for %d agents", n_spawn_unique, n);
+    if ((int)spawn.size() > 128) return fail(h, SSD_EUNSUPPORTED, "more than 128 spawn-list entries");
+    if ((int)apple.size() > 32 * MAX_POINT_ROUNDS || (int)waste.size() > 32 * MAX_POINT_ROUNDS)
+        return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * MAX_POINT_ROUNDS);
+    p.n_apple = (int)apple.size(); p.n_waste = (int)waste.size(); p.n_spawn = (int)spawn.size();
+    p.n_waste_start = n_waste_start;
+
+    // spawn probabilities as integer thresholds, computed with the reference's float64 arithmetic
+    // (cleanup_new.py:351-368; thresholdDepletion 0.4, thresholdRestoration 0.0, 0.5, 0.05 at :53-56)
+    std::vector<uint32_t> thr_apple(p.n_waste + 1);
+    std::vector<uint8_t> waste_on(p.n_waste + 1);
+    for (int k = 0; k <= p.n_waste; k++) {
+        volatile double waste_density = 0;
+        if (p.n_waste > 0) {
+            volatile double ratio = (double)(p.n_waste - k) / (double)p.n_waste;
+            waste_density = 1 - ratio;
+        }
+        double pa, pw;
+        if (waste_density >= 0.4) { pa = 0; pw = 0; }
+        else {
+            pw = 0.5;
+            if (waste_density <= 0.0) pa = 0.05;
+            else {
+                volatile double frac = (waste_density - 0.0) / (0.4 - 0.0);
+                volatile double one_minus = 1 - frac;
+                pa = one_minus * 0.05;
+            }
+        }
+        thr_apple[k] = prob_threshold(pa);
+        waste_on[k] = pw != 0;
+    }
+    const double SPAWN_PROB[4] = { 0, 0.005, 0.02, 0.05 };           // harvest_new.py:34
+    for (int i = 0; i < 4; i++) p.thr_harvest[i] = prob_threshold(SPAWN_PROB[i]);
+    p.thr_waste = prob_threshold(0.5);
+
+    // observation window LUT: color_view (map_env.py:397-411); V[a][b] = tile[origin + a*S + b]
+    std::vector<uint16_t> lut(4 * SSD_LUT_STRIDE, 0);
+    for (int o = 0; o < 4; o++)
+        for (int i = 0; i < SSD_OBSW; i++)
+            for (int j = 0; j < SSD_OBSW; j++) {
+                int vi, vj;
+                if (o == ORI_UP) { vi = i; vj = j; }
+                else if (o == ORI_LEFT) { vi = j; vj = SSD_OBSW - 1 - i; }            // np.rot90(v)
+                else if (o == ORI_DOWN) { vi = SSD_OBSW - 1 - i; vj = SSD_OBSW - 1 - j; }  // np.rot90(v, k=2)
+                else { vi = SSD_OBSW - 1 - j; vj = i; }                              // np.rot90(v, k=1, axes=(1,0))
+                lut[o * SSD_LUT_STRIDE + i * SSD_OBSW + j] = (uint16_t)(vi * p.S + vj);
+            }
+    std::vector<uint32_t> pal(256);
+    build_palette(pal.data());
+
+    int rc;
+    if ((rc = upload(h, pal, &p.pal))) return rc;
+    if ((rc = upload(h, lut, &p.lut))) return rc;
+    if ((rc = upload(h, apple, &p.apple_pts))) return rc;
+    if ((rc = upload(h, waste, &p.waste_pts))) return rc;
+    if ((rc = upload(h, spawn, &p.spawn_pts))) return rc;
+    if ((rc = upload(h, thr_apple, &p.thr_apple))) return rc;
+    if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
+    if ((rc = upload(h, reset_map, &p.reset_map))) return rc;
+
+    // shared memory layout
+    p.tile_r16 = round_up(p.TH * p.S, 16);
+    p.stage_r16 = round_up(n * SSD_OBS_BYTES + 16 + 16, 16);
+    p.warp_bytes = p.tile_r16 + p.stage_r16 + (SCRATCH_DRAWS + SCRATCH_KEYS) * 4 + 32;
+    p.sm_apple = 1024 + round_up(4 * SSD_LUT_STRIDE * 2, 16);
+    p.sm_waste = p.sm_apple + round_up(p.n_apple * 2, 16);
+    p.sm_warp0 = p.sm_waste + round_up(p.n_waste * 2, 16);
+    p.smem_bytes = p.sm_warp0 + GRID_WARPS * p.warp_bytes;
+
+    void* st = nullptr;
+    size_t bytes = (size_t)p.E * p.rec_stride;
+    CUDA_TRY(h, cudaMalloc(&st, bytes));
+    h->dev_allocs.push_back(st);
+    CUDA_TRY(h, cudaMemset(st, 0, bytes));
+    p.state = (uint8_t*)st;
+
+    // persistent grid: enough CTAs to fill every SM at the achievable occupancy
+    const void* ks[4] = { (const void*)grid_step_kernel<SSD_ENV_CLEANUP>, (const void*)grid_step_kernel<SSD_ENV_HARVEST>,
+                          (const void*)grid_reset_kernel<SSD_ENV_CLEANUP>, (const void*)grid_reset_kernel<SSD_ENV_HARVEST> };
+    for (int i = 0; i < 4; i++)
+        CUDA_TRY(h, cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    int sms = 0, per_sm = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks[c.env_kind == SSD_ENV_CLEANUP ? 0 : 1],
+                                                              GRID_THREADS, p.smem_bytes));
+    if (per_sm < 1) return fail(h, SSD_EUNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", p.smem_bytes);
+    int want = (p.E + GRID_WARPS - 1) / GRID_WARPS;
+    h->grid_blocks = want < sms * per_sm ? want : sms * per_sm;
+    return SSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+__global__ void get_state_kernel(GridParams p, uint8_t* map, int32_t* pos, int32_t* ori, int32_t* t, double* theta)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    const uint8_t* rec = p.state + (size_t)env * p.rec_stride;
+    const uint8_t* hdr = rec + p.map_bytes;
+    const char chars[16] = { ' ', '@', 'A', 'H', 'R', 'S', '?', '?', '?', '?', '?', '?', '?', '?', '?', '?' };
+    if (map)
+        for (int r = 0; r < p.H; r++)
+            for (int c = 0; c < p.W; c++) map[((size_t)env * p.H + r) * p.W + c] = (uint8_t)chars[rec[r * p.Wp + c] & 15];
+    for (int a = 0; a < p.n; a++) {
+        uint32_t v = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[a];
+        if (pos) { pos[((size_t)env * p.n + a) * 2] = (int)(v & 255u); pos[((size_t)env * p.n + a) * 2 + 1] = (int)((v >> 8) & 255u); }
+        if (ori) ori[(size_t)env * p.n + a] = (int)((v >> 16) & 3u);
+    }
+    if (t) t[env] = *reinterpret_cast<const int*>(hdr + RO_T);
+    if (theta) theta[env] = *reinterpret_cast<const double*>(hdr + RO_THETA);
+}
+
+__global__ void set_state_kernel(GridParams p, const uint8_t* map, const int32_t* pos, const int32_t* ori,
+                                 const int32_t* t, const double* theta)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    uint8_t* rec = p.state + (size_t)env * p.rec_stride;
+    uint8_t* hdr = rec + p.map_bytes;
+    uint32_t bad = 0;
+    if (map) {
+        for (int i = 0; i < p.map_bytes; i++) rec[i] = (uint8_t)C_OUTSIDE;
+        int hc = 0;
+        for (int r = 0; r < p.H; r++)
+            for (int c = 0; c < p.W; c++) {
+                uint8_t ch = map[((size_t)env * p.H + r) * p.W + c];
+                uint8_t code = ch == ' ' ? C_EMPTY : ch == '@' ? C_WALL : ch == 'A' ? C_APPLE : ch == 'H' ? C_WASTE
+                             : ch == 'R' ? C_RIVER : ch == 'S' ? C_STREAM : 255;
+                if (code == 255) { bad |= 16; code = C_EMPTY; }
+                hc += code == C_WASTE;
+                rec[r * p.Wp + c] = code;
+            }
+        *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hc;
+    }
+    for (int a = 0; a < p.n; a++) {
+        uint32_t v = reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[a];
+        if (pos) v = (v & ~0xFFFFu) | (uint32_t)(pos[((size_t)env * p.n + a) * 2] & 255) | ((uint32_t)(pos[((size_t)env * p.n + a) * 2 + 1] & 255) << 8);
+        if (ori) v = (v & ~0xFF0000u) | ((uint32_t)(ori[(size_t)env * p.n + a] & 3) << 16);
+        reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[a] = v;
+    }
+    if (t) *reinterpret_cast<int*>(hdr + RO_T) = t[env];
+    if (theta) *reinterpret_cast<double*>(hdr + RO_THETA) = theta[env];
+    uint32_t f = *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS);
+    // like oracle/ref_harness.RefGridEnv.set_state: the stale apple list is rebuilt from the map
+    *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = ((f | 0x80000000u) & ~RF_STALE_EMPTY) | (bad << RF_ERR_SHIFT);
+}
+
+__global__ void set_theta_kernel(GridParams p, const double* theta)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    *reinterpret_cast<double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA) = theta[env];
+}
+
+__global__ void get_metrics_kernel(GridParams p, double* out)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    const uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
+    double* o = out + (size_t)env * SSD_METRIC_STRIDE;
+    double raw = 0;
+    for (int a = 0; a < SSD_MAXN; a++) {
+        int sr = reinterpret_cast<const int*>(hdr + RO_SUM_RAW)[a];
+        raw += (double)sr;
+        o[8 + a] = (double)reinterpret_cast<const uint32_t*>(hdr + RO_AGENT_A)[a];
+        o[16 + a] = (double)reinterpret_cast<const uint32_t*>(hdr + RO_AGENT_B)[a];
+        o[24 + a] = (double)sr;
+        o[32 + a] = (double)reinterpret_cast<const long long*>(hdr + RO_TSUM_RAW)[a];
+        o[40 + a] = reinterpret_cast<const double*>(hdr + RO_SUM_TR)[a];
+        o[48 + a] = reinterpret_cast<const double*>(hdr + RO_TSUM_TR)[a];
+    }
+    o[0] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_APPLES);
+    o[1] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_LOWDENS);
+    o[2] = raw;
+    o[3] = *reinterpret_cast<const double*>(hdr + RO_TRANSFERS);
+    o[4] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_DIRT);
+    o[5] = (double)((*reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS) >> RF_ERR_SHIFT) & 0xFFFFu);
+    o[6] = o[7] = 0;
+}
+
+// SeparateContractNegotiateStage.step, agreement stage (two_stage_train.py:266-281)
+__global__ void negotiate_kernel(GridParams p, const double* proposals, const double* accept, uint8_t* decision)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
+    const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+    const uint32_t env_id = p.first_env_id + (uint32_t)env;
+    const int n = p.n;
+    double prod = 1.0;
+    if (n > 3) {
+        // random.sample(range(1, n), 2): first two of the stateless shuffle of [1..n-1]
+        uint32_t k1 = 0, k2 = 0; int i1 = -1, i2 = -1;
+        for (int j = 0; j < n - 1; j++) {
+            uint32_t k = draw_u32(p.seed, env_id, episode, 0, SITE_NEGOTIATE, 0, (uint32_t)j);
+            if (i1 < 0 || k < k1) { k2 = k1; i2 = i1; k1 = k; i1 = j; }
+            else if (i2 < 0 || k < k2) { k2 = k; i2 = j; }
+        }
+        prod = __dmul_rn(prod, accept[(size_t)env * n + 1 + i1]);
+        prod = __dmul_rn(prod, accept[(size_t)env * n + 1 + i2]);
+    } else {
+        for (int i = 1; i < n; i++) prod = __dmul_rn(prod, accept[(size_t)env * n + i]);
+    }
+    double r = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0, SITE_NEGOTIATE, 1, 0), 1.0 / 4294967296.0);
+    bool dec = r < prod;
+    *reinterpret_cast<double*>(hdr + RO_THETA) = dec ? proposals[env] : 0.0;
+    if (decision) decision[env] = dec ? 1 : 0;
+}
+
+__global__ void random_actions_kernel(GridParams p, uint32_t step_index, int num_actions, uint8_t* actions)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    const uint32_t env_id = p.first_env_id + (uint32_t)env;
+    for (int b = 0; b * 4 < p.n; b++) {
+        Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
+        uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
+            actions[(size_t)env * p.n + b * 4 + j] = (uint8_t)(((uint64_t)w[j] * (uint32_t)num_actions) >> 32);
+    }
+}
+
+// =============================================================================================
+extern "C" {
+
+int ssd_abi_version(void) { return SSD_ABI_VERSION; }
+
+const char* ssd_last_error(const ssd_handle* h) { return h ? h->err : g_create_error; }
+
+void ssd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    Philox4 q = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+}
+
+int ssd_create(const ssd_config* cfg, ssd_handle** out)
+{
+    if (!cfg || !out) return fail(nullptr, SSD_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SSD_ABI_VERSION) return fail(nullptr, SSD_EINVAL, "abi_version %d != %d", cfg->abi_version, SSD_ABI_VERSION);
+    if (cfg->num_envs < 1) return fail(nullptr, SSD_EINVAL, "num_envs must be >= 1");
+    if (cfg->num_agents < 1 || cfg->num_agents > SSD_MAX_AGENTS) return fail(nullptr, SSD_EINVAL, "num_agents must be in [1, %d]", SSD_MAX_AGENTS);
+    if (cfg->env_kind != SSD_ENV_CLEANUP && cfg->env_kind != SSD_ENV_HARVEST)
+        return fail(nullptr, SSD_EUNSUPPORTED, "env_kind %d not supported by this build", cfg->env_kind);
+    if (cfg->contract_kind != SSD_CONTRACT_NONE &&
+        !((cfg->env_kind == SSD_ENV_CLEANUP && cfg->contract_kind == SSD_CONTRACT_CLEANUP) ||
+          (cfg->env_kind == SSD_ENV_HARVEST && cfg->contract_kind == SSD_CONTRACT_HARVEST_LOCAL)))
+        return fail(nullptr, SSD_EINVAL, "contract_kind %d does not apply to env_kind %d", cfg->contract_kind, cfg->env_kind);
+    if (cfg->contract_kind != SSD_CONTRACT_NONE && cfg->num_agents < 2)
+        return fail(nullptr, SSD_EINVAL, "contracts need at least 2 agents");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(nullptr, SSD_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SSD_EINVAL, "device %d out of range", cfg->device);
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, SSD_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ssd_handle* h = new ssd_handle();
+    h->cfg = *cfg;
+    h->launches = 0;
+    h->err[0] = 0;
+    if (cfg->ascii_map) h->ascii.assign(cfg->ascii_map, (size_t)cfg->map_h * cfg->map_w);
+    h->cfg.ascii_map = h->ascii.c_str();
+    int rc = setup_grid(h);
+    if (rc != SSD_OK) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+        ssd_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SSD_OK;
+}
+
+void ssd_destroy(ssd_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (void* d : h->dev_allocs) cudaFree(d);
+    delete h;
+}
+
+static int check_launch(ssd_handle* h, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, SSD_ECUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    h->launches++;
+    return SSD_OK;
+}
+
+int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t obs_env_stride, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    const GridParams& p = h->gp;
+    long long stride = obs_env_stride ? obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
+    if (stride < (long long)p.n * SSD_OBS_BYTES) return fail(h, SSD_EINVAL, "obs_env_stride too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.kind == SSD_ENV_CLEANUP)
+        grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+    else
+        grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+    return check_launch(h, "reset");
+}
+
+int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
+{
+    if (!h || !io) return SSD_EINVAL;
+    if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
+    const GridParams& p = h->gp;
+    StepIO k;
+    k.actions = (const uint8_t*)io->actions_dev;
+    k.obs = io->obs_dev;
+    k.obs_stride = io->obs_env_stride ? io->obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
+    if (k.obs_stride < (long long)p.n * SSD_OBS_BYTES) return fail(h, SSD_EINVAL, "obs_env_stride too small");
+    k.rew = io->rew_dev; k.base_rew = io->base_rew_dev; k.transfers = io->transfers_dev;
+    k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
+    if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.kind == SSD_ENV_CLEANUP)
+        grid_step_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+    else
+        grid_step_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+    return check_launch(h, "step");
+}
+
+#define SMALL_LAUNCH(kernel, ...)                                                         \
+    kernel<<<(h->gp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->gp, __VA_ARGS__)
+
+int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream)
+{
+    if (!h || !theta_dev) return SSD_EINVAL;
+    SMALL_LAUNCH(set_theta_kernel, theta_dev);
+    return check_launch(h, "set_contract_params");
+}
+
+int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev, void* stream)
+{
+    if (!h || !proposals_dev || !accept_dev) return SSD_EINVAL;
+    SMALL_LAUNCH(negotiate_kernel, proposals_dev, accept_dev, decision_dev);
+    return check_launch(h, "negotiate");
+}
+
+int ssd_get_state(ssd_handle* h, uint8_t* map_dev, int32_t* pos_dev, int32_t* ori_dev, int32_t* t_dev, double* theta_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    SMALL_LAUNCH(get_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
+    return check_launch(h, "get_state");
+}
+
+int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev, const int32_t* ori_dev, const int32_t* t_dev,
+                  const double* theta_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    SMALL_LAUNCH(set_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
+    return check_launch(h, "set_state");
+}
+
+int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
+{
+    if (!h || !out_dev) return SSD_EINVAL;
+    SMALL_LAUNCH(get_metrics_kernel, out_dev);
+    return check_launch(h, "get_metrics");
+}
+
+int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream)
+{
+    if (!h || !actions_dev || num_actions < 1 || num_actions > 255) return SSD_EINVAL;
+    SMALL_LAUNCH(random_actions_kernel, step_index, num_actions, actions_dev);
+    return check_launch(h, "random_actions");
+}
+
+int ssd_feature_dim(const ssd_handle* h) { return h ? h->gp.F : 0; }
+int64_t ssd_state_bytes_per_env(const ssd_handle* h) { return h ? h->gp.rec_stride : 0; }
+int64_t ssd_kernel_launches(const ssd_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// ssd_common.cuh — shared definitions for the sm_100a simulator kernels.
+//
+// Draw addressing (must match oracle/philox.py, which is what the reference is injected with):
+//   u32 = philox4x32_10(ctr = (idx >> 2, site | call << 8, t, episode), key = (seed, env_id))[idx & 3]
+// Site ids follow SURVEY.md §8a table R (reference file:line in oracle/philox.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SSD_MAXN 8            // agents per env ('1'..'9' colour ids exist, shipped configs use <= 8)
+#define SSD_VIEW 7            // CLEANUP_VIEW_SIZE / HARVEST_VIEW_SIZE (cleanup_new.py:51, harvest_new.py:36)
+#define SSD_OBSW 15
+#define SSD_OBS_PIX (SSD_OBSW * SSD_OBSW)          // 225 pixels / agent
+#define SSD_OBS_BYTES (SSD_OBS_PIX * 3)            // 675 B / agent
+#define SSD_LUT_STRIDE 228                         // 225 padded to a multiple of 4 entries
+
+// env_kind / contract_kind constants come from the public header
+#include "../../include/ssd_b200.h"
+
+// orientation ints: Agent.py:18-23
+enum { ORI_UP = 0, ORI_RIGHT = 1, ORI_DOWN = 2, ORI_LEFT = 3 };
+
+// cell codes stored in the low nibble of a tile byte (high nibble = agent paint / occupancy)
+enum { C_EMPTY = 0, C_WALL = 1, C_APPLE = 2, C_WASTE = 3, C_RIVER = 4, C_STREAM = 5, C_OUTSIDE = 15 };
+#define OCC_BIT 0x80u
+
+enum { SITE_MOVE_ORDER = 1, SITE_BEAM_ORDER = 2, SITE_SPAWN_DRAWS = 3, SITE_WASTE_ORDER = 4, SITE_SPAWN_ROT = 5,
+       SITE_SPAWN_POINT = 6, SITE_CONTRACT = 7, SITE_NEGOTIATE = 8, SITE_SELFDRIVE_RESET = 9,
+       SITE_FEAT_ORDER = 10, SITE_FEAT_ROT = 11, SITE_FEAT_SPAWN = 12, SITE_ACTIONS = 13 };
+
+// record flags
+#define RF_STALE_EMPTY 1u     // cleanup: current_apple_points is [] until the first step (cleanup_new.py:181 runs before the reset-time spawn)
+#define RF_ERR_SHIFT 8
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 r = { c0, c1, c2, c3 };
+    return r;
+}
+
+// one Philox block of a (site, call) at (t, episode) for env key (seed, env_id)
+__device__ __forceinline__ Philox4 draw_block(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t,
+                                              uint32_t site, uint32_t call, uint32_t block)
+{
+    return philox4x32_10(block, site | (call << 8), t, episode, seed, env_id);
+}
+__device__ __forceinline__ uint32_t pick(const Philox4& p, uint32_t w)
+{
+    return w == 0 ? p.x : (w == 1 ? p.y : (w == 2 ? p.z : p.w));
+}
+__device__ __forceinline__ uint32_t draw_u32(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t,
+                                             uint32_t site, uint32_t call, uint32_t idx)
+{
+    return pick(draw_block(seed, env_id, episode, t, site, call, idx >> 2), idx & 3);
+}

@@ -1,0 +1,793 @@
+// ssd_grid.cuh — sm_100a kernels for the gridworld envs (cleanup_new / harvest_new).
+//
+// Mapping: one WARP per environment, one LANE per agent for the move /
+// rotate / conflict logic (n <= 8, decisions are serial per env, so warp ballots + shuffles
+// give the reference's ordering without block barriers); all 32 lanes for the data-parallel
+// phases (tile load, spawn scans, observation gather).  The map lives as a padded uint8
+// tile in shared memory (7 cells of C_OUTSIDE border = the view radius), agents are
+// painted into the high nibble, and the rotated 15x15x3 windows are gathered into a
+// per-warp staging buffer that leaves through one TMA bulk store (cp.async.bulk) per env.
+//
+// Reference behaviour restated here (paths relative to the reference root):
+//   environments/map_env.py   step :216-304, update_moves :483-676, update_custom_moves :678-693,
+//                             update_map_fire :721-814, color_view :397-411, reset :306-342,
+//                             spawn_point :816-827, spawn_rotation :829-832
+//   environments/cleanup_new.py  step :211-267, custom_action :269-292, spawn_apples_and_waste :322-349,
+//                             compute_probabilities :351-368, custom_reset :171-189
+//   environments/harvest_new.py  step :181-239, spawn_apples :284-317, count_apples_in_radius :326-336
+//   contract/contract_list.py :22-27, :45-54 ; environments/two_stage_train.py :62-121, :159-187
+#pragma once
+#include "ssd_common.cuh"
+
+#define GRID_WARPS 8
+#define GRID_THREADS (GRID_WARPS * 32)
+#define SCRATCH_DRAWS 256               // u32 draws per warp scratch
+#define SCRATCH_KEYS 256                // u32 shuffle keys per warp scratch
+#define MAX_POINT_ROUNDS 8              // point lists are scanned 32 per round => <= 256 points
+#define FULL 0xffffffffu
+
+// record layout after the map bytes (all offsets relative to rec + map_bytes)
+#define RO_AGENTS 0        // u32[8]: row | col << 8 | ori << 16
+#define RO_T 32            // i32
+#define RO_EPISODE 36      // u32
+#define RO_THETA 40        // f64
+#define RO_FLAGS 48        // u32
+#define RO_HCOUNT 52       // u32 (#waste cells, cleanup)
+#define RO_APPLES 56       // u32 total_apples_eaten
+#define RO_LOWDENS 60      // u32 low_density_apples_eaten
+#define RO_DIRT 64         // u32 dirt_cleaned
+#define RO_TRANSFERS 72    // f64 metrics['transfers']
+#define RO_SUM_TR 80       // f64[8]
+#define RO_TSUM_TR 144     // f64[8]
+#define RO_TSUM_RAW 208    // i64[8]
+#define RO_SUM_RAW 272     // i32[8]
+#define RO_AGENT_A 304     // u32[8] waste_cleaned | apples_consumed
+#define RO_AGENT_B 336     // u32[8] close_apples_consumed
+#define RO_SIZE 368
+
+struct GridParams {
+    int E, n, H, W, Wp, S, TH;
+    int wpw;                 // words per map row (Wp / 4)
+    uint32_t wpw_magic;      // ceil(65536 / wpw): q = (w * magic) >> 16 for w < 65536 / wpw
+    int map_bytes;           // H * Wp rounded up to 16
+    int rec_stride;          // map_bytes + RO_SIZE
+    int tile_r16, stage_r16, warp_bytes, sm_apple, sm_waste, sm_warp0, smem_bytes;
+    int kind, contract, horizon;
+    int n_apple, n_waste, n_spawn, n_waste_start, F;
+    uint32_t seed, first_env_id;
+    double theta_low, theta_high, null_prob;
+    uint32_t thr_harvest[4]; // SPAWN_PROB thresholds (harvest_new.py:34)
+    uint32_t thr_waste;      // wasteSpawnProbability = 0.5
+    const uint32_t* pal;     // [256] packed RGB per tile byte
+    const uint16_t* lut;     // [4][SSD_LUT_STRIDE] window offsets per orientation
+    const uint16_t* apple_pts;
+    const uint16_t* waste_pts;
+    const uint16_t* spawn_pts;
+    const uint32_t* thr_apple;   // [n_waste + 1] apple spawn threshold by #waste
+    const uint8_t* waste_on;     // [n_waste + 1]
+    const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
+    uint8_t* state;
+};
+
+struct StepIO {
+    const uint8_t* actions;
+    uint8_t* obs; long long obs_stride;
+    double* rew; double* base_rew; double* transfers;
+    uint8_t* info; double* feat; uint8_t* done;
+};
+
+struct EnvRng { uint32_t seed, env_id, episode, t; };
+
+__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+__device__ __forceinline__ int dir_delta(int ori, int S)
+{
+    return ori == ORI_UP ? -S : (ori == ORI_RIGHT ? 1 : (ori == ORI_DOWN ? S : -1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile <-> HBM record
+__device__ __forceinline__ void tile_load(const GridParams& p, const uint8_t* rec, uint8_t* tile, int lane)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(rec);
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+    const int S4 = p.S >> 2, nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
+    for (int v = lane; v < nvec; v += 32) {
+        uint4 q = __ldg(src + v);
+        uint32_t w4[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int w = v * 4 + j;
+            if (w < nwords) {
+                int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
+                int cw = w - row * p.wpw;
+                tw[(row + SSD_VIEW) * S4 + 2 + cw] = w4[j];
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tile_store(const GridParams& p, uint8_t* rec, const uint8_t* tile, int lane)
+{
+    uint4* dst = reinterpret_cast<uint4*>(rec);
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+    const int S4 = p.S >> 2, nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
+    for (int v = lane; v < nvec; v += 32) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int w = v * 4 + j;
+            uint32_t x = 0x0F0F0F0Fu;
+            if (w < nwords) {
+                int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
+                int cw = w - row * p.wpw;
+                x = tw[(row + SSD_VIEW) * S4 + 2 + cw] & 0x0F0F0F0Fu;   // strip agent paint / occupancy
+            }
+            w4[j] = x;
+        }
+        dst[v] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update_moves (map_env.py:483-676).  Lane i < n holds agent i: `ao` tile offset of its cell.
+// Returns error bits.  On the fast path (no two movers share a target and no real move targets
+// an occupied cell) every mover simply moves, which is what the reference's first while-pass does.
+__device__ __forceinline__ uint32_t resolve_moves(int lane, int n, uint8_t* tile, const EnvRng& g,
+                                                  int& ao, bool has_move, int tgt)
+{
+    const bool act_lane = lane < n;
+    const unsigned movers = __ballot_sync(FULL, has_move);
+    if (movers == 0) return 0;
+    uint32_t mval = has_move ? (uint32_t)tgt : (0xFFFF0000u | (uint32_t)lane);
+    unsigned same = __match_any_sync(FULL, mval);
+    bool contested = has_move && (__popc(same) > 1);
+    if (act_lane) tile[ao] |= OCC_BIT;             // co-located lanes write the same value
+    __syncwarp();
+    bool real = has_move && tgt != ao;
+    bool occupied = real && (tile[tgt] & OCC_BIT);
+    __syncwarp();
+    if (act_lane) tile[ao] &= 0x7F;
+    __syncwarp();
+    if (__ballot_sync(FULL, contested || occupied) == 0) {
+        if (real) ao = tgt;
+        return 0;
+    }
+
+    // ---- slow path: literal ordering of the reference ------------------------------------------
+    uint32_t err = 0;
+    // shuffled priority (map_env.py:545-547): key of list position m = rank among movers
+    uint32_t key = 0xFFFFFFFFu;
+    if (has_move) key = draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_MOVE_ORDER, 0,
+                                 (uint32_t)__popc(movers & lanemask_lt(lane)));
+    int cur_mv = tgt;                               // agent_moves[agent]
+    // contested cells in lexicographic (row, col) order == increasing tile offset (np.unique, :548)
+    unsigned remaining = __ballot_sync(FULL, contested);
+    while (remaining) {
+        uint32_t v = ((remaining >> lane) & 1u) ? (uint32_t)tgt : 0xFFFFFFFFu;
+        int cmin = (int)__reduce_min_sync(FULL, v);
+        bool in_group = has_move && tgt == cmin;
+        unsigned group = __ballot_sync(FULL, in_group);
+        remaining &= ~group;
+        unsigned occm = __ballot_sync(FULL, act_lane && ao == cmin);   // live positions (:574)
+        bool cell_free = true;
+        if (occm) {
+            int occ = 31 - __clz(occm);             // agent_by_pos: the highest index wins duplicates
+            bool occ_has = (movers >> occ) & 1u;
+            int occ_mv = __shfl_sync(FULL, cur_mv, occ);
+            unsigned swapm = __ballot_sync(FULL, in_group && ao == occ_mv);
+            if (!occ_has || occ_mv == cmin) cell_free = false;      // conditions (1),(2) :585-595
+            else if (swapm) cell_free = false;                      // condition (3) :599-605
+        }
+        if (cell_free) {
+            uint32_t kmin = __reduce_min_sync(FULL, in_group ? key : 0xFFFFFFFFu);
+            unsigned cand = __ballot_sync(FULL, in_group && key == kmin);
+            if (lane == __ffs(cand) - 1) ao = cmin;                 // first contestant of the shuffled list (:610)
+        }
+        if (in_group) cur_mv = ao;                                   // :620-621
+    }
+    // remaining moves, multi-pass (:624-676)
+    unsigned live = movers;
+    while (live) {
+        const int snap = ao;                        // agent_by_pos snapshot (:625)
+        const unsigned copy = live;
+        const int num = __popc(live);
+        for (int i = 0; i < n; i++) {
+            if (!((copy >> i) & 1u) || !((live >> i) & 1u)) continue;
+            int mv_i = __shfl_sync(FULL, cur_mv, i);
+            int pos_i = __shfl_sync(FULL, ao, i);
+            unsigned occ_live = __ballot_sync(FULL, act_lane && ao == mv_i);
+            if (occ_live) {
+                unsigned snap_b = __ballot_sync(FULL, act_lane && snap == mv_i);
+                if (!snap_b) { err |= 2; live &= ~(1u << i); continue; }      // KeyError in the reference
+                int occ = 31 - __clz(snap_b);
+                int pos_occ = __shfl_sync(FULL, ao, occ);
+                int mv_occ_raw = __shfl_sync(FULL, cur_mv, occ);
+                int mv_occ = ((live >> occ) & 1u) ? mv_occ_raw : pos_occ;      // agent_moves.get(occ, pos)
+                if (occ == i) live &= ~(1u << i);
+                else if (!((copy >> occ) & 1u) || pos_occ == mv_occ) live &= ~(1u << i);
+                else if (mv_occ == pos_i && mv_i == pos_occ) live &= ~((1u << i) | (1u << occ));
+            } else {
+                if (lane == i) ao = mv_i;
+                live &= ~(1u << i);
+            }
+        }
+        if (__popc(live) == num) {                  // no progress: move everyone left (:673-676)
+            if ((live >> lane) & 1u) ao = cur_mv;
+            break;
+        }
+    }
+    return err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// update_custom_moves + update_map_fire (map_env.py:678-693, 721-814).  Occupancy bits must be set.
+// cls: 0 none, 1 FIRE, 2 CLEAN.  Returns #waste cells cleaned by all agents this step.
+__device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile, const EnvRng& g,
+                                          int ao, int ori, int cls, int& reward, int& cleaned)
+{
+    const bool act_lane = lane < n;
+    unsigned rem = __ballot_sync(FULL, act_lane && cls != 0);
+    if (!rem) return 0;
+    int total_cleaned = 0;
+    uint32_t bkey = act_lane ? draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_BEAM_ORDER, 0, (uint32_t)lane)
+                             : 0xFFFFFFFFu;
+    const bool ray_lane = lane < 15;
+    const int b = lane / 5, k = lane - 5 * b;
+    while (rem) {
+        bool mine = (rem >> lane) & 1u;
+        uint32_t kmin = __reduce_min_sync(FULL, mine ? bkey : 0xFFFFFFFFu);
+        unsigned cand = __ballot_sync(FULL, mine && bkey == kmin);
+        const int s = __ffs(cand) - 1;
+        rem &= ~(1u << s);
+        const int so = __shfl_sync(FULL, ao, s), sori = __shfl_sync(FULL, ori, s);
+        const bool sclean = __shfl_sync(FULL, cls, s) == 2;
+        const int d = dir_delta(sori, S), rt = dir_delta((sori + 1) & 3, S);
+        int cell = so + (b == 1 ? rt - d : (b == 2 ? -rt - d : 0)) + (k + 1) * d;
+        uint32_t code = ray_lane ? tile[cell] : (uint32_t)C_WALL;
+        uint32_t c = code & 15u;
+        bool pass = c != C_WALL && c != C_OUTSIDE;
+        bool agent_here = (code & OCC_BIT) != 0;
+        bool isH = c == C_WASTE;
+        unsigned stopm = __ballot_sync(FULL, ray_lane && (!pass || agent_here || (sclean && isH)));
+        unsigned raybits = (stopm >> (5 * b)) & 31u;
+        int first = raybits ? __ffs(raybits) - 1 : 5;
+        bool covered = ray_lane && pass && k <= first;
+        bool upd = covered && sclean && isH;
+        unsigned updm = __ballot_sync(FULL, upd);
+        unsigned hitm = __ballot_sync(FULL, covered && agent_here && !sclean);
+        if (upd) tile[cell] = (uint8_t)((code & 0xF0u) | C_RIVER);
+        while (hitm) {                               // Agent.hit(b"F"): -50 (Agent.py:178-180,224-226)
+            int hl = __ffs(hitm) - 1; hitm &= hitm - 1;
+            int hc = __shfl_sync(FULL, cell, hl);
+            unsigned victims = __ballot_sync(FULL, act_lane && ao == hc);
+            if (lane == 31 - __clz(victims)) reward -= 50;
+        }
+        int nclean = __popc(updm);
+        if (lane == s) { if (sclean) cleaned = nclean; else reward -= 1; }
+        total_cleaned += nclean;
+        __syncwarp();
+    }
+    return total_cleaned;
+}
+
+// fill scratch[0 .. 4*nblk) with Philox blocks 0..nblk-1 of (site, call)
+__device__ __forceinline__ void fill_draws(uint32_t* scratch, int lane, const EnvRng& g, uint32_t t,
+                                           uint32_t site, int nblk)
+{
+    for (int bl = lane; bl < nblk; bl += 32) {
+        Philox4 q = draw_block(g.seed, g.env_id, g.episode, t, site, 0, (uint32_t)bl);
+        reinterpret_cast<uint4*>(scratch)[bl] = make_uint4(q.x, q.y, q.z, q.w);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// cleanup spawn (cleanup_new.py:322-349).  Occupancy bits must be set.  `t` = 0 at reset.
+// Returns the number of waste cells spawned (0 or 1).
+__device__ __forceinline__ int cleanup_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
+                                             const uint16_t* sm_apple, const uint16_t* sm_waste,
+                                             const EnvRng& g, uint32_t t, int hcount)
+{
+    const uint32_t thrA = __ldg(p.thr_apple + hcount);
+    const bool waste_on = __ldg(p.waste_on + hcount) != 0;
+    if (thrA == 0 && !waste_on) return 0;
+    uint32_t* draws = scratch;
+    uint32_t* keys = scratch + SCRATCH_DRAWS;
+    // apples: eligible = no agent there and not already 'A'; draw index = rank among eligible (:328-335)
+    unsigned eligm[MAX_POINT_ROUNDS];
+    int M = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        int j = lane + 32 * q;
+        bool e = false;
+        if (q * 32 < p.n_apple) {
+            if (j < p.n_apple) { uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & 15u) != C_APPLE; }
+            eligm[q] = __ballot_sync(FULL, e);
+            M += __popc(eligm[q]);
+        } else eligm[q] = 0;
+    }
+    if (thrA) {
+        fill_draws(draws, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);
+        int base = 0;
+#pragma unroll
+        for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+            if (q * 32 < p.n_apple) {
+                if ((eligm[q] >> lane) & 1u) {
+                    int r = base + __popc(eligm[q] & lanemask_lt(lane));
+                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_APPLE); }
+                }
+                base += __popc(eligm[q]);
+            }
+        }
+        __syncwarp();
+    }
+    if (!waste_on) return 0;
+    // waste: shuffle waste_points (stateless: key per canonical index), scan non-'H' cells in that
+    // order, draw continues at rank M; first success spawns and breaks (:338-348)
+    unsigned candm[MAX_POINT_ROUNDS];
+    int C = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        int j = lane + 32 * q;
+        bool cnd = false;
+        if (q * 32 < p.n_waste) {
+            if (j < p.n_waste) cnd = (tile[sm_waste[j]] & 15u) != C_WASTE;
+            candm[q] = __ballot_sync(FULL, cnd);
+            C += __popc(candm[q]);
+        } else candm[q] = 0;
+    }
+    if (C == 0) return 0;
+    // number of failed draws before the first success
+    int kstar = -1;
+    for (int k0 = 0; k0 < C && kstar < 0; k0 += 32) {
+        uint32_t dr = draw_u32(g.seed, g.env_id, g.episode, t, SITE_SPAWN_DRAWS, 0, (uint32_t)(M + k0 + lane));
+        unsigned succ = __ballot_sync(FULL, (k0 + lane) < C && dr < p.thr_waste);
+        if (succ) kstar = k0 + __ffs(succ) - 1;
+    }
+    if (kstar < 0) return 0;
+    // keys of all waste points, then the (kstar+1)-th smallest (key, index) among candidates
+    for (int bl = lane; bl < ((p.n_waste + 3) >> 2); bl += 32) {
+        Philox4 qd = draw_block(g.seed, g.env_id, g.episode, t, SITE_WASTE_ORDER, 0, (uint32_t)bl);
+        reinterpret_cast<uint4*>(keys)[bl] = make_uint4(qd.x, qd.y, qd.z, qd.w);
+    }
+    __syncwarp();
+    int chosen = -1;
+    for (int it = 0; it <= kstar; it++) {
+        uint32_t bk = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
+#pragma unroll
+        for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+            if ((candm[q] >> lane) & 1u) {
+                int j = lane + 32 * q; uint32_t kk = keys[j];
+                if (kk < bk || (kk == bk && j < bj)) { bk = kk; bj = j; }
+            }
+        }
+        uint32_t kmin = __reduce_min_sync(FULL, bk);
+        int jmin = (int)__reduce_min_sync(FULL, (bk == kmin) ? (uint32_t)bj : 0x7FFFFFFFu);
+        chosen = jmin;
+        // remove it from the candidate set (uniform update of the owning lane's bit)
+        int ql = jmin >> 5, ll = jmin & 31;
+#pragma unroll
+        for (int q = 0; q < MAX_POINT_ROUNDS; q++) if (q == ql) candm[q] &= ~(1u << ll);
+    }
+    if (lane == 0) { int cell = sm_waste[chosen]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_WASTE); }
+    __syncwarp();
+    return 1;
+}
+
+// harvest spawn (harvest_new.py:284-317): neighbour counts read the pre-spawn map
+__device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
+                                              const uint16_t* sm_apple, const EnvRng& g, uint32_t t)
+{
+    const int S = p.S;
+    unsigned eligm[MAX_POINT_ROUNDS];
+    uint32_t mythr[MAX_POINT_ROUNDS];
+    int M = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        mythr[q] = 0; eligm[q] = 0;
+        if (q * 32 < p.n_apple) {
+            int j = lane + 32 * q;
+            bool e = false;
+            if (j < p.n_apple) {
+                int cell = sm_apple[j];
+                uint32_t code = tile[cell];
+                e = !(code & OCC_BIT) && (code & 15u) != C_APPLE;
+                if (e) {       // j*j + k*k <= APPLE_RADIUS(=2): the 3x3 block; own cell is not 'A'
+                    int cnt = 0;
+#pragma unroll
+                    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+                        for (int dc = -1; dc <= 1; dc++)
+                            if (dr | dc) cnt += ((tile[cell + dr * S + dc] & 15u) == C_APPLE);
+                    mythr[q] = p.thr_harvest[cnt < 3 ? cnt : 3];
+                }
+            }
+            eligm[q] = __ballot_sync(FULL, e);
+            M += __popc(eligm[q]);
+        }
+    }
+    if (M == 0) return;
+    fill_draws(scratch, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);   // also orders the tile reads above
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        if (q * 32 < p.n_apple) {
+            if ((eligm[q] >> lane) & 1u) {
+                int r = base + __popc(eligm[q] & lanemask_lt(lane));
+                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_APPLE); }
+            }
+            base += __popc(eligm[q]);
+        }
+    }
+    __syncwarp();
+}
+
+// count_apples_in_radius(5, loc) (harvest_new.py:326-336): the 21 cells with j*j + k*k <= 5
+__device__ __forceinline__ int count_apples_r5(const uint8_t* tile, int o, int S)
+{
+    int cnt = 0;
+#pragma unroll
+    for (int dr = -2; dr <= 2; dr++)
+#pragma unroll
+        for (int dc = -2; dc <= 2; dc++)
+            if (dr * dr + dc * dc <= 5) cnt += ((tile[o + dr * S + dc] & 15u) == C_APPLE);
+    return cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observations: gather the rotated windows of all agents into `stage` (word-aligned to the
+// global destination modulo 16) and ship them with one bulk async copy.
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void write_obs(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
+                                          const uint32_t* sm_pal, const uint16_t* sm_lut,
+                                          const uint32_t* sm_abase /* [8]: window origin | lut row << 16 */,
+                                          uint8_t* gdst)
+{
+    const int n = p.n;
+    const int L = n * SSD_OBS_BYTES;
+    const int npix = n * SSD_OBS_PIX;
+    const uint32_t gaddr = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    const bool word_ok = (gaddr & 3u) == 0;
+    const int shift = word_ok ? (int)gaddr : 0;
+    uint32_t* sw = reinterpret_cast<uint32_t*>(stage + shift);
+    const int G = (npix + 3) >> 2;                    // groups of 4 pixels = 12 bytes = 3 words
+    for (int gi = lane; gi < G; gi += 32) {
+        int q0 = gi * 4;
+        int a = q0 / SSD_OBS_PIX;
+        int pp = q0 - a * SSD_OBS_PIX;
+        uint32_t px[4];
+#pragma unroll
+        for (int kx = 0; kx < 4; kx++) {
+            if (pp >= SSD_OBS_PIX) { pp -= SSD_OBS_PIX; a++; }
+            int aa = a < n ? a : n - 1;
+            uint32_t ab = sm_abase[aa];
+            int off = (int)(ab & 0xFFFFu) + (int)sm_lut[(ab >> 16) + pp];
+            px[kx] = sm_pal[tile[off]];
+            pp++;
+        }
+        sw[gi * 3 + 0] = px[0] | (px[1] << 24);
+        sw[gi * 3 + 1] = (px[1] >> 8) | (px[2] << 16);
+        sw[gi * 3 + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    __syncwarp();
+    if (word_ok) {
+        const int a0 = (16 - shift) & 15;               // head bytes up to the first 16-B boundary
+        const int mid = (L - a0) & ~15;
+        const int tail0 = a0 + mid;
+        // head / tail: whole words first, then bytes
+        if (lane < (a0 >> 2)) reinterpret_cast<uint32_t*>(gdst)[lane] = sw[lane];
+        {
+            int tw = (L - tail0) >> 2;
+            if (lane < tw) reinterpret_cast<uint32_t*>(gdst + tail0)[lane] = sw[(tail0 >> 2) + lane];
+            int tb0 = tail0 + tw * 4;
+            if (lane < L - tb0) gdst[tb0 + lane] = (stage + shift)[tb0 + lane];
+        }
+        if (mid > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage + shift + a0);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(gdst + a0), "r"(saddr), "r"(mid) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    } else {
+        for (int i = lane; i < L; i += 32) gdst[i] = stage[i];
+    }
+}
+
+// per-env setup of the window tables used by write_obs
+__device__ __forceinline__ void set_abase(int lane, int n, int S, uint32_t* sm_abase, int ao, int ori)
+{
+    // window origin V[0][0] = tile offset of (row - 7, col - 7); lut row = orientation
+    if (lane < n) sm_abase[lane] = (uint32_t)(ao - SSD_VIEW * S - SSD_VIEW) | ((uint32_t)(ori * SSD_LUT_STRIDE) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SharedTables {
+    const uint32_t* pal; const uint16_t* lut; const uint16_t* apple; const uint16_t* waste;
+};
+__device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, uint8_t* smem)
+{
+    uint32_t* pal = reinterpret_cast<uint32_t*>(smem);
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + 1024);
+    uint16_t* apple = reinterpret_cast<uint16_t*>(smem + p.sm_apple);
+    uint16_t* waste = reinterpret_cast<uint16_t*>(smem + p.sm_waste);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) pal[i] = __ldg(p.pal + i);
+    for (int i = threadIdx.x; i < 4 * SSD_LUT_STRIDE; i += blockDim.x) lut[i] = __ldg(p.lut + i);
+    for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple[i] = __ldg(p.apple_pts + i);
+    for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste[i] = __ldg(p.waste_pts + i);
+    __syncthreads();
+    SharedTables t = { pal, lut, apple, waste };
+    return t;
+}
+
+// =============================================================================================
+// STEP
+template <int KIND>
+__global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParams p, const StepIO io)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const SharedTables tb = load_shared_tables(p, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
+    uint8_t* stage = tile + p.tile_r16;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
+    uint32_t* sm_abase = scratch + SCRATCH_DRAWS + SCRATCH_KEYS;
+    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
+    __syncwarp();
+    const int n = p.n, S = p.S;
+    const bool act_lane = lane < n;
+
+    for (int env = blockIdx.x * GRID_WARPS + warp; env < p.E; env += gridDim.x * GRID_WARPS) {
+        uint8_t* rec = p.state + (size_t)env * p.rec_stride;
+        uint8_t* hdr = rec + p.map_bytes;
+        tile_load(p, rec, tile, lane);
+        // ---- per-env scalars + agent registers
+        int t = *reinterpret_cast<const int*>(hdr + RO_T) + 1;                 // map_env.py:230
+        const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+        const double theta = *reinterpret_cast<const double*>(hdr + RO_THETA);
+        uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
+        int hcount = *reinterpret_cast<const int*>(hdr + RO_HCOUNT);
+        EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, (uint32_t)t };
+        int ao = 0, ori = 0, act = 4;
+        if (act_lane) {
+            uint32_t a = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[lane];
+            ao = ((int)(a & 255u) + SSD_VIEW) * S + 8 + (int)((a >> 8) & 255u);
+            ori = (int)((a >> 16) & 3u);
+            act = io.actions[(size_t)env * n + lane];
+        }
+        __syncwarp();
+
+        // ---- action decode (Agent.py:8-16,161-162,198-199) + rotations (map_env.py:514-516)
+        int cls = 0;                          // 0 none, 1 FIRE, 2 CLEAN
+        bool has_move = false;
+        int tgt = ao;
+        uint32_t err = 0;
+        if (act_lane) {
+            if (act <= 4) {
+                has_move = true;
+                if (act < 4) {
+                    // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
+                    int rel = act == 0 ? 3 : (act == 1 ? 1 : (act == 2 ? 0 : 2));
+                    int cand = ao + dir_delta((ori + rel) & 3, S);
+                    uint32_t c = tile[cand] & 15u;
+                    if (c != C_WALL && c != C_OUTSIDE) tgt = cand;           // return_valid_pos (Agent.py:111-119)
+                }
+            } else if (act == 5) ori = (ori + 1) & 3;                          // TURN_CLOCKWISE
+            else if (act == 6) ori = (ori + 3) & 3;                            // TURN_COUNTERCLOCKWISE
+            else if (KIND == SSD_ENV_HARVEST) { if (act == 7) cls = 1; else { err |= 8; has_move = true; } }
+            else if (act == 7) cls = 2;
+            else if (act == 8) cls = 1;
+            else { err |= 8; has_move = true; }
+        }
+        err |= resolve_moves(lane, n, tile, g, ao, has_move, tgt);
+
+        // ---- stale-list infos (cleanup_new.py:220-223, harvest_new.py:190-199) on the start-of-step map
+        int eaten = 0, eaten_close = 0, total_close = 0;
+        int reward = 0, cleaned = 0;
+        // co-located agents (possible after unresolved conflicts) share one cell
+        const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
+        if (act_lane) {
+            bool on_apple = (tile[ao] & 15u) == C_APPLE;
+            if (on_apple && !(flags & RF_STALE_EMPTY)) {
+                eaten = 1;
+                if (KIND == SSD_ENV_HARVEST) eaten_close = count_apples_r5(tile, ao, S) < 4;
+            }
+            // consume in agent order: the lowest-index co-located agent eats (map_env.py:244-247)
+            if (on_apple && lane == __ffs(grp) - 1) reward += 1;
+        }
+        __syncwarp();
+        if (act_lane) {
+            uint32_t c = tile[ao];
+            if ((c & 15u) == C_APPLE) c = C_EMPTY;
+            tile[ao] = (uint8_t)(c | OCC_BIT);      // occupancy for beams + spawn eligibility
+        }
+        __syncwarp();
+
+        // ---- beams, spawning
+        int ncleaned = fire_beams(lane, n, S, tile, g, ao, ori, cls, reward, cleaned);
+        if (KIND == SSD_ENV_CLEANUP) {
+            hcount -= ncleaned;
+            hcount += cleanup_spawn(p, lane, tile, scratch, tb.apple, tb.waste, g, (uint32_t)t, hcount);
+        } else {
+            harvest_spawn(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
+        }
+        if (KIND == SSD_ENV_HARVEST && act_lane) total_close = count_apples_r5(tile, ao, S);
+
+        // ---- write the map back (paint stripped), then paint agents for the observation
+        tile_store(p, rec, tile, lane);
+        __syncwarp();
+        // paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261)
+        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)((tile[ao] & 15u) | ((uint32_t)(lane + 1) << 4));
+        bulk_wait_read();                            // previous env's bulk store has drained `stage`
+        set_abase(lane, n, S, sm_abase, ao, ori);
+        __syncwarp();
+        write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase,
+                  io.obs + (size_t)env * (size_t)io.obs_stride);
+        if (act_lane) tile[ao] &= 15u;               // un-paint: the tile buffer is reused for the next env
+        // (stale tile contents are fully overwritten by the next tile_load; only the border must stay C_OUTSIDE)
+
+        // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
+        const double base = (double)reward;
+        double tr = 0.0;
+        if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
+        else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (total_close < 4 && eaten_close > 0) ? theta : 0.0;
+        double r = base, total_tr = 0.0;
+        if (p.contract != SSD_CONTRACT_NONE) {
+            const double nm1 = (double)(n - 1);
+            for (int i = 0; i < n; i++) {
+                double ti = __shfl_sync(FULL, tr, i);
+                if (i == lane) r = __dsub_rn(r, ti); else r = __dadd_rn(r, __ddiv_rn(ti, nm1));
+                total_tr = __dadd_rn(total_tr, ti);
+            }
+        }
+        // raw reward total (ints) for metrics['raw_env_rewards'] is derived from sum_raw on the host
+        const bool done = t == p.horizon;
+        if (act_lane) {
+            size_t o = (size_t)env * n + lane;
+            io.rew[o] = r;
+            if (io.base_rew) io.base_rew[o] = base;
+            if (io.transfers) io.transfers[o] = tr;
+            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] =
+                (uint32_t)eaten | ((uint32_t)(KIND == SSD_ENV_CLEANUP ? cleaned : eaten_close) << 8) | ((uint32_t)total_close << 16);
+            // agent record + accumulators
+            uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
+            reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
+            const double tm1 = (double)(t - 1);
+            reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
+            reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[lane] += (long long)(t - 1) * reward;
+            if (p.contract != SSD_CONTRACT_NONE) {
+                double* st = reinterpret_cast<double*>(hdr + RO_SUM_TR) + lane;
+                double* tt = reinterpret_cast<double*>(hdr + RO_TSUM_TR) + lane;
+                *st = __dadd_rn(*st, r);
+                *tt = __dadd_rn(*tt, __dmul_rn(tm1, r));
+            }
+            if (KIND == SSD_ENV_CLEANUP) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)cleaned;
+            else {
+                reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)eaten;
+                reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[lane] += (uint32_t)eaten_close;
+            }
+        }
+        unsigned eatm = __ballot_sync(FULL, eaten != 0), closem = __ballot_sync(FULL, eaten_close != 0);
+        unsigned errm = __ballot_sync(FULL, err != 0);
+        uint32_t errbits = __reduce_or_sync(FULL, err);
+        if (lane == 0) {
+            *reinterpret_cast<int*>(hdr + RO_T) = t;
+            *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = (flags & ~RF_STALE_EMPTY) | (errm ? (errbits << RF_ERR_SHIFT) : 0u);
+            *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
+            *reinterpret_cast<uint32_t*>(hdr + RO_APPLES) += (uint32_t)__popc(eatm);
+            if (KIND == SSD_ENV_HARVEST) *reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS) += (uint32_t)__popc(closem);
+            else *reinterpret_cast<uint32_t*>(hdr + RO_DIRT) += (uint32_t)ncleaned;
+            if (p.contract != SSD_CONTRACT_NONE) {
+                double* mt = reinterpret_cast<double*>(hdr + RO_TRANSFERS);
+                *mt = __dadd_rn(*mt, total_tr);
+            }
+            if (io.done) io.done[env] = done ? 1 : 0;
+        }
+        __syncwarp();
+    }
+    bulk_wait_read();      // smem must outlive the async bulk reads
+}
+
+// =============================================================================================
+// RESET: setup_agents + reset_map + custom_reset + reset-time spawn + contract sample + reset obs
+template <int KIND>
+__global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridParams p, const uint8_t* mask,
+                                                                  uint8_t* obs, long long obs_stride)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const SharedTables tb = load_shared_tables(p, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
+    uint8_t* stage = tile + p.tile_r16;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
+    uint32_t* sm_abase = scratch + SCRATCH_DRAWS + SCRATCH_KEYS;
+    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
+    __syncwarp();
+    const int n = p.n, S = p.S;
+    const bool act_lane = lane < n;
+
+    for (int env = blockIdx.x * GRID_WARPS + warp; env < p.E; env += gridDim.x * GRID_WARPS) {
+        if (mask && !mask[env]) continue;
+        uint8_t* rec = p.state + (size_t)env * p.rec_stride;
+        uint8_t* hdr = rec + p.map_bytes;
+        uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
+        uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+        // the first reset of a record (flags bit 31 clear) is episode 0; later resets increment
+        episode = (flags & 0x80000000u) ? episode + 1u : 0u;
+        EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, 0u };
+
+        // ---- setup_agents (cleanup_new.py:302-320 / harvest_new.py:132-141; map_env.py:816-832)
+        int ao = 0, ori = 0;
+        unsigned taken[4] = { 0, 0, 0, 0 };          // bit per canonical spawn entry (<= 128), uniform
+        for (int i = 0; i < n; i++) {
+            // shuffled list = canonical entries ordered by (key, idx); the LAST free entry wins (:822-825)
+            uint32_t bk = 0; int bj = -1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int j = lane + 32 * q;
+                if (j < p.n_spawn && !((taken[q] >> lane) & 1u)) {
+                    uint32_t kk = draw_u32(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_POINT, (uint32_t)i, (uint32_t)j);
+                    if (bj < 0 || kk > bk || (kk == bk && j > bj)) { bk = kk; bj = j; }
+                }
+            }
+            uint32_t kmax = __reduce_max_sync(FULL, bj >= 0 ? bk : 0u);
+            int jmax = (int)__reduce_max_sync(FULL, (bj >= 0 && bk == kmax) ? (uint32_t)(bj + 1) : 0u) - 1;
+            int cell = (int)__ldg(p.spawn_pts + jmax);
+            // every canonical entry on that cell becomes occupied (cleanup lists each point twice)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int j = lane + 32 * q;
+                bool same = j < p.n_spawn && (int)__ldg(p.spawn_pts + j) == cell;
+                taken[q] |= __ballot_sync(FULL, same);
+            }
+            uint32_t rdraw = draw_u32(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_ROT, (uint32_t)i, 0u) >> 30;
+            // list(ORIENTATIONS.keys()) = LEFT, RIGHT, UP, DOWN (map_env.py:22, :829-832)
+            int o = rdraw == 0 ? ORI_LEFT : (rdraw == 1 ? ORI_RIGHT : (rdraw == 2 ? ORI_UP : ORI_DOWN));
+            if (lane == i) { ao = cell; ori = o; }
+        }
+        // ---- reset_map + custom_reset: copy the initial map, mark occupancy, reset-time spawn (map_env.py:319-320)
+        tile_load(p, p.reset_map, tile, lane);
+        __syncwarp();
+        if (act_lane) tile[ao] |= OCC_BIT;
+        __syncwarp();
+        int hcount = p.n_waste_start;
+        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn(p, lane, tile, scratch, tb.apple, tb.waste, g, 0u, hcount);
+        else harvest_spawn(p, lane, tile, scratch, tb.apple, g, 0u);
+        tile_store(p, rec, tile, lane);
+        __syncwarp();
+        if (act_lane) tile[ao] &= 15u;               // MapEnv.reset never paints agents into the colour grid
+        bulk_wait_read();
+        set_abase(lane, n, S, sm_abase, ao, ori);
+        __syncwarp();
+        if (obs) write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, obs + (size_t)env * (size_t)obs_stride);
+
+        // ---- SeparateContractSubgameStage.reset (two_stage_train.py:163-168)
+        double theta = 0.0;
+        if (p.contract != SSD_CONTRACT_NONE) {
+            Philox4 q = draw_block(g.seed, g.env_id, g.episode, 0, SITE_CONTRACT, 0, 0);
+            double u0 = __dmul_rn((double)q.x, 1.0 / 4294967296.0), u1 = __dmul_rn((double)q.y, 1.0 / 4294967296.0);
+            theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1))
+                                       : p.theta_low;
+        }
+        // ---- record header
+        if (act_lane) {
+            uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
+            reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
+        }
+        for (int i = lane; i < (RO_SIZE - RO_T) / 4; i += 32) reinterpret_cast<uint32_t*>(hdr + RO_T)[i] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            *reinterpret_cast<uint32_t*>(hdr + RO_EPISODE) = episode;
+            *reinterpret_cast<double*>(hdr + RO_THETA) = theta;
+            *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = 0x80000000u | (KIND == SSD_ENV_CLEANUP ? RF_STALE_EMPTY : 0u);
+            *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
+        }
+        __syncwarp();
+    }
+    bulk_wait_read();
+}

@@ -1,0 +1,152 @@
+/*
+ * ssd_b200.h — C ABI of libssd_b200.so, the B200 (sm_100a) batched simulator for the
+ * sequential-social-dilemma environments of Algorithmic-Alignment-Lab/contracts.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the
+ * interface it exposes for this path is the Python MultiAgentEnv `reset()/step()` of the
+ * classes built by `utils/env_creator_functions.py:12-34`.  Each entry point below replaces
+ * the batched equivalent of one reference method (cited per function; paths relative to the
+ * reference root).  The Python binding a maintainer adds is a ctypes stub — see
+ * INTEGRATION.md and contracts_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: opaque handle, POD config, raw pointers + sizes, no C++/torch types;
+ *   - every function returns 0 on success or a negative SSD_E* code; the message is
+ *     available through ssd_last_error(handle) (or ssd_last_error(NULL) for create errors);
+ *   - all `_dev` pointers are device pointers owned by the CALLER (e.g. torch tensors via
+ *     tensor.data_ptr()); the library owns only the persistent per-env state;
+ *   - every call is asynchronous on the given `stream` (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and performs no host synchronisation;
+ *   - a handle is bound to one device and is not thread-safe; calls must be stream-ordered.
+ *   - env i of a handle has global id `first_env_id + i`; its random stream is
+ *     Philox4x32-10 keyed (seed, global id), so trajectories do not depend on how envs are
+ *     sharded over handles / GPUs.
+ */
+#ifndef SSD_B200_H
+#define SSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_ABI_VERSION 1
+
+/* env_kind: which reference class the handle simulates */
+#define SSD_ENV_CLEANUP 0           /* environments/cleanup_new.py  CleanupEnv   ('CleanupNew') */
+#define SSD_ENV_HARVEST 1           /* environments/harvest_new.py  HarvestEnv   ('HarvestNew') */
+#define SSD_ENV_CLEANUP_FEATURES 2  /* environments/cleanup_features.py CleanupFeatures ('Cleanup') */
+#define SSD_ENV_HARVEST_FEATURES 3  /* environments/harvest_features.py HarvestFeatures ('Harvest') */
+#define SSD_ENV_SELFDRIVE 4         /* environments/self_driving_car_accelerate.py ('SelfDrive') */
+
+/* contract_kind: contract/contract_list.py classes fused into the reward write */
+#define SSD_CONTRACT_NONE 0
+#define SSD_CONTRACT_CLEANUP 1              /* CleanupContract                 :7-27  */
+#define SSD_CONTRACT_HARVEST_LOCAL 2        /* HarvestFeaturemodLocalContract  :29-54 */
+#define SSD_CONTRACT_SELFDRIVE_DISTPROP 3   /* SelfdriveContractDistprop       :56-102 */
+
+#define SSD_MAX_AGENTS 8
+#define SSD_OBS_BYTES_PER_AGENT 675         /* 15 x 15 x 3 uint8 (map_env.py:397-411) */
+#define SSD_METRIC_STRIDE 56                /* doubles per env written by ssd_get_metrics */
+
+#define SSD_OK 0
+#define SSD_EINVAL (-1)
+#define SSD_ENOMEM (-2)
+#define SSD_ECUDA (-3)
+#define SSD_EUNSUPPORTED (-4)
+
+typedef struct ssd_handle ssd_handle;
+
+typedef struct ssd_config {
+    int32_t abi_version;      /* SSD_ABI_VERSION */
+    int32_t env_kind;
+    int32_t num_envs;         /* E, envs stepped per launch by this handle */
+    int32_t num_agents;       /* n in [1, 8] */
+    int32_t map_h, map_w;     /* gridworlds: ascii map size; ignored by selfdrive */
+    const char* ascii_map;    /* map_h * map_w chars, row-major (CLEANUP_MAP / HARVEST_MAP layout) */
+    int32_t horizon;          /* env `horizon` kwarg (cleanup_new.py:71): done when t == horizon */
+    int32_t contract_kind;
+    double theta_low;         /* contract_space.low[0]  (a float32 value, e.g. 0) */
+    double theta_high;        /* contract_space.high[0] (a float32 value, e.g. float32(0.2)) */
+    double null_prob;         /* SeparateContractSubgameStage null_prob (two_stage_train.py:152-166) */
+    uint32_t seed;            /* Philox key word 0 */
+    uint32_t first_env_id;    /* global id of env 0 (Philox key word 1 = first_env_id + i) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t flags;            /* reserved, 0 */
+} ssd_config;
+
+/* Buffers of one step.  Gridworld / feature envs: actions are uint8 [E][n] action ids
+ * (Agent.py:8-16,161-162,198-199); selfdrive: float32 [E][n] accelerations.
+ * NULL is allowed for every output except obs and rew. */
+typedef struct ssd_step_io {
+    const void* actions_dev;
+    uint8_t* obs_dev;         /* gridworlds: uint8 [E][n][15][15][3] (MapEnv.step 'curr_obs', map_env.py:269,284) */
+    int64_t obs_env_stride;   /* bytes between consecutive envs in obs_dev (>= n*675; 0 = dense) */
+    double* rew_dev;          /* [E][n] rewards AFTER contract transfers (two_stage_train.py:69-90) */
+    double* base_rew_dev;     /* [E][n] env rewards before transfers (MapEnv.step rewards, map_env.py:285) */
+    double* transfers_dev;    /* [E][n] Contract.compute_transfer values (contract_list.py) */
+    uint8_t* info_dev;        /* [E][n][4]: eaten_apples, cleaned_squares|eaten_close_apples, total_close_apples, 0 */
+    double* feature_obs_dev;  /* [E][n][F] infos['feature_obs'] (cleanup_new.py:243-251 F=12+n, harvest_new.py:215-222 F=10+2n) */
+    uint8_t* done_dev;        /* [E] dones['__all__'] (cleanup_new.py:242) */
+} ssd_step_io;
+
+/* --- lifetime ------------------------------------------------------------------------------- */
+/* Replaces env_creator(name, config) (utils/env_creator_functions.py:12-34) for E envs at once:
+ * parses the ascii map like MapEnv.__init__/CleanupEnv.__init__ (map_env.py:92-130,
+ * cleanup_new.py:106-125), uploads point lists / palette / spawn-probability thresholds. */
+int ssd_create(const ssd_config* cfg, ssd_handle** out);
+void ssd_destroy(ssd_handle* h);
+const char* ssd_last_error(const ssd_handle* h);
+
+/* --- the hot path ----------------------------------------------------------------------------- */
+/* MapEnv.reset + CleanupEnv/HarvestEnv.custom_reset + SeparateContractSubgameStage.reset
+ * (map_env.py:306-342, cleanup_new.py:171-209, harvest_new.py:143-176, two_stage_train.py:159-187)
+ * for the envs with mask_dev[i] != 0 (all envs when mask_dev is NULL).  Writes the reset
+ * observation of those envs (agents are NOT drawn in it, as in the reference). */
+int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t obs_env_stride, void* stream);
+
+/* MapEnv.step (map_env.py:216-304) + env step tail (cleanup_new.py:211-267 / harvest_new.py:181-239)
+ * + SeparateContractEnv.step reward redistribution (two_stage_train.py:62-121), one launch for E envs. */
+int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream);
+
+/* --- contract parameters / negotiation ----------------------------------------------------------- */
+/* theta_dev: double [E].  What SeparateContractNegotiateStage does with a0's proposal
+ * (two_stage_train.py:258-262) / a caller-chosen contract. */
+int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream);
+/* Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281):
+ * proposals_dev double [E] (a0's action[:-1]), accept_dev double [E][n] (each agent's action[-1]),
+ * decision_dev uint8 [E] out.  Chooses 2 of agents 1..n-1 when n > 3, multiplies their accept
+ * values, draws once and keeps the proposal as theta or zeroes it. */
+int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev,
+                  void* stream);
+
+/* --- state access (parity tests, checkpointing) ---------------------------------------------------- */
+/* map: uint8 chars [E][H][W] (MapEnv.world_map); pos: int32 [E][n][2] (row, col); ori: int32 [E][n]
+ * (Agent.int_orientation); t: int32 [E] (MapEnv.timesteps); theta: double [E].  NULL pointers are skipped. */
+int ssd_get_state(ssd_handle* h, uint8_t* map_dev, int32_t* pos_dev, int32_t* ori_dev, int32_t* t_dev,
+                  double* theta_dev, void* stream);
+int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev, const int32_t* ori_dev,
+                  const int32_t* t_dev, const double* theta_dev, void* stream);
+/* Episode accumulators behind env.metrics (cleanup_new.py:186-189,213-232,264-266; two_stage_train.py:92-99).
+ * out_dev: double [E][SSD_METRIC_STRIDE] =
+ *   [apples_eaten, low_density_eaten, raw_env_rewards, transfers, dirt_cleaned, err_flags, 0, 0,
+ *    agent_a[8], agent_b[8], sum_raw[8], tsum_raw[8], sum_transferred[8], tsum_transferred[8]] */
+int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream);
+
+/* --- utilities ------------------------------------------------------------------------------------------ */
+/* uniform random action ids in [0, num_actions) for benchmark rollouts, uint8 [E][n];
+ * drawn from Philox site 13 at counter `step_index` (no reference equivalent: RLlib's policy). */
+int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream);
+/* host-side Philox4x32-10 (so tests can pin the generator: KATs in tests/test_philox.py) */
+void ssd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int ssd_abi_version(void);
+int ssd_feature_dim(const ssd_handle* h);          /* F of feature_obs_dev */
+int64_t ssd_state_bytes_per_env(const ssd_handle* h);
+int64_t ssd_kernel_launches(const ssd_handle* h);  /* kernels launched through this handle so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD_B200_H */

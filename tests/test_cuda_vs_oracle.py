@@ -1,0 +1,64 @@
+"""GPU: CUDA path vs the C oracle on seeded random rollouts (many envs, every output, bit-exact)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+CRAMPED_CLEANUP = ["@@@@@@", "@PPPP@", "@PPPP@", "@HBBR@", "@PPPP@", "@@@@@@"]
+CRAMPED_HARVEST = ["@@@@@@", "@PPPP@", "@PAAP@", "@PAAP@", "@PPPP@", "@@@@@@"]
+
+CASES = [
+    # kind, n, map, E, steps, horizon, n_actions, seed, first_env_id
+    ("cleanup", 8, None, 192, 260, 100, 9, 73907, 0),
+    ("cleanup", 2, None, 67, 150, 1000, 8, 1, 4294967000),
+    ("cleanup", 3, None, 33, 120, 50, 9, 2, 17),
+    ("harvest", 4, None, 160, 220, 90, 8, 73907, 5),
+    ("harvest", 8, None, 64, 150, 1000, 8, 3, 0),
+    ("cleanup", 8, CRAMPED_CLEANUP, 128, 300, 1000, 9, 4, 0),
+    ("harvest", 8, CRAMPED_HARVEST, 128, 300, 1000, 5, 5, 0),
+    ("harvest", 1, None, 8, 60, 1000, 8, 6, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-n%d-%s-E%d" % (c[0], c[1], "stock" if c[2] is None else "cramped", c[3]))
+def test_rollout_matches_oracle(oracle_lib, case):
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    kind, n, amap, E, steps, horizon, nact, seed, first = case
+    amap = amap or (CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP)
+    contract = None if n < 2 else ("CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract")
+    orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first)
+    env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first)
+    rng = np.random.RandomState(seed)
+
+    def check_state(ctx):
+        so, sc = orc.get_state(), env.get_state()
+        for k in ("map", "pos", "ori", "t"):
+            gu.assert_same(k, sc[k].cpu().numpy(), so[k], ctx)
+        gu.assert_same("theta", sc["theta"].cpu().numpy(), so["theta"], ctx)
+
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    check_state("reset")
+    for t in range(steps):
+        a = rng.randint(0, nact, size=(E, n))
+        o = orc.step(a, want_features=False)
+        obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        ctx = "step %d" % t
+        gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+        gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+        gu.assert_same("base_rew", env.base_rew.cpu().numpy(), o["base_rew"], ctx)
+        gu.assert_same("transfers", env.transfers.cpu().numpy(), o["transfers"], ctx)
+        gu.assert_same("info", info.cpu().numpy()[..., :3], o["info"][..., :3], ctx)
+        gu.assert_same("done", done.cpu().numpy(), o["done"], ctx)
+        if t % 10 == 0 or o["done"].any():
+            check_state(ctx)
+        if o["done"].any():          # masked reset of the finished envs (all of them here: equal horizons)
+            mask = o["done"].copy()
+            mask[::3] = 0             # reset only a subset; the others keep running past the horizon
+            gu.assert_same("masked reset obs", env.reset(torch.as_tensor(mask).cuda()).cpu().numpy()[mask.astype(bool)],
+                           orc.reset(mask)[mask.astype(bool)], ctx)
+            check_state(ctx + " after reset")
+    gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
