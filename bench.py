@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the hot path on B200 (and the CPU reference arm).
+
+Metric (BASELINE.json): agent-steps/s, cleanup_new, 8 agents, observations included.
+Workload (`config.workload`): BASELINE configs[2] — CleanupEnv(num_agents=8) + CleanupContract with the
+two-stage negotiation prologue each episode, horizon 1000, iid uniform random actions, E envs
+per GPU (weak scaling: every rank owns E envs with global ids rank*E .. rank*E+E-1; no
+collective on the step path; one NCCL all-gather of episode statistics per episode).
+
+A "step" = one `ssd_step` launch over the rank's E envs (+ the action-generation launch).
+  value  : device-resident (actions generated on device, outputs stay in HBM), CUDA-event timed
+  e2e    : same step through the public API with HOST buffers: pinned actions -> H2D, step,
+           rewards + dones -> D2H, host sync every step (observations stay in the policy's
+           device batch tensor, as designed; `e2e_obs_to_host` additionally copies them out)
+  roofline: algorithmic bytes (840 B/agent-step) / measured ssd_step duration
+  cpu_baseline / --impl reference: the C oracle (port of the reference algorithm) on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = 8
+HORIZON = 1000
+N_ACTIONS = 8                      # cleanup_new with disable_firing (cleanup_new.py:90-92): Discrete(8)
+ALG_BYTES_PER_AGENT_STEP = 840.0
+SEED = 73907                       # reference seed multiplier (runner.py:130)
+WORKLOAD = "cleanup_new n=8 CleanupContract + negotiation prologue, horizon 1000, random actions"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_cpu(envs_per_thread, steps, warmup):
+    """The oracle port on all host cores (OpenMP).  Returns (agent-steps/s, cores, sample string)."""
+    from oracle import oracle
+    from contracts_b200.maps import CLEANUP_MAP
+    cores = os.cpu_count() or 1
+    E = envs_per_thread * cores
+    o = oracle.GridOracle("cleanup", E, N_AGENTS, CLEANUP_MAP, horizon=HORIZON, contract="CleanupContract", seed=SEED)
+    o.reset()
+    rng = np.random.RandomState(0)
+    acts = rng.randint(0, N_ACTIONS, size=(16, E, N_AGENTS)).astype(np.int32)
+    for t in range(warmup):
+        o.step(acts[t % 16], want_features=False)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        o.step(acts[t % 16], want_features=False)
+    dt = time.perf_counter() - t0
+    return E * N_AGENTS * steps / dt, cores, dt / steps * 1e3, \
+        "C oracle port, OpenMP x%d, %d envs x %d steps of the same workload (no negotiation prologue, no feature_obs)" % (cores, E, steps)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # ~10-30 s of CPU work: 64 envs per core, steps scaled so the run is bounded
+    steps, warm = max(args.steps, 1), max(args.warmup, 3)
+    per_core = 64
+    budget_steps = 300
+    if steps > budget_steps:
+        steps_run = budget_steps
+    else:
+        steps_run = steps
+    v, cores, ms, sample = run_cpu(per_core, steps_run, min(warm, 50))
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": v, "unit": "agent-steps/s", "n_gpus": args.gpus,
+        "steps": steps_run, "warmup": min(warm, 50), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs": per_core * cores, "agents": N_AGENTS, "horizon": HORIZON},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference itself is Python (cannot travel to the GPU box); this is its C restatement (oracle/) "
+                "on all host cores — ~100x faster per core than the Python reference (BASELINE.md: 3.9k/s/core)",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=131072, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from contracts_b200.batched import BatchedGridEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, n = args.envs, N_AGENTS
+    K, W = args.steps, max(args.warmup, 3)
+
+    env = BatchedGridEnv("cleanup_new", E, n, horizon=HORIZON, contract="CleanupContract", seed=SEED,
+                         first_env_id=rank * E, device=dev)
+    actions = torch.empty((E, n), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    stats_out = [torch.zeros((E, 56), dtype=torch.float64, device=dev)]
+    gathered = torch.zeros((world, 8), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def new_episode():
+        """reset + negotiation prologue (two_stage_train.py:257-281): a0 proposes theta ~ U[0, 0.2], others accept ~ U[0,1]."""
+        env.reset()
+        proposals = torch.rand((E,), dtype=torch.float64, device=dev, generator=gen) * 0.2
+        accept = torch.rand((E, n), dtype=torch.float64, device=dev, generator=gen)
+        env.negotiate(proposals, accept)
+
+    def end_episode():
+        """episode statistics -> one small NCCL all-gather (the only collective of the workload)."""
+        m = env.metrics_raw()
+        s = torch.stack([m[:, 0].sum(), m[:, 2].sum(), m[:, 3].sum(), m[:, 4].sum(),
+                         m[:, 40:48].sum(), m[:, 24:32].sum(), torch.tensor(float(E), device=dev, dtype=torch.float64),
+                         m[:, 5].max()])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s)
+            return gathered.sum(0)
+        return s
+
+    state = {"t": 0, "global_step": 0, "stats": None}
+
+    def one_step(device_actions=True, host_actions=None):
+        if state["t"] == 0:
+            new_episode()
+        if device_actions:
+            env.random_actions(state["global_step"], N_ACTIONS, out=actions)
+        else:
+            actions.copy_(host_actions, non_blocking=True)
+        env.step(actions, extras=False)
+        state["t"] += 1
+        state["global_step"] += 1
+        if state["t"] == HORIZON:
+            state["stats"] = end_episode()
+            state["t"] = 0
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then the timed device-resident run -------------------------------------------
+    for _ in range(W):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev0.record()
+    for k in range(K):
+        if state["t"] == 0:
+            new_episode()
+        env.random_actions(state["global_step"], N_ACTIONS, out=actions)
+        kev[k][0].record()
+        env.step(actions, extras=False)
+        kev[k][1].record()
+        state["t"] += 1
+        state["global_step"] += 1
+        if state["t"] == HORIZON:
+            state["stats"] = end_episode()
+            state["t"] = 0
+    ev1.record()
+    barrier()
+    launches = env.kernel_launches - l0
+    ms_total = ev0.elapsed_time(ev1)
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = world * E * n * K / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host results out, sync every step ----------------------------------
+    Ke = min(args.e2e_steps, K)
+    host_actions = [torch.randint(0, N_ACTIONS, (E, n), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    host_rew = torch.empty((E, n), dtype=torch.float64).pin_memory()
+    host_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    for i in range(3):
+        one_step(False, host_actions[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        one_step(False, host_actions[i % 4])
+        host_rew.copy_(env.rew, non_blocking=True)
+        host_done.copy_(env.done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * n * Ke / (float(e2e_ms.item()) * 1e-3)
+    # informational: also ship the observations to the host (PCIe-bound by construction)
+    obs_to_host = None
+    if rank == 0:
+        host_obs = torch.empty(env._obs_buf.shape, dtype=torch.uint8).pin_memory()
+        Ko = 10
+        torch.cuda.synchronize(dev)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for i in range(Ko):
+            one_step(False, host_actions[i % 4])
+            host_rew.copy_(env.rew, non_blocking=True)
+            host_obs.copy_(env._obs_buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        o1.record()
+        torch.cuda.synchronize(dev)
+        obs_to_host = E * n * Ko / (o0.elapsed_time(o1) * 1e-3)
+    barrier()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALG_BYTES_PER_AGENT_STEP * E * n / (step_ms * 1e-3) / 1e9
+        line = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents": n, "horizon": HORIZON,
+                       "l2": "working set %.0f MB/step (obs %.0f MB + state) exceeds the 126 MB L2" % (
+                           (E * (n * 675 + 2 * env.state_bytes_per_env)) / 1e6, E * n * 675 / 1e6),
+                       "parallelism": "env batch sharded over %d GPU(s), no collective on the step path" % world},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * n,
+                    "d2h_bytes_per_step": E * n * 8 + E, "steps": Ke,
+                    "note": "pinned host actions in, rewards+dones out, host sync every step; observations stay in the device batch tensor"},
+            "e2e_obs_to_host": {"value": obs_to_host, "unit": "agent-steps/s", "d2h_bytes_per_step": E * n * 675 + E * n * 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "grid_step_kernel<cleanup>",
+                         "kernel_ms": step_ms, "alg_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP},
+        }
+        if state["stats"] is not None:
+            s = state["stats"].tolist()
+            line["episode_stats"] = {"apples_eaten": s[0], "raw_env_rewards": s[1], "transfers": s[2],
+                                     "dirt_cleaned": s[3], "envs": s[6], "err_flags": s[7]}
+        if world == 1 and not args.no_cpu:
+            v, cores, ms, sample = run_cpu(64, 150, 20)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
