@@ -56,16 +56,14 @@ static uint32_t prob_threshold(double p)
 
 // DEFAULT_COLOURS (map_env.py:24-42) + CLEANUP_COLORS (cleanup_new.py:42-47), packed r | g << 8 | b << 16
 static uint32_t rgb(int r, int g, int b) { return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16); }
-static void build_palette(uint32_t* pal)
+static void build_palette(uint32_t* pal)   // index = tile byte value: cell codes 0..5, 6 + i = agent i, 15 = outside
 {
-    const uint32_t cell[16] = { rgb(0, 0, 0), rgb(180, 180, 180), rgb(0, 255, 0), rgb(99, 156, 194),
-                                rgb(113, 75, 24), rgb(113, 75, 24), 0, 0, 0, 0, 0, 0, 0, 0, 0, rgb(0, 0, 0) };
-    const uint32_t agent[9] = { rgb(0, 0, 255), rgb(2, 81, 154), rgb(204, 0, 204), rgb(216, 30, 54), rgb(254, 151, 0),
-                                rgb(100, 255, 255), rgb(99, 99, 255), rgb(250, 204, 255), rgb(238, 223, 16) };
-    for (int b = 0; b < 256; b++) {
-        int hi = b >> 4, lo = b & 15;
-        pal[b] = (hi >= 1 && hi <= 9) ? agent[hi - 1] : cell[lo];
-    }
+    const uint32_t v[16] = { rgb(0, 0, 0), rgb(180, 180, 180), rgb(0, 255, 0), rgb(99, 156, 194), rgb(113, 75, 24),
+                             rgb(113, 75, 24),
+                             rgb(0, 0, 255), rgb(2, 81, 154), rgb(204, 0, 204), rgb(216, 30, 54), rgb(254, 151, 0),
+                             rgb(100, 255, 255), rgb(99, 99, 255), rgb(250, 204, 255),
+                             0, rgb(0, 0, 0) };
+    for (int i = 0; i < 16; i++) pal[i] = v[i];
 }
 
 template <typename T>
@@ -92,6 +90,7 @@ static int setup_grid(ssd_handle* h)
     p.E = c.num_envs; p.n = n; p.H = H; p.W = W;
     p.Wp = round_up(W, 4); p.S = 8 + p.Wp + 8; p.TH = H + 2 * SSD_VIEW;
     p.wpw = p.Wp / 4; p.wpw_magic = (65536u + p.wpw - 1) / p.wpw;
+    p.s_magic = (uint32_t)((4294967296ull + p.S - 1) / p.S);
     p.map_bytes = round_up(H * p.Wp, 16);
     p.rec_stride = p.map_bytes + RO_SIZE;
     p.kind = c.env_kind; p.contract = c.contract_kind; p.horizon = c.horizon;
@@ -100,7 +99,8 @@ static int setup_grid(ssd_handle* h)
     p.F = c.env_kind == SSD_ENV_CLEANUP ? 12 + n : 10 + 2 * n;
 
     // parse the map like MapEnv.__init__ / CleanupEnv.__init__ / HarvestEnv.__init__
-    std::vector<uint16_t> apple, waste, spawn;
+    std::vector<uint16_t> apple, waste, spawn, apple_rc, waste_rc;
+    auto rc16 = [](int r, int col) { return (uint16_t)((r << 8) | col); };
     std::vector<uint8_t> reset_map(p.map_bytes, (uint8_t)C_OUTSIDE);
     int n_waste_start = 0, n_spawn_unique = 0;
     auto off = [&](int r, int col) { return (uint16_t)((r + SSD_VIEW) * p.S + 8 + col); };
@@ -111,12 +111,12 @@ static int setup_grid(ssd_handle* h)
             if (ch == '@') code = C_WALL;
             if (ch == 'P') { spawn.push_back(off(r, col)); n_spawn_unique++; if (c.env_kind == SSD_ENV_CLEANUP) spawn.push_back(off(r, col)); }
             if (c.env_kind == SSD_ENV_CLEANUP) {
-                if (ch == 'B') apple.push_back(off(r, col));
+                if (ch == 'B') { apple.push_back(off(r, col)); apple_rc.push_back(rc16(r, col)); }
                 if (ch == 'H') { code = C_WASTE; n_waste_start++; }
                 if (ch == 'R') code = C_RIVER;
                 if (ch == 'S') code = C_STREAM;
-                if (ch == 'H' || ch == 'R') waste.push_back(off(r, col));
-            } else if (ch == 'A') { apple.push_back(off(r, col)); code = C_APPLE; }
+                if (ch == 'H' || ch == 'R') { waste.push_back(off(r, col)); waste_rc.push_back(rc16(r, col)); }
+            } else if (ch == 'A') { apple.push_back(off(r, col)); apple_rc.push_back(rc16(r, col)); code = C_APPLE; }
             reset_map[r * p.Wp + col] = code;
         }
     // canonical spawn order is the sorted list (row-major offsets are already sorted; duplicates adjacent)
@@ -156,18 +156,20 @@ static int setup_grid(ssd_handle* h)
     p.thr_waste = prob_threshold(0.5);
 
     // observation window LUT: color_view (map_env.py:397-411); V[a][b] = tile[origin + a*S + b]
-    std::vector<uint16_t> lut(4 * SSD_LUT_STRIDE, 0);
-    for (int o = 0; o < 4; o++)
-        for (int i = 0; i < SSD_OBSW; i++)
-            for (int j = 0; j < SSD_OBSW; j++) {
-                int vi, vj;
+    // lut[phase][o][i] = offset of pixel (phase + i): the agent whose first word-aligned pixel is `phase`
+    // reads 4 consecutive entries with one 8-byte load
+    std::vector<uint16_t> lut(16 * SSD_LUT_STRIDE, 0);
+    for (int ph = 0; ph < 4; ph++)
+        for (int o = 0; o < 4; o++)
+            for (int px = ph; px < SSD_OBS_PIX; px++) {
+                int i = px / SSD_OBSW, j = px % SSD_OBSW, vi, vj;
                 if (o == ORI_UP) { vi = i; vj = j; }
                 else if (o == ORI_LEFT) { vi = j; vj = SSD_OBSW - 1 - i; }            // np.rot90(v)
                 else if (o == ORI_DOWN) { vi = SSD_OBSW - 1 - i; vj = SSD_OBSW - 1 - j; }  // np.rot90(v, k=2)
                 else { vi = SSD_OBSW - 1 - j; vj = i; }                              // np.rot90(v, k=1, axes=(1,0))
-                lut[o * SSD_LUT_STRIDE + i * SSD_OBSW + j] = (uint16_t)(vi * p.S + vj);
+                lut[(ph * 4 + o) * SSD_LUT_STRIDE + (px - ph)] = (uint16_t)(vi * p.S + vj);
             }
-    std::vector<uint32_t> pal(256);
+    std::vector<uint32_t> pal(16);
     build_palette(pal.data());
 
     int rc;
@@ -176,6 +178,8 @@ static int setup_grid(ssd_handle* h)
     if ((rc = upload(h, apple, &p.apple_pts))) return rc;
     if ((rc = upload(h, waste, &p.waste_pts))) return rc;
     if ((rc = upload(h, spawn, &p.spawn_pts))) return rc;
+    if ((rc = upload(h, apple_rc, &p.apple_rc))) return rc;
+    if ((rc = upload(h, waste_rc, &p.waste_rc))) return rc;
     if ((rc = upload(h, thr_apple, &p.thr_apple))) return rc;
     if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
     if ((rc = upload(h, reset_map, &p.reset_map))) return rc;
@@ -183,10 +187,14 @@ static int setup_grid(ssd_handle* h)
     // shared memory layout
     p.tile_r16 = round_up(p.TH * p.S, 16);
     p.stage_r16 = round_up(n * SSD_OBS_BYTES + 16 + 16, 16);
-    p.warp_bytes = p.tile_r16 + p.stage_r16 + (SCRATCH_DRAWS + SCRATCH_KEYS) * 4 + 32;
-    p.sm_apple = 1024 + round_up(4 * SSD_LUT_STRIDE * 2, 16);
+    if (p.stage_r16 < (SCRATCH_DRAWS + SCRATCH_KEYS) * 4) p.stage_r16 = (SCRATCH_DRAWS + SCRATCH_KEYS) * 4;
+    p.warp_bytes = p.tile_r16 + p.stage_r16 + 32;
+    p.sm_lut = 16 * 32 * 4;
+    p.sm_apple = p.sm_lut + round_up(16 * SSD_LUT_STRIDE * 2, 16);
     p.sm_waste = p.sm_apple + round_up(p.n_apple * 2, 16);
-    p.sm_warp0 = p.sm_waste + round_up(p.n_waste * 2, 16);
+    p.sm_apple_rc = p.sm_waste + round_up(p.n_waste * 2, 16);
+    p.sm_waste_rc = p.sm_apple_rc + round_up(p.n_apple * 2, 16);
+    p.sm_warp0 = p.sm_waste_rc + round_up(p.n_waste * 2, 16);
     p.smem_bytes = p.sm_warp0 + GRID_WARPS * p.warp_bytes;
 
     void* st = nullptr;

@@ -51,18 +51,21 @@ struct GridParams {
     uint32_t wpw_magic;      // ceil(65536 / wpw): q = (w * magic) >> 16 for w < 65536 / wpw
     int map_bytes;           // H * Wp rounded up to 16
     int rec_stride;          // map_bytes + RO_SIZE
-    int tile_r16, stage_r16, warp_bytes, sm_apple, sm_waste, sm_warp0, smem_bytes;
+    int tile_r16, stage_r16, warp_bytes, sm_lut, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;
     double theta_low, theta_high, null_prob;
     uint32_t thr_harvest[4]; // SPAWN_PROB thresholds (harvest_new.py:34)
     uint32_t thr_waste;      // wasteSpawnProbability = 0.5
-    const uint32_t* pal;     // [256] packed RGB per tile byte
-    const uint16_t* lut;     // [4][SSD_LUT_STRIDE] window offsets per orientation
+    const uint32_t* pal;     // [16] packed RGB per tile byte value (cell codes 0..5, agents 6..13, outside 15)
+    const uint16_t* lut;     // [4 phases][4 orientations][SSD_LUT_STRIDE] window offsets, phase-shifted copies
+    uint32_t s_magic;        // ceil(2^32 / S): row = umulhi(offset, s_magic)
     const uint16_t* apple_pts;
     const uint16_t* waste_pts;
     const uint16_t* spawn_pts;
+    const uint16_t* apple_rc;    // row << 8 | col of each apple point (feature_obs only)
+    const uint16_t* waste_rc;
     const uint32_t* thr_apple;   // [n_waste + 1] apple spawn threshold by #waste
     const uint8_t* waste_on;     // [n_waste + 1]
     const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
@@ -77,6 +80,12 @@ struct StepIO {
 };
 
 struct EnvRng { uint32_t seed, env_id, episode, t; };
+
+// per-CTA copies of the static tables in shared memory
+struct SharedTables {
+    const uint32_t* pal; const uint16_t* lut; const uint16_t* apple; const uint16_t* waste;
+    const uint16_t* apple_rc; const uint16_t* waste_rc;
+};
 
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 __device__ __forceinline__ int dir_delta(int ori, int S)
@@ -434,42 +443,133 @@ __device__ __forceinline__ int count_apples_r5(const uint8_t* tile, int o, int S
 }
 
 // ---------------------------------------------------------------------------------------------
+// infos['feature_obs'] (cleanup_new.py:235-251, harvest_new.py:208-222).  Lists are the row-major
+// scans of the post-step map (compute_current_apples / _wastes); np.argmin takes the first minimum,
+// i.e. the smallest (L1 distance, list index).  Returns (dist << 16 | index) or 0xFFFFFFFF.
+__device__ __forceinline__ uint32_t closest_point(int lane, const uint8_t* tile, const uint16_t* pts,
+                                                  const uint16_t* rc, int npts, uint32_t code, int ar, int ac)
+{
+    uint32_t best = 0xFFFFFFFFu;
+    for (int j = lane; j < npts; j += 32) {
+        if ((tile[pts[j]] & 15u) == code) {
+            int r = rc[j] >> 8, c = rc[j] & 255;
+            uint32_t key = ((uint32_t)(abs(r - ar) + abs(c - ac)) << 16) | (uint32_t)j;
+            best = key < best ? key : best;
+        }
+    }
+    return __reduce_min_sync(FULL, best);
+}
+__device__ __forceinline__ int count_points(int lane, const uint8_t* tile, const uint16_t* pts, int npts, uint32_t code)
+{
+    int cnt = 0;
+    for (int j0 = 0; j0 < npts; j0 += 32) {
+        int j = j0 + lane;
+        cnt += __popc(__ballot_sync(FULL, j < npts && (tile[pts[j]] & 15u) == code));
+    }
+    return cnt;
+}
+template <int KIND>
+__device__ __forceinline__ void write_features(const GridParams& p, const SharedTables& tb, int lane, const uint8_t* tile,
+                                               int ao, int ori, int cleaned, int total_close, int hcount, double* out)
+{
+    const int n = p.n, S = p.S;
+    const int my_r = ao / S - SSD_VIEW, my_c = ao % S - 8;
+    const int n_apples = count_points(lane, tile, tb.apple, p.n_apple, C_APPLE);
+    int ca_r = 0, ca_c = 0, cw_r = 0, cw_c = 0;        // sentinel [0, 0] when the list is empty
+    for (int a = 0; a < n; a++) {
+        int ar = __shfl_sync(FULL, my_r, a), ac = __shfl_sync(FULL, my_c, a);
+        uint32_t ka = closest_point(lane, tile, tb.apple, tb.apple_rc, p.n_apple, C_APPLE, ar, ac);
+        uint32_t kw = 0xFFFFFFFFu;
+        if (KIND == SSD_ENV_CLEANUP) kw = closest_point(lane, tile, tb.waste, tb.waste_rc, p.n_waste, C_WASTE, ar, ac);
+        if (lane == a) {
+            if (ka != 0xFFFFFFFFu) { ca_r = tb.apple_rc[ka & 0xFFFFu] >> 8; ca_c = tb.apple_rc[ka & 0xFFFFu] & 255; }
+            if (kw != 0xFFFFFFFFu) { cw_r = tb.waste_rc[kw & 0xFFFFu] >> 8; cw_c = tb.waste_rc[kw & 0xFFFFu] & 255; }
+        }
+    }
+    // compute_closest_pos (cleanup_new.py:405-412): distances are 0 for every other agent, so the
+    // argmin is agent 0 (agent 1 for agent 0; itself when alone)
+    const int cp = lane == 0 ? (n > 1 ? 1 : 0) : 0;
+    const int cp_r = __shfl_sync(FULL, my_r, cp), cp_c = __shfl_sync(FULL, my_c, cp), cp_o = __shfl_sync(FULL, ori, cp);
+    int cl[SSD_MAXN];
+#pragma unroll
+    for (int j = 0; j < SSD_MAXN; j++) cl[j] = __shfl_sync(FULL, cleaned, j);
+    if (lane < n) {
+        double* f = out + (size_t)lane * p.F;
+        f[0] = my_r; f[1] = my_c; f[2] = ori; f[3] = cp_r; f[4] = cp_c; f[5] = cp_o; f[6] = ca_r; f[7] = ca_c;
+        if (KIND == SSD_ENV_CLEANUP) {
+            f[8] = cw_r; f[9] = cw_c; f[10] = n_apples; f[11] = hcount;
+#pragma unroll
+            for (int j = 0; j < SSD_MAXN; j++) if (j < n) f[12 + j] = cl[j];
+        } else {
+            f[8] = total_close; f[9] = n_apples;
+            for (int j = 0; j < 2 * n; j++) f[10 + j] = 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // observations: gather the rotated windows of all agents into `stage` (word-aligned to the
 // global destination modulo 16) and ship them with one bulk async copy.
 __device__ __forceinline__ void bulk_wait_read()
 {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// Stream layout: agent a's 225 pixels start at byte 675*a of the env's block.  Work is split in
+// word-aligned groups of 4 pixels (12 B = 3 words).  Because 225 = 1 (mod 4), agent a's first
+// aligned pixel is phase = (-a) & 3; its full groups read a phase-shifted copy of the window LUT
+// with one 8-byte load, and the <= n groups that straddle two agents are done in one extra pass.
+__device__ __forceinline__ void pack4(uint32_t* dst, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3)
+{
+    dst[0] = p0 | (p1 << 24);
+    dst[1] = (p1 >> 8) | (p2 << 16);
+    dst[2] = (p2 >> 16) | (p3 << 8);
+}
 __device__ __forceinline__ void write_obs(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
                                           const uint32_t* sm_pal, const uint16_t* sm_lut,
-                                          const uint32_t* sm_abase /* [8]: window origin | lut row << 16 */,
-                                          uint8_t* gdst)
+                                          uint32_t* sm_abase /* [8] scratch: window origin | orientation << 16 */,
+                                          int ao, int ori, uint8_t* gdst)
 {
-    const int n = p.n;
+    const int n = p.n, S = p.S;
     const int L = n * SSD_OBS_BYTES;
-    const int npix = n * SSD_OBS_PIX;
     const uint32_t gaddr = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
     const bool word_ok = (gaddr & 3u) == 0;
     const int shift = word_ok ? (int)gaddr : 0;
     uint32_t* sw = reinterpret_cast<uint32_t*>(stage + shift);
-    const int G = (npix + 3) >> 2;                    // groups of 4 pixels = 12 bytes = 3 words
-    for (int gi = lane; gi < G; gi += 32) {
-        int q0 = gi * 4;
-        int a = q0 / SSD_OBS_PIX;
-        int pp = q0 - a * SSD_OBS_PIX;
-        uint32_t px[4];
-#pragma unroll
-        for (int kx = 0; kx < 4; kx++) {
-            if (pp >= SSD_OBS_PIX) { pp -= SSD_OBS_PIX; a++; }
-            int aa = a < n ? a : n - 1;
-            uint32_t ab = sm_abase[aa];
-            int off = (int)(ab & 0xFFFFu) + (int)sm_lut[(ab >> 16) + pp];
-            px[kx] = sm_pal[tile[off]];
-            pp++;
+    const uint32_t* pal_lane = sm_pal + lane;            // bank == lane: conflict-free palette reads
+    const int origin = ao - SSD_VIEW * S - SSD_VIEW;     // V[0][0] of this lane's agent
+    if (lane < n) sm_abase[lane] = (uint32_t)origin | ((uint32_t)ori << 16);
+    for (int a = 0; a < n; a++) {
+        const uint8_t* tb = tile + __shfl_sync(FULL, origin, a);
+        const int o_a = __shfl_sync(FULL, ori, a);
+        const int phase = (-a) & 3;
+        const int n_full = (SSD_OBS_PIX - phase) >> 2;
+        const int g0 = (SSD_OBS_PIX * a + phase) >> 2;   // flat index of the agent's first full group
+        const uint2* lg = reinterpret_cast<const uint2*>(sm_lut + (phase * 4 + o_a) * SSD_LUT_STRIDE);
+        for (int g = lane; g < n_full; g += 32) {
+            uint2 l = lg[g];
+            uint32_t c0 = tb[l.x & 0xFFFFu], c1 = tb[l.x >> 16], c2 = tb[l.y & 0xFFFFu], c3 = tb[l.y >> 16];
+            pack4(sw + (g0 + g) * 3, pal_lane[c0 << 5], pal_lane[c1 << 5], pal_lane[c2 << 5], pal_lane[c3 << 5]);
         }
-        sw[gi * 3 + 0] = px[0] | (px[1] << 24);
-        sw[gi * 3 + 1] = (px[1] >> 8) | (px[2] << 16);
-        sw[gi * 3 + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+    __syncwarp();
+    // groups straddling agent a | a+1 (and the partial last group): lane a, per-pixel path, phase-0 LUT
+    if (lane < n) {
+        const int phase = (-lane) & 3;
+        const int n_full = (SSD_OBS_PIX - phase) >> 2;
+        int pp = phase + 4 * n_full;                      // first pixel of agent `lane` not covered above
+        if (pp < SSD_OBS_PIX) {
+            const int gc = ((SSD_OBS_PIX * lane + phase) >> 2) + n_full;
+            int a = lane;
+            uint32_t px[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (pp >= SSD_OBS_PIX) { pp -= SSD_OBS_PIX; a++; }
+                uint32_t ab = sm_abase[a < n ? a : n - 1];
+                px[k] = pal_lane[(uint32_t)tile[(ab & 0xFFFFu) + sm_lut[(ab >> 16) * SSD_LUT_STRIDE + pp]] << 5];
+                pp++;
+            }
+            pack4(sw + gc * 3, px[0], px[1], px[2], px[3]);
+        }
     }
     __syncwarp();
     if (word_ok) {
@@ -499,29 +599,23 @@ __device__ __forceinline__ void write_obs(const GridParams& p, int lane, const u
     }
 }
 
-// per-env setup of the window tables used by write_obs
-__device__ __forceinline__ void set_abase(int lane, int n, int S, uint32_t* sm_abase, int ao, int ori)
-{
-    // window origin V[0][0] = tile offset of (row - 7, col - 7); lut row = orientation
-    if (lane < n) sm_abase[lane] = (uint32_t)(ao - SSD_VIEW * S - SSD_VIEW) | ((uint32_t)(ori * SSD_LUT_STRIDE) << 16);
-}
-
 // ---------------------------------------------------------------------------------------------
-struct SharedTables {
-    const uint32_t* pal; const uint16_t* lut; const uint16_t* apple; const uint16_t* waste;
-};
 __device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, uint8_t* smem)
 {
-    uint32_t* pal = reinterpret_cast<uint32_t*>(smem);
-    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + 1024);
+    uint32_t* pal = reinterpret_cast<uint32_t*>(smem);          // [16][32]: entry c replicated once per bank
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + p.sm_lut);
     uint16_t* apple = reinterpret_cast<uint16_t*>(smem + p.sm_apple);
     uint16_t* waste = reinterpret_cast<uint16_t*>(smem + p.sm_waste);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) pal[i] = __ldg(p.pal + i);
-    for (int i = threadIdx.x; i < 4 * SSD_LUT_STRIDE; i += blockDim.x) lut[i] = __ldg(p.lut + i);
+    uint16_t* apple_rc = reinterpret_cast<uint16_t*>(smem + p.sm_apple_rc);
+    uint16_t* waste_rc = reinterpret_cast<uint16_t*>(smem + p.sm_waste_rc);
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) pal[i] = __ldg(p.pal + (i >> 5));
+    for (int i = threadIdx.x; i < 16 * SSD_LUT_STRIDE; i += blockDim.x) lut[i] = __ldg(p.lut + i);
     for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple[i] = __ldg(p.apple_pts + i);
     for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste[i] = __ldg(p.waste_pts + i);
+    for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple_rc[i] = __ldg(p.apple_rc + i);
+    for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste_rc[i] = __ldg(p.waste_rc + i);
     __syncthreads();
-    SharedTables t = { pal, lut, apple, waste };
+    SharedTables t = { pal, lut, apple, waste, apple_rc, waste_rc };
     return t;
 }
 
@@ -535,8 +629,10 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
     uint8_t* stage = tile + p.tile_r16;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
-    uint32_t* sm_abase = scratch + SCRATCH_DRAWS + SCRATCH_KEYS;
+    // the spawn scratch (draws + shuffle keys) aliases the observation staging buffer: both are
+    // dead outside their phase once the previous env's bulk store has been read out
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
+    uint32_t* sm_abase = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
     for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
     __syncwarp();
     const int n = p.n, S = p.S;
@@ -610,6 +706,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
 
         // ---- beams, spawning
         int ncleaned = fire_beams(lane, n, S, tile, g, ao, ori, cls, reward, cleaned);
+        bulk_wait_read();                            // previous env's bulk store has drained `stage` (= scratch)
+        __syncwarp();
         if (KIND == SSD_ENV_CLEANUP) {
             hcount -= ncleaned;
             hcount += cleanup_spawn(p, lane, tile, scratch, tb.apple, tb.waste, g, (uint32_t)t, hcount);
@@ -617,19 +715,18 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
             harvest_spawn(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
         }
         if (KIND == SSD_ENV_HARVEST && act_lane) total_close = count_apples_r5(tile, ao, S);
+        if (io.feat) write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount,
+                                          io.feat + (size_t)env * n * p.F);
 
         // ---- write the map back (paint stripped), then paint agents for the observation
         tile_store(p, rec, tile, lane);
         __syncwarp();
-        // paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261)
-        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)((tile[ao] & 15u) | ((uint32_t)(lane + 1) << 4));
-        bulk_wait_read();                            // previous env's bulk store has drained `stage`
-        set_abase(lane, n, S, sm_abase, ao, ori);
+        // paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
+        // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_load.
+        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)(6 + lane);
         __syncwarp();
-        write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase,
+        write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, ao, ori,
                   io.obs + (size_t)env * (size_t)io.obs_stride);
-        if (act_lane) tile[ao] &= 15u;               // un-paint: the tile buffer is reused for the next env
-        // (stale tile contents are fully overwritten by the next tile_load; only the border must stay C_OUTSIDE)
 
         // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
         const double base = (double)reward;
@@ -637,11 +734,13 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
         if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
         else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (total_close < 4 && eaten_close > 0) ? theta : 0.0;
         double r = base, total_tr = 0.0;
-        if (p.contract != SSD_CONTRACT_NONE) {
-            const double nm1 = (double)(n - 1);
+        // Redistribution in the reference's order (two_stage_train.py:72-90).  When every transfer is
+        // +-0.0 the loop is the identity on r (and adds +0.0 to the totals), so it is skipped.
+        if (p.contract != SSD_CONTRACT_NONE && __ballot_sync(FULL, act_lane && tr != 0.0) != 0u) {
+            const double share = __ddiv_rn(tr, (double)(n - 1));      // transfers[i] / (len(acts) - 1)
             for (int i = 0; i < n; i++) {
-                double ti = __shfl_sync(FULL, tr, i);
-                if (i == lane) r = __dsub_rn(r, ti); else r = __dadd_rn(r, __ddiv_rn(ti, nm1));
+                double ti = __shfl_sync(FULL, tr, i), qi = __shfl_sync(FULL, share, i);
+                r = (i == lane) ? __dsub_rn(r, ti) : __dadd_rn(r, qi);
                 total_tr = __dadd_rn(total_tr, ti);
             }
         }
@@ -655,7 +754,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] =
                 (uint32_t)eaten | ((uint32_t)(KIND == SSD_ENV_CLEANUP ? cleaned : eaten_close) << 8) | ((uint32_t)total_close << 16);
             // agent record + accumulators
-            uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
+            uint32_t trow = __umulhi((uint32_t)ao, p.s_magic);
+            uint32_t row = trow - SSD_VIEW, col = (uint32_t)ao - trow * (uint32_t)S - 8u;
             reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
             const double tm1 = (double)(t - 1);
             reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
@@ -704,8 +804,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
     uint8_t* stage = tile + p.tile_r16;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
-    uint32_t* sm_abase = scratch + SCRATCH_DRAWS + SCRATCH_KEYS;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
+    uint32_t* sm_abase = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
     for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
     __syncwarp();
     const int n = p.n, S = p.S;
@@ -752,6 +852,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         }
         // ---- reset_map + custom_reset: copy the initial map, mark occupancy, reset-time spawn (map_env.py:319-320)
         tile_load(p, p.reset_map, tile, lane);
+        bulk_wait_read();                            // `stage` doubles as the spawn scratch
         __syncwarp();
         if (act_lane) tile[ao] |= OCC_BIT;
         __syncwarp();
@@ -761,10 +862,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         tile_store(p, rec, tile, lane);
         __syncwarp();
         if (act_lane) tile[ao] &= 15u;               // MapEnv.reset never paints agents into the colour grid
-        bulk_wait_read();
-        set_abase(lane, n, S, sm_abase, ao, ori);
         __syncwarp();
-        if (obs) write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, obs + (size_t)env * (size_t)obs_stride);
+        if (obs) write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, ao, ori, obs + (size_t)env * (size_t)obs_stride);
 
         // ---- SeparateContractSubgameStage.reset (two_stage_train.py:163-168)
         double theta = 0.0;

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", gu.fixture_names())
 def test_cuda_matches_reference_golden(name):
     fx = gu.load(name)
-    gu.replay(gu.CudaBackend(fx), fx, check_features=False)
+    gu.replay(gu.CudaBackend(fx), fx, check_features=True)
 
 
 @pytest.mark.parametrize("name", ["cleanup_n2", "cleanup_n5_short_horizon", "harvest_n4"])

@@ -44,9 +44,12 @@ def test_rollout_matches_oracle(oracle_lib, case):
     check_state("reset")
     for t in range(steps):
         a = rng.randint(0, nact, size=(E, n))
-        o = orc.step(a, want_features=False)
-        obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        wf = t % 7 == 0
+        o = orc.step(a, want_features=wf)
+        obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda(), want_features=wf)
         ctx = "step %d" % t
+        if wf:
+            gu.assert_same("feature_obs", env.feature_obs.cpu().numpy(), o["feature_obs"], ctx)
         gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
         gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
         gu.assert_same("base_rew", env.base_rew.cpu().numpy(), o["base_rew"], ctx)
