@@ -155,26 +155,11 @@ static int setup_grid(ssd_handle* h)
     for (int i = 0; i < 4; i++) p.thr_harvest[i] = prob_threshold(SPAWN_PROB[i]);
     p.thr_waste = prob_threshold(0.5);
 
-    // observation window LUT: color_view (map_env.py:397-411); V[a][b] = tile[origin + a*S + b]
-    // lut[phase][o][i] = offset of pixel (phase + i): the agent whose first word-aligned pixel is `phase`
-    // reads 4 consecutive entries with one 8-byte load
-    std::vector<uint16_t> lut(16 * SSD_LUT_STRIDE, 0);
-    for (int ph = 0; ph < 4; ph++)
-        for (int o = 0; o < 4; o++)
-            for (int px = ph; px < SSD_OBS_PIX; px++) {
-                int i = px / SSD_OBSW, j = px % SSD_OBSW, vi, vj;
-                if (o == ORI_UP) { vi = i; vj = j; }
-                else if (o == ORI_LEFT) { vi = j; vj = SSD_OBSW - 1 - i; }            // np.rot90(v)
-                else if (o == ORI_DOWN) { vi = SSD_OBSW - 1 - i; vj = SSD_OBSW - 1 - j; }  // np.rot90(v, k=2)
-                else { vi = SSD_OBSW - 1 - j; vj = i; }                              // np.rot90(v, k=1, axes=(1,0))
-                lut[(ph * 4 + o) * SSD_LUT_STRIDE + (px - ph)] = (uint16_t)(vi * p.S + vj);
-            }
     std::vector<uint32_t> pal(16);
     build_palette(pal.data());
 
     int rc;
     if ((rc = upload(h, pal, &p.pal))) return rc;
-    if ((rc = upload(h, lut, &p.lut))) return rc;
     if ((rc = upload(h, apple, &p.apple_pts))) return rc;
     if ((rc = upload(h, waste, &p.waste_pts))) return rc;
     if ((rc = upload(h, spawn, &p.spawn_pts))) return rc;
@@ -184,13 +169,18 @@ static int setup_grid(ssd_handle* h)
     if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
     if ((rc = upload(h, reset_map, &p.reset_map))) return rc;
 
-    // shared memory layout
+    // shared memory layout: CTA tables, then per warp [tile | rec slot 0 | rec slot 1 | stage | misc]
+    p.obs_items = (SSD_OBSW * n + 3) / 4;
     p.tile_r16 = round_up(p.TH * p.S, 16);
-    p.stage_r16 = round_up(n * SSD_OBS_BYTES + 16 + 16, 16);
+    p.stage_r16 = round_up(p.obs_items * 180 + 16, 16);
     if (p.stage_r16 < (SCRATCH_DRAWS + SCRATCH_KEYS) * 4) p.stage_r16 = (SCRATCH_DRAWS + SCRATCH_KEYS) * 4;
-    p.warp_bytes = p.tile_r16 + p.stage_r16 + 32;
-    p.sm_lut = 16 * 32 * 4;
-    p.sm_apple = p.sm_lut + round_up(16 * SSD_LUT_STRIDE * 2, 16);
+    p.off_rec = p.tile_r16;
+    p.off_stage = p.off_rec + 2 * p.rec_stride;
+    p.off_misc = p.off_stage + p.stage_r16;
+    p.warp_bytes = p.off_misc + MISC_BYTES;
+    p.sm_thr = 64;
+    p.sm_won = p.sm_thr + round_up((p.n_waste + 1) * 4, 16);
+    p.sm_apple = p.sm_won + round_up(p.n_waste + 1, 16);
     p.sm_waste = p.sm_apple + round_up(p.n_apple * 2, 16);
     p.sm_apple_rc = p.sm_waste + round_up(p.n_waste * 2, 16);
     p.sm_waste_rc = p.sm_apple_rc + round_up(p.n_apple * 2, 16);

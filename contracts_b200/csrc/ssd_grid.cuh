@@ -3,10 +3,14 @@
 // Mapping: one WARP per environment, one LANE per agent for the move /
 // rotate / conflict logic (n <= 8, decisions are serial per env, so warp ballots + shuffles
 // give the reference's ordering without block barriers); all 32 lanes for the data-parallel
-// phases (tile load, spawn scans, observation gather).  The map lives as a padded uint8
+// phases (tile expand, spawn scans, observation gather).  The map lives as a padded uint8
 // tile in shared memory (7 cells of C_OUTSIDE border = the view radius), agents are
-// painted into the high nibble, and the rotated 15x15x3 windows are gathered into a
-// per-warp staging buffer that leaves through one TMA bulk store (cp.async.bulk) per env.
+// painted into the high nibble.  All bulk HBM traffic goes through the bulk-copy (TMA) engine:
+// each warp prefetches the NEXT env's whole record (map + header) into a double-buffered
+// shared slot with cp.async.bulk + an mbarrier while it works on the current one, writes the
+// updated record back with one bulk store, and the rotated 15x15x3 windows are gathered
+// row-wise (4 output rows = 180 B per lane, conflict-free word stores) into a per-warp staging
+// buffer that leaves through one more bulk store per env.
 //
 // Reference behaviour restated here (paths relative to the reference root):
 //   environments/map_env.py   step :216-304, update_moves :483-676, update_custom_moves :678-693,
@@ -21,6 +25,7 @@
 
 #define GRID_WARPS 8
 #define GRID_THREADS (GRID_WARPS * 32)
+#define GRID_MIN_BLOCKS 3               // 24 warps / SM: registers <= 80, ~9 KB shared per warp
 #define SCRATCH_DRAWS 256               // u32 draws per warp scratch
 #define SCRATCH_KEYS 256                // u32 shuffle keys per warp scratch
 #define MAX_POINT_ROUNDS 8              // point lists are scanned 32 per round => <= 256 points
@@ -50,8 +55,12 @@ struct GridParams {
     int wpw;                 // words per map row (Wp / 4)
     uint32_t wpw_magic;      // ceil(65536 / wpw): q = (w * magic) >> 16 for w < 65536 / wpw
     int map_bytes;           // H * Wp rounded up to 16
-    int rec_stride;          // map_bytes + RO_SIZE
-    int tile_r16, stage_r16, warp_bytes, sm_lut, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
+    int rec_stride;          // map_bytes + RO_SIZE (multiple of 16: one bulk copy moves a record)
+    // shared memory layout.  CTA tables first, then one region per warp:
+    //   [tile | rec slot 0 | rec slot 1 | stage (obs staging, aliased by the spawn scratch) | misc]
+    int tile_r16, stage_r16, warp_bytes, off_rec, off_stage, off_misc;
+    int sm_thr, sm_won, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
+    int obs_items;           // ceil(15 n / 4): 4-row (180 B) work items of the observation gather
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;
@@ -59,7 +68,6 @@ struct GridParams {
     uint32_t thr_harvest[4]; // SPAWN_PROB thresholds (harvest_new.py:34)
     uint32_t thr_waste;      // wasteSpawnProbability = 0.5
     const uint32_t* pal;     // [16] packed RGB per tile byte value (cell codes 0..5, agents 6..13, outside 15)
-    const uint16_t* lut;     // [4 phases][4 orientations][SSD_LUT_STRIDE] window offsets, phase-shifted copies
     uint32_t s_magic;        // ceil(2^32 / S): row = umulhi(offset, s_magic)
     const uint16_t* apple_pts;
     const uint16_t* waste_pts;
@@ -72,6 +80,11 @@ struct GridParams {
     uint8_t* state;
 };
 
+// per-warp misc area
+#define MISC_VDESC 0        // int4[8]: per-agent view descriptor {offset of out[0][0], pixel step, row step, 0}
+#define MISC_MBAR 128       // u64[2]: record-prefetch mbarriers
+#define MISC_BYTES 144
+
 struct StepIO {
     const uint8_t* actions;
     uint8_t* obs; long long obs_stride;
@@ -83,8 +96,8 @@ struct EnvRng { uint32_t seed, env_id, episode, t; };
 
 // per-CTA copies of the static tables in shared memory
 struct SharedTables {
-    const uint32_t* pal; const uint16_t* lut; const uint16_t* apple; const uint16_t* waste;
-    const uint16_t* apple_rc; const uint16_t* waste_rc;
+    const uint32_t* pal; const uint32_t* thr_apple; const uint8_t* waste_on;
+    const uint16_t* apple; const uint16_t* waste; const uint16_t* apple_rc; const uint16_t* waste_rc;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
@@ -135,6 +148,69 @@ __device__ __forceinline__ void tile_store(const GridParams& p, uint8_t* rec, co
         dst[v] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
 }
+
+// shared-memory record slot <-> padded tile (step kernel; the record arrives / leaves by bulk copy)
+__device__ __forceinline__ void tile_expand(const GridParams& p, const uint8_t* recbuf, uint8_t* tile, int lane)
+{
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(recbuf);
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+    const int S4 = p.S >> 2, nwords = p.H * p.wpw;
+    for (int w = lane; w < nwords; w += 32) {
+        int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
+        tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] = rw[w];
+    }
+}
+__device__ __forceinline__ void tile_compress(const GridParams& p, uint8_t* recbuf, const uint8_t* tile, int lane)
+{
+    uint32_t* rw = reinterpret_cast<uint32_t*>(recbuf);
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+    const int S4 = p.S >> 2, nwords = p.H * p.wpw;
+    for (int w = lane; w < nwords; w += 32) {
+        int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
+        rw[w] = tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] & 0x0F0F0F0Fu;   // strip agent paint / occupancy
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk-copy (TMA) + mbarrier primitives.  Bulk async-groups are per thread: lane 0 issues and waits.
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion signalled on `bar` (expect_tx armed by the same lane)
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, void* bar)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// shared -> global, one bulk group per call
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // update_moves (map_env.py:483-676).  Lane i < n holds agent i: `ao` tile offset of its cell.
@@ -237,8 +313,10 @@ __device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile,
     unsigned rem = __ballot_sync(FULL, act_lane && cls != 0);
     if (!rem) return 0;
     int total_cleaned = 0;
-    uint32_t bkey = act_lane ? draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_BEAM_ORDER, 0, (uint32_t)lane)
-                             : 0xFFFFFFFFu;
+    // shuffled firing order (map_env.py:684-685); irrelevant (and not drawn) when a single agent fires
+    uint32_t bkey = (uint32_t)lane;
+    if (rem & (rem - 1))
+        bkey = act_lane ? draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_BEAM_ORDER, 0, (uint32_t)lane) : 0xFFFFFFFFu;
     const bool ray_lane = lane < 15;
     const int b = lane / 5, k = lane - 5 * b;
     while (rem) {
@@ -292,12 +370,16 @@ __device__ __forceinline__ void fill_draws(uint32_t* scratch, int lane, const En
 // ---------------------------------------------------------------------------------------------
 // cleanup spawn (cleanup_new.py:322-349).  Occupancy bits must be set.  `t` = 0 at reset.
 // Returns the number of waste cells spawned (0 or 1).
-__device__ __forceinline__ int cleanup_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
-                                             const uint16_t* sm_apple, const uint16_t* sm_waste,
-                                             const EnvRng& g, uint32_t t, int hcount)
+__device__ __forceinline__ bool cleanup_spawn_active(const SharedTables& tb, int hcount)
 {
-    const uint32_t thrA = __ldg(p.thr_apple + hcount);
-    const bool waste_on = __ldg(p.waste_on + hcount) != 0;
+    return tb.thr_apple[hcount] != 0 || tb.waste_on[hcount] != 0;
+}
+__device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile,
+                                             uint32_t* scratch, const EnvRng& g, uint32_t t, int hcount)
+{
+    const uint16_t* sm_apple = tb.apple; const uint16_t* sm_waste = tb.waste;
+    const uint32_t thrA = tb.thr_apple[hcount];
+    const bool waste_on = tb.waste_on[hcount] != 0;
     if (thrA == 0 && !waste_on) return 0;
     uint32_t* draws = scratch;
     uint32_t* keys = scratch + SCRATCH_DRAWS;
@@ -508,68 +590,57 @@ __device__ __forceinline__ void write_features(const GridParams& p, const Shared
 }
 
 // ---------------------------------------------------------------------------------------------
-// observations: gather the rotated windows of all agents into `stage` (word-aligned to the
-// global destination modulo 16) and ship them with one bulk async copy.
-__device__ __forceinline__ void bulk_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-// Stream layout: agent a's 225 pixels start at byte 675*a of the env's block.  Work is split in
-// word-aligned groups of 4 pixels (12 B = 3 words).  Because 225 = 1 (mod 4), agent a's first
-// aligned pixel is phase = (-a) & 3; its full groups read a phase-shifted copy of the window LUT
-// with one 8-byte load, and the <= n groups that straddle two agents are done in one extra pass.
+// observations (color_view, map_env.py:397-411): out[i][j] of agent a is a strided walk over the
+// painted tile: V[i][j] (UP), V[j][14-i] (LEFT), V[14-i][14-j] (DOWN), V[14-j][i] (RIGHT), with
+// V[a][b] = tile[origin + a*S + b].  So output row i starts at start0 + i*rs and advances by `step`
+// per pixel; {start0, step, rs} per agent live in vdesc.  The env's observation stream is 15 n rows
+// of 45 B; a work item is 4 consecutive rows = 60 pixels = 45 words (word aligned whatever the
+// agents), one item per lane, staged with conflict-free word stores (lane stride 45 words) and
+// shipped with one bulk async store (head / tail up to the 16-B boundaries by plain stores).
 __device__ __forceinline__ void pack4(uint32_t* dst, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3)
 {
-    dst[0] = p0 | (p1 << 24);
-    dst[1] = (p1 >> 8) | (p2 << 16);
-    dst[2] = (p2 >> 16) | (p3 << 8);
+    dst[0] = __byte_perm(p0, p1, 0x4210);
+    dst[1] = __byte_perm(p1, p2, 0x5421);
+    dst[2] = __byte_perm(p2, p3, 0x6542);
 }
-__device__ __forceinline__ void write_obs(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
-                                          const uint32_t* sm_pal, const uint16_t* sm_lut,
-                                          uint32_t* sm_abase /* [8] scratch: window origin | orientation << 16 */,
-                                          int ao, int ori, uint8_t* gdst)
+// PENDING: bulk groups of this lane-0 that may stay in flight while `stage` is rewritten
+template <int PENDING>
+__device__ __forceinline__ void gather_obs(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
+                                           const uint32_t* sm_pal, int4* vdesc, int ao, int ori, uint8_t* gdst)
 {
     const int n = p.n, S = p.S;
     const int L = n * SSD_OBS_BYTES;
     const uint32_t gaddr = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
     const bool word_ok = (gaddr & 3u) == 0;
-    const int shift = word_ok ? (int)gaddr : 0;
+    const int shift = word_ok ? (int)gaddr : 0;          // staged stream is congruent to gdst modulo 16
     uint32_t* sw = reinterpret_cast<uint32_t*>(stage + shift);
-    const uint32_t* pal_lane = sm_pal + lane;            // bank == lane: conflict-free palette reads
-    const int origin = ao - SSD_VIEW * S - SSD_VIEW;     // V[0][0] of this lane's agent
-    if (lane < n) sm_abase[lane] = (uint32_t)origin | ((uint32_t)ori << 16);
-    for (int a = 0; a < n; a++) {
-        const uint8_t* tb = tile + __shfl_sync(FULL, origin, a);
-        const int o_a = __shfl_sync(FULL, ori, a);
-        const int phase = (-a) & 3;
-        const int n_full = (SSD_OBS_PIX - phase) >> 2;
-        const int g0 = (SSD_OBS_PIX * a + phase) >> 2;   // flat index of the agent's first full group
-        const uint2* lg = reinterpret_cast<const uint2*>(sm_lut + (phase * 4 + o_a) * SSD_LUT_STRIDE);
-        for (int g = lane; g < n_full; g += 32) {
-            uint2 l = lg[g];
-            uint32_t c0 = tb[l.x & 0xFFFFu], c1 = tb[l.x >> 16], c2 = tb[l.y & 0xFFFFu], c3 = tb[l.y >> 16];
-            pack4(sw + (g0 + g) * 3, pal_lane[c0 << 5], pal_lane[c1 << 5], pal_lane[c2 << 5], pal_lane[c3 << 5]);
-        }
-    }
-    __syncwarp();
-    // groups straddling agent a | a+1 (and the partial last group): lane a, per-pixel path, phase-0 LUT
     if (lane < n) {
-        const int phase = (-lane) & 3;
-        const int n_full = (SSD_OBS_PIX - phase) >> 2;
-        int pp = phase + 4 * n_full;                      // first pixel of agent `lane` not covered above
-        if (pp < SSD_OBS_PIX) {
-            const int gc = ((SSD_OBS_PIX * lane + phase) >> 2) + n_full;
-            int a = lane;
-            uint32_t px[4];
+        const int origin = ao - SSD_VIEW * S - SSD_VIEW;     // V[0][0] of this lane's agent
+        const int last = SSD_OBSW - 1;
+        int start0 = origin, step = 1, rs = S;               // UP
+        if (ori == ORI_RIGHT) { start0 = origin + last * S; step = -S; rs = 1; }
+        else if (ori == ORI_DOWN) { start0 = origin + last * S + last; step = -1; rs = -S; }
+        else if (ori == ORI_LEFT) { start0 = origin + last; step = S; rs = -1; }
+        vdesc[lane] = make_int4(start0, step, rs, 0);
+    }
+    if (lane == 0) bulk_wait_read<PENDING>();                // the previous env's store has drained `stage`
+    __syncwarp();
+    if (lane < p.obs_items) {
+        uint32_t col[60];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (pp >= SSD_OBS_PIX) { pp -= SSD_OBS_PIX; a++; }
-                uint32_t ab = sm_abase[a < n ? a : n - 1];
-                px[k] = pal_lane[(uint32_t)tile[(ab & 0xFFFFu) + sm_lut[(ab >> 16) * SSD_LUT_STRIDE + pp]] << 5];
-                pp++;
-            }
-            pack4(sw + gc * 3, px[0], px[1], px[2], px[3]);
+        for (int q = 0; q < 4; q++) {
+            const int r = 4 * lane + q;
+            int a = (int)(((uint32_t)r * 0x8889u) >> 19);    // r / 15
+            int i = r - 15 * a;
+            if (a >= n) { a = n - 1; i = SSD_OBSW - 1; }     // rows past the stream end: harmless in-bounds reads
+            const int4 d = vdesc[a];
+            const uint8_t* src = tile + (d.x + i * d.z);
+#pragma unroll
+            for (int j = 0; j < SSD_OBSW; j++) col[15 * q + j] = sm_pal[src[j * d.y]];
         }
+        uint32_t* dst = sw + 45 * lane;
+#pragma unroll
+        for (int g4 = 0; g4 < 15; g4++) pack4(dst + 3 * g4, col[4 * g4], col[4 * g4 + 1], col[4 * g4 + 2], col[4 * g4 + 3]);
     }
     __syncwarp();
     if (word_ok) {
@@ -585,14 +656,9 @@ __device__ __forceinline__ void write_obs(const GridParams& p, int lane, const u
             if (lane < L - tb0) gdst[tb0 + lane] = (stage + shift)[tb0 + lane];
         }
         if (mid > 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage + shift + a0);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(gdst + a0), "r"(saddr), "r"(mid) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            if (lane == 0) bulk_store(gdst + a0, stage + shift + a0, (uint32_t)mid);
         }
     } else {
         for (int i = lane; i < L; i += 32) gdst[i] = stage[i];
@@ -602,46 +668,72 @@ __device__ __forceinline__ void write_obs(const GridParams& p, int lane, const u
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, uint8_t* smem)
 {
-    uint32_t* pal = reinterpret_cast<uint32_t*>(smem);          // [16][32]: entry c replicated once per bank
-    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + p.sm_lut);
+    uint32_t* pal = reinterpret_cast<uint32_t*>(smem);          // [16]: 16 distinct banks, no replication needed
+    uint32_t* thr = reinterpret_cast<uint32_t*>(smem + p.sm_thr);
+    uint8_t* won = smem + p.sm_won;
     uint16_t* apple = reinterpret_cast<uint16_t*>(smem + p.sm_apple);
     uint16_t* waste = reinterpret_cast<uint16_t*>(smem + p.sm_waste);
     uint16_t* apple_rc = reinterpret_cast<uint16_t*>(smem + p.sm_apple_rc);
     uint16_t* waste_rc = reinterpret_cast<uint16_t*>(smem + p.sm_waste_rc);
-    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) pal[i] = __ldg(p.pal + (i >> 5));
-    for (int i = threadIdx.x; i < 16 * SSD_LUT_STRIDE; i += blockDim.x) lut[i] = __ldg(p.lut + i);
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) pal[i] = __ldg(p.pal + i);
+    for (int i = threadIdx.x; i <= p.n_waste; i += blockDim.x) { thr[i] = __ldg(p.thr_apple + i); won[i] = __ldg(p.waste_on + i); }
     for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple[i] = __ldg(p.apple_pts + i);
     for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste[i] = __ldg(p.waste_pts + i);
     for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple_rc[i] = __ldg(p.apple_rc + i);
     for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste_rc[i] = __ldg(p.waste_rc + i);
-    __syncthreads();
-    SharedTables t = { pal, lut, apple, waste, apple_rc, waste_rc };
+    SharedTables t = { pal, thr, won, apple, waste, apple_rc, waste_rc };
     return t;
 }
 
 // =============================================================================================
 // STEP
 template <int KIND>
-__global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParams p, const StepIO io)
+__global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kernel(const GridParams p, const StepIO io)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const SharedTables tb = load_shared_tables(p, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
-    uint8_t* stage = tile + p.tile_r16;
+    uint8_t* recs = tile + p.off_rec;                 // two record slots (double buffer)
+    uint8_t* stage = tile + p.off_stage;
     // the spawn scratch (draws + shuffle keys) aliases the observation staging buffer: both are
     // dead outside their phase once the previous env's bulk store has been read out
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
-    uint32_t* sm_abase = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
+    int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + p.off_misc + MISC_MBAR);
     for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
-    __syncwarp();
+    if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();                                  // tables + barriers visible
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
+    const int env_stride = gridDim.x * GRID_WARPS;
+    const uint32_t rec_bytes = (uint32_t)p.rec_stride;
 
-    for (int env = blockIdx.x * GRID_WARPS + warp; env < p.E; env += gridDim.x * GRID_WARPS) {
-        uint8_t* rec = p.state + (size_t)env * p.rec_stride;
+    int env = blockIdx.x * GRID_WARPS + warp;
+    int act_next = 4;
+    if (env < p.E) {
+        if (lane == 0) bulk_load(recs, p.state + (size_t)env * p.rec_stride, rec_bytes, mbar);
+        if (act_lane) act_next = io.actions[(size_t)env * n + lane];
+    }
+    for (uint32_t it = 0; env < p.E; env += env_stride, it++) {
+        const uint32_t slot = it & 1u;
+        uint8_t* rec = recs + slot * p.rec_stride;    // this env's record, in shared memory
         uint8_t* hdr = rec + p.map_bytes;
-        tile_load(p, rec, tile, lane);
+        // ---- prefetch the next env's record into the other slot (its previous contents left
+        //      through the bulk store of the previous iteration: wait until that has read it)
+        const int env_nx = env + env_stride;
+        int act = act_next;
+        if (env_nx < p.E) {
+            if (lane == 0) {
+                bulk_wait_read<1>();                  // all but the newest group (an observation store)
+                bulk_load(recs + (slot ^ 1u) * p.rec_stride, p.state + (size_t)env_nx * p.rec_stride, rec_bytes,
+                          mbar + (slot ^ 1u));
+            }
+            if (act_lane) act_next = io.actions[(size_t)env_nx * n + lane];
+        }
+        mbar_wait(mbar + slot, (it >> 1) & 1u);
+        tile_expand(p, rec, tile, lane);
         // ---- per-env scalars + agent registers
         int t = *reinterpret_cast<const int*>(hdr + RO_T) + 1;                 // map_env.py:230
         const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
@@ -649,13 +741,12 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
         uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
         int hcount = *reinterpret_cast<const int*>(hdr + RO_HCOUNT);
         EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, (uint32_t)t };
-        int ao = 0, ori = 0, act = 4;
+        int ao = 0, ori = 0;
         if (act_lane) {
             uint32_t a = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[lane];
             ao = ((int)(a & 255u) + SSD_VIEW) * S + 8 + (int)((a >> 8) & 255u);
             ori = (int)((a >> 16) & 3u);
-            act = io.actions[(size_t)env * n + lane];
-        }
+        } else act = 4;
         __syncwarp();
 
         // ---- action decode (Agent.py:8-16,161-162,198-199) + rotations (map_env.py:514-516)
@@ -706,27 +797,24 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
 
         // ---- beams, spawning
         int ncleaned = fire_beams(lane, n, S, tile, g, ao, ori, cls, reward, cleaned);
-        bulk_wait_read();                            // previous env's bulk store has drained `stage` (= scratch)
-        __syncwarp();
         if (KIND == SSD_ENV_CLEANUP) {
             hcount -= ncleaned;
-            hcount += cleanup_spawn(p, lane, tile, scratch, tb.apple, tb.waste, g, (uint32_t)t, hcount);
+            if (cleanup_spawn_active(tb, hcount)) {
+                if (lane == 0) bulk_wait_read<0>();  // previous env's observation store has drained `stage` (= scratch)
+                __syncwarp();
+                hcount += cleanup_spawn(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
+            }
         } else {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
             harvest_spawn(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
         }
         if (KIND == SSD_ENV_HARVEST && act_lane) total_close = count_apples_r5(tile, ao, S);
         if (io.feat) write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount,
                                           io.feat + (size_t)env * n * p.F);
 
-        // ---- write the map back (paint stripped), then paint agents for the observation
-        tile_store(p, rec, tile, lane);
-        __syncwarp();
-        // paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
-        // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_load.
-        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)(6 + lane);
-        __syncwarp();
-        write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, ao, ori,
-                  io.obs + (size_t)env * (size_t)io.obs_stride);
+        // ---- map back into the record slot (paint stripped)
+        tile_compress(p, rec, tile, lane);
 
         // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
         const double base = (double)reward;
@@ -744,7 +832,6 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
                 total_tr = __dadd_rn(total_tr, ti);
             }
         }
-        // raw reward total (ints) for metrics['raw_env_rewards'] is derived from sum_raw on the host
         const bool done = t == p.horizon;
         if (act_lane) {
             size_t o = (size_t)env * n + lane;
@@ -753,20 +840,22 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
             if (io.transfers) io.transfers[o] = tr;
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] =
                 (uint32_t)eaten | ((uint32_t)(KIND == SSD_ENV_CLEANUP ? cleaned : eaten_close) << 8) | ((uint32_t)total_close << 16);
-            // agent record + accumulators
+            // agent record + accumulators (in the shared record slot)
             uint32_t trow = __umulhi((uint32_t)ao, p.s_magic);
             uint32_t row = trow - SSD_VIEW, col = (uint32_t)ao - trow * (uint32_t)S - 8u;
             reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
-            const double tm1 = (double)(t - 1);
-            reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
-            reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[lane] += (long long)(t - 1) * reward;
+            if (reward != 0) {
+                reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
+                reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[lane] += (long long)(t - 1) * reward;
+            }
             if (p.contract != SSD_CONTRACT_NONE) {
+                const double tm1 = (double)(t - 1);
                 double* st = reinterpret_cast<double*>(hdr + RO_SUM_TR) + lane;
                 double* tt = reinterpret_cast<double*>(hdr + RO_TSUM_TR) + lane;
                 *st = __dadd_rn(*st, r);
                 *tt = __dadd_rn(*tt, __dmul_rn(tm1, r));
             }
-            if (KIND == SSD_ENV_CLEANUP) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)cleaned;
+            if (KIND == SSD_ENV_CLEANUP) { if (cleaned) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)cleaned; }
             else {
                 reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)eaten;
                 reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[lane] += (uint32_t)eaten_close;
@@ -788,9 +877,19 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_step_kernel(const GridParam
             }
             if (io.done) io.done[env] = done ? 1 : 0;
         }
+        // ---- the record leaves with one bulk store
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(p.state + (size_t)env * p.rec_stride, rec, rec_bytes);
+
+        // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
+        // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_expand.
+        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)(6 + lane);
+        // gather_obs: waits (lane 0) until at most the record store above is still in flight, syncs the warp
+        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, io.obs + (size_t)env * (size_t)io.obs_stride);
         __syncwarp();
     }
-    bulk_wait_read();      // smem must outlive the async bulk reads
+    if (lane == 0) bulk_wait_read<0>();      // smem must outlive the async bulk reads
 }
 
 // =============================================================================================
@@ -803,11 +902,11 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     const SharedTables tb = load_shared_tables(p, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
-    uint8_t* stage = tile + p.tile_r16;
+    uint8_t* stage = tile + p.off_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
-    uint32_t* sm_abase = reinterpret_cast<uint32_t*>(stage + p.stage_r16);
+    int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
     for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
-    __syncwarp();
+    __syncthreads();
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
 
@@ -852,18 +951,18 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         }
         // ---- reset_map + custom_reset: copy the initial map, mark occupancy, reset-time spawn (map_env.py:319-320)
         tile_load(p, p.reset_map, tile, lane);
-        bulk_wait_read();                            // `stage` doubles as the spawn scratch
+        if (lane == 0) bulk_wait_read<0>();          // `stage` doubles as the spawn scratch
         __syncwarp();
         if (act_lane) tile[ao] |= OCC_BIT;
         __syncwarp();
         int hcount = p.n_waste_start;
-        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn(p, lane, tile, scratch, tb.apple, tb.waste, g, 0u, hcount);
+        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn(p, tb, lane, tile, scratch, g, 0u, hcount);
         else harvest_spawn(p, lane, tile, scratch, tb.apple, g, 0u);
         tile_store(p, rec, tile, lane);
         __syncwarp();
         if (act_lane) tile[ao] &= 15u;               // MapEnv.reset never paints agents into the colour grid
         __syncwarp();
-        if (obs) write_obs(p, lane, tile, stage, tb.pal, tb.lut, sm_abase, ao, ori, obs + (size_t)env * (size_t)obs_stride);
+        if (obs) gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, obs + (size_t)env * (size_t)obs_stride);
 
         // ---- SeparateContractSubgameStage.reset (two_stage_train.py:163-168)
         double theta = 0.0;
@@ -888,5 +987,5 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         }
         __syncwarp();
     }
-    bulk_wait_read();
+    if (lane == 0) bulk_wait_read<0>();
 }
