@@ -23,10 +23,23 @@ struct ssd_handle {
     std::string ascii;
     GridParams gp;
     int grid_blocks;
+    bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
     char err[512];
     std::vector<void*> dev_allocs;
 };
+
+typedef void (*step_kernel_t)(const GridParams, const StepIO);
+static step_kernel_t step_kernel_fn(int kind, bool rounds4, bool feat)
+{
+    if (kind == SSD_ENV_CLEANUP) {
+        if (rounds4) return feat ? grid_step_kernel<SSD_ENV_CLEANUP, 4, true> : grid_step_kernel<SSD_ENV_CLEANUP, 4, false>;
+        return feat ? grid_step_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, true> : grid_step_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, false>;
+    }
+    if (rounds4) return feat ? grid_step_kernel<SSD_ENV_HARVEST, 4, true> : grid_step_kernel<SSD_ENV_HARVEST, 4, false>;
+    return feat ? grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, true> : grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false>;
+}
+static const void* step_kernel_ptr(int kind, bool rounds4, bool feat) { return (const void*)step_kernel_fn(kind, rounds4, feat); }
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
 {
@@ -195,13 +208,16 @@ static int setup_grid(ssd_handle* h)
     p.state = (uint8_t*)st;
 
     // persistent grid: enough CTAs to fill every SM at the achievable occupancy
-    const void* ks[4] = { (const void*)grid_step_kernel<SSD_ENV_CLEANUP>, (const void*)grid_step_kernel<SSD_ENV_HARVEST>,
-                          (const void*)grid_reset_kernel<SSD_ENV_CLEANUP>, (const void*)grid_reset_kernel<SSD_ENV_HARVEST> };
-    for (int i = 0; i < 4; i++)
-        CUDA_TRY(h, cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    h->rounds4 = p.n_apple <= 128 && p.n_waste <= 128;
+    const void* reset_k = c.env_kind == SSD_ENV_CLEANUP ? (const void*)grid_reset_kernel<SSD_ENV_CLEANUP>
+                                                        : (const void*)grid_reset_kernel<SSD_ENV_HARVEST>;
+    CUDA_TRY(h, cudaFuncSetAttribute(reset_k, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    for (int feat = 0; feat < 2; feat++)
+        CUDA_TRY(h, cudaFuncSetAttribute(step_kernel_ptr(c.env_kind, h->rounds4, feat != 0),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     int sms = 0, per_sm = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks[c.env_kind == SSD_ENV_CLEANUP ? 0 : 1],
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_ptr(c.env_kind, h->rounds4, false),
                                                               GRID_THREADS, p.smem_bytes));
     if (per_sm < 1) return fail(h, SSD_EUNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", p.smem_bytes);
     int want = (p.E + GRID_WARPS - 1) / GRID_WARPS;
@@ -220,7 +236,7 @@ __global__ void get_state_kernel(GridParams p, uint8_t* map, int32_t* pos, int32
     const char chars[16] = { ' ', '@', 'A', 'H', 'R', 'S', '?', '?', '?', '?', '?', '?', '?', '?', '?', '?' };
     if (map)
         for (int r = 0; r < p.H; r++)
-            for (int c = 0; c < p.W; c++) map[((size_t)env * p.H + r) * p.W + c] = (uint8_t)chars[rec[r * p.Wp + c] & 15];
+            for (int c = 0; c < p.W; c++) map[((size_t)env * p.H + r) * p.W + c] = (uint8_t)chars[(rec[r * p.Wp + c] >> 2) & 15];
     for (int a = 0; a < p.n; a++) {
         uint32_t v = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[a];
         if (pos) { pos[((size_t)env * p.n + a) * 2] = (int)(v & 255u); pos[((size_t)env * p.n + a) * 2 + 1] = (int)((v >> 8) & 255u); }
@@ -434,10 +450,7 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
     k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
     if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.kind == SSD_ENV_CLEANUP)
-        grid_step_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
-    else
-        grid_step_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+    step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
     return check_launch(h, "step");
 }
 

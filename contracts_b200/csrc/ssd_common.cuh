@@ -12,7 +12,6 @@
 #define SSD_OBSW 15
 #define SSD_OBS_PIX (SSD_OBSW * SSD_OBSW)          // 225 pixels / agent
 #define SSD_OBS_BYTES (SSD_OBS_PIX * 3)            // 675 B / agent
-#define SSD_LUT_STRIDE 228                         // 225 padded to a multiple of 4 entries
 
 // env_kind / contract_kind constants come from the public header
 #include "../../include/ssd_b200.h"
@@ -20,8 +19,15 @@
 // orientation ints: Agent.py:18-23
 enum { ORI_UP = 0, ORI_RIGHT = 1, ORI_DOWN = 2, ORI_LEFT = 3 };
 
-// cell codes stored in the low nibble of a tile byte (high nibble = agent paint / occupancy)
-enum { C_EMPTY = 0, C_WALL = 1, C_APPLE = 2, C_WASTE = 3, C_RIVER = 4, C_STREAM = 5, C_OUTSIDE = 15 };
+// A tile byte is (palette index << 2) | occupancy bit 7: the byte is directly the byte offset of the
+// cell's colour in the 16-entry palette (no shift in the observation gather).  Palette indices:
+// cell codes 0..5, 6 + i = agent i painted for the observation, 15 = outside the map.
+enum { C_EMPTY = 0 << 2, C_WALL = 1 << 2, C_APPLE = 2 << 2, C_WASTE = 3 << 2, C_RIVER = 4 << 2, C_STREAM = 5 << 2,
+       C_OUTSIDE = 15 << 2 };
+#define CODE_MASK 0x7Cu
+#define CODE_MASK4 0x7C7C7C7Cu
+#define TILE_FILL4 0x3C3C3C3Cu        // C_OUTSIDE in every byte
+#define PAINT_CODE(i) ((6 + (i)) << 2)
 #define OCC_BIT 0x80u
 
 enum { SITE_MOVE_ORDER = 1, SITE_BEAM_ORDER = 2, SITE_SPAWN_DRAWS = 3, SITE_WASTE_ORDER = 4, SITE_SPAWN_ROT = 5,

@@ -137,11 +137,11 @@ __device__ __forceinline__ void tile_store(const GridParams& p, uint8_t* rec, co
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int w = v * 4 + j;
-            uint32_t x = 0x0F0F0F0Fu;
+            uint32_t x = TILE_FILL4;
             if (w < nwords) {
                 int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
                 int cw = w - row * p.wpw;
-                x = tw[(row + SSD_VIEW) * S4 + 2 + cw] & 0x0F0F0F0Fu;   // strip agent paint / occupancy
+                x = tw[(row + SSD_VIEW) * S4 + 2 + cw] & CODE_MASK4;   // strip agent paint / occupancy
             }
             w4[j] = x;
         }
@@ -167,7 +167,7 @@ __device__ __forceinline__ void tile_compress(const GridParams& p, uint8_t* recb
     const int S4 = p.S >> 2, nwords = p.H * p.wpw;
     for (int w = lane; w < nwords; w += 32) {
         int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-        rw[w] = tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] & 0x0F0F0F0Fu;   // strip agent paint / occupancy
+        rw[w] = tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] & CODE_MASK4;   // strip agent paint / occupancy
     }
 }
 
@@ -212,36 +212,34 @@ __device__ __forceinline__ void bulk_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One out-of-line copy of the 10 Philox rounds for the step kernel (the inlined form is ~80
+// instructions per call site; the hot loop has to fit the instruction cache).
+__device__ __noinline__ uint4 draw_block_ool(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t,
+                                             uint32_t site_call, uint32_t block)
+{
+    Philox4 q = philox4x32_10(block, site_call, t, episode, seed, env_id);
+    return make_uint4(q.x, q.y, q.z, q.w);
+}
+__device__ __forceinline__ uint32_t draw_u32_ool(const EnvRng& g, uint32_t t, uint32_t site, uint32_t idx)
+{
+    uint4 q = draw_block_ool(g.seed, g.env_id, g.episode, t, site, idx >> 2);
+    const uint32_t w = idx & 3u;
+    return w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+}
+
 // ---------------------------------------------------------------------------------------------
-// update_moves (map_env.py:483-676).  Lane i < n holds agent i: `ao` tile offset of its cell.
-// Returns error bits.  On the fast path (no two movers share a target and no real move targets
-// an occupied cell) every mover simply moves, which is what the reference's first while-pass does.
-__device__ __forceinline__ uint32_t resolve_moves(int lane, int n, uint8_t* tile, const EnvRng& g,
-                                                  int& ao, bool has_move, int tgt)
+// The literal ordering of the reference (rare: some movers share a target or a real move targets an
+// occupied cell).  Out of line: it is cold and would otherwise bloat the hot loop's instruction
+// footprint.  Returns err << 16 | new tile offset.
+__device__ __noinline__ uint32_t resolve_moves_slow(int lane, int n, uint32_t seed, uint32_t env_id, uint32_t episode,
+                                                    uint32_t t, int ao, bool has_move, int tgt, unsigned movers,
+                                                    bool contested)
 {
     const bool act_lane = lane < n;
-    const unsigned movers = __ballot_sync(FULL, has_move);
-    if (movers == 0) return 0;
-    uint32_t mval = has_move ? (uint32_t)tgt : (0xFFFF0000u | (uint32_t)lane);
-    unsigned same = __match_any_sync(FULL, mval);
-    bool contested = has_move && (__popc(same) > 1);
-    if (act_lane) tile[ao] |= OCC_BIT;             // co-located lanes write the same value
-    __syncwarp();
-    bool real = has_move && tgt != ao;
-    bool occupied = real && (tile[tgt] & OCC_BIT);
-    __syncwarp();
-    if (act_lane) tile[ao] &= 0x7F;
-    __syncwarp();
-    if (__ballot_sync(FULL, contested || occupied) == 0) {
-        if (real) ao = tgt;
-        return 0;
-    }
-
-    // ---- slow path: literal ordering of the reference ------------------------------------------
     uint32_t err = 0;
     // shuffled priority (map_env.py:545-547): key of list position m = rank among movers
     uint32_t key = 0xFFFFFFFFu;
-    if (has_move) key = draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_MOVE_ORDER, 0,
+    if (has_move) key = draw_u32(seed, env_id, episode, t, SITE_MOVE_ORDER, 0,
                                  (uint32_t)__popc(movers & lanemask_lt(lane)));
     int cur_mv = tgt;                               // agent_moves[agent]
     // contested cells in lexicographic (row, col) order == increasing tile offset (np.unique, :548)
@@ -300,7 +298,35 @@ __device__ __forceinline__ uint32_t resolve_moves(int lane, int n, uint8_t* tile
             break;
         }
     }
-    return err;
+    return (err << 16) | (uint32_t)ao;
+}
+
+// update_moves (map_env.py:483-676).  Lane i < n holds agent i: `ao` tile offset of its cell.
+// Returns error bits.  On the fast path (no two movers share a target and no real move targets an
+// occupied cell) every mover simply moves, which is what the reference's first while-pass does.
+__device__ __forceinline__ uint32_t resolve_moves(int lane, int n, uint8_t* tile, const EnvRng& g,
+                                                  int& ao, bool has_move, int tgt)
+{
+    const bool act_lane = lane < n;
+    const unsigned movers = __ballot_sync(FULL, has_move);
+    if (movers == 0) return 0;
+    uint32_t mval = has_move ? (uint32_t)tgt : (0xFFFF0000u | (uint32_t)lane);
+    unsigned same = __match_any_sync(FULL, mval);
+    bool contested = has_move && (__popc(same) > 1);
+    if (act_lane) tile[ao] |= OCC_BIT;             // co-located lanes write the same value
+    __syncwarp();
+    bool real = has_move && tgt != ao;
+    bool occupied = real && (tile[tgt] & OCC_BIT);
+    __syncwarp();
+    if (act_lane) tile[ao] &= 0x7F;
+    __syncwarp();
+    if (__ballot_sync(FULL, contested || occupied) == 0) {
+        if (real) ao = tgt;
+        return 0;
+    }
+    const uint32_t r = resolve_moves_slow(lane, n, g.seed, g.env_id, g.episode, g.t, ao, has_move, tgt, movers, contested);
+    ao = (int)(r & 0xFFFFu);
+    return r >> 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,7 +342,7 @@ __device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile,
     // shuffled firing order (map_env.py:684-685); irrelevant (and not drawn) when a single agent fires
     uint32_t bkey = (uint32_t)lane;
     if (rem & (rem - 1))
-        bkey = act_lane ? draw_u32(g.seed, g.env_id, g.episode, g.t, SITE_BEAM_ORDER, 0, (uint32_t)lane) : 0xFFFFFFFFu;
+        bkey = act_lane ? draw_u32_ool(g, g.t, SITE_BEAM_ORDER, (uint32_t)lane) : 0xFFFFFFFFu;
     const bool ray_lane = lane < 15;
     const int b = lane / 5, k = lane - 5 * b;
     while (rem) {
@@ -330,7 +356,7 @@ __device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile,
         const int d = dir_delta(sori, S), rt = dir_delta((sori + 1) & 3, S);
         int cell = so + (b == 1 ? rt - d : (b == 2 ? -rt - d : 0)) + (k + 1) * d;
         uint32_t code = ray_lane ? tile[cell] : (uint32_t)C_WALL;
-        uint32_t c = code & 15u;
+        uint32_t c = code & CODE_MASK;
         bool pass = c != C_WALL && c != C_OUTSIDE;
         bool agent_here = (code & OCC_BIT) != 0;
         bool isH = c == C_WASTE;
@@ -341,7 +367,7 @@ __device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile,
         bool upd = covered && sclean && isH;
         unsigned updm = __ballot_sync(FULL, upd);
         unsigned hitm = __ballot_sync(FULL, covered && agent_here && !sclean);
-        if (upd) tile[cell] = (uint8_t)((code & 0xF0u) | C_RIVER);
+        if (upd) tile[cell] = (uint8_t)((code & OCC_BIT) | C_RIVER);
         while (hitm) {                               // Agent.hit(b"F"): -50 (Agent.py:178-180,224-226)
             int hl = __ffs(hitm) - 1; hitm &= hitm - 1;
             int hc = __shfl_sync(FULL, cell, hl);
@@ -361,8 +387,7 @@ __device__ __forceinline__ void fill_draws(uint32_t* scratch, int lane, const En
                                            uint32_t site, int nblk)
 {
     for (int bl = lane; bl < nblk; bl += 32) {
-        Philox4 q = draw_block(g.seed, g.env_id, g.episode, t, site, 0, (uint32_t)bl);
-        reinterpret_cast<uint4*>(scratch)[bl] = make_uint4(q.x, q.y, q.z, q.w);
+        reinterpret_cast<uint4*>(scratch)[bl] = draw_block_ool(g.seed, g.env_id, g.episode, t, site, (uint32_t)bl);
     }
     __syncwarp();
 }
@@ -374,6 +399,7 @@ __device__ __forceinline__ bool cleanup_spawn_active(const SharedTables& tb, int
 {
     return tb.thr_apple[hcount] != 0 || tb.waste_on[hcount] != 0;
 }
+template <int ROUNDS>
 __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile,
                                              uint32_t* scratch, const EnvRng& g, uint32_t t, int hcount)
 {
@@ -384,14 +410,14 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
     uint32_t* draws = scratch;
     uint32_t* keys = scratch + SCRATCH_DRAWS;
     // apples: eligible = no agent there and not already 'A'; draw index = rank among eligible (:328-335)
-    unsigned eligm[MAX_POINT_ROUNDS];
+    unsigned eligm[ROUNDS];
     int M = 0;
 #pragma unroll
-    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+    for (int q = 0; q < ROUNDS; q++) {
         int j = lane + 32 * q;
         bool e = false;
         if (q * 32 < p.n_apple) {
-            if (j < p.n_apple) { uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & 15u) != C_APPLE; }
+            if (j < p.n_apple) { uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE; }
             eligm[q] = __ballot_sync(FULL, e);
             M += __popc(eligm[q]);
         } else eligm[q] = 0;
@@ -400,11 +426,11 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
         fill_draws(draws, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);
         int base = 0;
 #pragma unroll
-        for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        for (int q = 0; q < ROUNDS; q++) {
             if (q * 32 < p.n_apple) {
                 if ((eligm[q] >> lane) & 1u) {
                     int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_APPLE); }
+                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); }
                 }
                 base += __popc(eligm[q]);
             }
@@ -414,14 +440,14 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
     if (!waste_on) return 0;
     // waste: shuffle waste_points (stateless: key per canonical index), scan non-'H' cells in that
     // order, draw continues at rank M; first success spawns and breaks (:338-348)
-    unsigned candm[MAX_POINT_ROUNDS];
+    unsigned candm[ROUNDS];
     int C = 0;
 #pragma unroll
-    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+    for (int q = 0; q < ROUNDS; q++) {
         int j = lane + 32 * q;
         bool cnd = false;
         if (q * 32 < p.n_waste) {
-            if (j < p.n_waste) cnd = (tile[sm_waste[j]] & 15u) != C_WASTE;
+            if (j < p.n_waste) cnd = (tile[sm_waste[j]] & CODE_MASK) != C_WASTE;
             candm[q] = __ballot_sync(FULL, cnd);
             C += __popc(candm[q]);
         } else candm[q] = 0;
@@ -430,22 +456,21 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
     // number of failed draws before the first success
     int kstar = -1;
     for (int k0 = 0; k0 < C && kstar < 0; k0 += 32) {
-        uint32_t dr = draw_u32(g.seed, g.env_id, g.episode, t, SITE_SPAWN_DRAWS, 0, (uint32_t)(M + k0 + lane));
+        uint32_t dr = draw_u32_ool(g, t, SITE_SPAWN_DRAWS, (uint32_t)(M + k0 + lane));
         unsigned succ = __ballot_sync(FULL, (k0 + lane) < C && dr < p.thr_waste);
         if (succ) kstar = k0 + __ffs(succ) - 1;
     }
     if (kstar < 0) return 0;
     // keys of all waste points, then the (kstar+1)-th smallest (key, index) among candidates
     for (int bl = lane; bl < ((p.n_waste + 3) >> 2); bl += 32) {
-        Philox4 qd = draw_block(g.seed, g.env_id, g.episode, t, SITE_WASTE_ORDER, 0, (uint32_t)bl);
-        reinterpret_cast<uint4*>(keys)[bl] = make_uint4(qd.x, qd.y, qd.z, qd.w);
+        reinterpret_cast<uint4*>(keys)[bl] = draw_block_ool(g.seed, g.env_id, g.episode, t, SITE_WASTE_ORDER, (uint32_t)bl);
     }
     __syncwarp();
     int chosen = -1;
     for (int it = 0; it <= kstar; it++) {
         uint32_t bk = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
 #pragma unroll
-        for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+        for (int q = 0; q < ROUNDS; q++) {
             if ((candm[q] >> lane) & 1u) {
                 int j = lane + 32 * q; uint32_t kk = keys[j];
                 if (kk < bk || (kk == bk && j < bj)) { bk = kk; bj = j; }
@@ -457,23 +482,24 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
         // remove it from the candidate set (uniform update of the owning lane's bit)
         int ql = jmin >> 5, ll = jmin & 31;
 #pragma unroll
-        for (int q = 0; q < MAX_POINT_ROUNDS; q++) if (q == ql) candm[q] &= ~(1u << ll);
+        for (int q = 0; q < ROUNDS; q++) if (q == ql) candm[q] &= ~(1u << ll);
     }
-    if (lane == 0) { int cell = sm_waste[chosen]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_WASTE); }
+    if (lane == 0) { int cell = sm_waste[chosen]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_WASTE); }
     __syncwarp();
     return 1;
 }
 
 // harvest spawn (harvest_new.py:284-317): neighbour counts read the pre-spawn map
+template <int ROUNDS>
 __device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
                                               const uint16_t* sm_apple, const EnvRng& g, uint32_t t)
 {
     const int S = p.S;
-    unsigned eligm[MAX_POINT_ROUNDS];
-    uint32_t mythr[MAX_POINT_ROUNDS];
+    unsigned eligm[ROUNDS];
+    uint32_t mythr[ROUNDS];
     int M = 0;
 #pragma unroll
-    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+    for (int q = 0; q < ROUNDS; q++) {
         mythr[q] = 0; eligm[q] = 0;
         if (q * 32 < p.n_apple) {
             int j = lane + 32 * q;
@@ -481,14 +507,14 @@ __device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uin
             if (j < p.n_apple) {
                 int cell = sm_apple[j];
                 uint32_t code = tile[cell];
-                e = !(code & OCC_BIT) && (code & 15u) != C_APPLE;
+                e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE;
                 if (e) {       // j*j + k*k <= APPLE_RADIUS(=2): the 3x3 block; own cell is not 'A'
                     int cnt = 0;
 #pragma unroll
                     for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
                         for (int dc = -1; dc <= 1; dc++)
-                            if (dr | dc) cnt += ((tile[cell + dr * S + dc] & 15u) == C_APPLE);
+                            if (dr | dc) cnt += ((tile[cell + dr * S + dc] & CODE_MASK) == C_APPLE);
                     mythr[q] = p.thr_harvest[cnt < 3 ? cnt : 3];
                 }
             }
@@ -500,11 +526,11 @@ __device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uin
     fill_draws(scratch, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);   // also orders the tile reads above
     int base = 0;
 #pragma unroll
-    for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+    for (int q = 0; q < ROUNDS; q++) {
         if (q * 32 < p.n_apple) {
             if ((eligm[q] >> lane) & 1u) {
                 int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & 0xF0u) | C_APPLE); }
+                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); }
             }
             base += __popc(eligm[q]);
         }
@@ -520,7 +546,7 @@ __device__ __forceinline__ int count_apples_r5(const uint8_t* tile, int o, int S
     for (int dr = -2; dr <= 2; dr++)
 #pragma unroll
         for (int dc = -2; dc <= 2; dc++)
-            if (dr * dr + dc * dc <= 5) cnt += ((tile[o + dr * S + dc] & 15u) == C_APPLE);
+            if (dr * dr + dc * dc <= 5) cnt += ((tile[o + dr * S + dc] & CODE_MASK) == C_APPLE);
     return cnt;
 }
 
@@ -533,7 +559,7 @@ __device__ __forceinline__ uint32_t closest_point(int lane, const uint8_t* tile,
 {
     uint32_t best = 0xFFFFFFFFu;
     for (int j = lane; j < npts; j += 32) {
-        if ((tile[pts[j]] & 15u) == code) {
+        if ((tile[pts[j]] & CODE_MASK) == code) {
             int r = rc[j] >> 8, c = rc[j] & 255;
             uint32_t key = ((uint32_t)(abs(r - ar) + abs(c - ac)) << 16) | (uint32_t)j;
             best = key < best ? key : best;
@@ -546,7 +572,7 @@ __device__ __forceinline__ int count_points(int lane, const uint8_t* tile, const
     int cnt = 0;
     for (int j0 = 0; j0 < npts; j0 += 32) {
         int j = j0 + lane;
-        cnt += __popc(__ballot_sync(FULL, j < npts && (tile[pts[j]] & 15u) == code));
+        cnt += __popc(__ballot_sync(FULL, j < npts && (tile[pts[j]] & CODE_MASK) == code));
     }
     return cnt;
 }
@@ -636,7 +662,8 @@ __device__ __forceinline__ void gather_obs(const GridParams& p, int lane, const 
             const int4 d = vdesc[a];
             const uint8_t* src = tile + (d.x + i * d.z);
 #pragma unroll
-            for (int j = 0; j < SSD_OBSW; j++) col[15 * q + j] = sm_pal[src[j * d.y]];
+            for (int j = 0; j < SSD_OBSW; j++)      // a tile byte IS the byte offset of its palette entry
+                col[15 * q + j] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(sm_pal) + src[j * d.y]);
         }
         uint32_t* dst = sw + 45 * lane;
 #pragma unroll
@@ -687,7 +714,9 @@ __device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, 
 
 // =============================================================================================
 // STEP
-template <int KIND>
+// ROUNDS: 32-point rounds the apple / waste point lists need (4 covers the stock cleanup map);
+// FEAT: the variant that also writes infos['feature_obs'] (kept out of the hot variant's code).
+template <int KIND, int ROUNDS, bool FEAT>
 __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kernel(const GridParams p, const StepIO io)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -701,7 +730,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + p.off_misc + MISC_MBAR);
-    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
+    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
     if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();                                  // tables + barriers visible
@@ -761,7 +790,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
                     // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
                     int rel = act == 0 ? 3 : (act == 1 ? 1 : (act == 2 ? 0 : 2));
                     int cand = ao + dir_delta((ori + rel) & 3, S);
-                    uint32_t c = tile[cand] & 15u;
+                    uint32_t c = tile[cand] & CODE_MASK;
                     if (c != C_WALL && c != C_OUTSIDE) tgt = cand;           // return_valid_pos (Agent.py:111-119)
                 }
             } else if (act == 5) ori = (ori + 1) & 3;                          // TURN_CLOCKWISE
@@ -779,7 +808,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
         // co-located agents (possible after unresolved conflicts) share one cell
         const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
         if (act_lane) {
-            bool on_apple = (tile[ao] & 15u) == C_APPLE;
+            bool on_apple = (tile[ao] & CODE_MASK) == C_APPLE;
             if (on_apple && !(flags & RF_STALE_EMPTY)) {
                 eaten = 1;
                 if (KIND == SSD_ENV_HARVEST) eaten_close = count_apples_r5(tile, ao, S) < 4;
@@ -790,7 +819,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
         __syncwarp();
         if (act_lane) {
             uint32_t c = tile[ao];
-            if ((c & 15u) == C_APPLE) c = C_EMPTY;
+            if ((c & CODE_MASK) == C_APPLE) c = C_EMPTY;
             tile[ao] = (uint8_t)(c | OCC_BIT);      // occupancy for beams + spawn eligibility
         }
         __syncwarp();
@@ -802,16 +831,16 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             if (cleanup_spawn_active(tb, hcount)) {
                 if (lane == 0) bulk_wait_read<0>();  // previous env's observation store has drained `stage` (= scratch)
                 __syncwarp();
-                hcount += cleanup_spawn(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
+                hcount += cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
             }
         } else {
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
-            harvest_spawn(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
+            harvest_spawn<ROUNDS>(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
         }
         if (KIND == SSD_ENV_HARVEST && act_lane) total_close = count_apples_r5(tile, ao, S);
-        if (io.feat) write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount,
-                                          io.feat + (size_t)env * n * p.F);
+        if (FEAT) write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount,
+                                       io.feat + (size_t)env * n * p.F);
 
         // ---- map back into the record slot (paint stripped)
         tile_compress(p, rec, tile, lane);
@@ -884,7 +913,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
 
         // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
         // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_expand.
-        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)(6 + lane);
+        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
         // gather_obs: waits (lane 0) until at most the record store above is still in flight, syncs the warp
         gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, io.obs + (size_t)env * (size_t)io.obs_stride);
         __syncwarp();
@@ -905,7 +934,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     uint8_t* stage = tile + p.off_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
-    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0x0F0F0F0Fu;
+    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
     __syncthreads();
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
@@ -956,11 +985,11 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         if (act_lane) tile[ao] |= OCC_BIT;
         __syncwarp();
         int hcount = p.n_waste_start;
-        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn(p, tb, lane, tile, scratch, g, 0u, hcount);
-        else harvest_spawn(p, lane, tile, scratch, tb.apple, g, 0u);
+        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn<MAX_POINT_ROUNDS>(p, tb, lane, tile, scratch, g, 0u, hcount);
+        else harvest_spawn<MAX_POINT_ROUNDS>(p, lane, tile, scratch, tb.apple, g, 0u);
         tile_store(p, rec, tile, lane);
         __syncwarp();
-        if (act_lane) tile[ao] &= 15u;               // MapEnv.reset never paints agents into the colour grid
+        if (act_lane) tile[ao] &= CODE_MASK;              // MapEnv.reset never paints agents into the colour grid
         __syncwarp();
         if (obs) gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, obs + (size_t)env * (size_t)obs_stride);
 
