@@ -150,6 +150,7 @@ def main():
     import torch
     import torch.distributed as dist
     from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,8 +167,6 @@ def main():
     actions = torch.empty((E, n), dtype=torch.uint8, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
-    stats_out = [torch.zeros((E, 56), dtype=torch.float64, device=dev)]
-    gathered = torch.zeros((world, 8), dtype=torch.float64, device=dev) if world > 1 else None
 
     def new_episode():
         """reset + negotiation prologue (two_stage_train.py:257-281): a0 proposes theta ~ U[0, 0.2], others accept ~ U[0,1]."""
@@ -178,14 +177,10 @@ def main():
 
     def end_episode():
         """episode statistics -> one small NCCL all-gather (the only collective of the workload)."""
-        m = env.metrics_raw()
-        s = torch.stack([m[:, 0].sum(), m[:, 2].sum(), m[:, 3].sum(), m[:, 4].sum(),
-                         m[:, 40:48].sum(), m[:, 24:32].sum(), torch.tensor(float(E), device=dev, dtype=torch.float64),
-                         m[:, 5].max()])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, s)
-            return gathered.sum(0)
-        return s
+        g = sharding.gather_episode_stats(sharding.local_episode_stats(env.metrics_raw()))
+        total = g.sum(0)
+        total[7] = g[:, 7].max()
+        return total
 
     state = {"t": 0, "global_step": 0, "stats": None}
 

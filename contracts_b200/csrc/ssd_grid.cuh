@@ -149,26 +149,42 @@ __device__ __forceinline__ void tile_store(const GridParams& p, uint8_t* rec, co
     }
 }
 
-// shared-memory record slot <-> padded tile (step kernel; the record arrives / leaves by bulk copy)
-__device__ __forceinline__ void tile_expand(const GridParams& p, const uint8_t* recbuf, uint8_t* tile, int lane)
+// shared-memory record slot <-> padded tile (step kernel; the record arrives / leaves by bulk copy).
+// Lane l moves map words l, l + 32, ...; the tile word of each is loop-invariant across envs, so the
+// first MAP_REG_WORDS of them are computed once per warp and kept in registers.
+#define MAP_REG_WORDS 6
+struct MapWords { int tw[MAP_REG_WORDS]; };
+__device__ __forceinline__ int map_tile_word(const GridParams& p, int w)
+{
+    int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
+    return (row + SSD_VIEW) * (p.S >> 2) + 2 + (w - row * p.wpw);
+}
+__device__ __forceinline__ MapWords map_words_init(const GridParams& p, int lane)
+{
+    MapWords m;
+#pragma unroll
+    for (int k = 0; k < MAP_REG_WORDS; k++) m.tw[k] = map_tile_word(p, lane + 32 * k);
+    return m;
+}
+__device__ __forceinline__ void tile_expand(const GridParams& p, const MapWords& m, const uint8_t* recbuf, uint8_t* tile, int lane)
 {
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(recbuf);
     uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
-    const int S4 = p.S >> 2, nwords = p.H * p.wpw;
-    for (int w = lane; w < nwords; w += 32) {
-        int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-        tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] = rw[w];
-    }
+    const int nwords = p.H * p.wpw;
+#pragma unroll
+    for (int k = 0; k < MAP_REG_WORDS; k++)
+        if (lane + 32 * k < nwords) tw[m.tw[k]] = rw[lane + 32 * k];
+    for (int w = lane + 32 * MAP_REG_WORDS; w < nwords; w += 32) tw[map_tile_word(p, w)] = rw[w];
 }
-__device__ __forceinline__ void tile_compress(const GridParams& p, uint8_t* recbuf, const uint8_t* tile, int lane)
+__device__ __forceinline__ void tile_compress(const GridParams& p, const MapWords& m, uint8_t* recbuf, const uint8_t* tile, int lane)
 {
     uint32_t* rw = reinterpret_cast<uint32_t*>(recbuf);
     const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-    const int S4 = p.S >> 2, nwords = p.H * p.wpw;
-    for (int w = lane; w < nwords; w += 32) {
-        int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-        rw[w] = tw[(row + SSD_VIEW) * S4 + 2 + (w - row * p.wpw)] & CODE_MASK4;   // strip agent paint / occupancy
-    }
+    const int nwords = p.H * p.wpw;
+#pragma unroll
+    for (int k = 0; k < MAP_REG_WORDS; k++)
+        if (lane + 32 * k < nwords) rw[lane + 32 * k] = tw[m.tw[k]] & CODE_MASK4;   // strip agent paint / occupancy
+    for (int w = lane + 32 * MAP_REG_WORDS; w < nwords; w += 32) rw[w] = tw[map_tile_word(p, w)] & CODE_MASK4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -738,12 +754,20 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
     const bool act_lane = lane < n;
     const int env_stride = gridDim.x * GRID_WARPS;
     const uint32_t rec_bytes = (uint32_t)p.rec_stride;
+    const MapWords mw = map_words_init(p, lane);
 
     int env = blockIdx.x * GRID_WARPS + warp;
+    // running global pointers of the current env (advanced by one grid stride per iteration)
+    uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
+    const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
+    const uint8_t* g_act = io.actions + (size_t)env * n + (act_lane ? lane : 0);
+    const size_t g_act_step = (size_t)env_stride * n;
+    uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
+    const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
     int act_next = 4;
     if (env < p.E) {
-        if (lane == 0) bulk_load(recs, p.state + (size_t)env * p.rec_stride, rec_bytes, mbar);
-        if (act_lane) act_next = io.actions[(size_t)env * n + lane];
+        if (lane == 0) bulk_load(recs, g_rec, rec_bytes, mbar);
+        if (act_lane) act_next = *g_act;
     }
     for (uint32_t it = 0; env < p.E; env += env_stride, it++) {
         const uint32_t slot = it & 1u;
@@ -756,13 +780,12 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
         if (env_nx < p.E) {
             if (lane == 0) {
                 bulk_wait_read<1>();                  // all but the newest group (an observation store)
-                bulk_load(recs + (slot ^ 1u) * p.rec_stride, p.state + (size_t)env_nx * p.rec_stride, rec_bytes,
-                          mbar + (slot ^ 1u));
+                bulk_load(recs + (slot ^ 1u) * p.rec_stride, g_rec + g_rec_step, rec_bytes, mbar + (slot ^ 1u));
             }
-            if (act_lane) act_next = io.actions[(size_t)env_nx * n + lane];
+            if (act_lane) act_next = g_act[g_act_step];
         }
         mbar_wait(mbar + slot, (it >> 1) & 1u);
-        tile_expand(p, rec, tile, lane);
+        tile_expand(p, mw, rec, tile, lane);
         // ---- per-env scalars + agent registers
         int t = *reinterpret_cast<const int*>(hdr + RO_T) + 1;                 // map_env.py:230
         const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
@@ -788,7 +811,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
                 has_move = true;
                 if (act < 4) {
                     // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
-                    int rel = act == 0 ? 3 : (act == 1 ? 1 : (act == 2 ? 0 : 2));
+                    int rel = (0x2013 >> (4 * act)) & 3;
                     int cand = ao + dir_delta((ori + rel) & 3, S);
                     uint32_t c = tile[cand] & CODE_MASK;
                     if (c != C_WALL && c != C_OUTSIDE) tgt = cand;           // return_valid_pos (Agent.py:111-119)
@@ -843,7 +866,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
                                        io.feat + (size_t)env * n * p.F);
 
         // ---- map back into the record slot (paint stripped)
-        tile_compress(p, rec, tile, lane);
+        tile_compress(p, mw, rec, tile, lane);
 
         // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
         const double base = (double)reward;
@@ -909,13 +932,14 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
         // ---- the record leaves with one bulk store
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store(p.state + (size_t)env * p.rec_stride, rec, rec_bytes);
+        if (lane == 0) bulk_store(g_rec, rec, rec_bytes);
 
         // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
         // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_expand.
         if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
         // gather_obs: waits (lane 0) until at most the record store above is still in flight, syncs the warp
-        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, io.obs + (size_t)env * (size_t)io.obs_stride);
+        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
+        g_rec += g_rec_step; g_act += g_act_step; g_obs += g_obs_step;
         __syncwarp();
     }
     if (lane == 0) bulk_wait_read<0>();      // smem must outlive the async bulk reads
