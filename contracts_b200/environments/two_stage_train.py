@@ -1,0 +1,205 @@
+"""Contract wrappers with the reference's names and dict API (environments/two_stage_train.py:17-358).
+
+The reward redistribution of `SeparateContractEnv.step` (:62-121) is not evaluated here: it is fused into the
+step kernel (selected by the contract's class name), this module only shapes the dict outputs.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from .. import spaces
+
+_FUSED = ("CleanupContract", "HarvestFeaturemodLocalContract")
+
+
+class SeparateContractEnv:
+    """two_stage_train.py:17-127."""
+    metadata = {"render.modes": ["rgb_array"]}
+
+    def __init__(self, base_env, contract, num_agents, convolutional, env_params=None, null_prob=0.0, **kwargs):
+        self.num_agents = num_agents
+        self.base_env = base_env
+        self.contract = contract
+        self.contract_low = self.contract.contract_space.low
+        self.contract_high = self.contract.contract_space.high
+        self.contract_state = {"a" + str(i): 0 for i in range(self.num_agents)}
+        self.convolutional = convolutional
+        self.null_prob = null_prob
+        name = type(contract).__name__
+        if name not in _FUSED:
+            raise NotImplementedError("contract %s has no fused device transfer function" % name)
+        base_env._bind_contract(name, self.contract_low[0], self.contract_high[0], null_prob)
+        self.agent_ids = ["a%d" % i for i in range(num_agents)]
+        if self.convolutional:
+            contract_space = spaces.Box(low=np.concatenate((self.contract_low, np.array([0.0]))),
+                                        high=np.concatenate((self.contract_high, np.array([3.0]))))
+            obs_space = self.base_env.observation_space
+            d = {"contract": contract_space}
+            for k in ("features", "image"):
+                if k in obs_space.keys():
+                    d[k] = obs_space[k]
+            self.observation_space = spaces.Dict(d)
+        else:
+            self.observation_space = spaces.Box(
+                low=np.concatenate((self.base_env.observation_space.low, self.contract_low, np.array([0.0]))),
+                high=np.concatenate((self.base_env.observation_space.high, self.contract_high, np.array([3.0]))))
+        self.params = None
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _theta(self):
+        return self.base_env.batch.get_state()["theta"][0:1].cpu().numpy().astype(np.float64)
+
+    def _with_contract(self, obs, state_of):
+        out = {}
+        for k in self.agent_ids:
+            tail = np.array([state_of(k)])
+            if self.convolutional:
+                out[k] = obs[k]
+                out[k].update({"contract": np.concatenate((self.params[k], tail))})
+            else:
+                out[k] = np.concatenate((obs[k], self.params[k], tail))
+        return out
+
+    def step(self, acts):
+        raw_obs, _, dones, infos = self.base_env.step(acts)
+        L = self.base_env._last
+        self.obs = {k: raw_obs[k] for k in acts.keys()}
+        rews = {k: np.float64(L["rew"][int(k[1:])]) for k in acts.keys()}     # after transfers (kernel)
+        self.last_transfers = {k: L["transfers"][int(k[1:])] for k in acts.keys()}
+        for k in acts.keys():
+            infos[k]["contract_param"] = self.params[k]
+        return self._with_contract(self.obs, lambda k: 0), rews, dones, infos
+
+    def render(self, mode="rgb"):
+        return self.base_env.render()
+
+    def reset(self):
+        raise NotImplementedError
+
+    @property
+    def metrics(self):
+        return self.base_env.metrics
+
+
+class SeparateContractSubgameStage(SeparateContractEnv):
+    """two_stage_train.py:129-187: every reset samples theta ~ U(low, high) (or `low` with prob. null_prob)."""
+
+    def __init__(self, base_env, contract, num_agents, convolutional, env_params=None, null_prob=0.0, **kwargs):
+        super().__init__(base_env, contract, num_agents, convolutional, env_params, null_prob)
+        self.action_space = self.base_env.action_space
+
+    def reset(self):
+        base_obs = self.base_env.reset()           # the reset kernel also draws theta (two_stage_train.py:163-166)
+        self.obs = copy.deepcopy(base_obs)
+        rand_val = self._theta()
+        self.contract_state = {k: 0 for k in self.agent_ids}
+        self.params = {k: rand_val for k in self.agent_ids}
+        return self._with_contract(self.obs, lambda k: 0)
+
+
+class SeparateContractNegotiateStage(SeparateContractEnv):
+    """two_stage_train.py:190-358: propose (state 2) -> accept / reject (state 3) -> frozen-policy rollout.
+
+    The reference loads a frozen RLlib PPO policy (`trainer_config`, `trainer_env`, `trainer_path`); that
+    forward pass is outside the accelerated path.  Here `policy` is any callable
+    `policy(obs, agent_id) -> action` playing that role; with `policy=None` the subgame is rolled out with
+    uniform random actions generated on the device (what the throughput benchmark uses).
+    """
+
+    def __init__(self, base_env, contract, num_agents, horizon, trainer_config=None, trainer_env=None,
+                 trainer_path=None, convolutional=True, shared=True, env_params=None, policy=None, **kwargs):
+        super().__init__(base_env, contract, num_agents, convolutional)
+        self.horizon = horizon
+        self.shared = shared
+        self.policy = policy
+        self.action_space = spaces.Box(low=np.concatenate((self.contract_low, np.array([0.0]))),
+                                       high=np.concatenate((self.contract_high, np.array([1.0]))))
+        self._metrics = {"contract": -1, "accepted": 0}
+
+    @property
+    def metrics(self):
+        return self._metrics
+
+    def reset(self):
+        self._metrics = {"contract": -1, "accepted": 0}
+        base_obs = self.base_env.reset()
+        self.obs = copy.deepcopy(base_obs)
+        self.last_seen_obs = copy.deepcopy(base_obs)
+        self.params = None
+        self.contract_state = {k: 2 for k in self.agent_ids}
+        zeros = {k: np.zeros(self.contract_low.shape) for k in self.agent_ids}
+        saved, self.params = self.params, zeros
+        out = self._with_contract(self.obs, lambda k: self.contract_state[k])
+        self.params = saved
+        return out
+
+    def step(self, acts):
+        b = self.base_env.batch
+        n = self.num_agents
+        if self.contract_state["a0"] == 2:
+            proposal = np.asarray(acts["a0"][:-1], dtype=np.float64)
+            self._metrics["contract"] = acts["a0"][:-1]
+            self.params = {k: proposal for k in acts.keys()}
+            self.contract_state = {k: 3 for k in self.agent_ids}
+            rews = {k: 0.0 for k in self.agent_ids}
+            dones = {"__all__": False}
+            infos = {k: {} for k in self.agent_ids}
+        elif self.contract_state["a0"] == 3:
+            accept = torch.tensor([[float(acts[k][-1]) for k in self.agent_ids]], dtype=torch.float64)
+            dec = b.negotiate(torch.tensor([float(self.params["a0"][0])], dtype=torch.float64), accept)
+            decision = int(dec[0].item())
+            self._metrics["accepted"] = decision
+            for k in self.agent_ids:
+                self.contract_state[k] = 0
+                self.params[k] = self.params[k] if decision == 1 else np.zeros(shape=self.contract_low.shape)
+            rews = {k: 0.0 for k in self.agent_ids}
+            dones = {"__all__": True}
+            infos = {k: {} for k in self.agent_ids}
+            if self.policy is None:
+                rews, infos = self._random_rollout(rews, infos)
+            else:
+                env_done, steps = False, 0
+                while not env_done and steps < self.horizon:
+                    act_dict = {}
+                    for k in self.agent_ids:
+                        if self.convolutional:
+                            o = self.obs[k]
+                            o.update({"contract": np.concatenate((self.params[k], np.array([0])))})
+                        else:
+                            o = np.concatenate((self.obs[k], self.params[k], np.array([0])))
+                        act_dict[k] = self.policy(o, k)
+                    _, env_rews, env_dones, infos = super().step(act_dict)
+                    self.last_seen_obs = {k: self.obs[k] for k in self.agent_ids}
+                    env_done = env_dones["__all__"]
+                    steps += 1
+                    for k in self.agent_ids:
+                        rews[k] += env_rews[k]
+        else:
+            raise RuntimeError("negotiation episode is over: call reset()")
+        saved_obs = self.obs
+        out = self._with_contract(self.last_seen_obs, lambda k: self.contract_state[k])
+        self.obs = saved_obs
+        return out, rews, dones, infos
+
+    def _random_rollout(self, rews, infos):
+        """<= horizon subgame steps with device-generated uniform random actions; rewards summed on the device."""
+        b = self.base_env.batch
+        na = self.base_env.action_space.n
+        total = torch.zeros_like(b.rew)
+        steps = 0
+        done = False
+        while not done and steps < self.horizon:
+            a = b.random_actions(steps, na)
+            b.step(a, want_features=False)
+            total += b.rew
+            steps += 1
+            self.base_env.timesteps += 1
+            if steps % 64 == 0 or steps == self.horizon:
+                done = bool(b.done[0].item())
+        tot = total[0].cpu().numpy()
+        rews = {k: rews[k] + tot[i] for i, k in enumerate(self.agent_ids)}
+        self.last_seen_obs = self.base_env._image_obs(b.obs[0].cpu().numpy()) if self.base_env.image_obs else self.last_seen_obs
+        for k in self.agent_ids:
+            infos[k]["contract_param"] = self.params[k]
+        return rews, infos

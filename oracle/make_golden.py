@@ -77,9 +77,109 @@ def run_scenario(name):
     return out
 
 
+# name -> (kind, n, seed, env_id, negotiate horizon, base env horizon, episodes, action ids)
+NEGOTIATE_SCENARIOS = {
+    "negotiate_cleanup_n2": ("cleanup", 2, 21, 3, 30, 1000, 4, 9),
+    "negotiate_cleanup_n5": ("cleanup", 5, 22, 40, 1000, 25, 4, 9),     # ends on the base env's own horizon
+    "negotiate_harvest_n4": ("harvest", 4, 23, 7, 20, 1000, 4, 8),
+}
+
+
+def run_negotiate(name):
+    """SeparateContractNegotiateStage episodes: reset -> proposal step -> agreement step + scripted rollout."""
+    from .ref_harness import RefNegotiateEnv
+    kind, n, seed, env_id, horizon, base_horizon, episodes, act_hi = NEGOTIATE_SCENARIOS[name]
+    rng = np.random.RandomState(sum(map(ord, name)))
+    steps = min(horizon, base_horizon)
+    table = rng.randint(0, act_hi, size=(steps, n))
+    ref = RefNegotiateEnv(kind, n, seed, env_id, horizon, base_horizon, table)
+    high = 0.2 if kind == "cleanup" else 10.0
+    rec = {k: [] for k in ("reset_obs", "reset_contract_obs", "acts", "obs2", "contract_obs2", "rew2", "obs3",
+                           "contract_obs3", "rew3", "accepted", "t_end", "base_metrics")}
+    keys = None
+    for ep in range(episodes):
+        r0 = ref.reset()
+        acts = np.stack([rng.uniform(0, high, size=n), rng.uniform(0.55, 1.0, size=n)], axis=1)
+        if ep == 1:
+            acts[1:, 1] = 0.0          # a certain rejection
+        s2 = ref.step(acts)
+        s3 = ref.step(acts)
+        assert not s2["done"] and s3["done"]
+        m = ref.base_metrics()
+        keys = sorted(m.keys())
+        for k, v in (("reset_obs", r0["obs"]), ("reset_contract_obs", r0["contract_obs"]), ("acts", acts),
+                     ("obs2", s2["obs"]), ("contract_obs2", s2["contract_obs"]), ("rew2", s2["rew"]),
+                     ("obs3", s3["obs"]), ("contract_obs3", s3["contract_obs"]), ("rew3", s3["rew"]),
+                     ("accepted", s3["accepted"]), ("t_end", s3["t"]), ("base_metrics", [m[k] for k in keys])):
+            rec[k].append(v)
+    out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon, "base_horizon": base_horizon,
+           "table": table, "metric_keys": np.array(keys)}
+    out.update({k: np.array(v) for k, v in rec.items()})
+    return out
+
+
+# image_obs=False + non-convolutional wrapper: flat feature-vector observations (cleanup_new.py:193-202,243-254;
+# two_stage_train.py:113-121,182-187).  name -> (kind, n, seed, env_id, horizon, episodes, steps, action ids)
+FLATOBS_SCENARIOS = {
+    "flatobs_cleanup_n3": ("cleanup", 3, 31, 2, 25, 2, 25, 9),
+    "flatobs_harvest_n3": ("harvest", 3, 32, 6, 25, 2, 25, 8),
+}
+
+
+def run_flatobs(name):
+    from . import ref_harness as rh
+    from . import philox as px
+    kind, n, seed, env_id, horizon, episodes, steps, act_hi = FLATOBS_SCENARIOS[name]
+    rh.install()
+    from utils.env_creator_functions import env_creator
+    import contract.contract_list as cl
+    ctx = rh.DrawContext(seed, env_id)
+    with rh.active(ctx):
+        ctx.begin(px.EPISODE_CONSTRUCT, 0)
+        base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                           dict(num_agents=n, env_params={}, image_obs=False, horizon=horizon))
+        c = cl.CleanupContract(n) if kind == "cleanup" else cl.HarvestFeaturemodLocalContract(n)
+        env = env_creator("ContractWrapperSubgame", dict(num_agents=n, base_env=base, contract=c, convolutional=False))
+    keys = ["a%d" % i for i in range(n)]
+    rng = np.random.RandomState(sum(map(ord, name)))
+    out = {"reset_obs": [], "actions": [], "obs": [], "rew": []}
+    for ep in range(episodes):
+        with rh.active(ctx):
+            ctx.begin(ep, 0)
+            o = env.reset()
+        out["reset_obs"].append(np.stack([np.asarray(o[k], dtype=np.float64) for k in keys]))
+        for k in ("actions", "obs", "rew"):
+            out[k].append([])
+        for t in range(steps):
+            a = rng.randint(0, act_hi, size=n)
+            with rh.active(ctx):
+                ctx.begin(ep, base.timesteps + 1)
+                o, r, d, info = env.step({k: int(x) for k, x in zip(keys, a)})
+            out["actions"][-1].append(a)
+            out["obs"][-1].append(np.stack([np.asarray(o[k], dtype=np.float64) for k in keys]))
+            out["rew"][-1].append(np.array([r[k] for k in keys], dtype=np.float64))
+    res = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon}
+    res.update({k: np.array(v) for k, v in out.items()})
+    res["space_low"] = np.asarray(env.observation_space.low, dtype=np.float64)
+    res["space_high"] = np.asarray(env.observation_space.high, dtype=np.float64)
+    return res
+
+
 def main(names=None):
     os.makedirs(OUT, exist_ok=True)
-    for name in (names or SCENARIOS):
+    for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS)):
+        if name in FLATOBS_SCENARIOS:
+            data = run_flatobs(name)
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **data)
+            print("%-28s %7.1f KiB  obs=%s" % (name, os.path.getsize(path) / 1024, data["obs"].shape))
+            continue
+        if name in NEGOTIATE_SCENARIOS:
+            data = run_negotiate(name)
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **data)
+            print("%-28s %7.1f KiB  accepted=%s t_end=%s" % (name, os.path.getsize(path) / 1024, data["accepted"], data["t_end"]))
+            continue
         data = run_scenario(name)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

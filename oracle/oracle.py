@@ -48,6 +48,7 @@ def lib():
         L.oracle_set_state.argtypes = [vp] * 6
         L.oracle_get_metrics.argtypes = [vp, vp]
         L.oracle_feature_dim.argtypes = [vp]
+        L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
         L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
@@ -125,6 +126,14 @@ class GridOracle:
         m, p, o = prep(map, np.uint8, (E, self.H, self.W)), prep(pos, np.int32, (E, n, 2)), prep(ori, np.int32, (E, n))
         tt, th = prep(t, np.int32, (E,)), prep(theta, np.float64, (E,))
         lib().oracle_set_state(self._h, _p(m), _p(p), _p(o), _p(tt), _p(th))
+
+    def negotiate(self, proposals, accept):
+        """Agreement stage (two_stage_train.py:266-281): returns the uint8 [E] accept decisions; sets theta."""
+        p = np.ascontiguousarray(np.broadcast_to(np.asarray(proposals, dtype=np.float64), (self.E,)))
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(accept, dtype=np.float64), (self.E, self.n)))
+        dec = np.zeros(self.E, np.uint8)
+        lib().oracle_negotiate(self._h, _p(p), _p(a), _p(dec))
+        return dec
 
     def metrics_raw(self):
         out = np.zeros((self.E, METRIC_STRIDE))

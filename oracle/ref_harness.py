@@ -314,3 +314,86 @@ class RefGridEnv:
             a.full_map = mwa
             if b.world_map[a.pos[0], a.pos[1]] not in [b"F", b"C"]:
                 b.single_update_world_color_map(a.pos[0], a.pos[1], a.get_char_id())
+
+
+class ScriptedTrainer:
+    """Stands in for the frozen RLlib PPOTrainer of SeparateContractNegotiateStage (two_stage_train.py:220-221,
+    299-313): `compute_single_action` is called once per active agent per inner step, in agent order, and
+    returns the next entry of a fixed action table [steps, n]."""
+
+    def __init__(self, table):
+        self.table = np.asarray(table)
+        self.calls = 0
+
+    def compute_single_action(self, obs, policy_id=None):
+        t, i = divmod(self.calls, self.table.shape[1])
+        self.calls += 1
+        return int(self.table[t % self.table.shape[0], i])
+
+
+class RefNegotiateEnv:
+    """The reference's SeparateContractNegotiateStage (two_stage_train.py:190-358) under RNG injection, with the
+    PPOTrainer construction (:220-221) bypassed: the object is allocated without running that __init__ and the
+    fields it sets are assigned here (no reference source is edited)."""
+
+    def __init__(self, kind, num_agents, seed, env_id, horizon, base_horizon, table, ascii_map=None):
+        install()
+        import gym
+        from utils.env_creator_functions import env_creator
+        import contract.contract_list as cl
+        import environments.two_stage_train as tst
+        self.kind, self.n = kind, num_agents
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        cfg = dict(num_agents=num_agents, env_params={}, image_obs=True, horizon=base_horizon)
+        if ascii_map is not None:
+            cfg["ascii_map"] = ascii_map
+        with active(self.ctx):
+            self.ctx.begin(px.EPISODE_CONSTRUCT, 0)
+            self.base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew", cfg)
+        c = cl.CleanupContract(num_agents) if kind == "cleanup" else cl.HarvestFeaturemodLocalContract(num_agents)
+        env = object.__new__(tst.SeparateContractNegotiateStage)
+        tst.SeparateContractEnv.__init__(env, self.base, c, num_agents, True)
+        env.horizon = horizon
+        env.convolutional = True
+        env.shared = True
+        env.frozen_trainer = ScriptedTrainer(table)
+        env.action_space = gym.spaces.Box(low=np.concatenate((env.contract_low, np.array([0.0]))),
+                                          high=np.concatenate((env.contract_high, np.array([1.0]))))
+        env.metrics = {"contract": -1, "accepted": 0}
+        self.env = env
+        self.keys = ["a%d" % i for i in range(num_agents)]
+        orig_step = self.base.step
+
+        def stepped(acts):      # every inner base step gets its own draw coordinates (episode, t)
+            self.ctx.begin(self.episode, self.base.timesteps + 1)
+            return orig_step(acts)
+        self.base.step = stepped
+
+    def _pack(self, obs):
+        return {"obs": np.stack([np.rint(obs[k]["image"] * 255.0).astype(np.uint8) for k in self.keys]),
+                "contract_obs": np.stack([np.asarray(obs[k]["contract"], dtype=np.float64) for k in self.keys])}
+
+    def reset(self):
+        self.episode += 1
+        self.env.frozen_trainer.calls = 0
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        return self._pack(obs)
+
+    def step(self, acts):
+        """acts: float array [n, 2] = (proposal, accept probability) per agent."""
+        d = {k: np.asarray(a, dtype=np.float64) for k, a in zip(self.keys, acts)}
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs, rew, done, info = self.env.step(d)
+        out = self._pack(obs)
+        out["rew"] = np.array([rew[k] for k in self.keys], dtype=np.float64)
+        out["done"] = bool(done["__all__"])
+        out["accepted"] = int(self.env.metrics["accepted"])
+        out["t"] = int(self.base.timesteps)
+        return out
+
+    def base_metrics(self):
+        return {k: float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v) for k, v in self.base.metrics.items()}

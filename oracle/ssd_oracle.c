@@ -44,7 +44,7 @@ enum { CONTRACT_NONE = 0, CONTRACT_CLEANUP = 1, CONTRACT_HARVEST_LOCAL = 2 };
 enum { ORI_UP = 0, ORI_RIGHT = 1, ORI_DOWN = 2, ORI_LEFT = 3 };   /* Agent.py:18-23 */
 enum {
     SITE_MOVE_ORDER = 1, SITE_BEAM_ORDER = 2, SITE_SPAWN_DRAWS = 3, SITE_WASTE_ORDER = 4,
-    SITE_SPAWN_ROT = 5, SITE_SPAWN_POINT = 6, SITE_CONTRACT = 7
+    SITE_SPAWN_ROT = 5, SITE_SPAWN_POINT = 6, SITE_CONTRACT = 7, SITE_NEGOTIATE = 8
 };
 
 typedef struct { int16_t r, c; } pt;
@@ -851,3 +851,30 @@ void oracle_get_metrics(void* h, double* out)
     }
 }
 int oracle_feature_dim(void* h) { return ((batch_t*)h)->F; }
+
+/* Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281).
+ * proposals [E] (a0's action[:-1]), accept [E][n] (every agent's action[-1]), decision [E] out.
+ * n > 3: chosen = random.sample(range(1, n), 2) = the first two entries of the stateless shuffle of
+ * [1 .. n-1] (site NEGOTIATE call 0); prod = 1 * accept[chosen[0]] * accept[chosen[1]] in that order;
+ * decision = random.random() (site NEGOTIATE call 1) < prod; theta = proposal if accepted else 0. */
+void oracle_negotiate(void* h, const double* proposals, const double* accept, uint8_t* decision)
+{
+    batch_t* b = (batch_t*)h;
+    int n = b->n;
+    for (int i = 0; i < b->E; i++) {
+        env_t* e = &b->envs[i];
+        double prod = 1;
+        if (n > 3) {
+            int order[MAXN];
+            shuffle_order(e, 0, SITE_NEGOTIATE, 0, n - 1, order);
+            prod *= accept[(size_t)i * n + 1 + order[0]];
+            prod *= accept[(size_t)i * n + 1 + order[1]];
+        } else {
+            for (int a = 1; a < n; a++) prod *= accept[(size_t)i * n + a];
+        }
+        double r = draw_f64(e, 0, SITE_NEGOTIATE, 1, 0);
+        int dec = r < prod;
+        e->theta = dec ? proposals[i] : 0.0;
+        if (decision) decision[i] = (uint8_t)dec;
+    }
+}

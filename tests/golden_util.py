@@ -15,8 +15,15 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def fixture_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+OTHER_SCHEMAS = ("negotiate_", "selfdrive_", "features_", "flatobs_")
+
+
+def fixture_names(prefix=None):
+    """Step-replay fixtures (default) or the fixtures of another schema (`prefix`)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    if prefix is None:
+        return [n for n in names if not n.startswith(OTHER_SCHEMAS)]
+    return [n for n in names if n.startswith(prefix)]
 
 
 def load(name):
