@@ -165,9 +165,63 @@ def run_flatobs(name):
     return res
 
 
+# name -> (n, seed, env_id, contract, episodes, max steps/episode, action scale)
+SELFDRIVE_SCENARIOS = {
+    "selfdrive_n8": (8, 51, 0, True, 3, 400, 0.12),
+    "selfdrive_n2": (2, 52, 9, True, 3, 400, 0.12),
+    "selfdrive_n4_nocontract": (4, 53, 1000, False, 2, 400, 0.12),
+    "selfdrive_n8_fast": (8, 54, 77, True, 3, 400, 0.3),          # accelerations mostly clipped: more overtaking attempts
+    "selfdrive_n1": (1, 55, 2, False, 2, 100, 0.12),
+}
+
+
+def run_selfdrive(name):
+    """Episodes run until every car is done (or max steps); actions are seeded float32 accelerations, biased
+    forward so that episodes finish.  Steps after the end are padded with NaN / zeros and `length` says where."""
+    from .ref_harness import RefCarEnv
+    n, seed, env_id, contract, episodes, max_steps, scale = SELFDRIVE_SCENARIOS[name]
+    ref = RefCarEnv(n, seed, env_id, contract=contract)
+    rng = np.random.RandomState(sum(map(ord, name)))
+    keys = ("obs", "active", "rew", "done", "just_passed", "ambulance_rank", "ambulance_dist_to_front", "pos", "vel",
+            "metric_transfers", "base_rew", "transfers")
+    rec = {k: [] for k in keys}
+    out = {"reset_obs": [], "reset_theta": [], "actions": [], "length": []}
+    for ep in range(episodes):
+        r0 = ref.reset()
+        out["reset_obs"].append(r0["obs"])
+        out["reset_theta"].append(r0.get("theta", np.float64(0.0)))
+        acts = (rng.uniform(-0.6, 1.0, size=(max_steps, n)) * scale).astype(np.float32)
+        out["actions"].append(acts)
+        ep_rec = {k: [] for k in keys}
+        steps = 0
+        for t in range(max_steps):
+            o = ref.step(acts[t])
+            steps += 1
+            for k in keys:
+                ep_rec[k].append(o.get(k, np.zeros(n)))
+            if o["done"][-1]:
+                break
+        out["length"].append(steps)
+        for k in keys:
+            a = np.array(ep_rec[k], dtype=np.float64)
+            pad = np.full((max_steps - steps,) + a.shape[1:], np.nan)
+            rec[k].append(np.concatenate([a, pad], axis=0))
+    res = {"n": n, "seed": seed, "env_id": env_id, "contract": contract}
+    res.update({k: np.array(v) for k, v in out.items()})
+    res.update({k: np.array(v) for k, v in rec.items()})
+    return res
+
+
 def main(names=None):
     os.makedirs(OUT, exist_ok=True)
-    for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS)):
+    for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS) + list(SELFDRIVE_SCENARIOS)):
+        if name in SELFDRIVE_SCENARIOS:
+            data = run_selfdrive(name)
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **data)
+            print("%-28s %7.1f KiB  lengths=%s transfers=%s" % (name, os.path.getsize(path) / 1024, data["length"],
+                                                              np.nanmax(np.abs(data["transfers"]), axis=(1, 2))))
+            continue
         if name in FLATOBS_SCENARIOS:
             data = run_flatobs(name)
             path = os.path.join(OUT, name + ".npz")

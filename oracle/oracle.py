@@ -16,16 +16,17 @@ _LIB = None
 KIND = {"cleanup": 0, "harvest": 1}
 CONTRACT = {None: 0, "none": 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2}
 METRIC_STRIDE = 8 + 6 * 8
+SOURCES = ("ssd_oracle.c", "selfdrive_oracle.c", "features_oracle.c")
 
 
 def build(force=False):
     """Compile the oracle with the system gcc (the image's $CC has no OpenMP runtime)."""
-    src = os.path.join(_HERE, "ssd_oracle.c")
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in SOURCES]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    base = [cc, "-O2", "-std=c11", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO, src, "-lm"]
+    base = [cc, "-O2", "-std=c11", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO] + srcs + ["-lm"]
     try:
         subprocess.run(base[:4] + ["-fopenmp"] + base[4:], check=True, capture_output=True)
     except (subprocess.CalledProcessError, FileNotFoundError):
@@ -49,6 +50,14 @@ def lib():
         L.oracle_get_metrics.argtypes = [vp, vp]
         L.oracle_feature_dim.argtypes = [vp]
         L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
+        L.car_oracle_create.restype = vp
+        L.car_oracle_create.argtypes = [i32, i32, i32, f64, f64, f64, f64, f64, f64, f64, u32, u32]
+        L.car_oracle_destroy.argtypes = [vp]
+        L.car_oracle_obs_dim.argtypes = [vp]
+        L.car_oracle_reset.argtypes = [vp] * 4
+        L.car_oracle_step.argtypes = [vp] * 8
+        L.car_oracle_get_state.argtypes = [vp] * 6
+        L.car_oracle_set_theta.argtypes = [vp, vp]
         L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
@@ -139,3 +148,52 @@ class GridOracle:
         out = np.zeros((self.E, METRIC_STRIDE))
         lib().oracle_get_metrics(self._h, _p(out))
         return out
+
+
+class CarOracle:
+    """E independent SelfAcceleratingCarEnv (+ optional SelfdriveContractDistprop subgame wrapper)."""
+
+    def __init__(self, num_envs, num_agents, contract=False, low_bound=-10.0, high_bound=10.0, start_vel=0.2,
+                 start_vel_ambulance=0.8, theta_low=0.0, theta_high=100.0, null_prob=0.0, seed=73907, first_env_id=0):
+        self.E, self.n = int(num_envs), int(num_agents)
+        self._h = lib().car_oracle_create(self.E, self.n, 1 if contract else 0, float(low_bound), float(high_bound),
+                                          float(start_vel), float(start_vel_ambulance), float(theta_low),
+                                          float(theta_high), float(null_prob), int(seed) & 0xFFFFFFFF, int(first_env_id))
+        if not self._h:
+            raise ValueError("car_oracle_create failed")
+        self.D = lib().car_oracle_obs_dim(self._h)
+        self.episode = np.full(self.E, -1, dtype=np.int64)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().car_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        sel = np.ones(self.E, bool) if m is None else m.astype(bool)
+        self.episode[sel] += 1
+        ep = self.episode.astype(np.uint32)
+        obs = np.zeros((self.E, self.n, self.D))
+        lib().car_oracle_reset(self._h, _p(m), _p(ep), _p(obs))
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.E, self.n)
+        E, n = self.E, self.n
+        out = {"obs": np.zeros((E, n, self.D)), "rew": np.zeros((E, n)), "base_rew": np.zeros((E, n)),
+               "transfers": np.zeros((E, n)), "info": np.zeros((E, n, 4)), "done": np.zeros((E, n + 1), np.uint8)}
+        lib().car_oracle_step(self._h, _p(a), _p(out["obs"]), _p(out["rew"]), _p(out["base_rew"]), _p(out["transfers"]),
+                              _p(out["info"]), _p(out["done"]))
+        return out
+
+    def get_state(self):
+        E, n = self.E, self.n
+        st = {"pos": np.zeros((E, n)), "vel": np.zeros((E, n)), "theta": np.zeros(E), "transfers": np.zeros(E),
+              "t": np.zeros(E, np.int32)}
+        lib().car_oracle_get_state(self._h, _p(st["pos"]), _p(st["vel"]), _p(st["theta"]), _p(st["transfers"]), _p(st["t"]))
+        return st
+
+    def set_theta(self, theta):
+        th = np.ascontiguousarray(np.broadcast_to(np.asarray(theta, dtype=np.float64), (self.E,)))
+        lib().car_oracle_set_theta(self._h, _p(th))

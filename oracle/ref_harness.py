@@ -397,3 +397,80 @@ class RefNegotiateEnv:
 
     def base_metrics(self):
         return {k: float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v) for k, v in self.base.metrics.items()}
+
+
+class RefCarEnv:
+    """The reference's SelfAcceleratingCarEnv (+ SeparateContractSubgameStage / SelfdriveContractDistprop) under RNG
+    injection.  Done agents stop acting (what RLlib does once a done flag was returned); actions are passed as
+    Python floats so that the arithmetic stays float64 under NumPy >= 2 scalar promotion."""
+
+    def __init__(self, num_agents, seed, env_id, contract=True, null_prob=0.0):
+        install()
+        from utils.env_creator_functions import env_creator
+        import contract.contract_list as cl
+        self.n = num_agents
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        self.keys = ["a%d" % i for i in range(num_agents)]
+        self.base = env_creator("SelfDrive", dict(num_agents=num_agents))
+        self.wrapped = bool(contract)
+        if contract:
+            c = cl.SelfdriveContractDistprop(num_agents)
+            self.env = env_creator("ContractWrapperSubgame", dict(num_agents=num_agents, base_env=self.base, contract=c,
+                                                                  convolutional=False, null_prob=null_prob))
+            orig = c.compute_transfer
+
+            def capture(obs, acts, rews, params, infos=None):
+                self._base_rew = dict(rews)
+                tr = orig(obs, acts, rews, params, infos)
+                self._transfers = dict(tr)
+                return tr
+            c.compute_transfer = capture
+        else:
+            self.env = self.base
+        self.t = 0
+
+    def _obs(self, obs):
+        D = 2 * (self.n + 1) + 3
+        out = np.full((self.n, D + (2 if self.wrapped else 0)), np.nan)
+        for i, k in enumerate(self.keys):
+            if k in obs:
+                out[i] = np.asarray(obs[k], dtype=np.float64)
+        return out
+
+    def reset(self):
+        self.episode += 1
+        self.t = 0
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        out = {"obs": self._obs(obs)}
+        if self.wrapped:
+            out["theta"] = np.float64(self.env.params["a0"][0])
+        return out
+
+    def step(self, actions):
+        acting = [k for k in self.keys if not self.base.agent_dones[k]]
+        acts = {k: [float(np.float32(actions[int(k[1:])]))] for k in acting}
+        self.t += 1
+        with active(self.ctx):
+            self.ctx.begin(self.episode, self.t)
+            obs, rew, done, info = self.env.step(acts)
+        n = self.n
+        out = {"obs": self._obs(obs), "active": np.array([k in acts for k in self.keys], dtype=np.uint8),
+               "rew": np.array([rew.get(k, 0.0) for k in self.keys], dtype=np.float64),
+               "done": np.array([done[k] for k in self.keys] + [done["__all__"]], dtype=np.uint8),
+               "just_passed": np.array([bool(info[k]["just_passed"]) if k in info else False for k in self.keys], dtype=np.uint8),
+               "ambulance_rank": np.float64(info[acting[0]]["ambulance_rank"]),
+               "ambulance_dist_to_front": np.float64(info[acting[0]]["ambulance_dist_to_front"]),
+               "pos": np.array([self.base.agent_positions[k] for k in self.keys], dtype=np.float64),
+               "vel": np.array([self.base.agent_vels[k] for k in self.keys], dtype=np.float64),
+               "metric_transfers": np.float64(self.base.metrics["transfers"])}
+        if self.wrapped:
+            out["base_rew"] = np.array([self._base_rew.get(k, 0.0) for k in self.keys], dtype=np.float64)
+            tr = np.zeros(n)
+            for i, k in enumerate(self.keys):
+                v = self._transfers.get(k, 0)
+                tr[i] = v[0] if isinstance(v, tuple) else v
+            out["transfers"] = tr
+        return out

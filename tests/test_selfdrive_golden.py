@@ -1,0 +1,97 @@
+"""SelfAcceleratingCarEnv + SelfdriveContractDistprop (self_driving_car_accelerate.py:49-250,
+contract_list.py:66-102): the reference's golden episodes (tests/golden/selfdrive_*.npz) replayed through the C
+oracle on CPU and through the CUDA path on GPU.  Everything is float64 and compared bit-exactly (the north star's
+fp32 tolerance is not needed: the <= 8-car kinematics run in fp64 on the device)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+NAMES = gu.fixture_names("selfdrive_")
+
+
+def test_selfdrive_fixtures_present():
+    assert len(NAMES) >= 5
+
+
+class _OracleCar:
+    def __init__(self, oracle_mod, fx):
+        self.o = oracle_mod.CarOracle(1, int(fx["n"]), contract=bool(fx["contract"]), seed=int(fx["seed"]),
+                                      first_env_id=int(fx["env_id"]))
+
+    def reset(self):
+        obs = self.o.reset()[0]
+        return obs, self.o.get_state()["theta"][0]
+
+    def step(self, a):
+        r = self.o.step(np.asarray(a)[None])
+        st = self.o.get_state()
+        out = {k: v[0] for k, v in r.items()}
+        out.update(pos=st["pos"][0], vel=st["vel"][0], metric_transfers=st["transfers"][0])
+        return out
+
+
+class _CudaCar:
+    def __init__(self, fx, E=5, index=3):
+        from contracts_b200.selfdrive import BatchedCarEnv
+        self.i = index
+        self.env = BatchedCarEnv(E, int(fx["n"]), contract="SelfdriveContractDistprop" if bool(fx["contract"]) else None,
+                                 seed=int(fx["seed"]), first_env_id=(int(fx["env_id"]) - index) & 0xFFFFFFFF)
+
+    def reset(self):
+        obs = self.env.reset()[self.i].cpu().numpy()
+        return obs, self.env.get_state()["theta"][self.i].item()
+
+    def step(self, a):
+        import torch
+        acts = torch.zeros((self.env.E, self.env.n), dtype=torch.float32)
+        acts[:] = torch.as_tensor(np.asarray(a, dtype=np.float32))
+        obs, rew, done, info = self.env.step(acts.cuda())
+        st = self.env.get_state()
+        i = self.i
+        return {"obs": obs[i].cpu().numpy(), "rew": rew[i].cpu().numpy(), "base_rew": self.env.base_rew[i].cpu().numpy(),
+                "transfers": self.env.transfers[i].cpu().numpy(), "info": info[i].cpu().numpy(),
+                "done": done[i].cpu().numpy(), "pos": st["pos"][i].cpu().numpy(), "vel": st["vel"][i].cpu().numpy(),
+                "metric_transfers": st["transfers"][i].item()}
+
+
+def replay(backend, fx):
+    n = int(fx["n"])
+    wrapped = bool(fx["contract"])
+    D = 2 * (n + 1) + 3
+    for ep in range(fx["actions"].shape[0]):
+        obs, theta = backend.reset()
+        ctx = "reset ep %d" % ep
+        gu.assert_same("reset obs", obs, fx["reset_obs"][ep][:, :D], ctx)
+        if wrapped:
+            gu.assert_same("theta", theta, fx["reset_theta"][ep], ctx)
+            gu.assert_same("obs theta", fx["reset_obs"][ep][:, D], np.full(n, theta), ctx)
+        for t in range(int(fx["length"][ep])):
+            ctx = "ep %d step %d" % (ep, t)
+            o = backend.step(fx["actions"][ep, t])
+            act = fx["active"][ep, t].astype(bool)
+            gu.assert_same("active", o["info"][:, 1], fx["active"][ep, t], ctx)
+            gu.assert_same("obs", o["obs"][act], fx["obs"][ep, t][act][:, :D], ctx)
+            gu.assert_same("rew", o["rew"][act], fx["rew"][ep, t][act], ctx)
+            gu.assert_same("done", o["done"], fx["done"][ep, t], ctx)
+            gu.assert_same("just_passed", o["info"][:, 0], fx["just_passed"][ep, t], ctx)
+            first = int(np.argmax(act))
+            gu.assert_same("ambulance_rank", o["info"][first, 2], fx["ambulance_rank"][ep, t], ctx)
+            gu.assert_same("ambulance_dist_to_front", o["info"][first, 3], fx["ambulance_dist_to_front"][ep, t], ctx)
+            gu.assert_same("pos", o["pos"], fx["pos"][ep, t], ctx)
+            gu.assert_same("vel", o["vel"], fx["vel"][ep, t], ctx)
+            if wrapped:
+                gu.assert_same("base_rew", o["base_rew"][act], fx["base_rew"][ep, t][act], ctx)
+                gu.assert_same("transfers", o["transfers"], fx["transfers"][ep, t], ctx)
+                gu.assert_same("metric transfers", o["metric_transfers"], fx["metric_transfers"][ep, t], ctx)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_selfdrive_matches_reference(oracle_lib, name):
+    replay(_OracleCar(oracle_lib, gu.load(name)), gu.load(name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_selfdrive_matches_reference(name):
+    replay(_CudaCar(gu.load(name)), gu.load(name))
