@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
 
-SSD_ABI_VERSION = 1
+SSD_ABI_VERSION = 2
 ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "selfdrive": 4}
 CONTRACT_KIND = {None: 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2,
                  "SelfdriveContractDistprop": 3}
@@ -29,7 +29,7 @@ class ssd_config(ctypes.Structure):
         ("ascii_map", ctypes.c_char_p), ("horizon", ctypes.c_int32), ("contract_kind", ctypes.c_int32),
         ("theta_low", ctypes.c_double), ("theta_high", ctypes.c_double), ("null_prob", ctypes.c_double),
         ("seed", ctypes.c_uint32), ("first_env_id", ctypes.c_uint32), ("device", ctypes.c_int32),
-        ("flags", ctypes.c_int32),
+        ("flags", ctypes.c_int32), ("env_params", ctypes.c_double * 8),
     ]
 
 
@@ -41,11 +41,17 @@ class ssd_step_io(ctypes.Structure):
     ]
 
 
+class ssd_selfdrive_io(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("actions_dev", "obs_dev", "rew_dev", "base_rew_dev", "transfers_dev",
+                                               "info_dev", "done_dev")]
+
+
 EXPORTS = [
     "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_last_error", "ssd_reset", "ssd_step",
     "ssd_set_contract_params", "ssd_negotiate", "ssd_get_state", "ssd_set_state", "ssd_get_metrics",
     "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
-    "ssd_kernel_launches",
+    "ssd_kernel_launches", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
+    "ssd_selfdrive_random_actions",
 ]
 
 _LIB = None
@@ -77,6 +83,10 @@ def load():
     L.ssd_random_actions.argtypes = [vp, u32, i32, vp, vp]
     L.ssd_philox4x32_10.argtypes = [vp, vp, vp]
     L.ssd_philox4x32_10.restype = None
+    L.ssd_selfdrive_reset.argtypes = [vp, vp, vp, vp]
+    L.ssd_selfdrive_step.argtypes = [vp, ctypes.POINTER(ssd_selfdrive_io), vp]
+    L.ssd_selfdrive_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ssd_selfdrive_random_actions.argtypes = [vp, u32, ctypes.c_float, ctypes.c_float, vp, vp]
     L.ssd_feature_dim.argtypes = [vp]
     L.ssd_state_bytes_per_env.argtypes = [vp]
     L.ssd_state_bytes_per_env.restype = i64

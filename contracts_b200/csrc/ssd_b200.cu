@@ -15,6 +15,7 @@
 
 #include "../../include/ssd_b200.h"
 #include "ssd_grid.cuh"
+#include "ssd_selfdrive.cuh"
 
 static thread_local char g_create_error[512] = "";
 
@@ -22,6 +23,7 @@ struct ssd_handle {
     ssd_config cfg;
     std::string ascii;
     GridParams gp;
+    CarParams cp;
     int grid_blocks;
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
@@ -226,6 +228,43 @@ static int setup_grid(ssd_handle* h)
 }
 
 // ---------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_zalloc(ssd_handle* h, size_t count, T** out)
+{
+    void* d = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
+    h->dev_allocs.push_back(d);
+    CUDA_TRY(h, cudaMemset(d, 0, (count ? count : 1) * sizeof(T)));
+    *out = reinterpret_cast<T*>(d);
+    return SSD_OK;
+}
+
+static int setup_selfdrive(ssd_handle* h)
+{
+    const ssd_config& c = h->cfg;
+    CarParams& p = h->cp;
+    memset(&p, 0, sizeof(p));
+    p.E = c.num_envs; p.n = c.num_agents; p.D = 2 * (c.num_agents + 1) + 3; p.contract = c.contract_kind;
+    p.low_bound = c.env_params[0]; p.high_bound = c.env_params[1]; p.start_vel = c.env_params[2]; p.start_vel_amb = c.env_params[3];
+    if (!(p.low_bound < p.high_bound)) return fail(h, SSD_EINVAL, "selfdrive: env_params must hold low_bound < high_bound");
+    p.theta_low = c.theta_low; p.theta_high = c.theta_high; p.null_prob = c.null_prob;
+    p.seed = c.seed; p.first_env_id = c.first_env_id;
+    const size_t E = (size_t)p.E;
+    int rc;
+    if ((rc = dev_zalloc(h, E * p.n, &p.pos))) return rc;
+    if ((rc = dev_zalloc(h, E * p.n, &p.vel))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.theta))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.m_transfers))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.dist_front))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.crossed))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.meta))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.t))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.episode))) return rc;
+    h->grid_blocks = (p.E + CAR_THREADS - 1) / CAR_THREADS;
+    return SSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // small utility kernels
 __global__ void get_state_kernel(GridParams p, uint8_t* map, int32_t* pos, int32_t* ori, int32_t* t, double* theta)
 {
@@ -376,13 +415,14 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     if (cfg->abi_version != SSD_ABI_VERSION) return fail(nullptr, SSD_EINVAL, "abi_version %d != %d", cfg->abi_version, SSD_ABI_VERSION);
     if (cfg->num_envs < 1) return fail(nullptr, SSD_EINVAL, "num_envs must be >= 1");
     if (cfg->num_agents < 1 || cfg->num_agents > SSD_MAX_AGENTS) return fail(nullptr, SSD_EINVAL, "num_agents must be in [1, %d]", SSD_MAX_AGENTS);
-    if (cfg->env_kind != SSD_ENV_CLEANUP && cfg->env_kind != SSD_ENV_HARVEST)
+    if (cfg->env_kind != SSD_ENV_CLEANUP && cfg->env_kind != SSD_ENV_HARVEST && cfg->env_kind != SSD_ENV_SELFDRIVE)
         return fail(nullptr, SSD_EUNSUPPORTED, "env_kind %d not supported by this build", cfg->env_kind);
     if (cfg->contract_kind != SSD_CONTRACT_NONE &&
         !((cfg->env_kind == SSD_ENV_CLEANUP && cfg->contract_kind == SSD_CONTRACT_CLEANUP) ||
-          (cfg->env_kind == SSD_ENV_HARVEST && cfg->contract_kind == SSD_CONTRACT_HARVEST_LOCAL)))
+          (cfg->env_kind == SSD_ENV_HARVEST && cfg->contract_kind == SSD_CONTRACT_HARVEST_LOCAL) ||
+          (cfg->env_kind == SSD_ENV_SELFDRIVE && cfg->contract_kind == SSD_CONTRACT_SELFDRIVE_DISTPROP)))
         return fail(nullptr, SSD_EINVAL, "contract_kind %d does not apply to env_kind %d", cfg->contract_kind, cfg->env_kind);
-    if (cfg->contract_kind != SSD_CONTRACT_NONE && cfg->num_agents < 2)
+    if (cfg->contract_kind != SSD_CONTRACT_NONE && cfg->num_agents < 2 && cfg->env_kind != SSD_ENV_SELFDRIVE)
         return fail(nullptr, SSD_EINVAL, "contracts need at least 2 agents");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -396,7 +436,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     h->err[0] = 0;
     if (cfg->ascii_map) h->ascii.assign(cfg->ascii_map, (size_t)cfg->map_h * cfg->map_w);
     h->cfg.ascii_map = h->ascii.c_str();
-    int rc = setup_grid(h);
+    int rc = cfg->env_kind == SSD_ENV_SELFDRIVE ? setup_selfdrive(h) : setup_grid(h);
     if (rc != SSD_OK) {
         snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
         ssd_destroy(h);
@@ -422,9 +462,16 @@ static int check_launch(ssd_handle* h, const char* what)
     return SSD_OK;
 }
 
+#define REQUIRE_GRID(h) \
+    if ((h)->cfg.env_kind != SSD_ENV_CLEANUP && (h)->cfg.env_kind != SSD_ENV_HARVEST) \
+        return fail(h, SSD_EINVAL, "%s: handle is not a gridworld (env_kind %d)", __func__, (h)->cfg.env_kind)
+#define REQUIRE_CAR(h) \
+    if ((h)->cfg.env_kind != SSD_ENV_SELFDRIVE) return fail(h, SSD_EINVAL, "%s: handle is not a selfdrive env", __func__)
+
 int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t obs_env_stride, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     const GridParams& p = h->gp;
     long long stride = obs_env_stride ? obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
     if (stride < (long long)p.n * SSD_OBS_BYTES) return fail(h, SSD_EINVAL, "obs_env_stride too small");
@@ -439,6 +486,7 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
 int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
 {
     if (!h || !io) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     const GridParams& p = h->gp;
     StepIO k;
@@ -460,13 +508,17 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
 int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream)
 {
     if (!h || !theta_dev) return SSD_EINVAL;
-    SMALL_LAUNCH(set_theta_kernel, theta_dev);
+    if (h->cfg.env_kind == SSD_ENV_SELFDRIVE)
+        car_set_theta_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, theta_dev);
+    else
+        SMALL_LAUNCH(set_theta_kernel, theta_dev);
     return check_launch(h, "set_contract_params");
 }
 
 int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev, void* stream)
 {
     if (!h || !proposals_dev || !accept_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(negotiate_kernel, proposals_dev, accept_dev, decision_dev);
     return check_launch(h, "negotiate");
 }
@@ -474,6 +526,7 @@ int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* acce
 int ssd_get_state(ssd_handle* h, uint8_t* map_dev, int32_t* pos_dev, int32_t* ori_dev, int32_t* t_dev, double* theta_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(get_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
     return check_launch(h, "get_state");
 }
@@ -482,6 +535,7 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
                   const double* theta_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(set_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
     return check_launch(h, "set_state");
 }
@@ -489,6 +543,7 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
 int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 {
     if (!h || !out_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(get_metrics_kernel, out_dev);
     return check_launch(h, "get_metrics");
 }
@@ -496,12 +551,54 @@ int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream)
 {
     if (!h || !actions_dev || num_actions < 1 || num_actions > 255) return SSD_EINVAL;
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(random_actions_kernel, step_index, num_actions, actions_dev);
     return check_launch(h, "random_actions");
 }
 
-int ssd_feature_dim(const ssd_handle* h) { return h ? h->gp.F : 0; }
-int64_t ssd_state_bytes_per_env(const ssd_handle* h) { return h ? h->gp.rec_stride : 0; }
+// ---- selfdrive -------------------------------------------------------------------------------------
+int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_CAR(h);
+    car_reset_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, mask_dev, obs_dev);
+    return check_launch(h, "selfdrive_reset");
+}
+
+int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream)
+{
+    if (!h || !io) return SSD_EINVAL;
+    REQUIRE_CAR(h);
+    if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
+    if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 31)) return fail(h, SSD_EINVAL, "info_dev must be 32-byte aligned");
+    CarIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev };
+    car_step_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, k);
+    return check_launch(h, "selfdrive_step");
+}
+
+int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, double* theta_dev, double* transfers_dev,
+                            int32_t* t_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_CAR(h);
+    car_get_state_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, pos_dev, vel_dev, theta_dev, transfers_dev, t_dev);
+    return check_launch(h, "selfdrive_get_state");
+}
+
+int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, float hi, float* actions_dev, void* stream)
+{
+    if (!h || !actions_dev) return SSD_EINVAL;
+    REQUIRE_CAR(h);
+    car_random_actions_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, step_index, lo, hi, actions_dev);
+    return check_launch(h, "selfdrive_random_actions");
+}
+
+int ssd_feature_dim(const ssd_handle* h) { return !h ? 0 : (h->cfg.env_kind == SSD_ENV_SELFDRIVE ? h->cp.D : h->gp.F); }
+int64_t ssd_state_bytes_per_env(const ssd_handle* h)
+{
+    if (!h) return 0;
+    return h->cfg.env_kind == SSD_ENV_SELFDRIVE ? (int64_t)(16 * h->cp.n + 44) : (int64_t)h->gp.rec_stride;
+}
 int64_t ssd_kernel_launches(const ssd_handle* h) { return h ? h->launches : 0; }
 
 }  // extern "C"

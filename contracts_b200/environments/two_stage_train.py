@@ -10,7 +10,7 @@ import torch
 
 from .. import spaces
 
-_FUSED = ("CleanupContract", "HarvestFeaturemodLocalContract")
+_FUSED = ("CleanupContract", "HarvestFeaturemodLocalContract", "SelfdriveContractDistprop")
 
 
 class SeparateContractEnv:
@@ -53,6 +53,8 @@ class SeparateContractEnv:
     def _with_contract(self, obs, state_of):
         out = {}
         for k in self.agent_ids:
+            if k not in obs:            # selfdrive: cars that are done no longer act / observe
+                continue
             tail = np.array([state_of(k)])
             if self.convolutional:
                 out[k] = obs[k]

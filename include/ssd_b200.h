@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SSD_ABI_VERSION 1
+#define SSD_ABI_VERSION 2
 
 /* env_kind: which reference class the handle simulates */
 #define SSD_ENV_CLEANUP 0           /* environments/cleanup_new.py  CleanupEnv   ('CleanupNew') */
@@ -75,6 +75,8 @@ typedef struct ssd_config {
     uint32_t first_env_id;    /* global id of env 0 (Philox key word 1 = first_env_id + i) */
     int32_t device;           /* CUDA device ordinal */
     int32_t flags;            /* reserved, 0 */
+    double env_params[8];     /* selfdrive: low_bound, high_bound, start_vel, start_vel_ambulance
+                                 (SelfAcceleratingCarEnv.__init__, self_driving_car_accelerate.py:19); else unused */
 } ssd_config;
 
 /* Buffers of one step.  Gridworld / feature envs: actions are uint8 [E][n] action ids
@@ -134,6 +136,29 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
  *   [apples_eaten, low_density_eaten, raw_env_rewards, transfers, dirt_cleaned, err_flags, 0, 0,
  *    agent_a[8], agent_b[8], sum_raw[8], tsum_raw[8], sum_transferred[8], tsum_transferred[8]] */
 int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream);
+
+/* --- SelfAcceleratingCarEnv (env_kind SSD_ENV_SELFDRIVE) -------------------------------------------------
+ * environments/self_driving_car_accelerate.py reset :49-79 / step :151-250 (collision_on=False), optionally with
+ * SelfdriveContractDistprop (contract/contract_list.py:66-102) + SeparateContractSubgameStage
+ * (two_stage_train.py:62-121,159-187) fused.  Agents that are done stop acting (RLlib semantics).  All values are
+ * float64; D = 2 (n + 1) + 3 observation elements per car (ssd_feature_dim returns D). */
+typedef struct ssd_selfdrive_io {
+    const float* actions_dev;   /* [E][n] accelerations */
+    double* obs_dev;            /* [E][n][D]  (rows of cars that did not act this step are still written) */
+    double* rew_dev;            /* [E][n] after transfers; 0 for cars that did not act */
+    double* base_rew_dev;       /* [E][n] nullable */
+    double* transfers_dev;      /* [E][n] nullable: value of each car's transfer tuple */
+    double* info_dev;           /* [E][n][4] nullable: just_passed, acted, ambulance_rank, ambulance_dist_to_front
+                                   (last two in the row of the first acting car, like infos[key_lst[0]]) */
+    uint8_t* done_dev;          /* [E][n+1] nullable: per-car dones, then '__all__' */
+} ssd_selfdrive_io;
+int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
+int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream);
+/* pos/vel double [E][n], theta / transfers metric double [E], t int32 [E]; NULL pointers are skipped */
+int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, double* theta_dev, double* transfers_dev,
+                            int32_t* t_dev, void* stream);
+/* uniform float32 accelerations in [lo, hi) for benchmark rollouts, [E][n] */
+int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, float hi, float* actions_dev, void* stream);
 
 /* --- utilities ------------------------------------------------------------------------------------------ */
 /* uniform random action ids in [0, num_actions) for benchmark rollouts, uint8 [E][n];

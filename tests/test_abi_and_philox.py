@@ -39,14 +39,15 @@ def test_config_struct_matches_header():
     """ctypes mirror of ssd_config / ssd_step_io has the field order of the header."""
     from contracts_b200 import _lib
     text = open(os.path.join(ROOT, "include", "ssd_b200.h")).read()
-    for struct, cls in (("ssd_config", _lib.ssd_config), ("ssd_step_io", _lib.ssd_step_io)):
+    for struct, cls in (("ssd_config", _lib.ssd_config), ("ssd_step_io", _lib.ssd_step_io),
+                        ("ssd_selfdrive_io", _lib.ssd_selfdrive_io)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
         for decl in body.split(";"):
             decl = decl.strip()
             if decl:
-                fields += [re.sub(r"[\*\s]", "", f.split()[-1]) for f in decl.split(",")]
+                fields += [re.sub(r"\[.*\]|[\*\s]", "", f.split()[-1]) for f in decl.split(",")]
         assert fields == [f[0] for f in cls._fields_], struct
 
 

@@ -95,3 +95,66 @@ def test_oracle_selfdrive_matches_reference(oracle_lib, name):
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_selfdrive_matches_reference(name):
     replay(_CudaCar(gu.load(name)), gu.load(name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in NAMES if "nocontract" not in n and n != "selfdrive_n1"])
+def test_dropin_selfdrive_dict_api(name):
+    """env_creator('SelfDrive') + ContractWrapperSubgame(SelfdriveContractDistprop), the reference's flat obs layout."""
+    from contracts_b200.contract import contract_list
+    from contracts_b200.utils.env_creator_functions import env_creator, get_base_env_tag
+    fx = gu.load(name)
+    n = int(fx["n"])
+    base = env_creator(get_base_env_tag({"environment": "selfdrive"}), dict(num_agents=n, seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+    env = env_creator("ContractWrapperSubgame", dict(num_agents=n, base_env=base, contract=contract_list.SelfdriveContractDistprop(n),
+                                                     convolutional=False))
+    keys = ["a%d" % i for i in range(n)]
+    assert env.observation_space.shape == (2 * (n + 1) + 3 + 2,)
+    for ep in range(fx["actions"].shape[0]):
+        obs = env.reset()
+        gu.assert_same("reset obs", np.stack([obs[k] for k in keys]), fx["reset_obs"][ep], "ep %d" % ep)
+        for t in range(int(fx["length"][ep])):
+            ctx = "ep %d step %d" % (ep, t)
+            acting = [k for i, k in enumerate(keys) if fx["active"][ep, t][i]]
+            obs, rew, done, info = env.step({k: np.array([fx["actions"][ep, t][int(k[1:])]]) for k in acting})
+            assert sorted(obs.keys()) == acting and sorted(rew.keys()) == acting, ctx
+            for k in acting:
+                i = int(k[1:])
+                gu.assert_same("obs", obs[k], fx["obs"][ep, t][i], ctx)
+                gu.assert_same("rew", rew[k], fx["rew"][ep, t][i], ctx)
+                assert info[k]["just_passed"] == bool(fx["just_passed"][ep, t][i]), ctx
+            gu.assert_same("done", [done[k] for k in keys] + [done["__all__"]], fx["done"][ep, t], ctx)
+            gu.assert_same("ambulance_rank", info[acting[0]]["ambulance_rank"], fx["ambulance_rank"][ep, t], ctx)
+            gu.assert_same("metric", base.metrics["transfers"], fx["metric_transfers"][ep, t], ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,E,contract", [(8, 4099, True), (3, 515, True), (5, 130, False)])
+def test_cuda_selfdrive_rollout_matches_oracle(oracle_lib, n, E, contract):
+    """Random rollouts, every output, bit-exact, incl. masked re-resets of finished envs."""
+    import torch
+    from contracts_b200.selfdrive import BatchedCarEnv
+    env = BatchedCarEnv(E, n, contract="SelfdriveContractDistprop" if contract else None, seed=7, first_env_id=123)
+    orc = oracle_lib.CarOracle(E, n, contract=contract, seed=7, first_env_id=123)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    rng = np.random.RandomState(n)
+    for t in range(260):
+        a = (rng.uniform(-0.7, 1.0, size=(E, n)) * 0.15).astype(np.float32)
+        o = orc.step(a)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ctx = "step %d" % t
+        gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+        gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+        gu.assert_same("base_rew", env.base_rew.cpu().numpy(), o["base_rew"], ctx)
+        gu.assert_same("transfers", env.transfers.cpu().numpy(), o["transfers"], ctx)
+        gu.assert_same("info", info.cpu().numpy(), o["info"], ctx)
+        gu.assert_same("done", done.cpu().numpy(), o["done"], ctx)
+        fin = o["done"][:, -1].astype(bool)
+        if t % 9 == 0 and fin.any():
+            mask = fin.astype(np.uint8)
+            r1 = env.reset(torch.from_numpy(mask).cuda()).cpu().numpy()
+            r2 = orc.reset(mask)
+            gu.assert_same("masked reset obs", r1[fin], r2[fin], ctx)
+    so, sc = orc.get_state(), env.get_state()
+    for k in ("pos", "vel", "theta", "transfers", "t"):
+        gu.assert_same(k, sc[k].cpu().numpy(), so[k], "end")
