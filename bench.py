@@ -36,6 +36,17 @@ SEED = 73907                       # reference seed multiplier (runner.py:130)
 WORKLOAD = "cleanup_new n=8 CleanupContract + negotiation prologue, horizon 1000, random actions"
 
 
+def ncu_traffic(envs, agents):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture (same workload and size), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if t["envs"] == envs and t["agents"] == agents:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,7 +308,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "grid_step_kernel<cleanup>",
+                         "traffic": ncu_traffic(E, n), "alg_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * E * n,
+                         "peak_source": peak_src, "kernel": "grid_step_kernel<cleanup>",
                          "kernel_ms": step_ms, "alg_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP},
         }
         if state["stats"] is not None:
