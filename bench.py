@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--envs", type=int, default=131072, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph-steps", type=int, default=50, help="env steps per captured CUDA graph (1 = no graphs)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -169,6 +170,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     E, n = args.envs, N_AGENTS
     K, W = args.steps, max(args.warmup, 3)
@@ -216,17 +219,81 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- warm-up, then the timed device-resident run -------------------------------------------
-    for _ in range(W):
+    # The inner loop (action generation + step) is launch-bound from Python, so GRAPH_STEPS consecutive steps are
+    # captured once in a CUDA graph and replayed; episode boundaries (reset + negotiation prologue + statistics
+    # all-gather) stay outside the graph.  Fresh actions every replay come from the handle's device step counter.
+    G = args.graph_steps
+    while HORIZON % G:
+        G -= 1
+    for _ in range(max(W, 3)):
         one_step()
+    barrier()
+    graph = None
+    if G > 1:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                                   # warm the capture stream
+                env.random_actions(None, N_ACTIONS, out=actions)
+                env.step(actions, extras=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(G):
+                env.random_actions(None, N_ACTIONS, out=actions)
+                env.step(actions, extras=False)
+        torch.cuda.synchronize(dev)
+    state["t"] = 0                                               # start the timed region at an episode boundary
+
+    def run_steps(k):
+        """k env steps (k a multiple of G when graphs are on), crossing episode boundaries as needed."""
+        done = 0
+        launches = 0
+        while done < k:
+            if state["t"] == 0:
+                new_episode()
+            if graph is not None:
+                graph.replay()
+                m, launches = G, launches + 3 * G
+            else:
+                env.random_actions(state["global_step"], N_ACTIONS, out=actions)
+                env.step(actions, extras=False)
+                m, launches = 1, launches + 2
+            done += m
+            state["t"] += m
+            state["global_step"] += m
+            if state["t"] >= HORIZON:
+                state["stats"] = end_episode()
+                state["t"] = 0
+        return launches
+
+    K = max(G, (K // G) * G)
+    run_steps(max(G, (W // G) * G))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = env.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ev0.record()
-    for k in range(K):
+    graph_launches = run_steps(K)
+    ev1.record()
+    barrier()
+    launches = (env.kernel_launches - l0) + (graph_launches if graph is not None else 0)
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = world * E * n * K / (ms_total * 1e-3)
+
+    # ---- the step kernel alone (roofline): CUDA events around each ssd_step of an un-graphed stretch -------
+    Kk = HORIZON                     # one whole episode: the cost of a step varies along it (spawning starts late)
+    state["t"] = 0
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    for k in range(Kk):
         if state["t"] == 0:
             new_episode()
         env.random_actions(state["global_step"], N_ACTIONS, out=actions)
@@ -238,17 +305,8 @@ def main():
         if state["t"] == HORIZON:
             state["stats"] = end_episode()
             state["t"] = 0
-    ev1.record()
     barrier()
-    launches = env.kernel_launches - l0
-    ms_total = ev0.elapsed_time(ev1)
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    clocks = sampler.stop() if rank == 0 else None
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    value = world * E * n * K / (ms_total * 1e-3)
 
     # ---- e2e: host buffers in, host results out, sync every step ----------------------------------
     Ke = min(args.e2e_steps, K)
@@ -300,7 +358,8 @@ def main():
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents": n, "horizon": HORIZON,
                        "l2": "working set %.0f MB/step (obs %.0f MB + state) exceeds the 126 MB L2" % (
                            (E * (n * 675 + 2 * env.state_bytes_per_env)) / 1e6, E * n * 675 / 1e6),
-                       "parallelism": "env batch sharded over %d GPU(s), no collective on the step path" % world},
+                       "parallelism": "env batch sharded over %d GPU(s), no collective on the step path" % world,
+                       "cuda_graph_steps": G},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * n,
                     "d2h_bytes_per_step": E * n * 8 + E, "steps": Ke,
                     "note": "pinned host actions in, rewards+dones out, host sync every step; observations stay in the device batch tensor"},

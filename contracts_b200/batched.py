@@ -127,6 +127,9 @@ class BatchedGridEnv:
         return self.obs, self.rew, self.done, self.info
 
     def random_actions(self, step_index, num_actions, out=None):
+        """Uniform random actions; step_index=None uses the handle's device-side counter (CUDA-graph friendly)."""
+        if step_index is None:
+            step_index = 0xFFFFFFFF
         if out is None:
             out = torch.empty((self.E, self.n), dtype=torch.uint8, device=self.device)
         _lib.check(self._h, self.lib.ssd_random_actions(self._h, int(step_index), int(num_actions), _ptr(out), self._stream()))

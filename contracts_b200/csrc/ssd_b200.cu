@@ -25,6 +25,7 @@ struct ssd_handle {
     GridParams gp;
     CarParams cp;
     int grid_blocks;
+    uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
     char err[512];
@@ -382,10 +383,15 @@ __global__ void negotiate_kernel(GridParams p, const double* proposals, const do
     if (decision) decision[env] = dec ? 1 : 0;
 }
 
-__global__ void random_actions_kernel(GridParams p, uint32_t step_index, int num_actions, uint8_t* actions)
+// step_index == SSD_STEP_AUTO: take the index from the handle's device counter (bumped by a follow-up
+// one-thread kernel), so that a captured CUDA graph draws fresh actions at every replay
+__global__ void counter_bump_kernel(uint32_t* counter) { *counter += 1u; }
+
+__global__ void random_actions_kernel(GridParams p, uint32_t step_index, const uint32_t* counter, int num_actions, uint8_t* actions)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
+    if (counter) step_index = *counter;
     const uint32_t env_id = p.first_env_id + (uint32_t)env;
     for (int b = 0; b * 4 < p.n; b++) {
         Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
@@ -437,6 +443,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     if (cfg->ascii_map) h->ascii.assign(cfg->ascii_map, (size_t)cfg->map_h * cfg->map_w);
     h->cfg.ascii_map = h->ascii.c_str();
     int rc = cfg->env_kind == SSD_ENV_SELFDRIVE ? setup_selfdrive(h) : setup_grid(h);
+    if (rc == SSD_OK) rc = dev_zalloc(h, 1, &h->d_counter);
     if (rc != SSD_OK) {
         snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
         ssd_destroy(h);
@@ -552,7 +559,9 @@ int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, 
 {
     if (!h || !actions_dev || num_actions < 1 || num_actions > 255) return SSD_EINVAL;
     REQUIRE_GRID(h);
-    SMALL_LAUNCH(random_actions_kernel, step_index, num_actions, actions_dev);
+    const bool autoidx = step_index == SSD_STEP_AUTO;
+    SMALL_LAUNCH(random_actions_kernel, step_index, autoidx ? h->d_counter : nullptr, num_actions, actions_dev);
+    if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "random_actions");
 }
 
@@ -589,7 +598,10 @@ int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, f
 {
     if (!h || !actions_dev) return SSD_EINVAL;
     REQUIRE_CAR(h);
-    car_random_actions_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, step_index, lo, hi, actions_dev);
+    const bool autoidx = step_index == SSD_STEP_AUTO;
+    car_random_actions_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, step_index, autoidx ? h->d_counter : nullptr,
+                                                                                         lo, hi, actions_dev);
+    if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "selfdrive_random_actions");
 }
 

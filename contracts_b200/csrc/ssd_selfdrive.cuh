@@ -268,10 +268,12 @@ __global__ void __launch_bounds__(CAR_THREADS) car_step_kernel(const CarParams p
     car_write_obs(p, s_pos, s_vel, io.obs, env - lane, lane, valid);
 }
 
-__global__ void car_random_actions_kernel(const CarParams p, uint32_t step_index, float lo, float hi, float* actions)
+__global__ void car_random_actions_kernel(const CarParams p, uint32_t step_index, const uint32_t* counter, float lo, float hi,
+                                          float* actions)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
+    if (counter) step_index = *counter;
     const uint32_t env_id = p.first_env_id + (uint32_t)env;
     for (int b = 0; b * 4 < p.n; b++) {
         Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);

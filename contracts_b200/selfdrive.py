@@ -83,6 +83,8 @@ class BatchedCarEnv:
         return self.obs, self.rew, self.done, self.info
 
     def random_actions(self, step_index, lo=-0.1, hi=0.1, out=None):
+        if step_index is None:
+            step_index = 0xFFFFFFFF
         if out is None:
             out = torch.empty((self.E, self.n), dtype=torch.float32, device=self.device)
         _lib.check(self._h, self.lib.ssd_selfdrive_random_actions(self._h, int(step_index), float(lo), float(hi), _ptr(out),

@@ -162,7 +162,10 @@ int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, f
 
 /* --- utilities ------------------------------------------------------------------------------------------ */
 /* uniform random action ids in [0, num_actions) for benchmark rollouts, uint8 [E][n];
- * drawn from Philox site 13 at counter `step_index` (no reference equivalent: RLlib's policy). */
+ * drawn from Philox site 13 at counter `step_index` (no reference equivalent: RLlib's policy).
+ * step_index == SSD_STEP_AUTO takes (and then bumps) a per-handle device counter instead, so the call can be
+ * captured in a CUDA graph and still draw fresh actions at every replay. */
+#define SSD_STEP_AUTO 0xFFFFFFFFu
 int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream);
 /* host-side Philox4x32-10 (so tests can pin the generator: KATs in tests/test_philox.py) */
 void ssd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
