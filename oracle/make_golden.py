@@ -212,9 +212,58 @@ def run_selfdrive(name):
     return res
 
 
+# name -> (kind, n, seed, env_id, contract, horizon, episodes, steps/episode, action ids, action probs)
+FEATURES_SCENARIOS = {
+    "features_cleanup_n8": ("cleanup", 8, 61, 5, True, 1000, 1, 400, 8, [.12, .12, .12, .12, .06, .06, .06, .34]),
+    "features_cleanup_n2_short": ("cleanup", 2, 62, 6, True, 60, 3, 60, 9, [.1, .1, .1, .1, .05, .05, .05, .4, .05]),
+    "features_harvest_n8": ("harvest", 8, 63, 7, True, 1000, 1, 400, 7, None),
+    "features_harvest_n4_short": ("harvest", 4, 64, 8, True, 50, 3, 50, 8, None),
+    "features_cleanup_n3_nocontract": ("cleanup", 3, 65, 9, False, 1000, 1, 200, 8, [.12, .12, .12, .12, .06, .06, .06, .34]),
+}
+
+
+def run_features(name):
+    from .ref_harness import RefFeatEnv
+    kind, n, seed, env_id, contract, horizon, episodes, steps, act_hi, act_p = FEATURES_SCENARIOS[name]
+    ref = RefFeatEnv(kind, n, seed, env_id, contract=contract, horizon=horizon)
+    rng = np.random.RandomState(sum(map(ord, name)))
+    keys = ("actions", "obs", "pos", "ori", "cells", "rew", "done", "info0", "info1", "base_rew", "transfers")
+    rec = {k: [] for k in keys}
+    rst = {k: [] for k in ("obs", "pos", "ori", "cells", "theta")}
+    metrics = []
+    for ep in range(episodes):
+        s0 = ref.reset()
+        for k in ("obs", "pos", "ori", "cells"):
+            rst[k].append(s0[k])
+        rst["theta"].append(s0.get("theta", np.float64(0.0)))
+        for k in keys:
+            rec[k].append([])
+        for t in range(steps):
+            a = rng.choice(act_hi, size=n, p=act_p).astype(np.int32)
+            o = ref.step(a)
+            rec["actions"][-1].append(a)
+            for k in keys[1:]:
+                rec[k][-1].append(o.get(k, np.zeros(n)) if k not in ("base_rew",) else o.get(k, o["rew"]))
+        metrics.append(ref.metrics())
+    out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon, "contract": contract,
+           "metric_keys": np.array(sorted(metrics[0].keys())),
+           "metrics": np.array([[m[k] for k in sorted(m.keys())] for m in metrics], dtype=np.float64)}
+    out.update({k: np.array(v) for k, v in rec.items()})
+    out.update({"reset_" + k: np.array(v) for k, v in rst.items()})
+    return out
+
+
 def main(names=None):
     os.makedirs(OUT, exist_ok=True)
-    for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS) + list(SELFDRIVE_SCENARIOS)):
+    for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS) + list(SELFDRIVE_SCENARIOS)
+                 + list(FEATURES_SCENARIOS)):
+        if name in FEATURES_SCENARIOS:
+            data = run_features(name)
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **data)
+            print("%-32s %7.1f KiB  steps=%s rewards=%.0f transfers=%.3f" % (name, os.path.getsize(path) / 1024, data["actions"].shape,
+                                                                             data["base_rew"].sum(), np.abs(data["transfers"]).sum()))
+            continue
         if name in SELFDRIVE_SCENARIOS:
             data = run_selfdrive(name)
             path = os.path.join(OUT, name + ".npz")

@@ -50,6 +50,14 @@ def lib():
         L.oracle_get_metrics.argtypes = [vp, vp]
         L.oracle_feature_dim.argtypes = [vp]
         L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
+        L.feat_oracle_create.restype = vp
+        L.feat_oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
+        L.feat_oracle_destroy.argtypes = [vp]
+        L.feat_oracle_dim.argtypes = [vp]
+        L.feat_oracle_reset.argtypes = [vp] * 4
+        L.feat_oracle_step.argtypes = [vp] * 8
+        L.feat_oracle_get_metrics.argtypes = [vp, vp]
+        L.feat_oracle_get_state.argtypes = [vp] * 6
         L.car_oracle_create.restype = vp
         L.car_oracle_create.argtypes = [i32, i32, i32, f64, f64, f64, f64, f64, f64, f64, u32, u32]
         L.car_oracle_destroy.argtypes = [vp]
@@ -197,3 +205,58 @@ class CarOracle:
     def set_theta(self, theta):
         th = np.ascontiguousarray(np.broadcast_to(np.asarray(theta, dtype=np.float64), (self.E,)))
         lib().car_oracle_set_theta(self._h, _p(th))
+
+
+class FeatOracle:
+    """E independent CleanupFeatures / HarvestFeatures envs (+ optional subgame contract wrapper)."""
+
+    def __init__(self, kind, num_envs, num_agents, ascii_map, horizon=1000, contract=None, theta_low=0.0,
+                 theta_high=None, null_prob=0.0, seed=73907, first_env_id=0):
+        self.kind = kind
+        self.E, self.n = int(num_envs), int(num_agents)
+        self.H, self.W = len(ascii_map), len(ascii_map[0])
+        if theta_high is None:
+            theta_high = float(np.float32(0.2)) if kind == "cleanup" else float(np.float32(10.0))
+        flat = "".join(ascii_map).encode("ascii")
+        self._h = lib().feat_oracle_create(KIND[kind], self.E, self.n, self.H, self.W, flat, int(horizon),
+                                           CONTRACT[contract], float(theta_low), float(theta_high), float(null_prob),
+                                           int(seed) & 0xFFFFFFFF, int(first_env_id))
+        if not self._h:
+            raise ValueError("feat_oracle_create failed (bad sizes / map)")
+        self.F = lib().feat_oracle_dim(self._h)
+        self.episode = np.full(self.E, -1, dtype=np.int64)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().feat_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        sel = np.ones(self.E, bool) if m is None else m.astype(bool)
+        self.episode[sel] += 1
+        ep = self.episode.astype(np.uint32)
+        obs = np.zeros((self.E, self.n, self.F))
+        lib().feat_oracle_reset(self._h, _p(m), _p(ep), _p(obs))
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.E, self.n)
+        E, n = self.E, self.n
+        out = {"obs": np.zeros((E, n, self.F)), "rew": np.zeros((E, n)), "base_rew": np.zeros((E, n)),
+               "transfers": np.zeros((E, n)), "info": np.zeros((E, n, 4), np.int32), "done": np.zeros(E, np.uint8)}
+        lib().feat_oracle_step(self._h, _p(a), _p(out["obs"]), _p(out["rew"]), _p(out["base_rew"]), _p(out["transfers"]),
+                               _p(out["info"]), _p(out["done"]))
+        return out
+
+    def metrics_raw(self):
+        out = np.zeros((self.E, 40))
+        lib().feat_oracle_get_metrics(self._h, _p(out))
+        return out
+
+    def get_state(self):
+        E, n = self.E, self.n
+        st = {"pos": np.zeros((E, n, 2), np.int32), "ori": np.zeros((E, n), np.int32),
+              "cells": np.zeros((E, self.H, self.W), np.uint8), "theta": np.zeros(E), "t": np.zeros(E, np.int32)}
+        lib().feat_oracle_get_state(self._h, _p(st["pos"]), _p(st["ori"]), _p(st["cells"]), _p(st["theta"]), _p(st["t"]))
+        return st

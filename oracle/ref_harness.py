@@ -474,3 +474,83 @@ class RefCarEnv:
                 tr[i] = v[0] if isinstance(v, tuple) else v
             out["transfers"] = tr
         return out
+
+
+class RefFeatEnv:
+    """The reference's CleanupFeatures / HarvestFeatures (+ SeparateContractSubgameStage) under RNG injection."""
+
+    def __init__(self, kind, num_agents, seed, env_id, contract=True, horizon=1000, null_prob=0.0):
+        install()
+        from utils.env_creator_functions import env_creator
+        import contract.contract_list as cl
+        self.kind, self.n = kind, num_agents
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        self.keys = ["a%d" % i for i in range(num_agents)]
+        with active(self.ctx):
+            self.ctx.begin(px.EPISODE_CONSTRUCT, 0)
+            self.base = env_creator("Cleanup" if kind == "cleanup" else "Harvest", dict(num_agents=num_agents, horizon=horizon))
+        self.wrapped = bool(contract)
+        if contract:
+            c = cl.CleanupContract(num_agents) if kind == "cleanup" else cl.HarvestFeaturemodLocalContract(num_agents)
+            self.env = env_creator("ContractWrapperSubgame", dict(num_agents=num_agents, base_env=self.base, contract=c,
+                                                                  convolutional=False, null_prob=null_prob))
+            orig = c.compute_transfer
+
+            def capture(obs, acts, rews, params, infos=None):
+                self._base_rew = dict(rews)
+                tr = orig(obs, acts, rews, params, infos)
+                self._transfers = dict(tr)
+                return tr
+            c.compute_transfer = capture
+        else:
+            self.env = self.base
+
+    def _cells(self):
+        b = self.base
+        cells = np.zeros((len(b.map), len(b.map[0])), dtype=np.uint8)
+        for r, c in b.current_apple_points:
+            cells[r, c] = 1
+        for r, c in getattr(b, "current_waste_points", []):
+            cells[r, c] = 2
+        return cells
+
+    def _snap(self, obs):
+        b = self.base
+        out = {"obs": np.stack([np.asarray(obs[k], dtype=np.float64) for k in self.keys]),
+               "pos": np.array([b.agent_pos[k] for k in self.keys], dtype=np.int32),
+               "ori": np.array([int(b.agent_orientation[k]) for k in self.keys], dtype=np.int32),
+               "cells": self._cells()}
+        return out
+
+    def reset(self):
+        self.episode += 1
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        out = self._snap(obs)
+        if self.wrapped:
+            out["theta"] = np.float64(self.env.params["a0"][0])
+        return out
+
+    def step(self, actions):
+        acts = {k: int(a) for k, a in zip(self.keys, actions)}
+        with active(self.ctx):
+            self.ctx.begin(self.episode, self.base.timesteps + 1)
+            obs, rew, done, info = self.env.step(acts)
+        out = self._snap(obs)
+        out["rew"] = np.array([rew[k] for k in self.keys], dtype=np.float64)
+        out["done"] = bool(done["__all__"])
+        if self.kind == "cleanup":
+            out["info0"] = np.array([info[k]["cleaned_squares"] for k in self.keys], dtype=np.int32)
+            out["info1"] = np.zeros(self.n, dtype=np.int32)
+        else:
+            out["info0"] = np.array([info[k]["eaten_apples"] for k in self.keys], dtype=np.int32)
+            out["info1"] = np.array([info[k]["eaten_close_apples"] for k in self.keys], dtype=np.int32)
+        if self.wrapped:
+            out["base_rew"] = np.array([self._base_rew[k] for k in self.keys], dtype=np.float64)
+            out["transfers"] = np.array([self._transfers[k] for k in self.keys], dtype=np.float64)
+        return out
+
+    def metrics(self):
+        return {k: float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v) for k, v in self.base.metrics.items()}

@@ -1,0 +1,130 @@
+"""CleanupFeatures / HarvestFeatures ('Cleanup' / 'Harvest' tags; cleanup_features.py:48-336,
+harvest_features.py:60-364) + contract wrapper: the reference's golden episodes
+(tests/golden/features_*.npz) replayed bit-exactly through the C oracle (CPU) and the CUDA path (GPU)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+NAMES = gu.fixture_names("features_")
+
+
+def test_features_fixtures_present():
+    assert len(NAMES) >= 5
+
+
+def _maps(kind):
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    return CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP
+
+
+def _metrics(kind, n, raw):
+    m = {"raw_env_rewards": raw[1], "transfers": raw[2]}
+    if kind == "cleanup":
+        m["dirt_cleaned"] = raw[0]
+    else:
+        m["total_apples_eaten"] = raw[3]
+        m["low_density_apples_eaten"] = raw[4]
+    return m
+
+
+class _Oracle:
+    def __init__(self, mod, fx):
+        kind = str(fx["kind"])
+        self.o = mod.FeatOracle(kind, 1, int(fx["n"]), _maps(kind), horizon=int(fx["horizon"]),
+                                contract=gu.contract_name(fx), seed=int(fx["seed"]), first_env_id=int(fx["env_id"]))
+
+    def reset(self):
+        return self.o.reset()[0]
+
+    def step(self, a):
+        return {k: v[0] for k, v in self.o.step(np.asarray(a)[None]).items()}
+
+    def state(self):
+        return {k: v[0] for k, v in self.o.get_state().items()}
+
+    def metrics_raw(self):
+        return self.o.metrics_raw()[0]
+
+
+class _Cuda:
+    def __init__(self, fx, E=4, index=2):
+        from contracts_b200.features import BatchedFeatureEnv
+        kind = str(fx["kind"])
+        self.i = index
+        self.env = BatchedFeatureEnv(kind, E, int(fx["n"]), horizon=int(fx["horizon"]), contract=gu.contract_name(fx),
+                                     seed=int(fx["seed"]), first_env_id=(int(fx["env_id"]) - index) & 0xFFFFFFFF)
+
+    def reset(self):
+        return self.env.reset()[self.i].cpu().numpy()
+
+    def step(self, a):
+        import torch
+        acts = torch.zeros((self.env.E, self.env.n), dtype=torch.uint8)
+        acts[:] = torch.as_tensor(np.asarray(a).astype(np.uint8))
+        obs, rew, done, info = self.env.step(acts.cuda())
+        i = self.i
+        return {"obs": obs[i].cpu().numpy(), "rew": rew[i].cpu().numpy(), "base_rew": self.env.base_rew[i].cpu().numpy(),
+                "transfers": self.env.transfers[i].cpu().numpy(), "info": info[i].cpu().numpy(), "done": int(done[i].item())}
+
+    def state(self):
+        return {k: v[self.i].cpu().numpy() for k, v in self.env.get_state().items()}
+
+    def metrics_raw(self):
+        return self.env.metrics_raw()[self.i].cpu().numpy()
+
+
+def replay(backend, fx):
+    kind, n = str(fx["kind"]), int(fx["n"])
+    wrapped = bool(fx["contract"])
+    F = 12 + n if kind == "cleanup" else 10 + 2 * n
+    for ep in range(fx["actions"].shape[0]):
+        ctx = "reset ep %d" % ep
+        obs = backend.reset()
+        st = backend.state()
+        gu.assert_same("reset obs", obs, fx["reset_obs"][ep][:, :F], ctx)
+        gu.assert_same("reset pos", st["pos"], fx["reset_pos"][ep], ctx)
+        gu.assert_same("reset ori", st["ori"], fx["reset_ori"][ep], ctx)
+        gu.assert_same("reset cells", st["cells"], fx["reset_cells"][ep], ctx)
+        if wrapped:
+            gu.assert_same("reset theta", st["theta"], fx["reset_theta"][ep], ctx)
+        for t in range(fx["actions"].shape[1]):
+            ctx = "ep %d step %d" % (ep, t)
+            o = backend.step(fx["actions"][ep, t])
+            st = backend.state()
+            gu.assert_same("pos", st["pos"], fx["pos"][ep, t], ctx)
+            gu.assert_same("ori", st["ori"], fx["ori"][ep, t], ctx)
+            gu.assert_same("cells", st["cells"], fx["cells"][ep, t], ctx)
+            gu.assert_same("obs", o["obs"], fx["obs"][ep, t][:, :F], ctx)
+            gu.assert_same("rew", o["rew"], fx["rew"][ep, t], ctx)
+            gu.assert_same("base_rew", o["base_rew"], fx["base_rew"][ep, t], ctx)
+            if wrapped:
+                gu.assert_same("transfers", o["transfers"], fx["transfers"][ep, t], ctx)
+            gu.assert_same("info0", o["info"][:, 0], fx["info0"][ep, t], ctx)
+            gu.assert_same("info1", o["info"][:, 1], fx["info1"][ep, t], ctx)
+            gu.assert_same("done", int(o["done"]), int(fx["done"][ep, t]), ctx)
+        raw = np.asarray(backend.metrics_raw(), dtype=np.float64)
+        want = dict(zip([str(k) for k in fx["metric_keys"]], fx["metrics"][ep]))
+        for k, v in _metrics(kind, n, raw).items():
+            gu.assert_same("metric " + k, np.float64(v), np.float64(want[k]), "ep %d" % ep)
+        if "equality" in want:
+            from contracts_b200.environments.gridworld import equality, sustainability
+            gu.assert_same("equality", np.float64(equality(list(raw[8:8 + n]))), np.float64(want["equality"]), "ep %d" % ep)
+            gu.assert_same("sustainability", np.float64(sustainability(list(raw[8:8 + n]), list(raw[16:16 + n]))),
+                           np.float64(want["sustainability"]), "ep %d" % ep)
+            if wrapped:
+                gu.assert_same("transfer_equality", np.float64(equality(list(raw[24:24 + n]))),
+                               np.float64(want["transfer_equality"]), "ep %d" % ep)
+                gu.assert_same("transfer_sustainability", np.float64(sustainability(list(raw[24:24 + n]), list(raw[32:32 + n]))),
+                               np.float64(want["transfer_sustainability"]), "ep %d" % ep)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_features_match_reference(oracle_lib, name):
+    replay(_Oracle(oracle_lib, gu.load(name)), gu.load(name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_features_match_reference(name):
+    replay(_Cuda(gu.load(name)), gu.load(name))
