@@ -46,12 +46,17 @@ class ssd_selfdrive_io(ctypes.Structure):
                                                "info_dev", "done_dev")]
 
 
+class ssd_feat_io(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("actions_dev", "obs_dev", "rew_dev", "base_rew_dev", "transfers_dev",
+                                               "info_dev", "done_dev")]
+
+
 EXPORTS = [
     "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_last_error", "ssd_reset", "ssd_step",
     "ssd_set_contract_params", "ssd_negotiate", "ssd_get_state", "ssd_set_state", "ssd_get_metrics",
     "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
     "ssd_kernel_launches", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
-    "ssd_selfdrive_random_actions",
+    "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
 ]
 
 _LIB = None
@@ -87,6 +92,10 @@ def load():
     L.ssd_selfdrive_step.argtypes = [vp, ctypes.POINTER(ssd_selfdrive_io), vp]
     L.ssd_selfdrive_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ssd_selfdrive_random_actions.argtypes = [vp, u32, ctypes.c_float, ctypes.c_float, vp, vp]
+    L.ssd_feat_reset.argtypes = [vp, vp, vp, vp]
+    L.ssd_feat_step.argtypes = [vp, ctypes.POINTER(ssd_feat_io), vp]
+    L.ssd_feat_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ssd_feat_get_metrics.argtypes = [vp, vp, vp]
     L.ssd_feature_dim.argtypes = [vp]
     L.ssd_state_bytes_per_env.argtypes = [vp]
     L.ssd_state_bytes_per_env.restype = i64

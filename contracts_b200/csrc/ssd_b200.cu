@@ -10,12 +10,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/ssd_b200.h"
 #include "ssd_grid.cuh"
 #include "ssd_selfdrive.cuh"
+#include "ssd_features.cuh"
 
 static thread_local char g_create_error[512] = "";
 
@@ -24,6 +26,7 @@ struct ssd_handle {
     std::string ascii;
     GridParams gp;
     CarParams cp;
+    FeatParams fp;
     int grid_blocks;
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
@@ -94,6 +97,34 @@ static int upload(ssd_handle* h, const std::vector<T>& v, const T** out)
     return SSD_OK;
 }
 
+// spawn probabilities by #waste cells as integer thresholds, computed with the reference's float64 arithmetic
+// (cleanup_new.py:351-368 == cleanup_features.py:286-303; thresholdDepletion 0.4, thresholdRestoration 0.0, 0.5, 0.05)
+static void cleanup_probability_table(int area, std::vector<uint32_t>& thr_apple, std::vector<uint8_t>& waste_on)
+{
+    thr_apple.assign(area + 1, 0u);
+    waste_on.assign(area + 1, 0);
+    for (int k = 0; k <= area; k++) {
+        volatile double waste_density = 0;
+        if (area > 0) {
+            volatile double ratio = (double)(area - k) / (double)area;
+            waste_density = 1 - ratio;
+        }
+        double pa, pw;
+        if (waste_density >= 0.4) { pa = 0; pw = 0; }
+        else {
+            pw = 0.5;
+            if (waste_density <= 0.0) pa = 0.05;
+            else {
+                volatile double frac = (waste_density - 0.0) / (0.4 - 0.0);
+                volatile double one_minus = 1 - frac;
+                pa = one_minus * 0.05;
+            }
+        }
+        thr_apple[k] = prob_threshold(pa);
+        waste_on[k] = pw != 0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 static int setup_grid(ssd_handle* h)
 {
@@ -143,30 +174,9 @@ static int setup_grid(ssd_handle* h)
     p.n_apple = (int)apple.size(); p.n_waste = (int)waste.size(); p.n_spawn = (int)spawn.size();
     p.n_waste_start = n_waste_start;
 
-    // spawn probabilities as integer thresholds, computed with the reference's float64 arithmetic
-    // (cleanup_new.py:351-368; thresholdDepletion 0.4, thresholdRestoration 0.0, 0.5, 0.05 at :53-56)
-    std::vector<uint32_t> thr_apple(p.n_waste + 1);
-    std::vector<uint8_t> waste_on(p.n_waste + 1);
-    for (int k = 0; k <= p.n_waste; k++) {
-        volatile double waste_density = 0;
-        if (p.n_waste > 0) {
-            volatile double ratio = (double)(p.n_waste - k) / (double)p.n_waste;
-            waste_density = 1 - ratio;
-        }
-        double pa, pw;
-        if (waste_density >= 0.4) { pa = 0; pw = 0; }
-        else {
-            pw = 0.5;
-            if (waste_density <= 0.0) pa = 0.05;
-            else {
-                volatile double frac = (waste_density - 0.0) / (0.4 - 0.0);
-                volatile double one_minus = 1 - frac;
-                pa = one_minus * 0.05;
-            }
-        }
-        thr_apple[k] = prob_threshold(pa);
-        waste_on[k] = pw != 0;
-    }
+    std::vector<uint32_t> thr_apple;
+    std::vector<uint8_t> waste_on;
+    cleanup_probability_table(p.n_waste, thr_apple, waste_on);
     const double SPAWN_PROB[4] = { 0, 0.005, 0.02, 0.05 };           // harvest_new.py:34
     for (int i = 0; i < 4; i++) p.thr_harvest[i] = prob_threshold(SPAWN_PROB[i]);
     p.thr_waste = prob_threshold(0.5);
@@ -262,6 +272,81 @@ static int setup_selfdrive(ssd_handle* h)
     if ((rc = dev_zalloc(h, E, &p.t))) return rc;
     if ((rc = dev_zalloc(h, E, &p.episode))) return rc;
     h->grid_blocks = (p.E + CAR_THREADS - 1) / CAR_THREADS;
+    return SSD_OK;
+}
+
+static int setup_features(ssd_handle* h)
+{
+    const ssd_config& c = h->cfg;
+    FeatParams& p = h->fp;
+    memset(&p, 0, sizeof(p));
+    const int H = c.map_h, W = c.map_w, n = c.num_agents;
+    const bool cleanup = c.env_kind == SSD_ENV_CLEANUP_FEATURES;
+    if (H < 1 || W < 1 || H > 255 || W > 255) return fail(h, SSD_EINVAL, "map size %dx%d out of range", H, W);
+    if (!c.ascii_map || (int)h->ascii.size() != H * W) return fail(h, SSD_EINVAL, "ascii_map must hold map_h*map_w chars");
+    p.E = c.num_envs; p.n = n; p.kind = c.env_kind; p.H = H; p.W = W; p.horizon = c.horizon; p.contract = c.contract_kind;
+    p.F = cleanup ? 12 + n : 10 + 2 * n;
+    p.seed = c.seed; p.first_env_id = c.first_env_id;
+    p.theta_low = c.theta_low; p.theta_high = c.theta_high; p.null_prob = c.null_prob;
+    std::vector<uint8_t> wall(H * W, 0), waste_start;
+    std::vector<int16_t> apple_idx(H * W, -1), waste_idx(H * W, -1);
+    std::vector<uint16_t> apple_rc, waste_rc, spawn_rc;
+    for (int r = 0; r < H; r++)
+        for (int col = 0; col < W; col++) {
+            const char ch = h->ascii[r * W + col];
+            const uint16_t rc = (uint16_t)((r << 8) | col);
+            if (ch == '@') wall[r * W + col] = 1;
+            if (ch == 'P') spawn_rc.push_back(rc);
+            if (ch == (cleanup ? 'B' : 'A')) { apple_idx[r * W + col] = (int16_t)apple_rc.size(); apple_rc.push_back(rc); }
+            if (cleanup && (ch == 'H' || ch == 'R')) {
+                waste_idx[r * W + col] = (int16_t)waste_rc.size(); waste_rc.push_back(rc); waste_start.push_back(ch == 'H');
+            }
+        }
+    if ((int)spawn_rc.size() < n) return fail(h, SSD_EINVAL, "map has %d spawn points for %d agents", (int)spawn_rc.size(), n);
+    if (apple_rc.size() > 32 * FEAT_MASK_WORDS || waste_rc.size() > 32 * FEAT_MASK_WORDS)
+        return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * FEAT_MASK_WORDS);
+    p.n_apple = (int)apple_rc.size(); p.n_waste = (int)waste_rc.size(); p.n_spawn = (int)spawn_rc.size(); p.potential = p.n_waste;
+    std::vector<int16_t> nbr(std::max<size_t>(apple_rc.size(), 1) * 8, -1);      // 3x3 neighbours (j*j + k*k <= APPLE_RADIUS = 2)
+    for (size_t i = 0; i < apple_rc.size(); i++) {
+        int q = 0;
+        for (int j = -1; j <= 1; j++)
+            for (int k = -1; k <= 1; k++) {
+                if (!j && !k) continue;
+                const int r = (apple_rc[i] >> 8) + j, col = (apple_rc[i] & 255) + k;
+                nbr[i * 8 + q++] = (r >= 0 && r < H && col >= 0 && col < W) ? apple_idx[r * W + col] : (int16_t)-1;
+            }
+    }
+    std::vector<uint32_t> thr_apple;
+    std::vector<uint8_t> waste_on;
+    cleanup_probability_table(p.potential, thr_apple, waste_on);
+    const double SPAWN_PROB[4] = { 0, 0.005, 0.02, 0.05 };           // harvest_features.py:36
+    for (int i = 0; i < 4; i++) p.thr_harvest[i] = prob_threshold(SPAWN_PROB[i]);
+    p.thr_waste = prob_threshold(0.5);
+    int rc;
+    if ((rc = upload(h, wall, &p.wall))) return rc;
+    if ((rc = upload(h, apple_idx, &p.apple_idx))) return rc;
+    if ((rc = upload(h, waste_idx, &p.waste_idx))) return rc;
+    if ((rc = upload(h, apple_rc, &p.apple_rc))) return rc;
+    if ((rc = upload(h, waste_rc, &p.waste_rc))) return rc;
+    if ((rc = upload(h, nbr, &p.apple_nbr))) return rc;
+    if ((rc = upload(h, spawn_rc, &p.spawn_rc))) return rc;
+    if ((rc = upload(h, waste_start, &p.waste_start))) return rc;
+    if ((rc = upload(h, thr_apple, &p.thr_apple))) return rc;
+    if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
+    const size_t E = (size_t)p.E;
+    if ((rc = dev_zalloc(h, E * n, &p.agents))) return rc;
+    if ((rc = dev_zalloc(h, E * FEAT_MASK_WORDS, &p.apple_mask))) return rc;
+    if ((rc = dev_zalloc(h, E * FEAT_MASK_WORDS, &p.waste_mask))) return rc;
+    if ((rc = dev_zalloc(h, E * p.n_apple, &p.apple_stamp))) return rc;
+    if ((rc = dev_zalloc(h, E * p.n_waste, &p.waste_stamp))) return rc;
+    if ((rc = dev_zalloc(h, E * 4, &p.counters))) return rc;
+    if ((rc = dev_zalloc(h, E, &p.theta))) return rc;
+    if ((rc = dev_zalloc(h, E * 8, &p.metrics))) return rc;
+    if ((rc = dev_zalloc(h, E * n, &p.sum_raw))) return rc;
+    if ((rc = dev_zalloc(h, E * n, &p.tsum_raw))) return rc;
+    if ((rc = dev_zalloc(h, E * n, &p.sum_tr))) return rc;
+    if ((rc = dev_zalloc(h, E * n, &p.tsum_tr))) return rc;
+    h->grid_blocks = (p.E + FEAT_THREADS - 1) / FEAT_THREADS;
     return SSD_OK;
 }
 
@@ -421,11 +506,13 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     if (cfg->abi_version != SSD_ABI_VERSION) return fail(nullptr, SSD_EINVAL, "abi_version %d != %d", cfg->abi_version, SSD_ABI_VERSION);
     if (cfg->num_envs < 1) return fail(nullptr, SSD_EINVAL, "num_envs must be >= 1");
     if (cfg->num_agents < 1 || cfg->num_agents > SSD_MAX_AGENTS) return fail(nullptr, SSD_EINVAL, "num_agents must be in [1, %d]", SSD_MAX_AGENTS);
-    if (cfg->env_kind != SSD_ENV_CLEANUP && cfg->env_kind != SSD_ENV_HARVEST && cfg->env_kind != SSD_ENV_SELFDRIVE)
+    if (cfg->env_kind < SSD_ENV_CLEANUP || cfg->env_kind > SSD_ENV_SELFDRIVE)
         return fail(nullptr, SSD_EUNSUPPORTED, "env_kind %d not supported by this build", cfg->env_kind);
     if (cfg->contract_kind != SSD_CONTRACT_NONE &&
         !((cfg->env_kind == SSD_ENV_CLEANUP && cfg->contract_kind == SSD_CONTRACT_CLEANUP) ||
           (cfg->env_kind == SSD_ENV_HARVEST && cfg->contract_kind == SSD_CONTRACT_HARVEST_LOCAL) ||
+          (cfg->env_kind == SSD_ENV_CLEANUP_FEATURES && cfg->contract_kind == SSD_CONTRACT_CLEANUP) ||
+          (cfg->env_kind == SSD_ENV_HARVEST_FEATURES && cfg->contract_kind == SSD_CONTRACT_HARVEST_LOCAL) ||
           (cfg->env_kind == SSD_ENV_SELFDRIVE && cfg->contract_kind == SSD_CONTRACT_SELFDRIVE_DISTPROP)))
         return fail(nullptr, SSD_EINVAL, "contract_kind %d does not apply to env_kind %d", cfg->contract_kind, cfg->env_kind);
     if (cfg->contract_kind != SSD_CONTRACT_NONE && cfg->num_agents < 2 && cfg->env_kind != SSD_ENV_SELFDRIVE)
@@ -442,7 +529,8 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     h->err[0] = 0;
     if (cfg->ascii_map) h->ascii.assign(cfg->ascii_map, (size_t)cfg->map_h * cfg->map_w);
     h->cfg.ascii_map = h->ascii.c_str();
-    int rc = cfg->env_kind == SSD_ENV_SELFDRIVE ? setup_selfdrive(h) : setup_grid(h);
+    const bool is_feat = cfg->env_kind == SSD_ENV_CLEANUP_FEATURES || cfg->env_kind == SSD_ENV_HARVEST_FEATURES;
+    int rc = cfg->env_kind == SSD_ENV_SELFDRIVE ? setup_selfdrive(h) : (is_feat ? setup_features(h) : setup_grid(h));
     if (rc == SSD_OK) rc = dev_zalloc(h, 1, &h->d_counter);
     if (rc != SSD_OK) {
         snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
@@ -472,6 +560,9 @@ static int check_launch(ssd_handle* h, const char* what)
 #define REQUIRE_GRID(h) \
     if ((h)->cfg.env_kind != SSD_ENV_CLEANUP && (h)->cfg.env_kind != SSD_ENV_HARVEST) \
         return fail(h, SSD_EINVAL, "%s: handle is not a gridworld (env_kind %d)", __func__, (h)->cfg.env_kind)
+#define IS_FEAT(h) ((h)->cfg.env_kind == SSD_ENV_CLEANUP_FEATURES || (h)->cfg.env_kind == SSD_ENV_HARVEST_FEATURES)
+#define REQUIRE_FEAT(h) \
+    if (!IS_FEAT(h)) return fail(h, SSD_EINVAL, "%s: handle is not a feature env (env_kind %d)", __func__, (h)->cfg.env_kind)
 #define REQUIRE_CAR(h) \
     if ((h)->cfg.env_kind != SSD_ENV_SELFDRIVE) return fail(h, SSD_EINVAL, "%s: handle is not a selfdrive env", __func__)
 
@@ -517,6 +608,8 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
     if (!h || !theta_dev) return SSD_EINVAL;
     if (h->cfg.env_kind == SSD_ENV_SELFDRIVE)
         car_set_theta_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, theta_dev);
+    else if (IS_FEAT(h))
+        feat_set_theta_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, theta_dev);
     else
         SMALL_LAUNCH(set_theta_kernel, theta_dev);
     return check_launch(h, "set_contract_params");
@@ -558,11 +651,53 @@ int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream)
 {
     if (!h || !actions_dev || num_actions < 1 || num_actions > 255) return SSD_EINVAL;
-    REQUIRE_GRID(h);
     const bool autoidx = step_index == SSD_STEP_AUTO;
+    if (IS_FEAT(h)) {
+        feat_random_actions_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, step_index, autoidx ? h->d_counter : nullptr,
+                                                                                              num_actions, actions_dev);
+        if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
+        return check_launch(h, "random_actions");
+    }
+    REQUIRE_GRID(h);
     SMALL_LAUNCH(random_actions_kernel, step_index, autoidx ? h->d_counter : nullptr, num_actions, actions_dev);
     if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "random_actions");
+}
+
+// ---- feature envs --------------------------------------------------------------------------------------
+int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_FEAT(h);
+    feat_reset_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, mask_dev, obs_dev);
+    return check_launch(h, "feat_reset");
+}
+
+int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
+{
+    if (!h || !io) return SSD_EINVAL;
+    REQUIRE_FEAT(h);
+    if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
+    if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
+    FeatIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev };
+    feat_step_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, k);
+    return check_launch(h, "feat_step");
+}
+
+int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev, int32_t* t_dev, void* stream)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_FEAT(h);
+    feat_get_state_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, pos_dev, ori_dev, cells_dev, theta_dev, t_dev);
+    return check_launch(h, "feat_get_state");
+}
+
+int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream)
+{
+    if (!h || !out_dev) return SSD_EINVAL;
+    REQUIRE_FEAT(h);
+    feat_get_metrics_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, out_dev);
+    return check_launch(h, "feat_get_metrics");
 }
 
 // ---- selfdrive -------------------------------------------------------------------------------------
@@ -605,10 +740,15 @@ int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, f
     return check_launch(h, "selfdrive_random_actions");
 }
 
-int ssd_feature_dim(const ssd_handle* h) { return !h ? 0 : (h->cfg.env_kind == SSD_ENV_SELFDRIVE ? h->cp.D : h->gp.F); }
+int ssd_feature_dim(const ssd_handle* h)
+{
+    if (!h) return 0;
+    return h->cfg.env_kind == SSD_ENV_SELFDRIVE ? h->cp.D : (IS_FEAT(h) ? h->fp.F : h->gp.F);
+}
 int64_t ssd_state_bytes_per_env(const ssd_handle* h)
 {
     if (!h) return 0;
+    if (IS_FEAT(h)) return (int64_t)(2 * (h->fp.n_apple + h->fp.n_waste) + 64 * FEAT_MASK_WORDS / 8 + 36 * h->fp.n + 88);
     return h->cfg.env_kind == SSD_ENV_SELFDRIVE ? (int64_t)(16 * h->cp.n + 44) : (int64_t)h->gp.rec_stride;
 }
 int64_t ssd_kernel_launches(const ssd_handle* h) { return h ? h->launches : 0; }

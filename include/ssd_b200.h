@@ -160,13 +160,37 @@ int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, dou
 /* uniform float32 accelerations in [lo, hi) for benchmark rollouts, [E][n] */
 int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, float hi, float* actions_dev, void* stream);
 
+/* --- CleanupFeatures / HarvestFeatures (env_kind SSD_ENV_CLEANUP_FEATURES / SSD_ENV_HARVEST_FEATURES) ----------
+ * environments/cleanup_features.py step :156-254 / reset :256-284, environments/harvest_features.py step :173-287 /
+ * reset :289-336, optionally with CleanupContract / HarvestFeaturemodLocalContract + SeparateContractSubgameStage
+ * fused (two_stage_train.py:62-121,159-187).  ssd_create takes the same ascii map as the gridworld kinds.
+ * F = ssd_feature_dim(h) = 12 + n (cleanup) or 10 + 2 n (harvest) float64 features per agent. */
+typedef struct ssd_feat_io {
+    const uint8_t* actions_dev; /* [E][n] action ids (cleanup 0-8: moves, stay, turns, clean 7, fire 8; harvest 0-7) */
+    double* obs_dev;            /* [E][n][F] */
+    double* rew_dev;            /* [E][n] after transfers */
+    double* base_rew_dev;       /* [E][n] nullable */
+    double* transfers_dev;      /* [E][n] nullable */
+    uint8_t* info_dev;          /* [E][n][4] nullable: cleanup (cleaned_squares,0,0,0); harvest (eaten_apples, eaten_close_apples,0,0) */
+    uint8_t* done_dev;          /* [E] nullable: dones['__all__'] (timesteps == horizon) */
+} ssd_feat_io;
+int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
+int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream);
+/* pos int32 [E][n][2], ori int32 [E][n], cells uint8 [E][H][W] (1 = apple, 2 = waste in the current lists),
+ * theta double [E], t int32 [E]; NULL pointers are skipped */
+int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev,
+                       int32_t* t_dev, void* stream);
+/* double [E][40]: dirt_cleaned, raw_env_rewards, transfers, total_apples_eaten, low_density_apples_eaten, 0, 0, 0,
+ * per agent: sum r [8], sum t*r [8], sum transferred r [8], sum t * transferred r [8] */
+int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream);
+
 /* --- utilities ------------------------------------------------------------------------------------------ */
 /* uniform random action ids in [0, num_actions) for benchmark rollouts, uint8 [E][n];
  * drawn from Philox site 13 at counter `step_index` (no reference equivalent: RLlib's policy).
  * step_index == SSD_STEP_AUTO takes (and then bumps) a per-handle device counter instead, so the call can be
  * captured in a CUDA graph and still draw fresh actions at every replay. */
 #define SSD_STEP_AUTO 0xFFFFFFFFu
-int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream);
+int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream);   /* gridworld and feature kinds */
 /* host-side Philox4x32-10 (so tests can pin the generator: KATs in tests/test_philox.py) */
 void ssd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int ssd_abi_version(void);

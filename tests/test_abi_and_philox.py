@@ -40,7 +40,7 @@ def test_config_struct_matches_header():
     from contracts_b200 import _lib
     text = open(os.path.join(ROOT, "include", "ssd_b200.h")).read()
     for struct, cls in (("ssd_config", _lib.ssd_config), ("ssd_step_io", _lib.ssd_step_io),
-                        ("ssd_selfdrive_io", _lib.ssd_selfdrive_io)):
+                        ("ssd_selfdrive_io", _lib.ssd_selfdrive_io), ("ssd_feat_io", _lib.ssd_feat_io)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

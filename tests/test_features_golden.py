@@ -128,3 +128,69 @@ def test_oracle_features_match_reference(oracle_lib, name):
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_features_match_reference(name):
     replay(_Cuda(gu.load(name)), gu.load(name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in NAMES if "nocontract" not in n])
+def test_dropin_feature_env_dict_api(name):
+    """env_creator('Cleanup' / 'Harvest') + ContractWrapperSubgame (non-convolutional): obs = concat(features, theta, [0])."""
+    from contracts_b200.contract import contract_list
+    from contracts_b200.utils.env_creator_functions import env_creator, get_base_env_tag
+    fx = gu.load(name)
+    kind, n = str(fx["kind"]), int(fx["n"])
+    base = env_creator(get_base_env_tag({"environment": kind}), dict(num_agents=n, horizon=int(fx["horizon"]),
+                                                                      seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+    env = env_creator("ContractWrapperSubgame", dict(num_agents=n, base_env=base, contract=getattr(contract_list, gu.contract_name(fx))(n),
+                                                     convolutional=False))
+    keys = ["a%d" % i for i in range(n)]
+    for ep in range(fx["actions"].shape[0]):
+        obs = env.reset()
+        gu.assert_same("reset obs", np.stack([obs[k] for k in keys]), fx["reset_obs"][ep], "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            ctx = "ep %d step %d" % (ep, t)
+            obs, rew, done, info = env.step({k: int(a) for k, a in zip(keys, fx["actions"][ep, t])})
+            gu.assert_same("obs", np.stack([obs[k] for k in keys]), fx["obs"][ep, t], ctx)
+            gu.assert_same("rew", np.array([rew[k] for k in keys]), fx["rew"][ep, t], ctx)
+            d = bool(fx["done"][ep, t])
+            assert done == {"__all__": d, "a0": d, "a1": d}, ctx
+        m = base.metrics
+        want = dict(zip([str(k) for k in fx["metric_keys"]], fx["metrics"][ep]))
+        assert set(m.keys()) == set(want.keys()), (sorted(m), sorted(want))
+        for k, v in want.items():
+            gu.assert_same("metric " + k, np.float64(m[k]), np.float64(v), "ep %d" % ep)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,E,nact", [("cleanup", 8, 2050, 9), ("harvest", 8, 1030, 8), ("cleanup", 3, 257, 8), ("harvest", 1, 64, 8)])
+def test_cuda_features_rollout_matches_oracle(oracle_lib, kind, n, E, nact):
+    """Random rollouts at batch size, every output incl. masked re-resets and metrics, bit-exact vs the C oracle."""
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    contract = None if n < 2 else ("CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract")
+    env = BatchedFeatureEnv(kind, E, n, horizon=70, contract=contract, seed=9, first_env_id=4000000000)
+    orc = oracle_lib.FeatOracle(kind, E, n, _maps(kind), horizon=70, contract=contract, seed=9, first_env_id=4000000000)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    rng = np.random.RandomState(n)
+    p = None
+    if kind == "cleanup":
+        p = np.array([.11, .11, .11, .11, .05, .05, .05, .36, .05][:nact]); p = p / p.sum()
+    for t in range(160):
+        a = rng.choice(nact, size=(E, n), p=p)
+        o = orc.step(a)
+        obs, rew, done, info = env.step(torch.from_numpy(a.astype(np.uint8)).cuda())
+        ctx = "step %d" % t
+        gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+        gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+        gu.assert_same("base_rew", env.base_rew.cpu().numpy(), o["base_rew"], ctx)
+        gu.assert_same("transfers", env.transfers.cpu().numpy(), o["transfers"], ctx)
+        gu.assert_same("info", info.cpu().numpy()[..., :2], o["info"][..., :2], ctx)
+        gu.assert_same("done", done.cpu().numpy(), o["done"], ctx)
+        if o["done"].any():
+            gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), ctx)
+            mask = o["done"].copy(); mask[::4] = 0
+            r1 = env.reset(torch.from_numpy(mask).cuda()).cpu().numpy()
+            r2 = orc.reset(mask)
+            gu.assert_same("masked reset obs", r1[mask.astype(bool)], r2[mask.astype(bool)], ctx)
+    so, sc = orc.get_state(), env.get_state()
+    for k in ("pos", "ori", "cells", "theta", "t"):
+        gu.assert_same(k, sc[k].cpu().numpy(), so[k], "end")
