@@ -239,11 +239,13 @@ def main():
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        lcap = env.kernel_launches
         with torch.cuda.graph(graph, stream=side):
             for _ in range(G):
                 env.random_actions(None, N_ACTIONS, out=actions)
                 env.step(actions, extras=False)
         torch.cuda.synchronize(dev)
+        per_graph = env.kernel_launches - lcap                   # kernels captured in one graph (counted by the C ABI)
     state["t"] = 0                                               # start the timed region at an episode boundary
 
     def run_steps(k):
@@ -255,11 +257,11 @@ def main():
                 new_episode()
             if graph is not None:
                 graph.replay()
-                m, launches = G, launches + 3 * G
+                m, launches = G, launches + per_graph
             else:
                 env.random_actions(state["global_step"], N_ACTIONS, out=actions)
                 env.step(actions, extras=False)
-                m, launches = 1, launches + 2
+                m = 1
             done += m
             state["t"] += m
             state["global_step"] += m
@@ -280,7 +282,7 @@ def main():
     graph_launches = run_steps(K)
     ev1.record()
     barrier()
-    launches = (env.kernel_launches - l0) + (graph_launches if graph is not None else 0)
+    launches = (env.kernel_launches - l0) + graph_launches       # eager launches are counted by the C ABI itself
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)

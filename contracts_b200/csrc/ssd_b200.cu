@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -16,6 +17,7 @@
 
 #include "../../include/ssd_b200.h"
 #include "ssd_grid.cuh"
+#include "ssd_grid2.cuh"
 #include "ssd_selfdrive.cuh"
 #include "ssd_features.cuh"
 
@@ -28,6 +30,8 @@ struct ssd_handle {
     CarParams cp;
     FeatParams fp;
     int grid_blocks;
+    int obs_blocks;          // two-kernel step (ssd_grid2.cuh): grid of the observe kernel; 0 = single-kernel step (v3)
+    uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
@@ -46,6 +50,17 @@ static step_kernel_t step_kernel_fn(int kind, bool rounds4, bool feat)
     return feat ? grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, true> : grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false>;
 }
 static const void* step_kernel_ptr(int kind, bool rounds4, bool feat) { return (const void*)step_kernel_fn(kind, rounds4, feat); }
+
+typedef void (*obs_kernel_t)(const GridParams, const StepIO, uint32_t*);
+static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat)
+{
+    if (kind == SSD_ENV_CLEANUP) {
+        if (rounds4) return feat ? grid_obs_kernel<SSD_ENV_CLEANUP, 4, true> : grid_obs_kernel<SSD_ENV_CLEANUP, 4, false>;
+        return feat ? grid_obs_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, true> : grid_obs_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, false>;
+    }
+    if (rounds4) return feat ? grid_obs_kernel<SSD_ENV_HARVEST, 4, true> : grid_obs_kernel<SSD_ENV_HARVEST, 4, false>;
+    return feat ? grid_obs_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, true> : grid_obs_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false>;
+}
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
 {
@@ -123,6 +138,17 @@ static void cleanup_probability_table(int area, std::vector<uint32_t>& thr_apple
         thr_apple[k] = prob_threshold(pa);
         waste_on[k] = pw != 0;
     }
+}
+
+template <typename T>
+static int dev_zalloc(ssd_handle* h, size_t count, T** out)
+{
+    void* d = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
+    h->dev_allocs.push_back(d);
+    CUDA_TRY(h, cudaMemset(d, 0, (count ? count : 1) * sizeof(T)));
+    *out = reinterpret_cast<T*>(d);
+    return SSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,21 +261,30 @@ static int setup_grid(ssd_handle* h)
     if (per_sm < 1) return fail(h, SSD_EUNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", p.smem_bytes);
     int want = (p.E + GRID_WARPS - 1) / GRID_WARPS;
     h->grid_blocks = want < sms * per_sm ? want : sms * per_sm;
+
+    // two-kernel step: observe kernel, per warp [tile | rec slot 0 | rec slot 1 | stage | misc]
+    p.g2_rec = p.tile_r16;
+    p.g2_stage = p.g2_rec + 2 * (p.map_bytes + OBS_HDR_BYTES);
+    p.g2_misc = p.g2_stage + p.stage_r16;
+    p.g2_warp_bytes = p.g2_misc + MISC_BYTES;
+    p.g2_smem_bytes = p.sm_warp0 + GRID_WARPS * p.g2_warp_bytes;
+    h->obs_blocks = 0;
+    const char* sel = getenv("SSD_GRID_KERNEL");
+    if (!(sel && strcmp(sel, "v3") == 0)) {
+        int per_sm2 = 0;
+        for (int feat = 0; feat < 2; feat++)
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false),
+                                                                  GRID_THREADS, p.g2_smem_bytes));
+        if (per_sm2 < 1) return fail(h, SSD_EUNSUPPORTED, "observe kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
+        h->obs_blocks = want < sms * per_sm2 ? want : sms * per_sm2;
+        if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
+    }
     return SSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-static int dev_zalloc(ssd_handle* h, size_t count, T** out)
-{
-    void* d = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
-    h->dev_allocs.push_back(d);
-    CUDA_TRY(h, cudaMemset(d, 0, (count ? count : 1) * sizeof(T)));
-    *out = reinterpret_cast<T*>(d);
-    return SSD_OK;
-}
-
 static int setup_selfdrive(ssd_handle* h)
 {
     const ssd_config& c = h->cfg;
@@ -596,7 +631,15 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
     k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
     if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+    if (h->obs_blocks > 0) {
+        const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
+        if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
+        else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
+        h->launches++;
+        obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k, h->d_res);
+        if (p.kind == SSD_ENV_HARVEST) { h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res); }
+    } else
+        step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
     return check_launch(h, "step");
 }
 

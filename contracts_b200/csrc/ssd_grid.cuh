@@ -61,6 +61,8 @@ struct GridParams {
     int tile_r16, stage_r16, warp_bytes, off_rec, off_stage, off_misc;
     int sm_thr, sm_won, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
     int obs_items;           // ceil(15 n / 4): 4-row (180 B) work items of the observation gather
+    // observe kernel (ssd_grid2.cuh), per warp: [tile | rec slot 0 | rec slot 1 | stage | misc]
+    int g2_rec, g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;
@@ -410,19 +412,20 @@ __device__ __forceinline__ void fill_draws(uint32_t* scratch, int lane, const En
 
 // ---------------------------------------------------------------------------------------------
 // cleanup spawn (cleanup_new.py:322-349).  Occupancy bits must be set.  `t` = 0 at reset.
-// Returns the number of waste cells spawned (0 or 1).
+// Updates hcount (#waste cells); returns whether the map changed.
 __device__ __forceinline__ bool cleanup_spawn_active(const SharedTables& tb, int hcount)
 {
     return tb.thr_apple[hcount] != 0 || tb.waste_on[hcount] != 0;
 }
 template <int ROUNDS>
-__device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile,
-                                             uint32_t* scratch, const EnvRng& g, uint32_t t, int hcount)
+__device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile,
+                                              uint32_t* scratch, const EnvRng& g, uint32_t t, int& hcount)
 {
     const uint16_t* sm_apple = tb.apple; const uint16_t* sm_waste = tb.waste;
     const uint32_t thrA = tb.thr_apple[hcount];
     const bool waste_on = tb.waste_on[hcount] != 0;
-    if (thrA == 0 && !waste_on) return 0;
+    if (thrA == 0 && !waste_on) return false;
+    bool spawned = false;
     uint32_t* draws = scratch;
     uint32_t* keys = scratch + SCRATCH_DRAWS;
     // apples: eligible = no agent there and not already 'A'; draw index = rank among eligible (:328-335)
@@ -446,14 +449,15 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
             if (q * 32 < p.n_apple) {
                 if ((eligm[q] >> lane) & 1u) {
                     int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); }
+                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
                 }
                 base += __popc(eligm[q]);
             }
         }
         __syncwarp();
     }
-    if (!waste_on) return 0;
+    const bool apples = __any_sync(FULL, spawned);
+    if (!waste_on) return apples;
     // waste: shuffle waste_points (stateless: key per canonical index), scan non-'H' cells in that
     // order, draw continues at rank M; first success spawns and breaks (:338-348)
     unsigned candm[ROUNDS];
@@ -468,7 +472,7 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
             C += __popc(candm[q]);
         } else candm[q] = 0;
     }
-    if (C == 0) return 0;
+    if (C == 0) return apples;
     // number of failed draws before the first success
     int kstar = -1;
     for (int k0 = 0; k0 < C && kstar < 0; k0 += 32) {
@@ -476,7 +480,7 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
         unsigned succ = __ballot_sync(FULL, (k0 + lane) < C && dr < p.thr_waste);
         if (succ) kstar = k0 + __ffs(succ) - 1;
     }
-    if (kstar < 0) return 0;
+    if (kstar < 0) return apples;
     // keys of all waste points, then the (kstar+1)-th smallest (key, index) among candidates
     for (int bl = lane; bl < ((p.n_waste + 3) >> 2); bl += 32) {
         reinterpret_cast<uint4*>(keys)[bl] = draw_block_ool(g.seed, g.env_id, g.episode, t, SITE_WASTE_ORDER, (uint32_t)bl);
@@ -502,12 +506,13 @@ __device__ __forceinline__ int cleanup_spawn(const GridParams& p, const SharedTa
     }
     if (lane == 0) { int cell = sm_waste[chosen]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_WASTE); }
     __syncwarp();
-    return 1;
+    hcount += 1;
+    return true;
 }
 
 // harvest spawn (harvest_new.py:284-317): neighbour counts read the pre-spawn map
 template <int ROUNDS>
-__device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
+__device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
                                               const uint16_t* sm_apple, const EnvRng& g, uint32_t t)
 {
     const int S = p.S;
@@ -538,20 +543,22 @@ __device__ __forceinline__ void harvest_spawn(const GridParams& p, int lane, uin
             M += __popc(eligm[q]);
         }
     }
-    if (M == 0) return;
+    if (M == 0) return false;
     fill_draws(scratch, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);   // also orders the tile reads above
     int base = 0;
+    bool spawned = false;
 #pragma unroll
     for (int q = 0; q < ROUNDS; q++) {
         if (q * 32 < p.n_apple) {
             if ((eligm[q] >> lane) & 1u) {
                 int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); }
+                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
             }
             base += __popc(eligm[q]);
         }
     }
     __syncwarp();
+    return __any_sync(FULL, spawned);
 }
 
 // count_apples_in_radius(5, loc) (harvest_new.py:326-336): the 21 cells with j*j + k*k <= 5
@@ -854,7 +861,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             if (cleanup_spawn_active(tb, hcount)) {
                 if (lane == 0) bulk_wait_read<0>();  // previous env's observation store has drained `stage` (= scratch)
                 __syncwarp();
-                hcount += cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
+                cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
             }
         } else {
             if (lane == 0) bulk_wait_read<0>();
@@ -1009,7 +1016,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
         if (act_lane) tile[ao] |= OCC_BIT;
         __syncwarp();
         int hcount = p.n_waste_start;
-        if (KIND == SSD_ENV_CLEANUP) hcount += cleanup_spawn<MAX_POINT_ROUNDS>(p, tb, lane, tile, scratch, g, 0u, hcount);
+        if (KIND == SSD_ENV_CLEANUP) cleanup_spawn<MAX_POINT_ROUNDS>(p, tb, lane, tile, scratch, g, 0u, hcount);
         else harvest_spawn<MAX_POINT_ROUNDS>(p, lane, tile, scratch, tb.apple, g, 0u);
         tile_store(p, rec, tile, lane);
         __syncwarp();

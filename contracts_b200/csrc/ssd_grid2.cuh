@@ -1,0 +1,471 @@
+// ssd_grid2.cuh — the gridworld step as two kernels (v5): LOGIC (lane = env) + OBSERVE (warp = env).
+//
+// Why two mappings.  The reference's per-env decision logic (update_moves, consume, beams, reward
+// redistribution) is serial and tiny (n <= 8 agents).  Run with a warp per env (v3, grid_step_kernel) it
+// keeps 8 of 32 lanes busy and costs ~600 warp-instructions per env; run with a lane per env it costs
+// ~200, but a fused kernel that alternates both mappings inside one warp (v4, measured: 884 instead of
+// 1411 warp-instructions per env, yet 0.49-0.64 ms instead of 0.36 ms) needs the 32 maps of a chunk in
+// shared memory and is left with 6-13 warps per SM.  So the step is split:
+//
+//   grid_logic_kernel    one THREAD per env, no shared-memory staging: action decode, rotations, moves,
+//                        consume, beams on the env's compact map in global memory (each thread touches a few
+//                        dozen bytes of its own 464-byte map; L1/L2 serve them), then — cleanup — contract
+//                        transfers, rewards, outputs and the record header.  E / 148 = 886 envs per SM fit in
+//                        one wave, so the kernel's time is one thread's dependency chain.
+//                        Envs whose moves are contested (a few %) are resolved by the whole warp, lane =
+//                        agent, with the literal reference ordering (resolve_moves_slow).
+//   grid_obs_kernel      one WARP per env, 24 warps per SM: record prefetch by bulk async copy (double
+//                        buffered), map -> padded tile, spawn scans (ballot ranks), observation gather and
+//                        one bulk async store of the n 15x15x3 windows.  This is the HBM-bound part.
+//   grid_reward_kernel   harvest only: the contract transfer needs total_close_apples of the post-spawn
+//                        map, so transfers / rewards / header run after grid_obs_kernel (thread per env).
+//
+// Per-agent results travel between the kernels in a u32 [E][8] scratch array (RS_* fields).
+// Reference behaviour restated here: see the citations in ssd_grid.cuh (same functions, same order).
+#pragma once
+#include "ssd_grid.cuh"
+
+#define LOGIC_THREADS 128
+#define LOGIC_WARPS (LOGIC_THREADS / 32)
+#define G2_CLAIM 0x01u       // scratch mark in a compact-map byte: cell reserved as a move target
+
+// per-(agent, env) result word
+#define RS_CLEANED_MASK 3u          // bits 0-1  cleaned_squares (0..3)
+#define RS_EATEN 4u                 // bit 2     eaten_apples (stale list)
+#define RS_EATEN_CLOSE 8u           // bit 3     eaten_close_apples
+#define RS_CLOSE_SHIFT 4            // bits 4-8  total_close_apples (0..21)
+#define RS_REWARD_SHIFT 16          // bits 16-31 reward accumulator (int16)
+
+// record bytes the observe kernel needs: map + agents + (t, episode, theta) + (flags, hcount, ...)
+#define OBS_HDR_BYTES 64
+
+__device__ __forceinline__ int rc_off(uint32_t rc, int Wp) { return (int)(rc & 255u) * Wp + (int)((rc >> 8) & 255u); }
+__device__ __forceinline__ uint32_t rc_lex(uint32_t rc) { return ((rc & 255u) << 8) | ((rc >> 8) & 255u); }
+__device__ __forceinline__ int ori_dr(int d) { return d == ORI_UP ? -1 : (d == ORI_DOWN ? 1 : 0); }
+__device__ __forceinline__ int ori_dc(int d) { return d == ORI_RIGHT ? 1 : (d == ORI_LEFT ? -1 : 0); }
+
+// count_apples_in_radius(5, loc) on the compact map (explicit bounds): harvest_new.py:326-336
+__device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, int H, int W, int Wp)
+{
+    int cnt = 0;
+#pragma unroll
+    for (int dr = -2; dr <= 2; dr++)
+#pragma unroll
+        for (int dc = -2; dc <= 2; dc++)
+            if (dr * dr + dc * dc <= 5) {
+                int r = row + dr, c = col + dc;
+                if ((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W) cnt += ((map[r * Wp + c] & CODE_MASK) == C_APPLE);
+            }
+    return cnt;
+}
+
+// one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map.  Occupancy bits are
+// set on every agent cell.  The three rays are distinct lines, so applying H -> R immediately is the same
+// as the reference's deferred `updates` list.  Returns the number of cleaned cells.
+__device__ __noinline__ int g2_fire(uint8_t* map, uint32_t* ag /* lane-strided */, uint32_t* res, int n, int s, bool clean,
+                                    int H, int W, int Wp)
+{
+    const uint32_t v = ag[s * 32];
+    const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u), ori = (int)((v >> 16) & 3u);
+    const int dr = ori_dr(ori), dc = ori_dc(ori);
+    const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);       // right = clockwise of dir
+    int nup = 0;
+    for (int b = 0; b < 3; b++) {
+        int r = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0)) + dr;
+        int c = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0)) + dc;
+        for (int i = 0; i < 5; i++) {
+            if (!((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W)) break;
+            const int o = r * Wp + c;
+            const uint32_t code = map[o], cc = code & CODE_MASK;
+            if (cc == C_WALL) break;
+            const bool isH = clean && cc == C_WASTE;
+            if (isH) { map[o] = (uint8_t)((code & OCC_BIT) | C_RIVER); nup++; }
+            if (code & OCC_BIT) {
+                if (!clean) {                                               // Agent.hit(b"F"): -50 (Agent.py:224-226)
+                    const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
+                    int victim = -1;
+                    for (int a = 0; a < n; a++) if ((ag[a * 32] & 0xFFFFu) == cell) victim = a;
+                    if (victim >= 0) res[victim * 32] -= 50u << RS_REWARD_SHIFT;
+                }
+                break;
+            }
+            if (isH) break;
+            r += dr; c += dc;
+        }
+    }
+    return nup;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transfers + redistribution + outputs + header accumulators of one env (lane = env).
+// rsp[a * rstride]: RS_* word of agent a (incl. total_close for harvest).  contract_list.py:22-27,45-54;
+// two_stage_train.py:72-99; cleanup_new.py:213-253 / harvest_new.py:183-224.
+template <int KIND>
+__device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& io, int env, uint8_t* hdr,
+                                            const uint32_t* rsp, int rstride, double theta, int t)
+{
+    const int n = p.n;
+    const size_t o = (size_t)env * n;
+    double rj[SSD_MAXN];
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) rj[a] = a < n ? (double)((int)rsp[a * rstride] >> RS_REWARD_SHIFT) : 0.0;
+    if (io.base_rew) {
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) if (a < n) io.base_rew[o + a] = rj[a];
+    }
+    // A zero transfer leaves every reward bit-identical (rewards are never -0.0), so it is skipped.
+    double total_tr = 0.0;
+    if (p.contract != SSD_CONTRACT_NONE) {
+        const double nm1 = (double)(n - 1);
+        for (int i = 0; i < n; i++) {                  // rolled: one copy of the fp64 division
+            {
+                const uint32_t w = rsp[i * rstride];
+                double tr;
+                if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)(w & RS_CLEANED_MASK));
+                else tr = (((w >> RS_CLOSE_SHIFT) & 31u) < 4u && (w & RS_EATEN_CLOSE)) ? theta : 0.0;
+                if (io.transfers) io.transfers[o + i] = tr;
+                if (tr != 0.0) {
+                    const double share = __ddiv_rn(tr, nm1), neg = -tr;
+#pragma unroll
+                    for (int j = 0; j < SSD_MAXN; j++) rj[j] = __dadd_rn(rj[j], j == i ? neg : share);
+                    total_tr = __dadd_rn(total_tr, tr);
+                }
+            }
+        }
+    } else if (io.transfers) {
+        for (int i = 0; i < n; i++) io.transfers[o + i] = 0.0;
+    }
+    const int tm1i = t - 1;
+    const double tm1 = (double)tm1i;
+    uint32_t n_eaten = 0, n_close = 0;
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) {
+        if (a < n) {
+            const uint32_t w = rsp[a * rstride];
+            const int reward = (int)w >> RS_REWARD_SHIFT;
+            const uint32_t eaten = (w >> 2) & 1u, eclose = (w >> 3) & 1u, cleaned = w & RS_CLEANED_MASK;
+            const uint32_t tclose = (w >> RS_CLOSE_SHIFT) & 31u;
+            n_eaten += eaten; n_close += eclose;
+            io.rew[o + a] = rj[a];
+            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o + a] =
+                eaten | ((KIND == SSD_ENV_CLEANUP ? cleaned : eclose) << 8) | (tclose << 16);
+            if (reward != 0) {
+                reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a] += reward;
+                reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a] += (long long)tm1i * reward;
+            }
+            if (p.contract != SSD_CONTRACT_NONE && rj[a] != 0.0) {
+                double* st = reinterpret_cast<double*>(hdr + RO_SUM_TR) + a;
+                double* tt = reinterpret_cast<double*>(hdr + RO_TSUM_TR) + a;
+                *st = __dadd_rn(*st, rj[a]);
+                *tt = __dadd_rn(*tt, __dmul_rn(tm1, rj[a]));
+            }
+            if (KIND == SSD_ENV_CLEANUP) { if (cleaned) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] += cleaned; }
+            else {
+                if (eaten) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] += eaten;
+                if (eclose) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a] += eclose;
+            }
+        }
+    }
+    if (n_eaten) *reinterpret_cast<uint32_t*>(hdr + RO_APPLES) += n_eaten;
+    if (KIND == SSD_ENV_HARVEST && n_close) *reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS) += n_close;
+    if (total_tr != 0.0) {
+        double* mt = reinterpret_cast<double*>(hdr + RO_TRANSFERS);
+        *mt = __dadd_rn(*mt, total_tr);
+    }
+    if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
+}
+
+// =============================================================================================
+// LOGIC: one thread per env.  Shared memory only holds the lane-strided per-agent arrays.
+template <int KIND>
+__global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
+{
+    __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* agA = s_arr[warp][0]; uint32_t* resA = s_arr[warp][1]; uint32_t* mvA = s_arr[warp][2];
+    uint32_t* ag = agA + lane; uint32_t* res = resA + lane; uint32_t* mv = mvA + lane; uint32_t* key = s_arr[warp][3] + lane;
+    const int n = p.n, H = p.H, W = p.W, Wp = p.Wp;
+    const bool act_lane = lane < n;
+    const int env0 = blockIdx.x * LOGIC_THREADS + warp * 32;       // first env of this warp
+    const bool valid = env0 + lane < p.E;
+    const int env = valid ? env0 + lane : p.E - 1;
+    uint8_t* map = p.state + (size_t)env * p.rec_stride;           // this env's compact map, in global memory
+    uint8_t* hdr = map + p.map_bytes;
+
+    int t = 0, hcount = 0; uint32_t episode = 0, flags = 0; double theta = 0.0;
+    uint32_t err = 0, movers = 0, firem = 0, cleanm = 0;
+    bool slow = false;
+    if (valid) {
+        const uint4 a0 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS + 16);
+        const uint4 s0 = *reinterpret_cast<const uint4*>(hdr + RO_T);        // t, episode, theta
+        const uint2 s1 = *reinterpret_cast<const uint2*>(hdr + RO_FLAGS);    // flags, hcount
+        ag[0] = a0.x; ag[32] = a0.y; ag[64] = a0.z; ag[96] = a0.w;
+        ag[128] = a1.x; ag[160] = a1.y; ag[192] = a1.z; ag[224] = a1.w;
+        t = (int)s0.x + 1;                                                    // map_env.py:230
+        episode = s0.y;
+        theta = __hiloint2double((int)s0.w, (int)s0.z);
+        flags = s1.x; hcount = (int)s1.y;
+        // ---- packed action ids
+        const uint8_t* g_act = io.actions + (size_t)env * n;
+        uint32_t act_lo = 0x04040404u, act_hi = 0x04040404u;
+        if (n == 8 && (reinterpret_cast<uintptr_t>(io.actions) & 7u) == 0) {
+            const uint2 a = *reinterpret_cast<const uint2*>(g_act); act_lo = a.x; act_hi = a.y;
+        } else {
+            for (int a = 0; a < n; a++) {
+                const uint32_t b = g_act[a];
+                if (a < 4) act_lo = (act_lo & ~(255u << (8 * a))) | (b << (8 * a));
+                else act_hi = (act_hi & ~(255u << (8 * (a - 4)))) | (b << (8 * (a - 4)));
+            }
+        }
+        // ---- decode, rotations (map_env.py:514-516), move targets (Agent.py:8-16,161-162,198-199)
+        for (int a = 0; a < n; a++) {
+            const uint32_t v = ag[a * 32];
+            const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u);
+            int ori = (int)((v >> 16) & 3u);
+            const int act = (int)(((a < 4 ? act_lo : act_hi) >> (8 * (a & 3))) & 255u);
+            uint32_t tg = v & 0xFFFFu;
+            if (act <= 4) {
+                movers |= 1u << a;
+                if (act < 4) {
+                    // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
+                    const int d = (ori + ((0x2013 >> (4 * act)) & 3)) & 3;
+                    const int nr = row + ori_dr(d), nc = col + ori_dc(d);
+                    if ((unsigned)nr < (unsigned)H && (unsigned)nc < (unsigned)W &&
+                        (map[nr * Wp + nc] & CODE_MASK) != C_WALL)                // return_valid_pos (Agent.py:111-119)
+                        tg = (uint32_t)nr | ((uint32_t)nc << 8);
+                }
+            } else if (act == 5) ori = (ori + 1) & 3;                            // TURN_CLOCKWISE
+            else if (act == 6) ori = (ori + 3) & 3;                              // TURN_COUNTERCLOCKWISE
+            else if (KIND == SSD_ENV_HARVEST) { if (act == 7) firem |= 1u << a; else { err |= 8; movers |= 1u << a; } }
+            else if (act == 7) cleanm |= 1u << a;
+            else if (act == 8) firem |= 1u << a;
+            else { err |= 8; movers |= 1u << a; }
+            ag[a * 32] = (v & 0xFFFFu) | ((uint32_t)ori << 16);
+            mv[a * 32] = tg;
+            res[a * 32] = 0u;
+        }
+        if (movers) {
+            // fast path test: no two movers share a target and no real move targets an occupied cell
+            for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] |= OCC_BIT;
+            for (int a = 0; a < n; a++) {
+                if (!((movers >> a) & 1u)) continue;
+                const uint32_t tg = mv[a * 32];
+                const int o = rc_off(tg, Wp);
+                const uint32_t c = map[o];
+                if ((c & G2_CLAIM) || ((c & OCC_BIT) && tg != (ag[a * 32] & 0xFFFFu))) slow = true;
+                map[o] = (uint8_t)(c | G2_CLAIM);
+            }
+            for (int a = 0; a < n; a++) {
+                map[rc_off(ag[a * 32], Wp)] &= CODE_MASK;
+                if ((movers >> a) & 1u) map[rc_off(mv[a * 32], Wp)] &= CODE_MASK;
+            }
+            if (!slow)
+                for (int a = 0; a < n; a++)
+                    if ((movers >> a) & 1u) ag[a * 32] = (ag[a * 32] & 0xFFFF0000u) | mv[a * 32];
+        }
+    }
+    __syncwarp();
+    // ---- contested moves: the literal reference ordering, one env at a time, lane = agent
+    unsigned slowm = __ballot_sync(FULL, slow);
+    while (slowm) {
+        const int r = __ffs(slowm) - 1; slowm &= slowm - 1;
+        const uint32_t movers_r = __shfl_sync(FULL, movers, r);
+        const uint32_t ep_r = __shfl_sync(FULL, episode, r), t_r = (uint32_t)__shfl_sync(FULL, t, r);
+        uint32_t v = 0; int ao = 0, tgt = 0; bool has_move = false;
+        if (act_lane) {
+            v = agA[lane * 32 + r];
+            ao = (int)rc_lex(v);                             // lexicographic (row, col) cell id
+            has_move = (movers_r >> lane) & 1u;
+            tgt = has_move ? (int)rc_lex(mvA[lane * 32 + r]) : ao;
+        }
+        const uint32_t mval = has_move ? (uint32_t)tgt : (0xFFFF0000u | (uint32_t)lane);
+        const unsigned same = __match_any_sync(FULL, mval);              // all lanes: not under a short-circuit
+        const bool contested = has_move && (__popc(same) > 1);
+        const uint32_t rr = resolve_moves_slow(lane, n, p.seed, p.first_env_id + (uint32_t)(env0 + r), ep_r, t_r,
+                                               ao, has_move, tgt, movers_r, contested);
+        if (act_lane) agA[lane * 32 + r] = (v & 0xFFFF0000u) | rc_lex(rr & 0xFFFFu);
+        const uint32_t e2 = __reduce_or_sync(FULL, rr >> 16);
+        if (lane == r) err |= e2;
+    }
+    __syncwarp();
+    if (!valid) return;
+
+    // ---- stale-list infos on the start-of-step map (cleanup_new.py:220-223, harvest_new.py:190-199)
+    for (int a = 0; a < n; a++) {
+        const uint32_t v = ag[a * 32];
+        if ((map[rc_off(v, Wp)] & CODE_MASK) == C_APPLE && !(flags & RF_STALE_EMPTY)) {
+            uint32_t rs = RS_EATEN;
+            if (KIND == SSD_ENV_HARVEST &&
+                g2_count_r5(map, (int)(v & 255u), (int)((v >> 8) & 255u), H, W, Wp) < 4) rs |= RS_EATEN_CLOSE;
+            res[a * 32] = rs;
+        }
+    }
+    // ---- consume in agent order (map_env.py:244-247)
+    uint32_t rem = firem | cleanm;
+    for (int a = 0; a < n; a++) {
+        const int o = rc_off(ag[a * 32], Wp);
+        const uint32_t c = map[o];
+        if ((c & CODE_MASK) == C_APPLE) { res[a * 32] += 1u << RS_REWARD_SHIFT; map[o] = (uint8_t)C_EMPTY; }
+    }
+    // ---- beams in shuffled agent order (map_env.py:678-693); keys only matter when >= 2 agents fire
+    int ncleaned = 0;
+    if (rem) {
+        for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] |= OCC_BIT;       // beams stop at agents
+        const bool multi = (rem & (rem - 1)) != 0;
+        if (multi) {
+            for (int b = 0; b < 2; b++)
+                if (rem & (0xFu << (4 * b))) {
+                    const uint4 q = draw_block_ool(p.seed, p.first_env_id + (uint32_t)env, episode, (uint32_t)t,
+                                                   SITE_BEAM_ORDER, (uint32_t)b);
+                    key[(4 * b) * 32] = q.x; key[(4 * b + 1) * 32] = q.y; key[(4 * b + 2) * 32] = q.z; key[(4 * b + 3) * 32] = q.w;
+                }
+        }
+        while (rem) {
+            int s = __ffs(rem) - 1;
+            if (multi) {
+                uint32_t best = key[s * 32];
+                for (uint32_t m2 = rem & (rem - 1); m2; m2 &= m2 - 1) {
+                    const int a = __ffs(m2) - 1;
+                    const uint32_t kk = key[a * 32];
+                    if (kk < best) { best = kk; s = a; }
+                }
+            }
+            rem &= ~(1u << s);
+            const bool clean = (cleanm >> s) & 1u;
+            const int nup = g2_fire(map, ag, res, n, s, clean, H, W, Wp);
+            if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
+            else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
+        }
+        for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] &= CODE_MASK;
+    }
+    if (KIND == SSD_ENV_CLEANUP) hcount -= ncleaned;
+
+    // ---- record header (the observe kernel reads agents, t, episode, flags, hcount from it)
+    *reinterpret_cast<uint4*>(hdr + RO_AGENTS) = make_uint4(ag[0], ag[32], ag[64], ag[96]);
+    *reinterpret_cast<uint4*>(hdr + RO_AGENTS + 16) = make_uint4(ag[128], ag[160], ag[192], ag[224]);
+    *reinterpret_cast<int*>(hdr + RO_T) = t;
+    *reinterpret_cast<uint2*>(hdr + RO_FLAGS) =
+        make_uint2((flags & ~RF_STALE_EMPTY) | (err ? (err << RF_ERR_SHIFT) : 0u), (uint32_t)hcount);
+    if (KIND == SSD_ENV_CLEANUP && ncleaned) *reinterpret_cast<uint32_t*>(hdr + RO_DIRT) += (uint32_t)ncleaned;
+    uint32_t rs[SSD_MAXN];
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) rs[a] = a < n ? res[a * 32] : 0u;
+    uint4* rg = reinterpret_cast<uint4*>(res_g + (size_t)env * SSD_MAXN);
+    rg[0] = make_uint4(rs[0], rs[1], rs[2], rs[3]);
+    rg[1] = make_uint4(rs[4], rs[5], rs[6], rs[7]);
+    // cleanup: nothing below depends on the spawn, so rewards / outputs are finished here
+    if (KIND == SSD_ENV_CLEANUP) env_rewards<KIND>(p, io, env, hdr, res, 32, theta, t);
+}
+
+// harvest: rewards after the observe kernel has added total_close_apples to the result words
+__global__ void __launch_bounds__(LOGIC_THREADS) grid_reward_kernel(const GridParams p, const StepIO io, const uint32_t* __restrict__ res_g)
+{
+    const int env = blockIdx.x * LOGIC_THREADS + threadIdx.x;
+    if (env >= p.E) return;
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
+    const int t = *reinterpret_cast<const int*>(hdr + RO_T);
+    const double theta = *reinterpret_cast<const double*>(hdr + RO_THETA);
+    env_rewards<SSD_ENV_HARVEST>(p, io, env, hdr, res_g + (size_t)env * SSD_MAXN, 1, theta, t);
+}
+
+// =============================================================================================
+// OBSERVE: one warp per env.  Spawn + observation windows.  Per warp:
+//   [tile | rec slot 0 | rec slot 1 | stage (obs staging, aliased by the spawn scratch) | misc]
+// A rec slot holds the map + the first OBS_HDR_BYTES of the header.
+template <int KIND, int ROUNDS, bool FEAT>
+__global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_obs_kernel(const GridParams p, const StepIO io,
+                                                                                 uint32_t* __restrict__ res_g)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const SharedTables tb = load_shared_tables(p, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tile = smem + p.sm_warp0 + warp * p.g2_warp_bytes;
+    uint8_t* recs = tile + p.g2_rec;
+    uint8_t* stage = tile + p.g2_stage;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
+    int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + p.g2_misc + MISC_MBAR);
+    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
+    if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int n = p.n, S = p.S;
+    const bool act_lane = lane < n;
+    const int env_stride = gridDim.x * GRID_WARPS;
+    const uint32_t slot_bytes = (uint32_t)(p.map_bytes + OBS_HDR_BYTES);
+    const MapWords mw = map_words_init(p, lane);
+
+    int env = blockIdx.x * GRID_WARPS + warp;
+    uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
+    const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
+    uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
+    const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
+    if (env < p.E && lane == 0) bulk_load(recs, g_rec, slot_bytes, mbar);
+    for (uint32_t it = 0; env < p.E; env += env_stride, it++) {
+        const uint32_t slot = it & 1u;
+        uint8_t* rec = recs + slot * slot_bytes;
+        const uint8_t* hdr = rec + p.map_bytes;
+        // prefetch the next env's record into the other slot (its previous contents may still be leaving
+        // through the map store of the previous iteration: wait until that has been read)
+        if (env + env_stride < p.E && lane == 0) {
+            bulk_wait_read<1>();                      // all but the newest group (an observation store)
+            bulk_load(recs + (slot ^ 1u) * slot_bytes, g_rec + g_rec_step, slot_bytes, mbar + (slot ^ 1u));
+        }
+        mbar_wait(mbar + slot, (it >> 1) & 1u);
+        tile_expand(p, mw, rec, tile, lane);
+        const uint32_t t = *reinterpret_cast<const uint32_t*>(hdr + RO_T);          // already incremented by the logic kernel
+        const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+        int hcount = *reinterpret_cast<const int*>(hdr + RO_HCOUNT);
+        const EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, t };
+        int ao = 0, ori = 0;
+        if (act_lane) {
+            const uint32_t a = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[lane];
+            ao = ((int)(a & 255u) + SSD_VIEW) * S + 8 + (int)((a >> 8) & 255u);
+            ori = (int)((a >> 16) & 3u);
+        }
+        __syncwarp();
+        if (act_lane) tile[ao] |= OCC_BIT;            // spawn eligibility: "no agent there" (co-located lanes write the same value)
+        __syncwarp();
+        // ---- spawn
+        bool changed = false;
+        if (KIND == SSD_ENV_CLEANUP) {
+            if (cleanup_spawn_active(tb, hcount)) {
+                if (lane == 0) bulk_wait_read<0>();   // the previous observation store has drained `stage` (= scratch)
+                __syncwarp();
+                const int before = hcount;
+                changed = cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, t, hcount);
+                if (hcount != before && lane == 0)
+                    *reinterpret_cast<int*>(g_rec + p.map_bytes + RO_HCOUNT) = hcount;
+            }
+        } else {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            changed = harvest_spawn<ROUNDS>(p, lane, tile, scratch, tb.apple, g, t);
+        }
+        int total_close = 0;
+        if (KIND == SSD_ENV_HARVEST && act_lane) {
+            total_close = count_apples_r5(tile, ao, S);
+            res_g[(size_t)env * SSD_MAXN + lane] |= (uint32_t)total_close << RS_CLOSE_SHIFT;
+        }
+        if (FEAT) {
+            const int cleaned = (KIND == SSD_ENV_CLEANUP && act_lane) ? (int)(res_g[(size_t)env * SSD_MAXN + lane] & RS_CLEANED_MASK) : 0;
+            write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount, io.feat + (size_t)env * n * p.F);
+        }
+        // ---- the map goes back only when the spawn changed it
+        if (changed) {
+            tile_compress(p, mw, rec, tile, lane);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_store(g_rec, rec, (uint32_t)p.map_bytes);
+        } else if (lane == 0) bulk_wait_read<0>();   // no map store in flight: the previous observation store must have drained `stage`
+        // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261)
+        const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
+        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
+        // gather_obs waits (lane 0) until at most the map store above is still in flight, then syncs the warp
+        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
+        g_rec += g_rec_step; g_obs += g_obs_step;
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_read<0>();      // smem must outlive the async bulk reads
+}
