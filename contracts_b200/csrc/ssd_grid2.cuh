@@ -59,38 +59,57 @@ __device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, in
     return cnt;
 }
 
-// one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map.  Occupancy bits are
-// set on every agent cell.  The three rays are distinct lines, so applying H -> R immediately is the same
-// as the reference's deferred `updates` list.  Returns the number of cleaned cells.
-__device__ __noinline__ int g2_fire(uint8_t* map, uint32_t* ag /* lane-strided */, uint32_t* res, int n, int s, bool clean,
-                                    int H, int W, int Wp)
+// one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map in global memory.
+// The 15 ray cells are loaded up front (independent loads, one memory round trip), then walked in
+// registers.  "Agent on this cell" is a 64-bit hash filter over the agents' cells followed by the exact
+// comparison.  The three rays are distinct lines, so applying H -> R immediately is the same as the
+// reference's deferred `updates` list.  Returns the number of cleaned cells.
+__device__ __forceinline__ uint32_t cell_hash(int r, int c) { return (uint32_t)(r * 7 + c) & 63u; }
+__device__ __noinline__ int g2_fire(uint8_t* map, const uint32_t* ag /* lane-strided */, uint32_t* res, int n, int s, bool clean,
+                                    unsigned long long occ_filter, int H, int W, int Wp)
 {
     const uint32_t v = ag[s * 32];
     const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u), ori = (int)((v >> 16) & 3u);
     const int dr = ori_dr(ori), dc = ori_dc(ori);
     const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);       // right = clockwise of dir
-    int nup = 0;
+    uint32_t code[15];
+#pragma unroll
     for (int b = 0; b < 3; b++) {
-        int r = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0)) + dr;
-        int c = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0)) + dc;
+        const int r0 = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0));
+        const int c0 = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0));
+#pragma unroll
         for (int i = 0; i < 5; i++) {
-            if (!((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W)) break;
-            const int o = r * Wp + c;
-            const uint32_t code = map[o], cc = code & CODE_MASK;
-            if (cc == C_WALL) break;
-            const bool isH = clean && cc == C_WASTE;
-            if (isH) { map[o] = (uint8_t)((code & OCC_BIT) | C_RIVER); nup++; }
-            if (code & OCC_BIT) {
-                if (!clean) {                                               // Agent.hit(b"F"): -50 (Agent.py:224-226)
-                    const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
-                    int victim = -1;
-                    for (int a = 0; a < n; a++) if ((ag[a * 32] & 0xFFFFu) == cell) victim = a;
-                    if (victim >= 0) res[victim * 32] -= 50u << RS_REWARD_SHIFT;
+            const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
+            const bool inb = (unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W;
+            code[b * 5 + i] = inb ? (uint32_t)map[r * Wp + c] : (uint32_t)C_WALL;      // out of bounds stops a ray like a wall
+        }
+    }
+    int nup = 0;
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const int r0 = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0));
+        const int c0 = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0));
+        bool alive = true;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const uint32_t cc = code[b * 5 + i] & CODE_MASK;
+            if (alive) {
+                if (cc == C_WALL) alive = false;
+                else {
+                    const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
+                    const bool isH = clean && cc == C_WASTE;
+                    if (isH) { map[r * Wp + c] = (uint8_t)C_RIVER; nup++; alive = false; }
+                    if ((occ_filter >> cell_hash(r, c)) & 1ull) {
+                        const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
+                        int victim = -1;
+                        for (int a = 0; a < n; a++) if ((ag[a * 32] & 0xFFFFu) == cell) victim = a;
+                        if (victim >= 0) {
+                            if (!clean) res[victim * 32] -= 50u << RS_REWARD_SHIFT;      // Agent.hit(b"F"): -50 (Agent.py:224-226)
+                            alive = false;
+                        }
+                    }
                 }
-                break;
             }
-            if (isH) break;
-            r += dr; c += dc;
         }
     }
     return nup;
@@ -176,14 +195,18 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 }
 
 // =============================================================================================
-// LOGIC: one thread per env.  Shared memory only holds the lane-strided per-agent arrays.
+// LOGIC: one thread per env.  Agent state lives in registers (loops over the n <= 8 agents are fully
+// unrolled), map bytes are read from global memory in batches of independent loads (one memory round
+// trip per batch), conflicts are found by pairwise comparisons instead of marks in the map.  Shared
+// memory only holds lane-strided copies of the per-agent arrays for the two places that index agents
+// dynamically (the warp-cooperative contested-move resolution and the beam walk).
 template <int KIND>
 __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* agA = s_arr[warp][0]; uint32_t* resA = s_arr[warp][1]; uint32_t* mvA = s_arr[warp][2];
-    uint32_t* ag = agA + lane; uint32_t* res = resA + lane; uint32_t* mv = mvA + lane; uint32_t* key = s_arr[warp][3] + lane;
+    uint32_t* agA = s_arr[warp][0]; uint32_t* mvA = s_arr[warp][2];
+    uint32_t* ags = agA + lane; uint32_t* res = s_arr[warp][1] + lane; uint32_t* mvs = mvA + lane; uint32_t* key = s_arr[warp][3] + lane;
     const int n = p.n, H = p.H, W = p.W, Wp = p.Wp;
     const bool act_lane = lane < n;
     const int env0 = blockIdx.x * LOGIC_THREADS + warp * 32;       // first env of this warp
@@ -194,14 +217,14 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
 
     int t = 0, hcount = 0; uint32_t episode = 0, flags = 0; double theta = 0.0;
     uint32_t err = 0, movers = 0, firem = 0, cleanm = 0;
+    uint32_t ag[SSD_MAXN], tg[SSD_MAXN];
     bool slow = false;
     if (valid) {
         const uint4 a0 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS);
         const uint4 a1 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS + 16);
         const uint4 s0 = *reinterpret_cast<const uint4*>(hdr + RO_T);        // t, episode, theta
         const uint2 s1 = *reinterpret_cast<const uint2*>(hdr + RO_FLAGS);    // flags, hcount
-        ag[0] = a0.x; ag[32] = a0.y; ag[64] = a0.z; ag[96] = a0.w;
-        ag[128] = a1.x; ag[160] = a1.y; ag[192] = a1.z; ag[224] = a1.w;
+        ag[0] = a0.x; ag[1] = a0.y; ag[2] = a0.z; ag[3] = a0.w; ag[4] = a1.x; ag[5] = a1.y; ag[6] = a1.z; ag[7] = a1.w;
         t = (int)s0.x + 1;                                                    // map_env.py:230
         episode = s0.y;
         theta = __hiloint2double((int)s0.w, (int)s0.z);
@@ -218,52 +241,63 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
                 else act_hi = (act_hi & ~(255u << (8 * (a - 4)))) | (b << (8 * (a - 4)));
             }
         }
-        // ---- decode, rotations (map_env.py:514-516), move targets (Agent.py:8-16,161-162,198-199)
-        for (int a = 0; a < n; a++) {
-            const uint32_t v = ag[a * 32];
-            const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u);
-            int ori = (int)((v >> 16) & 3u);
-            const int act = (int)(((a < 4 ? act_lo : act_hi) >> (8 * (a & 3))) & 255u);
-            uint32_t tg = v & 0xFFFFu;
-            if (act <= 4) {
-                movers |= 1u << a;
-                if (act < 4) {
-                    // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
-                    const int d = (ori + ((0x2013 >> (4 * act)) & 3)) & 3;
-                    const int nr = row + ori_dr(d), nc = col + ori_dc(d);
-                    if ((unsigned)nr < (unsigned)H && (unsigned)nc < (unsigned)W &&
-                        (map[nr * Wp + nc] & CODE_MASK) != C_WALL)                // return_valid_pos (Agent.py:111-119)
-                        tg = (uint32_t)nr | ((uint32_t)nc << 8);
+        // ---- decode, rotations (map_env.py:514-516), candidate cells (Agent.py:8-16,161-162,198-199)
+        uint32_t cand[SSD_MAXN], wallb[SSD_MAXN];
+        uint32_t want = 0;                                       // movers with a real candidate cell inside the map
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            cand[a] = 0; wallb[a] = C_WALL;
+            if (a < n) {
+                const uint32_t v = ag[a];
+                const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u);
+                int ori = (int)((v >> 16) & 3u);
+                const int act = (int)(((a < 4 ? act_lo : act_hi) >> (8 * (a & 3))) & 255u);
+                if (act <= 4) {
+                    movers |= 1u << a;
+                    if (act < 4) {
+                        // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
+                        const int d = (ori + ((0x2013 >> (4 * act)) & 3)) & 3;
+                        const int nr = row + ori_dr(d), nc = col + ori_dc(d);
+                        if ((unsigned)nr < (unsigned)H && (unsigned)nc < (unsigned)W) {
+                            want |= 1u << a;
+                            cand[a] = (uint32_t)nr | ((uint32_t)nc << 8);
+                        }
+                    }
+                } else if (act == 5) ori = (ori + 1) & 3;                            // TURN_CLOCKWISE
+                else if (act == 6) ori = (ori + 3) & 3;                              // TURN_COUNTERCLOCKWISE
+                else if (KIND == SSD_ENV_HARVEST) { if (act == 7) firem |= 1u << a; else { err |= 8; movers |= 1u << a; } }
+                else if (act == 7) cleanm |= 1u << a;
+                else if (act == 8) firem |= 1u << a;
+                else { err |= 8; movers |= 1u << a; }
+                ag[a] = (v & 0xFFFFu) | ((uint32_t)ori << 16);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++)                       // independent loads: one round trip
+            if ((want >> a) & 1u) wallb[a] = map[rc_off(cand[a], Wp)];
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++)                       // return_valid_pos (Agent.py:111-119)
+            tg[a] = (((want >> a) & 1u) && (wallb[a] & CODE_MASK) != C_WALL) ? cand[a] : (ag[a] & 0xFFFFu);
+        // ---- fast path test: no two movers share a target and no real move targets an occupied cell
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if ((movers >> a) & 1u) {
+                const bool real = tg[a] != (ag[a] & 0xFFFFu);
+#pragma unroll
+                for (int b = 0; b < SSD_MAXN; b++) {
+                    if (b == a || b >= n) continue;
+                    if (b > a && ((movers >> b) & 1u) && tg[b] == tg[a]) slow = true;
+                    if (real && (ag[b] & 0xFFFFu) == tg[a]) slow = true;
                 }
-            } else if (act == 5) ori = (ori + 1) & 3;                            // TURN_CLOCKWISE
-            else if (act == 6) ori = (ori + 3) & 3;                              // TURN_COUNTERCLOCKWISE
-            else if (KIND == SSD_ENV_HARVEST) { if (act == 7) firem |= 1u << a; else { err |= 8; movers |= 1u << a; } }
-            else if (act == 7) cleanm |= 1u << a;
-            else if (act == 8) firem |= 1u << a;
-            else { err |= 8; movers |= 1u << a; }
-            ag[a * 32] = (v & 0xFFFFu) | ((uint32_t)ori << 16);
-            mv[a * 32] = tg;
-            res[a * 32] = 0u;
-        }
-        if (movers) {
-            // fast path test: no two movers share a target and no real move targets an occupied cell
-            for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] |= OCC_BIT;
-            for (int a = 0; a < n; a++) {
-                if (!((movers >> a) & 1u)) continue;
-                const uint32_t tg = mv[a * 32];
-                const int o = rc_off(tg, Wp);
-                const uint32_t c = map[o];
-                if ((c & G2_CLAIM) || ((c & OCC_BIT) && tg != (ag[a * 32] & 0xFFFFu))) slow = true;
-                map[o] = (uint8_t)(c | G2_CLAIM);
             }
-            for (int a = 0; a < n; a++) {
-                map[rc_off(ag[a * 32], Wp)] &= CODE_MASK;
-                if ((movers >> a) & 1u) map[rc_off(mv[a * 32], Wp)] &= CODE_MASK;
-            }
-            if (!slow)
-                for (int a = 0; a < n; a++)
-                    if ((movers >> a) & 1u) ag[a * 32] = (ag[a * 32] & 0xFFFF0000u) | mv[a * 32];
         }
+        if (!slow) {
+#pragma unroll
+            for (int a = 0; a < SSD_MAXN; a++)
+                if ((movers >> a) & 1u) ag[a] = (ag[a] & 0xFFFF0000u) | tg[a];
+        }
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) { ags[a * 32] = ag[a]; mvs[a * 32] = tg[a]; res[a * 32] = 0u; }
     }
     __syncwarp();
     // ---- contested moves: the literal reference ordering, one env at a time, lane = agent
@@ -290,28 +324,53 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
     }
     __syncwarp();
     if (!valid) return;
+    if (slow) {
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) ag[a] = ags[a * 32];
+    }
 
-    // ---- stale-list infos on the start-of-step map (cleanup_new.py:220-223, harvest_new.py:190-199)
-    for (int a = 0; a < n; a++) {
-        const uint32_t v = ag[a * 32];
-        if ((map[rc_off(v, Wp)] & CODE_MASK) == C_APPLE && !(flags & RF_STALE_EMPTY)) {
-            uint32_t rs = RS_EATEN;
-            if (KIND == SSD_ENV_HARVEST &&
-                g2_count_r5(map, (int)(v & 255u), (int)((v >> 8) & 255u), H, W, Wp) < 4) rs |= RS_EATEN_CLOSE;
-            res[a * 32] = rs;
+    // ---- cells under the agents: stale-list infos on the start-of-step map (cleanup_new.py:220-223,
+    //      harvest_new.py:190-199), then consume in agent order (map_env.py:244-247): of co-located
+    //      agents the lowest index eats
+    uint32_t under[SSD_MAXN];
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) under[a] = a < n ? (uint32_t)map[rc_off(ag[a], Wp)] : 0u;
+    uint32_t on_apple = 0, first = 0;
+    unsigned long long occ_filter = 0ull;
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) {
+        if (a < n) {
+            if ((under[a] & CODE_MASK) == C_APPLE) on_apple |= 1u << a;
+            bool dup = false;
+#pragma unroll
+            for (int b = 0; b < a; b++) if ((ag[b] & 0xFFFFu) == (ag[a] & 0xFFFFu)) dup = true;
+            if (!dup) first |= 1u << a;
+            occ_filter |= 1ull << cell_hash((int)(ag[a] & 255u), (int)((ag[a] >> 8) & 255u));
         }
     }
-    // ---- consume in agent order (map_env.py:244-247)
-    uint32_t rem = firem | cleanm;
-    for (int a = 0; a < n; a++) {
-        const int o = rc_off(ag[a * 32], Wp);
-        const uint32_t c = map[o];
-        if ((c & CODE_MASK) == C_APPLE) { res[a * 32] += 1u << RS_REWARD_SHIFT; map[o] = (uint8_t)C_EMPTY; }
+    if (on_apple) {
+        const bool stale_ok = !(flags & RF_STALE_EMPTY);
+        for (uint32_t m = on_apple; m; m &= m - 1) {
+            const int a = __ffs(m) - 1;
+            const uint32_t v = ags[a * 32];
+            uint32_t rs = 0;
+            if (stale_ok) {
+                rs = RS_EATEN;
+                if (KIND == SSD_ENV_HARVEST &&
+                    g2_count_r5(map, (int)(v & 255u), (int)((v >> 8) & 255u), H, W, Wp) < 4) rs |= RS_EATEN_CLOSE;
+            }
+            if ((first >> a) & 1u) rs += 1u << RS_REWARD_SHIFT;
+            res[a * 32] = rs;
+        }
+        for (uint32_t m = on_apple & first; m; m &= m - 1) {
+            const int a = __ffs(m) - 1;
+            map[rc_off(ags[a * 32], Wp)] = (uint8_t)C_EMPTY;
+        }
     }
     // ---- beams in shuffled agent order (map_env.py:678-693); keys only matter when >= 2 agents fire
+    uint32_t rem = firem | cleanm;
     int ncleaned = 0;
     if (rem) {
-        for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] |= OCC_BIT;       // beams stop at agents
         const bool multi = (rem & (rem - 1)) != 0;
         if (multi) {
             for (int b = 0; b < 2; b++)
@@ -333,27 +392,23 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(map, ag, res, n, s, clean, H, W, Wp);
+            const int nup = g2_fire(map, ags, res, n, s, clean, occ_filter, H, W, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }
-        for (int a = 0; a < n; a++) map[rc_off(ag[a * 32], Wp)] &= CODE_MASK;
     }
     if (KIND == SSD_ENV_CLEANUP) hcount -= ncleaned;
 
     // ---- record header (the observe kernel reads agents, t, episode, flags, hcount from it)
-    *reinterpret_cast<uint4*>(hdr + RO_AGENTS) = make_uint4(ag[0], ag[32], ag[64], ag[96]);
-    *reinterpret_cast<uint4*>(hdr + RO_AGENTS + 16) = make_uint4(ag[128], ag[160], ag[192], ag[224]);
+    *reinterpret_cast<uint4*>(hdr + RO_AGENTS) = make_uint4(ag[0], ag[1], ag[2], ag[3]);
+    *reinterpret_cast<uint4*>(hdr + RO_AGENTS + 16) = make_uint4(ag[4], ag[5], ag[6], ag[7]);
     *reinterpret_cast<int*>(hdr + RO_T) = t;
     *reinterpret_cast<uint2*>(hdr + RO_FLAGS) =
         make_uint2((flags & ~RF_STALE_EMPTY) | (err ? (err << RF_ERR_SHIFT) : 0u), (uint32_t)hcount);
     if (KIND == SSD_ENV_CLEANUP && ncleaned) *reinterpret_cast<uint32_t*>(hdr + RO_DIRT) += (uint32_t)ncleaned;
-    uint32_t rs[SSD_MAXN];
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) rs[a] = a < n ? res[a * 32] : 0u;
     uint4* rg = reinterpret_cast<uint4*>(res_g + (size_t)env * SSD_MAXN);
-    rg[0] = make_uint4(rs[0], rs[1], rs[2], rs[3]);
-    rg[1] = make_uint4(rs[4], rs[5], rs[6], rs[7]);
+    rg[0] = make_uint4(res[0], res[32], res[64], res[96]);
+    rg[1] = make_uint4(res[128], res[160], res[192], res[224]);
     // cleanup: nothing below depends on the spawn, so rewards / outputs are finished here
     if (KIND == SSD_ENV_CLEANUP) env_rewards<KIND>(p, io, env, hdr, res, 32, theta, t);
 }
