@@ -61,15 +61,15 @@ __device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, in
 
 // one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map in global memory.
 // The 15 ray cells are loaded up front (independent loads, one memory round trip), then walked in
-// registers.  "Agent on this cell" is a 64-bit hash filter over the agents' cells followed by the exact
-// comparison.  The three rays are distinct lines, so applying H -> R immediately is the same as the
-// reference's deferred `updates` list.  Returns the number of cleaned cells.
-__device__ __forceinline__ uint32_t cell_hash(int r, int c) { return (uint32_t)(r * 7 + c) & 63u; }
-__device__ __noinline__ int g2_fire(uint8_t* map, const uint32_t* ag /* lane-strided */, uint32_t* res, int n, int s, bool clean,
-                                    unsigned long long occ_filter, int H, int W, int Wp)
+// registers.  "Agent on this cell" compares the cell with the (register-resident) cells of all agents:
+// branch-free, because with 32 envs per warp some lane always takes the rare path.  The three rays are
+// distinct lines, so applying H -> R immediately is the same as the reference's deferred `updates` list.
+// Returns the number of cleaned cells.
+struct AgentCells { uint32_t c[SSD_MAXN]; };        // row | col << 8 of each agent (0xFFFFFFFF: no agent)
+__device__ __noinline__ int g2_fire(uint8_t* map, uint32_t shooter, const AgentCells ac, uint32_t* res /* lane-strided */,
+                                    bool clean, int H, int W, int Wp)
 {
-    const uint32_t v = ag[s * 32];
-    const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u), ori = (int)((v >> 16) & 3u);
+    const int row = (int)(shooter & 255u), col = (int)((shooter >> 8) & 255u), ori = (int)((shooter >> 16) & 3u);
     const int dr = ori_dr(ori), dc = ori_dc(ori);
     const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);       // right = clockwise of dir
     uint32_t code[15];
@@ -93,23 +93,18 @@ __device__ __noinline__ int g2_fire(uint8_t* map, const uint32_t* ag /* lane-str
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             const uint32_t cc = code[b * 5 + i] & CODE_MASK;
-            if (alive) {
-                if (cc == C_WALL) alive = false;
-                else {
-                    const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
-                    const bool isH = clean && cc == C_WASTE;
-                    if (isH) { map[r * Wp + c] = (uint8_t)C_RIVER; nup++; alive = false; }
-                    if ((occ_filter >> cell_hash(r, c)) & 1ull) {
-                        const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
-                        int victim = -1;
-                        for (int a = 0; a < n; a++) if ((ag[a * 32] & 0xFFFFu) == cell) victim = a;
-                        if (victim >= 0) {
-                            if (!clean) res[victim * 32] -= 50u << RS_REWARD_SHIFT;      // Agent.hit(b"F"): -50 (Agent.py:224-226)
-                            alive = false;
-                        }
-                    }
+            const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
+            const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
+            int victim = -1;                                    // agent_by_pos: the highest index wins duplicates
+#pragma unroll
+            for (int a = 0; a < SSD_MAXN; a++) victim = ac.c[a] == cell ? a : victim;
+            if (alive && cc != C_WALL) {
+                if (clean && cc == C_WASTE) { map[r * Wp + c] = (uint8_t)C_RIVER; nup++; alive = false; }
+                if (victim >= 0) {
+                    if (!clean) res[victim * 32] -= 50u << RS_REWARD_SHIFT;          // Agent.hit(b"F"): -50 (Agent.py:224-226)
+                    alive = false;
                 }
-            }
+            } else alive = false;
         }
     }
     return nup;
@@ -157,31 +152,63 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
     const int tm1i = t - 1;
     const double tm1 = (double)tm1i;
     uint32_t n_eaten = 0, n_close = 0;
+    bool any_raw = false, any_tr = false, any_a = false, any_b = false;
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a < n) {
             const uint32_t w = rsp[a * rstride];
-            const int reward = (int)w >> RS_REWARD_SHIFT;
             const uint32_t eaten = (w >> 2) & 1u, eclose = (w >> 3) & 1u, cleaned = w & RS_CLEANED_MASK;
             const uint32_t tclose = (w >> RS_CLOSE_SHIFT) & 31u;
             n_eaten += eaten; n_close += eclose;
             io.rew[o + a] = rj[a];
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o + a] =
                 eaten | ((KIND == SSD_ENV_CLEANUP ? cleaned : eclose) << 8) | (tclose << 16);
-            if (reward != 0) {
-                reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a] += reward;
-                reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a] += (long long)tm1i * reward;
+            any_raw |= ((int)w >> RS_REWARD_SHIFT) != 0;
+            any_tr |= rj[a] != 0.0;
+            any_a |= (KIND == SSD_ENV_CLEANUP ? cleaned : eaten) != 0;
+            any_b |= eclose != 0;
+        }
+    }
+    // episode accumulators: all loads of a group first (one memory round trip), then the stores.  Adding a
+    // zero reward leaves an accumulator bit-identical (sums are never -0.0), so untouched groups are skipped.
+    if (any_raw) {
+        int sr[SSD_MAXN]; long long ts[SSD_MAXN];
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { sr[a] = reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a]; ts[a] = reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a]; }
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a < n) {
+                const int reward = (int)rsp[a * rstride] >> RS_REWARD_SHIFT;
+                if (reward != 0) {
+                    reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a] = sr[a] + reward;
+                    reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a] = ts[a] + (long long)tm1i * reward;
+                }
             }
-            if (p.contract != SSD_CONTRACT_NONE && rj[a] != 0.0) {
-                double* st = reinterpret_cast<double*>(hdr + RO_SUM_TR) + a;
-                double* tt = reinterpret_cast<double*>(hdr + RO_TSUM_TR) + a;
-                *st = __dadd_rn(*st, rj[a]);
-                *tt = __dadd_rn(*tt, __dmul_rn(tm1, rj[a]));
+        }
+    }
+    if (p.contract != SSD_CONTRACT_NONE && any_tr) {
+        double st[SSD_MAXN], tt[SSD_MAXN];
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { st[a] = reinterpret_cast<double*>(hdr + RO_SUM_TR)[a]; tt[a] = reinterpret_cast<double*>(hdr + RO_TSUM_TR)[a]; }
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a < n && rj[a] != 0.0) {
+                reinterpret_cast<double*>(hdr + RO_SUM_TR)[a] = __dadd_rn(st[a], rj[a]);
+                reinterpret_cast<double*>(hdr + RO_TSUM_TR)[a] = __dadd_rn(tt[a], __dmul_rn(tm1, rj[a]));
             }
-            if (KIND == SSD_ENV_CLEANUP) { if (cleaned) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] += cleaned; }
-            else {
-                if (eaten) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] += eaten;
-                if (eclose) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a] += eclose;
+        }
+    }
+    if (any_a || any_b) {
+        uint32_t ca[SSD_MAXN], cb[SSD_MAXN];
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { ca[a] = reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a]; cb[a] = reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a]; }
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a < n) {
+                const uint32_t w = rsp[a * rstride];
+                const uint32_t da = KIND == SSD_ENV_CLEANUP ? (w & RS_CLEANED_MASK) : ((w >> 2) & 1u), db = (w >> 3) & 1u;
+                if (da) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] = ca[a] + da;
+                if (KIND == SSD_ENV_HARVEST && db) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a] = cb[a] + db;
             }
         }
     }
@@ -201,7 +228,7 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 // memory only holds lane-strided copies of the per-agent arrays for the two places that index agents
 // dynamically (the warp-cooperative contested-move resolution and the beam walk).
 template <int KIND>
-__global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
+__global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,7 +363,9 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) under[a] = a < n ? (uint32_t)map[rc_off(ag[a], Wp)] : 0u;
     uint32_t on_apple = 0, first = 0;
-    unsigned long long occ_filter = 0ull;
+    AgentCells ac;
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) ac.c[a] = a < n ? (ag[a] & 0xFFFFu) : 0xFFFFFFFFu;
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a < n) {
@@ -345,7 +374,6 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
 #pragma unroll
             for (int b = 0; b < a; b++) if ((ag[b] & 0xFFFFu) == (ag[a] & 0xFFFFu)) dup = true;
             if (!dup) first |= 1u << a;
-            occ_filter |= 1ull << cell_hash((int)(ag[a] & 255u), (int)((ag[a] >> 8) & 255u));
         }
     }
     if (on_apple) {
@@ -392,7 +420,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_logic_kernel(const GridPar
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(map, ags, res, n, s, clean, occ_filter, H, W, Wp);
+            const int nup = g2_fire(map, ags[s * 32], ac, res, clean, H, W, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }
