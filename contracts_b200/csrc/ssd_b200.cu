@@ -31,6 +31,7 @@ struct ssd_handle {
     FeatParams fp;
     int grid_blocks;
     int obs_blocks;          // two-kernel step (ssd_grid2.cuh): grid of the observe kernel; 0 = single-kernel step (v3)
+    int obs_vpl;             // 16-byte map vectors per lane in the observe kernel (1 or 2)
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
@@ -52,14 +53,16 @@ static step_kernel_t step_kernel_fn(int kind, bool rounds4, bool feat)
 static const void* step_kernel_ptr(int kind, bool rounds4, bool feat) { return (const void*)step_kernel_fn(kind, rounds4, feat); }
 
 typedef void (*obs_kernel_t)(const GridParams, const StepIO, uint32_t*);
-static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat)
+template <int KIND, bool FEAT>
+static obs_kernel_t obs_pick(bool rounds4, int vpl)
 {
-    if (kind == SSD_ENV_CLEANUP) {
-        if (rounds4) return feat ? grid_obs_kernel<SSD_ENV_CLEANUP, 4, true> : grid_obs_kernel<SSD_ENV_CLEANUP, 4, false>;
-        return feat ? grid_obs_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, true> : grid_obs_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, false>;
-    }
-    if (rounds4) return feat ? grid_obs_kernel<SSD_ENV_HARVEST, 4, true> : grid_obs_kernel<SSD_ENV_HARVEST, 4, false>;
-    return feat ? grid_obs_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, true> : grid_obs_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false>;
+    if (rounds4) return vpl == 1 ? grid_obs_kernel<KIND, 4, FEAT, 1> : grid_obs_kernel<KIND, 4, FEAT, 2>;
+    return vpl == 1 ? grid_obs_kernel<KIND, MAX_POINT_ROUNDS, FEAT, 1> : grid_obs_kernel<KIND, MAX_POINT_ROUNDS, FEAT, 2>;
+}
+static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat, int vpl)
+{
+    if (kind == SSD_ENV_CLEANUP) return feat ? obs_pick<SSD_ENV_CLEANUP, true>(rounds4, vpl) : obs_pick<SSD_ENV_CLEANUP, false>(rounds4, vpl);
+    return feat ? obs_pick<SSD_ENV_HARVEST, true>(rounds4, vpl) : obs_pick<SSD_ENV_HARVEST, false>(rounds4, vpl);
 }
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
@@ -262,23 +265,25 @@ static int setup_grid(ssd_handle* h)
     int want = (p.E + GRID_WARPS - 1) / GRID_WARPS;
     h->grid_blocks = want < sms * per_sm ? want : sms * per_sm;
 
-    // two-kernel step: observe kernel, per warp [tile | rec slot 0 | rec slot 1 | stage | misc]
-    p.g2_rec = p.tile_r16;
-    p.g2_stage = p.g2_rec + 2 * (p.map_bytes + OBS_HDR_BYTES);
+    // two-kernel step: observe kernel, per warp [tile | stage | misc]
+    p.g2_stage = p.tile_r16;
     p.g2_misc = p.g2_stage + p.stage_r16;
     p.g2_warp_bytes = p.g2_misc + MISC_BYTES;
-    p.g2_smem_bytes = p.sm_warp0 + GRID_WARPS * p.g2_warp_bytes;
+    p.g2_smem_bytes = p.sm_warp0 + OBS_WARPS * p.g2_warp_bytes;
     h->obs_blocks = 0;
     const char* sel = getenv("SSD_GRID_KERNEL");
-    if (!(sel && strcmp(sel, "v3") == 0)) {
+    h->obs_vpl = (p.map_bytes / 16 + 31) / 32;
+    if (!(sel && strcmp(sel, "v3") == 0) && h->obs_vpl <= 2) {
         int per_sm2 = 0;
         for (int feat = 0; feat < 2; feat++)
-            CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0),
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0, h->obs_vpl),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false),
-                                                                  GRID_THREADS, p.g2_smem_bytes));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false, h->obs_vpl),
+                                                                  OBS_WARPS * 32, p.g2_smem_bytes));
         if (per_sm2 < 1) return fail(h, SSD_EUNSUPPORTED, "observe kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
-        h->obs_blocks = want < sms * per_sm2 ? want : sms * per_sm2;
+        const int want_obs = (p.E + OBS_WARPS - 1) / OBS_WARPS;
+        h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
+        if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d\n", OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks);
         if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
     }
     return SSD_OK;
@@ -636,7 +641,7 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
         if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         h->launches++;
-        obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k, h->d_res);
+        obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, h->obs_vpl)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
         if (p.kind == SSD_ENV_HARVEST) { h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res); }
     } else
         step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);

@@ -23,7 +23,9 @@
 #pragma once
 #include "ssd_common.cuh"
 
+#ifndef GRID_WARPS
 #define GRID_WARPS 8
+#endif
 #define GRID_THREADS (GRID_WARPS * 32)
 #define GRID_MIN_BLOCKS 3               // 24 warps / SM: registers <= 80, ~9 KB shared per warp
 #define SCRATCH_DRAWS 256               // u32 draws per warp scratch
@@ -61,8 +63,8 @@ struct GridParams {
     int tile_r16, stage_r16, warp_bytes, off_rec, off_stage, off_misc;
     int sm_thr, sm_won, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
     int obs_items;           // ceil(15 n / 4): 4-row (180 B) work items of the observation gather
-    // observe kernel (ssd_grid2.cuh), per warp: [tile | rec slot 0 | rec slot 1 | stage | misc]
-    int g2_rec, g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
+    // observe kernel (ssd_grid2.cuh), per warp: [tile | stage | misc]
+    int g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;

@@ -27,6 +27,12 @@
 
 #define LOGIC_THREADS 128
 #define LOGIC_WARPS (LOGIC_THREADS / 32)
+#ifndef OBS_WARPS
+#define OBS_WARPS 7           // observe kernel: 4 CTAs of 7 warps per SM (~7 KB shared memory per warp, <= 72 registers)
+#endif
+#ifndef OBS_MAXREG
+#define OBS_MAXREG 72
+#endif
 #define G2_CLAIM 0x01u       // scratch mark in a compact-map byte: cell reserved as a move target
 
 // per-(agent, env) result word
@@ -35,9 +41,6 @@
 #define RS_EATEN_CLOSE 8u           // bit 3     eaten_close_apples
 #define RS_CLOSE_SHIFT 4            // bits 4-8  total_close_apples (0..21)
 #define RS_REWARD_SHIFT 16          // bits 16-31 reward accumulator (int16)
-
-// record bytes the observe kernel needs: map + agents + (t, episode, theta) + (flags, hcount, ...)
-#define OBS_HDR_BYTES 64
 
 __device__ __forceinline__ int rc_off(uint32_t rc, int Wp) { return (int)(rc & 255u) * Wp + (int)((rc >> 8) & 255u); }
 __device__ __forceinline__ uint32_t rc_lex(uint32_t rc) { return ((rc & 255u) << 8) | ((rc >> 8) & 255u); }
@@ -453,59 +456,74 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_reward_kernel(const GridPa
 }
 
 // =============================================================================================
-// OBSERVE: one warp per env.  Spawn + observation windows.  Per warp:
-//   [tile | rec slot 0 | rec slot 1 | stage (obs staging, aliased by the spawn scratch) | misc]
-// A rec slot holds the map + the first OBS_HDR_BYTES of the header.
-template <int KIND, int ROUNDS, bool FEAT>
-__global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_obs_kernel(const GridParams p, const StepIO io,
-                                                                                 uint32_t* __restrict__ res_g)
+// OBSERVE: one warp per env.  Spawn + observation windows.  Per warp: [tile | stage (obs staging, aliased
+// by the spawn scratch) | misc].  The compact map (VPL 16-byte vectors per lane) and the first 14 header
+// words (agents, t, episode, theta, flags, #waste) of the NEXT env are prefetched into registers while
+// the current env is processed; the map goes back to HBM only when the spawn changed it.
+template <int KIND, int ROUNDS, bool FEAT, int VPL>
+__global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const SharedTables tb = load_shared_tables(p, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.g2_warp_bytes;
-    uint8_t* recs = tile + p.g2_rec;
     uint8_t* stage = tile + p.g2_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + p.g2_misc + MISC_MBAR);
     for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
-    if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                                  // tables visible
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
-    const int env_stride = gridDim.x * GRID_WARPS;
-    const uint32_t slot_bytes = (uint32_t)(p.map_bytes + OBS_HDR_BYTES);
-    const MapWords mw = map_words_init(p, lane);
+    const int env_stride = gridDim.x * OBS_WARPS;
+    // tile word of each map word this lane moves (vector v = lane + 32 k covers map words 4 v .. 4 v + 3)
+    const int nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
+    int tw[VPL][4];
+#pragma unroll
+    for (int k = 0; k < VPL; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = 4 * (lane + 32 * k) + j;
+            tw[k][j] = w < nwords ? map_tile_word(p, w) : -1;
+        }
+    uint32_t* tw32 = reinterpret_cast<uint32_t*>(tile);
 
-    int env = blockIdx.x * GRID_WARPS + warp;
+    int env = blockIdx.x * OBS_WARPS + warp;
     uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
     const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
     uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
     const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
-    if (env < p.E && lane == 0) bulk_load(recs, g_rec, slot_bytes, mbar);
-    for (uint32_t it = 0; env < p.E; env += env_stride, it++) {
-        const uint32_t slot = it & 1u;
-        uint8_t* rec = recs + slot * slot_bytes;
-        const uint8_t* hdr = rec + p.map_bytes;
-        // prefetch the next env's record into the other slot (its previous contents may still be leaving
-        // through the map store of the previous iteration: wait until that has been read)
-        if (env + env_stride < p.E && lane == 0) {
-            bulk_wait_read<1>();                      // all but the newest group (an observation store)
-            bulk_load(recs + (slot ^ 1u) * slot_bytes, g_rec + g_rec_step, slot_bytes, mbar + (slot ^ 1u));
+    uint4 pref[VPL];
+    uint32_t hw = 0;                                  // header word `lane` (lanes 0..13)
+    if (env < p.E) {
+#pragma unroll
+        for (int k = 0; k < VPL; k++) if (lane + 32 * k < nvec) pref[k] = reinterpret_cast<const uint4*>(g_rec)[lane + 32 * k];
+        if (lane < 14) hw = reinterpret_cast<const uint32_t*>(g_rec + p.map_bytes)[lane];
+    }
+    for (; env < p.E; env += env_stride) {
+        // ---- map -> padded tile, header scalars
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            if (lane + 32 * k < nvec) {
+                const uint32_t w4[4] = { pref[k].x, pref[k].y, pref[k].z, pref[k].w };
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (tw[k][j] >= 0) tw32[tw[k][j]] = w4[j];
+            }
         }
-        mbar_wait(mbar + slot, (it >> 1) & 1u);
-        tile_expand(p, mw, rec, tile, lane);
-        const uint32_t t = *reinterpret_cast<const uint32_t*>(hdr + RO_T);          // already incremented by the logic kernel
-        const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
-        int hcount = *reinterpret_cast<const int*>(hdr + RO_HCOUNT);
+        const uint32_t t = __shfl_sync(FULL, hw, RO_T / 4);               // already incremented by the logic kernel
+        const uint32_t episode = __shfl_sync(FULL, hw, RO_EPISODE / 4);
+        int hcount = (int)__shfl_sync(FULL, hw, RO_HCOUNT / 4);
         const EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, t };
         int ao = 0, ori = 0;
         if (act_lane) {
-            const uint32_t a = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[lane];
-            ao = ((int)(a & 255u) + SSD_VIEW) * S + 8 + (int)((a >> 8) & 255u);
-            ori = (int)((a >> 16) & 3u);
+            ao = ((int)(hw & 255u) + SSD_VIEW) * S + 8 + (int)((hw >> 8) & 255u);
+            ori = (int)((hw >> 16) & 3u);
+        }
+        // ---- prefetch the next env (in flight while this one is processed)
+        if (env + env_stride < p.E) {
+            const uint8_t* nx = g_rec + g_rec_step;
+#pragma unroll
+            for (int k = 0; k < VPL; k++) if (lane + 32 * k < nvec) pref[k] = reinterpret_cast<const uint4*>(nx)[lane + 32 * k];
+            if (lane < 14) hw = reinterpret_cast<const uint32_t*>(nx + p.map_bytes)[lane];
         }
         __syncwarp();
         if (act_lane) tile[ao] |= OCC_BIT;            // spawn eligibility: "no agent there" (co-located lanes write the same value)
@@ -535,18 +553,24 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_obs_kernel
             const int cleaned = (KIND == SSD_ENV_CLEANUP && act_lane) ? (int)(res_g[(size_t)env * SSD_MAXN + lane] & RS_CLEANED_MASK) : 0;
             write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount, io.feat + (size_t)env * n * p.F);
         }
-        // ---- the map goes back only when the spawn changed it
+        // ---- the map goes back only when the spawn changed it (paint / occupancy stripped)
         if (changed) {
-            tile_compress(p, mw, rec, tile, lane);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_store(g_rec, rec, (uint32_t)p.map_bytes);
-        } else if (lane == 0) bulk_wait_read<0>();   // no map store in flight: the previous observation store must have drained `stage`
+#pragma unroll
+            for (int k = 0; k < VPL; k++) {
+                if (lane + 32 * k < nvec) {
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) w4[j] = tw[k][j] >= 0 ? (tw32[tw[k][j]] & CODE_MASK4) : TILE_FILL4;
+                    reinterpret_cast<uint4*>(g_rec)[lane + 32 * k] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            }
+        }
         // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261)
         const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
+        __syncwarp();
         if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
-        // gather_obs waits (lane 0) until at most the map store above is still in flight, then syncs the warp
-        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
+        // gather_obs waits (lane 0) until the previous observation store has drained `stage`, then syncs the warp
+        gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
         g_rec += g_rec_step; g_obs += g_obs_step;
         __syncwarp();
     }
