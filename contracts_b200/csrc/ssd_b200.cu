@@ -266,7 +266,11 @@ static int setup_grid(ssd_handle* h)
     h->grid_blocks = want < sms * per_sm ? want : sms * per_sm;
 
     // two-kernel step: observe kernel, per warp [tile | stage | misc]
-    p.g2_stage = p.tile_r16;
+    {
+        const int Hp = round_up(H, 4);
+        p.hpw = Hp / 4; p.S2 = 8 + Hp + 8; p.tile2_off = p.tile_r16;
+        p.g2_stage = p.tile2_off + round_up((p.Wp + 2 * SSD_VIEW) * p.S2, 16);
+    }
     p.g2_misc = p.g2_stage + p.stage_r16;
     p.g2_warp_bytes = p.g2_misc + MISC_BYTES;
     p.g2_smem_bytes = p.sm_warp0 + OBS_WARPS * p.g2_warp_bytes;

@@ -65,6 +65,7 @@ struct GridParams {
     int obs_items;           // ceil(15 n / 4): 4-row (180 B) work items of the observation gather
     // observe kernel (ssd_grid2.cuh), per warp: [tile | stage | misc]
     int g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
+    int S2, hpw, tile2_off;  // transposed tile: row stride 8 + Hp + 8, words per transposed row (Hp / 4), byte offset from T
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;
@@ -654,6 +655,35 @@ __device__ __forceinline__ void pack4(uint32_t* dst, uint32_t p0, uint32_t p1, u
     dst[1] = __byte_perm(p1, p2, 0x5421);
     dst[2] = __byte_perm(p2, p3, 0x6542);
 }
+// the staged observation stream of one env (L bytes at stage + shift, congruent to gdst modulo 16) -> HBM:
+// one bulk async store for the 16-byte aligned middle, plain stores for the head / tail
+__device__ __forceinline__ void obs_stream_store(int lane, uint8_t* stage, int shift, bool word_ok, int L, uint8_t* gdst)
+{
+    uint32_t* sw = reinterpret_cast<uint32_t*>(stage + shift);
+    __syncwarp();
+    if (word_ok) {
+        const int a0 = (16 - shift) & 15;               // head bytes up to the first 16-B boundary
+        const int mid = (L - a0) & ~15;
+        const int tail0 = a0 + mid;
+        // head / tail: whole words first, then bytes
+        if (lane < (a0 >> 2)) reinterpret_cast<uint32_t*>(gdst)[lane] = sw[lane];
+        {
+            int tw = (L - tail0) >> 2;
+            if (lane < tw) reinterpret_cast<uint32_t*>(gdst + tail0)[lane] = sw[(tail0 >> 2) + lane];
+            int tb0 = tail0 + tw * 4;
+            if (lane < L - tb0) gdst[tb0 + lane] = (stage + shift)[tb0 + lane];
+        }
+        if (mid > 0) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_store(gdst + a0, stage + shift + a0, (uint32_t)mid);
+        }
+    } else {
+        for (int i = lane; i < L; i += 32) gdst[i] = stage[i];
+    }
+}
+
+
 // PENDING: bulk groups of this lane-0 that may stay in flight while `stage` is rewritten
 template <int PENDING>
 __device__ __forceinline__ void gather_obs(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
@@ -694,27 +724,7 @@ __device__ __forceinline__ void gather_obs(const GridParams& p, int lane, const 
 #pragma unroll
         for (int g4 = 0; g4 < 15; g4++) pack4(dst + 3 * g4, col[4 * g4], col[4 * g4 + 1], col[4 * g4 + 2], col[4 * g4 + 3]);
     }
-    __syncwarp();
-    if (word_ok) {
-        const int a0 = (16 - shift) & 15;               // head bytes up to the first 16-B boundary
-        const int mid = (L - a0) & ~15;
-        const int tail0 = a0 + mid;
-        // head / tail: whole words first, then bytes
-        if (lane < (a0 >> 2)) reinterpret_cast<uint32_t*>(gdst)[lane] = sw[lane];
-        {
-            int tw = (L - tail0) >> 2;
-            if (lane < tw) reinterpret_cast<uint32_t*>(gdst + tail0)[lane] = sw[(tail0 >> 2) + lane];
-            int tb0 = tail0 + tw * 4;
-            if (lane < L - tb0) gdst[tb0 + lane] = (stage + shift)[tb0 + lane];
-        }
-        if (mid > 0) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_store(gdst + a0, stage + shift + a0, (uint32_t)mid);
-        }
-    } else {
-        for (int i = lane; i < L; i += 32) gdst[i] = stage[i];
-    }
+    obs_stream_store(lane, stage, shift, word_ok, L, gdst);
 }
 
 // ---------------------------------------------------------------------------------------------

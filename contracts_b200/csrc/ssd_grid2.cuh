@@ -28,10 +28,10 @@
 #define LOGIC_THREADS 128
 #define LOGIC_WARPS (LOGIC_THREADS / 32)
 #ifndef OBS_WARPS
-#define OBS_WARPS 7           // observe kernel: 4 CTAs of 7 warps per SM (~7 KB shared memory per warp, <= 72 registers)
+#define OBS_WARPS 8           // observe kernel: 3 CTAs of 8 warps per SM (~8.4 KB shared memory per warp, <= 80 registers)
 #endif
 #ifndef OBS_MAXREG
-#define OBS_MAXREG 72
+#define OBS_MAXREG 80
 #endif
 #define G2_CLAIM 0x01u       // scratch mark in a compact-map byte: cell reserved as a move target
 
@@ -455,9 +455,97 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_reward_kernel(const GridPa
     env_rewards<SSD_ENV_HARVEST>(p, io, env, hdr, res_g + (size_t)env * SSD_MAXN, 1, theta, t);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Observation gather of the observe kernel.  The kernel is bound by shared-memory wavefronts (ncu:
+// l1tex__data_pipe_lsu_wavefronts at ~79 % of peak with the byte-wise gather of ssd_grid.cuh, a third of
+// them bank conflicts of the per-pixel tile reads), so here an output row is read as 5 aligned WORDS:
+// every output row of color_view (map_env.py:397-411) is a run of 15 consecutive bytes, forwards or
+// backwards, either of the row-major tile T (UP, DOWN) or of its transpose T2 (LEFT, RIGHT):
+//   UP    out[i][j] = V[i][j]        T : run at origin  + i S,          forwards
+//   DOWN  out[i][j] = V[14-i][14-j]  T : run at origin  + (14 - i) S,   backwards
+//   LEFT  out[i][j] = V[j][14-i]     T2: run at origin2 + (14 - i) S2,  forwards
+//   RIGHT out[i][j] = V[14-j][i]     T2: run at origin2 + i S2,         backwards
+// with V[a][b] = T[origin + a S + b] = T2[origin2 + b S2 + a].  T2 is rebuilt per env from the painted T by
+// 4x4 byte-block transposes (8 PRMT per block, one block per lane).
+__device__ __forceinline__ void transpose_tile(const GridParams& p, int lane, const uint8_t* tile, uint8_t* tile2)
+{
+    const uint32_t* t = reinterpret_cast<const uint32_t*>(tile);
+    uint32_t* t2 = reinterpret_cast<uint32_t*>(tile2);
+    const int S4 = p.S >> 2, S24 = p.S2 >> 2, nbj = p.wpw, nblk = p.hpw * nbj;
+    for (int b = lane; b < nblk; b += 32) {
+        const int bi = (int)(((uint32_t)b * p.wpw_magic) >> 16), bj = b - bi * nbj;   // block row / word column
+        const uint32_t* src = t + (4 * bi + SSD_VIEW) * S4 + 2 + bj;
+        const uint32_t r0 = src[0], r1 = src[S4], r2 = src[2 * S4], r3 = src[3 * S4];
+        const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
+        const uint32_t t2a = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+        uint32_t* dst = t2 + (4 * bj + SSD_VIEW) * S24 + 2 + bi;
+        dst[0] = __byte_perm(t0, t1, 0x5410);
+        dst[S24] = __byte_perm(t0, t1, 0x7632);
+        dst[2 * S24] = __byte_perm(t2a, t3, 0x5410);
+        dst[3 * S24] = __byte_perm(t2a, t3, 0x7632);
+    }
+}
+
+// ao: the agent's cell in T.  `tile` is the base of [T | T2]; vdesc entries hold offsets relative to it.
+__device__ __forceinline__ void gather_obs2(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
+                                            const uint32_t* sm_pal, int4* vdesc, int ao, int ori, uint8_t* gdst)
+{
+    const int n = p.n, S = p.S, S2 = p.S2;
+    const int L = n * SSD_OBS_BYTES;
+    const uint32_t gaddr = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    const bool word_ok = (gaddr & 3u) == 0;
+    const int shift = word_ok ? (int)gaddr : 0;          // staged stream is congruent to gdst modulo 16
+    uint32_t* sw = reinterpret_cast<uint32_t*>(stage + shift);
+    if (lane < n) {
+        const uint32_t trow = __umulhi((uint32_t)ao, p.s_magic);            // ao / S
+        const int row = (int)trow - SSD_VIEW, col = ao - (int)trow * S - 8;
+        const int origin = ao - SSD_VIEW * S - SSD_VIEW;                     // V[0][0] in T
+        const int origin2 = p.tile2_off + (col + SSD_VIEW) * S2 + 8 + row - SSD_VIEW * S2 - SSD_VIEW;   // V[0][0] in T2
+        const int last = SSD_OBSW - 1;
+        int lo0 = origin, rstep = S, back = 0;                                // UP
+        if (ori == ORI_DOWN) { lo0 = origin + last * S; rstep = -S; back = 1; }
+        else if (ori == ORI_LEFT) { lo0 = origin2 + last * S2; rstep = -S2; }
+        else if (ori == ORI_RIGHT) { lo0 = origin2; rstep = S2; back = 1; }
+        vdesc[lane] = make_int4(lo0, rstep, back, 0);
+    }
+    if (lane == 0) bulk_wait_read<0>();                  // the previous env's store has drained `stage`
+    __syncwarp();
+    if (lane < p.obs_items) {
+        uint32_t col[60];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int r = 4 * lane + q;
+            int a = (int)(((uint32_t)r * 0x8889u) >> 19);    // r / 15
+            int i = r - 15 * a;
+            if (a >= n) { a = n - 1; i = SSD_OBSW - 1; }     // rows past the stream end: harmless in-bounds reads
+            const int4 d = vdesc[a];
+            const int lo = d.x + i * d.y;                     // lowest byte of the 15-byte run
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(tile + (lo & ~3));
+            const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3], w4 = wsrc[4];
+            const uint32_t sh = (uint32_t)(lo & 3) * 8u;
+            uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);
+            uint32_t b2 = __funnelshift_r(w2, w3, sh), b3 = __funnelshift_r(w3, w4, sh);   // bytes lo .. lo + 15
+            if (d.z) {                                        // backwards: pixel j is byte 14 - j
+                const uint32_t r0 = __byte_perm(b2, b3, 0x3456), r1 = __byte_perm(b1, b2, 0x3456);
+                const uint32_t r2 = __byte_perm(b0, b1, 0x3456), r3 = __byte_perm(b0, b0, 0x0012);
+                b0 = r0; b1 = r1; b2 = r2; b3 = r3;
+            }
+            const uint32_t bw[4] = { b0, b1, b2, b3 };
+#pragma unroll
+            for (int j = 0; j < SSD_OBSW; j++)               // a tile byte IS the byte offset of its palette entry
+                col[15 * q + j] = *reinterpret_cast<const uint32_t*>(
+                    reinterpret_cast<const uint8_t*>(sm_pal) + __byte_perm(bw[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3)));
+        }
+        uint32_t* dst = sw + 45 * lane;
+#pragma unroll
+        for (int g4 = 0; g4 < 15; g4++) pack4(dst + 3 * g4, col[4 * g4], col[4 * g4 + 1], col[4 * g4 + 2], col[4 * g4 + 3]);
+    }
+    obs_stream_store(lane, stage, shift, word_ok, L, gdst);
+}
+
 // =============================================================================================
 // OBSERVE: one warp per env.  Spawn + observation windows.  Per warp: [tile | stage (obs staging, aliased
-// by the spawn scratch) | misc].  The compact map (VPL 16-byte vectors per lane) and the first 14 header
+// by the spawn scratch) | misc], tile = [T | T2 (transposed)].  The compact map (VPL 16-byte vectors per lane) and the first 14 header
 // words (agents, t, episode, theta, flags, #waste) of the NEXT env are prefetched into registers while
 // the current env is processed; the map goes back to HBM only when the spawn changed it.
 template <int KIND, int ROUNDS, bool FEAT, int VPL>
@@ -470,7 +558,8 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
     uint8_t* stage = tile + p.g2_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
-    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
+    uint8_t* tile2 = tile + p.tile2_off;             // transposed tile (gather_obs2)
+    for (int i = lane; i < (p.g2_stage >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;   // T and T2
     __syncthreads();                                  // tables visible
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
@@ -569,8 +658,10 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
         const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
         __syncwarp();
         if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
-        // gather_obs waits (lane 0) until the previous observation store has drained `stage`, then syncs the warp
-        gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
+        __syncwarp();
+        transpose_tile(p, lane, tile, tile2);
+        // gather_obs2 waits (lane 0) until the previous observation store has drained `stage`, then syncs the warp
+        gather_obs2(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
         g_rec += g_rec_step; g_obs += g_obs_step;
         __syncwarp();
     }
