@@ -309,6 +309,29 @@ def main():
             state["t"] = 0
     barrier()
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    # per-kernel split of the step (library-side CUDA events around each kernel), sampled every 10th step of one more episode
+    kern_ms = None
+    try:
+        env.enable_timing(True)
+        acc = []
+        for k in range(HORIZON):
+            if state["t"] == 0:
+                new_episode()
+            env.random_actions(state["global_step"], N_ACTIONS, out=actions)
+            env.step(actions, extras=False)
+            if k % 10 == 5:
+                acc.append(env.step_times_ms())
+            state["t"] += 1
+            state["global_step"] += 1
+            if state["t"] == HORIZON:
+                state["stats"] = end_episode()
+                state["t"] = 0
+        kern_ms = (float(np.mean([a for a, _ in acc])), float(np.mean([b for _, b in acc])))
+    except Exception as exc:                                     # single-kernel fallback (SSD_GRID_KERNEL=v3) has no split
+        print("per-kernel timing unavailable: %s" % exc, file=sys.stderr)
+    finally:
+        env.enable_timing(False)
+    barrier()
 
     # ---- e2e: host buffers in, host results out, sync every step ----------------------------------
     Ke = min(args.e2e_steps, K)
@@ -370,9 +393,18 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(E, n), "alg_bytes_per_launch": ALG_BYTES_PER_AGENT_STEP * E * n,
-                         "peak_source": peak_src, "kernel": "grid_step_kernel<cleanup>",
+                         "peak_source": peak_src,
+                         "kernel": "one env step = grid_logic_kernel + grid_obs_kernel (cleanup), CUDA events around ssd_step",
                          "kernel_ms": step_ms, "alg_bytes_per_agent_step": ALG_BYTES_PER_AGENT_STEP},
         }
+        if kern_ms is not None:
+            # the dominant kernel on its own: observation stream + the map / header words it reads (+ the map when the
+            # spawn changed it, ~1/3 of the steps): 5400 + 464 + 56 + 464/3 B per env
+            obs_alg = (n * 675 + env.state_map_bytes + 56 + env.state_map_bytes / 3.0) * E
+            line["roofline"]["kernels"] = [
+                {"name": "grid_logic_kernel", "ms": kern_ms[0]},
+                {"name": "grid_obs_kernel", "ms": kern_ms[1], "alg_bytes_per_launch": obs_alg,
+                 "achieved": obs_alg / (kern_ms[1] * 1e-3) / 1e9, "frac": obs_alg / (kern_ms[1] * 1e-3) / 1e9 / peak}]
         if state["stats"] is not None:
             s = state["stats"].tolist()
             line["episode_stats"] = {"apples_eaten": s[0], "raw_env_rewards": s[1], "transfers": s[2],

@@ -55,7 +55,7 @@ EXPORTS = [
     "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_last_error", "ssd_reset", "ssd_step",
     "ssd_set_contract_params", "ssd_negotiate", "ssd_get_state", "ssd_set_state", "ssd_get_metrics",
     "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
-    "ssd_kernel_launches", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
+    "ssd_kernel_launches", "ssd_enable_timing", "ssd_get_step_times", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
     "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
 ]
 
@@ -101,6 +101,8 @@ def load():
     L.ssd_state_bytes_per_env.restype = i64
     L.ssd_kernel_launches.argtypes = [vp]
     L.ssd_kernel_launches.restype = i64
+    L.ssd_enable_timing.argtypes = [vp, ctypes.c_int32]
+    L.ssd_get_step_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     if L.ssd_abi_version() != SSD_ABI_VERSION:
         raise SsdError("libssd_b200.so ABI %d != binding ABI %d" % (L.ssd_abi_version(), SSD_ABI_VERSION))
     _LIB = L

@@ -178,6 +178,21 @@ class BatchedGridEnv:
     def kernel_launches(self):
         return int(self.lib.ssd_kernel_launches(self._h))
 
+    def enable_timing(self, on=True):
+        """bracket the step's kernels with CUDA events (measurement only; not graph-capturable)"""
+        _lib.check(self._h, self.lib.ssd_enable_timing(self._h, 1 if on else 0))
+
+    def step_times_ms(self):
+        """(logic kernel ms, observe kernel ms) of the last step taken with timing enabled"""
+        out = (ctypes.c_double * 2)()
+        _lib.check(self._h, self.lib.ssd_get_step_times(self._h, out))
+        return float(out[0]), float(out[1])
+
+    @property
+    def state_map_bytes(self):
+        """bytes of the compact map inside an env record (rows padded to 4 cells, total to 16 bytes)"""
+        return ((self.H * ((self.W + 3) // 4 * 4)) + 15) // 16 * 16
+
     @property
     def state_bytes_per_env(self):
         return int(self.lib.ssd_state_bytes_per_env(self._h))

@@ -32,6 +32,8 @@ struct ssd_handle {
     int grid_blocks;
     int obs_blocks;          // two-kernel step (ssd_grid2.cuh): grid of the observe kernel; 0 = single-kernel step (v3)
     int obs_vpl;             // 16-byte map vectors per lane in the observe kernel (1 or 2)
+    cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
+    bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
@@ -570,6 +572,8 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     ssd_handle* h = new ssd_handle();
     h->cfg = *cfg;
     h->launches = 0;
+    h->timing = false;
+    h->tev[0] = h->tev[1] = h->tev[2] = nullptr;
     h->err[0] = 0;
     if (cfg->ascii_map) h->ascii.assign(cfg->ascii_map, (size_t)cfg->map_h * cfg->map_w);
     h->cfg.ascii_map = h->ascii.c_str();
@@ -590,6 +594,7 @@ void ssd_destroy(ssd_handle* h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     for (void* d : h->dev_allocs) cudaFree(d);
+    for (int i = 0; i < 3; i++) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
     delete h;
 }
 
@@ -642,11 +647,14 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
     cudaStream_t s = (cudaStream_t)stream;
     if (h->obs_blocks > 0) {
         const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
+        if (h->timing) cudaEventRecord(h->tev[0], s);
         if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         h->launches++;
+        if (h->timing) cudaEventRecord(h->tev[1], s);
         obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, h->obs_vpl)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
         if (p.kind == SSD_ENV_HARVEST) { h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res); }
+        if (h->timing) cudaEventRecord(h->tev[2], s);
     } else
         step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
     return check_launch(h, "step");
@@ -790,6 +798,30 @@ int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, f
                                                                                          lo, hi, actions_dev);
     if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "selfdrive_random_actions");
+}
+
+int ssd_enable_timing(ssd_handle* h, int32_t on)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    if (on && !h->tev[0])
+        for (int i = 0; i < 3; i++) CUDA_TRY(h, cudaEventCreate(&h->tev[i]));
+    h->timing = on != 0;
+    return SSD_OK;
+}
+
+int ssd_get_step_times(ssd_handle* h, double* out_ms)
+{
+    if (!h || !out_ms) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    if (!h->tev[0]) return fail(h, SSD_EINVAL, "ssd_get_step_times: timing was never enabled");
+    float a = 0.f, b = 0.f;
+    CUDA_TRY(h, cudaEventSynchronize(h->tev[2]));
+    if (h->obs_blocks <= 0) return fail(h, SSD_EUNSUPPORTED, "ssd_get_step_times: the single-kernel step has no per-kernel times");
+    CUDA_TRY(h, cudaEventElapsedTime(&a, h->tev[0], h->tev[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&b, h->tev[1], h->tev[2]));
+    out_ms[0] = a; out_ms[1] = b;
+    return SSD_OK;
 }
 
 int ssd_feature_dim(const ssd_handle* h)

@@ -196,6 +196,11 @@ void ssd_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 int ssd_abi_version(void);
 int ssd_feature_dim(const ssd_handle* h);          /* F of feature_obs_dev */
 int64_t ssd_state_bytes_per_env(const ssd_handle* h);
+/* Measurement only (bench.py roofline): with timing on, ssd_step brackets its kernels with CUDA events on the
+ * launch stream (not capturable in a CUDA graph).  ssd_get_step_times waits for the last step and returns
+ * out_ms[0] = logic kernel, out_ms[1] = observe (+ harvest reward) kernel, in milliseconds. */
+int ssd_enable_timing(ssd_handle* h, int32_t on);
+int ssd_get_step_times(ssd_handle* h, double* out_ms);
 int64_t ssd_kernel_launches(const ssd_handle* h);  /* kernels launched through this handle so far */
 
 #ifdef __cplusplus
