@@ -14,6 +14,7 @@ SSD_ABI_VERSION = 2
 ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "selfdrive": 4}
 CONTRACT_KIND = {None: 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2,
                  "SelfdriveContractDistprop": 3}
+FLAG_COLLECTIVE_REWARD, FLAG_INEQUITY_AVERSE = 1, 2     # SSD_FLAG_* (ssd_config.flags)
 OBS_BYTES_PER_AGENT = 675
 METRIC_STRIDE = 56
 

@@ -36,7 +36,8 @@ class BatchedGridEnv:
 
     def __init__(self, kind, num_envs, num_agents, ascii_map=None, horizon=1000, contract=None,
                  theta_low=0.0, theta_high=None, null_prob=0.0, seed=73907, first_env_id=0,
-                 device=None, padded_obs=False):
+                 device=None, padded_obs=False,
+                 use_collective_reward=False, inequity_averse_reward=False, alpha=0.0, beta=0.0):
         if kind not in ("cleanup_new", "harvest_new"):
             raise ValueError("BatchedGridEnv kind must be cleanup_new or harvest_new, got %r" % (kind,))
         if not torch.cuda.is_available():
@@ -62,7 +63,11 @@ class BatchedGridEnv:
             map_h=self.H, map_w=self.W, ascii_map=self._flat, horizon=self.horizon,
             contract_kind=_lib.CONTRACT_KIND[contract], theta_low=self.theta_low, theta_high=self.theta_high,
             null_prob=float(null_prob), seed=self.seed, first_env_id=self.first_env_id,
-            device=self.device.index or 0, flags=0)
+            device=self.device.index or 0,
+            # MapEnv reward shaping kwargs (map_env.py:69-72,289-301)
+            flags=(_lib.FLAG_COLLECTIVE_REWARD if use_collective_reward else 0)
+            | (_lib.FLAG_INEQUITY_AVERSE if inequity_averse_reward else 0))
+        cfg.env_params[0], cfg.env_params[1] = float(alpha), float(beta)
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))

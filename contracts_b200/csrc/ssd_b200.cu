@@ -170,7 +170,13 @@ static int setup_grid(ssd_handle* h)
     p.wpw = p.Wp / 4; p.wpw_magic = (65536u + p.wpw - 1) / p.wpw;
     p.s_magic = (uint32_t)((4294967296ull + p.S - 1) / p.S);
     p.map_bytes = round_up(H * p.Wp, 16);
-    p.rec_stride = p.map_bytes + RO_SIZE;
+    p.reward_mode = c.flags & (SSD_FLAG_COLLECTIVE_REWARD | SSD_FLAG_INEQUITY_AVERSE);
+    if (c.flags & ~(SSD_FLAG_COLLECTIVE_REWARD | SSD_FLAG_INEQUITY_AVERSE)) return fail(h, SSD_EINVAL, "unknown flags 0x%x", c.flags);
+    if ((p.reward_mode & RM_INEQUITY) && n < 2)          // assert self.num_agents > 1 (map_env.py:294)
+        return fail(h, SSD_EINVAL, "inequity_averse_reward needs more than one agent");
+    p.alpha = c.env_params[0]; p.beta = c.env_params[1];
+    p.hdr_bytes = p.reward_mode ? RO_XSIZE : RO_SIZE;
+    p.rec_stride = p.map_bytes + p.hdr_bytes;
     p.kind = c.env_kind; p.contract = c.contract_kind; p.horizon = c.horizon;
     p.seed = c.seed; p.first_env_id = c.first_env_id;
     p.theta_low = c.theta_low; p.theta_high = c.theta_high; p.null_prob = c.null_prob;
@@ -471,14 +477,19 @@ __global__ void get_metrics_kernel(GridParams p, double* out)
         raw += (double)sr;
         o[8 + a] = (double)reinterpret_cast<const uint32_t*>(hdr + RO_AGENT_A)[a];
         o[16 + a] = (double)reinterpret_cast<const uint32_t*>(hdr + RO_AGENT_B)[a];
-        o[24 + a] = (double)sr;
-        o[32 + a] = (double)reinterpret_cast<const long long*>(hdr + RO_TSUM_RAW)[a];
+        if (p.reward_mode) {                           // shaped rewards: float64 sums in the record extension
+            o[24 + a] = reinterpret_cast<const double*>(hdr + RO_XSUM)[a];
+            o[32 + a] = reinterpret_cast<const double*>(hdr + RO_XTSUM)[a];
+        } else {
+            o[24 + a] = (double)sr;
+            o[32 + a] = (double)reinterpret_cast<const long long*>(hdr + RO_TSUM_RAW)[a];
+        }
         o[40 + a] = reinterpret_cast<const double*>(hdr + RO_SUM_TR)[a];
         o[48 + a] = reinterpret_cast<const double*>(hdr + RO_TSUM_TR)[a];
     }
     o[0] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_APPLES);
     o[1] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_LOWDENS);
-    o[2] = raw;
+    o[2] = p.reward_mode ? *reinterpret_cast<const double*>(hdr + RO_XRAW) : raw;
     o[3] = *reinterpret_cast<const double*>(hdr + RO_TRANSFERS);
     o[4] = (double)*reinterpret_cast<const uint32_t*>(hdr + RO_DIRT);
     o[5] = (double)((*reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS) >> RF_ERR_SHIFT) & 0xFFFFu);

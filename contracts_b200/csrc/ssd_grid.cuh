@@ -51,13 +51,24 @@
 #define RO_AGENT_A 304     // u32[8] waste_cleaned | apples_consumed
 #define RO_AGENT_B 336     // u32[8] close_apples_consumed
 #define RO_SIZE 368
+// extension, present only when rewards are shaped (use_collective_reward / inequity_averse_reward,
+// map_env.py:289-301): the env rewards are float64 then, so their episode sums are too
+#define RO_XSUM 368        // f64[8] sum_t r
+#define RO_XTSUM 432       // f64[8] sum_t t * r
+#define RO_XRAW 496        // f64 metrics['raw_env_rewards']
+#define RO_XSIZE 512
+#define RM_COLLECTIVE 1
+#define RM_INEQUITY 2
 
 struct GridParams {
     int E, n, H, W, Wp, S, TH;
     int wpw;                 // words per map row (Wp / 4)
     uint32_t wpw_magic;      // ceil(65536 / wpw): q = (w * magic) >> 16 for w < 65536 / wpw
     int map_bytes;           // H * Wp rounded up to 16
-    int rec_stride;          // map_bytes + RO_SIZE (multiple of 16: one bulk copy moves a record)
+    int rec_stride;          // map_bytes + hdr_bytes (multiple of 16: one bulk copy moves a record)
+    int hdr_bytes;           // RO_SIZE, or RO_XSIZE when rewards are shaped
+    int reward_mode;         // RM_* bits
+    double alpha, beta;      // inequity aversion weights (map_env.py:71-72)
     // shared memory layout.  CTA tables first, then one region per warp:
     //   [tile | rec slot 0 | rec slot 1 | stage (obs staging, aliased by the spawn scratch) | misc]
     int tile_r16, stage_r16, warp_bytes, off_rec, off_stage, off_misc;
@@ -84,6 +95,29 @@ struct GridParams {
     const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
     uint8_t* state;
 };
+
+// use_collective_reward / inequity_averse_reward (map_env.py:289-301): the shaped reward of agent a from the
+// integer env rewards ri[0..n).  Differences and their partial sums are exact integers; alpha * sum,
+// beta * sum, their sum, the division by (num_agents - 1) and the subtraction are float64, in that order.
+__device__ __noinline__ double shaped_reward(const GridParams& p, const int* ri, int a)
+{
+    const int n = p.n;
+    int coll = 0;
+    for (int j = 0; j < n; j++) coll += ri[j];
+    const bool collective = p.reward_mode & RM_COLLECTIVE;
+    const int ra = collective ? coll : ri[a];
+    double r = (double)ra;
+    if (p.reward_mode & RM_INEQUITY) {
+        int sp = 0, sn = 0;
+        for (int j = 0; j < n; j++) {
+            const int d = (collective ? coll : ri[j]) - ra;
+            if (d > 0) sp += d; else sn += d;
+        }
+        const double dis = __dmul_rn(p.alpha, (double)sp), adv = __dmul_rn(p.beta, (double)sn);
+        r = __dsub_rn(r, __ddiv_rn(__dadd_rn(dis, adv), (double)(n - 1)));
+    }
+    return r;
+}
 
 // per-warp misc area
 #define MISC_VDESC 0        // int4[8]: per-agent view descriptor {offset of out[0][0], pixel step, row step, 0}
@@ -888,7 +922,13 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
         tile_compress(p, mw, rec, tile, lane);
 
         // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
-        const double base = (double)reward;
+        double base = (double)reward;
+        if (p.reward_mode) {                           // shaped env rewards (map_env.py:289-301)
+            int ri[SSD_MAXN];
+#pragma unroll
+            for (int j = 0; j < SSD_MAXN; j++) ri[j] = __shfl_sync(FULL, reward, j);
+            if (act_lane) base = shaped_reward(p, ri, lane);
+        }
         double tr = 0.0;
         if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
         else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (total_close < 4 && eaten_close > 0) ? theta : 0.0;
@@ -904,6 +944,9 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             }
         }
         const bool done = t == p.horizon;
+        double raw_step = 0.0;
+        if (p.reward_mode)
+            for (int i = 0; i < n; i++) raw_step = __dadd_rn(raw_step, __shfl_sync(FULL, base, i));
         if (act_lane) {
             size_t o = (size_t)env * n + lane;
             io.rew[o] = r;
@@ -915,7 +958,12 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             uint32_t trow = __umulhi((uint32_t)ao, p.s_magic);
             uint32_t row = trow - SSD_VIEW, col = (uint32_t)ao - trow * (uint32_t)S - 8u;
             reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
-            if (reward != 0) {
+            if (p.reward_mode) {
+                double* xs = reinterpret_cast<double*>(hdr + RO_XSUM) + lane;
+                double* xt = reinterpret_cast<double*>(hdr + RO_XTSUM) + lane;
+                *xs = __dadd_rn(*xs, base);
+                *xt = __dadd_rn(*xt, __dmul_rn((double)(t - 1), base));
+            } else if (reward != 0) {
                 reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
                 reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[lane] += (long long)(t - 1) * reward;
             }
@@ -945,6 +993,10 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             if (p.contract != SSD_CONTRACT_NONE) {
                 double* mt = reinterpret_cast<double*>(hdr + RO_TRANSFERS);
                 *mt = __dadd_rn(*mt, total_tr);
+            }
+            if (p.reward_mode) {                       // raw_rewards = ((0 + r0) + r1) + ... (cleanup_new.py:228-232)
+                double* xr = reinterpret_cast<double*>(hdr + RO_XRAW);
+                *xr = __dadd_rn(*xr, raw_step);
             }
             if (io.done) io.done[env] = done ? 1 : 0;
         }
@@ -1049,7 +1101,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
             uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
             reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
         }
-        for (int i = lane; i < (RO_SIZE - RO_T) / 4; i += 32) reinterpret_cast<uint32_t*>(hdr + RO_T)[i] = 0u;
+        for (int i = lane; i < (p.hdr_bytes - RO_T) / 4; i += 32) reinterpret_cast<uint32_t*>(hdr + RO_T)[i] = 0u;
         __syncwarp();
         if (lane == 0) {
             *reinterpret_cast<uint32_t*>(hdr + RO_EPISODE) = episode;

@@ -126,6 +126,26 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
     double rj[SSD_MAXN];
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) rj[a] = a < n ? (double)((int)rsp[a * rstride] >> RS_REWARD_SHIFT) : 0.0;
+    if (p.reward_mode) {                               // shaped env rewards (map_env.py:289-301) and their f64 episode sums
+        int ri[SSD_MAXN];
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) ri[a] = a < n ? ((int)rsp[a * rstride] >> RS_REWARD_SHIFT) : 0;
+        double raw_step = 0.0;                         // raw_rewards = ((0 + r0) + r1) + ... (cleanup_new.py:228-232)
+        const double tm1s = (double)(t - 1);
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a < n) {
+                rj[a] = shaped_reward(p, ri, a);
+                raw_step = __dadd_rn(raw_step, rj[a]);
+                double* xs = reinterpret_cast<double*>(hdr + RO_XSUM) + a;
+                double* xt = reinterpret_cast<double*>(hdr + RO_XTSUM) + a;
+                *xs = __dadd_rn(*xs, rj[a]);
+                *xt = __dadd_rn(*xt, __dmul_rn(tm1s, rj[a]));
+            }
+        }
+        double* xr = reinterpret_cast<double*>(hdr + RO_XRAW);
+        *xr = __dadd_rn(*xr, raw_step);
+    }
     if (io.base_rew) {
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) if (a < n) io.base_rew[o + a] = rj[a];
@@ -174,7 +194,7 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
     }
     // episode accumulators: all loads of a group first (one memory round trip), then the stores.  Adding a
     // zero reward leaves an accumulator bit-identical (sums are never -0.0), so untouched groups are skipped.
-    if (any_raw) {
+    if (any_raw && !p.reward_mode) {
         int sr[SSD_MAXN]; long long ts[SSD_MAXN];
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) if (a < n) { sr[a] = reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a]; ts[a] = reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a]; }

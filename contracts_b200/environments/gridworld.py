@@ -9,9 +9,13 @@ Differences from the reference that a caller can observe:
   * randomness is a counter-based Philox stream keyed (seed, env_id) instead of the process-global
     NumPy / stdlib generators (kwargs `seed`, `env_id`); given the same draws the results are
     bit-identical (tests/test_dropin_api.py replays the reference's golden vectors through this API);
-  * beams are not drawn by `render()` (the reference paints them only into the rendered full map);
-  * `return_agent_actions`, `use_collective_reward`, `inequity_averse_reward` (off in every shipped
-    config) are rejected loudly.
+  * beams are not drawn by `render()` (the reference paints them only into the rendered full map).
+
+`use_collective_reward` / `inequity_averse_reward` (+ `alpha`, `beta`; map_env.py:289-301) run on the
+device (fused into the reward write).  `return_agent_actions` is accepted and has, as in the reference,
+no effect on what CleanupEnv / HarvestEnv return: their `step`/`reset` keep only `curr_obs` of the
+MapEnv observation dict (cleanup_new.py:204,258; harvest_new.py:171,230), so `other_agent_actions`,
+`visible_agents` and `prev_visible_agents` (map_env.py:271-282) never reach the caller.
 """
 import numpy as np
 import torch
@@ -36,9 +40,11 @@ class _GridWorldEnv:
                  return_agent_actions=False, use_collective_reward=False, inequity_averse_reward=False,
                  alpha=0.0, beta=0.0, horizon=1000, one_hot_id=False,
                  num_envs=1, seed=73907, env_id=0, device=None, **kwargs):
-        if return_agent_actions or use_collective_reward or inequity_averse_reward:
-            raise NotImplementedError("return_agent_actions / use_collective_reward / inequity_averse_reward "
-                                      "are not part of the accelerated path")
+        if inequity_averse_reward and int(num_agents) < 2:
+            raise AssertionError("Cannot use inequity aversion with only one agent!")     # map_env.py:294
+        self.return_agent_actions = return_agent_actions
+        self.use_collective_reward, self.inequity_averse_reward = bool(use_collective_reward), bool(inequity_averse_reward)
+        self.alpha, self.beta = alpha, beta
         self.ascii_map = list(self.DEFAULT_MAP if ascii_map is None else ascii_map)
         self.num_agents = int(num_agents)
         self.disable_firing, self.image_obs, self.one_hot_id = disable_firing, image_obs, one_hot_id
@@ -78,7 +84,10 @@ class _GridWorldEnv:
             c = self._contract or (None, 0.0, 0.0, 0.0)
             self._batch = BatchedGridEnv(self.KIND, self.num_envs, self.num_agents, self.ascii_map, horizon=self.horizon,
                                          contract=c[0], theta_low=c[1], theta_high=c[2], null_prob=c[3],
-                                         seed=self.seed, first_env_id=self.env_id, device=self.device)
+                                         seed=self.seed, first_env_id=self.env_id, device=self.device,
+                                         use_collective_reward=self.use_collective_reward,
+                                         inequity_averse_reward=self.inequity_averse_reward,
+                                         alpha=self.alpha, beta=self.beta)
         return self._batch
 
     def _bind_contract(self, name, low, high, null_prob):
@@ -131,7 +140,8 @@ class _GridWorldEnv:
             infos[k]["feature_obs"] = L["feat"][i].copy()
         d = L["done"]
         dones = {"__all__": d, "a0": d, "a1": d}            # the reference hard-codes these keys (cleanup_new.py:242)
-        rews = {k: int(L["base_rew"][i]) for i, k in enumerate(self.agent_ids)}
+        rews = {k: (np.float64(L["base_rew"][i]) if self.inequity_averse_reward else int(L["base_rew"][i]))
+                for i, k in enumerate(self.agent_ids)}
         if not self.image_obs:
             obs_d = {k: L["feat"][i].copy() for i, k in enumerate(self.agent_ids)}
         else:
@@ -149,12 +159,16 @@ class _GridWorldEnv:
         m = self._metrics_from_raw(raw)
         m["transfers"] = self._num(raw[3])
         if self.timesteps == self.horizon:
-            m["equality"] = equality([int(x) for x in raw[24:24 + n]])
-            m["sustainability"] = sustainability([int(x) for x in raw[24:24 + n]], [int(x) for x in raw[32:32 + n]])
+            m["equality"] = equality([self._rew(x) for x in raw[24:24 + n]])
+            m["sustainability"] = sustainability([self._rew(x) for x in raw[24:24 + n]], [self._rew(x) for x in raw[32:32 + n]])
             if self._contract is not None and self._contract[0] is not None:
                 m["transfer_sustainability"] = sustainability(list(raw[40:40 + n]), list(raw[48:48 + n]))
                 m["transfer_equality"] = equality(list(raw[40:40 + n]))
         return m
+
+    def _rew(self, x):
+        """Env rewards are Python ints unless inequity aversion made them float64 (map_env.py:293-300)."""
+        return float(x) if self.inequity_averse_reward else int(x)
 
     @staticmethod
     def _num(x):
@@ -235,7 +249,7 @@ class CleanupEnv(_GridWorldEnv):
         return {"eaten_apples": int(row[0]), "cleaned_squares": int(row[1])}
 
     def _metrics_from_raw(self, raw):
-        m = {"total_apples_eaten": int(raw[0]), "raw_env_rewards": int(raw[2]), "dirt_cleaned": int(raw[4])}
+        m = {"total_apples_eaten": int(raw[0]), "raw_env_rewards": self._rew(raw[2]), "dirt_cleaned": int(raw[4])}
         for i in range(self.num_agents):
             m["a%d-waste_cleaned" % i] = int(raw[8 + i])
         return m
@@ -273,7 +287,7 @@ class HarvestEnv(_GridWorldEnv):
         return {"eaten_apples": int(row[0]), "eaten_close_apples": int(row[1])}
 
     def _metrics_from_raw(self, raw):
-        m = {"total_apples_eaten": int(raw[0]), "low_density_apples_eaten": int(raw[1]), "raw_env_rewards": int(raw[2])}
+        m = {"total_apples_eaten": int(raw[0]), "low_density_apples_eaten": int(raw[1]), "raw_env_rewards": self._rew(raw[2])}
         for i in range(self.num_agents):
             m["a%d-apples_consumed" % i] = int(raw[8 + i])
             m["a%d-close_apples_consumed" % i] = int(raw[16 + i])

@@ -59,6 +59,11 @@ extern "C" {
 
 typedef struct ssd_handle ssd_handle;
 
+/* ssd_config.flags, cleanup_new / harvest_new: MapEnv kwargs use_collective_reward and
+ * inequity_averse_reward (map_env.py:69-70): reward shaping at the end of MapEnv.step (map_env.py:289-301) */
+#define SSD_FLAG_COLLECTIVE_REWARD 1
+#define SSD_FLAG_INEQUITY_AVERSE 2
+
 typedef struct ssd_config {
     int32_t abi_version;      /* SSD_ABI_VERSION */
     int32_t env_kind;
@@ -74,9 +79,11 @@ typedef struct ssd_config {
     uint32_t seed;            /* Philox key word 0 */
     uint32_t first_env_id;    /* global id of env 0 (Philox key word 1 = first_env_id + i) */
     int32_t device;           /* CUDA device ordinal */
-    int32_t flags;            /* reserved, 0 */
+    int32_t flags;            /* SSD_FLAG_* bits (gridworlds), else 0 */
     double env_params[8];     /* selfdrive: low_bound, high_bound, start_vel, start_vel_ambulance
-                                 (SelfAcceleratingCarEnv.__init__, self_driving_car_accelerate.py:19); else unused */
+                                 (SelfAcceleratingCarEnv.__init__, self_driving_car_accelerate.py:19);
+                                 cleanup_new / harvest_new: alpha, beta of inequity_averse_reward
+                                 (map_env.py:71-72,293-300); else unused */
 } ssd_config;
 
 /* Buffers of one step.  Gridworld / feature envs: actions are uint8 [E][n] action ids

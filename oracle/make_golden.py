@@ -33,6 +33,22 @@ SCENARIOS = {
                            [.22, .22, .22, .22, .03, .03, .03, .03]),
     "cleanup_open_n6": ("cleanup", 6, 44, 11, OPEN_CLEANUP, 1000, 1, 300, 9, None),
     "cleanup_n8_nocontract": ("cleanup", 8, 3, 5, None, 1000, 1, 120, 9, None),
+    # use_collective_reward / inequity_averse_reward (map_env.py:289-301); short horizons so that the episode
+    # metrics (equality / sustainability over the shaped rewards) are produced
+    "cleanup_n4_collective": ("cleanup", 4, 51, 21, None, 60, 2, 60, 9, None),
+    "harvest_n5_inequity": ("harvest", 5, 52, 22, None, 50, 2, 50, 8, None),
+    "cleanup_cramped_n8_inequity": ("cleanup", 8, 53, 23, CRAMPED_CLEANUP, 80, 2, 80, 9,
+                                    [.16, .16, .16, .16, .04, .04, .04, .12, .12]),
+    "harvest_cramped_n6_collective_inequity": ("harvest", 6, 54, 24, CRAMPED_HARVEST, 40, 2, 40, 8, None),
+}
+
+# extra MapEnv kwargs of a scenario (cleanup_new.py:60-74)
+SCENARIO_KWARGS = {
+    "cleanup_n4_collective": dict(use_collective_reward=True),
+    "harvest_n5_inequity": dict(inequity_averse_reward=True, alpha=5.0, beta=0.05),
+    "cleanup_cramped_n8_inequity": dict(inequity_averse_reward=True, alpha=0.7, beta=-0.3),
+    "harvest_cramped_n6_collective_inequity": dict(use_collective_reward=True, inequity_averse_reward=True,
+                                                   alpha=1.5, beta=0.25),
 }
 
 
@@ -40,7 +56,8 @@ def run_scenario(name):
     from .ref_harness import RefGridEnv
     kind, n, seed, env_id, amap, horizon, episodes, steps, act_hi, act_p = SCENARIOS[name]
     contract = not name.endswith("nocontract")
-    ref = RefGridEnv(kind, n, seed, env_id, contract=contract, ascii_map=amap, horizon=horizon)
+    kw = SCENARIO_KWARGS.get(name, {})
+    ref = RefGridEnv(kind, n, seed, env_id, contract=contract, ascii_map=amap, horizon=horizon, **kw)
     b = ref.base
     ascii_map = amap if amap is not None else ["".join(ch.decode() for ch in row) for row in b.base_map]
     rng = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
@@ -69,7 +86,9 @@ def run_scenario(name):
         metrics.append(m)
     out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon, "contract": contract,
            "ascii_map": np.array(ascii_map), "metric_keys": np.array(sorted(metrics[0].keys())),
-           "metrics": np.array([[m[k] for k in sorted(m.keys())] for m in metrics], dtype=np.float64)}
+           "metrics": np.array([[m[k] for k in sorted(m.keys())] for m in metrics], dtype=np.float64),
+           "reward_mode": (1 if kw.get("use_collective_reward") else 0) | (2 if kw.get("inequity_averse_reward") else 0),
+           "alpha": np.float64(kw.get("alpha", 0.0)), "beta": np.float64(kw.get("beta", 0.0))}
     for k, v in rec.items():
         out[k] = np.array(v)
     for k, v in rst.items():
@@ -247,7 +266,9 @@ def run_features(name):
         metrics.append(ref.metrics())
     out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon, "contract": contract,
            "metric_keys": np.array(sorted(metrics[0].keys())),
-           "metrics": np.array([[m[k] for k in sorted(m.keys())] for m in metrics], dtype=np.float64)}
+           "metrics": np.array([[m[k] for k in sorted(m.keys())] for m in metrics], dtype=np.float64),
+           "reward_mode": (1 if kw.get("use_collective_reward") else 0) | (2 if kw.get("inequity_averse_reward") else 0),
+           "alpha": np.float64(kw.get("alpha", 0.0)), "beta": np.float64(kw.get("beta", 0.0))}
     out.update({k: np.array(v) for k, v in rec.items()})
     out.update({"reset_" + k: np.array(v) for k, v in rst.items()})
     return out

@@ -50,6 +50,7 @@ def lib():
         L.oracle_get_metrics.argtypes = [vp, vp]
         L.oracle_feature_dim.argtypes = [vp]
         L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
+        L.oracle_set_reward_shaping.argtypes = [vp, i32, f64, f64]
         L.feat_oracle_create.restype = vp
         L.feat_oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
         L.feat_oracle_destroy.argtypes = [vp]
@@ -87,7 +88,8 @@ class GridOracle:
     """E independent cleanup_new / harvest_new envs (+ optional subgame contract wrapper)."""
 
     def __init__(self, kind, num_envs, num_agents, ascii_map, horizon=1000, contract=None,
-                 theta_low=0.0, theta_high=None, null_prob=0.0, seed=73907, first_env_id=0):
+                 theta_low=0.0, theta_high=None, null_prob=0.0, seed=73907, first_env_id=0,
+                 use_collective_reward=False, inequity_averse_reward=False, alpha=0.0, beta=0.0):
         self.kind = kind
         self.E, self.n = int(num_envs), int(num_agents)
         self.H, self.W = len(ascii_map), len(ascii_map[0])
@@ -101,6 +103,9 @@ class GridOracle:
             raise ValueError("oracle_create failed (bad sizes / map)")
         self.F = lib().oracle_feature_dim(self._h)
         self.episode = np.full(self.E, -1, dtype=np.int64)
+        mode = (1 if use_collective_reward else 0) | (2 if inequity_averse_reward else 0)
+        if mode and lib().oracle_set_reward_shaping(self._h, mode, float(alpha), float(beta)) != 0:
+            raise ValueError("inequity_averse_reward needs more than one agent (map_env.py:294)")
 
     def __del__(self):
         if getattr(self, "_h", None):

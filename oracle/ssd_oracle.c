@@ -66,6 +66,8 @@ typedef struct {
     /* config */
     int kind, n, H, W, horizon, contract;
     double theta_low, theta_high, null_prob;
+    int reward_mode;                                /* 1 use_collective_reward | 2 inequity_averse_reward (map_env.py:289-301) */
+    double alpha, beta;
     uint32_t seed, env_id;
     const static_t* s;
     /* dynamic state */
@@ -590,6 +592,33 @@ typedef struct {
     uint8_t* done;       /* [1] */
 } step_out;
 
+/* use_collective_reward / inequity_averse_reward (map_env.py:289-301).  The env rewards are Python ints, so
+ * every difference and both partial sums are exact; alpha * sum, beta * sum, their sum, the division by
+ * (num_agents - 1) and the final subtraction are float64 operations in that order. */
+static void shape_rewards(const env_t* e, double* r)
+{
+    int n = e->n;
+    if (e->reward_mode & 1) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += r[i];
+        for (int i = 0; i < n; i++) r[i] = s;
+    }
+    if (e->reward_mode & 2) {
+        double tmp[MAXN];
+        for (int i = 0; i < n; i++) {
+            double sp = 0, sn = 0;
+            for (int j = 0; j < n; j++) {
+                double d = r[j] - r[i];
+                if (d > 0) sp += d; else if (d < 0) sn += d;
+            }
+            volatile double dis = e->alpha * sp, adv = e->beta * sn;
+            volatile double q = (dis + adv) / (double)(n - 1);
+            tmp[i] = r[i] - q;
+        }
+        for (int i = 0; i < n; i++) r[i] = tmp[i];
+    }
+}
+
 static void env_step(env_t* e, const int32_t* actions, step_out* o, int want_feat)
 {
     int n = e->n;
@@ -618,6 +647,7 @@ static void env_step(env_t* e, const int32_t* actions, step_out* o, int want_fea
         color_view(e, i, o->obs + (size_t)i * OBSW * OBSW * 3);
         base[i] = (double)e->reward_acc[i]; e->reward_acc[i] = 0;       /* compute_reward, Agent.py:87-90 */
     }
+    shape_rewards(e, base);
 
     /* CleanupEnv.step / HarvestEnv.step tails (cleanup_new.py:213-253, harvest_new.py:183-224) */
     int eaten[MAXN], cleaned[MAXN], eaten_close[MAXN], total_close[MAXN];
@@ -770,6 +800,14 @@ void* oracle_create(int kind, int E, int n, int H, int W, const char* ascii, int
         env_init(&b->envs[i], &b->st, kind, n, H, W, horizon, contract, theta_low, theta_high, null_prob,
                  seed, first_env_id + (uint32_t)i);
     return b;
+}
+/* MapEnv kwargs use_collective_reward, inequity_averse_reward, alpha, beta (map_env.py:69-72) */
+int oracle_set_reward_shaping(void* h, int mode, double alpha, double beta)
+{
+    batch_t* b = (batch_t*)h;
+    if (!b || mode < 0 || mode > 3 || ((mode & 2) && b->n < 2)) return -1;     /* assert num_agents > 1, map_env.py:294 */
+    for (int i = 0; i < b->E; i++) { b->envs[i].reward_mode = mode; b->envs[i].alpha = alpha; b->envs[i].beta = beta; }
+    return 0;
 }
 void oracle_destroy(void* h) { batch_t* b = (batch_t*)h; if (b) { free(b->envs); free(b); } }
 

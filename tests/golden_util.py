@@ -31,6 +31,15 @@ def load(name):
     return {k: d[k] for k in d.files}
 
 
+def shaping_kwargs(fx):
+    """use_collective_reward / inequity_averse_reward / alpha / beta of a fixture (absent in older fixtures)."""
+    mode = int(fx["reward_mode"]) if "reward_mode" in fx else 0
+    if not mode:
+        return {}
+    return dict(use_collective_reward=bool(mode & 1), inequity_averse_reward=bool(mode & 2),
+                alpha=float(fx["alpha"]), beta=float(fx["beta"]))
+
+
 def contract_name(fx):
     if not bool(fx["contract"]):
         return None
@@ -49,6 +58,23 @@ def assert_same(name, got, want, ctx):
         ok = np.array_equal(got.astype(np.int64), want.astype(np.int64))
     if not ok:
         raise AssertionError("%s mismatch at %s\n got: %r\nwant: %r" % (name, ctx, got, want))
+
+
+def equality(totals):
+    """compute_equality (cleanup_new.py:422-434) from the per-agent reward sums, same operation order."""
+    eq, total = 0, 0
+    for i in totals:
+        for j in totals:
+            eq += abs(i - j)
+        total += i
+    if total == 0:
+        total = 0.001
+    return 1 - eq / (2 * len(totals) * total)
+
+
+def sustainability(totals, tsums):
+    """compute_sustainability (cleanup_new.py:436-445) from the per-agent sum r and sum t*r."""
+    return np.mean([ts / max(tot, 1) for tot, ts in zip(totals, tsums)])
 
 
 def metrics_from_raw(kind, n, contract, raw):
@@ -102,13 +128,23 @@ def replay(backend, fx, check_features=True):
         want = dict(zip(keys, fx["metrics"][ep]))
         for k, v in got.items():
             assert_same("metric " + k, np.float64(v), np.float64(want[k]), "ep %d" % ep)
+        if "equality" in want:          # episode ended: cleanup_new.py:264-266, two_stage_train.py:97-99
+            totals, tsums = list(raw[24:24 + n]), list(raw[32:32 + n])
+            assert_same("equality", np.float64(equality(totals)), np.float64(want["equality"]), "ep %d" % ep)
+            assert_same("sustainability", np.float64(sustainability(totals, tsums)),
+                        np.float64(want["sustainability"]), "ep %d" % ep)
+            if "transfer_equality" in want:
+                totals, tsums = list(raw[40:40 + n]), list(raw[48:48 + n])
+                assert_same("transfer_equality", np.float64(equality(totals)), np.float64(want["transfer_equality"]), "ep %d" % ep)
+                assert_same("transfer_sustainability", np.float64(sustainability(totals, tsums)),
+                            np.float64(want["transfer_sustainability"]), "ep %d" % ep)
 
 
 class OracleBackend:
     def __init__(self, oracle_mod, fx):
         self.o = oracle_mod.GridOracle(str(fx["kind"]), 1, int(fx["n"]), [str(r) for r in fx["ascii_map"]],
                                        horizon=int(fx["horizon"]), contract=contract_name(fx),
-                                       seed=int(fx["seed"]), first_env_id=int(fx["env_id"]))
+                                       seed=int(fx["seed"]), first_env_id=int(fx["env_id"]), **shaping_kwargs(fx))
 
     def reset(self):
         return self.o.reset()[0]
@@ -134,7 +170,7 @@ class CudaBackend:
         first = (int(fx["env_id"]) - index) & 0xFFFFFFFF
         self.env = BatchedGridEnv(kind, num_envs, int(fx["n"]), [str(r) for r in fx["ascii_map"]],
                                   horizon=int(fx["horizon"]), contract=contract_name(fx), seed=int(fx["seed"]),
-                                  first_env_id=first, padded_obs=padded_obs)
+                                  first_env_id=first, padded_obs=padded_obs, **shaping_kwargs(fx))
         self.n = int(fx["n"])
 
     def reset(self):

@@ -19,19 +19,27 @@ CASES = [
     ("cleanup", 8, CRAMPED_CLEANUP, 128, 300, 1000, 9, 4, 0),
     ("harvest", 8, CRAMPED_HARVEST, 128, 300, 1000, 5, 5, 0),
     ("harvest", 1, None, 8, 60, 1000, 8, 6, 0),
+    # reward shaping (map_env.py:289-301): use_collective_reward / inequity_averse_reward
+    ("cleanup", 8, None, 96, 160, 70, 9, 7, 0, dict(inequity_averse_reward=True, alpha=5.0, beta=0.05)),
+    ("harvest", 4, None, 96, 160, 70, 8, 8, 0, dict(use_collective_reward=True)),
+    ("cleanup", 8, CRAMPED_CLEANUP, 64, 200, 1000, 9, 9, 0, dict(use_collective_reward=True, inequity_averse_reward=True, alpha=0.3, beta=-1.1)),
+    ("harvest", 8, CRAMPED_HARVEST, 64, 200, 90, 8, 10, 0, dict(inequity_averse_reward=True, alpha=-0.7, beta=0.9)),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-n%d-%s-E%d" % (c[0], c[1], "stock" if c[2] is None else "cramped", c[3]))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-n%d-%s-E%d%s" % (c[0], c[1], "stock" if c[2] is None else "cramped", c[3],
+                                                                           "-shaped" if len(c) > 9 else ""))
 def test_rollout_matches_oracle(oracle_lib, case):
     import torch
     from contracts_b200.batched import BatchedGridEnv
     from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
-    kind, n, amap, E, steps, horizon, nact, seed, first = case
+    kind, n, amap, E, steps, horizon, nact, seed, first = case[:9]
+    shaping = case[9] if len(case) > 9 else {}
     amap = amap or (CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP)
     contract = None if n < 2 else ("CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract")
-    orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first)
-    env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first)
+    orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first, **shaping)
+    env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=horizon, contract=contract, seed=seed, first_env_id=first,
+                         **shaping)
     rng = np.random.RandomState(seed)
 
     def check_state(ctx):

@@ -16,7 +16,9 @@ def _make(fx, image_obs=True):
     tag = get_base_env_tag({"environment": kind + "_new"})
     base = env_creator(tag, dict(num_agents=n, env_params={}, image_obs=image_obs, disable_firing=False,
                                  ascii_map=[str(r) for r in fx["ascii_map"]], horizon=int(fx["horizon"]),
-                                 seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+                                 seed=int(fx["seed"]), env_id=int(fx["env_id"]),
+                                 return_agent_actions=bool(gu.shaping_kwargs(fx)),   # no effect, as in the reference
+                                 **gu.shaping_kwargs(fx)))
     if not bool(fx["contract"]):
         return base, base
     cname = gu.contract_name(fx)
