@@ -15,6 +15,7 @@ ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "sel
 CONTRACT_KIND = {None: 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2,
                  "SelfdriveContractDistprop": 3}
 FLAG_COLLECTIVE_REWARD, FLAG_INEQUITY_AVERSE = 1, 2     # SSD_FLAG_* (ssd_config.flags)
+SOLVER_RULE = {"max": 0, "majority": 1}                 # SSD_SOLVER_RULE_* (two_stage_train.py:751,758)
 OBS_BYTES_PER_AGENT = 675
 METRIC_STRIDE = 56
 
@@ -58,6 +59,7 @@ EXPORTS = [
     "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
     "ssd_kernel_launches", "ssd_enable_timing", "ssd_get_step_times", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
     "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
+    "ssd_global_view", "ssd_concat_obs", "ssd_solver_sample", "ssd_solver_choose",
 ]
 
 _LIB = None
@@ -97,6 +99,10 @@ def load():
     L.ssd_feat_step.argtypes = [vp, ctypes.POINTER(ssd_feat_io), vp]
     L.ssd_feat_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ssd_feat_get_metrics.argtypes = [vp, vp, vp]
+    L.ssd_global_view.argtypes = [vp, vp, vp]
+    L.ssd_concat_obs.argtypes = [vp, vp, i64, vp, vp]
+    L.ssd_solver_sample.argtypes = [vp, i32, vp, vp]
+    L.ssd_solver_choose.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.ssd_feature_dim.argtypes = [vp]
     L.ssd_state_bytes_per_env.argtypes = [vp]
     L.ssd_state_bytes_per_env.restype = i64

@@ -25,6 +25,31 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def solver_sample(batch, num_samples):
+    """Candidate contracts of NegotiationSolver.negotiate (two_stage_train.py:705-746) for every env of `batch` (any
+    Batched*Env): float64 [E, 1 + num_samples], column 0 = the null contract, the others float32-valued samples."""
+    params = torch.empty((batch.E, num_samples + 1), dtype=torch.float64, device=batch.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(batch.device).cuda_stream)
+    _lib.check(batch._h, batch.lib.ssd_solver_sample(batch._h, int(num_samples), _ptr(params), stream))
+    return params
+
+
+def solver_choose(batch, params, vals, rule="majority"):
+    """compute_best_param (two_stage_train.py:748-776): vals float64 [E, 1 + S, n] = the caller's value function for
+    every candidate and agent.  Sets each env's contract parameter; returns (theta [E], chosen index [E])."""
+    E, S1 = params.shape
+    vals = torch.as_tensor(vals, dtype=torch.float64, device=batch.device).contiguous()
+    if tuple(vals.shape) != (E, S1, batch.n):
+        raise ValueError("vals must be [E, 1 + S, n] = %r, got %r" % ((E, S1, batch.n), tuple(vals.shape)))
+    params = params.to(device=batch.device, dtype=torch.float64).contiguous()
+    best = torch.empty((E,), dtype=torch.float64, device=batch.device)
+    idx = torch.empty((E,), dtype=torch.int32, device=batch.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(batch.device).cuda_stream)
+    _lib.check(batch._h, batch.lib.ssd_solver_choose(batch._h, S1 - 1, _lib.SOLVER_RULE[rule], _ptr(params), _ptr(vals),
+                                                     _ptr(best), _ptr(idx), stream))
+    return best, idx
+
+
 class BatchedGridEnv:
     """E environments of one kind on one device.
 
@@ -152,6 +177,28 @@ class BatchedGridEnv:
         dec = torch.empty((self.E,), dtype=torch.uint8, device=self.device)
         _lib.check(self._h, self.lib.ssd_negotiate(self._h, _ptr(proposals), _ptr(accept), _ptr(dec), self._stream()))
         return dec
+
+    # ---- JointEnv output layouts (two_stage_train.py:476-617) ---------------------------------------
+    def global_view(self, out=None):
+        """MapEnv.global_view() of every env (map_env.py:394-395): uint8 [E, H, W, 3]; `global_obs` is this / 255."""
+        if out is None:
+            out = torch.empty((self.E, self.H, self.W, 3), dtype=torch.uint8, device=self.device)
+        _lib.check(self._h, self.lib.ssd_global_view(self._h, _ptr(out), self._stream()))
+        return out
+
+    def concatenated_obs(self, out=None):
+        """The agents' windows concatenated along the channel axis (two_stage_train.py:527-533): uint8 [E, 15, 15, 3 n]."""
+        if out is None:
+            out = torch.empty((self.E, 15, 15, 3 * self.n), dtype=torch.uint8, device=self.device)
+        _lib.check(self._h, self.lib.ssd_concat_obs(self._h, _ptr(self._obs_buf), self.obs_stride, _ptr(out), self._stream()))
+        return out
+
+    # ---- NegotiationSolver (two_stage_train.py:619-776) ---------------------------------------------
+    def solver_sample(self, num_samples):
+        return solver_sample(self, num_samples)
+
+    def solver_choose(self, params, vals, rule="majority"):
+        return solver_choose(self, params, vals, rule)
 
     def get_state(self):
         E, n, dev = self.E, self.n, self.device

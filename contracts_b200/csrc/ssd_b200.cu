@@ -18,6 +18,7 @@
 #include "../../include/ssd_b200.h"
 #include "ssd_grid.cuh"
 #include "ssd_grid2.cuh"
+#include "ssd_views.cuh"
 #include "ssd_selfdrive.cuh"
 #include "ssd_features.cuh"
 
@@ -692,6 +693,75 @@ int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* acce
     REQUIRE_GRID(h);
     SMALL_LAUNCH(negotiate_kernel, proposals_dev, accept_dev, decision_dev);
     return check_launch(h, "negotiate");
+}
+
+// ---- JointEnv output layouts (two_stage_train.py:476-617) ----------------------------------------
+int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream)
+{
+    if (!h || !out_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    if (reinterpret_cast<uintptr_t>(out_dev) & 3) return fail(h, SSD_EINVAL, "out_dev must be 4-byte aligned");
+    const GridParams& p = h->gp;
+    global_view_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * p.map_bytes, (cudaStream_t)stream>>>(p, out_dev);
+    return check_launch(h, "global_view");
+}
+
+int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream)
+{
+    if (!h || !obs_dev || !out_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    const GridParams& p = h->gp;
+    const int64_t dense = (int64_t)p.n * SSD_OBS_BYTES;
+    if (obs_env_stride == 0) obs_env_stride = dense;
+    if (obs_env_stride < dense) return fail(h, SSD_EINVAL, "obs_env_stride %lld < %lld", (long long)obs_env_stride, (long long)dense);
+    if ((reinterpret_cast<uintptr_t>(out_dev) | reinterpret_cast<uintptr_t>(obs_dev)) & 3)
+        return fail(h, SSD_EINVAL, "obs_dev and out_dev must be 4-byte aligned");
+    concat_obs_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * (int)dense, (cudaStream_t)stream>>>(p, obs_dev, obs_env_stride, out_dev);
+    return check_launch(h, "concat_obs");
+}
+
+// ---- NegotiationSolver (two_stage_train.py:619-776) ------------------------------------------------
+static SolverParams solver_params(ssd_handle* h)
+{
+    SolverParams s;
+    memset(&s, 0, sizeof(s));
+    s.seed = h->cfg.seed; s.first_env_id = h->cfg.first_env_id;
+    s.low = h->cfg.theta_low; s.high = h->cfg.theta_high;
+    s.E = h->cfg.num_envs; s.n = h->cfg.num_agents;
+    if (h->cfg.env_kind == SSD_ENV_SELFDRIVE) {
+        s.episode = reinterpret_cast<const uint8_t*>(h->cp.episode); s.episode_stride = 4; s.episode_mask = 0xFFFFFFFFu;
+        s.theta = reinterpret_cast<uint8_t*>(h->cp.theta); s.theta_stride = 8;
+    } else if (IS_FEAT(h)) {
+        s.episode = reinterpret_cast<const uint8_t*>(h->fp.counters + (size_t)3 * h->fp.E); s.episode_stride = 4; s.episode_mask = 0x7FFFFFFFu;
+        s.theta = reinterpret_cast<uint8_t*>(h->fp.theta); s.theta_stride = 8;
+    } else {
+        const GridParams& p = h->gp;
+        s.episode = p.state + p.map_bytes + RO_EPISODE; s.episode_stride = p.rec_stride; s.episode_mask = 0xFFFFFFFFu;
+        s.theta = p.state + p.map_bytes + RO_THETA; s.theta_stride = p.rec_stride;
+    }
+    return s;
+}
+
+int ssd_solver_sample(ssd_handle* h, int32_t num_samples, double* params_dev, void* stream)
+{
+    if (!h || !params_dev || num_samples < 0) return SSD_EINVAL;
+    if (h->cfg.contract_kind == SSD_CONTRACT_NONE) return fail(h, SSD_EINVAL, "solver_sample: the handle has no contract");
+    const SolverParams s = solver_params(h);
+    const long long total = (long long)s.E * (num_samples + 1);
+    if (total > 0x7FFFFFFFll) return fail(h, SSD_EINVAL, "solver_sample: E * (1 + num_samples) too large");
+    solver_sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(s, num_samples, params_dev);
+    return check_launch(h, "solver_sample");
+}
+
+int ssd_solver_choose(ssd_handle* h, int32_t num_samples, int32_t rule, const double* params_dev, const double* vals_dev,
+                      double* best_param_dev, int32_t* best_index_dev, void* stream)
+{
+    if (!h || !params_dev || !vals_dev || num_samples < 0) return SSD_EINVAL;
+    if (rule != SOLVER_RULE_MAX && rule != SOLVER_RULE_MAJORITY) return fail(h, SSD_EINVAL, "solver_choose: unknown decision rule %d", rule);
+    if (h->cfg.contract_kind == SSD_CONTRACT_NONE) return fail(h, SSD_EINVAL, "solver_choose: the handle has no contract");
+    const SolverParams s = solver_params(h);
+    solver_choose_kernel<<<(s.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(s, num_samples, rule, params_dev, vals_dev, best_param_dev, best_index_dev);
+    return check_launch(h, "solver_choose");
 }
 
 int ssd_get_state(ssd_handle* h, uint8_t* map_dev, int32_t* pos_dev, int32_t* ori_dev, int32_t* t_dev, double* theta_dev, void* stream)

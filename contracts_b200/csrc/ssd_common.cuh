@@ -32,7 +32,7 @@ enum { C_EMPTY = 0 << 2, C_WALL = 1 << 2, C_APPLE = 2 << 2, C_WASTE = 3 << 2, C_
 
 enum { SITE_MOVE_ORDER = 1, SITE_BEAM_ORDER = 2, SITE_SPAWN_DRAWS = 3, SITE_WASTE_ORDER = 4, SITE_SPAWN_ROT = 5,
        SITE_SPAWN_POINT = 6, SITE_CONTRACT = 7, SITE_NEGOTIATE = 8, SITE_SELFDRIVE_RESET = 9,
-       SITE_FEAT_ORDER = 10, SITE_FEAT_ROT = 11, SITE_FEAT_SPAWN = 12, SITE_ACTIONS = 13 };
+       SITE_FEAT_ORDER = 10, SITE_FEAT_ROT = 11, SITE_FEAT_SPAWN = 12, SITE_ACTIONS = 13, SITE_SOLVER = 14 };
 
 // record flags
 #define RF_STALE_EMPTY 1u     // cleanup: current_apple_points is [] until the first step (cleanup_new.py:181 runs before the reset-time spawn)

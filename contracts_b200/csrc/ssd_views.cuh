@@ -1,0 +1,173 @@
+// ssd_views.cuh — the JointEnv output layouts (environments/two_stage_train.py:476-617), written from device state:
+//
+//   global_view_kernel   `global_obs`: MapEnv.global_view() (map_env.py:394-395) = the whole world_map_color with the
+//                        agents painted (map_env.py:257-261), uint8 [E][H][W][3]; JointEnv.reset / global_step return
+//                        it / 255 (cleanup_new.py:299-300, harvest_new.py:178-179)
+//   concat_obs_kernel    `concatenated_obs`: np.concatenate of the agents' windows along the channel axis
+//                        (two_stage_train.py:527-533,604-609): uint8 [E][n][15][15][3] -> [E][15][15][3 n]
+//
+// Both are pure byte streams bound by HBM (global view: map_bytes read + 3 H W written per env; concat: 675 n
+// read + written per env).  A CTA owns VIEW_GROUP = 4 consecutive envs, so its output range is a whole number of
+// 32-bit words whatever the per-env byte count is, stages the inputs in shared memory with 16-byte loads and
+// writes aligned words.
+#pragma once
+#include "ssd_grid.cuh"
+
+#define VIEW_THREADS 128
+#define VIEW_GROUP 4
+
+__global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridParams p, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t vsm[];            // VIEW_GROUP compact maps
+    __shared__ uint32_t s_pal[16];
+    const int env0 = blockIdx.x * VIEW_GROUP;
+    const int G = min(VIEW_GROUP, p.E - env0);
+    const int nvec = p.map_bytes >> 4;
+    if (threadIdx.x < 16) s_pal[threadIdx.x] = p.pal[threadIdx.x];
+    for (int i = threadIdx.x; i < G * nvec; i += VIEW_THREADS) {
+        const int g = i / nvec, v = i - g * nvec;
+        reinterpret_cast<uint4*>(vsm)[i] = reinterpret_cast<const uint4*>(p.state + (size_t)(env0 + g) * p.rec_stride)[v];
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {                                    // paint in agent order: the highest index wins a shared cell
+        const uint8_t* hdr = p.state + (size_t)(env0 + threadIdx.x) * p.rec_stride + p.map_bytes;
+        const uint32_t* ag = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS);
+        // MapEnv.reset (map_env.py:306-342) never paints the agents into world_map_color: they appear from the first step on
+        const int na = *reinterpret_cast<const int*>(hdr + RO_T) > 0 ? p.n : 0;
+        for (int a = 0; a < na; a++) {
+            const uint32_t v = ag[a];
+            vsm[threadIdx.x * p.map_bytes + (int)(v & 255u) * p.Wp + (int)((v >> 8) & 255u)] = (uint8_t)PAINT_CODE(a);
+        }
+    }
+    __syncthreads();
+    const int per_env = p.H * p.W * 3, total = G * per_env;
+    uint8_t* dst = out + (size_t)env0 * per_env;              // env0 % 4 == 0: word aligned
+    for (int w = threadIdx.x; 4 * w < total; w += VIEW_THREADS) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gb = 4 * w + k;
+            if (gb < total) {
+                const int g = gb / per_env, b = gb - g * per_env;
+                const int cell = b / 3, ch = b - 3 * cell;
+                const int r = cell / p.W, c = cell - r * p.W;
+                const uint32_t code = vsm[g * p.map_bytes + r * p.Wp + c] & CODE_MASK;
+                word |= ((s_pal[code >> 2] >> (8 * ch)) & 255u) << (8 * k);
+            }
+        }
+        if (4 * w + 3 < total) reinterpret_cast<uint32_t*>(dst)[w] = word;
+        else for (int k = 0; 4 * w + k < total; k++) dst[4 * w + k] = (uint8_t)(word >> (8 * k));
+    }
+}
+
+__global__ void __launch_bounds__(VIEW_THREADS) concat_obs_kernel(const GridParams p, const uint8_t* __restrict__ obs,
+                                                                  long long obs_stride, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t vsm[];            // VIEW_GROUP x n windows
+    const int n = p.n, per_env = n * SSD_OBS_BYTES;
+    const int env0 = blockIdx.x * VIEW_GROUP;
+    const int G = min(VIEW_GROUP, p.E - env0);
+    const int total = G * per_env;
+    if (obs_stride == per_env) {                              // dense batch tensor: the group is one aligned word run
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(obs + (size_t)env0 * per_env);
+        for (int w = threadIdx.x; 4 * w + 3 < total; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(vsm)[w] = src[w];
+        for (int b = (total & ~3) + threadIdx.x; b < total; b += VIEW_THREADS) vsm[b] = obs[(size_t)env0 * per_env + b];
+    } else {
+        for (int b = threadIdx.x; b < total; b += VIEW_THREADS) {
+            const int g = b / per_env;
+            vsm[b] = obs[(size_t)(env0 + g) * obs_stride + (b - g * per_env)];
+        }
+    }
+    __syncthreads();
+    uint8_t* dst = out + (size_t)env0 * per_env;
+    const int n3 = 3 * n;
+    for (int w = threadIdx.x; 4 * w < total; w += VIEW_THREADS) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gb = 4 * w + k;
+            if (gb < total) {
+                const int g = gb / per_env, q = gb - g * per_env;         // q = pixel * 3 n + 3 a + ch
+                const int pix = q / n3, ach = q - pix * n3;
+                const int a = ach / 3, ch = ach - 3 * a;
+                word |= (uint32_t)vsm[g * per_env + a * SSD_OBS_BYTES + pix * 3 + ch] << (8 * k);
+            }
+        }
+        if (4 * w + 3 < total) reinterpret_cast<uint32_t*>(dst)[w] = word;
+        else for (int k = 0; 4 * w + k < total; k++) dst[4 * w + k] = (uint8_t)(word >> (8 * k));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NegotiationSolver (environments/two_stage_train.py:619-776), batched over envs.  The value-function
+// queries (compute_vals :693-703, an RLlib policy forward) stay with the caller; the device side is
+//   solver_sample_kernel   negotiate :705-746: candidate 0 is the null contract `contract_space.low`, candidates
+//                          1..S are `contract_param_space.sample()` — gym 0.21 Box.sample: float32(uniform(low, high))
+//                          evaluated in float64 — drawn from the env's Philox stream (site SOLVER, one draw each);
+//   solver_choose_kernel   compute_best_param :748-776 on the caller's values [E][1 + S][n]: rule `max` = first
+//                          argmax of the per-candidate welfare sum(vals) (agent order, left to right); rule
+//                          `majority` = the same over {null} + candidates that at least half of the agents strictly
+//                          prefer to the null contract, a candidate's parameter being looked up through
+//                          `all_vals.index(k1)` (the FIRST candidate with identical values).  The winner becomes the
+//                          env's contract parameter (reset :675-676).
+// Works for every env kind: episode / theta are addressed through (pointer, byte stride, mask).
+struct SolverParams {
+    int E, n;
+    uint32_t seed, first_env_id;
+    double low, high;
+    const uint8_t* episode; long long episode_stride; uint32_t episode_mask;
+    uint8_t* theta; long long theta_stride;
+};
+#define SOLVER_RULE_MAX 0
+#define SOLVER_RULE_MAJORITY 1
+
+__global__ void solver_sample_kernel(const SolverParams p, int S, double* __restrict__ params)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (env, candidate)
+    if (idx >= p.E * (S + 1)) return;
+    const int env = idx / (S + 1), k = idx - env * (S + 1);
+    double v = p.low;
+    if (k > 0) {
+        const uint32_t episode = *reinterpret_cast<const uint32_t*>(p.episode + (size_t)env * p.episode_stride) & p.episode_mask;
+        const uint32_t u = draw_u32(p.seed, p.first_env_id + (uint32_t)env, episode, 0u, SITE_SOLVER, 0u, (uint32_t)(k - 1));
+        const double x = __dadd_rn(p.low, __dmul_rn(__dsub_rn(p.high, p.low), (double)u * 2.3283064365386963e-10));
+        v = (double)(float)x;                                       // .astype(np.float32)
+    }
+    params[idx] = v;
+}
+
+__global__ void solver_choose_kernel(const SolverParams p, int S, int rule, const double* __restrict__ params,
+                                     const double* __restrict__ vals, double* __restrict__ best_param, int* __restrict__ best_idx)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    const int n = p.n;
+    const double* V = vals + (size_t)env * (S + 1) * n;
+    const double* P = params + (size_t)env * (S + 1);
+    int best = 0;                       // the null contract is always a candidate
+    double best_w = 0.0;
+    for (int a = 0; a < n; a++) best_w = __dadd_rn(best_w, V[a]);
+    for (int k = 1; k <= S; k++) {
+        const double* vk = V + (size_t)k * n;
+        if (rule == SOLVER_RULE_MAJORITY) {
+            int accepted = 0;
+            for (int a = 0; a < n; a++) accepted += vk[a] > V[a];
+            if (accepted < n - accepted) continue;
+        }
+        double w = 0.0;
+        for (int a = 0; a < n; a++) w = __dadd_rn(w, vk[a]);
+        if (w > best_w) { best_w = w; best = k; }     // np.argmax: the first maximum
+    }
+    int src = best;
+    if (rule == SOLVER_RULE_MAJORITY && best > 0) {   // all_params[all_vals.index(k1)]
+        for (int j = 0; j < best; j++) {
+            bool same = true;
+            for (int a = 0; a < n; a++) same = same && (V[(size_t)j * n + a] == V[(size_t)best * n + a]);
+            if (same) { src = j; break; }
+        }
+    }
+    const double theta = P[src];
+    if (best_param) best_param[env] = theta;
+    if (best_idx) best_idx[env] = src;
+    *reinterpret_cast<double*>(p.theta + (size_t)env * p.theta_stride) = theta;
+}

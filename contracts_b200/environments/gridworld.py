@@ -194,7 +194,9 @@ class _GridWorldEnv:
         return rgb
 
     def global_view(self):
-        return self.full_map_to_colors().astype(np.uint8)
+        """world_map_color without its padding (map_env.py:394-395), written by the device (`ssd_global_view`).  Unlike
+        `full_map_to_colors` it shows the agents only from the first step on (MapEnv.reset does not paint them)."""
+        return self.batch.global_view()[0].cpu().numpy()
 
     def get_global_obs(self):
         return {"image": self.global_view() / 255}

@@ -205,3 +205,163 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
         for k in self.agent_ids:
             infos[k]["contract_param"] = self.params[k]
         return rews, infos
+
+
+class JointEnv:
+    """two_stage_train.py:476-617: one centralised controller 'a0' acts for every agent.
+
+    `global_obs`: the observation is the whole colour map (`base_env.get_global_obs()`); `concatenated_obs`: the
+    agents' windows concatenated along the channel axis; otherwise (`duplicate_obs` or not) the flat-observation
+    variant for Box action spaces (selfdrive).  The image layouts are written on the device
+    (`ssd_global_view` / `ssd_concat_obs`); rewards are summed, infos summed key by key, as in the reference.
+    """
+
+    def __init__(self, base_env, num_agents=2, duplicate_obs=False, concatenated_obs=False, global_obs=False, **kwargs):
+        self.base_env = base_env
+        self.num_agents = num_agents
+        self.duplicate_obs = duplicate_obs
+        self.global_obs = global_obs
+        self.concatenated_obs = concatenated_obs
+        if global_obs:
+            self.observation_space = self.base_env.global_observation_space
+            self.action_space = self.base_env.global_action_space
+        elif concatenated_obs:
+            self.observation_space = self.base_env.concatenated_observation_space
+            self.action_space = self.base_env.global_action_space
+        else:
+            if self.duplicate_obs:
+                self.observation_space = spaces.Box(
+                    low=np.concatenate([self.base_env.observation_space.low] * self.num_agents),
+                    high=np.concatenate([self.base_env.observation_space.high] * self.num_agents))
+            else:
+                self.observation_space = self.base_env.observation_space
+            self.action_space = spaces.Box(low=np.concatenate([self.base_env.action_space.low] * self.num_agents),
+                                           high=np.concatenate([self.base_env.action_space.high] * self.num_agents))
+            self.curr_agent_lst = ["a" + str(i) for i in range(self.num_agents)]
+
+    @property
+    def metrics(self):
+        return self.base_env.metrics
+
+    def _concatenated(self):
+        img = self.base_env.batch.concatenated_obs()[0].cpu().numpy()
+        return {"a0": {"image": img.astype(np.float64) / 255}}
+
+    def reset(self):
+        base_obs = self.base_env.reset()
+        if self.global_obs:
+            return {"a0": self.base_env.get_global_obs()}
+        elif self.concatenated_obs:
+            return self._concatenated()
+        else:
+            self.agent_obs = base_obs.copy()
+            self.curr_agent_lst = ["a" + str(i) for i in range(self.num_agents)]
+            return {"a0": np.concatenate([base_obs["a" + str(i)] for i in range(self.num_agents)])}
+
+    def step(self, acts):
+        if self.global_obs or self.concatenated_obs:
+            agent_list = ["a" + str(i) for i in range(self.num_agents)]
+            action_dict = {"a" + str(i): acts["a0"][i] for i in range(self.num_agents)}
+            _, env_rews, env_dones, env_infos = self.base_env.step(action_dict)
+            obs = {"a0": self.base_env.get_global_obs()} if self.global_obs else self._concatenated()
+            rews = {"a0": sum([rew for rew in env_rews.values()])}        # straightforward sum, not average (:592)
+            dones = {"a0": env_dones["__all__"], "__all__": env_dones["__all__"]}
+            infos = {"a0": {key: sum([env_infos[agent][key] for agent in agent_list])
+                            for key in env_infos[agent_list[0]].keys()}}
+            return obs, rews, dones, infos
+        k = self.base_env.action_space.shape[0]
+        action_dict = {}
+        for i in range(self.num_agents):
+            if "a" + str(i) in self.curr_agent_lst:
+                action_dict["a" + str(i)] = np.array(acts["a0"][i * k:(i + 1) * k])
+        base_obs, env_rews, env_dones, env_infos = self.base_env.step(action_dict)
+        for agent in self.curr_agent_lst:
+            self.agent_obs[agent] = base_obs[agent]
+        if self.duplicate_obs:
+            obs = {"a0": np.concatenate([self.agent_obs["a" + str(i)] for i in range(self.num_agents)])}
+        else:
+            obs = {"a0": self.agent_obs[self.curr_agent_lst[0]]}
+        rews = {"a0": sum([rew for rew in env_rews.values()])}
+        dones = {"a0": env_dones["__all__"], "__all__": env_dones["__all__"]}
+        infos = {"a0": {key: sum([env_infos[agent][key] for agent in self.curr_agent_lst])
+                        for key in env_infos[self.curr_agent_lst[0]].keys()}}
+        for i in range(self.num_agents):
+            if "a" + str(i) in self.curr_agent_lst and env_dones.get("a" + str(i), False):
+                self.curr_agent_lst.remove("a" + str(i))
+        return obs, rews, dones, infos
+
+    def render(self, mode="rgb"):
+        return self.base_env.render()
+
+
+class NegotiationSolver(SeparateContractEnv):
+    """two_stage_train.py:619-776: at every reset, sample `contract_samples` contracts, query the agents' frozen value
+    functions for each (plus the null contract) and keep the best one under `decision_rule` ('max' | 'majority').
+
+    The reference loads a frozen RLlib PPO policy (`trainer_config`, `trainer_env`, `trainer_path`) and reads
+    `model.value_function()` after `compute_single_action` (:693-703); that forward pass is outside the accelerated
+    path.  Here `value_fn(obs, agent_id) -> float` plays that role (obs = the agent's observation with the candidate
+    contract appended, exactly what the reference feeds its policy).  Candidate sampling and the decision rule run on
+    the device (`ssd_solver_sample` / `ssd_solver_choose`).  The chosen parameter is float32-valued like gym's
+    `Box.sample()`; the transfers are float64 arithmetic on it, as under the NumPy the reference pins.
+    """
+
+    def __init__(self, base_env, contract, num_agents, horizon=1000, trainer_config=None, trainer_env=None, trainer_path=None,
+                 convolutional=True, shared=True, env_params=None, contract_samples=50, decision_rule="majority",
+                 value_fn=None, **kwargs):
+        super().__init__(base_env, contract, num_agents, convolutional)
+        if value_fn is None:
+            raise ValueError("NegotiationSolver needs value_fn(obs, agent_id) -> float (the frozen policy's value function)")
+        if decision_rule not in ("max", "majority"):
+            raise ValueError("decision_rule must be 'max' or 'majority'")
+        self.horizon = horizon
+        self.shared = shared
+        self.value_fn = value_fn
+        self.contract_param_space = spaces.Box(low=contract.contract_space.low, high=contract.contract_space.high)
+        self.num_samples = contract_samples
+        self.decision_rule = decision_rule
+        self.config = trainer_config
+        self.action_space = self.base_env.action_space
+        self._metrics = {"contract": -1, "accepted": 0}
+
+    @property
+    def metrics(self):
+        return self._metrics
+
+    def _obs_with(self, param):
+        out = {}
+        for k in self.agent_ids:
+            if self.convolutional:
+                o = dict(self.obs[k])
+                o["contract"] = np.concatenate((param, np.array([0])))
+            else:
+                o = np.concatenate((self.obs[k], param, np.array([0])))
+            out[k] = o
+        return out
+
+    def compute_vals(self, obs):
+        return {k: self.value_fn(obs[k], k) for k in obs}
+
+    def negotiate(self):
+        b = self.base_env.batch
+        params = b.solver_sample(self.num_samples)                       # [E, 1 + S] on the device
+        cand = params[0].cpu().numpy()
+        vals = np.zeros((1, self.num_samples + 1, self.num_agents))
+        for c, theta in enumerate(cand):                                  # null contract first (:709-724)
+            v = self.compute_vals(self._obs_with(np.array([theta])))
+            vals[0, c] = [v[k] for k in self.agent_ids]
+        full = torch.zeros((b.E, self.num_samples + 1, self.num_agents), dtype=torch.float64, device=b.device)
+        full[0] = torch.as_tensor(vals[0])
+        best, _ = b.solver_choose(params, full, self.decision_rule)
+        return np.array([best[0].item()], dtype=np.float32)
+
+    def reset(self):
+        self._metrics = {"contract": -1, "accepted": 0}
+        base_obs = self.base_env.reset()
+        self.obs = copy.deepcopy(base_obs)
+        self.last_seen_obs = copy.deepcopy(base_obs)
+        self.params = None
+        self.contract_state = {k: 0 for k in self.agent_ids}
+        self.contract_param = self.negotiate()
+        self.params = {k: self.contract_param for k in self.agent_ids}
+        return self._with_contract(self.obs, lambda k: 0)

@@ -2,12 +2,11 @@
 `get_base_env_tag`, and (when ray is installed) the same `register_env` calls (:12-60)."""
 from ..contract import contract_list  # noqa: F401  (the reference module imports it for its side effect)
 from ..environments.gridworld import CleanupEnv, HarvestEnv
-from ..environments.two_stage_train import SeparateContractNegotiateStage, SeparateContractSubgameStage
+from ..environments.two_stage_train import (JointEnv, NegotiationSolver, SeparateContractNegotiateStage,
+                                            SeparateContractSubgameStage)
 
 _OUT_OF_SCOPE = {
     "ContractWrapperCombined": "SeparateContractCombinedStage is unused by every shipped config",
-    "NegotiationSolver": "value-function contract solver (needs the RLlib policy); see DESIGN.md 'next'",
-    "JointEnv": "single-controller baseline; see DESIGN.md 'next'",
 }
 
 
@@ -31,6 +30,8 @@ _CREATORS = {
     "CleanupNew": CleanupEnv,
     "ContractWrapperNegotiate": SeparateContractNegotiateStage,
     "ContractWrapperSubgame": SeparateContractSubgameStage,
+    "NegotiationSolver": NegotiationSolver,
+    "JointEnv": JointEnv,
 }
 TAGS = list(_CREATORS) + list(_OUT_OF_SCOPE)
 

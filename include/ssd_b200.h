@@ -131,6 +131,28 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
 int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev,
                   void* stream);
 
+/* --- JointEnv output layouts (environments/two_stage_train.py:476-617) ----------------------------- */
+/* `global_obs`: MapEnv.global_view() (map_env.py:394-395; base_env.get_global_obs(), cleanup_new.py:299-300,
+ * harvest_new.py:178-179, before the / 255): the whole colour map with agents, uint8 [E][H][W][3]. */
+int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream);
+/* `concatenated_obs`: np.concatenate of the agents' windows along the channel axis (two_stage_train.py:527-533,
+ * 604-609): obs_dev uint8 [E][n][15][15][3] (env stride obs_env_stride, 0 = dense) -> out_dev uint8 [E][15][15][3n]. */
+int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream);
+
+/* --- NegotiationSolver (environments/two_stage_train.py:619-776); every env kind ------------------- */
+#define SSD_SOLVER_RULE_MAX 0        /* decision_rule 'max'      (:751-757) */
+#define SSD_SOLVER_RULE_MAJORITY 1   /* decision_rule 'majority' (:758-773) */
+/* negotiate() :705-746, the candidate contracts: params_dev double [E][1 + num_samples]; [e][0] = contract_space.low
+ * (the null contract), [e][1 + i] = contract_param_space.sample() = float32(uniform(low, high)) from the env's
+ * Philox stream.  The caller evaluates its value function V(s, c) per agent for every candidate (compute_vals
+ * :693-703 — an RLlib policy forward in the reference). */
+int ssd_solver_sample(ssd_handle* h, int32_t num_samples, double* params_dev, void* stream);
+/* compute_best_param() :748-776 on vals_dev double [E][1 + num_samples][n]; the chosen parameter becomes the env's
+ * contract parameter (reset :675-676) and is also written to best_param_dev double [E] / best_index_dev int32 [E]
+ * (either may be NULL). */
+int ssd_solver_choose(ssd_handle* h, int32_t num_samples, int32_t rule, const double* params_dev, const double* vals_dev,
+                      double* best_param_dev, int32_t* best_index_dev, void* stream);
+
 /* --- state access (parity tests, checkpointing) ---------------------------------------------------- */
 /* map: uint8 chars [E][H][W] (MapEnv.world_map); pos: int32 [E][n][2] (row, col); ori: int32 [E][n]
  * (Agent.int_orientation); t: int32 [E] (MapEnv.timesteps); theta: double [E].  NULL pointers are skipped. */

@@ -274,10 +274,82 @@ def run_features(name):
     return out
 
 
+# NegotiationSolver (two_stage_train.py:619-776) with the scripted value function of oracle/scripted.py.
+# name -> (kind, n, seed, env_id, contract_samples, decision_rule, episodes, steps per episode, action ids)
+SOLVER_SCENARIOS = {
+    "solver_cleanup_n4_majority": ("cleanup", 4, 61, 31, 12, "majority", 4, 12, 9),
+    "solver_harvest_n3_max": ("harvest", 3, 62, 32, 9, "max", 3, 12, 8),
+    "solver_cleanup_n2_majority": ("cleanup", 2, 63, 33, 20, "majority", 4, 6, 9),
+    "solver_harvest_n8_majority": ("harvest", 8, 64, 34, 50, "majority", 3, 6, 8),
+}
+
+
+def run_solver(name):
+    from .ref_harness import RefSolverEnv
+    kind, n, seed, env_id, S, rule, episodes, steps, act_hi = SOLVER_SCENARIOS[name]
+    ref = RefSolverEnv(kind, n, seed, env_id, S, rule)
+    rng = np.random.RandomState(sum(map(ord, name)))
+    rec = {k: [] for k in ("reset_obs", "reset_contract_obs", "params", "vals", "theta", "actions", "obs", "contract_obs", "rew")}
+    for ep in range(episodes):
+        r = ref.reset()
+        for k, v in (("reset_obs", r["obs"]), ("reset_contract_obs", r["contract_obs"]), ("params", r["params"]),
+                     ("vals", r["vals"]), ("theta", r["theta"])):
+            rec[k].append(v)
+        for k in ("actions", "obs", "contract_obs", "rew"):
+            rec[k].append([])
+        for t in range(steps):
+            a = rng.randint(0, act_hi, size=n)
+            o = ref.step(a)
+            rec["actions"][-1].append(a)
+            for k in ("obs", "contract_obs", "rew"):
+                rec[k][-1].append(o[k])
+    out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "num_samples": S, "rule": rule}
+    out.update({k: np.array(v) for k, v in rec.items()})
+    return out
+
+
+# JointEnv (two_stage_train.py:476-617).  name -> (kind, n, seed, env_id, mode, horizon, episodes, steps, action ids)
+JOINT_SCENARIOS = {
+    "joint_cleanup_n2_concatenated": ("cleanup", 2, 71, 41, "concatenated", 40, 2, 40, 9),   # cleanup-joint-2agents.json
+    "joint_cleanup_n3_global": ("cleanup", 3, 72, 42, "global", 30, 2, 30, 9),
+    "joint_harvest_n4_global": ("harvest", 4, 73, 43, "global", 30, 2, 30, 8),
+    "joint_harvest_n5_concatenated": ("harvest", 5, 74, 44, "concatenated", 25, 2, 25, 8),
+}
+
+
+def run_joint(name):
+    from .ref_harness import RefJointEnv
+    kind, n, seed, env_id, mode, horizon, episodes, steps, act_hi = JOINT_SCENARIOS[name]
+    ref = RefJointEnv(kind, n, seed, env_id, mode, horizon=horizon)
+    rng = np.random.RandomState(sum(map(ord, name)))
+    keys = ("obs", "rew", "done", "eaten_apples", "info1", "feature_obs")
+    rec = {k: [] for k in keys + ("actions", "reset_obs")}
+    for ep in range(episodes):
+        rec["reset_obs"].append(ref.reset())
+        for k in keys + ("actions",):
+            rec[k].append([])
+        for t in range(steps):
+            a = rng.randint(0, act_hi, size=n)
+            o = ref.step(a)
+            rec["actions"][-1].append(a)
+            for k in keys:
+                rec[k][-1].append(o[k])
+    out = {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "mode": mode, "horizon": horizon}
+    out.update({k: np.array(v) for k, v in rec.items()})
+    return out
+
+
 def main(names=None):
     os.makedirs(OUT, exist_ok=True)
     for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS) + list(SELFDRIVE_SCENARIOS)
-                 + list(FEATURES_SCENARIOS)):
+                 + list(FEATURES_SCENARIOS) + list(SOLVER_SCENARIOS) + list(JOINT_SCENARIOS)):
+        if name in SOLVER_SCENARIOS or name in JOINT_SCENARIOS:
+            data = run_solver(name) if name in SOLVER_SCENARIOS else run_joint(name)
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **data)
+            print("%-32s %7.1f KiB  obs=%s %s" % (name, os.path.getsize(path) / 1024, data["obs"].shape,
+                                                  ("theta=%s" % data["theta"]) if "theta" in data else ""))
+            continue
         if name in FEATURES_SCENARIOS:
             data = run_features(name)
             path = os.path.join(OUT, name + ".npz")

@@ -51,6 +51,7 @@ def lib():
         L.oracle_feature_dim.argtypes = [vp]
         L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
         L.oracle_set_reward_shaping.argtypes = [vp, i32, f64, f64]
+        L.oracle_global_view.argtypes = [vp, vp]
         L.feat_oracle_create.restype = vp
         L.feat_oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
         L.feat_oracle_destroy.argtypes = [vp]
@@ -161,6 +162,66 @@ class GridOracle:
         out = np.zeros((self.E, METRIC_STRIDE))
         lib().oracle_get_metrics(self._h, _p(out))
         return out
+
+    def global_view(self):
+        """MapEnv.global_view() (map_env.py:394-395) of every env: uint8 [E, H, W, 3]."""
+        out = np.zeros((self.E, self.H, self.W, 3), np.uint8)
+        lib().oracle_global_view(self._h, _p(out))
+        return out
+
+    def set_theta(self, theta):
+        self.set_state(theta=theta)
+
+
+def concatenated_obs(obs):
+    """JointEnv `concatenated_obs` (two_stage_train.py:527-533,604-609): np.concatenate of the agents' windows
+    along the channel axis.  obs [E, n, 15, 15, 3] -> [E, 15, 15, 3 n]."""
+    return np.concatenate([obs[:, a] for a in range(obs.shape[1])], axis=-1)
+
+
+def solver_candidates(seed, env_id, episode, low, high, num_samples):
+    """NegotiationSolver.negotiate (two_stage_train.py:705-746), the candidate contracts of one env: the null contract
+    `contract_space.low` followed by `contract_param_space.sample()` x num_samples.  gym (pinned 0.21.0, not vendored by
+    the reference) implements Box.sample for a bounded box as `np_random.uniform(low, high).astype(float32)`, the uniform
+    evaluated in float64 as low + (high - low) * u; u is the env's Philox draw (site SOLVER, index i) at t = 0."""
+    from . import philox as px
+    out = [np.float64(low)]
+    for i in range(num_samples):
+        u = px.draws_f64(seed, env_id, episode, 0, px.SITE_SOLVER, 0, i)[0]
+        out.append(np.float64(np.float32(np.float64(low) + (np.float64(high) - np.float64(low)) * u)))
+    return np.array(out)
+
+
+def solver_choose(params, vals, rule):
+    """NegotiationSolver.compute_best_param (two_stage_train.py:748-776) for one env, restated with the reference's own
+    list operations.  params [1 + S], vals [1 + S, n] (row 0 = the null contract).  Returns (parameter, index)."""
+    all_vals = [tuple(np.float64(x) for x in row) for row in vals]
+    all_params = list(range(len(params)))
+
+    def best_max(vs, ps):
+        welfares = []
+        for k in vs:
+            w = 0
+            for x in k:                    # sum(k.values()): left to right from 0
+                w = w + x
+            welfares.append(w)
+        return ps[int(np.argmax(welfares))]
+
+    if rule == "max":
+        idx = best_max(all_vals, all_params)
+    elif rule == "majority":
+        default = all_vals[0]
+        acc_vals, acc_params = [default], [all_params[0]]
+        for k1 in all_vals[1:]:
+            accepted = sum(1 for a in range(len(k1)) if k1[a] > default[a])
+            rejected = len(k1) - accepted
+            if accepted >= rejected:
+                acc_vals.append(k1)
+                acc_params.append(all_params[all_vals.index(k1)])
+        idx = best_max(acc_vals, acc_params)
+    else:
+        raise ValueError(rule)
+    return np.float64(params[idx]), idx
 
 
 class CarOracle:

@@ -43,6 +43,7 @@ SITE_FEAT_ORDER = 10     # R11 cleanup_features.py:107 / harvest_features.py:118
 SITE_FEAT_ROT = 11       # R11 cleanup_features.py:109 / harvest_features.py:122 np.random.randint(0,4)
 SITE_FEAT_SPAWN = 12     # R11 cleanup_features.py:115,122 / harvest_features.py:148 random.random()
 SITE_ACTIONS = 13        # synthetic random actions for benchmarks (not a reference site)
+SITE_SOLVER = 14         # two_stage_train.py:725  contract_param_space.sample() (gym Box.sample -> uniform)
 
 EPISODE_CONSTRUCT = 0xFFFFFFFF  # draws consumed by MapEnv.__init__ -> setup_agents (map_env.py:131)
 

@@ -127,7 +127,10 @@ def _np_rand(*shape):
 def _np_uniform(low=0.0, high=1.0, size=None):
     if _CTX is None:
         return _ORIG["np.uniform"](low, high, size)
-    u = _CTX.f64(px.SITE_CONTRACT, 0, 1)[0]                   # two_stage_train.py:164
+    if _caller_name() == "sample":                            # gym Box.sample <- negotiate (two_stage_train.py:725)
+        u = _CTX.f64(px.SITE_SOLVER, 0, _CTX.next_call(px.SITE_SOLVER))[0]
+    else:
+        u = _CTX.f64(px.SITE_CONTRACT, 0, 1)[0]               # two_stage_train.py:164
     low64 = np.asarray(low, dtype=np.float64)
     high64 = np.asarray(high, dtype=np.float64)
     return low64 + (high64 - low64) * u
@@ -397,6 +400,146 @@ class RefNegotiateEnv:
 
     def base_metrics(self):
         return {k: float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v) for k, v in self.base.metrics.items()}
+
+
+class ScriptedValueTrainer:
+    """Stands in for the frozen PPOTrainer of NegotiationSolver.compute_vals (two_stage_train.py:693-703):
+    `compute_single_action(obs)` then `get_policy(id).model.value_function().item()` once per agent, in agent
+    order.  The value is oracle/scripted.py:scripted_value of the observation just passed in."""
+
+    class _Val:
+        def __init__(self, v):
+            self.v = v
+
+        def item(self):
+            return self.v
+
+    def __init__(self, num_agents, scale):
+        self.n, self.scale, self.calls, self._obs = num_agents, scale, 0, None
+
+    def compute_single_action(self, obs, policy_id=None):
+        self._obs, self._agent = obs, self.calls % self.n
+        self.calls += 1
+        return 4
+
+    def get_policy(self, policy_id):
+        return self
+
+    @property
+    def model(self):
+        return self
+
+    def value_function(self):
+        from .scripted import scripted_value
+        return self._Val(scripted_value(self._obs, self._agent, self.n, self.scale))
+
+
+class RefSolverEnv:
+    """The reference's NegotiationSolver (two_stage_train.py:619-776) under RNG injection; the PPOTrainer
+    construction (:652-653) is bypassed like in RefNegotiateEnv (no reference source is edited).
+
+    NumPy drift: `contract_param_space.sample()` is a float32 array.  Under the NumPy the reference pins (< 1.24 via
+    ray 2.2 / tf 2.11, requirements.yml) a float32 SCALAR combined with a Python int promotes to float64
+    (`-params[k][0] * cleaned_squares`, contract_list.py:26; `rews[i] -= transfers[i]`, two_stage_train.py:85), so the
+    transfers are float64 arithmetic on a float32-valued theta.  NumPy >= 2 (NEP 50, this container) would keep
+    float32.  The harness restores the pinned behaviour by widening the stored parameter arrays to float64 after
+    reset() — the values are unchanged."""
+
+    def __init__(self, kind, num_agents, seed, env_id, num_samples, decision_rule, horizon=1000):
+        install()
+        import gym
+        from utils.env_creator_functions import env_creator
+        import contract.contract_list as cl
+        import environments.two_stage_train as tst
+        self.kind, self.n = kind, num_agents
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        with active(self.ctx):
+            self.ctx.begin(px.EPISODE_CONSTRUCT, 0)
+            self.base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                                    dict(num_agents=num_agents, env_params={}, image_obs=True, horizon=horizon))
+        c = cl.CleanupContract(num_agents) if kind == "cleanup" else cl.HarvestFeaturemodLocalContract(num_agents)
+        env = object.__new__(tst.NegotiationSolver)
+        tst.SeparateContractEnv.__init__(env, self.base, c, num_agents, True)
+        env.horizon, env.convolutional, env.shared = horizon, True, True
+        self.trainer = env.frozen_trainer = ScriptedValueTrainer(num_agents, float(c.contract_space.high[0]))
+        env.contract_param_space = gym.spaces.Box(low=c.contract_space.low, high=c.contract_space.high)
+        env.contract_low = c.contract_space.low
+        env.num_samples, env.decision_rule, env.config = num_samples, decision_rule, {}
+        self.env = env
+        self.keys = ["a%d" % i for i in range(num_agents)]
+        self.all_vals = self.all_params = None
+        orig = env.compute_best_param
+
+        def capture(all_vals, all_params, dec_rule=None):
+            if dec_rule is None:                      # the outer call: the full candidate list
+                self.all_vals = np.array([[v[k] for k in self.keys] for v in all_vals], dtype=np.float64)
+                self.all_params = np.array([np.asarray(p, dtype=np.float64)[0] for p in all_params])
+            return orig(all_vals, all_params, dec_rule)
+        env.compute_best_param = capture
+
+    def reset(self):
+        self.episode += 1
+        self.trainer.calls = 0
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        self.env.params = {k: np.asarray(v, dtype=np.float64) for k, v in self.env.params.items()}
+        return {"obs": np.stack([np.rint(obs[k]["image"] * 255.0).astype(np.uint8) for k in self.keys]),
+                "contract_obs": np.stack([np.asarray(obs[k]["contract"], dtype=np.float64) for k in self.keys]),
+                "params": self.all_params.copy(), "vals": self.all_vals.copy(),
+                "theta": np.float64(np.asarray(self.env.contract_param)[0])}
+
+    def step(self, actions):
+        acts = {k: int(a) for k, a in zip(self.keys, actions)}
+        with active(self.ctx):
+            self.ctx.begin(self.episode, self.base.timesteps + 1)
+            obs, rew, done, info = self.env.step(acts)
+        return {"obs": np.stack([np.rint(obs[k]["image"] * 255.0).astype(np.uint8) for k in self.keys]),
+                "contract_obs": np.stack([np.asarray(obs[k]["contract"], dtype=np.float64) for k in self.keys]),
+                "rew": np.array([rew[k] for k in self.keys], dtype=np.float64), "done": bool(done["__all__"])}
+
+
+class RefJointEnv:
+    """The reference's JointEnv (two_stage_train.py:476-617) over CleanupEnv / HarvestEnv under RNG injection."""
+
+    def __init__(self, kind, num_agents, seed, env_id, mode, horizon=1000):
+        install()
+        from utils.env_creator_functions import env_creator
+        self.kind, self.n, self.mode = kind, num_agents, mode
+        self.ctx = DrawContext(seed, env_id)
+        self.episode = -1
+        with active(self.ctx):
+            self.ctx.begin(px.EPISODE_CONSTRUCT, 0)
+            self.base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                                    dict(num_agents=num_agents, env_params={}, image_obs=True, horizon=horizon,
+                                         disable_firing=False))
+            self.env = env_creator("JointEnv", dict(base_env=self.base, num_agents=num_agents,
+                                                    global_obs=mode == "global", concatenated_obs=mode == "concatenated"))
+
+    @staticmethod
+    def _img(obs):
+        o = obs["a0"]
+        return np.rint(o["image"] * 255.0).astype(np.uint8)
+
+    def reset(self):
+        self.episode += 1
+        with active(self.ctx):
+            self.ctx.begin(self.episode, 0)
+            obs = self.env.reset()
+        assert list(obs.keys()) == ["a0"]
+        return self._img(obs)
+
+    def step(self, actions):
+        with active(self.ctx):
+            self.ctx.begin(self.episode, self.base.timesteps + 1)
+            obs, rew, done, info = self.env.step({"a0": np.asarray(actions)})
+        assert sorted(done.keys()) == ["__all__", "a0"] and list(rew.keys()) == ["a0"]
+        i = info["a0"]
+        return {"obs": self._img(obs), "rew": np.float64(rew["a0"]), "done": bool(done["__all__"]),
+                "eaten_apples": int(i["eaten_apples"]),
+                "info1": int(i["cleaned_squares" if self.kind == "cleanup" else "eaten_close_apples"]),
+                "feature_obs": np.asarray(i["feature_obs"], dtype=np.float64)}
 
 
 class RefCarEnv:

@@ -888,6 +888,19 @@ void oracle_get_metrics(void* h, double* out)
         }
     }
 }
+/* MapEnv.global_view() (map_env.py:394-395): world_map_color without its padding, uint8 [E][H][W][3].  Agents
+ * appear in it from the first step on: MapEnv.reset (map_env.py:306-342) never paints them into the colour map. */
+void oracle_global_view(void* h, uint8_t* out)
+{
+    batch_t* b = (batch_t*)h;
+    for (int i = 0; i < b->E; i++) {
+        env_t* e = &b->envs[i];
+        uint8_t* o = out + (size_t)i * b->H * b->W * 3;
+        for (int r = 0; r < b->H; r++)
+            for (int c = 0; c < b->W; c++)
+                memcpy(o + ((size_t)r * b->W + c) * 3, e->color[r + VIEW][c + VIEW], 3);
+    }
+}
 int oracle_feature_dim(void* h) { return ((batch_t*)h)->F; }
 
 /* Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281).

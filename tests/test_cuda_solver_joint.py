@@ -1,0 +1,167 @@
+"""GPU: NegotiationSolver (candidates + decision rules) and the JointEnv output layouts on the device, against the
+reference-generated fixtures (batched C-ABI path and drop-in dict API) and against the oracle at larger sizes."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(fx, E=3, index=1, contract=True, **kw):
+    from contracts_b200.batched import BatchedGridEnv
+    kind = str(fx["kind"])
+    cname = ("CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract") if contract else None
+    return BatchedGridEnv(kind + "_new", E, int(fx["n"]), contract=cname, seed=int(fx["seed"]),
+                          first_env_id=(int(fx["env_id"]) - index) & 0xFFFFFFFF, **kw)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("solver_"))
+def test_solver_batched_matches_reference(name):
+    import torch
+    fx = gu.load(name)
+    n, S, rule, i = int(fx["n"]), int(fx["num_samples"]), str(fx["rule"]), 1
+    env = _batch(fx)
+    rng = np.random.RandomState(5)
+    for ep in range(fx["params"].shape[0]):
+        gu.assert_same("reset obs", env.reset()[i].cpu().numpy(), fx["reset_obs"][ep], "ep %d" % ep)
+        params = env.solver_sample(S)
+        gu.assert_same("candidates", params[i].cpu().numpy(), fx["params"][ep], "ep %d" % ep)
+        vals = rng.uniform(-1, 1, size=(env.E, S + 1, n))
+        vals[i] = fx["vals"][ep]
+        theta, idx = env.solver_choose(params, torch.as_tensor(vals).cuda(), rule)
+        gu.assert_same("theta", theta[i].item(), fx["theta"][ep], "ep %d" % ep)
+        gu.assert_same("theta in state", env.get_state()["theta"].cpu().numpy(), theta.cpu().numpy(), "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            a = torch.as_tensor(np.broadcast_to(fx["actions"][ep, t].astype(np.uint8), (env.E, n)).copy()).cuda()
+            obs, rew, done, info = env.step(a)
+            gu.assert_same("obs", obs[i].cpu().numpy(), fx["obs"][ep, t], "ep %d step %d" % (ep, t))
+            gu.assert_same("rew", rew[i].cpu().numpy(), fx["rew"][ep, t], "ep %d step %d" % (ep, t))
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("solver_"))
+def test_solver_dict_api_replays_reference(name):
+    from contracts_b200.contract import contract_list
+    from contracts_b200.utils.env_creator_functions import env_creator
+    from oracle.scripted import scripted_value
+    fx = gu.load(name)
+    kind, n, S, rule = str(fx["kind"]), int(fx["n"]), int(fx["num_samples"]), str(fx["rule"])
+    base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                       dict(num_agents=n, env_params={}, image_obs=True, seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+    contract = getattr(contract_list, gu.contract_name({"contract": True, "kind": kind}))(n)
+    scale = float(contract.contract_space.high[0])
+    env = env_creator("NegotiationSolver", dict(
+        base_env=base, contract=contract, num_agents=n, horizon=1000, trainer_config={}, trainer_env=None, trainer_path=None,
+        convolutional=True, shared=True, contract_samples=S, decision_rule=rule,
+        value_fn=lambda obs, k: scripted_value(obs, int(k[1:]), n, scale)))
+    keys = ["a%d" % i for i in range(n)]
+    for ep in range(fx["params"].shape[0]):
+        obs = env.reset()
+        for i, k in enumerate(keys):
+            gu.assert_same("reset image", obs[k]["image"], fx["reset_obs"][ep][i].astype(np.float64) / 255, "ep %d" % ep)
+            gu.assert_same("reset contract", obs[k]["contract"], fx["reset_contract_obs"][ep][i], "ep %d" % ep)
+        gu.assert_same("theta", np.float64(env.contract_param[0]), fx["theta"][ep], "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            ctx = "ep %d step %d" % (ep, t)
+            obs, rew, done, info = env.step({k: int(fx["actions"][ep, t][i]) for i, k in enumerate(keys)})
+            for i, k in enumerate(keys):
+                gu.assert_same("image", obs[k]["image"], fx["obs"][ep, t][i].astype(np.float64) / 255, ctx)
+                gu.assert_same("contract", obs[k]["contract"], fx["contract_obs"][ep, t][i], ctx)
+                gu.assert_same("reward", rew[k], fx["rew"][ep, t][i], ctx)
+
+
+def test_solver_rules_match_oracle_with_ties(oracle_lib):
+    """Random values on a coarse lattice (many welfare ties and duplicate candidates), both rules, every env kind."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.features import BatchedFeatureEnv
+    from contracts_b200.selfdrive import BatchedCarEnv
+    rng = np.random.RandomState(11)
+    E, S = 300, 7
+    envs = [(BatchedGridEnv("cleanup_new", E, 5, contract="CleanupContract", seed=9, first_env_id=1000), float(np.float32(0.2)), 1000),
+            (BatchedFeatureEnv("harvest", E, 4, contract="HarvestFeaturemodLocalContract", seed=9, first_env_id=7), float(np.float32(10.0)), 7),
+            (BatchedCarEnv(E, 3, contract="SelfdriveContractDistprop", seed=9, first_env_id=50), float(np.float32(100.0)), 50)]
+    from contracts_b200.batched import solver_choose, solver_sample
+    for env, high, first in envs:
+        n = env.n
+        for ep in range(2):
+            env.reset()
+            params = solver_sample(env, S)
+            pc = params.cpu().numpy()
+            for e in (0, 1, E - 1):
+                want = oracle_lib.solver_candidates(9, first + e, ep, 0.0, high, S)
+                gu.assert_same("candidates", pc[e], want, "%s ep %d env %d" % (type(env).__name__, ep, e))
+            for rule in ("max", "majority"):
+                vals = rng.randint(0, 3, size=(E, S + 1, n)).astype(np.float64) * 0.5
+                vals[::5, 3] = vals[::5, 1]                 # duplicate candidates: all_vals.index() picks the first
+                theta, idx = solver_choose(env, params, torch.as_tensor(vals).cuda(), rule)
+                th, ix = theta.cpu().numpy(), idx.cpu().numpy()
+                for e in range(E):
+                    wt, wi = oracle_lib.solver_choose(pc[e], vals[e], rule)
+                    assert ix[e] == wi and gu.bits(th[e]) == gu.bits(wt), (type(env).__name__, rule, e, ix[e], wi)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("joint_"))
+def test_joint_layouts_batched_match_reference(name):
+    import torch
+    fx = gu.load(name)
+    n, mode, i = int(fx["n"]), str(fx["mode"]), 2
+    env = _batch(fx, E=5, index=i, contract=False, horizon=int(fx["horizon"]))
+    view = (lambda: env.global_view()[i].cpu().numpy()) if mode == "global" else (lambda: env.concatenated_obs()[i].cpu().numpy())
+    for ep in range(fx["actions"].shape[0]):
+        env.reset()
+        gu.assert_same("reset obs", view(), fx["reset_obs"][ep], "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            a = torch.as_tensor(np.broadcast_to(fx["actions"][ep, t].astype(np.uint8), (env.E, n)).copy()).cuda()
+            obs, rew, done, info = env.step(a)
+            gu.assert_same("obs", view(), fx["obs"][ep, t], "ep %d step %d" % (ep, t))
+            gu.assert_same("done", int(done[i].item()), int(fx["done"][ep, t]), "ep %d step %d" % (ep, t))
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("joint_"))
+def test_joint_dict_api_replays_reference(name):
+    from contracts_b200.utils.env_creator_functions import env_creator
+    fx = gu.load(name)
+    kind, n, mode = str(fx["kind"]), int(fx["n"]), str(fx["mode"])
+    base = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                       dict(num_agents=n, env_params={}, image_obs=True, disable_firing=False, horizon=int(fx["horizon"]),
+                            seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+    env = env_creator("JointEnv", dict(base_env=base, num_agents=n, global_obs=mode == "global",
+                                       concatenated_obs=mode == "concatenated"))
+    assert tuple(env.observation_space["image"].shape) == tuple(fx["reset_obs"].shape[1:])
+    assert list(env.action_space.nvec) == [9 if kind == "cleanup" else 8] * n
+    for ep in range(fx["actions"].shape[0]):
+        obs = env.reset()
+        assert list(obs.keys()) == ["a0"]
+        gu.assert_same("reset image", obs["a0"]["image"], fx["reset_obs"][ep].astype(np.float64) / 255, "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            ctx = "ep %d step %d" % (ep, t)
+            obs, rew, done, info = env.step({"a0": fx["actions"][ep, t]})
+            gu.assert_same("image", obs["a0"]["image"], fx["obs"][ep, t].astype(np.float64) / 255, ctx)
+            gu.assert_same("reward", np.float64(rew["a0"]), fx["rew"][ep, t], ctx)
+            d = bool(fx["done"][ep, t])
+            assert done == {"a0": d, "__all__": d}, ctx
+            assert info["a0"]["eaten_apples"] == fx["eaten_apples"][ep, t], ctx
+            assert info["a0"]["cleaned_squares" if kind == "cleanup" else "eaten_close_apples"] == fx["info1"][ep, t], ctx
+            gu.assert_same("feature_obs", info["a0"]["feature_obs"], fx["feature_obs"][ep, t], ctx)
+
+
+@pytest.mark.parametrize("kind,n,E", [("cleanup", 8, 257), ("harvest", 3, 130), ("cleanup", 1, 6)])
+def test_joint_layouts_match_oracle(oracle_lib, kind, n, E):
+    """Larger batches (E not a multiple of the kernel's 4-env groups), dense and padded observation tensors."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    amap = CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP
+    for padded in (False, True):
+        orc = oracle_lib.GridOracle(kind, E, n, amap, seed=3, first_env_id=10)
+        env = BatchedGridEnv(kind + "_new", E, n, amap, seed=3, first_env_id=10, padded_obs=padded)
+        rng = np.random.RandomState(2)
+        obs_o = orc.reset()
+        env.reset()
+        for t in range(12):
+            gu.assert_same("global view", env.global_view().cpu().numpy(), orc.global_view(), "t %d" % t)
+            gu.assert_same("concatenated", env.concatenated_obs().cpu().numpy(), oracle_lib.concatenated_obs(obs_o), "t %d" % t)
+            a = rng.randint(0, 8, size=(E, n))
+            obs_o = orc.step(a, want_features=False)["obs"]
+            env.step(torch.as_tensor(a.astype(np.uint8)).cuda())

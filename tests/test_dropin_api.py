@@ -77,7 +77,7 @@ def test_env_creator_rejects_unknown_and_out_of_scope():
     with pytest.raises(ValueError):
         env_creator("Nope", {})
     with pytest.raises(NotImplementedError):
-        env_creator("JointEnv", {})
+        env_creator("ContractWrapperCombined", {})
 
 
 def test_render_and_global_obs():
