@@ -97,26 +97,42 @@ struct GridParams {
 };
 
 // use_collective_reward / inequity_averse_reward (map_env.py:289-301): the shaped reward of agent a from the
-// integer env rewards ri[0..n).  Differences and their partial sums are exact integers; alpha * sum,
-// beta * sum, their sum, the division by (num_agents - 1) and the subtraction are float64, in that order.
-__device__ __noinline__ double shaped_reward(const GridParams& p, const int* ri, int a)
+// integer env rewards.  Differences and their partial sums are exact integers; alpha * sum, beta * sum, their
+// sum, the division by (num_agents - 1) and the subtraction are float64, in that order.  (Scalar arguments and
+// no local arrays: a GridParams reference into a non-inlined function would copy the kernel parameters to the stack.)
+__device__ __forceinline__ double inequity_term(int ra, int sp, int sn, double alpha, double beta, int n)
 {
-    const int n = p.n;
+    const double dis = __dmul_rn(alpha, (double)sp), adv = __dmul_rn(beta, (double)sn);
+    return __dsub_rn((double)ra, __ddiv_rn(__dadd_rn(dis, adv), (double)(n - 1)));
+}
+// thread per env: the int16 rewards sit in the RS_* words rsp[j * rstride] (bits 16-31)
+__device__ __noinline__ double shaped_reward(int mode, double alpha, double beta, int n, const uint32_t* rsp, int rstride, int a)
+{
     int coll = 0;
-    for (int j = 0; j < n; j++) coll += ri[j];
-    const bool collective = p.reward_mode & RM_COLLECTIVE;
-    const int ra = collective ? coll : ri[a];
-    double r = (double)ra;
-    if (p.reward_mode & RM_INEQUITY) {
-        int sp = 0, sn = 0;
-        for (int j = 0; j < n; j++) {
-            const int d = (collective ? coll : ri[j]) - ra;
-            if (d > 0) sp += d; else sn += d;
-        }
-        const double dis = __dmul_rn(p.alpha, (double)sp), adv = __dmul_rn(p.beta, (double)sn);
-        r = __dsub_rn(r, __ddiv_rn(__dadd_rn(dis, adv), (double)(n - 1)));
+    for (int j = 0; j < n; j++) coll += (int)rsp[j * rstride] >> 16;
+    const bool collective = mode & RM_COLLECTIVE;
+    const int ra = collective ? coll : ((int)rsp[a * rstride] >> 16);
+    if (!(mode & RM_INEQUITY)) return (double)ra;
+    int sp = 0, sn = 0;
+    for (int j = 0; j < n; j++) {
+        const int d = (collective ? coll : ((int)rsp[j * rstride] >> 16)) - ra;
+        if (d > 0) sp += d; else sn += d;
     }
-    return r;
+    return inequity_term(ra, sp, sn, alpha, beta, n);
+}
+// warp per env, lane = agent (every lane calls)
+__device__ __noinline__ double shaped_reward_warp(int mode, double alpha, double beta, int n, int reward)
+{
+    int coll = 0;
+    for (int j = 0; j < n; j++) coll += __shfl_sync(FULL, reward, j);
+    const bool collective = mode & RM_COLLECTIVE;
+    const int ra = collective ? coll : reward;
+    int sp = 0, sn = 0;
+    for (int j = 0; j < n; j++) {
+        const int d = (collective ? coll : __shfl_sync(FULL, reward, j)) - ra;
+        if (d > 0) sp += d; else sn += d;
+    }
+    return (mode & RM_INEQUITY) ? inequity_term(ra, sp, sn, alpha, beta, n) : (double)ra;
 }
 
 // per-warp misc area
@@ -923,12 +939,8 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
 
         // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
         double base = (double)reward;
-        if (p.reward_mode) {                           // shaped env rewards (map_env.py:289-301)
-            int ri[SSD_MAXN];
-#pragma unroll
-            for (int j = 0; j < SSD_MAXN; j++) ri[j] = __shfl_sync(FULL, reward, j);
-            if (act_lane) base = shaped_reward(p, ri, lane);
-        }
+        if (p.reward_mode)                             // shaped env rewards (map_env.py:289-301)
+            base = shaped_reward_warp(p.reward_mode, p.alpha, p.beta, n, act_lane ? reward : 0);
         double tr = 0.0;
         if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
         else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (total_close < 4 && eaten_close > 0) ? theta : 0.0;

@@ -63,54 +63,115 @@ __device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, in
 }
 
 // one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map in global memory.
-// The 15 ray cells are loaded up front (independent loads, one memory round trip), then walked in
-// registers.  "Agent on this cell" compares the cell with the (register-resident) cells of all agents:
-// branch-free, because with 32 envs per warp some lane always takes the rare path.  The three rays are
-// distinct lines, so applying H -> R immediately is the same as the reference's deferred `updates` list.
-// Returns the number of cleaned cells.
-struct AgentCells { uint32_t c[SSD_MAXN]; };        // row | col << 8 of each agent (0xFFFFFFFF: no agent)
-__device__ __noinline__ int g2_fire(uint8_t* map, uint32_t shooter, const AgentCells ac, uint32_t* res /* lane-strided */,
-                                    bool clean, int H, int W, int Wp)
+//
+// In the shooter's frame (along = steps in the firing direction, across = steps to its right) the three rays are
+//   centre  across  0, along 1..5      right  across +1, along 0..4      left  across -1, along 0..4
+// (firing_points :766-779: the side rays start beside the shooter).  Which agents stand on a ray cell is found per
+// AGENT, not per cell: with x = (drow + 64) | (dcol + 64) << 8 relative to the shooter, one PRMT (selector by
+// orientation) over x and 0x8080 - x gives y = (along + 64) | (across + 64) << 8, and z = y - 0x3F40 is
+// along (left ray), 0x100 + along (centre) or 0x200 + along (right) exactly for the agents on a ray: bit
+// (z & 7) + 8 (z >> 8) of a 32-bit occupancy mask.  The 15 ray cells are loaded up front (independent loads, one
+// memory round trip; cells outside the map read as walls) and classified through 32-bit lookup words shifted by
+// the cell code, so a ray is walked with three 5-bit masks: a ray stops at its first wall / agent / (CLEAN beam)
+// waste cell (:785-805).  The rays are distinct lines, so applying H -> R immediately equals the reference's
+// deferred `updates` list.  Returns the number of cleaned cells.
+#define RAY_L 0            // mask bit of cell i of the left / centre / right ray: RAY_x + i (centre: along = i + 1)
+#define RAY_C 9
+#define RAY_R 16
+
+// Agent.hit for the agents' cell `bit` of the occupancy mask: the highest index wins duplicates (agent_by_pos)
+__device__ __noinline__ void g2_hit(const uint32_t* ags /* lane-strided */, int n, uint32_t* res, uint32_t cs, uint32_t sel, uint32_t bit)
+{
+    int victim = -1;
+    for (int a = 0; a < n; a++) {
+        const uint32_t v = ags[a * 32];
+        const uint32_t x = (v & 0xFFFFu) + cs, z = __byte_perm(x, 0x8080u - x, sel) - 0x3F40u;
+        if ((z & 0xFFFFFCF8u) == 0u && ((z & 7u) | ((z >> 5) & 0x18u)) == bit) victim = a;
+    }
+    if (victim >= 0) res[victim * 32] -= 50u << RS_REWARD_SHIFT;            // Agent.hit(b"F"): -50 (Agent.py:224-226)
+}
+
+__device__ __forceinline__ uint32_t ray_mask(uint32_t lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4)
+{
+    uint32_t m = (lut >> (c4 & 0x1Cu)) & 1u;
+    m = m * 2u + ((lut >> (c3 & 0x1Cu)) & 1u);
+    m = m * 2u + ((lut >> (c2 & 0x1Cu)) & 1u);
+    m = m * 2u + ((lut >> (c1 & 0x1Cu)) & 1u);
+    return m * 2u + ((lut >> (c0 & 0x1Cu)) & 1u);
+}
+
+__device__ __forceinline__ int g2_fire(uint8_t* map, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN], const uint32_t* ags, int n,
+                                       uint32_t* res, bool clean, int H, int W, int Wp)
 {
     const int row = (int)(shooter & 255u), col = (int)((shooter >> 8) & 255u), ori = (int)((shooter >> 16) & 3u);
     const int dr = ori_dr(ori), dc = ori_dc(ori);
     const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);       // right = clockwise of dir
-    uint32_t code[15];
+    // cells of the map in front of the shooter; the side rays start on the shooter's own row / column
+    const int ahead = ori == ORI_UP ? row : (ori == ORI_DOWN ? H - 1 - row : (ori == ORI_LEFT ? col : W - 1 - col));
+    const int n0 = min(ahead, 5), ns = min(ahead + 1, 5);
+    const bool okr = (unsigned)(row + rr) < (unsigned)H && (unsigned)(col + rcl) < (unsigned)W;
+    const bool okl = (unsigned)(row - rr) < (unsigned)H && (unsigned)(col - rcl) < (unsigned)W;
+    const int step = dr * Wp + dc, side = rr * Wp + rcl, base = row * Wp + col;
+    const int nr = okr ? ns : 0, nl = okl ? ns : 0;
+    uint32_t cc[5], cr[5], cl[5];
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
-        const int r0 = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0));
-        const int c0 = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0));
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
-            const bool inb = (unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W;
-            code[b * 5 + i] = inb ? (uint32_t)map[r * Wp + c] : (uint32_t)C_WALL;      // out of bounds stops a ray like a wall
-        }
+    for (int i = 0; i < 5; i++) {
+        cc[i] = i < n0 ? (uint32_t)map[base + (i + 1) * step] : (uint32_t)C_WALL;
+        cr[i] = i < nr ? (uint32_t)map[base + side + i * step] : (uint32_t)C_WALL;
+        cl[i] = i < nl ? (uint32_t)map[base - side + i * step] : (uint32_t)C_WALL;
     }
+    // agents on the rays
+    const uint32_t sel = ori == ORI_UP ? 0x3214u : (ori == ORI_DOWN ? 0x3250u : (ori == ORI_RIGHT ? 0x3201u : 0x3245u));
+    const uint32_t cs = 0x4040u - (shooter & 0xFFFFu);
+    uint32_t occ = 0;
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) {
+        const uint32_t x = agc[a] + cs;                                       // absent agents (0xFFFF): bits above 15 set
+        const uint32_t z = __byte_perm(x, 0x8080u - x, sel) - 0x3F40u;
+        const uint32_t b = 1u << ((z & 7u) | ((z >> 5) & 0x18u));
+        occ |= (z & 0xFFFFFCF8u) == 0u ? b : 0u;
+    }
+    occ &= (31u << RAY_L) | (31u << RAY_C) | (31u << RAY_R);
+    const uint32_t WL = 1u << C_WALL, HL = clean ? 1u << C_WASTE : 0u;        // lookup words indexed by the cell code
+    const uint32_t wall = ray_mask(WL, cl[0], cl[1], cl[2], cl[3], cl[4]) << RAY_L | ray_mask(WL, cc[0], cc[1], cc[2], cc[3], cc[4]) << RAY_C
+                        | ray_mask(WL, cr[0], cr[1], cr[2], cr[3], cr[4]) << RAY_R;
+    const uint32_t waste = ray_mask(HL, cl[0], cl[1], cl[2], cl[3], cl[4]) << RAY_L | ray_mask(HL, cc[0], cc[1], cc[2], cc[3], cc[4]) << RAY_C
+                         | ray_mask(HL, cr[0], cr[1], cr[2], cr[3], cr[4]) << RAY_R;
+    const uint32_t stop = wall | waste | occ;
     int nup = 0;
 #pragma unroll
     for (int b = 0; b < 3; b++) {
-        const int r0 = row + (b == 1 ? rr - dr : (b == 2 ? -rr - dr : 0));
-        const int c0 = col + (b == 1 ? rcl - dc : (b == 2 ? -rcl - dc : 0));
-        bool alive = true;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            const uint32_t cc = code[b * 5 + i] & CODE_MASK;
-            const int r = r0 + (i + 1) * dr, c = c0 + (i + 1) * dc;
-            const uint32_t cell = (uint32_t)r | ((uint32_t)c << 8);
-            int victim = -1;                                    // agent_by_pos: the highest index wins duplicates
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) victim = ac.c[a] == cell ? a : victim;
-            if (alive && cc != C_WALL) {
-                if (clean && cc == C_WASTE) { map[r * Wp + c] = (uint8_t)C_RIVER; nup++; alive = false; }
-                if (victim >= 0) {
-                    if (!clean) res[victim * 32] -= 50u << RS_REWARD_SHIFT;          // Agent.hit(b"F"): -50 (Agent.py:224-226)
-                    alive = false;
-                }
-            } else alive = false;
+        const int sh = b == 0 ? RAY_L : (b == 1 ? RAY_C : RAY_R);
+        const uint32_t s5 = (stop >> sh) & 31u;
+        const uint32_t f = (s5 & (0u - s5)) << sh;                            // the ray's first stopping cell (0: none)
+        if (f & ~wall) {
+            if (f & waste) {                                                   // CLEAN: H -> R (cleanup_new.py:285-290)
+                const int i = __ffs(f) - 1 - sh;
+                map[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step] = (uint8_t)C_RIVER;
+                nup++;
+            }
+            if (!clean && (f & occ)) g2_hit(ags, n, res, cs, sel, (uint32_t)(__ffs(f) - 1));
         }
     }
     return nup;
+}
+
+// fire-and-forget global reductions (RED): the add happens at the L2, nothing comes back to the thread
+__device__ __forceinline__ void red_add(uint32_t* p, uint32_t v)
+{
+    asm volatile("red.global.add.u32 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(int* p, int v)
+{
+    asm volatile("red.global.add.s32 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(long long* p, long long v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(double* p, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,15 +188,12 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) rj[a] = a < n ? (double)((int)rsp[a * rstride] >> RS_REWARD_SHIFT) : 0.0;
     if (p.reward_mode) {                               // shaped env rewards (map_env.py:289-301) and their f64 episode sums
-        int ri[SSD_MAXN];
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) ri[a] = a < n ? ((int)rsp[a * rstride] >> RS_REWARD_SHIFT) : 0;
         double raw_step = 0.0;                         // raw_rewards = ((0 + r0) + r1) + ... (cleanup_new.py:228-232)
         const double tm1s = (double)(t - 1);
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) {
             if (a < n) {
-                rj[a] = shaped_reward(p, ri, a);
+                rj[a] = shaped_reward(p.reward_mode, p.alpha, p.beta, n, rsp, rstride, a);
                 raw_step = __dadd_rn(raw_step, rj[a]);
                 double* xs = reinterpret_cast<double*>(hdr + RO_XSUM) + a;
                 double* xt = reinterpret_cast<double*>(hdr + RO_XTSUM) + a;
@@ -175,7 +233,6 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
     const int tm1i = t - 1;
     const double tm1 = (double)tm1i;
     uint32_t n_eaten = 0, n_close = 0;
-    bool any_raw = false, any_tr = false, any_a = false, any_b = false;
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a < n) {
@@ -186,61 +243,32 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
             io.rew[o + a] = rj[a];
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o + a] =
                 eaten | ((KIND == SSD_ENV_CLEANUP ? cleaned : eclose) << 8) | (tclose << 16);
-            any_raw |= ((int)w >> RS_REWARD_SHIFT) != 0;
-            any_tr |= rj[a] != 0.0;
-            any_a |= (KIND == SSD_ENV_CLEANUP ? cleaned : eaten) != 0;
-            any_b |= eclose != 0;
         }
     }
-    // episode accumulators: all loads of a group first (one memory round trip), then the stores.  Adding a
-    // zero reward leaves an accumulator bit-identical (sums are never -0.0), so untouched groups are skipped.
-    if (any_raw && !p.reward_mode) {
-        int sr[SSD_MAXN]; long long ts[SSD_MAXN];
+    // episode accumulators: fire-and-forget reductions (RED at the L2, no load round trip in this thread's
+    // dependency chain).  One add per address and step, so a float64 RED rounds exactly like `*p = *p + x`.  Adding a
+    // zero leaves an accumulator bit-identical (sums are never -0.0), so zero terms are skipped.
 #pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { sr[a] = reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a]; ts[a] = reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a]; }
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a < n) {
-                const int reward = (int)rsp[a * rstride] >> RS_REWARD_SHIFT;
-                if (reward != 0) {
-                    reinterpret_cast<int*>(hdr + RO_SUM_RAW)[a] = sr[a] + reward;
-                    reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[a] = ts[a] + (long long)tm1i * reward;
-                }
+    for (int a = 0; a < SSD_MAXN; a++) {
+        if (a < n) {
+            const uint32_t w = rsp[a * rstride];
+            const int reward = (int)w >> RS_REWARD_SHIFT;
+            if (reward != 0 && !p.reward_mode) {
+                red_add(reinterpret_cast<int*>(hdr + RO_SUM_RAW) + a, reward);
+                red_add(reinterpret_cast<long long*>(hdr + RO_TSUM_RAW) + a, (long long)tm1i * reward);
             }
-        }
-    }
-    if (p.contract != SSD_CONTRACT_NONE && any_tr) {
-        double st[SSD_MAXN], tt[SSD_MAXN];
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { st[a] = reinterpret_cast<double*>(hdr + RO_SUM_TR)[a]; tt[a] = reinterpret_cast<double*>(hdr + RO_TSUM_TR)[a]; }
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a < n && rj[a] != 0.0) {
-                reinterpret_cast<double*>(hdr + RO_SUM_TR)[a] = __dadd_rn(st[a], rj[a]);
-                reinterpret_cast<double*>(hdr + RO_TSUM_TR)[a] = __dadd_rn(tt[a], __dmul_rn(tm1, rj[a]));
+            if (p.contract != SSD_CONTRACT_NONE && rj[a] != 0.0) {
+                red_add(reinterpret_cast<double*>(hdr + RO_SUM_TR) + a, rj[a]);
+                red_add(reinterpret_cast<double*>(hdr + RO_TSUM_TR) + a, __dmul_rn(tm1, rj[a]));
             }
+            const uint32_t da = KIND == SSD_ENV_CLEANUP ? (w & RS_CLEANED_MASK) : ((w >> 2) & 1u), db = (w >> 3) & 1u;
+            if (da) red_add(reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A) + a, da);
+            if (KIND == SSD_ENV_HARVEST && db) red_add(reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B) + a, db);
         }
     }
-    if (any_a || any_b) {
-        uint32_t ca[SSD_MAXN], cb[SSD_MAXN];
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) if (a < n) { ca[a] = reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a]; cb[a] = reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a]; }
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a < n) {
-                const uint32_t w = rsp[a * rstride];
-                const uint32_t da = KIND == SSD_ENV_CLEANUP ? (w & RS_CLEANED_MASK) : ((w >> 2) & 1u), db = (w >> 3) & 1u;
-                if (da) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[a] = ca[a] + da;
-                if (KIND == SSD_ENV_HARVEST && db) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[a] = cb[a] + db;
-            }
-        }
-    }
-    if (n_eaten) *reinterpret_cast<uint32_t*>(hdr + RO_APPLES) += n_eaten;
-    if (KIND == SSD_ENV_HARVEST && n_close) *reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS) += n_close;
-    if (total_tr != 0.0) {
-        double* mt = reinterpret_cast<double*>(hdr + RO_TRANSFERS);
-        *mt = __dadd_rn(*mt, total_tr);
-    }
+    if (n_eaten) red_add(reinterpret_cast<uint32_t*>(hdr + RO_APPLES), n_eaten);
+    if (KIND == SSD_ENV_HARVEST && n_close) red_add(reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS), n_close);
+    if (total_tr != 0.0) red_add(reinterpret_cast<double*>(hdr + RO_TRANSFERS), total_tr);
     if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
 }
 
@@ -386,9 +414,9 @@ __global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const Grid
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) under[a] = a < n ? (uint32_t)map[rc_off(ag[a], Wp)] : 0u;
     uint32_t on_apple = 0, first = 0;
-    AgentCells ac;
+    uint32_t agc[SSD_MAXN];                                  // agents' cells for the beams (absent: 0xFFFF)
 #pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) ac.c[a] = a < n ? (ag[a] & 0xFFFFu) : 0xFFFFFFFFu;
+    for (int a = 0; a < SSD_MAXN; a++) agc[a] = a < n ? (ag[a] & 0xFFFFu) : 0xFFFFu;
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a < n) {
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const Grid
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(map, ags[s * 32], ac, res, clean, H, W, Wp);
+            const int nup = g2_fire(map, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }
@@ -456,7 +484,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const Grid
     *reinterpret_cast<int*>(hdr + RO_T) = t;
     *reinterpret_cast<uint2*>(hdr + RO_FLAGS) =
         make_uint2((flags & ~RF_STALE_EMPTY) | (err ? (err << RF_ERR_SHIFT) : 0u), (uint32_t)hcount);
-    if (KIND == SSD_ENV_CLEANUP && ncleaned) *reinterpret_cast<uint32_t*>(hdr + RO_DIRT) += (uint32_t)ncleaned;
+    if (KIND == SSD_ENV_CLEANUP && ncleaned) red_add(reinterpret_cast<uint32_t*>(hdr + RO_DIRT), (uint32_t)ncleaned);
     uint4* rg = reinterpret_cast<uint4*>(res_g + (size_t)env * SSD_MAXN);
     rg[0] = make_uint4(res[0], res[32], res[64], res[96]);
     rg[1] = make_uint4(res[128], res[160], res[192], res[224]);
