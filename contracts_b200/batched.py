@@ -193,6 +193,21 @@ class BatchedGridEnv:
         _lib.check(self._h, self.lib.ssd_concat_obs(self._h, _ptr(self._obs_buf), self.obs_stride, _ptr(out), self._stream()))
         return out
 
+    # ---- policy-side consumer (environments/Networks/vision_net.py:150-181) -----------------------------
+    _POLICY_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+    def policy_inputs(self, dtype=torch.float32, with_contract=True, image=None, contract=None):
+        """The current observations as VisionNetwork.forward feeds its convolutions: image [E*n, 3, 15, 15] =
+        (`curr_obs / 255`).float().permute(0, 3, 1, 2), contract [E*n, 10] = (theta, 0) repeated 5 times."""
+        B = self.E * self.n
+        if image is None:
+            image = torch.empty((B, 3, 15, 15), dtype=dtype, device=self.device)
+        if with_contract and contract is None:
+            contract = torch.empty((B, 10), dtype=dtype, device=self.device)
+        _lib.check(self._h, self.lib.ssd_policy_inputs(self._h, _ptr(self._obs_buf), self.obs_stride, self._POLICY_DTYPES[dtype],
+                                                       _ptr(image), _ptr(contract) if with_contract else None, self._stream()))
+        return (image, contract) if with_contract else image
+
     # ---- NegotiationSolver (two_stage_train.py:619-776) ---------------------------------------------
     def solver_sample(self, num_samples):
         return solver_sample(self, num_samples)

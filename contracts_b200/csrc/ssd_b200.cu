@@ -720,6 +720,27 @@ int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride
     return check_launch(h, "concat_obs");
 }
 
+// ---- policy-side consumer (environments/Networks/vision_net.py:150-181) -----------------------------------
+int ssd_policy_inputs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, int32_t dtype, void* image_dev, void* contract_dev,
+                      void* stream)
+{
+    if (!h || !obs_dev || !image_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    const GridParams& p = h->gp;
+    const int64_t dense = (int64_t)p.n * SSD_OBS_BYTES;
+    if (obs_env_stride == 0) obs_env_stride = dense;
+    if (obs_env_stride < dense) return fail(h, SSD_EINVAL, "obs_env_stride %lld < %lld", (long long)obs_env_stride, (long long)dense);
+    if (p.n * 10 > VIEW_THREADS) return fail(h, SSD_EUNSUPPORTED, "policy_inputs: too many agents");
+    const dim3 grid(p.E), block(VIEW_THREADS);
+    const size_t smem = (size_t)((dense + 15) / 16 * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == POLICY_F32) policy_inputs_kernel<float><<<grid, block, smem, s>>>(p, obs_dev, obs_env_stride, (float*)image_dev, (float*)contract_dev);
+    else if (dtype == POLICY_F16) policy_inputs_kernel<__half><<<grid, block, smem, s>>>(p, obs_dev, obs_env_stride, (__half*)image_dev, (__half*)contract_dev);
+    else if (dtype == POLICY_BF16) policy_inputs_kernel<__nv_bfloat16><<<grid, block, smem, s>>>(p, obs_dev, obs_env_stride, (__nv_bfloat16*)image_dev, (__nv_bfloat16*)contract_dev);
+    else return fail(h, SSD_EINVAL, "policy_inputs: dtype must be SSD_POLICY_F32, _F16 or _BF16");
+    return check_launch(h, "policy_inputs");
+}
+
 // ---- NegotiationSolver (two_stage_train.py:619-776) ------------------------------------------------
 static SolverParams solver_params(ssd_handle* h)
 {

@@ -171,3 +171,49 @@ __global__ void solver_choose_kernel(const SolverParams p, int S, int rule, cons
     if (best_idx) best_idx[env] = src;
     *reinterpret_cast<double*>(p.theta + (size_t)env * p.theta_stride) = theta;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Policy-side consumer: what VisionNetwork.forward (environments/Networks/vision_net.py:150-181) does to the observation
+// before its first convolution, fused into one pass over the uint8 batch tensor:
+//   image    `orig_obs["image"].float().permute(0, 3, 1, 2)` with image = curr_obs / 255 (cleanup_new.py:258, a float64
+//            quotient that RLlib hands over as float32): uint8 [E][n][15][15][3] -> T [E n][3][15][15],
+//            value = T(float32(float64(x) / 255.0)) through a 256-entry table;
+//   contract `orig_obs["contract"].float().repeat(1, 5)` (vision_net.py:160-161): (theta, 0) five times, T [E n][10].
+// T = float32, float16 or bfloat16 (POLICY_F32 / F16 / BF16).  HBM-bound: 675 B read, 675 sizeof(T) written per agent.
+// One CTA per env; the windows are staged in shared memory, the outputs leave as coalesced element runs.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#define POLICY_F32 0
+#define POLICY_F16 1
+#define POLICY_BF16 2
+
+template <typename T> __device__ __forceinline__ T policy_cast(float v);
+template <> __device__ __forceinline__ float policy_cast<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half policy_cast<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 policy_cast<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(VIEW_THREADS) policy_inputs_kernel(const GridParams p, const uint8_t* __restrict__ obs, long long obs_stride,
+                                                                     T* __restrict__ image, T* __restrict__ contract)
+{
+    extern __shared__ __align__(16) uint8_t vsm[];            // n windows
+    __shared__ float lut[256];
+    const int env = blockIdx.x, n = p.n, per_env = n * SSD_OBS_BYTES;
+    for (int i = threadIdx.x; i < 256; i += VIEW_THREADS) lut[i] = __double2float_rn(__ddiv_rn((double)i, 255.0));
+    const uint8_t* src = obs + (size_t)env * obs_stride;
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)per_env) & 3) == 0)
+        for (int w = threadIdx.x; w < per_env / 4; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(vsm)[w] = reinterpret_cast<const uint32_t*>(src)[w];
+    else
+        for (int b = threadIdx.x; b < per_env; b += VIEW_THREADS) vsm[b] = src[b];
+    __syncthreads();
+    T* dst = image + (size_t)env * per_env;
+    for (int o = threadIdx.x; o < per_env; o += VIEW_THREADS) {          // o = a * 675 + c * 225 + pixel
+        const int a = o / SSD_OBS_BYTES, r = o - a * SSD_OBS_BYTES;
+        const int c = r / SSD_OBS_PIX, pix = r - c * SSD_OBS_PIX;
+        dst[o] = policy_cast<T>(lut[vsm[a * SSD_OBS_BYTES + pix * 3 + c]]);
+    }
+    if (contract && threadIdx.x < n * 10) {
+        const double theta = *reinterpret_cast<const double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA);
+        contract[(size_t)env * n * 10 + threadIdx.x] = policy_cast<T>((threadIdx.x & 1) ? 0.0f : __double2float_rn(theta));
+    }
+}

@@ -139,6 +139,16 @@ int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream);
  * 604-609): obs_dev uint8 [E][n][15][15][3] (env stride obs_env_stride, 0 = dense) -> out_dev uint8 [E][15][15][3n]. */
 int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream);
 
+/* --- policy-side consumer (environments/Networks/vision_net.py:150-181) --------------------------------- */
+#define SSD_POLICY_F32 0
+#define SSD_POLICY_F16 1
+#define SSD_POLICY_BF16 2
+/* The observation as VisionNetwork.forward feeds its first convolution, in one pass over the uint8 batch tensor:
+ * image_dev T [E*n][3][15][15] = (`curr_obs / 255` as float32).permute(0, 3, 1, 2) (:159,167) cast to T;
+ * contract_dev (nullable) T [E*n][10] = (theta, 0) repeated 5 times (:160-161).  T by `dtype`. */
+int ssd_policy_inputs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, int32_t dtype, void* image_dev,
+                      void* contract_dev, void* stream);
+
 /* --- NegotiationSolver (environments/two_stage_train.py:619-776); every env kind ------------------- */
 #define SSD_SOLVER_RULE_MAX 0        /* decision_rule 'max'      (:751-757) */
 #define SSD_SOLVER_RULE_MAJORITY 1   /* decision_rule 'majority' (:758-773) */

@@ -165,3 +165,27 @@ def test_joint_layouts_match_oracle(oracle_lib, kind, n, E):
             a = rng.randint(0, 8, size=(E, n))
             obs_o = orc.step(a, want_features=False)["obs"]
             env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+
+
+@pytest.mark.parametrize("kind,n,E,padded", [("cleanup", 8, 37, False), ("harvest", 3, 20, True), ("cleanup", 5, 9, False)])
+def test_policy_inputs_match_vision_net_preprocessing(kind, n, E, padded):
+    """image = (curr_obs / 255 in float64 -> float32).permute(0, 3, 1, 2), contract = (theta, 0) x 5
+    (environments/Networks/vision_net.py:159-167), in float32 / float16 / bfloat16."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    cname = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    env = BatchedGridEnv(kind + "_new", E, n, contract=cname, seed=4, first_env_id=3, padded_obs=padded)
+    env.reset()
+    rng = np.random.RandomState(1)
+    for t in range(5):
+        env.step(torch.as_tensor(rng.randint(0, 8, size=(E, n)).astype(np.uint8)).cuda())
+    obs = env.obs.cpu().numpy()
+    want = torch.from_numpy((obs / 255).reshape(E * n, 15, 15, 3)).float().permute(0, 3, 1, 2).contiguous()
+    theta = env.get_state()["theta"].cpu()
+    wc = torch.stack([theta, torch.zeros_like(theta)], dim=1).float().repeat_interleave(n, dim=0).repeat(1, 5)
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        img, con = env.policy_inputs(dt)
+        assert img.dtype == dt and tuple(img.shape) == (E * n, 3, 15, 15) and tuple(con.shape) == (E * n, 10)
+        assert torch.equal(img.cpu(), want.to(dt)), dt
+        assert torch.equal(con.cpu(), wc.to(dt)), dt
+    assert torch.equal(env.policy_inputs(torch.float32, with_contract=False).cpu(), want)
