@@ -186,6 +186,17 @@ class BatchedGridEnv:
         _lib.check(self._h, self.lib.ssd_global_view(self._h, _ptr(out), self._stream()))
         return out
 
+    def record_beams(self, on=True):
+        """Keep the cells crossed by the beams of each step (MapEnv.beam_pos) so that `render()` can draw them."""
+        _lib.check(self._h, self.lib.ssd_record_beams(self._h, 1 if on else 0))
+
+    def render(self, out=None):
+        """MapEnv.full_map_to_colors() of every env (map_env.py:389-392): uint8 [E, H, W, 3], beams included when recorded."""
+        if out is None:
+            out = torch.empty((self.E, self.H, self.W, 3), dtype=torch.uint8, device=self.device)
+        _lib.check(self._h, self.lib.ssd_render(self._h, _ptr(out), self._stream()))
+        return out
+
     def concatenated_obs(self, out=None):
         """The agents' windows concatenated along the channel axis (two_stage_train.py:527-533): uint8 [E, 15, 15, 3 n]."""
         if out is None:

@@ -36,6 +36,7 @@ struct ssd_handle {
     cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
+    uint8_t* d_beam;         // ssd_record_beams: [E][map_bytes] beam overlay of the last step
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
@@ -635,6 +636,7 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
     long long stride = obs_env_stride ? obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
     if (stride < (long long)p.n * SSD_OBS_BYTES) return fail(h, SSD_EINVAL, "obs_env_stride too small");
     cudaStream_t s = (cudaStream_t)stream;
+    if (p.beam) beam_clear_kernel<<<(p.E + 3) / 4, 128, 0, s>>>(p, mask_dev);                 // self.beam_pos = [] (map_env.py:316)
     if (p.kind == SSD_ENV_CLEANUP)
         grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
     else
@@ -657,6 +659,7 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
     k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
     if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     if (h->obs_blocks > 0) {
         const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
         if (h->timing) cudaEventRecord(h->tev[0], s);
@@ -702,8 +705,34 @@ int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream)
     REQUIRE_GRID(h);
     if (reinterpret_cast<uintptr_t>(out_dev) & 3) return fail(h, SSD_EINVAL, "out_dev must be 4-byte aligned");
     const GridParams& p = h->gp;
-    global_view_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * p.map_bytes, (cudaStream_t)stream>>>(p, out_dev);
+    global_view_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * (p.map_bytes + round_up(p.H * p.W * 3, 4)), (cudaStream_t)stream>>>(p, out_dev, 0);
     return check_launch(h, "global_view");
+}
+
+// ---- render path (map_env.py:389-392,460-475) --------------------------------------------------------
+int ssd_record_beams(ssd_handle* h, int32_t enable)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    GridParams& p = h->gp;
+    if (!enable) { p.beam = nullptr; return SSD_OK; }
+    if (h->obs_blocks <= 0) return fail(h, SSD_EUNSUPPORTED, "record_beams: not available with the single-kernel step");
+    if (!h->d_beam) {
+        int rc = dev_zalloc(h, (size_t)p.E * p.map_bytes, &h->d_beam);
+        if (rc) return rc;
+    }
+    p.beam = h->d_beam;
+    return SSD_OK;
+}
+
+int ssd_render(ssd_handle* h, uint8_t* out_dev, void* stream)
+{
+    if (!h || !out_dev) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    if (reinterpret_cast<uintptr_t>(out_dev) & 3) return fail(h, SSD_EINVAL, "out_dev must be 4-byte aligned");
+    const GridParams& p = h->gp;
+    global_view_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * (p.map_bytes + round_up(p.H * p.W * 3, 4)), (cudaStream_t)stream>>>(p, out_dev, 1);
+    return check_launch(h, "render");
 }
 
 int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream)
@@ -716,7 +745,7 @@ int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride
     if (obs_env_stride < dense) return fail(h, SSD_EINVAL, "obs_env_stride %lld < %lld", (long long)obs_env_stride, (long long)dense);
     if ((reinterpret_cast<uintptr_t>(out_dev) | reinterpret_cast<uintptr_t>(obs_dev)) & 3)
         return fail(h, SSD_EINVAL, "obs_dev and out_dev must be 4-byte aligned");
-    concat_obs_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, VIEW_GROUP * (int)dense, (cudaStream_t)stream>>>(p, obs_dev, obs_env_stride, out_dev);
+    concat_obs_kernel<<<(p.E + VIEW_GROUP - 1) / VIEW_GROUP, VIEW_THREADS, 2 * VIEW_GROUP * (int)dense, (cudaStream_t)stream>>>(p, obs_dev, obs_env_stride, out_dev);
     return check_launch(h, "concat_obs");
 }
 

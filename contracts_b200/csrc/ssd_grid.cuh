@@ -94,6 +94,7 @@ struct GridParams {
     const uint8_t* waste_on;     // [n_waste + 1]
     const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
     uint8_t* state;
+    uint8_t* beam;               // optional [E][map_bytes]: beam_pos of the last step as a char overlay (render only)
 };
 
 // use_collective_reward / inequity_averse_reward (map_env.py:289-301): the shaped reward of agent a from the

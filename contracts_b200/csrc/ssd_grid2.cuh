@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t ray_mask(uint32_t lut, uint32_t c0, uint32_t
     return m * 2u + ((lut >> (c0 & 0x1Cu)) & 1u);
 }
 
-__device__ __forceinline__ int g2_fire(uint8_t* map, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN], const uint32_t* ags, int n,
+__device__ __forceinline__ int g2_fire(uint8_t* map, uint8_t* beam, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN], const uint32_t* ags, int n,
                                        uint32_t* res, bool clean, int H, int W, int Wp)
 {
     const int row = (int)(shooter & 255u), col = (int)((shooter >> 8) & 255u), ori = (int)((shooter >> 16) & 3u);
@@ -144,6 +144,11 @@ __device__ __forceinline__ int g2_fire(uint8_t* map, uint32_t shooter, const uin
         const int sh = b == 0 ? RAY_L : (b == 1 ? RAY_C : RAY_R);
         const uint32_t s5 = (stop >> sh) & 31u;
         const uint32_t f = (s5 & (0u - s5)) << sh;                            // the ray's first stopping cell (0: none)
+        if (beam) {                                                            // firing_points -> beam_pos (map_env.py:789,812)
+            const int cnt = f ? __ffs(f) - 1 - sh + ((f & ~wall) ? 1 : 0) : 5; // cells up to and including a non-wall stop
+            for (int i = 0; i < cnt; i++)
+                beam[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step] = clean ? (uint8_t)'C' : (uint8_t)'F';
+        }
         if (f & ~wall) {
             if (f & waste) {                                                   // CLEAN: H -> R (cleanup_new.py:285-290)
                 const int i = __ffs(f) - 1 - sh;
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const Grid
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(map, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
+            const int nup = g2_fire(map, p.beam ? p.beam + (size_t)env * p.map_bytes : nullptr, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }

@@ -16,7 +16,10 @@
 #define VIEW_THREADS 128
 #define VIEW_GROUP 4
 
-__global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridParams p, uint8_t* __restrict__ out)
+// full_map: 0 = global_view (agents from the first step on, no beams); 1 = MapEnv.full_map_to_colors (map_env.py:389-392,
+// the render() frame): agents always, then the beams of the last step on top (get_map_with_agents :354-375) when the
+// handle records them (GridParams::beam; 'F' (255, 255, 0), 'C' (100, 255, 255), DEFAULT_COLOURS map_env.py:40-41)
+__global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridParams p, uint8_t* __restrict__ out, const int full_map)
 {
     extern __shared__ __align__(16) uint8_t vsm[];            // VIEW_GROUP compact maps
     __shared__ uint32_t s_pal[16];
@@ -33,31 +36,43 @@ __global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridPar
         const uint8_t* hdr = p.state + (size_t)(env0 + threadIdx.x) * p.rec_stride + p.map_bytes;
         const uint32_t* ag = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS);
         // MapEnv.reset (map_env.py:306-342) never paints the agents into world_map_color: they appear from the first step on
-        const int na = *reinterpret_cast<const int*>(hdr + RO_T) > 0 ? p.n : 0;
+        const int na = (full_map || *reinterpret_cast<const int*>(hdr + RO_T) > 0) ? p.n : 0;
         for (int a = 0; a < na; a++) {
             const uint32_t v = ag[a];
             vsm[threadIdx.x * p.map_bytes + (int)(v & 255u) * p.Wp + (int)((v >> 8) & 255u)] = (uint8_t)PAINT_CODE(a);
         }
     }
     __syncthreads();
-    const int per_env = p.H * p.W * 3, total = G * per_env;
-    uint8_t* dst = out + (size_t)env0 * per_env;              // env0 % 4 == 0: word aligned
-    for (int w = threadIdx.x; 4 * w < total; w += VIEW_THREADS) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gb = 4 * w + k;
-            if (gb < total) {
-                const int g = gb / per_env, b = gb - g * per_env;
-                const int cell = b / 3, ch = b - 3 * cell;
-                const int r = cell / p.W, c = cell - r * p.W;
-                const uint32_t code = vsm[g * p.map_bytes + r * p.Wp + c] & CODE_MASK;
-                word |= ((s_pal[code >> 2] >> (8 * ch)) & 255u) << (8 * k);
-            }
+    if (full_map && p.beam) {                                 // beams overlay agents: palette slot 14 = 'F', agent 5's colour = 'C'
+        for (int i = threadIdx.x; i < G * p.map_bytes; i += VIEW_THREADS) {
+            const uint8_t bc = p.beam[(size_t)env0 * p.map_bytes + i];
+            if (bc) vsm[i] = bc == 'F' ? (uint8_t)(14 << 2) : (uint8_t)PAINT_CODE(5);
         }
-        if (4 * w + 3 < total) reinterpret_cast<uint32_t*>(dst)[w] = word;
-        else for (int k = 0; 4 * w + k < total; k++) dst[4 * w + k] = (uint8_t)(word >> (8 * k));
+        if (threadIdx.x == 0) s_pal[14] = 255u | (255u << 8);
+        __syncthreads();
     }
+    const int cells = p.H * p.W, per_env = cells * 3, total = G * per_env;
+    uint8_t* stage = vsm + VIEW_GROUP * p.map_bytes;          // the group's output bytes
+    for (int i = threadIdx.x; i < G * cells; i += VIEW_THREADS) {
+        const int g = i / cells, cell = i - g * cells;
+        const int r = cell / p.W, c = cell - r * p.W;
+        const uint32_t col = s_pal[(vsm[g * p.map_bytes + r * p.Wp + c] & CODE_MASK) >> 2];
+        uint8_t* o = stage + 3 * i;
+        o[0] = (uint8_t)col; o[1] = (uint8_t)(col >> 8); o[2] = (uint8_t)(col >> 16);
+    }
+    __syncthreads();
+    uint8_t* dst = out + (size_t)env0 * per_env;              // env0 % 4 == 0: word aligned
+    for (int w = threadIdx.x; 4 * w + 3 < total; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(stage)[w];
+    for (int k = (total & ~3) + threadIdx.x; k < total; k += VIEW_THREADS) dst[k] = stage[k];
+}
+
+// MapEnv.reset: self.beam_pos = [] (map_env.py:316) for the envs being reset; one warp per env
+__global__ void beam_clear_kernel(const GridParams p, const uint8_t* __restrict__ mask)
+{
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (env >= p.E || (mask && !mask[env])) return;
+    uint4* b = reinterpret_cast<uint4*>(p.beam + (size_t)env * p.map_bytes);
+    for (int i = lane; i < (p.map_bytes >> 4); i += 32) b[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __global__ void __launch_bounds__(VIEW_THREADS) concat_obs_kernel(const GridParams p, const uint8_t* __restrict__ obs,
@@ -79,23 +94,20 @@ __global__ void __launch_bounds__(VIEW_THREADS) concat_obs_kernel(const GridPara
         }
     }
     __syncthreads();
-    uint8_t* dst = out + (size_t)env0 * per_env;
+    uint8_t* stage = vsm + VIEW_GROUP * per_env;              // the group's output bytes
     const int n3 = 3 * n;
-    for (int w = threadIdx.x; 4 * w < total; w += VIEW_THREADS) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gb = 4 * w + k;
-            if (gb < total) {
-                const int g = gb / per_env, q = gb - g * per_env;         // q = pixel * 3 n + 3 a + ch
-                const int pix = q / n3, ach = q - pix * n3;
-                const int a = ach / 3, ch = ach - 3 * a;
-                word |= (uint32_t)vsm[g * per_env + a * SSD_OBS_BYTES + pix * 3 + ch] << (8 * k);
-            }
+    for (int i = threadIdx.x; i < G * SSD_OBS_PIX; i += VIEW_THREADS) {
+        const int g = i / SSD_OBS_PIX, pix = i - g * SSD_OBS_PIX;
+        const uint8_t* src = vsm + g * per_env + pix * 3;
+        uint8_t* o = stage + g * per_env + pix * n3;
+        for (int a = 0; a < n; a++) {                         // out[pix][3 a + ch] = in[a][pix][ch]
+            o[3 * a] = src[a * SSD_OBS_BYTES]; o[3 * a + 1] = src[a * SSD_OBS_BYTES + 1]; o[3 * a + 2] = src[a * SSD_OBS_BYTES + 2];
         }
-        if (4 * w + 3 < total) reinterpret_cast<uint32_t*>(dst)[w] = word;
-        else for (int k = 0; 4 * w + k < total; k++) dst[4 * w + k] = (uint8_t)(word >> (8 * k));
     }
+    __syncthreads();
+    uint8_t* dst = out + (size_t)env0 * per_env;
+    for (int w = threadIdx.x; 4 * w + 3 < total; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(stage)[w];
+    for (int k = (total & ~3) + threadIdx.x; k < total; k += VIEW_THREADS) dst[k] = stage[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,10 +219,19 @@ __global__ void __launch_bounds__(VIEW_THREADS) policy_inputs_kernel(const GridP
         for (int b = threadIdx.x; b < per_env; b += VIEW_THREADS) vsm[b] = src[b];
     __syncthreads();
     T* dst = image + (size_t)env * per_env;
-    for (int o = threadIdx.x; o < per_env; o += VIEW_THREADS) {          // o = a * 675 + c * 225 + pixel
+    auto value = [&](int o) {                                            // o = a * 675 + c * 225 + pixel
         const int a = o / SSD_OBS_BYTES, r = o - a * SSD_OBS_BYTES;
         const int c = r / SSD_OBS_PIX, pix = r - c * SSD_OBS_PIX;
-        dst[o] = policy_cast<T>(lut[vsm[a * SSD_OBS_BYTES + pix * 3 + c]]);
+        return policy_cast<T>(lut[vsm[a * SSD_OBS_BYTES + pix * 3 + c]]);
+    };
+    if (sizeof(T) == 2 && (per_env & 1) == 0) {                          // 16-bit outputs leave two at a time
+        struct __align__(4) Pair { T x, y; };
+        for (int o = 2 * threadIdx.x; o < per_env; o += 2 * VIEW_THREADS) {
+            Pair v; v.x = value(o); v.y = value(o + 1);
+            *reinterpret_cast<Pair*>(dst + o) = v;
+        }
+    } else {
+        for (int o = threadIdx.x; o < per_env; o += VIEW_THREADS) dst[o] = value(o);
     }
     if (contract && threadIdx.x < n * 10) {
         const double theta = *reinterpret_cast<const double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA);

@@ -9,7 +9,7 @@ Differences from the reference that a caller can observe:
   * randomness is a counter-based Philox stream keyed (seed, env_id) instead of the process-global
     NumPy / stdlib generators (kwargs `seed`, `env_id`); given the same draws the results are
     bit-identical (tests/test_dropin_api.py replays the reference's golden vectors through this API);
-  * beams are not drawn by `render()` (the reference paints them only into the rendered full map).
+  * `render(mode="human")` does not open a matplotlib window: every mode returns the RGB frame.
 
 `use_collective_reward` / `inequity_averse_reward` (+ `alpha`, `beta`; map_env.py:289-301) run on the
 device (fused into the reward write).  `return_agent_actions` is accepted and has, as in the reference,
@@ -20,16 +20,9 @@ MapEnv observation dict (cleanup_new.py:204,258; harvest_new.py:171,230), so `ot
 import numpy as np
 import torch
 
-from .. import spaces
+from .. import _lib, spaces
 from ..batched import BatchedGridEnv
 from ..maps import CLEANUP_MAP, HARVEST_MAP
-
-# DEFAULT_COLOURS / CLEANUP_COLORS (map_env.py:24-42, cleanup_new.py:42-47) for render()
-_RENDER_COLOURS = {ord(" "): (0, 0, 0), ord("@"): (180, 180, 180), ord("A"): (0, 255, 0), ord("H"): (99, 156, 194),
-                   ord("R"): (113, 75, 24), ord("S"): (113, 75, 24)}
-_AGENT_COLOURS = [(0, 0, 255), (2, 81, 154), (204, 0, 204), (216, 30, 54), (254, 151, 0), (100, 255, 255),
-                  (99, 99, 255), (250, 204, 255), (238, 223, 16)]
-
 
 class _GridWorldEnv:
     KIND = None
@@ -88,6 +81,10 @@ class _GridWorldEnv:
                                          use_collective_reward=self.use_collective_reward,
                                          inequity_averse_reward=self.inequity_averse_reward,
                                          alpha=self.alpha, beta=self.beta)
+            try:                     # render() shows the beams of the last step (MapEnv.beam_pos); cheap at dict-API batch sizes
+                self._batch.record_beams(True)
+            except _lib.SsdError:    # the single-kernel fallback (maps > 1 KB) does not record them
+                pass
         return self._batch
 
     def _bind_contract(self, name, low, high, null_prob):
@@ -183,15 +180,9 @@ class _GridWorldEnv:
 
     # ---- rendering ---------------------------------------------------------------------------------------------
     def full_map_to_colors(self):
-        """RGB image of the whole map with agents (map_env.py:389-392); beams are not retained."""
-        st = self.batch.get_state()
-        chars = st["map"][0].cpu().numpy()
-        rgb = np.zeros(chars.shape + (3,), dtype=int)
-        for ch, col in _RENDER_COLOURS.items():
-            rgb[chars == ch] = col
-        for i, (r, c) in enumerate(st["pos"][0].cpu().numpy()):
-            rgb[r, c] = _AGENT_COLOURS[i]
-        return rgb
+        """RGB image of the whole map with the agents and the beams of the last step (map_env.py:354-375,389-392),
+        written by the device (`ssd_render`)."""
+        return self.batch.render()[0].cpu().numpy().astype(int)
 
     def global_view(self):
         """world_map_color without its padding (map_env.py:394-395), written by the device (`ssd_global_view`).  Unlike

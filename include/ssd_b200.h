@@ -139,6 +139,14 @@ int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream);
  * 604-609): obs_dev uint8 [E][n][15][15][3] (env stride obs_env_stride, 0 = dense) -> out_dev uint8 [E][15][15][3n]. */
 int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream);
 
+/* --- render path (environments/map_env.py:389-392,460-475) --------------------------------------------- */
+/* MapEnv.beam_pos (map_env.py:231,812) is only ever shown by render(): recording it is optional.  When enabled, every
+ * step also stores the cells its beams crossed (library-owned overlay, cleared at each step / reset). */
+int ssd_record_beams(ssd_handle* h, int32_t enable);
+/* MapEnv.full_map_to_colors() = render(mode='rgb_array') (map_env.py:389-392): the map with the agents and, when recorded,
+ * the beams of the last step on top (get_map_with_agents, map_env.py:354-375).  out_dev uint8 [E][H][W][3]. */
+int ssd_render(ssd_handle* h, uint8_t* out_dev, void* stream);
+
 /* --- policy-side consumer (environments/Networks/vision_net.py:150-181) --------------------------------- */
 #define SSD_POLICY_F32 0
 #define SSD_POLICY_F16 1

@@ -339,12 +339,43 @@ def run_joint(name):
     return out
 
 
+# render(mode='rgb_array') = full_map_to_colors (map_env.py:389-392,460-475): agents + the beams of the last step.
+# name -> (kind, n, seed, env_id, map, horizon, episodes, steps, action probabilities)
+RENDER_SCENARIOS = {
+    "render_cleanup_n6": ("cleanup", 6, 81, 51, None, 30, 2, 30, [.1, .1, .1, .1, .05, .1, .1, .2, .15]),
+    "render_harvest_n5": ("harvest", 5, 82, 52, None, 1000, 1, 40, [.12, .12, .12, .12, .06, .1, .1, .26]),
+    "render_cleanup_cramped_n8": ("cleanup", 8, 83, 53, CRAMPED_CLEANUP, 1000, 1, 40, [.1, .1, .1, .1, .05, .1, .1, .2, .15]),
+    "render_cleanup_open_n6": ("cleanup", 6, 84, 54, OPEN_CLEANUP, 1000, 1, 40, [.1, .1, .1, .1, .05, .1, .1, .2, .15]),
+}
+
+
+def run_render(name):
+    from .ref_harness import RefGridEnv
+    kind, n, seed, env_id, amap, horizon, episodes, steps, act_p = RENDER_SCENARIOS[name]
+    ref = RefGridEnv(kind, n, seed, env_id, contract=False, ascii_map=amap, horizon=horizon, disable_firing=False)
+    ascii_map = amap if amap is not None else ["".join(ch.decode() for ch in row) for row in ref.base.base_map]
+    rng = np.random.RandomState(sum(map(ord, name)))
+    frames, resets, actions = [], [], []
+    for ep in range(episodes):
+        ref.reset()
+        resets.append(np.asarray(ref.base.render(mode="rgb_array"), dtype=np.uint8))
+        frames.append([])
+        actions.append([])
+        for t in range(steps):
+            a = rng.choice(len(act_p), size=n, p=act_p).astype(np.int32)
+            ref.step(a)
+            actions[-1].append(a)
+            frames[-1].append(np.asarray(ref.base.render(mode="rgb_array"), dtype=np.uint8))
+    return {"kind": kind, "n": n, "seed": seed, "env_id": env_id, "horizon": horizon, "ascii_map": np.array(ascii_map),
+            "actions": np.array(actions), "obs": np.array(frames), "reset_obs": np.array(resets)}
+
+
 def main(names=None):
     os.makedirs(OUT, exist_ok=True)
     for name in (names or list(SCENARIOS) + list(NEGOTIATE_SCENARIOS) + list(FLATOBS_SCENARIOS) + list(SELFDRIVE_SCENARIOS)
-                 + list(FEATURES_SCENARIOS) + list(SOLVER_SCENARIOS) + list(JOINT_SCENARIOS)):
-        if name in SOLVER_SCENARIOS or name in JOINT_SCENARIOS:
-            data = run_solver(name) if name in SOLVER_SCENARIOS else run_joint(name)
+                 + list(FEATURES_SCENARIOS) + list(SOLVER_SCENARIOS) + list(JOINT_SCENARIOS) + list(RENDER_SCENARIOS)):
+        if name in SOLVER_SCENARIOS or name in JOINT_SCENARIOS or name in RENDER_SCENARIOS:
+            data = run_solver(name) if name in SOLVER_SCENARIOS else (run_joint(name) if name in JOINT_SCENARIOS else run_render(name))
             path = os.path.join(OUT, name + ".npz")
             np.savez_compressed(path, **data)
             print("%-32s %7.1f KiB  obs=%s %s" % (name, os.path.getsize(path) / 1024, data["obs"].shape,

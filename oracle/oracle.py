@@ -52,6 +52,7 @@ def lib():
         L.oracle_negotiate.argtypes = [vp, vp, vp, vp]
         L.oracle_set_reward_shaping.argtypes = [vp, i32, f64, f64]
         L.oracle_global_view.argtypes = [vp, vp]
+        L.oracle_render.argtypes = [vp, vp]
         L.feat_oracle_create.restype = vp
         L.feat_oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
         L.feat_oracle_destroy.argtypes = [vp]
@@ -167,6 +168,12 @@ class GridOracle:
         """MapEnv.global_view() (map_env.py:394-395) of every env: uint8 [E, H, W, 3]."""
         out = np.zeros((self.E, self.H, self.W, 3), np.uint8)
         lib().oracle_global_view(self._h, _p(out))
+        return out
+
+    def render(self):
+        """MapEnv.full_map_to_colors() (map_env.py:389-392) of every env, beams of the last step included: uint8 [E, H, W, 3]."""
+        out = np.zeros((self.E, self.H, self.W, 3), np.uint8)
+        lib().oracle_render(self._h, _p(out))
         return out
 
     def set_theta(self, theta):

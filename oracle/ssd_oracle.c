@@ -79,6 +79,7 @@ typedef struct {
     pt cur_apples[MAXPTS]; int n_cur_apples;       /* current_apple_points (stale by one step) */
     pt cur_wastes[MAXPTS]; int n_cur_wastes;
     double theta;
+    char beam[MAXH][MAXW];                          /* beam_pos of the last step as an overlay (0 = none; later entries win) */
     /* metrics accumulators (cleanup_new.py:186-189, harvest_new.py:152-156, two_stage_train.py:92-99) */
     double m_apples, m_low_density, m_raw, m_transfers, m_dirt;
     double m_agent_a[MAXN], m_agent_b[MAXN];       /* waste_cleaned | apples_consumed, close_apples_consumed */
@@ -374,6 +375,7 @@ static int update_map_fire(env_t* e, int shooter, char fire_char, int clean, pt*
         for (int i = 0; i < 5; i++) {           /* fire_len = all_actions["FIRE"] = 5 (cleanup_new.py:39,277,285) */
             if (next.r >= 0 && next.r < e->H && next.c >= 0 && next.c < e->W &&
                 e->world_map[next.r][next.c] != '@') {
+                e->beam[next.r][next.c] = fire_char;                     /* firing_points -> beam_pos (:789,812) */
                 if (clean && e->world_map[next.r][next.c] == 'H') { updates[n_up].r = next.r; updates[n_up].c = next.c; n_up++; }
                 if (in_agent_pos(e, next.r, next.c)) {
                     int hit = agent_by_pos_lookup(abp, n, next.r, next.c);
@@ -549,6 +551,7 @@ static void env_reset(env_t* e, uint32_t episode)
 {
     e->episode = episode;
     e->timesteps = 0;
+    memset(e->beam, 0, sizeof(e->beam));                     /* self.beam_pos = [] (map_env.py:316) */
     setup_agents(e);
     /* reset_map (map_env.py:710-719) */
     for (int r = 0; r < e->H; r++) for (int c = 0; c < e->W; c++) e->world_map[r][c] = ' ';
@@ -624,6 +627,7 @@ static void env_step(env_t* e, const int32_t* actions, step_out* o, int want_fea
     int n = e->n;
     int acls[MAXN]; pt avec[MAXN];
     e->timesteps += 1;                                       /* map_env.py:230 */
+    memset(e->beam, 0, sizeof(e->beam));                     /* self.beam_pos = [] (:231) */
     for (int i = 0; i < n; i++) {
         avec[i].r = avec[i].c = 0;
         acls[i] = action_class(e, actions[i], &avec[i]);
@@ -899,6 +903,21 @@ void oracle_global_view(void* h, uint8_t* out)
         for (int r = 0; r < b->H; r++)
             for (int c = 0; c < b->W; c++)
                 memcpy(o + ((size_t)r * b->W + c) * 3, e->color[r + VIEW][c + VIEW], 3);
+    }
+}
+/* MapEnv.full_map_to_colors() (map_env.py:389-392) = render(mode != 'human'): the char grid with agent ids, then the
+ * beams of the last step on top (get_map_with_agents :354-375), through the colour map.  uint8 [E][H][W][3]. */
+void oracle_render(void* h, uint8_t* out)
+{
+    batch_t* b = (batch_t*)h;
+    for (int i = 0; i < b->E; i++) {
+        env_t* e = &b->envs[i];
+        uint8_t* o = out + (size_t)i * b->H * b->W * 3;
+        for (int r = 0; r < b->H; r++)
+            for (int c = 0; c < b->W; c++) color_of(e->world_map[r][c], o + ((size_t)r * b->W + c) * 3);
+        for (int a = 0; a < e->n; a++) color_of((char)('1' + a), o + ((size_t)e->pos[a].r * b->W + e->pos[a].c) * 3);
+        for (int r = 0; r < b->H; r++)
+            for (int c = 0; c < b->W; c++) if (e->beam[r][c]) color_of(e->beam[r][c], o + ((size_t)r * b->W + c) * 3);
     }
 }
 int oracle_feature_dim(void* h) { return ((batch_t*)h)->F; }

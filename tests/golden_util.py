@@ -15,7 +15,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-OTHER_SCHEMAS = ("negotiate_", "selfdrive_", "features_", "flatobs_", "solver_", "joint_")
+OTHER_SCHEMAS = ("negotiate_", "selfdrive_", "features_", "flatobs_", "solver_", "joint_", "render_")
 
 
 def fixture_names(prefix=None):

@@ -189,3 +189,54 @@ def test_policy_inputs_match_vision_net_preprocessing(kind, n, E, padded):
         assert torch.equal(img.cpu(), want.to(dt)), dt
         assert torch.equal(con.cpu(), wc.to(dt)), dt
     assert torch.equal(env.policy_inputs(torch.float32, with_contract=False).cpu(), want)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("render_"))
+def test_render_with_beams_matches_reference(name):
+    """full_map_to_colors incl. the beams of the last step (map_env.py:354-375,389-392): batched path and dict API."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.utils.env_creator_functions import env_creator
+    fx = gu.load(name)
+    kind, n, i = str(fx["kind"]), int(fx["n"]), 1
+    amap = [str(r) for r in fx["ascii_map"]]
+    env = BatchedGridEnv(kind + "_new", 6, n, amap, horizon=int(fx["horizon"]), seed=int(fx["seed"]),
+                         first_env_id=(int(fx["env_id"]) - i) & 0xFFFFFFFF)
+    env.record_beams()
+    dropin = env_creator("CleanupNew" if kind == "cleanup" else "HarvestNew",
+                         dict(num_agents=n, env_params={}, ascii_map=amap, horizon=int(fx["horizon"]), disable_firing=False,
+                              seed=int(fx["seed"]), env_id=int(fx["env_id"])))
+    keys = ["a%d" % k for k in range(n)]
+    for ep in range(fx["actions"].shape[0]):
+        env.reset()
+        dropin.reset()
+        gu.assert_same("reset frame", env.render()[i].cpu().numpy(), fx["reset_obs"][ep], "ep %d" % ep)
+        gu.assert_same("reset frame (dict API)", dropin.render(mode="rgb_array"), fx["reset_obs"][ep], "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            a = torch.as_tensor(np.broadcast_to(fx["actions"][ep, t].astype(np.uint8), (env.E, n)).copy()).cuda()
+            env.step(a)
+            dropin.step({k: int(fx["actions"][ep, t][j]) for j, k in enumerate(keys)})
+            gu.assert_same("frame", env.render()[i].cpu().numpy(), fx["obs"][ep, t], "ep %d step %d" % (ep, t))
+            gu.assert_same("frame (dict API)", dropin.full_map_to_colors(), fx["obs"][ep, t], "ep %d step %d" % (ep, t))
+
+
+def test_render_matches_oracle_masked_reset(oracle_lib):
+    """Beam overlays across a larger batch, cleared per env by masked resets."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.maps import CLEANUP_MAP
+    E, n = 131, 8
+    orc = oracle_lib.GridOracle("cleanup", E, n, CLEANUP_MAP, horizon=15, seed=5, first_env_id=2)
+    env = BatchedGridEnv("cleanup_new", E, n, CLEANUP_MAP, horizon=15, seed=5, first_env_id=2)
+    env.record_beams()
+    rng = np.random.RandomState(3)
+    orc.reset(); env.reset()
+    for t in range(40):
+        a = rng.choice(9, size=(E, n), p=[.1, .1, .1, .1, .05, .1, .1, .2, .15])
+        o = orc.step(a, want_features=False)
+        env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        gu.assert_same("frame", env.render().cpu().numpy(), orc.render(), "t %d" % t)
+        if o["done"].any():
+            mask = o["done"].copy(); mask[::2] = 0
+            orc.reset(mask); env.reset(torch.as_tensor(mask).cuda())
+            gu.assert_same("frame after masked reset", env.render().cpu().numpy(), orc.render(), "t %d" % t)

@@ -64,3 +64,20 @@ def test_oracle_joint_layouts_match_reference(oracle_lib, name):
             for a in range(n):                    # sum([env_infos[agent]['feature_obs'] ...]) (:594-595)
                 feat = feat + o["feature_obs"][0, a]
             gu.assert_same("feature_obs", feat, fx["feature_obs"][ep, t], ctx)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names("render_"))
+def test_oracle_render_matches_reference(oracle_lib, name):
+    """full_map_to_colors incl. the beams of the last step (map_env.py:354-375,389-392)."""
+    fx = gu.load(name)
+    orc = oracle_lib.GridOracle(str(fx["kind"]), 1, int(fx["n"]), [str(r) for r in fx["ascii_map"]], horizon=int(fx["horizon"]),
+                                seed=int(fx["seed"]), first_env_id=int(fx["env_id"]))
+    beams = 0
+    for ep in range(fx["actions"].shape[0]):
+        orc.reset()
+        gu.assert_same("reset frame", orc.render()[0], fx["reset_obs"][ep], "ep %d" % ep)
+        for t in range(fx["actions"].shape[1]):
+            orc.step(fx["actions"][ep, t][None], want_features=False)
+            gu.assert_same("frame", orc.render()[0], fx["obs"][ep, t], "ep %d step %d" % (ep, t))
+            beams += int(((fx["obs"][ep, t] == (255, 255, 0)).all(-1) | (fx["obs"][ep, t] == (100, 255, 255)).all(-1)).sum())
+    assert beams > 20, "fixture shows no beams"

@@ -74,6 +74,39 @@ def run(name, env, n, nact, alg_bytes, steps, selfdrive=False, horizon=1000):
     return line
 
 
+def run_views(E=131072, n=8, reps=20):
+    """JointEnv output layouts and the policy-side consumer (ssd_views.cuh): HBM GB/s of each kernel at the headline
+    batch size (inputs and outputs exceed the L2, so every launch streams from / to HBM)."""
+    from contracts_b200.batched import BatchedGridEnv
+    env = BatchedGridEnv("cleanup_new", E, n, contract="CleanupContract")
+    env.reset()
+    for i in range(5):
+        env.step(env.random_actions(i, 8), extras=False)
+    gv = torch.empty((E, env.H, env.W, 3), dtype=torch.uint8, device=env.device)
+    cc = torch.empty((E, 15, 15, 3 * n), dtype=torch.uint8, device=env.device)
+    cases = [("global_view_kernel (JointEnv global_obs)", lambda: env.global_view(gv), env.state_map_bytes + 32 + env.H * env.W * 3),
+             ("concat_obs_kernel (JointEnv concatenated_obs)", lambda: env.concatenated_obs(cc), 2 * n * 675)]
+    for dt, size in ((torch.float32, 4), (torch.bfloat16, 2)):
+        img = torch.empty((E * n, 3, 15, 15), dtype=dt, device=env.device)
+        con = torch.empty((E * n, 10), dtype=dt, device=env.device)
+        cases.append(("policy_inputs_kernel %s (VisionNetwork preprocessing)" % str(dt).split(".")[1],
+                      lambda img=img, con=con, dt=dt: env.policy_inputs(dt, image=img, contract=con), n * 675 * (1 + size) + n * 10 * size + 8))
+    for name, fn, bytes_per_env in cases:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = bytes_per_env * E / (ms * 1e-3) / 1e9
+        print(json.dumps({"kernel": name, "envs": E, "agents": n, "kernel_ms": ms, "alg_bytes_per_env": bytes_per_env,
+                          "achieved_GBps": gbs, "hbm_peak_GBps": peak(), "frac_of_measured_hbm": gbs / peak()}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=300)
@@ -82,6 +115,7 @@ def main():
     from contracts_b200.features import BatchedFeatureEnv
     from contracts_b200.selfdrive import BatchedCarEnv
     K = args.steps
+    run_views()
     # algorithmic bytes per agent-step: observation + state read/write + rewards/actions/infos
     run("harvest_new n=4 E=16384 HarvestFeaturemodLocalContract", BatchedGridEnv("harvest_new", 16384, 4, contract="HarvestFeaturemodLocalContract"),
         4, 7, (2700 + 2 * 1008 + 4 * (1 + 8 + 4) + 1) / 4, K)
