@@ -198,14 +198,17 @@ def main():
 
     state = {"t": 0, "global_step": 0, "stats": None}
 
-    def one_step(device_actions=True, host_actions=None):
+    def one_step(device_actions=True, host_actions=None, host_out=None):
         if state["t"] == 0:
             new_episode()
         if device_actions:
             env.random_actions(state["global_step"], N_ACTIONS, out=actions)
+            env.step(actions, extras=False)
+        elif host_out is not None:      # the C ABI's host-buffer step: H2D actions, step, D2H rewards + dones, synchronous
+            env.step_host(host_actions, host_out[0], host_out[1])
         else:
             actions.copy_(host_actions, non_blocking=True)
-        env.step(actions, extras=False)
+            env.step(actions, extras=False)
         state["t"] += 1
         state["global_step"] += 1
         if state["t"] == HORIZON:
@@ -339,16 +342,13 @@ def main():
     host_rew = torch.empty((E, n), dtype=torch.float64).pin_memory()
     host_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
     for i in range(3):
-        one_step(False, host_actions[i % 4])
+        one_step(False, host_actions[i % 4], (host_rew, host_done))
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
-        one_step(False, host_actions[i % 4])
-        host_rew.copy_(env.rew, non_blocking=True)
-        host_done.copy_(env.done, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        one_step(False, host_actions[i % 4], (host_rew, host_done))     # returns with host_rew / host_done valid
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -387,7 +387,7 @@ def main():
                        "cuda_graph_steps": G},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * n,
                     "d2h_bytes_per_step": E * n * 8 + E, "steps": Ke,
-                    "note": "pinned host actions in, rewards+dones out, host sync every step; observations stay in the device batch tensor"},
+                    "note": "ssd_step_host: pinned host actions in, rewards+dones out, synchronous every step (the D2H copy overlaps the observe kernel); observations stay in the device batch tensor"},
             "e2e_obs_to_host": {"value": obs_to_host, "unit": "agent-steps/s", "d2h_bytes_per_step": E * n * 675 + E * n * 8},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -59,7 +59,7 @@ EXPORTS = [
     "ssd_random_actions", "ssd_philox4x32_10", "ssd_feature_dim", "ssd_state_bytes_per_env",
     "ssd_kernel_launches", "ssd_enable_timing", "ssd_get_step_times", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
     "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
-    "ssd_global_view", "ssd_concat_obs", "ssd_solver_sample", "ssd_solver_choose", "ssd_policy_inputs", "ssd_record_beams", "ssd_render",
+    "ssd_global_view", "ssd_concat_obs", "ssd_solver_sample", "ssd_solver_choose", "ssd_policy_inputs", "ssd_record_beams", "ssd_render", "ssd_step_host",
 ]
 
 _LIB = None
@@ -102,6 +102,7 @@ def load():
     L.ssd_global_view.argtypes = [vp, vp, vp]
     L.ssd_concat_obs.argtypes = [vp, vp, i64, vp, vp]
     L.ssd_solver_sample.argtypes = [vp, i32, vp, vp]
+    L.ssd_step_host.argtypes = [vp, ctypes.POINTER(ssd_step_io), vp, vp, vp, vp]
     L.ssd_record_beams.argtypes = [vp, i32]
     L.ssd_render.argtypes = [vp, vp, vp]
     L.ssd_policy_inputs.argtypes = [vp, vp, i64, i32, vp, vp, vp]

@@ -110,6 +110,7 @@ class BatchedGridEnv:
         self.info = torch.zeros((E, n, 4), dtype=torch.uint8, device=dev)
         self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
         self.feature_obs = None
+        self._host_actions_dev = None
         self._io = _lib.ssd_step_io()
 
     # ------------------------------------------------------------------------------------------
@@ -155,6 +156,33 @@ class BatchedGridEnv:
         io.done_dev = self.done.data_ptr()
         _lib.check(self._h, self.lib.ssd_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
+
+    def step_host(self, actions_host, rew_host, done_host=None, want_features=False):
+        """One step for a caller holding HOST tensors (pinned for asynchronous copies): uint8 actions [E, n] in,
+        float64 rewards [E, n] (and uint8 dones [E]) out, valid on return.  The rewards travel back while the
+        observe kernel still runs; the observations stay on the device in `self.obs`."""
+        for t, dt in ((actions_host, torch.uint8), (rew_host, torch.float64)) + (((done_host, torch.uint8),) if done_host is not None else ()):
+            if t.device.type != "cpu" or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("step_host needs contiguous CPU tensors: uint8 actions, float64 rewards, uint8 dones")
+        if self._host_actions_dev is None:
+            self._host_actions_dev = torch.empty((self.E, self.n), dtype=torch.uint8, device=self.device)
+        if want_features and self.feature_obs is None:
+            self.feature_obs = torch.zeros((self.E, self.n, self.F), dtype=torch.float64, device=self.device)
+        io = self._io
+        io.actions_dev = self._host_actions_dev.data_ptr()
+        io.obs_dev = self._obs_buf.data_ptr()
+        io.obs_env_stride = self.obs_stride
+        io.rew_dev = self.rew.data_ptr()
+        io.base_rew_dev = None
+        io.transfers_dev = None
+        io.info_dev = self.info.data_ptr()
+        io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
+        io.done_dev = self.done.data_ptr()
+        _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                   ctypes.c_void_p(rew_host.data_ptr()),
+                                                   ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
+                                                   self._stream()))
+        return self.obs, rew_host, done_host
 
     def random_actions(self, step_index, num_actions, out=None):
         """Uniform random actions; step_index=None uses the handle's device-side counter (CUDA-graph friendly)."""

@@ -37,6 +37,8 @@ struct ssd_handle {
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
     uint8_t* d_beam;         // ssd_record_beams: [E][map_bytes] beam overlay of the last step
+    cudaStream_t side;       // ssd_step_host: copy stream + its events (created on first use)
+    cudaEvent_t ev_rew, ev_copied;
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
@@ -608,6 +610,7 @@ void ssd_destroy(ssd_handle* h)
     cudaSetDevice(h->cfg.device);
     for (void* d : h->dev_allocs) cudaFree(d);
     for (int i = 0; i < 3; i++) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+    if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_rew); cudaEventDestroy(h->ev_copied); }
     delete h;
 }
 
@@ -644,13 +647,10 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
     return check_launch(h, "reset");
 }
 
-int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
+static int make_step_io(ssd_handle* h, const ssd_step_io* io, StepIO& k)
 {
-    if (!h || !io) return SSD_EINVAL;
-    REQUIRE_GRID(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     const GridParams& p = h->gp;
-    StepIO k;
     k.actions = (const uint8_t*)io->actions_dev;
     k.obs = io->obs_dev;
     k.obs_stride = io->obs_env_stride ? io->obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
@@ -658,7 +658,28 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
     k.rew = io->rew_dev; k.base_rew = io->base_rew_dev; k.transfers = io->transfers_dev;
     k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
     if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
+    return SSD_OK;
+}
+
+// ssd_step_host: rewards / dones go back to the host on the side stream as soon as the kernels producing them are enqueued
+struct HostCopy { double* rew_host; uint8_t* done_host; };
+static int copy_rewards(ssd_handle* h, const StepIO& k, cudaStream_t s, const HostCopy* hc)
+{
+    if (!hc) return SSD_OK;
+    const size_t na = (size_t)h->gp.E * h->gp.n;
+    CUDA_TRY(h, cudaEventRecord(h->ev_rew, s));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_rew, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(hc->rew_host, k.rew, na * sizeof(double), cudaMemcpyDeviceToHost, h->side));
+    if (hc->done_host) CUDA_TRY(h, cudaMemcpyAsync(hc->done_host, k.done, (size_t)h->gp.E, cudaMemcpyDeviceToHost, h->side));
+    CUDA_TRY(h, cudaEventRecord(h->ev_copied, h->side));
+    return SSD_OK;
+}
+
+// the kernels of one step on stream s.  The rewards / dones are final after the logic kernel for cleanup — BEFORE the
+// observe kernel — and after the reward kernel for harvest.
+static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const HostCopy* hc)
+{
+    const GridParams& p = h->gp;
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     if (h->obs_blocks > 0) {
         const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
@@ -667,12 +688,56 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
         else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         h->launches++;
         if (h->timing) cudaEventRecord(h->tev[1], s);
+        if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
         obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, h->obs_vpl)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
-        if (p.kind == SSD_ENV_HARVEST) { h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res); }
+        if (p.kind == SSD_ENV_HARVEST) {
+            h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
+            int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
+        }
         if (h->timing) cudaEventRecord(h->tev[2], s);
-    } else
+    } else {
         step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+        int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
+    }
     return check_launch(h, "step");
+}
+
+int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
+{
+    if (!h || !io) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    StepIO k;
+    int rc = make_step_io(h, io, k);
+    if (rc) return rc;
+    return launch_step(h, k, (cudaStream_t)stream, nullptr);
+}
+
+// One step with HOST buffers (what a CPU-side rollout worker holds): actions_host -> device, the step, rewards / dones ->
+// host; returns when the host outputs are valid.  The device -> host copy runs on a library-owned side stream as soon as
+// the rewards exist, so for cleanup it overlaps the observe kernel (observations stay in the device batch tensor).
+int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host, double* rew_host, uint8_t* done_host, void* stream)
+{
+    if (!h || !io || !actions_host || !rew_host) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    StepIO k;
+    int rc = make_step_io(h, io, k);
+    if (rc) return rc;
+    if (done_host && !k.done) return fail(h, SSD_EINVAL, "step_host: done_host needs io->done_dev");
+    const GridParams& p = h->gp;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->side) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_rew, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    }
+    const size_t na = (size_t)p.E * p.n;
+    CUDA_TRY(h, cudaMemcpyAsync(const_cast<uint8_t*>(k.actions), actions_host, na, cudaMemcpyHostToDevice, s));
+    const HostCopy hc = { rew_host, done_host };
+    rc = launch_step(h, k, s, &hc);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_copied));
+    return SSD_OK;
 }
 
 #define SMALL_LAUNCH(kernel, ...)                                                         \

@@ -119,6 +119,13 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
 /* MapEnv.step (map_env.py:216-304) + env step tail (cleanup_new.py:211-267 / harvest_new.py:181-239)
  * + SeparateContractEnv.step reward redistribution (two_stage_train.py:62-121), one launch for E envs. */
 int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream);
+/* The same step for a caller that holds HOST buffers (a CPU rollout worker, RLlib's sampler): copies
+ * actions_host (uint8 [E][n], pinned for asynchronous copies) into io->actions_dev, steps, copies the rewards
+ * (double [E][n], after transfers) and dones (uint8 [E], nullable) back, and returns when they are valid.  The device ->
+ * host copy starts as soon as the rewards exist — for cleanup_new that is before the observe kernel, so it overlaps
+ * it; the observations stay in the device batch tensor io->obs_dev. */
+int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host, double* rew_host, uint8_t* done_host,
+                  void* stream);
 
 /* --- contract parameters / negotiation ----------------------------------------------------------- */
 /* theta_dev: double [E].  What SeparateContractNegotiateStage does with a0's proposal

@@ -70,3 +70,26 @@ def test_full_size_rollout_properties(oracle_lib, kind, E, n, nact, contract):
     st2 = clone.get_state()
     for k in ("map", "pos", "ori", "t", "theta"):
         assert torch.equal(st[k], st2[k]), k
+
+
+def test_step_host_equals_step():
+    """ssd_step_host (host buffers, overlapped D2H copy) produces exactly what ssd_step + explicit copies produce."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    for kind, contract, nact in (("cleanup_new", "CleanupContract", 8), ("harvest_new", "HarvestFeaturemodLocalContract", 8)):
+        E, n = 300, 5
+        a = BatchedGridEnv(kind, E, n, contract=contract, seed=12, first_env_id=40, horizon=25)
+        b = BatchedGridEnv(kind, E, n, contract=contract, seed=12, first_env_id=40, horizon=25)
+        a.reset(); b.reset()
+        rng = np.random.RandomState(0)
+        rew_h = torch.empty((E, n), dtype=torch.float64).pin_memory()
+        done_h = torch.empty((E,), dtype=torch.uint8).pin_memory()
+        for t in range(30):
+            acts = torch.as_tensor(rng.randint(0, nact, size=(E, n)).astype(np.uint8)).pin_memory()
+            obs_a, rew_a, done_a, _ = a.step(acts.cuda())
+            obs_b, _, _ = b.step_host(acts, rew_h, done_h)
+            assert torch.equal(obs_a.cpu(), obs_b.cpu()), (kind, t)
+            assert np.array_equal(rew_a.cpu().numpy().view(np.uint64), rew_h.numpy().view(np.uint64)), (kind, t)
+            assert torch.equal(done_a.cpu(), done_h), (kind, t)
+            if done_h.any():
+                a.reset(done_a); b.reset(done_h.cuda())
