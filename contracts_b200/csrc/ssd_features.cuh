@@ -167,13 +167,16 @@ __device__ __forceinline__ void feat_spawn(const FeatParams& p, int env, uint32_
     }
 }
 
-// closest point of a list to each agent: smallest (L1 distance, birth stamp)  (np.argmin over the list in birth order)
+// closest point of a list to each agent: smallest (L1 distance, birth stamp)  (np.argmin over the list in birth order).
+// One key per (point, agent): distance << 24 | birth stamp << 8 | point index, so the search is a running minimum —
+// no data-dependent stamp loads on ties (the stamp of every live point is read once, coalesced across the warp's
+// envs: stamp[i][env]).  Distances are < 256, stamps 16 bits, indices < 256 (FEAT_MASK_WORDS * 32).
 __device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32_t* mask, int npts, const uint16_t* rc,
                                              const uint16_t* stamp, const uint32_t* pos, uint32_t* out_rc /* [MAXN] */)
 {
-    int bd[SSD_MAXN], bi[SSD_MAXN]; uint32_t bs[SSD_MAXN];
+    uint32_t best[SSD_MAXN]; int ar[SSD_MAXN], ac[SSD_MAXN];
 #pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) { bd[a] = 0x7fffffff; bi[a] = -1; bs[a] = 0u; }
+    for (int a = 0; a < SSD_MAXN; a++) { best[a] = 0xFFFFFFFFu; ar[a] = (int)(pos[a] & 255u); ac[a] = (int)((pos[a] >> 8) & 255u); }
     const int nw = (npts + 31) >> 5;
     for (int w = 0; w < nw; w++) {
         uint32_t m = mask[w * FEAT_THREADS];
@@ -181,23 +184,18 @@ __device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32
             const int b = __ffs(m) - 1; m &= m - 1;
             const int i = w * 32 + b;
             const uint32_t prc = __ldg(rc + i);
+            const uint32_t base = ((uint32_t)stamp[(size_t)i * E + env] << 8) | (uint32_t)i;
             const int pr = (int)(prc >> 8), pc = (int)(prc & 255u);
-            uint32_t st = 0u;
 #pragma unroll
             for (int a = 0; a < SSD_MAXN; a++) {
                 if (a >= n) continue;
-                const int d = abs(pr - (int)(pos[a] & 255u)) + abs(pc - (int)((pos[a] >> 8) & 255u));
-                if (d < bd[a]) { bd[a] = d; bi[a] = i; bs[a] = 0u; }
-                else if (d == bd[a]) {
-                    if (!bs[a]) bs[a] = stamp[(size_t)bi[a] * E + env];
-                    if (!st) st = stamp[(size_t)i * E + env];
-                    if (st < bs[a]) { bs[a] = st; bi[a] = i; }
-                }
+                const uint32_t d = (uint32_t)(abs(pr - ar[a]) + abs(pc - ac[a]));
+                best[a] = min(best[a], (d << 24) | base);
             }
         }
     }
 #pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) out_rc[a] = (a < n && bi[a] >= 0) ? (uint32_t)__ldg(rc + bi[a]) : 0u;   // sentinel [0, 0]
+    for (int a = 0; a < SSD_MAXN; a++) out_rc[a] = (a < n && best[a] != 0xFFFFFFFFu) ? (uint32_t)__ldg(rc + (best[a] & 255u)) : 0u;   // sentinel [0, 0]
 }
 
 // feature rows of all agents -> global memory through the warp-private tile

@@ -524,7 +524,9 @@ __device__ __forceinline__ void transpose_tile(const GridParams& p, int lane, co
 {
     const uint32_t* t = reinterpret_cast<const uint32_t*>(tile);
     uint32_t* t2 = reinterpret_cast<uint32_t*>(tile2);
-    const int S4 = p.S >> 2, S24 = p.S2 >> 2, nbj = p.wpw, nblk = p.hpw * nbj;
+    // whole 4-row groups as 4x4 blocks; the H % 4 remaining rows byte by byte (cleanup: 6 x 5 = 30 blocks = one pass
+    // of the warp + row 24, instead of 35 blocks = two passes).  The padding of T2 keeps its C_OUTSIDE fill.
+    const int S4 = p.S >> 2, S24 = p.S2 >> 2, nbj = p.wpw, full = p.H >> 2, nblk = full * nbj;
     for (int b = lane; b < nblk; b += 32) {
         const int bi = (int)(((uint32_t)b * p.wpw_magic) >> 16), bj = b - bi * nbj;   // block row / word column
         const uint32_t* src = t + (4 * bi + SSD_VIEW) * S4 + 2 + bj;
@@ -537,6 +539,9 @@ __device__ __forceinline__ void transpose_tile(const GridParams& p, int lane, co
         dst[2 * S24] = __byte_perm(t2a, t3, 0x5410);
         dst[3 * S24] = __byte_perm(t2a, t3, 0x7632);
     }
+    for (int r = 4 * full; r < p.H; r++)
+        for (int c = lane; c < p.W; c += 32)
+            tile2[(c + SSD_VIEW) * p.S2 + 8 + r] = tile[(r + SSD_VIEW) * p.S + 8 + c];
 }
 
 // ao: the agent's cell in T.  `tile` is the base of [T | T2]; vdesc entries hold offsets relative to it.
