@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatPara
                             n_cur_apple, n_cur_waste);
 }
 
-__global__ void __launch_bounds__(FEAT_THREADS) feat_step_kernel(const FeatParams p, const FeatIO io)
+#ifndef FEAT_MIN_BLOCKS
+#define FEAT_MIN_BLOCKS 4          // 128 registers: 16 warps per SM (measured best of 3..6, tools/sweep_feat.sh)
+#endif
+__global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kernel(const FeatParams p, const FeatIO io)
 {
     __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
     __shared__ double s_tile[(FEAT_THREADS / 32) * 32 * (FEAT_MAXF + 1)];
