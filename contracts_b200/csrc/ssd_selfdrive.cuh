@@ -47,30 +47,36 @@ __device__ __forceinline__ double car_u01(const CarParams& p, uint32_t env_id, u
     return __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, site, 0u, idx), 1.0 / 4294967296.0);
 }
 
-// each warp writes the observation rows of its 32 envs: lane j = element j of a row (:244-249)
+// each warp writes the observation rows of its 32 envs (:244-249).  The n * D doubles of an env and the envs of a warp
+// are contiguous in `obs`, so the warp walks the 32 * n * D block with flat, fully coalesced 256-byte stores; a lane
+// tracks (env, car, element) of its flat index incrementally.
 __device__ __forceinline__ void car_write_obs(const CarParams& p, const double* s_pos, const double* s_vel, double* obs,
                                               int env0, int lane, unsigned valid_mask)
 {
-    const int n = p.n, D = p.D;
-    for (int el = 0; el < 32; el++) {
-        if (!((valid_mask >> el) & 1u)) continue;
-        const int col = (threadIdx.x & ~31) + el;
-        double* row0 = obs + (size_t)(env0 + el) * n * D;
-        const double p0 = s_pos[col];
-        for (int k = 0; k < n; k++) {
-            if (lane < D) {
-                const double pk = s_pos[k * CAR_STRIDE + col];
-                double v;
-                if (lane == 0) v = pk;
-                else if (lane == 1) v = s_vel[k * CAR_STRIDE + col];
-                else if (lane < 2 + n) v = __dsub_rn(s_pos[(lane - 2) * CAR_STRIDE + col], pk);
-                else if (lane < 2 + 2 * n) v = s_vel[(lane - 2 - n) * CAR_STRIDE + col];
-                else if (lane == 2 + 2 * n) v = p0 > 0 ? 1.0 : 0.0;
-                else if (lane == 3 + 2 * n) v = pk > 0 ? 1.0 : 0.0;
-                else v = 0.0;
-                row0[k * D + lane] = v;
-            }
+    const int n = p.n, D = p.D, total = 32 * n * D;
+    double* base = obs + (size_t)env0 * n * D;
+    const int col0 = threadIdx.x & ~31;
+    int el = 0, k = 0, j = lane;                        // flat index f = (el * n + k) * D + j
+    while (j >= D) { j -= D; k++; }
+    while (k >= n) { k -= n; el++; }
+    for (int f = lane; f < total; f += 32) {
+        if ((valid_mask >> el) & 1u) {
+            const int col = col0 + el;
+            const double pk = s_pos[k * CAR_STRIDE + col];
+            double v;
+            if (j < 2) v = j == 0 ? pk : s_vel[k * CAR_STRIDE + col];
+            else if (j < 2 + 2 * n) {
+                const int q = j - 2;
+                const double x = (q < n ? s_pos : s_vel)[(q < n ? q : q - n) * CAR_STRIDE + col];
+                v = q < n ? __dsub_rn(x, pk) : x;
+            } else if (j == 2 + 2 * n) v = s_pos[col] > 0 ? 1.0 : 0.0;
+            else if (j == 3 + 2 * n) v = pk > 0 ? 1.0 : 0.0;
+            else v = 0.0;
+            base[f] = v;
         }
+        j += 32;
+        while (j >= D) { j -= D; k++; }
+        while (k >= n) { k -= n; el++; }
     }
 }
 
