@@ -83,7 +83,17 @@ __global__ void __launch_bounds__(VIEW_THREADS) concat_obs_kernel(const GridPara
     const int env0 = blockIdx.x * VIEW_GROUP;
     const int G = min(VIEW_GROUP, p.E - env0);
     const int total = G * per_env;
-    if (obs_stride == per_env) {                              // dense batch tensor: the group is one aligned word run
+    __shared__ uint64_t bar;
+    // dense batch tensor and a 16-byte multiple per group (n % 4 == 0): the group moves with one bulk (TMA) copy each way
+    const bool bulk = obs_stride == per_env && G == VIEW_GROUP && (total & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_load(vsm, obs + (size_t)env0 * per_env, (uint32_t)total, &bar);
+        mbar_wait(&bar, 0);
+    } else if (obs_stride == per_env) {                       // dense: the group is one aligned word run
         const uint32_t* src = reinterpret_cast<const uint32_t*>(obs + (size_t)env0 * per_env);
         for (int w = threadIdx.x; 4 * w + 3 < total; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(vsm)[w] = src[w];
         for (int b = (total & ~3) + threadIdx.x; b < total; b += VIEW_THREADS) vsm[b] = obs[(size_t)env0 * per_env + b];
@@ -104,8 +114,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) concat_obs_kernel(const GridPara
             o[3 * a] = src[a * SSD_OBS_BYTES]; o[3 * a + 1] = src[a * SSD_OBS_BYTES + 1]; o[3 * a + 2] = src[a * SSD_OBS_BYTES + 2];
         }
     }
-    __syncthreads();
     uint8_t* dst = out + (size_t)env0 * per_env;
+    if (bulk) {
+        fence_async_smem();                                   // the staged bytes become visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) { bulk_store(dst, stage, (uint32_t)total); bulk_wait_read<0>(); }
+        return;
+    }
+    __syncthreads();
     for (int w = threadIdx.x; 4 * w + 3 < total; w += VIEW_THREADS) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(stage)[w];
     for (int k = (total & ~3) + threadIdx.x; k < total; k += VIEW_THREADS) dst[k] = stage[k];
 }
