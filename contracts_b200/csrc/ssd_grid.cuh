@@ -299,6 +299,27 @@ __device__ __forceinline__ uint32_t draw_u32_ool(const EnvRng& g, uint32_t t, ui
     return w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
 }
 
+// Two Philox blocks of the same (env, episode, t) with interleaved rounds: two independent dependency chains instead of
+// two calls back to back (the spawn is latency-bound).  Results go to shared memory; a null pointer skips the store.
+__device__ __noinline__ void draw_blocks2_ool(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t,
+                                              uint32_t site_a, uint32_t block_a, uint4* dst_a,
+                                              uint32_t site_b, uint32_t block_b, uint4* dst_b)
+{
+    uint32_t a0 = block_a, a1 = site_a, a2 = t, a3 = episode, b0 = block_b, b1 = site_b, b2 = t, b3 = episode;
+    uint32_t k0 = seed, k1 = env_id;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t ah0 = __umulhi(0xD2511F53u, a0), al0 = 0xD2511F53u * a0, ah1 = __umulhi(0xCD9E8D57u, a2), al1 = 0xCD9E8D57u * a2;
+        const uint32_t bh0 = __umulhi(0xD2511F53u, b0), bl0 = 0xD2511F53u * b0, bh1 = __umulhi(0xCD9E8D57u, b2), bl1 = 0xCD9E8D57u * b2;
+        const uint32_t na0 = ah1 ^ a1 ^ k0, na2 = ah0 ^ a3 ^ k1, nb0 = bh1 ^ b1 ^ k0, nb2 = bh0 ^ b3 ^ k1;
+        a0 = na0; a1 = al1; a2 = na2; a3 = al0;
+        b0 = nb0; b1 = bl1; b2 = nb2; b3 = bl0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    if (dst_a) *dst_a = make_uint4(a0, a1, a2, a3);
+    if (dst_b) *dst_b = make_uint4(b0, b1, b2, b3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The literal ordering of the reference (rare: some movers share a target or a real move targets an
 // occupied cell).  Out of line: it is cold and would otherwise bloat the hot loop's instruction
@@ -495,8 +516,33 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
             M += __popc(eligm[q]);
         } else eligm[q] = 0;
     }
+    // waste candidates = non-'H' cells of waste_points (apple points and waste points are disjoint, so the apple
+    // spawns below cannot change them)
+    unsigned candm[ROUNDS] = {};
+    int C = 0;
+    if (waste_on) {
+#pragma unroll
+        for (int q = 0; q < ROUNDS; q++) {
+            int j = lane + 32 * q;
+            bool cnd = false;
+            if (q * 32 < p.n_waste) {
+                if (j < p.n_waste) cnd = (tile[sm_waste[j]] & CODE_MASK) != C_WASTE;
+                candm[q] = __ballot_sync(FULL, cnd);
+                C += __popc(candm[q]);
+            } else candm[q] = 0;
+        }
+    }
+    // one Philox pass for everything this spawn can need: the apple draws [0, M), the first waste draws [M, M + wfirst)
+    // (the waste scan stops at its first success, p = 0.5) and the shuffle keys of the waste points
+    const int wfirst = C > 0 ? min(min(C, 8), SCRATCH_DRAWS - M) : 0;
+    const int nblk = (thrA || wfirst) ? (M + wfirst + 3) >> 2 : 0;
+    const int nkblk = C > 0 ? (p.n_waste + 3) >> 2 : 0;
+    for (int bl = lane; __any_sync(FULL, bl < nblk || bl < nkblk); bl += 32)
+        draw_blocks2_ool(g.seed, g.env_id, g.episode, t,
+                         SITE_SPAWN_DRAWS, (uint32_t)bl, bl < nblk ? reinterpret_cast<uint4*>(draws) + bl : nullptr,
+                         SITE_WASTE_ORDER, (uint32_t)bl, bl < nkblk ? reinterpret_cast<uint4*>(keys) + bl : nullptr);
+    __syncwarp();
     if (thrA) {
-        fill_draws(draws, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);
         int base = 0;
 #pragma unroll
         for (int q = 0; q < ROUNDS; q++) {
@@ -511,35 +557,22 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
         __syncwarp();
     }
     const bool apples = __any_sync(FULL, spawned);
-    if (!waste_on) return apples;
+    if (!waste_on || C == 0) return apples;
     // waste: shuffle waste_points (stateless: key per canonical index), scan non-'H' cells in that
     // order, draw continues at rank M; first success spawns and breaks (:338-348)
-    unsigned candm[ROUNDS];
-    int C = 0;
-#pragma unroll
-    for (int q = 0; q < ROUNDS; q++) {
-        int j = lane + 32 * q;
-        bool cnd = false;
-        if (q * 32 < p.n_waste) {
-            if (j < p.n_waste) cnd = (tile[sm_waste[j]] & CODE_MASK) != C_WASTE;
-            candm[q] = __ballot_sync(FULL, cnd);
-            C += __popc(candm[q]);
-        } else candm[q] = 0;
-    }
-    if (C == 0) return apples;
     // number of failed draws before the first success
     int kstar = -1;
-    for (int k0 = 0; k0 < C && kstar < 0; k0 += 32) {
+    {
+        const unsigned succ = __ballot_sync(FULL, lane < wfirst && draws[M + lane] < p.thr_waste);
+        if (succ) kstar = __ffs(succ) - 1;
+    }
+    for (int k0 = wfirst; k0 < C && kstar < 0; k0 += 32) {
         uint32_t dr = draw_u32_ool(g, t, SITE_SPAWN_DRAWS, (uint32_t)(M + k0 + lane));
         unsigned succ = __ballot_sync(FULL, (k0 + lane) < C && dr < p.thr_waste);
         if (succ) kstar = k0 + __ffs(succ) - 1;
     }
     if (kstar < 0) return apples;
-    // keys of all waste points, then the (kstar+1)-th smallest (key, index) among candidates
-    for (int bl = lane; bl < ((p.n_waste + 3) >> 2); bl += 32) {
-        reinterpret_cast<uint4*>(keys)[bl] = draw_block_ool(g.seed, g.env_id, g.episode, t, SITE_WASTE_ORDER, (uint32_t)bl);
-    }
-    __syncwarp();
+    // the (kstar+1)-th smallest (key, index) among the candidates
     int chosen = -1;
     for (int it = 0; it <= kstar; it++) {
         uint32_t bk = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;

@@ -677,6 +677,7 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
         __syncwarp();
         // ---- spawn
         bool changed = false;
+#ifndef OBS_SKIP_SPAWN         // OBS_SKIP_*: timing experiments only (tools/sweep_obs_parts.sh), results are wrong
         if (KIND == SSD_ENV_CLEANUP) {
             if (cleanup_spawn_active(tb, hcount)) {
                 if (lane == 0) bulk_wait_read<0>();   // the previous observation store has drained `stage` (= scratch)
@@ -691,6 +692,7 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
             __syncwarp();
             changed = harvest_spawn<ROUNDS>(p, lane, tile, scratch, tb.apple, g, t);
         }
+#endif
         int total_close = 0;
         if (KIND == SSD_ENV_HARVEST && act_lane) {
             total_close = count_apples_r5(tile, ao, S);
@@ -717,9 +719,13 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
         __syncwarp();
         if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
         __syncwarp();
+#ifndef OBS_SKIP_TRANSPOSE
         transpose_tile(p, lane, tile, tile2);
+#endif
         // gather_obs2 waits (lane 0) until the previous observation store has drained `stage`, then syncs the warp
+#ifndef OBS_SKIP_GATHER
         gather_obs2(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
+#endif
         g_rec += g_rec_step; g_obs += g_obs_step;
         __syncwarp();
     }
