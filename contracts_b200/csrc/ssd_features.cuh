@@ -467,21 +467,26 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kerne
             if (io.transfers) io.transfers[o] = tr[a];
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = cleanup ? (uint32_t)cleaned[a] : ((uint32_t)eaten[a] | ((uint32_t)eaten_close[a] << 8));
             p.agents[so] = pos[a];
-            if (reward[a]) { p.sum_raw[so] += (uint32_t)reward[a]; p.tsum_raw[so] += (unsigned long long)(t - 1) * (unsigned long long)reward[a]; }
+            // episode accumulators as fire-and-forget reductions (one add per address and step: a float64 RED rounds
+            // exactly like `x = x + y`), so no load round trip sits in the thread's dependency chain
+            if (reward[a]) {
+                red_add(p.sum_raw + so, (uint32_t)reward[a]);
+                red_add(reinterpret_cast<long long*>(p.tsum_raw + so), (long long)((unsigned long long)(t - 1) * (unsigned long long)reward[a]));
+            }
             if (r[a] != 0.0) {
-                p.sum_tr[so] = __dadd_rn(p.sum_tr[so], r[a]);
-                p.tsum_tr[so] = __dadd_rn(p.tsum_tr[so], __dmul_rn((double)(t - 1), r[a]));
+                red_add(p.sum_tr + so, r[a]);
+                red_add(p.tsum_tr + so, __dmul_rn((double)(t - 1), r[a]));
             }
         }
 #pragma unroll
         for (int w = 0; w < FEAT_MASK_WORDS; w++) { p.apple_mask[(size_t)w * p.E + env] = am[w * FEAT_THREADS]; p.waste_mask[(size_t)w * p.E + env] = wm[w * FEAT_THREADS]; }
         p.counters[(size_t)0 * p.E + env] = next_apple; p.counters[(size_t)1 * p.E + env] = next_waste;
         p.counters[(size_t)2 * p.E + env] = (uint32_t)t;
-        if (dirt) p.metrics[(size_t)0 * p.E + env] += (double)dirt;
-        if (raw != 0.0) p.metrics[(size_t)1 * p.E + env] = __dadd_rn(p.metrics[(size_t)1 * p.E + env], raw);
-        if (p.contract != SSD_CONTRACT_NONE) p.metrics[(size_t)2 * p.E + env] = __dadd_rn(p.metrics[(size_t)2 * p.E + env], total);
-        if (n_eaten) p.metrics[(size_t)3 * p.E + env] += (double)n_eaten;
-        if (n_close) p.metrics[(size_t)4 * p.E + env] += (double)n_close;
+        if (dirt) red_add(p.metrics + (size_t)0 * p.E + env, (double)dirt);
+        if (raw != 0.0) red_add(p.metrics + (size_t)1 * p.E + env, raw);
+        if (p.contract != SSD_CONTRACT_NONE && total != 0.0) red_add(p.metrics + (size_t)2 * p.E + env, total);
+        if (n_eaten) red_add(p.metrics + (size_t)3 * p.E + env, (double)n_eaten);
+        if (n_close) red_add(p.metrics + (size_t)4 * p.E + env, (double)n_close);
         if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
     }
     feat_write_obs(p, mine, env, s_tile + (threadIdx.x >> 5) * 32 * (FEAT_MAXF + 1), io.obs, pos, ca, cw, close5, cleaned,
