@@ -475,16 +475,6 @@ __device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile,
     return total_cleaned;
 }
 
-// fill scratch[0 .. 4*nblk) with Philox blocks 0..nblk-1 of (site, call)
-__device__ __forceinline__ void fill_draws(uint32_t* scratch, int lane, const EnvRng& g, uint32_t t,
-                                           uint32_t site, int nblk)
-{
-    for (int bl = lane; bl < nblk; bl += 32) {
-        reinterpret_cast<uint4*>(scratch)[bl] = draw_block_ool(g.seed, g.env_id, g.episode, t, site, (uint32_t)bl);
-    }
-    __syncwarp();
-}
-
 // ---------------------------------------------------------------------------------------------
 // cleanup spawn (cleanup_new.py:322-349).  Occupancy bits must be set.  `t` = 0 at reset.
 // Updates hcount (#waste cells); returns whether the map changed.
@@ -631,7 +621,18 @@ __device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uin
         }
     }
     if (M == 0) return false;
-    fill_draws(scratch, lane, g, t, SITE_SPAWN_DRAWS, (M + 3) >> 2);   // also orders the tile reads above
+    {   // draws [0, M): Philox blocks lane and lane + 32 as two interleaved chains (M > 128 needs more than 32 blocks)
+        const int nblk = (M + 3) >> 2;
+        uint4* d4 = reinterpret_cast<uint4*>(scratch);
+        if (nblk <= 32) {
+            if (lane < nblk) d4[lane] = draw_block_ool(g.seed, g.env_id, g.episode, t, SITE_SPAWN_DRAWS, (uint32_t)lane);
+        } else {
+            for (int bl = lane; __any_sync(FULL, bl < nblk); bl += 64)
+                draw_blocks2_ool(g.seed, g.env_id, g.episode, t, SITE_SPAWN_DRAWS, (uint32_t)bl, bl < nblk ? d4 + bl : nullptr,
+                                 SITE_SPAWN_DRAWS, (uint32_t)(bl + 32), bl + 32 < nblk ? d4 + bl + 32 : nullptr);
+        }
+        __syncwarp();                                                  // also orders the tile reads above
+    }
     int base = 0;
     bool spawned = false;
 #pragma unroll
