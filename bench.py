@@ -63,7 +63,38 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        h = self.nvml_handle
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for _, b in bits])
+            self.stop_flag.wait(0.005)
+
     def start(self):
+        """NVML polled every 5 ms from a thread (the timed region can be shorter than one nvidia-smi period);
+        nvidia-smi -lms as the fallback."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.nvml_handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            self.proc = "nvml"
+            return
+        except Exception:
+            self.proc = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -82,7 +113,11 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.proc == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+        else:
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -101,7 +136,7 @@ def run_cpu(envs_per_thread, steps, warmup):
     """The oracle port on all host cores (OpenMP).  Returns (agent-steps/s, cores, sample string)."""
     from oracle import oracle
     from contracts_b200.maps import CLEANUP_MAP
-    cores = os.cpu_count() or 1
+    cores = oracle.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: ask for every core
     E = envs_per_thread * cores
     o = oracle.GridOracle("cleanup", E, N_AGENTS, CLEANUP_MAP, horizon=HORIZON, contract="CleanupContract", seed=SEED)
     o.reset()

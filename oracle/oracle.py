@@ -53,6 +53,7 @@ def lib():
         L.oracle_set_reward_shaping.argtypes = [vp, i32, f64, f64]
         L.oracle_global_view.argtypes = [vp, vp]
         L.oracle_render.argtypes = [vp, vp]
+        L.oracle_set_num_threads.argtypes = [i32]
         L.feat_oracle_create.restype = vp
         L.feat_oracle_create.argtypes = [i32, i32, i32, i32, i32, ctypes.c_char_p, i32, i32, f64, f64, f64, u32, u32]
         L.feat_oracle_destroy.argtypes = [vp]
@@ -72,6 +73,11 @@ def lib():
         L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
+
+
+def set_num_threads(n):
+    """Threads of the oracle's OpenMP loops over envs; returns the count in effect (1 without OpenMP)."""
+    return int(lib().oracle_set_num_threads(int(n)))
 
 
 def _p(a):

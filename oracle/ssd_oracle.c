@@ -31,6 +31,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define MAXN 8
 #define MAXH 48
@@ -919,6 +922,17 @@ void oracle_render(void* h, uint8_t* out)
         for (int r = 0; r < b->H; r++)
             for (int c = 0; c < b->W; c++) if (e->beam[r][c]) color_of(e->beam[r][c], o + ((size_t)r * b->W + c) * 3);
     }
+}
+/* threads of the OpenMP loops over envs (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core) */
+int oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 int oracle_feature_dim(void* h) { return ((batch_t*)h)->F; }
 

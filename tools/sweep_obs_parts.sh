@@ -1,5 +1,5 @@
 # where the observe kernel's time goes: rebuild with one phase compiled out (results are wrong, timing only)
-for flag in NONE OBS_SKIP_SPAWN OBS_SKIP_TRANSPOSE OBS_SKIP_GATHER; do
+for flag in ${FLAGS:-NONE OBS_SKIP_SPAWN OBS_SKIP_TRANSPOSE OBS_SKIP_GATHER}; do
   python -c "
 from contracts_b200 import build
 build.build(force=True, extra_flags=['-D$flag'])" > /dev/null 2>&1 || { echo "$flag: build failed"; continue; }
