@@ -217,78 +217,59 @@ class JointEnv:
     """
 
     def __init__(self, base_env, num_agents=2, duplicate_obs=False, concatenated_obs=False, global_obs=False, **kwargs):
-        self.base_env = base_env
-        self.num_agents = num_agents
-        self.duplicate_obs = duplicate_obs
-        self.global_obs = global_obs
-        self.concatenated_obs = concatenated_obs
-        if global_obs:
-            self.observation_space = self.base_env.global_observation_space
-            self.action_space = self.base_env.global_action_space
-        elif concatenated_obs:
-            self.observation_space = self.base_env.concatenated_observation_space
-            self.action_space = self.base_env.global_action_space
-        else:
-            if self.duplicate_obs:
-                self.observation_space = spaces.Box(
-                    low=np.concatenate([self.base_env.observation_space.low] * self.num_agents),
-                    high=np.concatenate([self.base_env.observation_space.high] * self.num_agents))
-            else:
-                self.observation_space = self.base_env.observation_space
-            self.action_space = spaces.Box(low=np.concatenate([self.base_env.action_space.low] * self.num_agents),
-                                           high=np.concatenate([self.base_env.action_space.high] * self.num_agents))
-            self.curr_agent_lst = ["a" + str(i) for i in range(self.num_agents)]
+        self.base_env, self.num_agents = base_env, num_agents
+        self.duplicate_obs, self.concatenated_obs, self.global_obs = duplicate_obs, concatenated_obs, global_obs
+        self._ids = ["a%d" % i for i in range(num_agents)]
+        if global_obs or concatenated_obs:                       # image layouts: MultiDiscrete joint action (:503-508)
+            self.observation_space = (base_env.global_observation_space if global_obs
+                                      else base_env.concatenated_observation_space)
+            self.action_space = base_env.global_action_space
+        else:                                                    # flat layouts: tiled Box spaces (:509-523)
+            tile = lambda x: np.concatenate([x] * num_agents)    # noqa: E731
+            obs_space = base_env.observation_space
+            self.observation_space = spaces.Box(low=tile(obs_space.low), high=tile(obs_space.high)) if duplicate_obs else obs_space
+            self.action_space = spaces.Box(low=tile(base_env.action_space.low), high=tile(base_env.action_space.high))
+            self.curr_agent_lst = list(self._ids)
 
     @property
     def metrics(self):
         return self.base_env.metrics
 
-    def _concatenated(self):
+    def _image_obs(self):
+        if self.global_obs:
+            return {"a0": self.base_env.get_global_obs()}
         img = self.base_env.batch.concatenated_obs()[0].cpu().numpy()
         return {"a0": {"image": img.astype(np.float64) / 255}}
 
+    @staticmethod
+    def _joint(obs, env_rews, env_dones, env_infos, members):
+        """Summed reward (not the average, :592), the env-wide done flag, infos summed key by key (:594-595)."""
+        infos = {key: sum([env_infos[k][key] for k in members]) for key in env_infos[members[0]].keys()}
+        return obs, {"a0": sum([r for r in env_rews.values()])}, {"a0": env_dones["__all__"], "__all__": env_dones["__all__"]}, {"a0": infos}
+
     def reset(self):
-        base_obs = self.base_env.reset()
-        if self.global_obs:
-            return {"a0": self.base_env.get_global_obs()}
-        elif self.concatenated_obs:
-            return self._concatenated()
-        else:
-            self.agent_obs = base_obs.copy()
-            self.curr_agent_lst = ["a" + str(i) for i in range(self.num_agents)]
-            return {"a0": np.concatenate([base_obs["a" + str(i)] for i in range(self.num_agents)])}
+        first = self.base_env.reset()
+        if self.global_obs or self.concatenated_obs:
+            return self._image_obs()
+        self.agent_obs = dict(first)                             # assumes every agent is in the initial observation
+        self.curr_agent_lst = list(self._ids)
+        return {"a0": np.concatenate([first[k] for k in self._ids])}
 
     def step(self, acts):
-        if self.global_obs or self.concatenated_obs:
-            agent_list = ["a" + str(i) for i in range(self.num_agents)]
-            action_dict = {"a" + str(i): acts["a0"][i] for i in range(self.num_agents)}
-            _, env_rews, env_dones, env_infos = self.base_env.step(action_dict)
-            obs = {"a0": self.base_env.get_global_obs()} if self.global_obs else self._concatenated()
-            rews = {"a0": sum([rew for rew in env_rews.values()])}        # straightforward sum, not average (:592)
-            dones = {"a0": env_dones["__all__"], "__all__": env_dones["__all__"]}
-            infos = {"a0": {key: sum([env_infos[agent][key] for agent in agent_list])
-                            for key in env_infos[agent_list[0]].keys()}}
-            return obs, rews, dones, infos
-        k = self.base_env.action_space.shape[0]
-        action_dict = {}
-        for i in range(self.num_agents):
-            if "a" + str(i) in self.curr_agent_lst:
-                action_dict["a" + str(i)] = np.array(acts["a0"][i * k:(i + 1) * k])
-        base_obs, env_rews, env_dones, env_infos = self.base_env.step(action_dict)
-        for agent in self.curr_agent_lst:
-            self.agent_obs[agent] = base_obs[agent]
-        if self.duplicate_obs:
-            obs = {"a0": np.concatenate([self.agent_obs["a" + str(i)] for i in range(self.num_agents)])}
-        else:
-            obs = {"a0": self.agent_obs[self.curr_agent_lst[0]]}
-        rews = {"a0": sum([rew for rew in env_rews.values()])}
-        dones = {"a0": env_dones["__all__"], "__all__": env_dones["__all__"]}
-        infos = {"a0": {key: sum([env_infos[agent][key] for agent in self.curr_agent_lst])
-                        for key in env_infos[self.curr_agent_lst[0]].keys()}}
-        for i in range(self.num_agents):
-            if "a" + str(i) in self.curr_agent_lst and env_dones.get("a" + str(i), False):
-                self.curr_agent_lst.remove("a" + str(i))
-        return obs, rews, dones, infos
+        joint = acts["a0"]
+        if self.global_obs or self.concatenated_obs:             # global_step / concatenated_step (:572-617)
+            _, rews, dones, infos = self.base_env.step({k: joint[i] for i, k in enumerate(self._ids)})
+            return self._joint(self._image_obs(), rews, dones, infos, self._ids)
+        width = self.base_env.action_space.shape[0]              # each active agent's slice of the joint action (:540-546)
+        active = list(self.curr_agent_lst)
+        base_obs, rews, dones, infos = self.base_env.step(
+            {k: np.array(joint[i * width:(i + 1) * width]) for i, k in enumerate(self._ids) if k in active})
+        for k in active:
+            self.agent_obs[k] = base_obs[k]
+        obs = np.concatenate([self.agent_obs[k] for k in self._ids]) if self.duplicate_obs else self.agent_obs[active[0]]
+        out = self._joint({"a0": obs}, rews, dones, infos, active)
+        self.curr_agent_lst = [k for k in active if not dones.get(k, False)]     # finished agents stop acting (:562-566)
+        return out
 
     def render(self, mode="rgb"):
         return self.base_env.render()

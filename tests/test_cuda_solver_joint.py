@@ -240,3 +240,32 @@ def test_render_matches_oracle_masked_reset(oracle_lib):
             mask = o["done"].copy(); mask[::2] = 0
             orc.reset(mask); env.reset(torch.as_tensor(mask).cuda())
             gu.assert_same("frame after masked reset", env.render().cpu().numpy(), orc.render(), "t %d" % t)
+
+
+def test_joint_env_flat_variant_over_selfdrive():
+    """JointEnv without image observations (duplicate_obs, Box action spaces; two_stage_train.py:509-570) over the
+    selfdrive env: the joint step must equal the per-agent step of an identically seeded env, concatenated / summed."""
+    from contracts_b200.utils.env_creator_functions import env_creator
+    n = 4
+    solo = env_creator("SelfDrive", dict(num_agents=n, seed=7, env_id=3))
+    base = env_creator("SelfDrive", dict(num_agents=n, seed=7, env_id=3))
+    joint = env_creator("JointEnv", dict(base_env=base, num_agents=n, duplicate_obs=True))
+    keys = ["a%d" % i for i in range(n)]
+    assert joint.observation_space.shape == (n * solo.observation_space.shape[0],) and joint.action_space.shape == (n,)
+    o_solo, o_joint = solo.reset(), joint.reset()
+    gu.assert_same("reset obs", o_joint["a0"], np.concatenate([o_solo[k] for k in keys]), "reset")
+    rng = np.random.RandomState(4)
+    last = dict(o_solo)
+    active = list(keys)
+    for t in range(60):
+        a = rng.uniform(-0.1, 0.1, size=n).astype(np.float32)
+        o_s, r_s, d_s, i_s = solo.step({k: np.array([a[i]]) for i, k in enumerate(keys) if k in active})
+        o_j, r_j, d_j, i_j = joint.step({"a0": a})
+        last.update(o_s)
+        gu.assert_same("obs", o_j["a0"], np.concatenate([last[k] for k in keys]), "t %d" % t)
+        gu.assert_same("rew", np.float64(r_j["a0"]), np.float64(sum([r for r in r_s.values()])), "t %d" % t)
+        assert d_j == {"a0": d_s["__all__"], "__all__": d_s["__all__"]}
+        active = [k for k in active if not d_s.get(k, False)]
+        if d_s["__all__"]:
+            break
+    assert t > 5
