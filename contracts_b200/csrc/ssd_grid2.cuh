@@ -25,7 +25,12 @@
 #pragma once
 #include "ssd_grid.cuh"
 
+#ifndef LOGIC_THREADS
 #define LOGIC_THREADS 128
+#endif
+#ifndef LOGIC_MIN_BLOCKS
+#define LOGIC_MIN_BLOCKS 7    // 7 x 128 = 896 threads per SM: the E / 148 = 886 envs of the headline batch in one wave, 72 registers
+#endif
 #define LOGIC_WARPS (LOGIC_THREADS / 32)
 #ifndef OBS_WARPS
 #define OBS_WARPS 8           // observe kernel: 3 CTAs of 8 warps per SM (~8.4 KB shared memory per warp, <= 80 registers)
@@ -284,7 +289,7 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 // memory only holds lane-strided copies of the per-agent arrays for the two places that index agents
 // dynamically (the warp-cooperative contested-move resolution and the beam walk).
 template <int KIND>
-__global__ void __launch_bounds__(LOGIC_THREADS, 7) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
+__global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
