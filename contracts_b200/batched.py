@@ -178,10 +178,11 @@ class BatchedGridEnv:
         io.info_dev = self.info.data_ptr()
         io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
         io.done_dev = self.done.data_ptr()
-        _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
-                                                   ctypes.c_void_p(rew_host.data_ptr()),
-                                                   ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
-                                                   self._stream()))
+        with torch.cuda.device(self.device):          # the library creates its copy stream on the current device
+            _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                       ctypes.c_void_p(rew_host.data_ptr()),
+                                                       ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
+                                                       self._stream()))
         return self.obs, rew_host, done_host
 
     def random_actions(self, step_index, num_actions, out=None):

@@ -235,19 +235,24 @@ __global__ void __launch_bounds__(VIEW_THREADS) policy_inputs_kernel(const GridP
         for (int b = threadIdx.x; b < per_env; b += VIEW_THREADS) vsm[b] = src[b];
     __syncthreads();
     T* dst = image + (size_t)env * per_env;
-    auto value = [&](int o) {                                            // o = a * 675 + c * 225 + pixel
-        const int a = o / SSD_OBS_BYTES, r = o - a * SSD_OBS_BYTES;
-        const int c = r / SSD_OBS_PIX, pix = r - c * SSD_OBS_PIX;
-        return policy_cast<T>(lut[vsm[a * SSD_OBS_BYTES + pix * 3 + c]]);
-    };
-    if (sizeof(T) == 2 && (per_env & 1) == 0) {                          // 16-bit outputs leave two at a time
-        struct __align__(4) Pair { T x, y; };
-        for (int o = 2 * threadIdx.x; o < per_env; o += 2 * VIEW_THREADS) {
-            Pair v; v.x = value(o); v.y = value(o + 1);
-            *reinterpret_cast<Pair*>(dst + o) = v;
+    // four consecutive outputs per thread (one 8- or 16-byte store); (agent, channel, pixel) of the first by division,
+    // of the next three by stepping
+    struct __align__(4 * sizeof(T)) Quad { T v[4]; };
+    const bool quads = (per_env & 3) == 0 && (reinterpret_cast<uintptr_t>(image) & (4 * sizeof(T) - 1)) == 0;
+    const int step = quads ? 4 : 1;
+    for (int o = step * threadIdx.x; o < per_env; o += step * VIEW_THREADS) {          // o = a * 675 + c * 225 + pixel
+        int a = o / SSD_OBS_BYTES, r = o - a * SSD_OBS_BYTES;
+        int c = r / SSD_OBS_PIX, pix = r - c * SSD_OBS_PIX;
+        Quad q;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < step) {
+                q.v[k] = policy_cast<T>(lut[vsm[a * SSD_OBS_BYTES + pix * 3 + c]]);
+                if (++pix == SSD_OBS_PIX) { pix = 0; if (++c == 3) { c = 0; a++; } }
+            }
         }
-    } else {
-        for (int o = threadIdx.x; o < per_env; o += VIEW_THREADS) dst[o] = value(o);
+        if (quads) *reinterpret_cast<Quad*>(dst + o) = q;
+        else dst[o] = q.v[0];
     }
     if (contract && threadIdx.x < n * 10) {
         const double theta = *reinterpret_cast<const double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA);
