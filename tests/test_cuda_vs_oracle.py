@@ -19,6 +19,10 @@ CASES = [
     ("cleanup", 8, CRAMPED_CLEANUP, 128, 300, 1000, 9, 4, 0),
     ("harvest", 8, CRAMPED_HARVEST, 128, 300, 1000, 5, 5, 0),
     ("harvest", 1, None, 8, 60, 1000, 8, 6, 0),
+    # whole episodes at the benchmark's horizon: the late-episode regime (spawning active, apples depleted: > 128 spawn
+    # draws per step in harvest) and the re-reset at t = 1000
+    ("cleanup", 8, None, 40, 1100, 1000, 8, 11, 0),
+    ("harvest", 8, None, 40, 1100, 1000, 7, 12, 0),
     # reward shaping (map_env.py:289-301): use_collective_reward / inequity_averse_reward
     ("cleanup", 8, None, 96, 160, 70, 9, 7, 0, dict(inequity_averse_reward=True, alpha=5.0, beta=0.05)),
     ("harvest", 4, None, 96, 160, 70, 8, 8, 0, dict(use_collective_reward=True)),
