@@ -53,12 +53,18 @@ __global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridPar
     }
     const int cells = p.H * p.W, per_env = cells * 3, total = G * per_env;
     uint8_t* stage = vsm + VIEW_GROUP * p.map_bytes;          // the group's output bytes
-    for (int i = threadIdx.x; i < G * cells; i += VIEW_THREADS) {
-        const int g = i / cells, cell = i - g * cells;
-        const int r = cell / p.W, c = cell - r * p.W;
-        const uint32_t col = s_pal[(vsm[g * p.map_bytes + r * p.Wp + c] & CODE_MASK) >> 2];
-        uint8_t* o = stage + 3 * i;
-        o[0] = (uint8_t)col; o[1] = (uint8_t)(col >> 8); o[2] = (uint8_t)(col >> 16);
+    const int dq = VIEW_THREADS / p.W, dm = VIEW_THREADS - dq * p.W;       // (row, col) step of a thread's next cell
+    const int r0 = (int)threadIdx.x / p.W, c0 = (int)threadIdx.x - r0 * p.W;
+    for (int g = 0; g < G; g++) {
+        const uint8_t* m = vsm + g * p.map_bytes;
+        uint8_t* o = stage + g * per_env + 3 * threadIdx.x;
+        int r = r0, c = c0;
+        for (int cell = threadIdx.x; cell < cells; cell += VIEW_THREADS, o += 3 * VIEW_THREADS) {
+            const uint32_t col = s_pal[(m[r * p.Wp + c] & CODE_MASK) >> 2];
+            o[0] = (uint8_t)col; o[1] = (uint8_t)(col >> 8); o[2] = (uint8_t)(col >> 16);
+            c += dm; r += dq;
+            if (c >= p.W) { c -= p.W; r++; }
+        }
     }
     __syncthreads();
     uint8_t* dst = out + (size_t)env0 * per_env;              // env0 % 4 == 0: word aligned
