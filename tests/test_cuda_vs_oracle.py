@@ -77,3 +77,88 @@ def test_rollout_matches_oracle(oracle_lib, case):
                            orc.reset(mask)[mask.astype(bool)], ctx)
             check_state(ctx + " after reset")
     gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
+
+
+def _big_map(kind, H, W, seed):
+    """A random walled map near the size limits (48 x 64): compact form > 1 KB, so the fused fallback kernel steps it."""
+    rng = np.random.RandomState(seed)
+    g = np.full((H, W), " ", dtype="<U1")
+    g[0, :] = g[-1, :] = g[:, 0] = g[:, -1] = "@"
+    inner = [(r, c) for r in range(1, H - 1) for c in range(1, W - 1)]
+    rng.shuffle(inner)
+    kinds = (("P", 24), ("@", 60), ("B", 200), ("H", 90), ("R", 120), ("S", 30)) if kind == "cleanup" else (("P", 24), ("@", 60), ("A", 240))
+    k = 0
+    for ch, cnt in kinds:
+        for r, c in inner[k:k + cnt]:
+            g[r, c] = ch
+        k += cnt
+    return ["".join(row) for row in g]
+
+
+@pytest.mark.parametrize("kind,n,H,W", [("cleanup", 8, 44, 60), ("harvest", 6, 40, 63), ("cleanup", 3, 48, 64)])
+def test_big_map_fallback_kernel_matches_oracle(oracle_lib, kind, n, H, W):
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    amap = _big_map(kind, H, W, H * W)
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    E, steps = 24, 150
+    orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=60, contract=contract, seed=21, first_env_id=3)
+    env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=60, contract=contract, seed=21, first_env_id=3)
+    assert env.state_map_bytes > 1024
+    rng = np.random.RandomState(1)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    for t in range(steps):
+        a = rng.randint(0, 9 if kind == "cleanup" else 8, size=(E, n))
+        o = orc.step(a, want_features=(t % 5 == 0))
+        obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda(), want_features=(t % 5 == 0))
+        ctx = "step %d" % t
+        gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+        gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+        gu.assert_same("info", info.cpu().numpy()[..., :3], o["info"][..., :3], ctx)
+        if t % 5 == 0:
+            gu.assert_same("feature_obs", env.feature_obs.cpu().numpy(), o["feature_obs"], ctx)
+        if o["done"].any():
+            gu.assert_same("reset obs", env.reset(torch.as_tensor(o["done"]).cuda()).cpu().numpy()[o["done"].astype(bool)],
+                           orc.reset(o["done"])[o["done"].astype(bool)], ctx)
+    so, sc = orc.get_state(), env.get_state()
+    for k in ("map", "pos", "ori", "t"):
+        gu.assert_same(k, sc[k].cpu().numpy(), so[k], "end")
+    gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
+
+
+@pytest.mark.parametrize("kind,amap_name,n,nact", [("cleanup", "stock", 8, 9), ("cleanup", "cramped", 8, 9), ("harvest", "stock", 8, 8),
+                                                   ("harvest", "cramped", 8, 8)])
+def test_soak_many_envs_matches_oracle(oracle_lib, kind, amap_name, n, nact):
+    """Thousands of envs for a few dozen steps: rare paths (long contested chains, 4+ shooters per env, overlapping
+    agents, multi-apple spawns) at a rate the small rollouts do not reach."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    amap = {"stock": CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP,
+            "cramped": CRAMPED_CLEANUP if kind == "cleanup" else CRAMPED_HARVEST}[amap_name]
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    E, steps = 6000, 50
+    orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=1000, contract=contract, seed=99, first_env_id=123456)
+    env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=1000, contract=contract, seed=99, first_env_id=123456)
+    rng = np.random.RandomState(7)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    if kind == "cleanup" and amap_name == "stock":       # start inside the spawning regime: clean most of the waste
+        st = orc.get_state()
+        m = st["map"].copy()
+        waste = m == ord("H")
+        keep = rng.rand(*m.shape) < 0.6
+        m[waste & ~keep] = ord("R")
+        orc.set_state(map=m); env.set_state(map=m)
+    for t in range(steps):
+        a = rng.randint(0, nact, size=(E, n))
+        o = orc.step(a, want_features=False)
+        obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        ctx = "step %d" % t
+        gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+        gu.assert_same("info", info.cpu().numpy()[..., :3], o["info"][..., :3], ctx)
+        if t % 7 == 0 or t == steps - 1:
+            gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+            so, sc = orc.get_state(), env.get_state()
+            for k in ("map", "pos", "ori"):
+                gu.assert_same(k, sc[k].cpu().numpy(), so[k], ctx)
+    gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
