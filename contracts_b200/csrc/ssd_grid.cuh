@@ -587,35 +587,24 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
     return true;
 }
 
-// harvest spawn (harvest_new.py:284-317): neighbour counts read the pre-spawn map
+// harvest spawn (harvest_new.py:284-317): neighbour counts read the pre-spawn map.
+// Every eligible point consumes one draw (by rank), but only a draw below the LARGEST spawn probability (0.05) can spawn
+// whatever the neighbour count is.  So the 3x3 neighbour counts (8 tile reads) are evaluated only for those ~5 % of the
+// eligible points, compacted into a list: one pass of the warp instead of one per 32 points.
 template <int ROUNDS>
 __device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
                                               const uint16_t* sm_apple, const EnvRng& g, uint32_t t)
 {
     const int S = p.S;
     unsigned eligm[ROUNDS];
-    uint32_t mythr[ROUNDS];
     int M = 0;
 #pragma unroll
     for (int q = 0; q < ROUNDS; q++) {
-        mythr[q] = 0; eligm[q] = 0;
+        eligm[q] = 0;
         if (q * 32 < p.n_apple) {
-            int j = lane + 32 * q;
+            const int j = lane + 32 * q;
             bool e = false;
-            if (j < p.n_apple) {
-                int cell = sm_apple[j];
-                uint32_t code = tile[cell];
-                e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE;
-                if (e) {       // j*j + k*k <= APPLE_RADIUS(=2): the 3x3 block; own cell is not 'A'
-                    int cnt = 0;
-#pragma unroll
-                    for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-                        for (int dc = -1; dc <= 1; dc++)
-                            if (dr | dc) cnt += ((tile[cell + dr * S + dc] & CODE_MASK) == C_APPLE);
-                    mythr[q] = p.thr_harvest[cnt < 3 ? cnt : 3];
-                }
-            }
+            if (j < p.n_apple) { const uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE; }
             eligm[q] = __ballot_sync(FULL, e);
             M += __popc(eligm[q]);
         }
@@ -633,17 +622,42 @@ __device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uin
         }
         __syncwarp();                                                  // also orders the tile reads above
     }
-    int base = 0;
-    bool spawned = false;
+    // candidates: point index | draw rank << 16, compacted behind the draws (M <= 256 draws + M <= 256 entries)
+    uint32_t* list = scratch + SCRATCH_DRAWS;
+    const uint32_t thr_max = p.thr_harvest[3];                         // SPAWN_PROB is increasing (harvest_new.py:34)
+    int base = 0, ncand = 0;
 #pragma unroll
     for (int q = 0; q < ROUNDS; q++) {
         if (q * 32 < p.n_apple) {
-            if ((eligm[q] >> lane) & 1u) {
-                int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                if (scratch[r] < mythr[q]) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
-            }
+            const bool el = (eligm[q] >> lane) & 1u;
+            const int r = base + __popc(eligm[q] & lanemask_lt(lane));
+            const bool c = el && scratch[r] < thr_max;
+            const unsigned cm = __ballot_sync(FULL, c);
+            if (c) list[ncand + __popc(cm & lanemask_lt(lane))] = (uint32_t)(lane + 32 * q) | ((uint32_t)r << 16);
+            ncand += __popc(cm);
             base += __popc(eligm[q]);
         }
+    }
+    if (ncand == 0) return false;
+    __syncwarp();
+    // neighbour counts of the candidates on the PRE-spawn map (j*j + k*k <= APPLE_RADIUS(=2): the 3x3 block; the own cell
+    // is not 'A'), decisions first, writes after all of them
+    for (int k = lane; k < ncand; k += 32) {
+        const uint32_t ent = list[k];
+        const int cell = sm_apple[ent & 0xFFFFu];
+        int cnt = 0;
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+            for (int dc = -1; dc <= 1; dc++)
+                if (dr | dc) cnt += ((tile[cell + dr * S + dc] & CODE_MASK) == C_APPLE);
+        list[k] = scratch[ent >> 16] < p.thr_harvest[cnt < 3 ? cnt : 3] ? (uint32_t)cell : 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    bool spawned = false;
+    for (int k = lane; k < ncand; k += 32) {
+        const uint32_t cell = list[k];
+        if (cell != 0xFFFFFFFFu) { tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
     }
     __syncwarp();
     return __any_sync(FULL, spawned);
