@@ -10,13 +10,15 @@
 //   grid_logic_kernel    one THREAD per env, no shared-memory staging: action decode, rotations, moves,
 //                        consume, beams on the env's compact map in global memory (each thread touches a few
 //                        dozen bytes of its own 464-byte map; L1/L2 serve them), then — cleanup — contract
-//                        transfers, rewards, outputs and the record header.  E / 148 = 886 envs per SM fit in
-//                        one wave, so the kernel's time is one thread's dependency chain.
+//                        transfers, rewards, outputs and the record header; the episode accumulators are
+//                        updated with fire-and-forget REDs.  E / 148 = 886 envs per SM fit in one wave, so the
+//                        kernel's time is one thread's dependency chain.
 //                        Envs whose moves are contested (a few %) are resolved by the whole warp, lane =
 //                        agent, with the literal reference ordering (resolve_moves_slow).
-//   grid_obs_kernel      one WARP per env, 24 warps per SM: record prefetch by bulk async copy (double
-//                        buffered), map -> padded tile, spawn scans (ballot ranks), observation gather and
-//                        one bulk async store of the n 15x15x3 windows.  This is the HBM-bound part.
+//   grid_obs_kernel      one WARP per env, 24 warps per SM: the next env's map + header words are prefetched into
+//                        registers while the current env is processed; map -> padded tile, spawn scans (ballot
+//                        ranks, one interleaved two-chain Philox pass), paint, transposed tile, observation gather
+//                        and one bulk async store of the n 15x15x3 windows.  This is the HBM-bound part.
 //   grid_reward_kernel   harvest only: the contract transfer needs total_close_apples of the post-spawn
 //                        map, so transfers / rewards / header run after grid_obs_kernel (thread per env).
 //
@@ -38,7 +40,6 @@
 #ifndef OBS_MAXREG
 #define OBS_MAXREG 80
 #endif
-#define G2_CLAIM 0x01u       // scratch mark in a compact-map byte: cell reserved as a move target
 
 // per-(agent, env) result word
 #define RS_CLEANED_MASK 3u          // bits 0-1  cleaned_squares (0..3)
