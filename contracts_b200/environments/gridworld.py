@@ -42,7 +42,7 @@ class _GridWorldEnv:
         self.num_agents = int(num_agents)
         self.disable_firing, self.image_obs, self.one_hot_id = disable_firing, image_obs, one_hot_id
         self.horizon = int(horizon)
-        self.num_envs, self.seed, self.env_id, self.device = int(num_envs), int(seed), int(env_id), device
+        self.num_envs, self.seed_value, self.env_id, self.device = int(num_envs), int(seed), int(env_id), device
         self.agent_ids = ["a%d" % i for i in range(self.num_agents)]
         self.base_map = np.array([[c.encode() for c in row] for row in self.ascii_map])
         self._make_spaces()
@@ -77,7 +77,7 @@ class _GridWorldEnv:
             c = self._contract or (None, 0.0, 0.0, 0.0)
             self._batch = BatchedGridEnv(self.KIND, self.num_envs, self.num_agents, self.ascii_map, horizon=self.horizon,
                                          contract=c[0], theta_low=c[1], theta_high=c[2], null_prob=c[3],
-                                         seed=self.seed, first_env_id=self.env_id, device=self.device,
+                                         seed=self.seed_value, first_env_id=self.env_id, device=self.device,
                                          use_collective_reward=self.use_collective_reward,
                                          inequity_averse_reward=self.inequity_averse_reward,
                                          alpha=self.alpha, beta=self.beta)
@@ -86,6 +86,21 @@ class _GridWorldEnv:
             except _lib.SsdError:    # the single-kernel fallback (maps > 1 KB) does not record them
                 pass
         return self._batch
+
+    def seed(self, seed=None):
+        """MapEnv.seed (map_env.py:344-345) reseeds NumPy's global generator; here the Philox key of this env's stream.
+        Takes effect at the next reset (the device handle is rebuilt)."""
+        if seed is not None:
+            self.seed_value = int(seed)
+            if self._batch is not None:
+                self._batch.close()
+                self._batch = None
+        return [self.seed_value]
+
+    @property
+    def agent_pos(self):
+        """[[row, col], ...] of the agents in agent order (map_env.py:347-352)."""
+        return self.batch.get_state()["pos"][0].cpu().numpy().tolist()
 
     def _bind_contract(self, name, low, high, null_prob):
         """Called by the contract wrappers: rebuild the device handle with the contract fused in."""

@@ -117,3 +117,17 @@ def test_flat_feature_observations(name):
             ctx = "ep %d step %d" % (ep, t)
             gu.assert_same("obs", np.stack([obs[k] for k in keys]), fx["obs"][ep, t], ctx)
             gu.assert_same("rew", np.array([rew[k] for k in keys]), fx["rew"][ep, t], ctx)
+
+
+def test_seed_and_agent_pos():
+    """env.seed(s) re-keys the env's random stream (MapEnv.seed, map_env.py:344-345); agent_pos lists [row, col] per agent."""
+    from contracts_b200.utils.env_creator_functions import env_creator
+    a = env_creator("HarvestNew", dict(num_agents=4, env_params={}, seed=5))
+    b = env_creator("HarvestNew", dict(num_agents=4, env_params={}, seed=6))
+    oa, ob = a.reset(), b.reset()
+    assert any(not np.array_equal(oa[k]["image"], ob[k]["image"]) for k in oa) or a.agent_pos != b.agent_pos
+    assert b.seed(5) == [5]
+    ob = b.reset()
+    for k in oa:
+        gu.assert_same("image after reseeding", ob[k]["image"], oa[k]["image"], k)
+    assert a.agent_pos == b.agent_pos and len(a.agent_pos) == 4 and len(a.agent_pos[0]) == 2
