@@ -324,8 +324,9 @@ class NegotiationSolver(SeparateContractEnv):
         return {k: self.value_fn(obs[k], k) for k in obs}
 
     def negotiate(self):
-        b = self.base_env.batch
-        params = b.solver_sample(self.num_samples)                       # [E, 1 + S] on the device
+        from ..batched import solver_choose, solver_sample
+        b = self.base_env.batch                                          # any Batched*Env (grid, feature, selfdrive)
+        params = solver_sample(b, self.num_samples)                      # [E, 1 + S] on the device
         cand = params[0].cpu().numpy()
         vals = np.zeros((1, self.num_samples + 1, self.num_agents))
         for c, theta in enumerate(cand):                                  # null contract first (:709-724)
@@ -333,7 +334,7 @@ class NegotiationSolver(SeparateContractEnv):
             vals[0, c] = [v[k] for k in self.agent_ids]
         full = torch.zeros((b.E, self.num_samples + 1, self.num_agents), dtype=torch.float64, device=b.device)
         full[0] = torch.as_tensor(vals[0])
-        best, _ = b.solver_choose(params, full, self.decision_rule)
+        best, _ = solver_choose(b, params, full, self.decision_rule)
         return np.array([best[0].item()], dtype=np.float32)
 
     def reset(self):

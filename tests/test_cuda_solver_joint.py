@@ -269,3 +269,41 @@ def test_joint_env_flat_variant_over_selfdrive():
         if d_s["__all__"]:
             break
     assert t > 5
+
+
+@pytest.mark.parametrize("tag,contract_name,kwargs", [
+    ("SelfDrive", "SelfdriveContractDistprop", dict(num_agents=4)),
+    ("Cleanup", "CleanupContract", dict(num_agents=3, env_params={})),
+    ("Harvest", "HarvestFeaturemodLocalContract", dict(num_agents=3, env_params={})),
+])
+def test_negotiation_solver_over_flat_envs(oracle_lib, tag, contract_name, kwargs):
+    """NegotiationSolver (non-convolutional observations) over the selfdrive and feature envs: the contract it installs is
+    the oracle's choice for the same candidates and values, and it shows up in the observation tail (two_stage_train.py:684-690)."""
+    from contracts_b200.contract import contract_list
+    from contracts_b200.utils.env_creator_functions import env_creator
+    n = kwargs["num_agents"]
+    base = env_creator(tag, dict(seed=31, env_id=9, **kwargs))
+    contract = getattr(contract_list, contract_name)(n)
+    low, high = float(contract.contract_space.low[0]), float(contract.contract_space.high[0])
+    seen = []
+
+    def value_fn(obs, k):                      # depends on the candidate contract only: obs[-2] = theta
+        theta = float(obs[-2]) / high
+        i = int(k[1:])
+        v = np.float64(1.0 + (0.3 + 0.2 * i) * theta - (0.5 + 0.4 * i) * theta * theta)
+        seen.append((float(obs[-2]), i, v))
+        return v
+
+    env = env_creator("NegotiationSolver", dict(base_env=base, contract=contract, num_agents=n, horizon=100, trainer_config={},
+                                                trainer_env=None, trainer_path=None, convolutional=False, shared=True,
+                                                contract_samples=9, decision_rule="majority", value_fn=value_fn))
+    for ep in range(2):
+        seen.clear()
+        obs = env.reset()
+        params = oracle_lib.solver_candidates(31, 9, ep, low, high, 9)
+        vals = np.array([v for _, _, v in seen]).reshape(10, n)
+        gu.assert_same("candidates seen by the value function", np.array([t for t, i, _ in seen if i == 0]), params, "ep %d" % ep)
+        want, _ = oracle_lib.solver_choose(params, vals, "majority")
+        gu.assert_same("chosen contract", np.float64(env.contract_param[0]), want, "ep %d" % ep)
+        for k in obs:
+            gu.assert_same("observation tail", obs[k][-2:], np.array([want, 0.0]), "ep %d %s" % (ep, k))
