@@ -25,6 +25,17 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def negotiate(batch, proposals, accept):
+    """Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281) for every env of `batch` (any
+    Batched*Env): proposals [E], accept [E, n] float64.  Sets each env's contract parameter; returns uint8 [E]."""
+    proposals = torch.as_tensor(proposals, dtype=torch.float64, device=batch.device).expand(batch.E).contiguous()
+    accept = torch.as_tensor(accept, dtype=torch.float64, device=batch.device).expand(batch.E, batch.n).contiguous()
+    dec = torch.empty((batch.E,), dtype=torch.uint8, device=batch.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(batch.device).cuda_stream)
+    _lib.check(batch._h, batch.lib.ssd_negotiate(batch._h, _ptr(proposals), _ptr(accept), _ptr(dec), stream))
+    return dec
+
+
 def solver_sample(batch, num_samples):
     """Candidate contracts of NegotiationSolver.negotiate (two_stage_train.py:705-746) for every env of `batch` (any
     Batched*Env): float64 [E, 1 + num_samples], column 0 = the null contract, the others float32-valued samples."""

@@ -501,12 +501,11 @@ __global__ void get_metrics_kernel(GridParams p, double* out)
 }
 
 // SeparateContractNegotiateStage.step, agreement stage (two_stage_train.py:266-281)
-__global__ void negotiate_kernel(GridParams p, const double* proposals, const double* accept, uint8_t* decision)
+__global__ void negotiate_kernel(SolverParams p, const double* proposals, const double* accept, uint8_t* decision)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
-    const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+    const uint32_t episode = *reinterpret_cast<const uint32_t*>(p.episode + (size_t)env * p.episode_stride) & p.episode_mask;
     const uint32_t env_id = p.first_env_id + (uint32_t)env;
     const int n = p.n;
     double prod = 1.0;
@@ -525,7 +524,7 @@ __global__ void negotiate_kernel(GridParams p, const double* proposals, const do
     }
     double r = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0, SITE_NEGOTIATE, 1, 0), 1.0 / 4294967296.0);
     bool dec = r < prod;
-    *reinterpret_cast<double*>(hdr + RO_THETA) = dec ? proposals[env] : 0.0;
+    *reinterpret_cast<double*>(p.theta + (size_t)env * p.theta_stride) = dec ? proposals[env] : 0.0;
     if (decision) decision[env] = dec ? 1 : 0;
 }
 
@@ -755,11 +754,12 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
     return check_launch(h, "set_contract_params");
 }
 
+static SolverParams solver_params(ssd_handle* h);
 int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev, void* stream)
 {
     if (!h || !proposals_dev || !accept_dev) return SSD_EINVAL;
-    REQUIRE_GRID(h);
-    SMALL_LAUNCH(negotiate_kernel, proposals_dev, accept_dev, decision_dev);
+    const SolverParams sp = solver_params(h);            // every env kind: episode / theta addressed by (pointer, stride)
+    negotiate_kernel<<<(sp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sp, proposals_dev, accept_dev, decision_dev);
     return check_launch(h, "negotiate");
 }
 

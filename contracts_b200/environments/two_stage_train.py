@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import spaces
+from ..batched import negotiate
 
 _FUSED = ("CleanupContract", "HarvestFeaturemodLocalContract", "SelfdriveContractDistprop")
 
@@ -149,7 +150,7 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
             infos = {k: {} for k in self.agent_ids}
         elif self.contract_state["a0"] == 3:
             accept = torch.tensor([[float(acts[k][-1]) for k in self.agent_ids]], dtype=torch.float64)
-            dec = b.negotiate(torch.tensor([float(self.params["a0"][0])], dtype=torch.float64), accept)
+            dec = negotiate(b, torch.tensor([float(self.params["a0"][0])], dtype=torch.float64), accept)
             decision = int(dec[0].item())
             self._metrics["accepted"] = decision
             for k in self.agent_ids:
@@ -159,12 +160,15 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
             dones = {"__all__": True}
             infos = {k: {} for k in self.agent_ids}
             if self.policy is None:
+                if not hasattr(self.base_env, "image_obs"):
+                    raise NotImplementedError("the random-action subgame rollout exists for the grid worlds; pass policy=...")
                 rews, infos = self._random_rollout(rews, infos)
             else:
                 env_done, steps = False, 0
+                active = list(self.agent_ids)            # agents that finished stop acting (selfdrive; :286,325-333)
                 while not env_done and steps < self.horizon:
                     act_dict = {}
-                    for k in self.agent_ids:
+                    for k in active:
                         if self.convolutional:
                             o = self.obs[k]
                             o.update({"contract": np.concatenate((self.params[k], np.array([0])))})
@@ -172,11 +176,12 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
                             o = np.concatenate((self.obs[k], self.params[k], np.array([0])))
                         act_dict[k] = self.policy(o, k)
                     _, env_rews, env_dones, infos = super().step(act_dict)
-                    self.last_seen_obs = {k: self.obs[k] for k in self.agent_ids}
+                    self.last_seen_obs = {k: self.obs[k] if k in self.obs else self.last_seen_obs[k] for k in self.agent_ids}
                     env_done = env_dones["__all__"]
                     steps += 1
-                    for k in self.agent_ids:
+                    for k in active:
                         rews[k] += env_rews[k]
+                    active = [k for k in active if not env_dones.get(k, False)]
         else:
             raise RuntimeError("negotiation episode is over: call reset()")
         saved_obs = self.obs

@@ -134,7 +134,7 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
 /* Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281):
  * proposals_dev double [E] (a0's action[:-1]), accept_dev double [E][n] (each agent's action[-1]),
  * decision_dev uint8 [E] out.  Chooses 2 of agents 1..n-1 when n > 3, multiplies their accept
- * values, draws once and keeps the proposal as theta or zeroes it. */
+ * values, draws once and keeps the proposal as theta or zeroes it.  Every env kind. */
 int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev,
                   void* stream);
 

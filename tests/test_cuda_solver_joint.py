@@ -307,3 +307,51 @@ def test_negotiation_solver_over_flat_envs(oracle_lib, tag, contract_name, kwarg
         gu.assert_same("chosen contract", np.float64(env.contract_param[0]), want, "ep %d" % ep)
         for k in obs:
             gu.assert_same("observation tail", obs[k][-2:], np.array([want, 0.0]), "ep %d %s" % (ep, k))
+
+
+def test_negotiate_every_env_kind_matches_oracle(oracle_lib):
+    """ssd_negotiate on feature / selfdrive handles: the agreement draw depends only on (seed, env id, episode), so the
+    grid oracle with the same keys gives the expected decisions; theta = proposal or 0 (two_stage_train.py:266-281)."""
+    import torch
+    from contracts_b200.batched import negotiate
+    from contracts_b200.features import BatchedFeatureEnv
+    from contracts_b200.maps import CLEANUP_MAP
+    from contracts_b200.selfdrive import BatchedCarEnv
+    E = 500
+    rng = np.random.RandomState(3)
+    for n, make in ((5, lambda: BatchedCarEnv(E, 5, contract="SelfdriveContractDistprop", seed=77, first_env_id=1000)),
+                    (3, lambda: BatchedFeatureEnv("cleanup", E, 3, contract="CleanupContract", seed=77, first_env_id=1000)),
+                    (8, lambda: BatchedFeatureEnv("harvest", E, 8, contract="HarvestFeaturemodLocalContract", seed=77, first_env_id=1000))):
+        env = make()
+        orc = oracle_lib.GridOracle("cleanup", E, n, CLEANUP_MAP, contract="CleanupContract", seed=77, first_env_id=1000)
+        for ep in range(2):
+            env.reset(); orc.reset()
+            prop = rng.uniform(0, 0.2, size=E)
+            acc = rng.uniform(0.3, 1.0, size=(E, n))
+            dec = negotiate(env, torch.as_tensor(prop), torch.as_tensor(acc)).cpu().numpy()
+            want = orc.negotiate(prop, acc)
+            gu.assert_same("decisions", dec, want, "%s ep %d" % (type(env).__name__, ep))
+            assert 0 < dec.sum() < E
+            theta = env.get_state()["theta"].cpu().numpy()
+            gu.assert_same("theta", theta, np.where(want == 1, prop, 0.0), "%s ep %d" % (type(env).__name__, ep))
+
+
+def test_negotiate_stage_dict_api_over_selfdrive():
+    """ContractWrapperNegotiate over the selfdrive env with a scripted frozen policy: propose -> agree -> rollout."""
+    from contracts_b200.contract import contract_list
+    from contracts_b200.utils.env_creator_functions import env_creator
+    n = 3
+    base = env_creator("SelfDrive", dict(num_agents=n, seed=8, env_id=2))
+    env = env_creator("ContractWrapperNegotiate", dict(
+        base_env=base, contract=contract_list.SelfdriveContractDistprop(n), num_agents=n, horizon=400, convolutional=False,
+        policy=lambda obs, k: np.array([0.1], dtype=np.float32)))
+    keys = ["a%d" % i for i in range(n)]
+    obs = env.reset()
+    assert all(obs[k][-1] == 2 for k in keys)                           # negotiation state flag (two_stage_train.py:246-255)
+    acts = {k: np.array([50.0, 1.0]) for k in keys}                     # proposal 50, everybody accepts
+    obs, rew, done, info = env.step(acts)
+    assert done == {"__all__": False} and all(obs[k][-1] == 3 for k in keys)
+    obs, rew, done, info = env.step(acts)
+    assert done["__all__"] and env.metrics["accepted"] == 1
+    assert all(np.isfinite(rew[k]) and rew[k] < 0 for k in keys)        # -1 (-100 for the ambulance) per step until all passed
+    assert rew["a0"] < rew["a1"]
