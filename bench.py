@@ -63,31 +63,33 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
 
+    def _nvml_sample(self):
+        nv, h = self.nv, self.nvml_handle
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        r = int(self.get_reasons(h))
+        self.rows.append([str(sm), str(self.mx), "0"] + ["Active" if r & b else "Not Active" for _, b in self.bits])
+
     def _nvml_loop(self):
-        import pynvml as nv
-        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
-                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
-                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
-                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
-        bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        h = self.nvml_handle
-        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        while not self.stop_flag.is_set():
-            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-            r = int(get_reasons(h))
-            self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for _, b in bits])
-            self.stop_flag.wait(0.005)
+        while not self.stop_flag.wait(0.005):
+            self._nvml_sample()
 
     def start(self):
-        """NVML polled every 5 ms from a thread (the timed region can be shorter than one nvidia-smi period);
-        nvidia-smi -lms as the fallback."""
+        """NVML polled every 5 ms from a thread (the timed region can be shorter than one nvidia-smi period), first
+        sample taken synchronously, last one at stop(); nvidia-smi -lms as the fallback."""
         try:
             import pynvml as nv
             nv.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            self.nvml_handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.nvml_handle = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                     ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                     ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+            self.bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.nvml_handle, nv.NVML_CLOCK_SM))
+            self._nvml_sample()
             self.stop_flag = threading.Event()
             self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
@@ -116,6 +118,11 @@ class ClockSampler:
         if self.proc == "nvml":
             self.stop_flag.set()
             self.thread.join(timeout=1.0)
+            try:
+                if len(self.rows) < 3:               # a region shorter than two polling periods
+                    self._nvml_sample()
+            except Exception:
+                pass
         else:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -260,8 +267,8 @@ def main():
     # The inner loop (action generation + step) is launch-bound from Python, so GRAPH_STEPS consecutive steps are
     # captured once in a CUDA graph and replayed; episode boundaries (reset + negotiation prologue + statistics
     # all-gather) stay outside the graph.  Fresh actions every replay come from the handle's device step counter.
-    G = args.graph_steps
-    while HORIZON % G:
+    G = max(1, args.graph_steps)
+    while HORIZON % G or K % G:                                  # the timed region is EXACTLY K steps: G divides K
         G -= 1
     for _ in range(max(W, 3)):
         one_step()
