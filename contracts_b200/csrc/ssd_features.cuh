@@ -170,13 +170,22 @@ __device__ __forceinline__ void feat_spawn(const FeatParams& p, int env, uint32_
 // closest point of a list to each agent: smallest (L1 distance, birth stamp)  (np.argmin over the list in birth order).
 // One key per (point, agent): distance << 24 | birth stamp << 8 | point index, so the search is a running minimum —
 // no data-dependent stamp loads on ties (the stamp of every live point is read once, coalesced across the warp's
-// envs: stamp[i][env]).  Distances are < 256, stamps 16 bits, indices < 256 (FEAT_MASK_WORDS * 32).
+// envs: stamp[i][env]).  The L1 distances of a point to four agents at a time come from two VABSDIFF4.U8 (rows, columns:
+// agents packed one per byte) and one add; distances are < 256, stamps 16 bits, indices < 256 (FEAT_MASK_WORDS * 32).
 __device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32_t* mask, int npts, const uint16_t* rc,
                                              const uint16_t* stamp, const uint32_t* pos, uint32_t* out_rc /* [MAXN] */)
 {
-    uint32_t best[SSD_MAXN]; int ar[SSD_MAXN], ac[SSD_MAXN];
+    uint32_t best[SSD_MAXN];
+    uint32_t ar[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu }, ac[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu };     // absent agents: (127, 127), no byte carry
 #pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) { best[a] = 0xFFFFFFFFu; ar[a] = (int)(pos[a] & 255u); ac[a] = (int)((pos[a] >> 8) & 255u); }
+    for (int a = 0; a < SSD_MAXN; a++) {
+        best[a] = 0xFFFFFFFFu;
+        if (a < n) {
+            const uint32_t sh = 8u * (a & 3);
+            ar[a >> 2] = (ar[a >> 2] & ~(0xFFu << sh)) | ((pos[a] & 255u) << sh);
+            ac[a >> 2] = (ac[a >> 2] & ~(0xFFu << sh)) | (((pos[a] >> 8) & 255u) << sh);
+        }
+    }
     const int nw = (npts + 31) >> 5;
     for (int w = 0; w < nw; w++) {
         uint32_t m = mask[w * FEAT_THREADS];
@@ -185,12 +194,13 @@ __device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32
             const int i = w * 32 + b;
             const uint32_t prc = __ldg(rc + i);
             const uint32_t base = ((uint32_t)stamp[(size_t)i * E + env] << 8) | (uint32_t)i;
-            const int pr = (int)(prc >> 8), pc = (int)(prc & 255u);
+            const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
+            const uint32_t d[2] = { __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]), __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]) };
 #pragma unroll
             for (int a = 0; a < SSD_MAXN; a++) {
                 if (a >= n) continue;
-                const uint32_t d = (uint32_t)(abs(pr - ar[a]) + abs(pc - ac[a]));
-                best[a] = min(best[a], (d << 24) | base);
+                const uint32_t key = __byte_perm(d[a >> 2], 0u, 0x0444u | ((uint32_t)(a & 3) << 12)) | base;   // distance -> byte 3
+                best[a] = min(best[a], key);
             }
         }
     }
