@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
 
-SSD_ABI_VERSION = 2
+SSD_ABI_VERSION = 3
 ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "selfdrive": 4}
 CONTRACT_KIND = {None: 0, "CleanupContract": 1, "HarvestFeaturemodLocalContract": 2,
                  "SelfdriveContractDistprop": 3}
@@ -26,7 +26,7 @@ class SsdError(RuntimeError):
 
 class ssd_config(ctypes.Structure):
     _fields_ = [
-        ("abi_version", ctypes.c_int32), ("env_kind", ctypes.c_int32), ("num_envs", ctypes.c_int32),
+        ("abi_version", ctypes.c_int32), ("struct_size", ctypes.c_int32), ("env_kind", ctypes.c_int32), ("num_envs", ctypes.c_int32),
         ("num_agents", ctypes.c_int32), ("map_h", ctypes.c_int32), ("map_w", ctypes.c_int32),
         ("ascii_map", ctypes.c_char_p), ("horizon", ctypes.c_int32), ("contract_kind", ctypes.c_int32),
         ("theta_low", ctypes.c_double), ("theta_high", ctypes.c_double), ("null_prob", ctypes.c_double),
@@ -41,6 +41,35 @@ class ssd_step_io(ctypes.Structure):
         ("rew_dev", ctypes.c_void_p), ("base_rew_dev", ctypes.c_void_p), ("transfers_dev", ctypes.c_void_p),
         ("info_dev", ctypes.c_void_p), ("feature_obs_dev", ctypes.c_void_p), ("done_dev", ctypes.c_void_p),
     ]
+
+
+class ssd_host_layout(ctypes.Structure):
+    _fields_ = [
+        ("total_bytes", ctypes.c_int64), ("count_offset", ctypes.c_int64), ("done_offset", ctypes.c_int64),
+        ("rew_i8_offset", ctypes.c_int64), ("records_offset", ctypes.c_int64), ("record_bytes", ctypes.c_int32),
+        ("record_capacity", ctypes.c_int32),
+    ]
+
+
+STATS_LEN = 8
+
+
+def resolve_device(device):
+    """torch.device with an explicit index ('cuda' / None mean torch's CURRENT device, not GPU 0).  The C entry points
+    switch to the handle's device themselves (and restore the caller's), so a handle on cuda:1 works whatever the
+    current device is; streams are always taken from that device."""
+    import torch
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise SsdError("contracts_b200 needs a CUDA device, got %r (there is no CPU fallback)" % (device,))
+    return device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def make_config(**kw):
+    """ssd_config with abi_version / struct_size filled in."""
+    return ssd_config(abi_version=SSD_ABI_VERSION, struct_size=ctypes.sizeof(ssd_config), **kw)
 
 
 class ssd_selfdrive_io(ctypes.Structure):
@@ -60,6 +89,7 @@ EXPORTS = [
     "ssd_kernel_launches", "ssd_enable_timing", "ssd_get_step_times", "ssd_selfdrive_reset", "ssd_selfdrive_step", "ssd_selfdrive_get_state",
     "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
     "ssd_global_view", "ssd_concat_obs", "ssd_solver_sample", "ssd_solver_choose", "ssd_policy_inputs", "ssd_record_beams", "ssd_render", "ssd_step_host",
+    "ssd_step_host_async", "ssd_step_host_wait", "ssd_host_result_layout", "ssd_host_result_expand", "ssd_set_episode_stats",
 ]
 
 _LIB = None
@@ -84,7 +114,12 @@ def load():
     L.ssd_reset.argtypes = [vp, vp, vp, i64, vp]
     L.ssd_step.argtypes = [vp, ctypes.POINTER(ssd_step_io), vp]
     L.ssd_set_contract_params.argtypes = [vp, vp, vp]
-    L.ssd_negotiate.argtypes = [vp, vp, vp, vp, vp]
+    L.ssd_negotiate.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ssd_step_host_async.argtypes = [vp, ctypes.POINTER(ssd_step_io), vp, vp, ctypes.POINTER(i64), vp]
+    L.ssd_step_host_wait.argtypes = [vp, i64]
+    L.ssd_host_result_layout.argtypes = [vp, ctypes.POINTER(ssd_host_layout)]
+    L.ssd_host_result_expand.argtypes = [vp, vp, vp]
+    L.ssd_set_episode_stats.argtypes = [vp, vp]
     L.ssd_get_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ssd_set_state.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ssd_get_metrics.argtypes = [vp, vp, vp]

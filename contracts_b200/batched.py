@@ -25,14 +25,23 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def negotiate(batch, proposals, accept):
+def negotiate(batch, proposals, accept, mask=None, out=None):
     """Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281) for every env of `batch` (any
-    Batched*Env): proposals [E], accept [E, n] float64.  Sets each env's contract parameter; returns uint8 [E]."""
-    proposals = torch.as_tensor(proposals, dtype=torch.float64, device=batch.device).expand(batch.E).contiguous()
-    accept = torch.as_tensor(accept, dtype=torch.float64, device=batch.device).expand(batch.E, batch.n).contiguous()
-    dec = torch.empty((batch.E,), dtype=torch.uint8, device=batch.device)
+    Batched*Env): proposals [E], accept [E, n] float64.  Sets each env's contract parameter; returns uint8 [E].
+    mask (uint8 [E], optional): only the envs with mask != 0 negotiate (the ones that were just reset); the decision
+    bytes of the others are left as they are in `out`."""
+    def ready(x, shape):                                  # the hot caller passes tensors that need no conversion
+        return torch.is_tensor(x) and x.dtype == torch.float64 and x.device == batch.device and tuple(x.shape) == shape \
+            and x.is_contiguous()
+    if not ready(proposals, (batch.E,)):
+        proposals = torch.as_tensor(proposals, dtype=torch.float64, device=batch.device).expand(batch.E).contiguous()
+    if not ready(accept, (batch.E, batch.n)):
+        accept = torch.as_tensor(accept, dtype=torch.float64, device=batch.device).expand(batch.E, batch.n).contiguous()
+    if mask is not None and (mask.dtype != torch.uint8 or mask.device != batch.device or not mask.is_contiguous()):
+        mask = mask.to(device=batch.device, dtype=torch.uint8).contiguous()
+    dec = out if out is not None else (torch.empty if mask is None else torch.zeros)((batch.E,), dtype=torch.uint8, device=batch.device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(batch.device).cuda_stream)
-    _lib.check(batch._h, batch.lib.ssd_negotiate(batch._h, _ptr(proposals), _ptr(accept), _ptr(dec), stream))
+    _lib.check(batch._h, batch.lib.ssd_negotiate(batch._h, _ptr(mask), _ptr(proposals), _ptr(accept), _ptr(dec), stream))
     return dec
 
 
@@ -61,6 +70,36 @@ def solver_choose(batch, params, vals, rule="majority"):
     return best, idx
 
 
+class HostResult:
+    """One pinned result block of `ssd_step_host_async` with numpy views of its fields (valid after step_host_wait):
+    count (records in use), done uint8 [E], rew_i8 int8 [E, n], rec_env int32 [E], rec_rew float64 [E, n]."""
+
+    def __init__(self, batch):
+        lay = batch.host_result_layout()
+        self.batch, self.lay = batch, lay
+        self.block = torch.zeros((lay.total_bytes,), dtype=torch.uint8).pin_memory()
+        b = self.block.numpy()
+        E, n = batch.E, batch.n
+        self._count = b[lay.count_offset:lay.count_offset + 4].view(np.uint32)
+        self.done = b[lay.done_offset:lay.done_offset + E]
+        self.rew_i8 = b[lay.rew_i8_offset:lay.rew_i8_offset + E * n].view(np.int8).reshape(E, n)
+        rec = b[lay.records_offset:lay.records_offset + E * lay.record_bytes].reshape(E, lay.record_bytes)
+        self.rec_env = rec[:, 0:4].view(np.int32).reshape(E)
+        self.rec_rew = rec[:, 8:].view(np.float64).reshape(E, n)
+
+    @property
+    def count(self):
+        return int(self._count[0])
+
+    def rewards(self, out=None):
+        """dense float64 [E, n] (ssd_host_result_expand: int8 rewards widened, the exact records on top)"""
+        if out is None:
+            out = np.empty((self.batch.E, self.batch.n), dtype=np.float64)
+        _lib.check(self.batch._h, self.batch.lib.ssd_host_result_expand(self.batch._h, ctypes.c_void_p(self.block.data_ptr()),
+                                                                         out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+
 class BatchedGridEnv:
     """E environments of one kind on one device.
 
@@ -80,7 +119,7 @@ class BatchedGridEnv:
             raise _lib.SsdError("CUDA device required: contracts_b200 has no CPU fallback")
         self.lib = _lib.load()
         self.kind, self.E, self.n = kind, int(num_envs), int(num_agents)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = _lib.resolve_device(device)
         self.ascii_map = list(ascii_map) if ascii_map is not None else (
             CLEANUP_MAP if kind == "cleanup_new" else HARVEST_MAP)
         self.H, self.W = len(self.ascii_map), len(self.ascii_map[0])
@@ -94,19 +133,18 @@ class BatchedGridEnv:
         self.theta_high = float(np.float32(theta_high))
         self.seed, self.first_env_id = int(seed) & 0xFFFFFFFF, int(first_env_id) & 0xFFFFFFFF
         self._flat = "".join(self.ascii_map).encode("ascii")
-        cfg = _lib.ssd_config(
-            abi_version=_lib.SSD_ABI_VERSION, env_kind=_lib.ENV_KIND[kind], num_envs=self.E, num_agents=self.n,
+        cfg = _lib.make_config(
+            env_kind=_lib.ENV_KIND[kind], num_envs=self.E, num_agents=self.n,
             map_h=self.H, map_w=self.W, ascii_map=self._flat, horizon=self.horizon,
             contract_kind=_lib.CONTRACT_KIND[contract], theta_low=self.theta_low, theta_high=self.theta_high,
             null_prob=float(null_prob), seed=self.seed, first_env_id=self.first_env_id,
-            device=self.device.index or 0,
+            device=self.device.index,
             # MapEnv reward shaping kwargs (map_env.py:69-72,289-301)
             flags=(_lib.FLAG_COLLECTIVE_REWARD if use_collective_reward else 0)
             | (_lib.FLAG_INEQUITY_AVERSE if inequity_averse_reward else 0))
         cfg.env_params[0], cfg.env_params[1] = float(alpha), float(beta)
         h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
+        _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
         self.F = self.lib.ssd_feature_dim(self._h)
         E, n, dev = self.E, self.n, self.device
@@ -189,12 +227,48 @@ class BatchedGridEnv:
         io.info_dev = self.info.data_ptr()
         io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
         io.done_dev = self.done.data_ptr()
-        with torch.cuda.device(self.device):          # the library creates its copy stream on the current device
-            _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
-                                                       ctypes.c_void_p(rew_host.data_ptr()),
-                                                       ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
-                                                       self._stream()))
+        _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                   ctypes.c_void_p(rew_host.data_ptr()),
+                                                   ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
+                                                   self._stream()))
         return self.obs, rew_host, done_host
+
+    # ---- pipelined host-buffer step (RLlib BaseEnv send_actions / poll shape) ---------------------------------
+    def host_result_layout(self):
+        lay = _lib.ssd_host_layout()
+        _lib.check(self._h, self.lib.ssd_host_result_layout(self._h, ctypes.byref(lay)))
+        return lay
+
+    def new_host_result(self):
+        """A pinned host block for step_host_async + numpy views of its fields (`HostResult`)."""
+        return HostResult(self)
+
+    def step_host_async(self, actions_host, result, want_features=False, dense_rewards=False):
+        """Submit one step with HOST actions (pinned uint8 [E, n]); returns a ticket without synchronising.  The
+        compact result block (int8 rewards + exact float64 records + dones) is copied into `result` (a HostResult)
+        while the observe kernel runs; `step_host_wait(ticket)` makes it valid.  At most two steps in flight.
+        dense_rewards=True also writes the float64 [E, n] matrix to self.rew on the device."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous():
+            raise ValueError("step_host_async needs a contiguous CPU uint8 tensor [E, n] (pinned for an asynchronous copy)")
+        if want_features and self.feature_obs is None:
+            self.feature_obs = torch.zeros((self.E, self.n, self.F), dtype=torch.float64, device=self.device)
+        io = self._io
+        io.actions_dev = None
+        io.obs_dev = self._obs_buf.data_ptr()
+        io.obs_env_stride = self.obs_stride
+        io.rew_dev = self.rew.data_ptr() if dense_rewards else None
+        io.base_rew_dev = None
+        io.transfers_dev = None
+        io.info_dev = self.info.data_ptr()
+        io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
+        io.done_dev = self.done.data_ptr()
+        ticket = ctypes.c_int64(-1)
+        _lib.check(self._h, self.lib.ssd_step_host_async(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                         ctypes.c_void_p(result.block.data_ptr()), ctypes.byref(ticket), self._stream()))
+        return ticket.value
+
+    def step_host_wait(self, ticket):
+        _lib.check(self._h, self.lib.ssd_step_host_wait(self._h, int(ticket)))
 
     def random_actions(self, step_index, num_actions, out=None):
         """Uniform random actions; step_index=None uses the handle's device-side counter (CUDA-graph friendly)."""
@@ -210,13 +284,19 @@ class BatchedGridEnv:
         theta = torch.as_tensor(theta, dtype=torch.float64, device=self.device).expand(self.E).contiguous()
         _lib.check(self._h, self.lib.ssd_set_contract_params(self._h, _ptr(theta), self._stream()))
 
-    def negotiate(self, proposals, accept):
+    def negotiate(self, proposals, accept, mask=None, out=None):
         """Agreement stage (two_stage_train.py:266-281).  proposals [E], accept [E, n] float64.  Returns uint8 [E]."""
-        proposals = torch.as_tensor(proposals, dtype=torch.float64, device=self.device).expand(self.E).contiguous()
-        accept = torch.as_tensor(accept, dtype=torch.float64, device=self.device).expand(self.E, self.n).contiguous()
-        dec = torch.empty((self.E,), dtype=torch.uint8, device=self.device)
-        _lib.check(self._h, self.lib.ssd_negotiate(self._h, _ptr(proposals), _ptr(accept), _ptr(dec), self._stream()))
-        return dec
+        return negotiate(self, proposals, accept, mask, out)
+
+    def set_episode_stats(self, stats):
+        """stats: float64 CUDA tensor [8] (zeroed by the caller) or None.  While set, every reset() adds the accumulators
+        of the finished episodes it replaces: apples_eaten, raw_env_rewards, transfers, dirt_cleaned, sum of transferred
+        rewards, sum of raw rewards, episodes, max err_flags (sharding.STAT_FIELDS with `envs` = episodes)."""
+        if stats is not None and (stats.dtype != torch.float64 or stats.device != self.device or stats.numel() != _lib.STATS_LEN
+                                  or not stats.is_contiguous()):
+            raise ValueError("stats must be a contiguous float64 CUDA tensor of %d elements on %s" % (_lib.STATS_LEN, self.device))
+        self._stats = stats                              # keep it alive while the library holds its address
+        _lib.check(self._h, self.lib.ssd_set_episode_stats(self._h, _ptr(stats)))
 
     # ---- JointEnv output layouts (two_stage_train.py:476-617) ---------------------------------------
     def global_view(self, out=None):

@@ -39,7 +39,17 @@ struct ssd_handle {
     uint8_t* d_beam;         // ssd_record_beams: [E][map_bytes] beam overlay of the last step
     cudaStream_t side;       // ssd_step_host: copy stream + its events (created on first use)
     cudaEvent_t ev_rew, ev_copied;
-    uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO
+    // ssd_step_host_async: two slots, each with a device action buffer and a device result block
+    struct Slot {
+        uint8_t* d_actions; uint8_t* d_block;
+        cudaEvent_t ev_up, ev_rew, ev_copied, ev_logic;
+        void* host_block; int64_t ticket; bool busy; uint32_t copied_records;
+    } slot[2];
+    cudaStream_t s_in, s_out;
+    int64_t next_ticket;
+    uint32_t recent_count[2];
+    ssd_host_layout lay;
+    uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO: [0] index, [1] CTAs finished
     bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
     int64_t launches;
     char err[512];
@@ -87,6 +97,18 @@ static int fail(ssd_handle* h, int code, const char* fmt, ...)
     } while (0)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Every entry point runs on the handle's device whatever the caller's current device is, and leaves the caller's
+// current device as it found it.
+struct DeviceGuard {
+    int prev; bool switched;
+    explicit DeviceGuard(int dev) : prev(-1), switched(false)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h) DeviceGuard device_guard_((h)->cfg.device)
 
 // ceil(p * 2^32) clamped: (u32 * 2^-32 < p) <=> (u32 < T)
 static uint32_t prob_threshold(double p)
@@ -501,10 +523,11 @@ __global__ void get_metrics_kernel(GridParams p, double* out)
 }
 
 // SeparateContractNegotiateStage.step, agreement stage (two_stage_train.py:266-281)
-__global__ void negotiate_kernel(SolverParams p, const double* proposals, const double* accept, uint8_t* decision)
+__global__ void negotiate_kernel(SolverParams p, const uint8_t* mask, const double* proposals, const double* accept, uint8_t* decision)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
+    if (mask && !mask[env]) return;
     const uint32_t episode = *reinterpret_cast<const uint32_t*>(p.episode + (size_t)env * p.episode_stride) & p.episode_mask;
     const uint32_t env_id = p.first_env_id + (uint32_t)env;
     const int n = p.n;
@@ -528,22 +551,26 @@ __global__ void negotiate_kernel(SolverParams p, const double* proposals, const 
     if (decision) decision[env] = dec ? 1 : 0;
 }
 
-// step_index == SSD_STEP_AUTO: take the index from the handle's device counter (bumped by a follow-up
-// one-thread kernel), so that a captured CUDA graph draws fresh actions at every replay
-__global__ void counter_bump_kernel(uint32_t* counter) { *counter += 1u; }
-
-__global__ void random_actions_kernel(GridParams p, uint32_t step_index, const uint32_t* counter, int num_actions, uint8_t* actions)
+// step_index == SSD_STEP_AUTO: take the index from the handle's device counter (bumped by the last CTA to finish,
+// counter_finish in ssd_common.cuh), so that a captured CUDA graph draws fresh actions at every replay
+__global__ void random_actions_kernel(GridParams p, uint32_t step_index, uint32_t* counter, int num_actions, uint8_t* actions)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= p.E) return;
-    if (counter) step_index = *counter;
-    const uint32_t env_id = p.first_env_id + (uint32_t)env;
-    for (int b = 0; b * 4 < p.n; b++) {
-        Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
-        uint32_t w[4] = { q.x, q.y, q.z, q.w };
-        for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
-            actions[(size_t)env * p.n + b * 4 + j] = (uint8_t)(((uint64_t)w[j] * (uint32_t)num_actions) >> 32);
+    if (counter) step_index = *reinterpret_cast<volatile uint32_t*>(counter);
+    if (env < p.E) {
+        const uint32_t env_id = p.first_env_id + (uint32_t)env;
+        uint32_t packed[2] = { 0u, 0u };
+        for (int b = 0; b * 4 < p.n; b++) {
+            Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
+            uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
+                packed[b] |= (uint32_t)(((uint64_t)w[j] * (uint32_t)num_actions) >> 32) << (8 * j);
+        }
+        uint8_t* dst = actions + (size_t)env * p.n;
+        if (p.n == 8 && (reinterpret_cast<uintptr_t>(actions) & 7u) == 0) *reinterpret_cast<uint2*>(dst) = make_uint2(packed[0], packed[1]);
+        else for (int a = 0; a < p.n; a++) dst[a] = (uint8_t)(packed[a >> 2] >> (8 * (a & 3)));
     }
+    if (counter) counter_finish(counter, step_index);
 }
 
 // =============================================================================================
@@ -564,6 +591,9 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     if (!cfg || !out) return fail(nullptr, SSD_EINVAL, "null argument");
     *out = nullptr;
     if (cfg->abi_version != SSD_ABI_VERSION) return fail(nullptr, SSD_EINVAL, "abi_version %d != %d", cfg->abi_version, SSD_ABI_VERSION);
+    if (cfg->struct_size != (int32_t)sizeof(ssd_config))
+        return fail(nullptr, SSD_EINVAL, "ssd_config.struct_size %d != %d: the caller's declaration of ssd_config is out of date",
+                    cfg->struct_size, (int)sizeof(ssd_config));
     if (cfg->num_envs < 1) return fail(nullptr, SSD_EINVAL, "num_envs must be >= 1");
     if (cfg->num_agents < 1 || cfg->num_agents > SSD_MAX_AGENTS) return fail(nullptr, SSD_EINVAL, "num_agents must be in [1, %d]", SSD_MAX_AGENTS);
     if (cfg->env_kind < SSD_ENV_CLEANUP || cfg->env_kind > SSD_ENV_SELFDRIVE)
@@ -581,10 +611,17 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(nullptr, SSD_ECUDA, "no CUDA device available (this library has no CPU fallback)");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SSD_EINVAL, "device %d out of range", cfg->device);
-    cudaError_t e = cudaSetDevice(cfg->device);
-    if (e != cudaSuccess) return fail(nullptr, SSD_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     ssd_handle* h = new ssd_handle();
     h->cfg = *cfg;
+    ON_DEVICE(h);                                       // restores the caller's current device on return
+    {
+        int cur = -1;
+        cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess || cur != cfg->device) {
+            delete h;
+            return fail(nullptr, SSD_ECUDA, "cudaSetDevice(%d) failed: %s", cfg->device, cudaGetErrorString(e));
+        }
+    }
     h->launches = 0;
     h->timing = false;
     h->tev[0] = h->tev[1] = h->tev[2] = nullptr;
@@ -593,7 +630,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
     h->cfg.ascii_map = h->ascii.c_str();
     const bool is_feat = cfg->env_kind == SSD_ENV_CLEANUP_FEATURES || cfg->env_kind == SSD_ENV_HARVEST_FEATURES;
     int rc = cfg->env_kind == SSD_ENV_SELFDRIVE ? setup_selfdrive(h) : (is_feat ? setup_features(h) : setup_grid(h));
-    if (rc == SSD_OK) rc = dev_zalloc(h, 1, &h->d_counter);
+    if (rc == SSD_OK) rc = dev_zalloc(h, 2, &h->d_counter);
     if (rc != SSD_OK) {
         snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
         ssd_destroy(h);
@@ -606,10 +643,20 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out)
 void ssd_destroy(ssd_handle* h)
 {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
-    for (void* d : h->dev_allocs) cudaFree(d);
-    for (int i = 0; i < 3; i++) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
-    if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_rew); cudaEventDestroy(h->ev_copied); }
+    {
+        ON_DEVICE(h);
+        if (h->s_out) {                                 // let in-flight copies of the async host path finish
+            cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_out);
+            for (int i = 0; i < 2; i++) {
+                cudaEventDestroy(h->slot[i].ev_up); cudaEventDestroy(h->slot[i].ev_rew);
+                cudaEventDestroy(h->slot[i].ev_copied); cudaEventDestroy(h->slot[i].ev_logic);
+            }
+            cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out);
+        }
+        for (void* d : h->dev_allocs) cudaFree(d);
+        for (int i = 0; i < 3; i++) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+        if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_rew); cudaEventDestroy(h->ev_copied); }
+    }
     delete h;
 }
 
@@ -633,6 +680,7 @@ static int check_launch(ssd_handle* h, const char* what)
 int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t obs_env_stride, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     const GridParams& p = h->gp;
     long long stride = obs_env_stride ? obs_env_stride : (long long)p.n * SSD_OBS_BYTES;
@@ -646,9 +694,11 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
     return check_launch(h, "reset");
 }
 
-static int make_step_io(ssd_handle* h, const ssd_step_io* io, StepIO& k)
+static int make_step_io(ssd_handle* h, const ssd_step_io* io, StepIO& k, bool async_host = false)
 {
-    if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
+    memset(&k, 0, sizeof(k));
+    if (!async_host && (!io->actions_dev || !io->rew_dev)) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
+    if (!io->obs_dev) return fail(h, SSD_EINVAL, "obs_dev is required");
     const GridParams& p = h->gp;
     k.actions = (const uint8_t*)io->actions_dev;
     k.obs = io->obs_dev;
@@ -660,11 +710,26 @@ static int make_step_io(ssd_handle* h, const ssd_step_io* io, StepIO& k)
     return SSD_OK;
 }
 
-// ssd_step_host: rewards / dones go back to the host on the side stream as soon as the kernels producing them are enqueued
-struct HostCopy { double* rew_host; uint8_t* done_host; };
+// ssd_step_host / ssd_step_host_async: the results go back to the host on a copy stream as soon as the kernels producing
+// them are enqueued.  slot < 0: the synchronous form (dense float64 rewards + dones); else the slot's result block.
+struct HostCopy { double* rew_host; uint8_t* done_host; int slot; };
 static int copy_rewards(ssd_handle* h, const StepIO& k, cudaStream_t s, const HostCopy* hc)
 {
     if (!hc) return SSD_OK;
+    if (hc->slot >= 0) {
+        ssd_handle::Slot& sl = h->slot[hc->slot];
+        // the record prefix that travels: twice the recent maximum (+ slack); ssd_step_host_wait fetches a remainder
+        uint32_t want = 2u * std::max(h->recent_count[0], h->recent_count[1]) + 1024u;
+        if (want > (uint32_t)h->lay.record_capacity) want = (uint32_t)h->lay.record_capacity;
+        sl.copied_records = want;
+        CUDA_TRY(h, cudaEventRecord(sl.ev_rew, s));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, sl.ev_rew, 0));
+        CUDA_TRY(h, cudaMemcpyAsync(sl.host_block, sl.d_block, (size_t)h->lay.records_offset + (size_t)want * h->lay.record_bytes,
+                                    cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(h, cudaMemsetAsync(sl.d_block + h->lay.count_offset, 0, 4, h->s_out));     // ready for the slot's next step
+        CUDA_TRY(h, cudaEventRecord(sl.ev_copied, h->s_out));
+        return SSD_OK;
+    }
     const size_t na = (size_t)h->gp.E * h->gp.n;
     CUDA_TRY(h, cudaEventRecord(h->ev_rew, s));
     CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_rew, 0));
@@ -687,6 +752,7 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
         else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         h->launches++;
         if (h->timing) cudaEventRecord(h->tev[1], s);
+        if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
         if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
         obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, h->obs_vpl)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
         if (p.kind == SSD_ENV_HARVEST) {
@@ -696,6 +762,7 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
         if (h->timing) cudaEventRecord(h->tev[2], s);
     } else {
         step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
+        if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
     }
     return check_launch(h, "step");
@@ -704,6 +771,7 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
 int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
 {
     if (!h || !io) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     StepIO k;
     int rc = make_step_io(h, io, k);
@@ -717,6 +785,7 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream)
 int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host, double* rew_host, uint8_t* done_host, void* stream)
 {
     if (!h || !io || !actions_host || !rew_host) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     StepIO k;
     int rc = make_step_io(h, io, k);
@@ -731,11 +800,143 @@ int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host
     }
     const size_t na = (size_t)p.E * p.n;
     CUDA_TRY(h, cudaMemcpyAsync(const_cast<uint8_t*>(k.actions), actions_host, na, cudaMemcpyHostToDevice, s));
-    const HostCopy hc = { rew_host, done_host };
+    const HostCopy hc = { rew_host, done_host, -1 };
     rc = launch_step(h, k, s, &hc);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaEventSynchronize(h->ev_copied));
+    return SSD_OK;
+}
+
+// ---- pipelined host-buffer step (see include/ssd_b200.h) --------------------------------------------------------
+static void host_layout(const ssd_handle* h, ssd_host_layout* l)
+{
+    const int64_t E = h->gp.E, n = h->gp.n;
+    l->count_offset = 0;
+    l->done_offset = 64;
+    l->rew_i8_offset = l->done_offset + (E + 63) / 64 * 64;
+    l->records_offset = l->rew_i8_offset + (E * n + 63) / 64 * 64;
+    l->record_bytes = (int32_t)(8 + 8 * n);
+    l->record_capacity = (int32_t)E;
+    l->total_bytes = l->records_offset + E * l->record_bytes;
+}
+
+int ssd_host_result_layout(const ssd_handle* h, ssd_host_layout* out)
+{
+    if (!h || !out) return SSD_EINVAL;
+    if (h->cfg.env_kind != SSD_ENV_CLEANUP && h->cfg.env_kind != SSD_ENV_HARVEST) return SSD_EINVAL;
+    host_layout(h, out);
+    return SSD_OK;
+}
+
+static int async_setup(ssd_handle* h)
+{
+    if (h->s_out) return SSD_OK;
+    host_layout(h, &h->lay);
+    for (int i = 0; i < 2; i++) {
+        int rc;
+        if ((rc = dev_zalloc(h, (size_t)h->gp.E * h->gp.n, &h->slot[i].d_actions))) return rc;
+        if ((rc = dev_zalloc(h, (size_t)h->lay.total_bytes, &h->slot[i].d_block))) return rc;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_up, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_rew, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_copied, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_logic, cudaEventDisableTiming));
+        h->slot[i].busy = false; h->slot[i].ticket = -1;
+    }
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    h->next_ticket = 0;
+    h->recent_count[0] = h->recent_count[1] = 0;
+    return SSD_OK;
+}
+
+int ssd_step_host_async(ssd_handle* h, const ssd_step_io* io, const void* actions_host, void* result_host, int64_t* ticket_out,
+                        void* stream)
+{
+    if (!h || !io || !actions_host || !result_host || !ticket_out) return SSD_EINVAL;
+    ON_DEVICE(h);
+    REQUIRE_GRID(h);
+    int rc = async_setup(h);
+    if (rc) return rc;
+    const int si = (int)(h->next_ticket & 1);
+    ssd_handle::Slot& sl = h->slot[si];
+    if (sl.busy) return fail(h, SSD_EINVAL, "step_host_async: ticket %lld of this slot has not been waited for", (long long)sl.ticket);
+    StepIO k;
+    rc = make_step_io(h, io, k, true);
+    if (rc) return rc;
+    const GridParams& p = h->gp;
+    cudaStream_t s = (cudaStream_t)stream;
+    // copy-in stream: the slot's action buffer is free once the logic kernel of its previous step has run
+    if (sl.ticket >= 0) CUDA_TRY(h, cudaStreamWaitEvent(h->s_in, sl.ev_logic, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(sl.d_actions, actions_host, (size_t)p.E * p.n, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaEventRecord(sl.ev_up, h->s_in));
+    CUDA_TRY(h, cudaStreamWaitEvent(s, sl.ev_up, 0));
+    // the slot's result block was copied out (and its record count cleared) before the slot could be resubmitted, but
+    // the copy-out stream is not ordered with `s`: make it so
+    if (sl.ticket >= 0) CUDA_TRY(h, cudaStreamWaitEvent(s, sl.ev_copied, 0));
+    k.actions = sl.d_actions;
+    k.c_count = reinterpret_cast<uint32_t*>(sl.d_block + h->lay.count_offset);
+    k.c_done = sl.d_block + h->lay.done_offset;
+    k.c_rew8 = reinterpret_cast<int8_t*>(sl.d_block + h->lay.rew_i8_offset);
+    k.c_rec = sl.d_block + h->lay.records_offset;
+    sl.host_block = result_host;
+    const HostCopy hc = { nullptr, nullptr, si };
+    rc = launch_step(h, k, s, &hc);
+    if (rc) return rc;
+    sl.ticket = h->next_ticket++;
+    sl.busy = true;
+    *ticket_out = sl.ticket;
+    return SSD_OK;
+}
+
+int ssd_step_host_wait(ssd_handle* h, int64_t ticket)
+{
+    if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
+    REQUIRE_GRID(h);
+    if (!h->s_out || ticket < 0) return fail(h, SSD_EINVAL, "step_host_wait: unknown ticket %lld", (long long)ticket);
+    ssd_handle::Slot& sl = h->slot[ticket & 1];
+    if (!sl.busy || sl.ticket != ticket) return fail(h, SSD_EINVAL, "step_host_wait: ticket %lld is not in flight", (long long)ticket);
+    CUDA_TRY(h, cudaEventSynchronize(sl.ev_copied));
+    const uint32_t count = *reinterpret_cast<const volatile uint32_t*>((const uint8_t*)sl.host_block + h->lay.count_offset);
+    if (count > (uint32_t)h->lay.record_capacity) return fail(h, SSD_ECUDA, "step_host_wait: corrupt record count %u", count);
+    if (count > sl.copied_records) {                      // the predicted prefix was too short: fetch the rest (rare)
+        const size_t off = (size_t)h->lay.records_offset + (size_t)sl.copied_records * h->lay.record_bytes;
+        CUDA_TRY(h, cudaMemcpyAsync((uint8_t*)sl.host_block + off, sl.d_block + off,
+                                    (size_t)(count - sl.copied_records) * h->lay.record_bytes, cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
+    }
+    h->recent_count[ticket & 1] = count;
+    sl.busy = false;
+    return SSD_OK;
+}
+
+int ssd_host_result_expand(const ssd_handle* h, const void* result_host, double* rew_out)
+{
+    if (!h || !result_host || !rew_out) return SSD_EINVAL;
+    if (h->cfg.env_kind != SSD_ENV_CLEANUP && h->cfg.env_kind != SSD_ENV_HARVEST) return SSD_EINVAL;
+    ssd_host_layout l;
+    host_layout(h, &l);
+    const uint8_t* b = (const uint8_t*)result_host;
+    const int64_t E = h->gp.E, n = h->gp.n;
+    const int8_t* r8 = reinterpret_cast<const int8_t*>(b + l.rew_i8_offset);
+    for (int64_t i = 0; i < E * n; i++) rew_out[i] = (double)r8[i];
+    const uint32_t count = *reinterpret_cast<const uint32_t*>(b + l.count_offset);
+    if (count > (uint32_t)l.record_capacity) return SSD_EINVAL;
+    for (uint32_t r = 0; r < count; r++) {
+        const uint8_t* rec = b + l.records_offset + (size_t)r * l.record_bytes;
+        const int32_t env = *reinterpret_cast<const int32_t*>(rec);
+        if (env < 0 || env >= E) return SSD_EINVAL;
+        memcpy(rew_out + (size_t)env * n, rec + 8, (size_t)n * sizeof(double));
+    }
+    return SSD_OK;
+}
+
+int ssd_set_episode_stats(ssd_handle* h, double* stats_dev)
+{
+    if (!h) return SSD_EINVAL;
+    REQUIRE_GRID(h);
+    h->gp.stats = stats_dev;
     return SSD_OK;
 }
 
@@ -745,6 +946,7 @@ int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host
 int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream)
 {
     if (!h || !theta_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     if (h->cfg.env_kind == SSD_ENV_SELFDRIVE)
         car_set_theta_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, theta_dev);
     else if (IS_FEAT(h))
@@ -755,11 +957,13 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
 }
 
 static SolverParams solver_params(ssd_handle* h);
-int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev, void* stream)
+int ssd_negotiate(ssd_handle* h, const uint8_t* mask_dev, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev,
+                  void* stream)
 {
     if (!h || !proposals_dev || !accept_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     const SolverParams sp = solver_params(h);            // every env kind: episode / theta addressed by (pointer, stride)
-    negotiate_kernel<<<(sp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sp, proposals_dev, accept_dev, decision_dev);
+    negotiate_kernel<<<(sp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sp, mask_dev, proposals_dev, accept_dev, decision_dev);
     return check_launch(h, "negotiate");
 }
 
@@ -767,6 +971,7 @@ int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* acce
 int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream)
 {
     if (!h || !out_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     if (reinterpret_cast<uintptr_t>(out_dev) & 3) return fail(h, SSD_EINVAL, "out_dev must be 4-byte aligned");
     const GridParams& p = h->gp;
@@ -778,6 +983,7 @@ int ssd_global_view(ssd_handle* h, uint8_t* out_dev, void* stream)
 int ssd_record_beams(ssd_handle* h, int32_t enable)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     GridParams& p = h->gp;
     if (!enable) { p.beam = nullptr; return SSD_OK; }
@@ -793,6 +999,7 @@ int ssd_record_beams(ssd_handle* h, int32_t enable)
 int ssd_render(ssd_handle* h, uint8_t* out_dev, void* stream)
 {
     if (!h || !out_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     if (reinterpret_cast<uintptr_t>(out_dev) & 3) return fail(h, SSD_EINVAL, "out_dev must be 4-byte aligned");
     const GridParams& p = h->gp;
@@ -803,6 +1010,7 @@ int ssd_render(ssd_handle* h, uint8_t* out_dev, void* stream)
 int ssd_concat_obs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_stride, uint8_t* out_dev, void* stream)
 {
     if (!h || !obs_dev || !out_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     const GridParams& p = h->gp;
     const int64_t dense = (int64_t)p.n * SSD_OBS_BYTES;
@@ -819,6 +1027,7 @@ int ssd_policy_inputs(ssd_handle* h, const uint8_t* obs_dev, int64_t obs_env_str
                       void* stream)
 {
     if (!h || !obs_dev || !image_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     const GridParams& p = h->gp;
     const int64_t dense = (int64_t)p.n * SSD_OBS_BYTES;
@@ -860,6 +1069,7 @@ static SolverParams solver_params(ssd_handle* h)
 int ssd_solver_sample(ssd_handle* h, int32_t num_samples, double* params_dev, void* stream)
 {
     if (!h || !params_dev || num_samples < 0) return SSD_EINVAL;
+    ON_DEVICE(h);
     if (h->cfg.contract_kind == SSD_CONTRACT_NONE) return fail(h, SSD_EINVAL, "solver_sample: the handle has no contract");
     const SolverParams s = solver_params(h);
     const long long total = (long long)s.E * (num_samples + 1);
@@ -872,6 +1082,7 @@ int ssd_solver_choose(ssd_handle* h, int32_t num_samples, int32_t rule, const do
                       double* best_param_dev, int32_t* best_index_dev, void* stream)
 {
     if (!h || !params_dev || !vals_dev || num_samples < 0) return SSD_EINVAL;
+    ON_DEVICE(h);
     if (rule != SOLVER_RULE_MAX && rule != SOLVER_RULE_MAJORITY) return fail(h, SSD_EINVAL, "solver_choose: unknown decision rule %d", rule);
     if (h->cfg.contract_kind == SSD_CONTRACT_NONE) return fail(h, SSD_EINVAL, "solver_choose: the handle has no contract");
     const SolverParams s = solver_params(h);
@@ -882,6 +1093,7 @@ int ssd_solver_choose(ssd_handle* h, int32_t num_samples, int32_t rule, const do
 int ssd_get_state(ssd_handle* h, uint8_t* map_dev, int32_t* pos_dev, int32_t* ori_dev, int32_t* t_dev, double* theta_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     SMALL_LAUNCH(get_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
     return check_launch(h, "get_state");
@@ -891,6 +1103,7 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
                   const double* theta_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     SMALL_LAUNCH(set_state_kernel, map_dev, pos_dev, ori_dev, t_dev, theta_dev);
     return check_launch(h, "set_state");
@@ -899,6 +1112,7 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
 int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 {
     if (!h || !out_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     SMALL_LAUNCH(get_metrics_kernel, out_dev);
     return check_launch(h, "get_metrics");
@@ -907,16 +1121,15 @@ int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream)
 {
     if (!h || !actions_dev || num_actions < 1 || num_actions > 255) return SSD_EINVAL;
+    ON_DEVICE(h);
     const bool autoidx = step_index == SSD_STEP_AUTO;
     if (IS_FEAT(h)) {
         feat_random_actions_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, step_index, autoidx ? h->d_counter : nullptr,
                                                                                               num_actions, actions_dev);
-        if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
         return check_launch(h, "random_actions");
     }
     REQUIRE_GRID(h);
     SMALL_LAUNCH(random_actions_kernel, step_index, autoidx ? h->d_counter : nullptr, num_actions, actions_dev);
-    if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "random_actions");
 }
 
@@ -924,6 +1137,7 @@ int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, 
 int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_FEAT(h);
     feat_reset_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, mask_dev, obs_dev);
     return check_launch(h, "feat_reset");
@@ -932,6 +1146,7 @@ int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void
 int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
 {
     if (!h || !io) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_FEAT(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
@@ -943,6 +1158,7 @@ int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
 int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev, int32_t* t_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_FEAT(h);
     feat_get_state_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, pos_dev, ori_dev, cells_dev, theta_dev, t_dev);
     return check_launch(h, "feat_get_state");
@@ -951,6 +1167,7 @@ int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_
 int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 {
     if (!h || !out_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_FEAT(h);
     feat_get_metrics_kernel<<<(h->fp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->fp, out_dev);
     return check_launch(h, "feat_get_metrics");
@@ -960,6 +1177,7 @@ int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream)
 int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_CAR(h);
     car_reset_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, mask_dev, obs_dev);
     return check_launch(h, "selfdrive_reset");
@@ -968,6 +1186,7 @@ int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev,
 int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream)
 {
     if (!h || !io) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_CAR(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 31)) return fail(h, SSD_EINVAL, "info_dev must be 32-byte aligned");
@@ -980,6 +1199,7 @@ int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, dou
                             int32_t* t_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_CAR(h);
     car_get_state_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, pos_dev, vel_dev, theta_dev, transfers_dev, t_dev);
     return check_launch(h, "selfdrive_get_state");
@@ -988,17 +1208,18 @@ int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, dou
 int ssd_selfdrive_random_actions(ssd_handle* h, uint32_t step_index, float lo, float hi, float* actions_dev, void* stream)
 {
     if (!h || !actions_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_CAR(h);
     const bool autoidx = step_index == SSD_STEP_AUTO;
     car_random_actions_kernel<<<(h->cp.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cp, step_index, autoidx ? h->d_counter : nullptr,
                                                                                          lo, hi, actions_dev);
-    if (autoidx) { counter_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_counter); h->launches++; }
     return check_launch(h, "selfdrive_random_actions");
 }
 
 int ssd_enable_timing(ssd_handle* h, int32_t on)
 {
     if (!h) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     if (on && !h->tev[0])
         for (int i = 0; i < 3; i++) CUDA_TRY(h, cudaEventCreate(&h->tev[i]));
@@ -1009,6 +1230,7 @@ int ssd_enable_timing(ssd_handle* h, int32_t on)
 int ssd_get_step_times(ssd_handle* h, double* out_ms)
 {
     if (!h || !out_ms) return SSD_EINVAL;
+    ON_DEVICE(h);
     REQUIRE_GRID(h);
     if (!h->tev[0]) return fail(h, SSD_EINVAL, "ssd_get_step_times: timing was never enabled");
     float a = 0.f, b = 0.f;

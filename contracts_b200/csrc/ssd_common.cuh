@@ -75,3 +75,15 @@ __device__ __forceinline__ uint32_t draw_u32(uint32_t seed, uint32_t env_id, uin
 {
     return pick(draw_block(seed, env_id, episode, t, site, call, idx >> 2), idx & 3);
 }
+
+// SSD_STEP_AUTO (ssd_random_actions & co.): counter[0] = step index, counter[1] = CTAs finished.  Every CTA reads
+// counter[0] before it arrives at counter[1]; the last one to arrive bumps the index for the next launch, so a captured
+// CUDA graph draws fresh actions at every replay without a separate one-thread kernel.
+__device__ __forceinline__ void counter_finish(uint32_t* counter, uint32_t step_index)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter + 1, 1u) == gridDim.x - 1) { counter[1] = 0u; counter[0] = step_index + 1u; }
+    }
+}

@@ -543,16 +543,18 @@ __global__ void feat_set_theta_kernel(const FeatParams p, const double* theta)
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env < p.E) p.theta[env] = theta[env];
 }
-__global__ void feat_random_actions_kernel(const FeatParams p, uint32_t step_index, const uint32_t* counter, int num_actions, uint8_t* actions)
+__global__ void feat_random_actions_kernel(const FeatParams p, uint32_t step_index, uint32_t* counter, int num_actions, uint8_t* actions)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= p.E) return;
-    if (counter) step_index = *counter;
-    const uint32_t env_id = p.first_env_id + (uint32_t)env;
-    for (int b = 0; b * 4 < p.n; b++) {
-        Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
-        uint32_t w[4] = { q.x, q.y, q.z, q.w };
-        for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
-            actions[(size_t)env * p.n + b * 4 + j] = (uint8_t)(((uint64_t)w[j] * (uint32_t)num_actions) >> 32);
+    if (counter) step_index = *reinterpret_cast<volatile uint32_t*>(counter);
+    if (env < p.E) {
+        const uint32_t env_id = p.first_env_id + (uint32_t)env;
+        for (int b = 0; b * 4 < p.n; b++) {
+            Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
+            uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
+                actions[(size_t)env * p.n + b * 4 + j] = (uint8_t)(((uint64_t)w[j] * (uint32_t)num_actions) >> 32);
+        }
     }
+    if (counter) counter_finish(counter, step_index);
 }

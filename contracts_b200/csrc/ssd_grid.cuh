@@ -95,6 +95,7 @@ struct GridParams {
     const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
     uint8_t* state;
     uint8_t* beam;               // optional [E][map_bytes]: beam_pos of the last step as a char overlay (render only)
+    double* stats;               // optional [8]: ssd_set_episode_stats accumulator (added to by the reset kernel)
 };
 
 // use_collective_reward / inequity_averse_reward (map_env.py:289-301): the shaped reward of agent a from the
@@ -146,7 +147,27 @@ struct StepIO {
     uint8_t* obs; long long obs_stride;
     double* rew; double* base_rew; double* transfers;
     uint8_t* info; double* feat; uint8_t* done;
+    // compact result block of ssd_step_host_async (all null otherwise): int8 rewards, dones, and records
+    // { int32 env; int32 0; double rew[n] } for the envs whose rewards are not all integers in [-127, 127]
+    int8_t* c_rew8; uint8_t* c_done; uint32_t* c_count; uint8_t* c_rec;
 };
+
+// is `r` exactly an integer in [-127, 127]?  (bit pattern compared: -0.0 is not)
+__device__ __forceinline__ bool reward_fits_i8(double r, int& v)
+{
+    v = __double2int_rn(r);
+    return v >= -127 && v <= 127 && __double_as_longlong((double)v) == __double_as_longlong(r);
+}
+// slot of this thread's record in the compact block: one atomic per group of converged threads
+__device__ __forceinline__ uint32_t compact_slot(uint32_t* count)
+{
+    const unsigned am = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(am));
+    base = __shfl_sync(am, base, leader);
+    return base + (uint32_t)__popc(am & ((1u << lane) - 1u));
+}
 
 struct EnvRng { uint32_t seed, env_id, episode, t; };
 
@@ -1010,7 +1031,7 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
             for (int i = 0; i < n; i++) raw_step = __dadd_rn(raw_step, __shfl_sync(FULL, base, i));
         if (act_lane) {
             size_t o = (size_t)env * n + lane;
-            io.rew[o] = r;
+            if (io.rew) io.rew[o] = r;
             if (io.base_rew) io.base_rew[o] = base;
             if (io.transfers) io.transfers[o] = tr;
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] =
@@ -1060,6 +1081,21 @@ __global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kerne
                 *xr = __dadd_rn(*xr, raw_step);
             }
             if (io.done) io.done[env] = done ? 1 : 0;
+            if (io.c_done) io.c_done[env] = done ? 1 : 0;
+        }
+        if (io.c_rew8) {                               // compact result block (ssd_step_host_async), lane = agent
+            int v = 0;
+            const bool fits = reward_fits_i8(r, v);
+            const bool sparse = __ballot_sync(FULL, act_lane && !fits) != 0u;
+            if (act_lane) io.c_rew8[(size_t)env * n + lane] = (int8_t)(fits ? v : -128);
+            if (sparse) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(io.c_count, 1u);
+                slot = __shfl_sync(FULL, slot, 0);
+                uint8_t* rec_o = io.c_rec + (size_t)slot * (8 + 8 * n);
+                if (lane == 0) *reinterpret_cast<int2*>(rec_o) = make_int2(env, 0);
+                if (act_lane) reinterpret_cast<double*>(rec_o + 8)[lane] = r;
+            }
         }
         // ---- the record leaves with one bulk store
         fence_async_smem();
@@ -1095,12 +1131,41 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
 
-    for (int env = blockIdx.x * GRID_WARPS + warp; env < p.E; env += gridDim.x * GRID_WARPS) {
-        if (mask && !mask[env]) continue;
+    // The warp's envs are env0 + i * estride.  The mask bytes of 32 of them are read at once (one round trip, one
+    // ballot), so a sparse mask — a vectorised sampler in steady state resets ~E / horizon envs per step — costs a
+    // few loads per warp instead of one dependent load per env.
+    const int env0 = blockIdx.x * GRID_WARPS + warp, estride = gridDim.x * GRID_WARPS;
+    for (int i0 = 0; env0 + (long long)i0 * estride < p.E; i0 += 32) {
+      const long long el = env0 + (long long)(i0 + lane) * estride;
+      unsigned todo = __ballot_sync(FULL, el < p.E && (!mask || mask[el]));
+      while (todo) {
+        const int env = env0 + (i0 + __ffs(todo) - 1) * estride;
+        todo &= todo - 1;
         uint8_t* rec = p.state + (size_t)env * p.rec_stride;
         uint8_t* hdr = rec + p.map_bytes;
         uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
         uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+        if (p.stats && (flags & 0x80000000u)) {       // a finished episode is replaced: hand its accumulators over
+            double tr = 0.0, raw = 0.0;
+            if (act_lane) {
+                tr = reinterpret_cast<const double*>(hdr + RO_SUM_TR)[lane];
+                raw = p.reward_mode ? reinterpret_cast<const double*>(hdr + RO_XSUM)[lane]
+                                    : (double)reinterpret_cast<const int*>(hdr + RO_SUM_RAW)[lane];
+            }
+            for (int o = 16; o; o >>= 1) { tr += __shfl_xor_sync(FULL, tr, o); raw += __shfl_xor_sync(FULL, raw, o); }
+            if (lane == 0) {
+                atomicAdd(p.stats + 0, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_APPLES));
+                atomicAdd(p.stats + 1, p.reward_mode ? *reinterpret_cast<const double*>(hdr + RO_XRAW) : raw);
+                atomicAdd(p.stats + 2, *reinterpret_cast<const double*>(hdr + RO_TRANSFERS));
+                atomicAdd(p.stats + 3, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_DIRT));
+                atomicAdd(p.stats + 4, tr);
+                atomicAdd(p.stats + 5, raw);
+                atomicAdd(p.stats + 6, 1.0);
+                // non-negative doubles order like their bit patterns
+                atomicMax(reinterpret_cast<unsigned long long*>(p.stats + 7),
+                          (unsigned long long)__double_as_longlong((double)((flags >> RF_ERR_SHIFT) & 0xFFFFu)));
+            }
+        }
         // the first reset of a record (flags bit 31 clear) is episode 0; later resets increment
         episode = (flags & 0x80000000u) ? episode + 1u : 0u;
         EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, 0u };
@@ -1171,6 +1236,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
             *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
         }
         __syncwarp();
+      }
     }
     if (lane == 0) bulk_wait_read<0>();
 }

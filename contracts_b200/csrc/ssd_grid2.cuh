@@ -251,7 +251,7 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
             const uint32_t eaten = (w >> 2) & 1u, eclose = (w >> 3) & 1u, cleaned = w & RS_CLEANED_MASK;
             const uint32_t tclose = (w >> RS_CLOSE_SHIFT) & 31u;
             n_eaten += eaten; n_close += eclose;
-            io.rew[o + a] = rj[a];
+            if (io.rew) io.rew[o + a] = rj[a];
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o + a] =
                 eaten | ((KIND == SSD_ENV_CLEANUP ? cleaned : eclose) << 8) | (tclose << 16);
         }
@@ -281,6 +281,30 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
     if (KIND == SSD_ENV_HARVEST && n_close) red_add(reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS), n_close);
     if (total_tr != 0.0) red_add(reinterpret_cast<double*>(hdr + RO_TRANSFERS), total_tr);
     if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
+    if (io.c_rew8) {                                   // compact result block (ssd_step_host_async)
+        io.c_done[env] = t == p.horizon ? 1 : 0;
+        uint32_t lo = 0, hi = 0;
+        bool fits = true;
+#pragma unroll
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a < n) {
+                int v = 0;
+                const bool f = reward_fits_i8(rj[a], v);
+                fits = fits && f;
+                const uint32_t b = (uint32_t)(f ? v : -128) & 255u;
+                if (a < 4) lo |= b << (8 * a); else hi |= b << (8 * (a - 4));
+            }
+        }
+        if (n == 8) *reinterpret_cast<uint2*>(io.c_rew8 + o) = make_uint2(lo, hi);       // block offsets are 64-byte aligned
+        else
+            for (int a = 0; a < n; a++) io.c_rew8[o + a] = (int8_t)(((a < 4 ? lo : hi) >> (8 * (a & 3))) & 255u);
+        if (!fits) {
+            uint8_t* rec_o = io.c_rec + (size_t)compact_slot(io.c_count) * (8 + 8 * n);
+            *reinterpret_cast<int2*>(rec_o) = make_int2(env, 0);
+#pragma unroll
+            for (int a = 0; a < SSD_MAXN; a++) if (a < n) reinterpret_cast<double*>(rec_o + 8)[a] = rj[a];
+        }
+    }
 }
 
 // =============================================================================================

@@ -274,19 +274,21 @@ __global__ void __launch_bounds__(CAR_THREADS) car_step_kernel(const CarParams p
     car_write_obs(p, s_pos, s_vel, io.obs, env - lane, lane, valid);
 }
 
-__global__ void car_random_actions_kernel(const CarParams p, uint32_t step_index, const uint32_t* counter, float lo, float hi,
+__global__ void car_random_actions_kernel(const CarParams p, uint32_t step_index, uint32_t* counter, float lo, float hi,
                                           float* actions)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= p.E) return;
-    if (counter) step_index = *counter;
-    const uint32_t env_id = p.first_env_id + (uint32_t)env;
-    for (int b = 0; b * 4 < p.n; b++) {
-        Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
-        uint32_t w[4] = { q.x, q.y, q.z, q.w };
-        for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
-            actions[(size_t)env * p.n + b * 4 + j] = lo + (hi - lo) * ((float)(w[j] >> 8) * (1.0f / 16777216.0f));
+    if (counter) step_index = *reinterpret_cast<volatile uint32_t*>(counter);
+    if (env < p.E) {
+        const uint32_t env_id = p.first_env_id + (uint32_t)env;
+        for (int b = 0; b * 4 < p.n; b++) {
+            Philox4 q = philox4x32_10((uint32_t)b, SITE_ACTIONS, step_index, 0u, p.seed, env_id);
+            uint32_t w[4] = { q.x, q.y, q.z, q.w };
+            for (int j = 0; j < 4 && b * 4 + j < p.n; j++)
+                actions[(size_t)env * p.n + b * 4 + j] = lo + (hi - lo) * ((float)(w[j] >> 8) * (1.0f / 16777216.0f));
+        }
     }
+    if (counter) counter_finish(counter, step_index);
 }
 
 __global__ void car_get_state_kernel(const CarParams p, double* pos, double* vel, double* theta, double* m_transfers, int32_t* t)

@@ -30,22 +30,21 @@ class BatchedFeatureEnv:
             raise _lib.SsdError("CUDA device required: contracts_b200 has no CPU fallback")
         self.lib = _lib.load()
         self.kind, self.E, self.n = kind, int(num_envs), int(num_agents)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = _lib.resolve_device(device)
         self.ascii_map = list(ascii_map) if ascii_map is not None else (CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP)
         self.H, self.W = len(self.ascii_map), len(self.ascii_map[0])
         self.horizon, self.contract = int(horizon), contract
         if theta_high is None:
             theta_high = _DEFAULT_HIGH.get(contract, 0.0)
         self._flat = "".join(self.ascii_map).encode("ascii")
-        cfg = _lib.ssd_config(
-            abi_version=_lib.SSD_ABI_VERSION, env_kind=_lib.ENV_KIND[kind], num_envs=self.E, num_agents=self.n,
+        cfg = _lib.make_config(
+            env_kind=_lib.ENV_KIND[kind], num_envs=self.E, num_agents=self.n,
             map_h=self.H, map_w=self.W, ascii_map=self._flat, horizon=self.horizon,
             contract_kind=_lib.CONTRACT_KIND[contract], theta_low=float(np.float32(theta_low)),
             theta_high=float(np.float32(theta_high)), null_prob=float(null_prob), seed=int(seed) & 0xFFFFFFFF,
-            first_env_id=int(first_env_id) & 0xFFFFFFFF, device=self.device.index or 0, flags=0)
+            first_env_id=int(first_env_id) & 0xFFFFFFFF, device=self.device.index, flags=0)
         h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
+        _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
         self.F = self.lib.ssd_feature_dim(self._h)
         E, n, dev = self.E, self.n, self.device

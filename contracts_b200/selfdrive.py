@@ -25,18 +25,17 @@ class BatchedCarEnv:
             raise _lib.SsdError("CUDA device required: contracts_b200 has no CPU fallback")
         self.lib = _lib.load()
         self.E, self.n = int(num_envs), int(num_agents)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = _lib.resolve_device(device)
         self.contract = contract
-        cfg = _lib.ssd_config(
-            abi_version=_lib.SSD_ABI_VERSION, env_kind=_lib.ENV_KIND["selfdrive"], num_envs=self.E, num_agents=self.n,
+        cfg = _lib.make_config(
+            env_kind=_lib.ENV_KIND["selfdrive"], num_envs=self.E, num_agents=self.n,
             map_h=0, map_w=0, ascii_map=None, horizon=0, contract_kind=_lib.CONTRACT_KIND[contract],
             theta_low=float(np.float32(theta_low)), theta_high=float(np.float32(theta_high)), null_prob=float(null_prob),
-            seed=int(seed) & 0xFFFFFFFF, first_env_id=int(first_env_id) & 0xFFFFFFFF, device=self.device.index or 0, flags=0)
+            seed=int(seed) & 0xFFFFFFFF, first_env_id=int(first_env_id) & 0xFFFFFFFF, device=self.device.index, flags=0)
         cfg.env_params[0], cfg.env_params[1] = float(low_bound), float(high_bound)
         cfg.env_params[2], cfg.env_params[3] = float(start_vel), float(start_vel_ambulance)
         h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
+        _lib.check(None, self.lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
         self.D = self.lib.ssd_feature_dim(self._h)
         E, n, dev = self.E, self.n, self.device

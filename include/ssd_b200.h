@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SSD_ABI_VERSION 2
+#define SSD_ABI_VERSION 3
 
 /* env_kind: which reference class the handle simulates */
 #define SSD_ENV_CLEANUP 0           /* environments/cleanup_new.py  CleanupEnv   ('CleanupNew') */
@@ -66,6 +66,8 @@ typedef struct ssd_handle ssd_handle;
 
 typedef struct ssd_config {
     int32_t abi_version;      /* SSD_ABI_VERSION */
+    int32_t struct_size;      /* sizeof(ssd_config) as the caller compiled / declared it: ssd_create rejects a struct
+                                 that is shorter than the library's (a stale binding would otherwise be read past its end) */
     int32_t env_kind;
     int32_t num_envs;         /* E, envs stepped per launch by this handle */
     int32_t num_agents;       /* n in [1, 8] */
@@ -88,7 +90,8 @@ typedef struct ssd_config {
 
 /* Buffers of one step.  Gridworld / feature envs: actions are uint8 [E][n] action ids
  * (Agent.py:8-16,161-162,198-199); selfdrive: float32 [E][n] accelerations.
- * NULL is allowed for every output except obs and rew. */
+ * NULL is allowed for every output except obs and rew (rew_dev may be NULL in ssd_step_host_async, whose result
+ * block carries the rewards). */
 typedef struct ssd_step_io {
     const void* actions_dev;
     uint8_t* obs_dev;         /* gridworlds: uint8 [E][n][15][15][3] (MapEnv.step 'curr_obs', map_env.py:269,284) */
@@ -119,6 +122,17 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
 /* MapEnv.step (map_env.py:216-304) + env step tail (cleanup_new.py:211-267 / harvest_new.py:181-239)
  * + SeparateContractEnv.step reward redistribution (two_stage_train.py:62-121), one launch for E envs. */
 int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream);
+/* Error surface of the step.  ssd_step returns SSD_OK as soon as the launch is enqueued; conditions that only the
+ * kernel can see are recorded in a STICKY per-env flag word that lasts until the env is reset and is reported as
+ * `err_flags` by ssd_get_metrics (out[5]) / ssd_set_episode_stats (max over envs):
+ *   2  the reference would have raised KeyError in update_moves (map_env.py:640, agent_by_pos lookup)
+ *   8  an action id outside the env's action space (the agent stays in place; the reference raises KeyError in
+ *      Agent.action_map, Agent.py:161-162)
+ *   16 ssd_set_state was given a map character that is not one of ' @AHRS'
+ * The reference checks none of these eagerly either; callers that want a hard failure read err_flags at episode end
+ * (contracts_b200/environments/gridworld.py does and raises).  There is no `rng_mode=injected` / ssd_set_injected_draws:
+ * the only random stream is the counter-based Philox one (key = seed, global env id), which the parity harness injects
+ * into the unmodified reference instead (oracle/ref_harness.py). */
 /* The same step for a caller that holds HOST buffers (a CPU rollout worker, RLlib's sampler): copies
  * actions_host (uint8 [E][n], pinned for asynchronous copies) into io->actions_dev, steps, copies the rewards
  * (double [E][n], after transfers) and dones (uint8 [E], nullable) back, and returns when they are valid.  The device ->
@@ -126,6 +140,43 @@ int ssd_step(ssd_handle* h, const ssd_step_io* io, void* stream);
  * it; the observations stay in the device batch tensor io->obs_dev. */
 int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host, double* rew_host, uint8_t* done_host,
                   void* stream);
+
+/* Pipelined form of ssd_step_host (what RLlib's BaseEnv.send_actions() / poll() pair is to a vector env,
+ * utils/ray_config_utils.py:140 -> rollout worker): submit step k + 1 before waiting for step k.  Two slots.
+ *   ssd_step_host_async  uploads actions_host (uint8 [E][n], pinned) on a library-owned copy-in stream into the slot's
+ *                        device action buffer (io->actions_dev is ignored), runs the step on `stream`, and — as soon as
+ *                        the rewards exist, i.e. overlapping the observe kernel — copies ONE result block to
+ *                        result_host (pinned, ssd_host_result_layout().total_bytes) on a copy-out stream.  Returns
+ *                        without any host synchronisation; *ticket_out identifies the step (ticket & 1 = slot).
+ *   ssd_step_host_wait   blocks until that step's result block is valid in host memory (and the slot can be reused).
+ * At most two steps may be in flight; a slot must be waited for before it is submitted again (SSD_EINVAL otherwise).
+ *
+ * The result block is a LOSSLESS compact form of (rewards after transfers, dones).  Rewards on this path are small
+ * integers except in envs where a contract transfer was paid this step, so the block holds
+ *   count    uint32         number of records below
+ *   done     uint8 [E]      dones['__all__']
+ *   rew_i8   int8 [E][n]    the reward, valid for every env that is NOT in the record list
+ *   records  [count] x { int32 env; int32 0; double rew[n] }   envs with a reward that is not an integer in
+ *                           [-127, 127] (bit pattern compared, so -0.0 also lands here): all n exact float64 rewards;
+ *                           order unspecified (warp-aggregated atomics)
+ * at the byte offsets ssd_host_result_layout() reports.  Only the leading `count` records travel: the copy size is
+ * predicted from the previous steps and ssd_step_host_wait fetches the remainder in the (rare) case of a miss.
+ * ssd_host_result_expand() is the host-side convenience that rebuilds the dense float64 [E][n] matrix. */
+typedef struct ssd_host_layout {
+    int64_t total_bytes;      /* size of a result block (worst case: every env in the record list) */
+    int64_t count_offset;     /* uint32 */
+    int64_t done_offset;      /* uint8 [E] */
+    int64_t rew_i8_offset;    /* int8 [E][n] */
+    int64_t records_offset;   /* records, record_bytes each */
+    int32_t record_bytes;     /* 8 + 8 n */
+    int32_t record_capacity;  /* E */
+} ssd_host_layout;
+int ssd_host_result_layout(const ssd_handle* h, ssd_host_layout* out);
+int ssd_step_host_async(ssd_handle* h, const ssd_step_io* io, const void* actions_host, void* result_host,
+                        int64_t* ticket_out, void* stream);
+int ssd_step_host_wait(ssd_handle* h, int64_t ticket);
+/* host code only: rew_out double [E][n] from a valid result block */
+int ssd_host_result_expand(const ssd_handle* h, const void* result_host, double* rew_out);
 
 /* --- contract parameters / negotiation ----------------------------------------------------------- */
 /* theta_dev: double [E].  What SeparateContractNegotiateStage does with a0's proposal
@@ -135,8 +186,10 @@ int ssd_set_contract_params(ssd_handle* h, const double* theta_dev, void* stream
  * proposals_dev double [E] (a0's action[:-1]), accept_dev double [E][n] (each agent's action[-1]),
  * decision_dev uint8 [E] out.  Chooses 2 of agents 1..n-1 when n > 3, multiplies their accept
  * values, draws once and keeps the proposal as theta or zeroes it.  Every env kind. */
-int ssd_negotiate(ssd_handle* h, const double* proposals_dev, const double* accept_dev, uint8_t* decision_dev,
-                  void* stream);
+int ssd_negotiate(ssd_handle* h, const uint8_t* mask_dev, const double* proposals_dev, const double* accept_dev,
+                  uint8_t* decision_dev, void* stream);
+/* mask_dev (nullable, uint8 [E]): negotiate only in the envs with mask_dev[i] != 0 — the envs that were just reset when
+ * every env of the batch is at its own point of its episode (a vectorised sampler in steady state). */
 
 /* --- JointEnv output layouts (environments/two_stage_train.py:476-617) ----------------------------- */
 /* `global_obs`: MapEnv.global_view() (map_env.py:394-395; base_env.get_global_obs(), cleanup_new.py:299-300,
@@ -190,6 +243,13 @@ int ssd_set_state(ssd_handle* h, const uint8_t* map_dev, const int32_t* pos_dev,
  *   [apples_eaten, low_density_eaten, raw_env_rewards, transfers, dirt_cleaned, err_flags, 0, 0,
  *    agent_a[8], agent_b[8], sum_raw[8], tsum_raw[8], sum_transferred[8], tsum_transferred[8]] */
 int ssd_get_metrics(ssd_handle* h, double* out_dev, void* stream);
+/* Episode statistics without a pass over all envs (the MetricsCallback hand-off, utils/logger_utils.py:126-151):
+ * while stats_dev (double [SSD_STATS_LEN], caller-owned, caller-zeroed) is set, every ssd_reset adds the accumulators
+ * of each FINISHED episode it replaces (envs that had been reset before) to it with device atomics:
+ *   [apples_eaten, raw_env_rewards, transfers, dirt_cleaned, sum of transferred rewards, sum of raw rewards,
+ *    episodes, max err_flags].  NULL switches it off.  Gridworld kinds. */
+#define SSD_STATS_LEN 8
+int ssd_set_episode_stats(ssd_handle* h, double* stats_dev);
 
 /* --- SelfAcceleratingCarEnv (env_kind SSD_ENV_SELFDRIVE) -------------------------------------------------
  * environments/self_driving_car_accelerate.py reset :49-79 / step :151-250 (collision_on=False), optionally with
@@ -242,7 +302,7 @@ int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream);
 /* uniform random action ids in [0, num_actions) for benchmark rollouts, uint8 [E][n];
  * drawn from Philox site 13 at counter `step_index` (no reference equivalent: RLlib's policy).
  * step_index == SSD_STEP_AUTO takes (and then bumps) a per-handle device counter instead, so the call can be
- * captured in a CUDA graph and still draw fresh actions at every replay. */
+ * captured in a CUDA graph and still draw fresh actions at every replay (the last CTA to finish bumps the counter). */
 #define SSD_STEP_AUTO 0xFFFFFFFFu
 int ssd_random_actions(ssd_handle* h, uint32_t step_index, int32_t num_actions, uint8_t* actions_dev, void* stream);   /* gridworld and feature kinds */
 /* host-side Philox4x32-10 (so tests can pin the generator: KATs in tests/test_philox.py) */

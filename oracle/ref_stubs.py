@@ -11,6 +11,19 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
+# `oracle/stage_reference.py` (run by __graft_entry__.build() in the container) copies the unmodified reference modules
+# the path needs into this git-ignored directory, so that bench.py's CPU-baseline arm can time the REAL reference on the
+# GPU box, where /root/reference does not exist.  Parity tests never use the staged copy.
+STAGED_ROOT = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """/root/reference when present (container), else the staged copy (GPU box), else None."""
+    import os
+    for r in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isdir(os.path.join(r, "environments")):
+            return r
+    return None
 
 
 class Space:
@@ -67,11 +80,12 @@ def _mod(name, **attrs):
     return m
 
 
-def install():
+def install(root=None):
     """Put the stub modules in sys.modules and the reference root on sys.path."""
     import os
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError("reference tree %s not present (container-only)" % REFERENCE_ROOT)
+    root = root or REFERENCE_ROOT
+    if not os.path.isdir(root):
+        raise RuntimeError("reference tree %s not present (container-only)" % root)
     if "gym" not in sys.modules:
         spaces = _mod("gym.spaces", Space=Space, Box=Box, Discrete=Discrete,
                       MultiDiscrete=MultiDiscrete, Dict=Dict)
@@ -107,5 +121,5 @@ def install():
                    imshow=lambda *a, **k: None, show=lambda *a, **k: None,
                    savefig=lambda *a, **k: None)
         _mod("matplotlib", pyplot=plt)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)

@@ -40,7 +40,8 @@ def test_config_struct_matches_header():
     from contracts_b200 import _lib
     text = open(os.path.join(ROOT, "include", "ssd_b200.h")).read()
     for struct, cls in (("ssd_config", _lib.ssd_config), ("ssd_step_io", _lib.ssd_step_io),
-                        ("ssd_selfdrive_io", _lib.ssd_selfdrive_io), ("ssd_feat_io", _lib.ssd_feat_io)):
+                        ("ssd_selfdrive_io", _lib.ssd_selfdrive_io), ("ssd_feat_io", _lib.ssd_feat_io),
+                        ("ssd_host_layout", _lib.ssd_host_layout)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
@@ -49,6 +50,32 @@ def test_config_struct_matches_header():
             if decl:
                 fields += [re.sub(r"\[.*\]|[\*\s]", "", f.split()[-1]) for f in decl.split(",")]
         assert fields == [f[0] for f in cls._fields_], struct
+
+
+def test_create_rejects_stale_config_struct():
+    """abi_version and struct_size are checked before anything else (no GPU needed): a binding whose ssd_config
+    declaration is shorter than the library's must not be read past its end."""
+    from contracts_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _lib.make_config(env_kind=0, num_envs=4, num_agents=2, map_h=1, map_w=1, ascii_map=b"P", horizon=10)
+    cfg.struct_size = ctypes.sizeof(_lib.ssd_config) - 64            # e.g. a stub that stops before env_params
+    assert lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)) == -1 and not h.value
+    assert b"struct_size" in lib.ssd_last_error(None)
+    cfg = _lib.make_config(env_kind=0, num_envs=4, num_agents=2, map_h=1, map_w=1, ascii_map=b"P", horizon=10)
+    cfg.abi_version = _lib.SSD_ABI_VERSION - 1
+    assert lib.ssd_create(ctypes.byref(cfg), ctypes.byref(h)) == -1 and not h.value
+    assert b"abi_version" in lib.ssd_last_error(None)
+
+
+def test_integration_md_stub_matches_binding():
+    """The ctypes stub printed in INTEGRATION.md declares ssd_config with the same fields as the shipped binding."""
+    from contracts_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class ssd_config\(ctypes\.Structure\):(.*?)\n\n", text, flags=re.S)
+    assert m, "INTEGRATION.md must show the ssd_config ctypes stub"
+    names = re.findall(r'\("([a-z_0-9]+)",', m.group(1))
+    assert names == [f[0] for f in _lib.ssd_config._fields_]
 
 
 def test_no_cpu_fallback_without_gpu():

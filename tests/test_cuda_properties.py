@@ -93,3 +93,157 @@ def test_step_host_equals_step():
             assert torch.equal(done_a.cpu(), done_h), (kind, t)
             if done_h.any():
                 a.reset(done_a); b.reset(done_h.cuda())
+
+
+@pytest.mark.parametrize("kind,contract,E,n,theta", [("cleanup_new", "CleanupContract", 3000, 8, 0.15),
+                                                     ("cleanup_new", "CleanupContract", 700, 5, 0.0),
+                                                     ("harvest_new", "HarvestFeaturemodLocalContract", 2000, 4, 3.0),
+                                                     ("cleanup_new", None, 500, 3, 0.0)])
+def test_step_host_async_equals_step(kind, contract, E, n, theta):
+    """ssd_step_host_async / _wait (double-buffered slots, compact int8 + sparse float64 result block, predicted copy
+    size) delivers bit for bit what ssd_step produces: observations, dones, and — after ssd_host_result_expand — the
+    float64 rewards.  Two steps are kept in flight, as the pipelined caller does."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    a = BatchedGridEnv(kind, E, n, contract=contract, seed=5, first_env_id=11, horizon=60)
+    b = BatchedGridEnv(kind, E, n, contract=contract, seed=5, first_env_id=11, horizon=60)
+    a.reset(); b.reset()
+    if contract:
+        a.set_contract_params(theta); b.set_contract_params(theta)
+    rng = np.random.RandomState(1)
+    nact = 9 if kind == "cleanup_new" else 8
+    acts = [torch.as_tensor(rng.randint(0, nact, size=(E, n)).astype(np.uint8)).pin_memory() for _ in range(70)]
+    res = [b.new_host_result(), b.new_host_result()]
+    want = []
+    for t in range(70):
+        obs_a, rew_a, done_a, _ = a.step(acts[t].cuda())
+        want.append((rew_a.cpu().numpy().copy(), done_a.cpu().numpy().copy(), obs_a.cpu().numpy().copy() if t % 23 == 0 else None))
+        if done_a.any():
+            a.reset(done_a)
+            if contract:
+                a.set_contract_params(theta)
+    tickets, sparse_total = [], 0
+    def check(t):
+        nonlocal sparse_total
+        b.step_host_wait(tickets[t])
+        r = res[t & 1]
+        assert np.array_equal(r.rewards().view(np.uint64), want[t][0].view(np.uint64)), (kind, t)
+        assert np.array_equal(r.done, want[t][1]), (kind, t)
+        # the compact form itself: int8 where it says so, records exactly for the other envs, each env once
+        envs = r.rec_env[:r.count]
+        assert len(np.unique(envs)) == r.count
+        w = want[t][0]
+        fits = (w == np.round(w)) & (np.abs(w) <= 127) & ~(np.signbit(w) & (w == 0))
+        sparse_env = np.nonzero(~fits.all(1))[0]
+        assert np.array_equal(np.sort(envs), sparse_env), (kind, t)
+        sparse_total += r.count
+    for t in range(70):
+        tickets.append(b.step_host_async(acts[t], res[t & 1]))
+        if want[t][2] is not None:                      # observations are on the device, stream-ordered after the step
+            assert np.array_equal(b.obs.cpu().numpy(), want[t][2]), (kind, t)
+        if want[t][1].any():                            # device-side masked reset, stream-ordered, no host round trip
+            b.reset(b.done)
+            if contract:
+                b.set_contract_params(theta)
+        if t >= 1:
+            check(t - 1)
+    check(69)
+    if contract and theta:
+        assert sparse_total > 0                         # transfers were paid: the record path was exercised
+    else:
+        assert sparse_total == 0
+    # a slot that has not been waited for cannot be resubmitted
+    from contracts_b200 import _lib
+    t0 = b.step_host_async(acts[0], res[0]); t1 = b.step_host_async(acts[1], res[1])
+    with pytest.raises(_lib.SsdError):
+        b.step_host_async(acts[2], res[0])
+    b.step_host_wait(t0); b.step_host_wait(t1)
+
+
+def test_step_host_async_prefix_miss():
+    """The copied record prefix is predicted from the previous steps; when a step suddenly has far more records than
+    predicted (contract switched on for every env), ssd_step_host_wait fetches the remainder."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    E, n = 40000, 8
+    b = BatchedGridEnv("cleanup_new", E, n, contract="CleanupContract", seed=2, horizon=1000)
+    a = BatchedGridEnv("cleanup_new", E, n, contract="CleanupContract", seed=2, horizon=1000)
+    a.reset(); b.reset()
+    a.set_contract_params(0.0); b.set_contract_params(0.0)
+    res = [b.new_host_result(), b.new_host_result()]
+    rng = np.random.RandomState(3)
+    for t in range(6):
+        if t == 3:
+            a.set_contract_params(0.1); b.set_contract_params(0.1)
+        acts = torch.full((E, n), 7, dtype=torch.uint8).pin_memory() if t >= 2 else \
+            torch.as_tensor(rng.randint(0, 7, size=(E, n)).astype(np.uint8)).pin_memory()
+        _, rew_a, _, _ = a.step(acts.cuda())
+        tk = b.step_host_async(acts, res[t & 1])
+        b.step_host_wait(tk)
+        assert np.array_equal(res[t & 1].rewards().view(np.uint64), rew_a.cpu().numpy().view(np.uint64)), t
+        if t == 3:
+            assert res[t & 1].count > 1024 + 2 * 0        # more records than the predicted prefix (1024 after quiet steps)
+
+
+def test_masked_negotiate_and_episode_stats(oracle_lib):
+    """Steady-state sampler pieces: reset(mask) + negotiate(mask) touch only the masked envs, and the episode
+    statistics accumulated at reset equal the per-env metrics summed on the host."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    E, n = 512, 8
+    env = BatchedGridEnv("cleanup_new", E, n, contract="CleanupContract", seed=9, horizon=30)
+    stats = torch.zeros(8, dtype=torch.float64, device=env.device)
+    env.set_episode_stats(stats)
+    env.reset()
+    assert float(stats.abs().sum()) == 0.0                # first resets replace nothing
+    theta0 = env.get_state()["theta"].clone()
+    mask = (torch.arange(E, device=env.device) % 3 == 0).to(torch.uint8)
+    prop = torch.full((E,), 0.125, dtype=torch.float64, device=env.device)
+    acc = torch.ones((E, n), dtype=torch.float64, device=env.device)
+    dec = env.negotiate(prop, acc, mask=mask)
+    th = env.get_state()["theta"]
+    assert torch.equal(th[mask == 0], theta0[mask == 0])
+    assert bool((th[mask == 1] == 0.125).all()) and bool((dec[mask == 1] == 1).all()) and bool((dec[mask == 0] == 0).all())
+    full = BatchedGridEnv("cleanup_new", E, n, contract="CleanupContract", seed=9, horizon=30)
+    full.reset()
+    dec_full = full.negotiate(prop, torch.full((E, n), 0.5, dtype=torch.float64, device=env.device))
+    dec_m = env.negotiate(prop, torch.full((E, n), 0.5, dtype=torch.float64, device=env.device), mask=mask)
+    assert torch.equal(dec_m[mask == 1], dec_full[mask == 1])        # the same draw, masked or not
+    want = np.zeros(8)
+    for t in range(30):
+        env.step(env.random_actions(t, 9))
+    m = env.metrics_raw().cpu().numpy()
+    sel = mask.cpu().numpy() == 1
+    want[:] = [m[sel, 0].sum(), m[sel, 2].sum(), m[sel, 3].sum(), m[sel, 4].sum(), m[sel, 40:48].sum(), m[sel, 24:32].sum(),
+               sel.sum(), m[sel, 5].max()]
+    obs_before = env.obs.clone()
+    env.reset(mask)
+    got = stats.cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-9) and got[6] == sel.sum() and got[0] == want[0] and got[3] == want[3]
+    assert torch.equal(env.obs[mask == 0], obs_before[mask == 0])    # untouched envs keep their observation
+    st = env.get_state()
+    assert bool((st["t"][mask == 1] == 0).all()) and bool((st["t"][mask == 0] == 30).all())
+    env.set_episode_stats(None)
+    env.reset()
+    assert np.array_equal(stats.cpu().numpy(), got)
+
+
+def test_handle_on_non_current_device():
+    """A handle bound to cuda:1 works while cuda:0 is current, and no entry point changes the caller's device."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    e1 = BatchedGridEnv("cleanup_new", 64, 4, contract="CleanupContract", seed=3, device="cuda:1")
+    e0 = BatchedGridEnv("cleanup_new", 64, 4, contract="CleanupContract", seed=3, device="cuda")
+    assert e0.device.index == 0 and torch.cuda.current_device() == 0
+    o1, o0 = e1.reset(), e0.reset()
+    for t in range(20):
+        a0 = e0.random_actions(t, 9)
+        r1 = e1.step(a0.to("cuda:1"))
+        r0 = e0.step(a0)
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(r1[0].cpu(), r0[0].cpu()) and torch.equal(r1[1].cpu(), r0[1].cpu())
+    e1.close(); e0.close()
+    assert torch.cuda.current_device() == 0

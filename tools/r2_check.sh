@@ -1,0 +1,13 @@
+# round-2 regression on one GPU: gpu test-suite, smoke, the bench at two window sizes, the other configs, reference arm
+tag=${1:-r2a}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/${tag}_tests.log
+timeout 200 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1
+timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${tag}_bench20.json 2> gpurun_out/${tag}_bench20.err
+for c in harvest16k features1m harvestfeat1m selfdrive8; do
+  timeout 300 python bench.py --config $c --steps 200 --warmup 20 --no-cpu > gpurun_out/${tag}_bench_$c.json 2> gpurun_out/${tag}_bench_$c.err
+done
+timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.log
+nproc >> gpurun_out/${tag}_smi.log
