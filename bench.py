@@ -507,7 +507,7 @@ def main():
                 acc.append(env.step_times_ms())
                 run.after_step()
             kern_ms = (float(np.mean([a for a, _ in acc])), float(np.mean([b for _, b in acc])))
-        except Exception as exc:                                 # single-kernel fallback (SSD_GRID_KERNEL=v3) has no split
+        except Exception as exc:
             print("per-kernel timing unavailable: %s" % exc, file=sys.stderr)
         finally:
             env.enable_timing(False)
@@ -624,10 +624,9 @@ def main():
                          "share_of_timed_step": step_ms / (ms_total / K)},
         }
         if kern_ms is not None:
-            # the dominant kernel on its own: observation stream + the map / header words it reads (+ the map when the
-            # spawn changed it, ~1/3 of the steps)
-            mb = env.state_map_bytes
-            obs_alg = (n * 675 + mb + 56 + mb / 3.0) * E
+            # the dominant kernel on its own: the observation stream + the env's 128-byte hot line (read; its mask words
+            # written back when the spawn changed them)
+            obs_alg = (n * 675 + 128 + 32) * E
             line["roofline"]["kernels"] = [
                 {"name": "grid_logic_kernel", "ms": kern_ms[0]},
                 {"name": "grid_obs_kernel" + (" + grid_reward_kernel" if cfg.get("env") == "harvest_new" else ""), "ms": kern_ms[1],

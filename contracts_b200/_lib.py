@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
+# SSD_LIB_PATH: development only (A/B runs of differently built libraries); the shipped library is the in-tree one
+LIB_PATH = os.environ.get("SSD_LIB_PATH") or os.path.join(_HERE, "libssd_b200.so")
 
 SSD_ABI_VERSION = 3
 ENV_KIND = {"cleanup_new": 0, "harvest_new": 1, "cleanup": 2, "harvest": 3, "selfdrive": 4}

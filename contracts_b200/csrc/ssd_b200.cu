@@ -31,8 +31,8 @@ struct ssd_handle {
     CarParams cp;
     FeatParams fp;
     int grid_blocks;
-    int obs_blocks;          // two-kernel step (ssd_grid2.cuh): grid of the observe kernel; 0 = single-kernel step (v3)
-    int obs_vpl;             // 16-byte map vectors per lane in the observe kernel (1 or 2)
+    int obs_blocks;          // grid of the observe kernel (persistent: CTAs per SM x SMs, or fewer for small batches)
+    int logic_smem;          // dynamic shared memory of the logic kernel (cell table + per-warp mask copies)
     cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
@@ -50,35 +50,22 @@ struct ssd_handle {
     uint32_t recent_count[2];
     ssd_host_layout lay;
     uint32_t* d_counter;     // device step counter for SSD_STEP_AUTO: [0] index, [1] CTAs finished
-    bool rounds4;            // point lists fit 4 rounds of 32 (selects the step-kernel variant)
+    bool rounds4;            // point lists fit 4 rounds of 32 (selects the observe-kernel variant)
     int64_t launches;
     char err[512];
     std::vector<void*> dev_allocs;
 };
 
-typedef void (*step_kernel_t)(const GridParams, const StepIO);
-static step_kernel_t step_kernel_fn(int kind, bool rounds4, bool feat)
-{
-    if (kind == SSD_ENV_CLEANUP) {
-        if (rounds4) return feat ? grid_step_kernel<SSD_ENV_CLEANUP, 4, true> : grid_step_kernel<SSD_ENV_CLEANUP, 4, false>;
-        return feat ? grid_step_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, true> : grid_step_kernel<SSD_ENV_CLEANUP, MAX_POINT_ROUNDS, false>;
-    }
-    if (rounds4) return feat ? grid_step_kernel<SSD_ENV_HARVEST, 4, true> : grid_step_kernel<SSD_ENV_HARVEST, 4, false>;
-    return feat ? grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, true> : grid_step_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false>;
-}
-static const void* step_kernel_ptr(int kind, bool rounds4, bool feat) { return (const void*)step_kernel_fn(kind, rounds4, feat); }
-
 typedef void (*obs_kernel_t)(const GridParams, const StepIO, uint32_t*);
-template <int KIND, bool FEAT>
-static obs_kernel_t obs_pick(bool rounds4, int vpl)
+template <int KIND>
+static obs_kernel_t obs_pick(bool rounds4, bool feat)
 {
-    if (rounds4) return vpl == 1 ? grid_obs_kernel<KIND, 4, FEAT, 1> : grid_obs_kernel<KIND, 4, FEAT, 2>;
-    return vpl == 1 ? grid_obs_kernel<KIND, MAX_POINT_ROUNDS, FEAT, 1> : grid_obs_kernel<KIND, MAX_POINT_ROUNDS, FEAT, 2>;
+    if (rounds4) return feat ? grid_obs_kernel<KIND, 4, true> : grid_obs_kernel<KIND, 4, false>;
+    return feat ? grid_obs_kernel<KIND, MAX_POINT_ROUNDS, true> : grid_obs_kernel<KIND, MAX_POINT_ROUNDS, false>;
 }
-static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat, int vpl)
+static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat)
 {
-    if (kind == SSD_ENV_CLEANUP) return feat ? obs_pick<SSD_ENV_CLEANUP, true>(rounds4, vpl) : obs_pick<SSD_ENV_CLEANUP, false>(rounds4, vpl);
-    return feat ? obs_pick<SSD_ENV_HARVEST, true>(rounds4, vpl) : obs_pick<SSD_ENV_HARVEST, false>(rounds4, vpl);
+    return kind == SSD_ENV_CLEANUP ? obs_pick<SSD_ENV_CLEANUP>(rounds4, feat) : obs_pick<SSD_ENV_HARVEST>(rounds4, feat);
 }
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
@@ -191,9 +178,11 @@ static int setup_grid(ssd_handle* h)
     const int H = c.map_h, W = c.map_w, n = c.num_agents;
     if (H < 1 || W < 1 || H > 48 || W > 64) return fail(h, SSD_EINVAL, "map size %dx%d out of range (max 48x64)", H, W);
     if (!c.ascii_map || (int)h->ascii.size() != H * W) return fail(h, SSD_EINVAL, "ascii_map must hold map_h*map_w chars");
+    const bool cleanup = c.env_kind == SSD_ENV_CLEANUP;
     p.E = c.num_envs; p.n = n; p.H = H; p.W = W;
     p.Wp = round_up(W, 4); p.S = 8 + p.Wp + 8; p.TH = H + 2 * SSD_VIEW;
-    p.wpw = p.Wp / 4; p.wpw_magic = (65536u + p.wpw - 1) / p.wpw;
+    const int Hp = round_up(H, 4);
+    p.S2 = 8 + Hp + 8;
     p.s_magic = (uint32_t)((4294967296ull + p.S - 1) / p.S);
     p.map_bytes = round_up(H * p.Wp, 16);
     p.reward_mode = c.flags & (SSD_FLAG_COLLECTIVE_REWARD | SSD_FLAG_INEQUITY_AVERSE);
@@ -202,40 +191,63 @@ static int setup_grid(ssd_handle* h)
         return fail(h, SSD_EINVAL, "inequity_averse_reward needs more than one agent");
     p.alpha = c.env_params[0]; p.beta = c.env_params[1];
     p.hdr_bytes = p.reward_mode ? RO_XSIZE : RO_SIZE;
-    p.rec_stride = p.map_bytes + p.hdr_bytes;
+    p.rec_stride = round_up(p.hdr_bytes, 128);           // 512 (640 shaped): every env's hot line is one aligned 128-byte line
     p.kind = c.env_kind; p.contract = c.contract_kind; p.horizon = c.horizon;
     p.seed = c.seed; p.first_env_id = c.first_env_id;
     p.theta_low = c.theta_low; p.theta_high = c.theta_high; p.null_prob = c.null_prob;
-    p.F = c.env_kind == SSD_ENV_CLEANUP ? 12 + n : 10 + 2 * n;
+    p.F = cleanup ? 12 + n : 10 + 2 * n;
 
-    // parse the map like MapEnv.__init__ / CleanupEnv.__init__ / HarvestEnv.__init__
-    std::vector<uint16_t> apple, waste, spawn, apple_rc, waste_rc;
+    // parse the map like MapEnv.__init__ / CleanupEnv.__init__ / HarvestEnv.__init__.  Static part: walls, river, stream;
+    // dynamic part: apple points ('B' cleanup, 'A' harvest) and waste points ('H' / 'R'), in row-major (canonical) order.
+    p.tile_r16 = round_up(p.TH * p.S, 16);
+    const int tile2_bytes = round_up((p.Wp + 2 * SSD_VIEW) * p.S2, 16);
+    p.tile2_off = p.tile_r16;
+    p.g2_stage = p.tile2_off + tile2_bytes;
+    std::vector<uint16_t> spawn, apple_rc, waste_rc, apple_c, waste_c, cell_info(round_up(H * p.Wp, 8), 0);
+    std::vector<uint32_t> apple_pt(32 * MAX_POINT_ROUNDS, 0u), waste_pt(32 * MAX_POINT_ROUNDS, 0u);
+    std::vector<uint8_t> base_map(p.map_bytes, (uint8_t)C_OUTSIDE), tile0(p.g2_stage, (uint8_t)C_OUTSIDE);
     auto rc16 = [](int r, int col) { return (uint16_t)((r << 8) | col); };
-    std::vector<uint8_t> reset_map(p.map_bytes, (uint8_t)C_OUTSIDE);
-    int n_waste_start = 0, n_spawn_unique = 0;
-    auto off = [&](int r, int col) { return (uint16_t)((r + SSD_VIEW) * p.S + 8 + col); };
+    auto off = [&](int r, int col) { return (uint32_t)((r + SSD_VIEW) * p.S + 8 + col); };
+    auto off2 = [&](int r, int col) { return (uint32_t)((col + SSD_VIEW) * p.S2 + 8 + r); };
+    int n_spawn_unique = 0, n_waste_start = 0, na = 0, nw = 0;
     for (int r = 0; r < H; r++)
         for (int col = 0; col < W; col++) {
-            char ch = h->ascii[r * W + col];
-            uint8_t code = C_EMPTY;
-            if (ch == '@') code = C_WALL;
-            if (ch == 'P') { spawn.push_back(off(r, col)); n_spawn_unique++; if (c.env_kind == SSD_ENV_CLEANUP) spawn.push_back(off(r, col)); }
-            if (c.env_kind == SSD_ENV_CLEANUP) {
-                if (ch == 'B') { apple.push_back(off(r, col)); apple_rc.push_back(rc16(r, col)); }
-                if (ch == 'H') { code = C_WASTE; n_waste_start++; }
-                if (ch == 'R') code = C_RIVER;
-                if (ch == 'S') code = C_STREAM;
-                if (ch == 'H' || ch == 'R') { waste.push_back(off(r, col)); waste_rc.push_back(rc16(r, col)); }
-            } else if (ch == 'A') { apple.push_back(off(r, col)); apple_rc.push_back(rc16(r, col)); code = C_APPLE; }
-            reset_map[r * p.Wp + col] = code;
+            const char ch = h->ascii[r * W + col];
+            uint8_t code = C_EMPTY;                       // the cell's code with its dynamic content OFF
+            uint16_t info = 0;
+            if (ch == '@') { code = C_WALL; info = CI_WALL; }
+            if (ch == 'P') { spawn.push_back((uint16_t)off(r, col)); n_spawn_unique++; if (cleanup) spawn.push_back((uint16_t)off(r, col)); }
+            const bool apple_point = cleanup ? ch == 'B' : ch == 'A';
+            const bool waste_point = cleanup && (ch == 'H' || ch == 'R');
+            if (cleanup && ch == 'S') code = C_STREAM;
+            if (apple_point || waste_point) {
+                if ((apple_point ? na : nw) >= 32 * MAX_POINT_ROUNDS)
+                    return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * MAX_POINT_ROUNDS);
+                const uint32_t packed = off(r, col) | (off2(r, col) << 16);
+                if (apple_point) {
+                    if (!cleanup) p.reset_amask[na >> 5] |= 1u << (na & 31);       // harvest starts with every apple (harvest_new.py:143-156)
+                    apple_pt[na] = packed; apple_rc.push_back(rc16(r, col)); apple_c.push_back((uint16_t)(r * p.Wp + col));
+                    info = (uint16_t)(CI_APPLE | na); na++;
+                } else {
+                    code = C_RIVER;
+                    if (ch == 'H') { p.reset_wmask[nw >> 5] |= 1u << (nw & 31); n_waste_start++; }
+                    waste_pt[nw] = packed; waste_rc.push_back(rc16(r, col)); waste_c.push_back((uint16_t)(r * p.Wp + col));
+                    info = (uint16_t)(CI_WASTE | nw); nw++;
+                }
+            }
+            base_map[r * p.Wp + col] = code;
+            cell_info[r * p.Wp + col] = info;
+            tile0[off(r, col)] = code;
+            tile0[p.tile2_off + off2(r, col)] = code;
         }
     // canonical spawn order is the sorted list (row-major offsets are already sorted; duplicates adjacent)
     if (n_spawn_unique < n) return fail(h, SSD_EINVAL, "map has %d spawn points for %d agents", n_spawn_unique, n);
     if ((int)spawn.size() > 128) return fail(h, SSD_EUNSUPPORTED, "more than 128 spawn-list entries");
-    if ((int)apple.size() > 32 * MAX_POINT_ROUNDS || (int)waste.size() > 32 * MAX_POINT_ROUNDS)
-        return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * MAX_POINT_ROUNDS);
-    p.n_apple = (int)apple.size(); p.n_waste = (int)waste.size(); p.n_spawn = (int)spawn.size();
+    if ((p.S2 * (p.Wp + 2 * SSD_VIEW)) > 0xFFFF || p.TH * p.S > 0xFFFF) return fail(h, SSD_EUNSUPPORTED, "tile offsets exceed 16 bits");
+    p.n_apple = na; p.n_waste = nw; p.n_spawn = (int)spawn.size();
     p.n_waste_start = n_waste_start;
+    h->rounds4 = p.n_apple <= 128 && p.n_waste <= 128;
+    p.mw = h->rounds4 ? 4 : MAX_POINT_ROUNDS;
 
     std::vector<uint32_t> thr_apple;
     std::vector<uint8_t> waste_on;
@@ -249,32 +261,32 @@ static int setup_grid(ssd_handle* h)
 
     int rc;
     if ((rc = upload(h, pal, &p.pal))) return rc;
-    if ((rc = upload(h, apple, &p.apple_pts))) return rc;
-    if ((rc = upload(h, waste, &p.waste_pts))) return rc;
+    if ((rc = upload(h, apple_pt, &p.apple_pt))) return rc;
+    if ((rc = upload(h, waste_pt, &p.waste_pt))) return rc;
     if ((rc = upload(h, spawn, &p.spawn_pts))) return rc;
     if ((rc = upload(h, apple_rc, &p.apple_rc))) return rc;
     if ((rc = upload(h, waste_rc, &p.waste_rc))) return rc;
+    if ((rc = upload(h, apple_c, &p.apple_c))) return rc;
+    if ((rc = upload(h, waste_c, &p.waste_c))) return rc;
     if ((rc = upload(h, thr_apple, &p.thr_apple))) return rc;
     if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
-    if ((rc = upload(h, reset_map, &p.reset_map))) return rc;
+    if ((rc = upload(h, tile0, &p.tile0))) return rc;
+    if ((rc = upload(h, cell_info, &p.cell_info))) return rc;
+    if ((rc = upload(h, base_map, &p.base_map))) return rc;
 
-    // shared memory layout: CTA tables, then per warp [tile | rec slot 0 | rec slot 1 | stage | misc]
+    // shared memory of the observe / reset kernels: CTA tables, then per warp [T | T2 | stage | misc]
     p.obs_items = (SSD_OBSW * n + 3) / 4;
-    p.tile_r16 = round_up(p.TH * p.S, 16);
     p.stage_r16 = round_up(p.obs_items * 180 + 16, 16);
-    if (p.stage_r16 < (SCRATCH_DRAWS + SCRATCH_KEYS) * 4) p.stage_r16 = (SCRATCH_DRAWS + SCRATCH_KEYS) * 4;
-    p.off_rec = p.tile_r16;
-    p.off_stage = p.off_rec + 2 * p.rec_stride;
-    p.off_misc = p.off_stage + p.stage_r16;
-    p.warp_bytes = p.off_misc + MISC_BYTES;
+    if (p.stage_r16 < (SCRATCH_DRAWS + 2 * SCRATCH_KEYS) * 4) p.stage_r16 = (SCRATCH_DRAWS + 2 * SCRATCH_KEYS) * 4;
     p.sm_thr = 64;
     p.sm_won = p.sm_thr + round_up((p.n_waste + 1) * 4, 16);
-    p.sm_apple = p.sm_won + round_up(p.n_waste + 1, 16);
-    p.sm_waste = p.sm_apple + round_up(p.n_apple * 2, 16);
-    p.sm_apple_rc = p.sm_waste + round_up(p.n_waste * 2, 16);
+    p.sm_apple_rc = p.sm_won + round_up(p.n_waste + 1, 16);
     p.sm_waste_rc = p.sm_apple_rc + round_up(p.n_apple * 2, 16);
     p.sm_warp0 = p.sm_waste_rc + round_up(p.n_waste * 2, 16);
-    p.smem_bytes = p.sm_warp0 + GRID_WARPS * p.warp_bytes;
+    p.g2_misc = p.g2_stage + p.stage_r16;
+    p.g2_warp_bytes = p.g2_misc + MISC_BYTES;
+    p.g2_smem_bytes = p.sm_warp0 + OBS_WARPS * p.g2_warp_bytes;
+    static_assert(OBS_WARPS == GRID_WARPS, "the reset kernel shares the observe kernel's shared-memory layout");
 
     void* st = nullptr;
     size_t bytes = (size_t)p.E * p.rec_stride;
@@ -283,47 +295,31 @@ static int setup_grid(ssd_handle* h)
     CUDA_TRY(h, cudaMemset(st, 0, bytes));
     p.state = (uint8_t*)st;
 
-    // persistent grid: enough CTAs to fill every SM at the achievable occupancy
-    h->rounds4 = p.n_apple <= 128 && p.n_waste <= 128;
-    const void* reset_k = c.env_kind == SSD_ENV_CLEANUP ? (const void*)grid_reset_kernel<SSD_ENV_CLEANUP>
-                                                        : (const void*)grid_reset_kernel<SSD_ENV_HARVEST>;
-    CUDA_TRY(h, cudaFuncSetAttribute(reset_k, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    for (int feat = 0; feat < 2; feat++)
-        CUDA_TRY(h, cudaFuncSetAttribute(step_kernel_ptr(c.env_kind, h->rounds4, feat != 0),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
     int sms = 0, per_sm = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_ptr(c.env_kind, h->rounds4, false),
-                                                              GRID_THREADS, p.smem_bytes));
-    if (per_sm < 1) return fail(h, SSD_EUNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", p.smem_bytes);
+    const void* reset_k = cleanup ? (const void*)grid_reset_kernel<SSD_ENV_CLEANUP> : (const void*)grid_reset_kernel<SSD_ENV_HARVEST>;
+    CUDA_TRY(h, cudaFuncSetAttribute(reset_k, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reset_k, GRID_THREADS, p.g2_smem_bytes));
+    if (per_sm < 1) return fail(h, SSD_EUNSUPPORTED, "reset kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
     int want = (p.E + GRID_WARPS - 1) / GRID_WARPS;
     h->grid_blocks = want < sms * per_sm ? want : sms * per_sm;
 
-    // two-kernel step: observe kernel, per warp [tile | stage | misc]
-    {
-        const int Hp = round_up(H, 4);
-        p.hpw = Hp / 4; p.S2 = 8 + Hp + 8; p.tile2_off = p.tile_r16;
-        p.g2_stage = p.tile2_off + round_up((p.Wp + 2 * SSD_VIEW) * p.S2, 16);
-    }
-    p.g2_misc = p.g2_stage + p.stage_r16;
-    p.g2_warp_bytes = p.g2_misc + MISC_BYTES;
-    p.g2_smem_bytes = p.sm_warp0 + OBS_WARPS * p.g2_warp_bytes;
-    h->obs_blocks = 0;
-    const char* sel = getenv("SSD_GRID_KERNEL");
-    h->obs_vpl = (p.map_bytes / 16 + 31) / 32;
-    if (!(sel && strcmp(sel, "v3") == 0) && h->obs_vpl <= 2) {
-        int per_sm2 = 0;
-        for (int feat = 0; feat < 2; feat++)
-            CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0, h->obs_vpl),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false, h->obs_vpl),
-                                                                  OBS_WARPS * 32, p.g2_smem_bytes));
-        if (per_sm2 < 1) return fail(h, SSD_EUNSUPPORTED, "observe kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
-        const int want_obs = (p.E + OBS_WARPS - 1) / OBS_WARPS;
-        h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
-        if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d\n", OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks);
-        if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
-    }
+    // observe kernel: persistent grid at the achievable occupancy; logic kernel: cell table + per-warp mask copies
+    int per_sm2 = 0;
+    for (int feat = 0; feat < 2; feat++)
+        CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false),
+                                                              OBS_WARPS * 32, p.g2_smem_bytes));
+    if (per_sm2 < 1) return fail(h, SSD_EUNSUPPORTED, "observe kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
+    const int want_obs = (p.E + OBS_WARPS - 1) / OBS_WARPS;
+    h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
+    h->logic_smem = round_up(H * p.Wp * 2, 16) + LOGIC_WARPS * 2 * p.mw * 32 * 4;
+    const void* logic_k = cleanup ? (const void*)grid_logic_kernel<SSD_ENV_CLEANUP> : (const void*)grid_logic_kernel<SSD_ENV_HARVEST>;
+    CUDA_TRY(h, cudaFuncSetAttribute(logic_k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
+    if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d; logic smem %d B\n",
+                                     OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks, h->logic_smem);
+    if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
     return SSD_OK;
 }
 
@@ -434,12 +430,19 @@ __global__ void get_state_kernel(GridParams p, uint8_t* map, int32_t* pos, int32
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    const uint8_t* rec = p.state + (size_t)env * p.rec_stride;
-    const uint8_t* hdr = rec + p.map_bytes;
+    const uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
     const char chars[16] = { ' ', '@', 'A', 'H', 'R', 'S', '?', '?', '?', '?', '?', '?', '?', '?', '?', '?' };
-    if (map)
+    if (map) {                                             // the static map, then the dynamic cells from the masks
+        uint8_t* m = map + (size_t)env * p.H * p.W;
         for (int r = 0; r < p.H; r++)
-            for (int c = 0; c < p.W; c++) map[((size_t)env * p.H + r) * p.W + c] = (uint8_t)chars[(rec[r * p.Wp + c] >> 2) & 15];
+            for (int c = 0; c < p.W; c++) m[r * p.W + c] = (uint8_t)chars[(p.base_map[r * p.Wp + c] >> 2) & 15];
+        const uint32_t* am = reinterpret_cast<const uint32_t*>(hdr + RO_AMASK);
+        const uint32_t* wm = reinterpret_cast<const uint32_t*>(hdr + RO_WMASK);
+        for (int j = 0; j < p.n_apple; j++)
+            if ((am[j >> 5] >> (j & 31)) & 1u) { const int o = p.apple_c[j]; m[(o / p.Wp) * p.W + o % p.Wp] = 'A'; }
+        for (int j = 0; j < p.n_waste; j++)
+            if ((wm[j >> 5] >> (j & 31)) & 1u) { const int o = p.waste_c[j]; m[(o / p.Wp) * p.W + o % p.Wp] = 'H'; }
+    }
     for (int a = 0; a < p.n; a++) {
         uint32_t v = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[a];
         if (pos) { pos[((size_t)env * p.n + a) * 2] = (int)(v & 255u); pos[((size_t)env * p.n + a) * 2 + 1] = (int)((v >> 8) & 255u); }
@@ -454,21 +457,27 @@ __global__ void set_state_kernel(GridParams p, const uint8_t* map, const int32_t
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    uint8_t* rec = p.state + (size_t)env * p.rec_stride;
-    uint8_t* hdr = rec + p.map_bytes;
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
     uint32_t bad = 0;
     if (map) {
-        for (int i = 0; i < p.map_bytes; i++) rec[i] = (uint8_t)C_OUTSIDE;
+        // a map can differ from the static one only by apples on apple points and waste on waste points
+        const uint8_t* m = map + (size_t)env * p.H * p.W;
+        const char chars[16] = { ' ', '@', 'A', 'H', 'R', 'S', '?', '?', '?', '?', '?', '?', '?', '?', '?', '?' };
+        uint32_t am[MAX_POINT_ROUNDS] = {}, wm[MAX_POINT_ROUNDS] = {};
         int hc = 0;
         for (int r = 0; r < p.H; r++)
             for (int c = 0; c < p.W; c++) {
-                uint8_t ch = map[((size_t)env * p.H + r) * p.W + c];
-                uint8_t code = ch == ' ' ? C_EMPTY : ch == '@' ? C_WALL : ch == 'A' ? C_APPLE : ch == 'H' ? C_WASTE
-                             : ch == 'R' ? C_RIVER : ch == 'S' ? C_STREAM : 255;
-                if (code == 255) { bad |= 16; code = C_EMPTY; }
-                hc += code == C_WASTE;
-                rec[r * p.Wp + c] = code;
+                const uint8_t ch = m[r * p.W + c];
+                const uint32_t info = p.cell_info[r * p.Wp + c];
+                const uint8_t stat = (uint8_t)chars[(p.base_map[r * p.Wp + c] >> 2) & 15];
+                if ((info & CI_APPLE) && ch == 'A') am[(info & CI_IDX) >> 5] |= 1u << (info & 31u);
+                else if ((info & CI_WASTE) && ch == 'H') { wm[(info & CI_IDX) >> 5] |= 1u << (info & 31u); hc++; }
+                else if (ch != stat) bad |= 16;
             }
+        for (int q = 0; q < MAX_POINT_ROUNDS; q++) {
+            reinterpret_cast<uint32_t*>(hdr + RO_AMASK)[q] = am[q];
+            reinterpret_cast<uint32_t*>(hdr + RO_WMASK)[q] = wm[q];
+        }
         *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hc;
     }
     for (int a = 0; a < p.n; a++) {
@@ -488,14 +497,14 @@ __global__ void set_theta_kernel(GridParams p, const double* theta)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    *reinterpret_cast<double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA) = theta[env];
+    *reinterpret_cast<double*>(p.state + (size_t)env * p.rec_stride + RO_THETA) = theta[env];
 }
 
 __global__ void get_metrics_kernel(GridParams p, double* out)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    const uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
+    const uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
     double* o = out + (size_t)env * SSD_METRIC_STRIDE;
     double raw = 0;
     for (int a = 0; a < SSD_MAXN; a++) {
@@ -688,9 +697,9 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
     cudaStream_t s = (cudaStream_t)stream;
     if (p.beam) beam_clear_kernel<<<(p.E + 3) / 4, 128, 0, s>>>(p, mask_dev);                 // self.beam_pos = [] (map_env.py:316)
     if (p.kind == SSD_ENV_CLEANUP)
-        grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+        grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
     else
-        grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+        grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
     return check_launch(h, "reset");
 }
 
@@ -741,30 +750,28 @@ static int copy_rewards(ssd_handle* h, const StepIO& k, cudaStream_t s, const Ho
 
 // the kernels of one step on stream s.  The rewards / dones are final after the logic kernel for cleanup — BEFORE the
 // observe kernel — and after the reward kernel for harvest.
+// (Measured and dropped in round 2: launching a step as 2-8 env chunks with chunk c's observe kernel on a second stream
+// beside chunk c + 1's logic kernel, observe kernel capped at 72 registers so that a logic CTA fits beside three
+// observe CTAs: 0.264 ms -> 0.29 / 0.34 / 0.39 ms for 2 / 4 / 8 chunks, and the 72-register observe kernel alone is
+// 20 % slower; gpurun_out r2s sweep)
 static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const HostCopy* hc)
 {
     const GridParams& p = h->gp;
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
-    if (h->obs_blocks > 0) {
-        const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
-        if (h->timing) cudaEventRecord(h->tev[0], s);
-        if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
-        else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
-        h->launches++;
-        if (h->timing) cudaEventRecord(h->tev[1], s);
-        if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
-        if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
-        obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, h->obs_vpl)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
-        if (p.kind == SSD_ENV_HARVEST) {
-            h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
-            int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
-        }
-        if (h->timing) cudaEventRecord(h->tev[2], s);
-    } else {
-        step_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->grid_blocks, GRID_THREADS, p.smem_bytes, s>>>(p, k);
-        if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));
+    const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
+    if (h->timing) cudaEventRecord(h->tev[0], s);
+    if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
+    else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
+    h->launches++;
+    if (h->timing) cudaEventRecord(h->tev[1], s);
+    if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
+    if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
+    obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
+    if (p.kind == SSD_ENV_HARVEST) {
+        h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
     }
+    if (h->timing) cudaEventRecord(h->tev[2], s);
     return check_launch(h, "step");
 }
 
@@ -987,7 +994,6 @@ int ssd_record_beams(ssd_handle* h, int32_t enable)
     REQUIRE_GRID(h);
     GridParams& p = h->gp;
     if (!enable) { p.beam = nullptr; return SSD_OK; }
-    if (h->obs_blocks <= 0) return fail(h, SSD_EUNSUPPORTED, "record_beams: not available with the single-kernel step");
     if (!h->d_beam) {
         int rc = dev_zalloc(h, (size_t)p.E * p.map_bytes, &h->d_beam);
         if (rc) return rc;
@@ -1060,8 +1066,8 @@ static SolverParams solver_params(ssd_handle* h)
         s.theta = reinterpret_cast<uint8_t*>(h->fp.theta); s.theta_stride = 8;
     } else {
         const GridParams& p = h->gp;
-        s.episode = p.state + p.map_bytes + RO_EPISODE; s.episode_stride = p.rec_stride; s.episode_mask = 0xFFFFFFFFu;
-        s.theta = p.state + p.map_bytes + RO_THETA; s.theta_stride = p.rec_stride;
+        s.episode = p.state + RO_EPISODE; s.episode_stride = p.rec_stride; s.episode_mask = 0xFFFFFFFFu;
+        s.theta = p.state + RO_THETA; s.theta_stride = p.rec_stride;
     }
     return s;
 }
@@ -1235,7 +1241,6 @@ int ssd_get_step_times(ssd_handle* h, double* out_ms)
     if (!h->tev[0]) return fail(h, SSD_EINVAL, "ssd_get_step_times: timing was never enabled");
     float a = 0.f, b = 0.f;
     CUDA_TRY(h, cudaEventSynchronize(h->tev[2]));
-    if (h->obs_blocks <= 0) return fail(h, SSD_EUNSUPPORTED, "ssd_get_step_times: the single-kernel step has no per-kernel times");
     CUDA_TRY(h, cudaEventElapsedTime(&a, h->tev[0], h->tev[1]));
     CUDA_TRY(h, cudaEventElapsedTime(&b, h->tev[1], h->tev[2]));
     out_ms[0] = a; out_ms[1] = b;

@@ -1,16 +1,12 @@
-// ssd_grid.cuh — sm_100a kernels for the gridworld envs (cleanup_new / harvest_new).
+// ssd_grid.cuh — sm_100a kernels for the gridworld envs (cleanup_new / harvest_new): shared definitions, the spawn
+// and observation building blocks, and the reset kernel.  The step kernels are in ssd_grid2.cuh.
 //
-// Mapping: one WARP per environment, one LANE per agent for the move /
-// rotate / conflict logic (n <= 8, decisions are serial per env, so warp ballots + shuffles
-// give the reference's ordering without block barriers); all 32 lanes for the data-parallel
-// phases (tile expand, spawn scans, observation gather).  The map lives as a padded uint8
-// tile in shared memory (7 cells of C_OUTSIDE border = the view radius), agents are
-// painted into the high nibble.  All bulk HBM traffic goes through the bulk-copy (TMA) engine:
-// each warp prefetches the NEXT env's whole record (map + header) into a double-buffered
-// shared slot with cp.async.bulk + an mbarrier while it works on the current one, writes the
-// updated record back with one bulk store, and the rotated 15x15x3 windows are gathered
-// row-wise (4 output rows = 180 B per lane, conflict-free word stores) into a per-warp staging
-// buffer that leaves through one more bulk store per env.
+// State.  Everything that changes in a map is an apple on an apple point or waste on a waste point, so
+// an env's dynamic map state is two BITMASKS (bit j = point j of the canonical row-major point list holds an apple /
+// waste), kept in the first 128-byte line of the env's record together with the agents, t, episode, theta, flags and
+// #waste.  Walls, river, stream and the point lists are static per handle.  The step's decision logic works on that
+// one line + static tables; the observe kernel keeps a padded uint8 tile T of the map (7 cells of C_OUTSIDE border =
+// the view radius) AND its transpose T2 per warp in shared memory and only rewrites the dynamic cells for each env.
 //
 // Reference behaviour restated here (paths relative to the reference root):
 //   environments/map_env.py   step :216-304, update_moves :483-676, update_custom_moves :678-693,
@@ -27,72 +23,83 @@
 #define GRID_WARPS 8
 #endif
 #define GRID_THREADS (GRID_WARPS * 32)
-#define GRID_MIN_BLOCKS 3               // 24 warps / SM: registers <= 80, ~9 KB shared per warp
 #define SCRATCH_DRAWS 256               // u32 draws per warp scratch
 #define SCRATCH_KEYS 256                // u32 shuffle keys per warp scratch
-#define MAX_POINT_ROUNDS 8              // point lists are scanned 32 per round => <= 256 points
+#define MAX_POINT_ROUNDS 8              // point lists are handled 32 per round => <= 256 points, 8 mask words
 #define FULL 0xffffffffu
 
-// record layout after the map bytes (all offsets relative to rec + map_bytes)
+// record layout.  Bytes 0..127 are the HOT line (one coalesced 128-byte access per env), the episode accumulators follow.
 #define RO_AGENTS 0        // u32[8]: row | col << 8 | ori << 16
 #define RO_T 32            // i32
 #define RO_EPISODE 36      // u32
 #define RO_THETA 40        // f64
 #define RO_FLAGS 48        // u32
 #define RO_HCOUNT 52       // u32 (#waste cells, cleanup)
-#define RO_APPLES 56       // u32 total_apples_eaten
-#define RO_LOWDENS 60      // u32 low_density_apples_eaten
-#define RO_DIRT 64         // u32 dirt_cleaned
-#define RO_TRANSFERS 72    // f64 metrics['transfers']
-#define RO_SUM_TR 80       // f64[8]
-#define RO_TSUM_TR 144     // f64[8]
-#define RO_TSUM_RAW 208    // i64[8]
-#define RO_SUM_RAW 272     // i32[8]
-#define RO_AGENT_A 304     // u32[8] waste_cleaned | apples_consumed
-#define RO_AGENT_B 336     // u32[8] close_apples_consumed
-#define RO_SIZE 368
+#define RO_AMASK 64        // u32[8]: apple bitmask over the apple point list
+#define RO_WMASK 96        // u32[8]: waste bitmask over the waste point list (cleanup)
+#define RO_HOT 128
+#define RO_APPLES 128      // u32 total_apples_eaten
+#define RO_LOWDENS 132     // u32 low_density_apples_eaten
+#define RO_DIRT 136        // u32 dirt_cleaned
+#define RO_TRANSFERS 144   // f64 metrics['transfers']
+#define RO_SUM_TR 152      // f64[8]
+#define RO_TSUM_TR 216     // f64[8]
+#define RO_TSUM_RAW 280    // i64[8]
+#define RO_SUM_RAW 344     // i32[8]
+#define RO_AGENT_A 376     // u32[8] waste_cleaned | apples_consumed
+#define RO_AGENT_B 408     // u32[8] close_apples_consumed
+#define RO_SIZE 440
 // extension, present only when rewards are shaped (use_collective_reward / inequity_averse_reward,
 // map_env.py:289-301): the env rewards are float64 then, so their episode sums are too
-#define RO_XSUM 368        // f64[8] sum_t r
-#define RO_XTSUM 432       // f64[8] sum_t t * r
-#define RO_XRAW 496        // f64 metrics['raw_env_rewards']
-#define RO_XSIZE 512
+#define RO_XSUM 440        // f64[8] sum_t r
+#define RO_XTSUM 504       // f64[8] sum_t t * r
+#define RO_XRAW 568        // f64 metrics['raw_env_rewards']
+#define RO_XSIZE 576
 #define RM_COLLECTIVE 1
 #define RM_INEQUITY 2
 
+// static per-cell word of the logic kernel (cell_info[row * Wp + col])
+#define CI_IDX 0xFFu       // index in the apple / waste point list
+#define CI_WALL 0x2000u
+#define CI_APPLE 0x4000u   // the cell is an apple point
+#define CI_WASTE 0x8000u   // the cell is a waste point
+
 struct GridParams {
     int E, n, H, W, Wp, S, TH;
-    int wpw;                 // words per map row (Wp / 4)
-    uint32_t wpw_magic;      // ceil(65536 / wpw): q = (w * magic) >> 16 for w < 65536 / wpw
-    int map_bytes;           // H * Wp rounded up to 16
-    int rec_stride;          // map_bytes + hdr_bytes (multiple of 16: one bulk copy moves a record)
+    int map_bytes;           // H * Wp rounded up to 16: size of a compact map (beam overlay, views, get / set state)
+    int rec_stride;          // bytes per env record (512, or 640 when rewards are shaped)
     int hdr_bytes;           // RO_SIZE, or RO_XSIZE when rewards are shaped
+    int mw;                  // mask words per point list in use (4 or 8)
     int reward_mode;         // RM_* bits
     double alpha, beta;      // inequity aversion weights (map_env.py:71-72)
-    // shared memory layout.  CTA tables first, then one region per warp:
-    //   [tile | rec slot 0 | rec slot 1 | stage (obs staging, aliased by the spawn scratch) | misc]
-    int tile_r16, stage_r16, warp_bytes, off_rec, off_stage, off_misc;
-    int sm_thr, sm_won, sm_apple, sm_waste, sm_apple_rc, sm_waste_rc, sm_warp0, smem_bytes;
+    // shared memory of the observe / reset kernels: CTA tables first, then per warp [T | T2 | stage (obs staging, aliased
+    // by the spawn scratch) | misc]
+    int sm_thr, sm_won, sm_apple_rc, sm_waste_rc, sm_warp0;
+    int tile_r16, stage_r16, tile2_off, g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
+    int S2;                  // transposed tile: row stride 8 + Hp + 8
     int obs_items;           // ceil(15 n / 4): 4-row (180 B) work items of the observation gather
-    // observe kernel (ssd_grid2.cuh), per warp: [tile | stage | misc]
-    int g2_stage, g2_misc, g2_warp_bytes, g2_smem_bytes;
-    int S2, hpw, tile2_off;  // transposed tile: row stride 8 + Hp + 8, words per transposed row (Hp / 4), byte offset from T
     int kind, contract, horizon;
     int n_apple, n_waste, n_spawn, n_waste_start, F;
     uint32_t seed, first_env_id;
     double theta_low, theta_high, null_prob;
     uint32_t thr_harvest[4]; // SPAWN_PROB thresholds (harvest_new.py:34)
     uint32_t thr_waste;      // wasteSpawnProbability = 0.5
-    const uint32_t* pal;     // [16] packed RGB per tile byte value (cell codes 0..5, agents 6..13, outside 15)
     uint32_t s_magic;        // ceil(2^32 / S): row = umulhi(offset, s_magic)
-    const uint16_t* apple_pts;
-    const uint16_t* waste_pts;
-    const uint16_t* spawn_pts;
+    const uint32_t* pal;     // [16] packed RGB per tile byte value (cell codes 0..5, agents 6..13, outside 15)
+    const uint32_t* apple_pt;    // [256] offset in T | offset in T2 << 16 of each apple point (0 beyond the list)
+    const uint32_t* waste_pt;    // [256]
+    const uint16_t* spawn_pts;   // offsets in T
     const uint16_t* apple_rc;    // row << 8 | col of each apple point (feature_obs only)
     const uint16_t* waste_rc;
     const uint32_t* thr_apple;   // [n_waste + 1] apple spawn threshold by #waste
     const uint8_t* waste_on;     // [n_waste + 1]
-    const uint8_t* reset_map;    // [map_bytes] initial codes (walls + custom_reset)
+    const uint8_t* tile0;        // [tile_r16 + tile2 bytes]: static T | T2 with every dynamic cell OFF (apple point empty, waste point river)
+    const uint16_t* cell_info;   // [H * Wp] CI_* words (logic kernel)
+    const uint8_t* base_map;     // [map_bytes] compact static codes, dynamic cells OFF (views, get / set state)
+    const uint16_t* apple_c;     // compact offsets (row * Wp + col) of the points (views, get / set state)
+    const uint16_t* waste_c;
+    uint32_t reset_amask[MAX_POINT_ROUNDS];   // dynamic state of the reset map (harvest: every point holds an apple;
+    uint32_t reset_wmask[MAX_POINT_ROUNDS];   // cleanup: the 'H' cells), before the reset-time spawn
     uint8_t* state;
     uint8_t* beam;               // optional [E][map_bytes]: beam_pos of the last step as a char overlay (render only)
     double* stats;               // optional [8]: ssd_set_episode_stats accumulator (added to by the reset kernel)
@@ -139,8 +146,7 @@ __device__ __noinline__ double shaped_reward_warp(int mode, double alpha, double
 
 // per-warp misc area
 #define MISC_VDESC 0        // int4[8]: per-agent view descriptor {offset of out[0][0], pixel step, row step, 0}
-#define MISC_MBAR 128       // u64[2]: record-prefetch mbarriers
-#define MISC_BYTES 144
+#define MISC_BYTES 128
 
 struct StepIO {
     const uint8_t* actions;
@@ -174,94 +180,13 @@ struct EnvRng { uint32_t seed, env_id, episode, t; };
 // per-CTA copies of the static tables in shared memory
 struct SharedTables {
     const uint32_t* pal; const uint32_t* thr_apple; const uint8_t* waste_on;
-    const uint16_t* apple; const uint16_t* waste; const uint16_t* apple_rc; const uint16_t* waste_rc;
+    const uint16_t* apple_rc; const uint16_t* waste_rc;
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 __device__ __forceinline__ int dir_delta(int ori, int S)
 {
     return ori == ORI_UP ? -S : (ori == ORI_RIGHT ? 1 : (ori == ORI_DOWN ? S : -1));
-}
-
-// ---------------------------------------------------------------------------------------------
-// tile <-> HBM record
-__device__ __forceinline__ void tile_load(const GridParams& p, const uint8_t* rec, uint8_t* tile, int lane)
-{
-    const uint4* src = reinterpret_cast<const uint4*>(rec);
-    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
-    const int S4 = p.S >> 2, nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
-    for (int v = lane; v < nvec; v += 32) {
-        uint4 q = __ldg(src + v);
-        uint32_t w4[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int w = v * 4 + j;
-            if (w < nwords) {
-                int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-                int cw = w - row * p.wpw;
-                tw[(row + SSD_VIEW) * S4 + 2 + cw] = w4[j];
-            }
-        }
-    }
-}
-__device__ __forceinline__ void tile_store(const GridParams& p, uint8_t* rec, const uint8_t* tile, int lane)
-{
-    uint4* dst = reinterpret_cast<uint4*>(rec);
-    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-    const int S4 = p.S >> 2, nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
-    for (int v = lane; v < nvec; v += 32) {
-        uint32_t w4[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int w = v * 4 + j;
-            uint32_t x = TILE_FILL4;
-            if (w < nwords) {
-                int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-                int cw = w - row * p.wpw;
-                x = tw[(row + SSD_VIEW) * S4 + 2 + cw] & CODE_MASK4;   // strip agent paint / occupancy
-            }
-            w4[j] = x;
-        }
-        dst[v] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-    }
-}
-
-// shared-memory record slot <-> padded tile (step kernel; the record arrives / leaves by bulk copy).
-// Lane l moves map words l, l + 32, ...; the tile word of each is loop-invariant across envs, so the
-// first MAP_REG_WORDS of them are computed once per warp and kept in registers.
-#define MAP_REG_WORDS 6
-struct MapWords { int tw[MAP_REG_WORDS]; };
-__device__ __forceinline__ int map_tile_word(const GridParams& p, int w)
-{
-    int row = (int)(((uint32_t)w * p.wpw_magic) >> 16);
-    return (row + SSD_VIEW) * (p.S >> 2) + 2 + (w - row * p.wpw);
-}
-__device__ __forceinline__ MapWords map_words_init(const GridParams& p, int lane)
-{
-    MapWords m;
-#pragma unroll
-    for (int k = 0; k < MAP_REG_WORDS; k++) m.tw[k] = map_tile_word(p, lane + 32 * k);
-    return m;
-}
-__device__ __forceinline__ void tile_expand(const GridParams& p, const MapWords& m, const uint8_t* recbuf, uint8_t* tile, int lane)
-{
-    const uint32_t* rw = reinterpret_cast<const uint32_t*>(recbuf);
-    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
-    const int nwords = p.H * p.wpw;
-#pragma unroll
-    for (int k = 0; k < MAP_REG_WORDS; k++)
-        if (lane + 32 * k < nwords) tw[m.tw[k]] = rw[lane + 32 * k];
-    for (int w = lane + 32 * MAP_REG_WORDS; w < nwords; w += 32) tw[map_tile_word(p, w)] = rw[w];
-}
-__device__ __forceinline__ void tile_compress(const GridParams& p, const MapWords& m, uint8_t* recbuf, const uint8_t* tile, int lane)
-{
-    uint32_t* rw = reinterpret_cast<uint32_t*>(recbuf);
-    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-    const int nwords = p.H * p.wpw;
-#pragma unroll
-    for (int k = 0; k < MAP_REG_WORDS; k++)
-        if (lane + 32 * k < nwords) rw[lane + 32 * k] = tw[m.tw[k]] & CODE_MASK4;   // strip agent paint / occupancy
-    for (int w = lane + 32 * MAP_REG_WORDS; w < nwords; w += 32) rw[w] = tw[map_tile_word(p, w)] & CODE_MASK4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -415,133 +340,69 @@ __device__ __noinline__ uint32_t resolve_moves_slow(int lane, int n, uint32_t se
     return (err << 16) | (uint32_t)ao;
 }
 
-// update_moves (map_env.py:483-676).  Lane i < n holds agent i: `ao` tile offset of its cell.
-// Returns error bits.  On the fast path (no two movers share a target and no real move targets an
-// occupied cell) every mover simply moves, which is what the reference's first while-pass does.
-__device__ __forceinline__ uint32_t resolve_moves(int lane, int n, uint8_t* tile, const EnvRng& g,
-                                                  int& ao, bool has_move, int tgt)
+// ---------------------------------------------------------------------------------------------
+// Per-lane point registers: lane l owns points l, l + 32, ... of each list.  pt[q] = offset in T | offset in T2 << 16.
+template <int MW>
+struct PointRegs { uint32_t a[MW], w[MW]; };
+template <int MW>
+__device__ __forceinline__ PointRegs<MW> load_point_regs(const GridParams& p, int lane)
 {
-    const bool act_lane = lane < n;
-    const unsigned movers = __ballot_sync(FULL, has_move);
-    if (movers == 0) return 0;
-    uint32_t mval = has_move ? (uint32_t)tgt : (0xFFFF0000u | (uint32_t)lane);
-    unsigned same = __match_any_sync(FULL, mval);
-    bool contested = has_move && (__popc(same) > 1);
-    if (act_lane) tile[ao] |= OCC_BIT;             // co-located lanes write the same value
-    __syncwarp();
-    bool real = has_move && tgt != ao;
-    bool occupied = real && (tile[tgt] & OCC_BIT);
-    __syncwarp();
-    if (act_lane) tile[ao] &= 0x7F;
-    __syncwarp();
-    if (__ballot_sync(FULL, contested || occupied) == 0) {
-        if (real) ao = tgt;
-        return 0;
-    }
-    const uint32_t r = resolve_moves_slow(lane, n, g.seed, g.env_id, g.episode, g.t, ao, has_move, tgt, movers, contested);
-    ao = (int)(r & 0xFFFFu);
-    return r >> 16;
+    PointRegs<MW> r;
+#pragma unroll
+    for (int q = 0; q < MW; q++) { r.a[q] = __ldg(p.apple_pt + lane + 32 * q); r.w[q] = __ldg(p.waste_pt + lane + 32 * q); }
+    return r;
+}
+// bits of round q that belong to the list (point index < count)
+__device__ __forceinline__ uint32_t round_valid(int count, int q)
+{
+    const int left = count - 32 * q;
+    return left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+// write a dynamic cell into T and (when kept) T2
+__device__ __forceinline__ void put_cell(uint8_t* tile, uint8_t* tile2, uint32_t pt, uint32_t code)
+{
+    tile[pt & 0xFFFFu] = (uint8_t)code;
+    if (tile2) tile2[pt >> 16] = (uint8_t)code;
 }
 
 // ---------------------------------------------------------------------------------------------
-// update_custom_moves + update_map_fire (map_env.py:678-693, 721-814).  Occupancy bits must be set.
-// cls: 0 none, 1 FIRE, 2 CLEAN.  Returns #waste cells cleaned by all agents this step.
-__device__ __forceinline__ int fire_beams(int lane, int n, int S, uint8_t* tile, const EnvRng& g,
-                                          int ao, int ori, int cls, int& reward, int& cleaned)
-{
-    const bool act_lane = lane < n;
-    unsigned rem = __ballot_sync(FULL, act_lane && cls != 0);
-    if (!rem) return 0;
-    int total_cleaned = 0;
-    // shuffled firing order (map_env.py:684-685); irrelevant (and not drawn) when a single agent fires
-    uint32_t bkey = (uint32_t)lane;
-    if (rem & (rem - 1))
-        bkey = act_lane ? draw_u32_ool(g, g.t, SITE_BEAM_ORDER, (uint32_t)lane) : 0xFFFFFFFFu;
-    const bool ray_lane = lane < 15;
-    const int b = lane / 5, k = lane - 5 * b;
-    while (rem) {
-        bool mine = (rem >> lane) & 1u;
-        uint32_t kmin = __reduce_min_sync(FULL, mine ? bkey : 0xFFFFFFFFu);
-        unsigned cand = __ballot_sync(FULL, mine && bkey == kmin);
-        const int s = __ffs(cand) - 1;
-        rem &= ~(1u << s);
-        const int so = __shfl_sync(FULL, ao, s), sori = __shfl_sync(FULL, ori, s);
-        const bool sclean = __shfl_sync(FULL, cls, s) == 2;
-        const int d = dir_delta(sori, S), rt = dir_delta((sori + 1) & 3, S);
-        int cell = so + (b == 1 ? rt - d : (b == 2 ? -rt - d : 0)) + (k + 1) * d;
-        uint32_t code = ray_lane ? tile[cell] : (uint32_t)C_WALL;
-        uint32_t c = code & CODE_MASK;
-        bool pass = c != C_WALL && c != C_OUTSIDE;
-        bool agent_here = (code & OCC_BIT) != 0;
-        bool isH = c == C_WASTE;
-        unsigned stopm = __ballot_sync(FULL, ray_lane && (!pass || agent_here || (sclean && isH)));
-        unsigned raybits = (stopm >> (5 * b)) & 31u;
-        int first = raybits ? __ffs(raybits) - 1 : 5;
-        bool covered = ray_lane && pass && k <= first;
-        bool upd = covered && sclean && isH;
-        unsigned updm = __ballot_sync(FULL, upd);
-        unsigned hitm = __ballot_sync(FULL, covered && agent_here && !sclean);
-        if (upd) tile[cell] = (uint8_t)((code & OCC_BIT) | C_RIVER);
-        while (hitm) {                               // Agent.hit(b"F"): -50 (Agent.py:178-180,224-226)
-            int hl = __ffs(hitm) - 1; hitm &= hitm - 1;
-            int hc = __shfl_sync(FULL, cell, hl);
-            unsigned victims = __ballot_sync(FULL, act_lane && ao == hc);
-            if (lane == 31 - __clz(victims)) reward -= 50;
-        }
-        int nclean = __popc(updm);
-        if (lane == s) { if (sclean) cleaned = nclean; else reward -= 1; }
-        total_cleaned += nclean;
-        __syncwarp();
-    }
-    return total_cleaned;
-}
-
-// ---------------------------------------------------------------------------------------------
-// cleanup spawn (cleanup_new.py:322-349).  Occupancy bits must be set.  `t` = 0 at reset.
-// Updates hcount (#waste cells); returns whether the map changed.
+// cleanup spawn (cleanup_new.py:322-349).  Occupancy bits of the agents' cells must be set in T.  `t` = 0 at reset.
+// am / wm: the env's apple / waste masks (warp-uniform, updated); hcount: #waste cells (updated).  Returns whether
+// anything spawned.
 __device__ __forceinline__ bool cleanup_spawn_active(const SharedTables& tb, int hcount)
 {
     return tb.thr_apple[hcount] != 0 || tb.waste_on[hcount] != 0;
 }
-template <int ROUNDS>
-__device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile,
-                                              uint32_t* scratch, const EnvRng& g, uint32_t t, int& hcount)
+template <int MW>
+__device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile, uint8_t* tile2,
+                                              uint32_t* scratch, const EnvRng& g, uint32_t t, int& hcount,
+                                              const PointRegs<MW>& pr, uint32_t (&am)[MW], uint32_t (&wm)[MW])
 {
-    const uint16_t* sm_apple = tb.apple; const uint16_t* sm_waste = tb.waste;
     const uint32_t thrA = tb.thr_apple[hcount];
     const bool waste_on = tb.waste_on[hcount] != 0;
     if (thrA == 0 && !waste_on) return false;
-    bool spawned = false;
     uint32_t* draws = scratch;
     uint32_t* keys = scratch + SCRATCH_DRAWS;
     // apples: eligible = no agent there and not already 'A'; draw index = rank among eligible (:328-335)
-    unsigned eligm[ROUNDS];
+    unsigned eligm[MW];
     int M = 0;
 #pragma unroll
-    for (int q = 0; q < ROUNDS; q++) {
-        int j = lane + 32 * q;
-        bool e = false;
+    for (int q = 0; q < MW; q++) {
+        eligm[q] = 0;
         if (q * 32 < p.n_apple) {
-            if (j < p.n_apple) { uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE; }
-            eligm[q] = __ballot_sync(FULL, e);
+            const bool occ = (tile[pr.a[q] & 0xFFFFu] & OCC_BIT) != 0;            // beyond the list: offset 0, a border cell
+            eligm[q] = ~am[q] & round_valid(p.n_apple, q) & ~__ballot_sync(FULL, occ);
             M += __popc(eligm[q]);
-        } else eligm[q] = 0;
+        }
     }
     // waste candidates = non-'H' cells of waste_points (apple points and waste points are disjoint, so the apple
     // spawns below cannot change them)
-    unsigned candm[ROUNDS] = {};
+    unsigned candm[MW];
     int C = 0;
-    if (waste_on) {
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
-            int j = lane + 32 * q;
-            bool cnd = false;
-            if (q * 32 < p.n_waste) {
-                if (j < p.n_waste) cnd = (tile[sm_waste[j]] & CODE_MASK) != C_WASTE;
-                candm[q] = __ballot_sync(FULL, cnd);
-                C += __popc(candm[q]);
-            } else candm[q] = 0;
-        }
+    for (int q = 0; q < MW; q++) {
+        candm[q] = waste_on ? (~wm[q] & round_valid(p.n_waste, q)) : 0u;
+        C += __popc(candm[q]);
     }
     // one Philox pass for everything this spawn can need: the apple draws [0, M), the first waste draws [M, M + wfirst)
     // (the waste scan stops at its first success, p = 0.5) and the shuffle keys of the waste points
@@ -553,21 +414,22 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
                          SITE_SPAWN_DRAWS, (uint32_t)bl, bl < nblk ? reinterpret_cast<uint4*>(draws) + bl : nullptr,
                          SITE_WASTE_ORDER, (uint32_t)bl, bl < nkblk ? reinterpret_cast<uint4*>(keys) + bl : nullptr);
     __syncwarp();
+    bool apples = false;
     if (thrA) {
         int base = 0;
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
+        for (int q = 0; q < MW; q++) {
             if (q * 32 < p.n_apple) {
-                if ((eligm[q] >> lane) & 1u) {
-                    int r = base + __popc(eligm[q] & lanemask_lt(lane));
-                    if (draws[r] < thrA) { int cell = sm_apple[lane + 32 * q]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
-                }
+                bool sp = false;
+                if ((eligm[q] >> lane) & 1u) sp = draws[base + __popc(eligm[q] & lanemask_lt(lane))] < thrA;
+                if (sp) put_cell(tile, tile2, pr.a[q], C_APPLE);
+                const unsigned spm = __ballot_sync(FULL, sp);
+                am[q] |= spm;
+                apples = apples || spm != 0u;
                 base += __popc(eligm[q]);
             }
         }
-        __syncwarp();
     }
-    const bool apples = __any_sync(FULL, spawned);
     if (!waste_on || C == 0) return apples;
     // waste: shuffle waste_points (stateless: key per canonical index), scan non-'H' cells in that
     // order, draw continues at rank M; first success spawns and breaks (:338-348)
@@ -588,7 +450,7 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
     for (int it = 0; it <= kstar; it++) {
         uint32_t bk = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) {
+        for (int q = 0; q < MW; q++) {
             if ((candm[q] >> lane) & 1u) {
                 int j = lane + 32 * q; uint32_t kk = keys[j];
                 if (kk < bk || (kk == bk && j < bj)) { bk = kk; bj = j; }
@@ -600,10 +462,17 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
         // remove it from the candidate set (uniform update of the owning lane's bit)
         int ql = jmin >> 5, ll = jmin & 31;
 #pragma unroll
-        for (int q = 0; q < ROUNDS; q++) if (q == ql) candm[q] &= ~(1u << ll);
+        for (int q = 0; q < MW; q++) if (q == ql) candm[q] &= ~(1u << ll);
     }
-    if (lane == 0) { int cell = sm_waste[chosen]; tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_WASTE); }
-    __syncwarp();
+    {
+        const int ql = chosen >> 5, ll = chosen & 31;
+#pragma unroll
+        for (int q = 0; q < MW; q++)
+            if (q == ql) {
+                if (lane == ll) put_cell(tile, tile2, pr.w[q], C_WASTE);
+                wm[q] |= 1u << ll;
+            }
+    }
     hcount += 1;
     return true;
 }
@@ -612,21 +481,19 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
 // Every eligible point consumes one draw (by rank), but only a draw below the LARGEST spawn probability (0.05) can spawn
 // whatever the neighbour count is.  So the 3x3 neighbour counts (8 tile reads) are evaluated only for those ~5 % of the
 // eligible points, compacted into a list: one pass of the warp instead of one per 32 points.
-template <int ROUNDS>
-__device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint32_t* scratch,
-                                              const uint16_t* sm_apple, const EnvRng& g, uint32_t t)
+template <int MW>
+__device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint8_t* tile2, uint32_t* scratch,
+                                              const EnvRng& g, uint32_t t, const PointRegs<MW>& pr, uint32_t (&am)[MW])
 {
     const int S = p.S;
-    unsigned eligm[ROUNDS];
+    unsigned eligm[MW];
     int M = 0;
 #pragma unroll
-    for (int q = 0; q < ROUNDS; q++) {
+    for (int q = 0; q < MW; q++) {
         eligm[q] = 0;
         if (q * 32 < p.n_apple) {
-            const int j = lane + 32 * q;
-            bool e = false;
-            if (j < p.n_apple) { const uint32_t code = tile[sm_apple[j]]; e = !(code & OCC_BIT) && (code & CODE_MASK) != C_APPLE; }
-            eligm[q] = __ballot_sync(FULL, e);
+            const bool occ = (tile[pr.a[q] & 0xFFFFu] & OCC_BIT) != 0;
+            eligm[q] = ~am[q] & round_valid(p.n_apple, q) & ~__ballot_sync(FULL, occ);
             M += __popc(eligm[q]);
         }
     }
@@ -643,18 +510,19 @@ __device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uin
         }
         __syncwarp();                                                  // also orders the tile reads above
     }
-    // candidates: point index | draw rank << 16, compacted behind the draws (M <= 256 draws + M <= 256 entries)
+    // candidates: (round << 5 | lane) | draw rank << 16, compacted behind the draws (M <= 256 draws + M <= 256 entries)
     uint32_t* list = scratch + SCRATCH_DRAWS;
     const uint32_t thr_max = p.thr_harvest[3];                         // SPAWN_PROB is increasing (harvest_new.py:34)
     int base = 0, ncand = 0;
 #pragma unroll
-    for (int q = 0; q < ROUNDS; q++) {
+    for (int q = 0; q < MW; q++) {
         if (q * 32 < p.n_apple) {
             const bool el = (eligm[q] >> lane) & 1u;
             const int r = base + __popc(eligm[q] & lanemask_lt(lane));
             const bool c = el && scratch[r] < thr_max;
             const unsigned cm = __ballot_sync(FULL, c);
-            if (c) list[ncand + __popc(cm & lanemask_lt(lane))] = (uint32_t)(lane + 32 * q) | ((uint32_t)r << 16);
+            // the entry carries the point's offsets: the lane that evaluates it is not the lane that owns the point
+            if (c) { const int k = ncand + __popc(cm & lanemask_lt(lane)); list[k] = pr.a[q]; list[256 + k] = (uint32_t)(lane + 32 * q) | ((uint32_t)r << 16); }
             ncand += __popc(cm);
             base += __popc(eligm[q]);
         }
@@ -664,21 +532,29 @@ __device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uin
     // neighbour counts of the candidates on the PRE-spawn map (j*j + k*k <= APPLE_RADIUS(=2): the 3x3 block; the own cell
     // is not 'A'), decisions first, writes after all of them
     for (int k = lane; k < ncand; k += 32) {
-        const uint32_t ent = list[k];
-        const int cell = sm_apple[ent & 0xFFFFu];
+        const uint32_t pt = list[k], ent = list[256 + k];
+        const int cell = (int)(pt & 0xFFFFu);
         int cnt = 0;
 #pragma unroll
         for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
             for (int dc = -1; dc <= 1; dc++)
                 if (dr | dc) cnt += ((tile[cell + dr * S + dc] & CODE_MASK) == C_APPLE);
-        list[k] = scratch[ent >> 16] < p.thr_harvest[cnt < 3 ? cnt : 3] ? (uint32_t)cell : 0xFFFFFFFFu;
+        if (!(scratch[ent >> 16] < p.thr_harvest[cnt < 3 ? cnt : 3])) list[256 + k] = 0xFFFFFFFFu;
     }
     __syncwarp();
     bool spawned = false;
-    for (int k = lane; k < ncand; k += 32) {
-        const uint32_t cell = list[k];
-        if (cell != 0xFFFFFFFFu) { tile[cell] = (uint8_t)((tile[cell] & OCC_BIT) | C_APPLE); spawned = true; }
+    for (int k0 = 0; k0 < ncand; k0 += 32) {
+        const int k = k0 + lane;
+        const uint32_t ent = k < ncand ? list[256 + k] : 0xFFFFFFFFu;
+        if (ent != 0xFFFFFFFFu) { put_cell(tile, tile2, list[k], C_APPLE); spawned = true; }
+        // mask bits of the spawned points (point index = ent & 0xFFFF), gathered by round
+        const uint32_t j = ent & 0xFFFFu;
+#pragma unroll
+        for (int q = 0; q < MW; q++) {
+            uint32_t bit = (ent != 0xFFFFFFFFu && (j >> 5) == (uint32_t)q) ? (1u << (j & 31u)) : 0u;
+            am[q] |= __reduce_or_sync(FULL, bit);
+        }
     }
     __syncwarp();
     return __any_sync(FULL, spawned);
@@ -698,14 +574,16 @@ __device__ __forceinline__ int count_apples_r5(const uint8_t* tile, int o, int S
 
 // ---------------------------------------------------------------------------------------------
 // infos['feature_obs'] (cleanup_new.py:235-251, harvest_new.py:208-222).  Lists are the row-major
-// scans of the post-step map (compute_current_apples / _wastes); np.argmin takes the first minimum,
-// i.e. the smallest (L1 distance, list index).  Returns (dist << 16 | index) or 0xFFFFFFFF.
-__device__ __forceinline__ uint32_t closest_point(int lane, const uint8_t* tile, const uint16_t* pts,
-                                                  const uint16_t* rc, int npts, uint32_t code, int ar, int ac)
+// scans of the post-step map (compute_current_apples / _wastes) = the set bits of the masks in point order; np.argmin
+// takes the first minimum, i.e. the smallest (L1 distance, list index).  Returns (dist << 16 | index) or 0xFFFFFFFF.
+template <int MW>
+__device__ __forceinline__ uint32_t closest_point(int lane, const uint32_t (&m)[MW], const uint16_t* rc, int ar, int ac)
 {
     uint32_t best = 0xFFFFFFFFu;
-    for (int j = lane; j < npts; j += 32) {
-        if ((tile[pts[j]] & CODE_MASK) == code) {
+#pragma unroll
+    for (int q = 0; q < MW; q++) {
+        if ((m[q] >> lane) & 1u) {
+            const int j = lane + 32 * q;
             int r = rc[j] >> 8, c = rc[j] & 255;
             uint32_t key = ((uint32_t)(abs(r - ar) + abs(c - ac)) << 16) | (uint32_t)j;
             best = key < best ? key : best;
@@ -713,28 +591,22 @@ __device__ __forceinline__ uint32_t closest_point(int lane, const uint8_t* tile,
     }
     return __reduce_min_sync(FULL, best);
 }
-__device__ __forceinline__ int count_points(int lane, const uint8_t* tile, const uint16_t* pts, int npts, uint32_t code)
+template <int KIND, int MW>
+__device__ __forceinline__ void write_features(const GridParams& p, const SharedTables& tb, int lane, uint32_t hw /* agent word of lane < n */,
+                                               const uint32_t (&am)[MW], const uint32_t (&wm)[MW],
+                                               int cleaned, int total_close, int hcount, double* out)
 {
-    int cnt = 0;
-    for (int j0 = 0; j0 < npts; j0 += 32) {
-        int j = j0 + lane;
-        cnt += __popc(__ballot_sync(FULL, j < npts && (tile[pts[j]] & CODE_MASK) == code));
-    }
-    return cnt;
-}
-template <int KIND>
-__device__ __forceinline__ void write_features(const GridParams& p, const SharedTables& tb, int lane, const uint8_t* tile,
-                                               int ao, int ori, int cleaned, int total_close, int hcount, double* out)
-{
-    const int n = p.n, S = p.S;
-    const int my_r = ao / S - SSD_VIEW, my_c = ao % S - 8;
-    const int n_apples = count_points(lane, tile, tb.apple, p.n_apple, C_APPLE);
+    const int n = p.n;
+    const int my_r = (int)(hw & 255u), my_c = (int)((hw >> 8) & 255u), ori = (int)((hw >> 16) & 3u);
+    int n_apples = 0;
+#pragma unroll
+    for (int q = 0; q < MW; q++) n_apples += __popc(am[q]);
     int ca_r = 0, ca_c = 0, cw_r = 0, cw_c = 0;        // sentinel [0, 0] when the list is empty
     for (int a = 0; a < n; a++) {
         int ar = __shfl_sync(FULL, my_r, a), ac = __shfl_sync(FULL, my_c, a);
-        uint32_t ka = closest_point(lane, tile, tb.apple, tb.apple_rc, p.n_apple, C_APPLE, ar, ac);
+        uint32_t ka = closest_point<MW>(lane, am, tb.apple_rc, ar, ac);
         uint32_t kw = 0xFFFFFFFFu;
-        if (KIND == SSD_ENV_CLEANUP) kw = closest_point(lane, tile, tb.waste, tb.waste_rc, p.n_waste, C_WASTE, ar, ac);
+        if (KIND == SSD_ENV_CLEANUP) kw = closest_point<MW>(lane, wm, tb.waste_rc, ar, ac);
         if (lane == a) {
             if (ka != 0xFFFFFFFFu) { ca_r = tb.apple_rc[ka & 0xFFFFu] >> 8; ca_c = tb.apple_rc[ka & 0xFFFFu] & 255; }
             if (kw != 0xFFFFFFFFu) { cw_r = tb.waste_rc[kw & 0xFFFFu] >> 8; cw_c = tb.waste_rc[kw & 0xFFFFu] & 255; }
@@ -848,301 +720,76 @@ __device__ __forceinline__ void gather_obs(const GridParams& p, int lane, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, uint8_t* smem)
+__device__ __forceinline__ SharedTables load_shared_tables(const GridParams& p, uint8_t* smem, bool feat)
 {
     uint32_t* pal = reinterpret_cast<uint32_t*>(smem);          // [16]: 16 distinct banks, no replication needed
     uint32_t* thr = reinterpret_cast<uint32_t*>(smem + p.sm_thr);
     uint8_t* won = smem + p.sm_won;
-    uint16_t* apple = reinterpret_cast<uint16_t*>(smem + p.sm_apple);
-    uint16_t* waste = reinterpret_cast<uint16_t*>(smem + p.sm_waste);
     uint16_t* apple_rc = reinterpret_cast<uint16_t*>(smem + p.sm_apple_rc);
     uint16_t* waste_rc = reinterpret_cast<uint16_t*>(smem + p.sm_waste_rc);
     for (int i = threadIdx.x; i < 16; i += blockDim.x) pal[i] = __ldg(p.pal + i);
     for (int i = threadIdx.x; i <= p.n_waste; i += blockDim.x) { thr[i] = __ldg(p.thr_apple + i); won[i] = __ldg(p.waste_on + i); }
-    for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple[i] = __ldg(p.apple_pts + i);
-    for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste[i] = __ldg(p.waste_pts + i);
-    for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple_rc[i] = __ldg(p.apple_rc + i);
-    for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste_rc[i] = __ldg(p.waste_rc + i);
-    SharedTables t = { pal, thr, won, apple, waste, apple_rc, waste_rc };
+    if (feat) {
+        for (int i = threadIdx.x; i < p.n_apple; i += blockDim.x) apple_rc[i] = __ldg(p.apple_rc + i);
+        for (int i = threadIdx.x; i < p.n_waste; i += blockDim.x) waste_rc[i] = __ldg(p.waste_rc + i);
+    }
+    SharedTables t = { pal, thr, won, apple_rc, waste_rc };
     return t;
 }
-
-// =============================================================================================
-// STEP
-// ROUNDS: 32-point rounds the apple / waste point lists need (4 covers the stock cleanup map);
-// FEAT: the variant that also writes infos['feature_obs'] (kept out of the hot variant's code).
-template <int KIND, int ROUNDS, bool FEAT>
-__global__ void __launch_bounds__(GRID_THREADS, GRID_MIN_BLOCKS) grid_step_kernel(const GridParams p, const StepIO io)
+// this warp's [T | T2] <- the static tiles (every dynamic cell OFF)
+__device__ __forceinline__ void init_warp_tiles(const GridParams& p, uint8_t* tile, int lane)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const SharedTables tb = load_shared_tables(p, smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
-    uint8_t* recs = tile + p.off_rec;                 // two record slots (double buffer)
-    uint8_t* stage = tile + p.off_stage;
-    // the spawn scratch (draws + shuffle keys) aliases the observation staging buffer: both are
-    // dead outside their phase once the previous env's bulk store has been read out
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
-    int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + p.off_misc + MISC_MBAR);
-    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
-    if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();                                  // tables + barriers visible
-    const int n = p.n, S = p.S;
-    const bool act_lane = lane < n;
-    const int env_stride = gridDim.x * GRID_WARPS;
-    const uint32_t rec_bytes = (uint32_t)p.rec_stride;
-    const MapWords mw = map_words_init(p, lane);
-
-    int env = blockIdx.x * GRID_WARPS + warp;
-    // running global pointers of the current env (advanced by one grid stride per iteration)
-    uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
-    const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
-    const uint8_t* g_act = io.actions + (size_t)env * n + (act_lane ? lane : 0);
-    const size_t g_act_step = (size_t)env_stride * n;
-    uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
-    const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
-    int act_next = 4;
-    if (env < p.E) {
-        if (lane == 0) bulk_load(recs, g_rec, rec_bytes, mbar);
-        if (act_lane) act_next = *g_act;
+    const uint4* src = reinterpret_cast<const uint4*>(p.tile0);
+    for (int i = lane; i < (p.g2_stage >> 4); i += 32) reinterpret_cast<uint4*>(tile)[i] = __ldg(src + i);
+}
+// rewrite every dynamic cell of T (and T2) from the env's masks
+template <int MW>
+__device__ __forceinline__ void apply_masks(const GridParams& p, int lane, uint8_t* tile, uint8_t* tile2, const PointRegs<MW>& pr,
+                                            const uint32_t (&am)[MW], const uint32_t (&wm)[MW])
+{
+#pragma unroll
+    for (int q = 0; q < MW; q++) {
+        if (q * 32 < p.n_apple && lane + 32 * q < p.n_apple) put_cell(tile, tile2, pr.a[q], ((am[q] >> lane) & 1u) ? C_APPLE : C_EMPTY);
+        if (q * 32 < p.n_waste && lane + 32 * q < p.n_waste) put_cell(tile, tile2, pr.w[q], ((wm[q] >> lane) & 1u) ? C_WASTE : C_RIVER);
     }
-    for (uint32_t it = 0; env < p.E; env += env_stride, it++) {
-        const uint32_t slot = it & 1u;
-        uint8_t* rec = recs + slot * p.rec_stride;    // this env's record, in shared memory
-        uint8_t* hdr = rec + p.map_bytes;
-        // ---- prefetch the next env's record into the other slot (its previous contents left
-        //      through the bulk store of the previous iteration: wait until that has read it)
-        const int env_nx = env + env_stride;
-        int act = act_next;
-        if (env_nx < p.E) {
-            if (lane == 0) {
-                bulk_wait_read<1>();                  // all but the newest group (an observation store)
-                bulk_load(recs + (slot ^ 1u) * p.rec_stride, g_rec + g_rec_step, rec_bytes, mbar + (slot ^ 1u));
-            }
-            if (act_lane) act_next = g_act[g_act_step];
-        }
-        mbar_wait(mbar + slot, (it >> 1) & 1u);
-        tile_expand(p, mw, rec, tile, lane);
-        // ---- per-env scalars + agent registers
-        int t = *reinterpret_cast<const int*>(hdr + RO_T) + 1;                 // map_env.py:230
-        const uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
-        const double theta = *reinterpret_cast<const double*>(hdr + RO_THETA);
-        uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
-        int hcount = *reinterpret_cast<const int*>(hdr + RO_HCOUNT);
-        EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, (uint32_t)t };
-        int ao = 0, ori = 0;
-        if (act_lane) {
-            uint32_t a = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS)[lane];
-            ao = ((int)(a & 255u) + SSD_VIEW) * S + 8 + (int)((a >> 8) & 255u);
-            ori = (int)((a >> 16) & 3u);
-        } else act = 4;
-        __syncwarp();
-
-        // ---- action decode (Agent.py:8-16,161-162,198-199) + rotations (map_env.py:514-516)
-        int cls = 0;                          // 0 none, 1 FIRE, 2 CLEAN
-        bool has_move = false;
-        int tgt = ao;
-        uint32_t err = 0;
-        if (act_lane) {
-            if (act <= 4) {
-                has_move = true;
-                if (act < 4) {
-                    // egocentric -> world direction: LEFT ori+3, RIGHT ori+1, UP ori, DOWN ori+2 (rotate_action :844-853)
-                    int rel = (0x2013 >> (4 * act)) & 3;
-                    int cand = ao + dir_delta((ori + rel) & 3, S);
-                    uint32_t c = tile[cand] & CODE_MASK;
-                    if (c != C_WALL && c != C_OUTSIDE) tgt = cand;           // return_valid_pos (Agent.py:111-119)
-                }
-            } else if (act == 5) ori = (ori + 1) & 3;                          // TURN_CLOCKWISE
-            else if (act == 6) ori = (ori + 3) & 3;                            // TURN_COUNTERCLOCKWISE
-            else if (KIND == SSD_ENV_HARVEST) { if (act == 7) cls = 1; else { err |= 8; has_move = true; } }
-            else if (act == 7) cls = 2;
-            else if (act == 8) cls = 1;
-            else { err |= 8; has_move = true; }
-        }
-        err |= resolve_moves(lane, n, tile, g, ao, has_move, tgt);
-
-        // ---- stale-list infos (cleanup_new.py:220-223, harvest_new.py:190-199) on the start-of-step map
-        int eaten = 0, eaten_close = 0, total_close = 0;
-        int reward = 0, cleaned = 0;
-        // co-located agents (possible after unresolved conflicts) share one cell
-        const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
-        if (act_lane) {
-            bool on_apple = (tile[ao] & CODE_MASK) == C_APPLE;
-            if (on_apple && !(flags & RF_STALE_EMPTY)) {
-                eaten = 1;
-                if (KIND == SSD_ENV_HARVEST) eaten_close = count_apples_r5(tile, ao, S) < 4;
-            }
-            // consume in agent order: the lowest-index co-located agent eats (map_env.py:244-247)
-            if (on_apple && lane == __ffs(grp) - 1) reward += 1;
-        }
-        __syncwarp();
-        if (act_lane) {
-            uint32_t c = tile[ao];
-            if ((c & CODE_MASK) == C_APPLE) c = C_EMPTY;
-            tile[ao] = (uint8_t)(c | OCC_BIT);      // occupancy for beams + spawn eligibility
-        }
-        __syncwarp();
-
-        // ---- beams, spawning
-        int ncleaned = fire_beams(lane, n, S, tile, g, ao, ori, cls, reward, cleaned);
-        if (KIND == SSD_ENV_CLEANUP) {
-            hcount -= ncleaned;
-            if (cleanup_spawn_active(tb, hcount)) {
-                if (lane == 0) bulk_wait_read<0>();  // previous env's observation store has drained `stage` (= scratch)
-                __syncwarp();
-                cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, (uint32_t)t, hcount);
-            }
-        } else {
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-            harvest_spawn<ROUNDS>(p, lane, tile, scratch, tb.apple, g, (uint32_t)t);
-        }
-        if (KIND == SSD_ENV_HARVEST && act_lane) total_close = count_apples_r5(tile, ao, S);
-        if (FEAT) write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount,
-                                       io.feat + (size_t)env * n * p.F);
-
-        // ---- map back into the record slot (paint stripped)
-        tile_compress(p, mw, rec, tile, lane);
-
-        // ---- rewards + contract transfers (contract_list.py, two_stage_train.py:69-92), lane j = agent j
-        double base = (double)reward;
-        if (p.reward_mode)                             // shaped env rewards (map_env.py:289-301)
-            base = shaped_reward_warp(p.reward_mode, p.alpha, p.beta, n, act_lane ? reward : 0);
-        double tr = 0.0;
-        if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
-        else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (total_close < 4 && eaten_close > 0) ? theta : 0.0;
-        double r = base, total_tr = 0.0;
-        // Redistribution in the reference's order (two_stage_train.py:72-90).  When every transfer is
-        // +-0.0 the loop is the identity on r (and adds +0.0 to the totals), so it is skipped.
-        if (p.contract != SSD_CONTRACT_NONE && __ballot_sync(FULL, act_lane && tr != 0.0) != 0u) {
-            const double share = __ddiv_rn(tr, (double)(n - 1));      // transfers[i] / (len(acts) - 1)
-            for (int i = 0; i < n; i++) {
-                double ti = __shfl_sync(FULL, tr, i), qi = __shfl_sync(FULL, share, i);
-                r = (i == lane) ? __dsub_rn(r, ti) : __dadd_rn(r, qi);
-                total_tr = __dadd_rn(total_tr, ti);
-            }
-        }
-        const bool done = t == p.horizon;
-        double raw_step = 0.0;
-        if (p.reward_mode)
-            for (int i = 0; i < n; i++) raw_step = __dadd_rn(raw_step, __shfl_sync(FULL, base, i));
-        if (act_lane) {
-            size_t o = (size_t)env * n + lane;
-            if (io.rew) io.rew[o] = r;
-            if (io.base_rew) io.base_rew[o] = base;
-            if (io.transfers) io.transfers[o] = tr;
-            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] =
-                (uint32_t)eaten | ((uint32_t)(KIND == SSD_ENV_CLEANUP ? cleaned : eaten_close) << 8) | ((uint32_t)total_close << 16);
-            // agent record + accumulators (in the shared record slot)
-            uint32_t trow = __umulhi((uint32_t)ao, p.s_magic);
-            uint32_t row = trow - SSD_VIEW, col = (uint32_t)ao - trow * (uint32_t)S - 8u;
-            reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
-            if (p.reward_mode) {
-                double* xs = reinterpret_cast<double*>(hdr + RO_XSUM) + lane;
-                double* xt = reinterpret_cast<double*>(hdr + RO_XTSUM) + lane;
-                *xs = __dadd_rn(*xs, base);
-                *xt = __dadd_rn(*xt, __dmul_rn((double)(t - 1), base));
-            } else if (reward != 0) {
-                reinterpret_cast<int*>(hdr + RO_SUM_RAW)[lane] += reward;
-                reinterpret_cast<long long*>(hdr + RO_TSUM_RAW)[lane] += (long long)(t - 1) * reward;
-            }
-            if (p.contract != SSD_CONTRACT_NONE) {
-                const double tm1 = (double)(t - 1);
-                double* st = reinterpret_cast<double*>(hdr + RO_SUM_TR) + lane;
-                double* tt = reinterpret_cast<double*>(hdr + RO_TSUM_TR) + lane;
-                *st = __dadd_rn(*st, r);
-                *tt = __dadd_rn(*tt, __dmul_rn(tm1, r));
-            }
-            if (KIND == SSD_ENV_CLEANUP) { if (cleaned) reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)cleaned; }
-            else {
-                reinterpret_cast<uint32_t*>(hdr + RO_AGENT_A)[lane] += (uint32_t)eaten;
-                reinterpret_cast<uint32_t*>(hdr + RO_AGENT_B)[lane] += (uint32_t)eaten_close;
-            }
-        }
-        unsigned eatm = __ballot_sync(FULL, eaten != 0), closem = __ballot_sync(FULL, eaten_close != 0);
-        unsigned errm = __ballot_sync(FULL, err != 0);
-        uint32_t errbits = __reduce_or_sync(FULL, err);
-        if (lane == 0) {
-            *reinterpret_cast<int*>(hdr + RO_T) = t;
-            *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = (flags & ~RF_STALE_EMPTY) | (errm ? (errbits << RF_ERR_SHIFT) : 0u);
-            *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
-            *reinterpret_cast<uint32_t*>(hdr + RO_APPLES) += (uint32_t)__popc(eatm);
-            if (KIND == SSD_ENV_HARVEST) *reinterpret_cast<uint32_t*>(hdr + RO_LOWDENS) += (uint32_t)__popc(closem);
-            else *reinterpret_cast<uint32_t*>(hdr + RO_DIRT) += (uint32_t)ncleaned;
-            if (p.contract != SSD_CONTRACT_NONE) {
-                double* mt = reinterpret_cast<double*>(hdr + RO_TRANSFERS);
-                *mt = __dadd_rn(*mt, total_tr);
-            }
-            if (p.reward_mode) {                       // raw_rewards = ((0 + r0) + r1) + ... (cleanup_new.py:228-232)
-                double* xr = reinterpret_cast<double*>(hdr + RO_XRAW);
-                *xr = __dadd_rn(*xr, raw_step);
-            }
-            if (io.done) io.done[env] = done ? 1 : 0;
-            if (io.c_done) io.c_done[env] = done ? 1 : 0;
-        }
-        if (io.c_rew8) {                               // compact result block (ssd_step_host_async), lane = agent
-            int v = 0;
-            const bool fits = reward_fits_i8(r, v);
-            const bool sparse = __ballot_sync(FULL, act_lane && !fits) != 0u;
-            if (act_lane) io.c_rew8[(size_t)env * n + lane] = (int8_t)(fits ? v : -128);
-            if (sparse) {
-                uint32_t slot = 0;
-                if (lane == 0) slot = atomicAdd(io.c_count, 1u);
-                slot = __shfl_sync(FULL, slot, 0);
-                uint8_t* rec_o = io.c_rec + (size_t)slot * (8 + 8 * n);
-                if (lane == 0) *reinterpret_cast<int2*>(rec_o) = make_int2(env, 0);
-                if (act_lane) reinterpret_cast<double*>(rec_o + 8)[lane] = r;
-            }
-        }
-        // ---- the record leaves with one bulk store
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_store(g_rec, rec, rec_bytes);
-
-        // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261).
-        // Palette index 6 + i = agent i; the interior of the tile is rewritten by the next tile_expand.
-        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
-        // gather_obs: waits (lane 0) until at most the record store above is still in flight, syncs the warp
-        gather_obs<1>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
-        g_rec += g_rec_step; g_act += g_act_step; g_obs += g_obs_step;
-        __syncwarp();
-    }
-    if (lane == 0) bulk_wait_read<0>();      // smem must outlive the async bulk reads
 }
 
 // =============================================================================================
-// RESET: setup_agents + reset_map + custom_reset + reset-time spawn + contract sample + reset obs
+// RESET: setup_agents + reset_map + custom_reset + reset-time spawn + contract sample + reset obs.  One warp per env;
+// the warp's envs are env0 + i * estride, their mask bytes are read 32 at a time (one round trip, one ballot), so a
+// sparse mask — a vectorised sampler in steady state resets ~E / horizon envs per step — costs a few loads per warp.
 template <int KIND>
 __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridParams p, const uint8_t* mask,
                                                                   uint8_t* obs, long long obs_stride)
 {
+    constexpr int MW = MAX_POINT_ROUNDS;
     extern __shared__ __align__(16) uint8_t smem[];
-    const SharedTables tb = load_shared_tables(p, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tile = smem + p.sm_warp0 + warp * p.warp_bytes;
-    uint8_t* stage = tile + p.off_stage;
+    const int env0 = blockIdx.x * GRID_WARPS + warp, estride = gridDim.x * GRID_WARPS;
+    // nothing to do for this CTA (steady state: most of them)?  Leave before the table / tile set-up.
+    {
+        bool any = false;
+        for (long long e = env0 + (long long)lane * estride; e < p.E; e += 32ll * estride) any = any || !mask || mask[e];
+        if (!__syncthreads_or(any)) return;
+    }
+    const SharedTables tb = load_shared_tables(p, smem, false);
+    uint8_t* tile = smem + p.sm_warp0 + warp * p.g2_warp_bytes;
+    uint8_t* stage = tile + p.g2_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
-    int4* vdesc = reinterpret_cast<int4*>(tile + p.off_misc + MISC_VDESC);
-    for (int i = lane; i < (p.tile_r16 >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;
+    int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
+    const PointRegs<MW> pr = load_point_regs<MW>(p, lane);
+    init_warp_tiles(p, tile, lane);
     __syncthreads();
     const int n = p.n, S = p.S;
     const bool act_lane = lane < n;
 
-    // The warp's envs are env0 + i * estride.  The mask bytes of 32 of them are read at once (one round trip, one
-    // ballot), so a sparse mask — a vectorised sampler in steady state resets ~E / horizon envs per step — costs a
-    // few loads per warp instead of one dependent load per env.
-    const int env0 = blockIdx.x * GRID_WARPS + warp, estride = gridDim.x * GRID_WARPS;
     for (int i0 = 0; env0 + (long long)i0 * estride < p.E; i0 += 32) {
       const long long el = env0 + (long long)(i0 + lane) * estride;
       unsigned todo = __ballot_sync(FULL, el < p.E && (!mask || mask[el]));
       while (todo) {
         const int env = env0 + (i0 + __ffs(todo) - 1) * estride;
         todo &= todo - 1;
-        uint8_t* rec = p.state + (size_t)env * p.rec_stride;
-        uint8_t* hdr = rec + p.map_bytes;
+        uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
         uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
         uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
         if (p.stats && (flags & 0x80000000u)) {       // a finished episode is replaced: hand its accumulators over
@@ -1199,18 +846,20 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
             int o = rdraw == 0 ? ORI_LEFT : (rdraw == 1 ? ORI_RIGHT : (rdraw == 2 ? ORI_UP : ORI_DOWN));
             if (lane == i) { ao = cell; ori = o; }
         }
-        // ---- reset_map + custom_reset: copy the initial map, mark occupancy, reset-time spawn (map_env.py:319-320)
-        tile_load(p, p.reset_map, tile, lane);
+        // ---- reset_map + custom_reset: the initial dynamic state, occupancy, reset-time spawn (map_env.py:319-320)
+        uint32_t am[MW], wm[MW];
+#pragma unroll
+        for (int q = 0; q < MW; q++) { am[q] = p.reset_amask[q]; wm[q] = p.reset_wmask[q]; }
+        apply_masks<MW>(p, lane, tile, nullptr, pr, am, wm);
         if (lane == 0) bulk_wait_read<0>();          // `stage` doubles as the spawn scratch
         __syncwarp();
-        if (act_lane) tile[ao] |= OCC_BIT;
+        if (act_lane) tile[ao] |= OCC_BIT;           // co-located lanes write the same value
         __syncwarp();
         int hcount = p.n_waste_start;
-        if (KIND == SSD_ENV_CLEANUP) cleanup_spawn<MAX_POINT_ROUNDS>(p, tb, lane, tile, scratch, g, 0u, hcount);
-        else harvest_spawn<MAX_POINT_ROUNDS>(p, lane, tile, scratch, tb.apple, g, 0u);
-        tile_store(p, rec, tile, lane);
+        if (KIND == SSD_ENV_CLEANUP) cleanup_spawn<MW>(p, tb, lane, tile, nullptr, scratch, g, 0u, hcount, pr, am, wm);
+        else harvest_spawn<MW>(p, lane, tile, nullptr, scratch, g, 0u, pr, am);
         __syncwarp();
-        if (act_lane) tile[ao] &= CODE_MASK;              // MapEnv.reset never paints agents into the colour grid
+        if (act_lane) tile[ao] &= CODE_MASK;              // MapEnv.reset never paints agents into the colour grid; the tile is clean again
         __syncwarp();
         if (obs) gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, obs + (size_t)env * (size_t)obs_stride);
 
@@ -1222,13 +871,19 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
             theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1))
                                        : p.theta_low;
         }
-        // ---- record header
+        // ---- record: zero everything, then the hot line
+        for (int i = lane; i < p.hdr_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(hdr)[i] = 0u;
+        __syncwarp();
         if (act_lane) {
             uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
             reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
         }
-        for (int i = lane; i < (p.hdr_bytes - RO_T) / 4; i += 32) reinterpret_cast<uint32_t*>(hdr + RO_T)[i] = 0u;
-        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < MW; q++)
+            if (lane == q) {
+                reinterpret_cast<uint32_t*>(hdr + RO_AMASK)[q] = am[q];
+                reinterpret_cast<uint32_t*>(hdr + RO_WMASK)[q] = wm[q];
+            }
         if (lane == 0) {
             *reinterpret_cast<uint32_t*>(hdr + RO_EPISODE) = episode;
             *reinterpret_cast<double*>(hdr + RO_THETA) = theta;

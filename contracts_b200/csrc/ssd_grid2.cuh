@@ -1,24 +1,23 @@
-// ssd_grid2.cuh — the gridworld step as two kernels (v5): LOGIC (lane = env) + OBSERVE (warp = env).
+// ssd_grid2.cuh — the gridworld step as two kernels: LOGIC (lane = env) + OBSERVE (warp = env).
 //
 // Why two mappings.  The reference's per-env decision logic (update_moves, consume, beams, reward
-// redistribution) is serial and tiny (n <= 8 agents).  Run with a warp per env (v3, grid_step_kernel) it
-// keeps 8 of 32 lanes busy and costs ~600 warp-instructions per env; run with a lane per env it costs
-// ~200, but a fused kernel that alternates both mappings inside one warp (v4, measured: 884 instead of
-// 1411 warp-instructions per env, yet 0.49-0.64 ms instead of 0.36 ms) needs the 32 maps of a chunk in
-// shared memory and is left with 6-13 warps per SM.  So the step is split:
+// redistribution) is serial and tiny (n <= 8 agents).  Run with a warp per env it keeps 8 of 32 lanes busy and costs
+// ~600 warp-instructions per env; run with a lane per env it costs ~200, but a fused kernel that alternates both mappings
+// inside one warp (measured in round 1: 884 instead of 1411 warp-instructions per env, yet 0.49-0.64 ms instead of
+// 0.36 ms) is left with 6-13 warps per SM.  So the step is split:
 //
-//   grid_logic_kernel    one THREAD per env, no shared-memory staging: action decode, rotations, moves,
-//                        consume, beams on the env's compact map in global memory (each thread touches a few
-//                        dozen bytes of its own 464-byte map; L1/L2 serve them), then — cleanup — contract
-//                        transfers, rewards, outputs and the record header; the episode accumulators are
-//                        updated with fire-and-forget REDs.  E / 148 = 886 envs per SM fit in one wave, so the
-//                        kernel's time is one thread's dependency chain.
+//   grid_logic_kernel    one THREAD per env.  It reads the env's 128-byte hot line (agents, t, episode, theta, flags,
+//                        #waste, apple / waste bitmasks) and NOTHING else of the env: walls and "which point of which list
+//                        is this cell" come from a static per-cell table in shared memory, apples / waste from the masks.
+//                        Action decode, rotations, moves, consume, beams, then — cleanup — contract transfers, rewards,
+//                        outputs; the episode accumulators are updated with fire-and-forget REDs.
 //                        Envs whose moves are contested (a few %) are resolved by the whole warp, lane =
 //                        agent, with the literal reference ordering (resolve_moves_slow).
-//   grid_obs_kernel      one WARP per env, 24 warps per SM: the next env's map + header words are prefetched into
-//                        registers while the current env is processed; map -> padded tile, spawn scans (ballot
-//                        ranks, one interleaved two-chain Philox pass), paint, transposed tile, observation gather
-//                        and one bulk async store of the n 15x15x3 windows.  This is the HBM-bound part.
+//   grid_obs_kernel      one WARP per env, 24 warps per SM.  Each warp keeps the padded map tile T AND its transpose T2 in
+//                        shared memory for its whole life: per env it rewrites only the dynamic cells (apple / waste
+//                        points, from the masks) and the agents' cells, runs the spawn (ballot ranks over mask words, one
+//                        interleaved two-chain Philox pass), and gathers the n 15x15x3 windows into one bulk async store.
+//                        The next env's hot line is prefetched (one coalesced 128-byte load) meanwhile.  HBM-bound part.
 //   grid_reward_kernel   harvest only: the contract transfer needs total_close_apples of the post-spawn
 //                        map, so transfers / rewards / header run after grid_obs_kernel (thread per env).
 //
@@ -53,8 +52,13 @@ __device__ __forceinline__ uint32_t rc_lex(uint32_t rc) { return ((rc & 255u) <<
 __device__ __forceinline__ int ori_dr(int d) { return d == ORI_UP ? -1 : (d == ORI_DOWN ? 1 : 0); }
 __device__ __forceinline__ int ori_dc(int d) { return d == ORI_RIGHT ? 1 : (d == ORI_LEFT ? -1 : 0); }
 
-// count_apples_in_radius(5, loc) on the compact map (explicit bounds): harvest_new.py:326-336
-__device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, int H, int W, int Wp)
+// bit `idx` of a lane-strided mask array in shared memory (word w of this thread's env at mk[w * 32])
+__device__ __forceinline__ uint32_t mask_bit(const uint32_t* mk, uint32_t idx) { return (mk[(idx >> 5) * 32] >> (idx & 31u)) & 1u; }
+// does the cell with static word c hold an apple / waste?  (branch-free: the list bit ANDed with "is such a point")
+__device__ __forceinline__ uint32_t cell_has(const uint32_t* mk, uint32_t c, int kind_shift) { return (c >> kind_shift) & mask_bit(mk, c & CI_IDX); }
+
+// count_apples_in_radius(5, loc) (explicit bounds): harvest_new.py:326-336
+__device__ __noinline__ int g2_count_r5(const uint16_t* ci, const uint32_t* amk, int row, int col, int H, int W, int Wp)
 {
     int cnt = 0;
 #pragma unroll
@@ -63,12 +67,12 @@ __device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, in
         for (int dc = -2; dc <= 2; dc++)
             if (dr * dr + dc * dc <= 5) {
                 int r = row + dr, c = col + dc;
-                if ((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W) cnt += ((map[r * Wp + c] & CODE_MASK) == C_APPLE);
+                if ((unsigned)r < (unsigned)H && (unsigned)c < (unsigned)W) cnt += (int)cell_has(amk, ci[r * Wp + c], 14);
             }
     return cnt;
 }
 
-// one shooter's beam (update_map_fire, map_env.py:721-814) on the env's compact map in global memory.
+// one shooter's beam (update_map_fire, map_env.py:721-814).
 //
 // In the shooter's frame (along = steps in the firing direction, across = steps to its right) the three rays are
 //   centre  across  0, along 1..5      right  across +1, along 0..4      left  across -1, along 0..4
@@ -76,11 +80,10 @@ __device__ __noinline__ int g2_count_r5(const uint8_t* map, int row, int col, in
 // AGENT, not per cell: with x = (drow + 64) | (dcol + 64) << 8 relative to the shooter, one PRMT (selector by
 // orientation) over x and 0x8080 - x gives y = (along + 64) | (across + 64) << 8, and z = y - 0x3F40 is
 // along (left ray), 0x100 + along (centre) or 0x200 + along (right) exactly for the agents on a ray: bit
-// (z & 7) + 8 (z >> 8) of a 32-bit occupancy mask.  The 15 ray cells are loaded up front (independent loads, one
-// memory round trip; cells outside the map read as walls) and classified through 32-bit lookup words shifted by
-// the cell code, so a ray is walked with three 5-bit masks: a ray stops at its first wall / agent / (CLEAN beam)
-// waste cell (:785-805).  The rays are distinct lines, so applying H -> R immediately equals the reference's
-// deferred `updates` list.  Returns the number of cleaned cells.
+// (z & 7) + 8 (z >> 8) of a 32-bit occupancy mask.  The 15 ray cells' static words come from the shared-memory cell table
+// (cells outside the map count as walls), waste from the env's mask, so a ray is walked with three 5-bit masks: a ray
+// stops at its first wall / agent / (CLEAN beam) waste cell (:785-805).  The rays are distinct lines, so applying
+// H -> R immediately equals the reference's deferred `updates` list.  Returns the number of cleaned cells.
 #define RAY_L 0            // mask bit of cell i of the left / centre / right ray: RAY_x + i (centre: along = i + 1)
 #define RAY_C 9
 #define RAY_R 16
@@ -97,17 +100,8 @@ __device__ __noinline__ void g2_hit(const uint32_t* ags /* lane-strided */, int 
     if (victim >= 0) res[victim * 32] -= 50u << RS_REWARD_SHIFT;            // Agent.hit(b"F"): -50 (Agent.py:224-226)
 }
 
-__device__ __forceinline__ uint32_t ray_mask(uint32_t lut, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4)
-{
-    uint32_t m = (lut >> (c4 & 0x1Cu)) & 1u;
-    m = m * 2u + ((lut >> (c3 & 0x1Cu)) & 1u);
-    m = m * 2u + ((lut >> (c2 & 0x1Cu)) & 1u);
-    m = m * 2u + ((lut >> (c1 & 0x1Cu)) & 1u);
-    return m * 2u + ((lut >> (c0 & 0x1Cu)) & 1u);
-}
-
-__device__ __forceinline__ int g2_fire(uint8_t* map, uint8_t* beam, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN], const uint32_t* ags, int n,
-                                       uint32_t* res, bool clean, int H, int W, int Wp)
+__device__ __forceinline__ int g2_fire(const uint16_t* ci, uint32_t* wmk, uint8_t* beam, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN],
+                                       const uint32_t* ags, int n, uint32_t* res, bool clean, int H, int W, int Wp)
 {
     const int row = (int)(shooter & 255u), col = (int)((shooter >> 8) & 255u), ori = (int)((shooter >> 16) & 3u);
     const int dr = ori_dr(ori), dc = ori_dc(ori);
@@ -119,12 +113,15 @@ __device__ __forceinline__ int g2_fire(uint8_t* map, uint8_t* beam, uint32_t sho
     const bool okl = (unsigned)(row - rr) < (unsigned)H && (unsigned)(col - rcl) < (unsigned)W;
     const int step = dr * Wp + dc, side = rr * Wp + rcl, base = row * Wp + col;
     const int nr = okr ? ns : 0, nl = okl ? ns : 0;
-    uint32_t cc[5], cr[5], cl[5];
+    uint32_t wall = 0, waste = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        cc[i] = i < n0 ? (uint32_t)map[base + (i + 1) * step] : (uint32_t)C_WALL;
-        cr[i] = i < nr ? (uint32_t)map[base + side + i * step] : (uint32_t)C_WALL;
-        cl[i] = i < nl ? (uint32_t)map[base - side + i * step] : (uint32_t)C_WALL;
+        const uint32_t cc = i < n0 ? (uint32_t)ci[base + (i + 1) * step] : CI_WALL;
+        const uint32_t cr = i < nr ? (uint32_t)ci[base + side + i * step] : CI_WALL;
+        const uint32_t cl = i < nl ? (uint32_t)ci[base - side + i * step] : CI_WALL;
+        wall |= ((cl >> 13) & 1u) << (RAY_L + i) | ((cc >> 13) & 1u) << (RAY_C + i) | ((cr >> 13) & 1u) << (RAY_R + i);
+        if (clean)
+            waste |= cell_has(wmk, cl, 15) << (RAY_L + i) | cell_has(wmk, cc, 15) << (RAY_C + i) | cell_has(wmk, cr, 15) << (RAY_R + i);
     }
     // agents on the rays
     const uint32_t sel = ori == ORI_UP ? 0x3214u : (ori == ORI_DOWN ? 0x3250u : (ori == ORI_RIGHT ? 0x3201u : 0x3245u));
@@ -138,11 +135,6 @@ __device__ __forceinline__ int g2_fire(uint8_t* map, uint8_t* beam, uint32_t sho
         occ |= (z & 0xFFFFFCF8u) == 0u ? b : 0u;
     }
     occ &= (31u << RAY_L) | (31u << RAY_C) | (31u << RAY_R);
-    const uint32_t WL = 1u << C_WALL, HL = clean ? 1u << C_WASTE : 0u;        // lookup words indexed by the cell code
-    const uint32_t wall = ray_mask(WL, cl[0], cl[1], cl[2], cl[3], cl[4]) << RAY_L | ray_mask(WL, cc[0], cc[1], cc[2], cc[3], cc[4]) << RAY_C
-                        | ray_mask(WL, cr[0], cr[1], cr[2], cr[3], cr[4]) << RAY_R;
-    const uint32_t waste = ray_mask(HL, cl[0], cl[1], cl[2], cl[3], cl[4]) << RAY_L | ray_mask(HL, cc[0], cc[1], cc[2], cc[3], cc[4]) << RAY_C
-                         | ray_mask(HL, cr[0], cr[1], cr[2], cr[3], cr[4]) << RAY_R;
     const uint32_t stop = wall | waste | occ;
     int nup = 0;
 #pragma unroll
@@ -158,7 +150,8 @@ __device__ __forceinline__ int g2_fire(uint8_t* map, uint8_t* beam, uint32_t sho
         if (f & ~wall) {
             if (f & waste) {                                                   // CLEAN: H -> R (cleanup_new.py:285-290)
                 const int i = __ffs(f) - 1 - sh;
-                map[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step] = (uint8_t)C_RIVER;
+                const uint32_t c = ci[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step];
+                wmk[((c & CI_IDX) >> 5) * 32] &= ~(1u << (c & 31u));
                 nup++;
             }
             if (!clean && (f & occ)) g2_hit(ags, n, res, cs, sel, (uint32_t)(__ffs(f) - 1));
@@ -309,34 +302,50 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 
 // =============================================================================================
 // LOGIC: one thread per env.  Agent state lives in registers (loops over the n <= 8 agents are fully
-// unrolled), map bytes are read from global memory in batches of independent loads (one memory round
-// trip per batch), conflicts are found by pairwise comparisons instead of marks in the map.  Shared
-// memory only holds lane-strided copies of the per-agent arrays for the two places that index agents
-// dynamically (the warp-cooperative contested-move resolution and the beam walk).
+// unrolled).  The env's only global-memory input is its hot line; static per-cell words (wall / apple point / waste
+// point + list index) sit in shared memory, and so do lane-strided copies of the env's masks and of the per-agent
+// arrays for the places that index them dynamically (mask bits by point index, the warp-cooperative contested-move
+// resolution, the beam walk).
+// dynamic shared memory: [cell_info u16 H*Wp, padded to 16 B][per warp: apple mask [mw][32], waste mask [mw][32]]
 template <int KIND>
 __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
+    extern __shared__ __align__(16) uint8_t dsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.n, H = p.H, W = p.W, Wp = p.Wp, mw = p.mw;
+    const int ci_bytes = (H * Wp * 2 + 15) & ~15;
+    const uint16_t* ci = reinterpret_cast<const uint16_t*>(dsm);
+    for (int i = threadIdx.x; i < (ci_bytes >> 2); i += LOGIC_THREADS)
+        reinterpret_cast<uint32_t*>(dsm)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.cell_info) + i);
+    uint32_t* amk = reinterpret_cast<uint32_t*>(dsm + ci_bytes) + warp * 2 * mw * 32 + lane;
+    uint32_t* wmk = amk + mw * 32;
     uint32_t* agA = s_arr[warp][0]; uint32_t* mvA = s_arr[warp][2];
     uint32_t* ags = agA + lane; uint32_t* res = s_arr[warp][1] + lane; uint32_t* mvs = mvA + lane; uint32_t* key = s_arr[warp][3] + lane;
-    const int n = p.n, H = p.H, W = p.W, Wp = p.Wp;
     const bool act_lane = lane < n;
     const int env0 = blockIdx.x * LOGIC_THREADS + warp * 32;       // first env of this warp
     const bool valid = env0 + lane < p.E;
     const int env = valid ? env0 + lane : p.E - 1;
-    uint8_t* map = p.state + (size_t)env * p.rec_stride;           // this env's compact map, in global memory
-    uint8_t* hdr = map + p.map_bytes;
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride;           // this env's record
 
     int t = 0, hcount = 0; uint32_t episode = 0, flags = 0; double theta = 0.0;
     uint32_t err = 0, movers = 0, firem = 0, cleanm = 0;
     uint32_t ag[SSD_MAXN], tg[SSD_MAXN];
+    uint32_t act_lo = 0x04040404u, act_hi = 0x04040404u;
     bool slow = false;
     if (valid) {
         const uint4 a0 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS);
         const uint4 a1 = *reinterpret_cast<const uint4*>(hdr + RO_AGENTS + 16);
         const uint4 s0 = *reinterpret_cast<const uint4*>(hdr + RO_T);        // t, episode, theta
         const uint2 s1 = *reinterpret_cast<const uint2*>(hdr + RO_FLAGS);    // flags, hcount
+        for (int k = 0; k < mw; k += 4) {
+            const uint4 ma = *reinterpret_cast<const uint4*>(hdr + RO_AMASK + 4 * k);
+            amk[k * 32] = ma.x; amk[(k + 1) * 32] = ma.y; amk[(k + 2) * 32] = ma.z; amk[(k + 3) * 32] = ma.w;
+            if (KIND == SSD_ENV_CLEANUP) {
+                const uint4 mq = *reinterpret_cast<const uint4*>(hdr + RO_WMASK + 4 * k);
+                wmk[k * 32] = mq.x; wmk[(k + 1) * 32] = mq.y; wmk[(k + 2) * 32] = mq.z; wmk[(k + 3) * 32] = mq.w;
+            }
+        }
         ag[0] = a0.x; ag[1] = a0.y; ag[2] = a0.z; ag[3] = a0.w; ag[4] = a1.x; ag[5] = a1.y; ag[6] = a1.z; ag[7] = a1.w;
         t = (int)s0.x + 1;                                                    // map_env.py:230
         episode = s0.y;
@@ -344,7 +353,6 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
         flags = s1.x; hcount = (int)s1.y;
         // ---- packed action ids
         const uint8_t* g_act = io.actions + (size_t)env * n;
-        uint32_t act_lo = 0x04040404u, act_hi = 0x04040404u;
         if (n == 8 && (reinterpret_cast<uintptr_t>(io.actions) & 7u) == 0) {
             const uint2 a = *reinterpret_cast<const uint2*>(g_act); act_lo = a.x; act_hi = a.y;
         } else {
@@ -354,12 +362,15 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
                 else act_hi = (act_hi & ~(255u << (8 * (a - 4)))) | (b << (8 * (a - 4)));
             }
         }
+    }
+    __syncthreads();                                             // the cell table is in place
+    if (valid) {
         // ---- decode, rotations (map_env.py:514-516), candidate cells (Agent.py:8-16,161-162,198-199)
-        uint32_t cand[SSD_MAXN], wallb[SSD_MAXN];
+        uint32_t cand[SSD_MAXN];
         uint32_t want = 0;                                       // movers with a real candidate cell inside the map
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) {
-            cand[a] = 0; wallb[a] = C_WALL;
+            cand[a] = 0;
             if (a < n) {
                 const uint32_t v = ag[a];
                 const int row = (int)(v & 255u), col = (int)((v >> 8) & 255u);
@@ -386,11 +397,8 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
             }
         }
 #pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++)                       // independent loads: one round trip
-            if ((want >> a) & 1u) wallb[a] = map[rc_off(cand[a], Wp)];
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++)                       // return_valid_pos (Agent.py:111-119)
-            tg[a] = (((want >> a) & 1u) && (wallb[a] & CODE_MASK) != C_WALL) ? cand[a] : (ag[a] & 0xFFFFu);
+        for (int a = 0; a < SSD_MAXN; a++)                       // return_valid_pos (Agent.py:111-119): walls are static
+            tg[a] = (((want >> a) & 1u) && !(ci[rc_off(cand[a], Wp)] & CI_WALL)) ? cand[a] : (ag[a] & 0xFFFFu);
         // ---- fast path test: no two movers share a target and no real move targets an occupied cell
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) {
@@ -445,9 +453,6 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
     // ---- cells under the agents: stale-list infos on the start-of-step map (cleanup_new.py:220-223,
     //      harvest_new.py:190-199), then consume in agent order (map_env.py:244-247): of co-located
     //      agents the lowest index eats
-    uint32_t under[SSD_MAXN];
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) under[a] = a < n ? (uint32_t)map[rc_off(ag[a], Wp)] : 0u;
     uint32_t on_apple = 0, first = 0;
     uint32_t agc[SSD_MAXN];                                  // agents' cells for the beams (absent: 0xFFFF)
 #pragma unroll
@@ -455,13 +460,14 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a < n) {
-            if ((under[a] & CODE_MASK) == C_APPLE) on_apple |= 1u << a;
+            on_apple |= cell_has(amk, ci[rc_off(ag[a], Wp)], 14) << a;
             bool dup = false;
 #pragma unroll
             for (int b = 0; b < a; b++) if ((ag[b] & 0xFFFFu) == (ag[a] & 0xFFFFu)) dup = true;
             if (!dup) first |= 1u << a;
         }
     }
+    bool dirty = false;
     if (on_apple) {
         const bool stale_ok = !(flags & RF_STALE_EMPTY);
         for (uint32_t m = on_apple; m; m &= m - 1) {
@@ -471,15 +477,17 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
             if (stale_ok) {
                 rs = RS_EATEN;
                 if (KIND == SSD_ENV_HARVEST &&
-                    g2_count_r5(map, (int)(v & 255u), (int)((v >> 8) & 255u), H, W, Wp) < 4) rs |= RS_EATEN_CLOSE;
+                    g2_count_r5(ci, amk, (int)(v & 255u), (int)((v >> 8) & 255u), H, W, Wp) < 4) rs |= RS_EATEN_CLOSE;
             }
             if ((first >> a) & 1u) rs += 1u << RS_REWARD_SHIFT;
             res[a * 32] = rs;
         }
         for (uint32_t m = on_apple & first; m; m &= m - 1) {
             const int a = __ffs(m) - 1;
-            map[rc_off(ags[a * 32], Wp)] = (uint8_t)C_EMPTY;
+            const uint32_t c = ci[rc_off(ags[a * 32], Wp)];
+            amk[((c & CI_IDX) >> 5) * 32] &= ~(1u << (c & 31u));
         }
+        dirty = true;
     }
     // ---- beams in shuffled agent order (map_env.py:678-693); keys only matter when >= 2 agents fire
     uint32_t rem = firem | cleanm;
@@ -506,20 +514,27 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(map, p.beam ? p.beam + (size_t)env * p.map_bytes : nullptr, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
+            const int nup = g2_fire(ci, wmk, p.beam ? p.beam + (size_t)env * p.map_bytes : nullptr, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }
     }
     if (KIND == SSD_ENV_CLEANUP) hcount -= ncleaned;
 
-    // ---- record header (the observe kernel reads agents, t, episode, flags, hcount from it)
+    // ---- hot line back (the observe kernel reads agents, t, episode, flags, hcount, masks from it)
     *reinterpret_cast<uint4*>(hdr + RO_AGENTS) = make_uint4(ag[0], ag[1], ag[2], ag[3]);
     *reinterpret_cast<uint4*>(hdr + RO_AGENTS + 16) = make_uint4(ag[4], ag[5], ag[6], ag[7]);
     *reinterpret_cast<int*>(hdr + RO_T) = t;
     *reinterpret_cast<uint2*>(hdr + RO_FLAGS) =
         make_uint2((flags & ~RF_STALE_EMPTY) | (err ? (err << RF_ERR_SHIFT) : 0u), (uint32_t)hcount);
-    if (KIND == SSD_ENV_CLEANUP && ncleaned) red_add(reinterpret_cast<uint32_t*>(hdr + RO_DIRT), (uint32_t)ncleaned);
+    if (dirty)
+        for (int k = 0; k < mw; k += 4)
+            *reinterpret_cast<uint4*>(hdr + RO_AMASK + 4 * k) = make_uint4(amk[k * 32], amk[(k + 1) * 32], amk[(k + 2) * 32], amk[(k + 3) * 32]);
+    if (KIND == SSD_ENV_CLEANUP && ncleaned) {
+        for (int k = 0; k < mw; k += 4)
+            *reinterpret_cast<uint4*>(hdr + RO_WMASK + 4 * k) = make_uint4(wmk[k * 32], wmk[(k + 1) * 32], wmk[(k + 2) * 32], wmk[(k + 3) * 32]);
+        red_add(reinterpret_cast<uint32_t*>(hdr + RO_DIRT), (uint32_t)ncleaned);
+    }
     uint4* rg = reinterpret_cast<uint4*>(res_g + (size_t)env * SSD_MAXN);
     rg[0] = make_uint4(res[0], res[32], res[64], res[96]);
     rg[1] = make_uint4(res[128], res[160], res[192], res[224]);
@@ -532,48 +547,22 @@ __global__ void __launch_bounds__(LOGIC_THREADS) grid_reward_kernel(const GridPa
 {
     const int env = blockIdx.x * LOGIC_THREADS + threadIdx.x;
     if (env >= p.E) return;
-    uint8_t* hdr = p.state + (size_t)env * p.rec_stride + p.map_bytes;
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
     const int t = *reinterpret_cast<const int*>(hdr + RO_T);
     const double theta = *reinterpret_cast<const double*>(hdr + RO_THETA);
     env_rewards<SSD_ENV_HARVEST>(p, io, env, hdr, res_g + (size_t)env * SSD_MAXN, 1, theta, t);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Observation gather of the observe kernel.  The kernel is bound by shared-memory wavefronts (ncu:
-// l1tex__data_pipe_lsu_wavefronts at ~79 % of peak with the byte-wise gather of ssd_grid.cuh, a third of
-// them bank conflicts of the per-pixel tile reads), so here an output row is read as 5 aligned WORDS:
-// every output row of color_view (map_env.py:397-411) is a run of 15 consecutive bytes, forwards or
-// backwards, either of the row-major tile T (UP, DOWN) or of its transpose T2 (LEFT, RIGHT):
+// Observation gather of the observe kernel.  The kernel is bound by shared-memory wavefronts and instruction issue, so
+// an output row is read as 5 aligned WORDS: every output row of color_view (map_env.py:397-411) is a run of 15
+// consecutive bytes, forwards or backwards, either of the row-major tile T (UP, DOWN) or of its transpose T2 (LEFT, RIGHT):
 //   UP    out[i][j] = V[i][j]        T : run at origin  + i S,          forwards
 //   DOWN  out[i][j] = V[14-i][14-j]  T : run at origin  + (14 - i) S,   backwards
 //   LEFT  out[i][j] = V[j][14-i]     T2: run at origin2 + (14 - i) S2,  forwards
 //   RIGHT out[i][j] = V[14-j][i]     T2: run at origin2 + i S2,         backwards
-// with V[a][b] = T[origin + a S + b] = T2[origin2 + b S2 + a].  T2 is rebuilt per env from the painted T by
-// 4x4 byte-block transposes (8 PRMT per block, one block per lane).
-__device__ __forceinline__ void transpose_tile(const GridParams& p, int lane, const uint8_t* tile, uint8_t* tile2)
-{
-    const uint32_t* t = reinterpret_cast<const uint32_t*>(tile);
-    uint32_t* t2 = reinterpret_cast<uint32_t*>(tile2);
-    // whole 4-row groups as 4x4 blocks; the H % 4 remaining rows byte by byte (cleanup: 6 x 5 = 30 blocks = one pass
-    // of the warp + row 24, instead of 35 blocks = two passes).  The padding of T2 keeps its C_OUTSIDE fill.
-    const int S4 = p.S >> 2, S24 = p.S2 >> 2, nbj = p.wpw, full = p.H >> 2, nblk = full * nbj;
-    for (int b = lane; b < nblk; b += 32) {
-        const int bi = (int)(((uint32_t)b * p.wpw_magic) >> 16), bj = b - bi * nbj;   // block row / word column
-        const uint32_t* src = t + (4 * bi + SSD_VIEW) * S4 + 2 + bj;
-        const uint32_t r0 = src[0], r1 = src[S4], r2 = src[2 * S4], r3 = src[3 * S4];
-        const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
-        const uint32_t t2a = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
-        uint32_t* dst = t2 + (4 * bj + SSD_VIEW) * S24 + 2 + bi;
-        dst[0] = __byte_perm(t0, t1, 0x5410);
-        dst[S24] = __byte_perm(t0, t1, 0x7632);
-        dst[2 * S24] = __byte_perm(t2a, t3, 0x5410);
-        dst[3 * S24] = __byte_perm(t2a, t3, 0x7632);
-    }
-    for (int r = 4 * full; r < p.H; r++)
-        for (int c = lane; c < p.W; c += 32)
-            tile2[(c + SSD_VIEW) * p.S2 + 8 + r] = tile[(r + SSD_VIEW) * p.S + 8 + c];
-}
-
+// with V[a][b] = T[origin + a S + b] = T2[origin2 + b S2 + a].  T2 is not rebuilt per env: both tiles live in the warp's
+// shared memory for the whole kernel and only their dynamic cells are rewritten (apply_masks, paint).
 // ao: the agent's cell in T.  `tile` is the base of [T | T2]; vdesc entries hold offsets relative to it.
 __device__ __forceinline__ void gather_obs2(const GridParams& p, int lane, const uint8_t* tile, uint8_t* stage,
                                             const uint32_t* sm_pal, int4* vdesc, int ao, int ori, uint8_t* gdst)
@@ -632,78 +621,62 @@ __device__ __forceinline__ void gather_obs2(const GridParams& p, int lane, const
 }
 
 // =============================================================================================
-// OBSERVE: one warp per env.  Spawn + observation windows.  Per warp: [tile | stage (obs staging, aliased
-// by the spawn scratch) | misc], tile = [T | T2 (transposed)].  The compact map (VPL 16-byte vectors per lane) and the first 14 header
-// words (agents, t, episode, theta, flags, #waste) of the NEXT env are prefetched into registers while
-// the current env is processed; the map goes back to HBM only when the spawn changed it.
-template <int KIND, int ROUNDS, bool FEAT, int VPL>
+// OBSERVE: one warp per env.  Spawn + observation windows.  Per warp: [T | T2 | stage (obs staging, aliased
+// by the spawn scratch) | misc].  Lane l prefetches word l of the NEXT env's hot line (one coalesced 128-byte load) while
+// the current env is processed: words 0-7 agents, 8 t, 9 episode, 12 flags, 13 #waste, 16.. apple mask, 24.. waste mask.
+template <int KIND, int MW, bool FEAT>
 __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const SharedTables tb = load_shared_tables(p, smem);
+    const SharedTables tb = load_shared_tables(p, smem, FEAT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tile = smem + p.sm_warp0 + warp * p.g2_warp_bytes;
+    uint8_t* tile2 = tile + p.tile2_off;
     uint8_t* stage = tile + p.g2_stage;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
-    uint8_t* tile2 = tile + p.tile2_off;             // transposed tile (gather_obs2)
-    for (int i = lane; i < (p.g2_stage >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = TILE_FILL4;   // T and T2
+    const PointRegs<MW> pr = load_point_regs<MW>(p, lane);
+    init_warp_tiles(p, tile, lane);
     __syncthreads();                                  // tables visible
-    const int n = p.n, S = p.S;
+    const int n = p.n, S = p.S, S2 = p.S2;
     const bool act_lane = lane < n;
     const int env_stride = gridDim.x * OBS_WARPS;
-    // tile word of each map word this lane moves (vector v = lane + 32 k covers map words 4 v .. 4 v + 3)
-    const int nvec = p.map_bytes >> 4, nwords = p.H * p.wpw;
-    int tw[VPL][4];
-#pragma unroll
-    for (int k = 0; k < VPL; k++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int w = 4 * (lane + 32 * k) + j;
-            tw[k][j] = w < nwords ? map_tile_word(p, w) : -1;
-        }
-    uint32_t* tw32 = reinterpret_cast<uint32_t*>(tile);
 
     int env = blockIdx.x * OBS_WARPS + warp;
     uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
     const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
     uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
     const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
-    uint4 pref[VPL];
-    uint32_t hw = 0;                                  // header word `lane` (lanes 0..13)
-    if (env < p.E) {
-#pragma unroll
-        for (int k = 0; k < VPL; k++) if (lane + 32 * k < nvec) pref[k] = reinterpret_cast<const uint4*>(g_rec)[lane + 32 * k];
-        if (lane < 14) hw = reinterpret_cast<const uint32_t*>(g_rec + p.map_bytes)[lane];
-    }
+    uint32_t hw_next = 0;
+    if (env < p.E) hw_next = reinterpret_cast<const uint32_t*>(g_rec)[lane];
     for (; env < p.E; env += env_stride) {
-        // ---- map -> padded tile, header scalars
+        const uint32_t hw = hw_next;
+        if (env + env_stride < p.E) hw_next = reinterpret_cast<const uint32_t*>(g_rec + g_rec_step)[lane];
+        // ---- dynamic cells of T and T2 from the masks; header scalars
+        uint32_t am[MW], wm[MW];
 #pragma unroll
-        for (int k = 0; k < VPL; k++) {
-            if (lane + 32 * k < nvec) {
-                const uint32_t w4[4] = { pref[k].x, pref[k].y, pref[k].z, pref[k].w };
-#pragma unroll
-                for (int j = 0; j < 4; j++) if (tw[k][j] >= 0) tw32[tw[k][j]] = w4[j];
-            }
+        for (int q = 0; q < MW; q++) {
+            am[q] = __shfl_sync(FULL, hw, RO_AMASK / 4 + q);
+            wm[q] = KIND == SSD_ENV_CLEANUP ? __shfl_sync(FULL, hw, RO_WMASK / 4 + q) : 0u;
         }
+        apply_masks<MW>(p, lane, tile, tile2, pr, am, wm);
         const uint32_t t = __shfl_sync(FULL, hw, RO_T / 4);               // already incremented by the logic kernel
         const uint32_t episode = __shfl_sync(FULL, hw, RO_EPISODE / 4);
         int hcount = (int)__shfl_sync(FULL, hw, RO_HCOUNT / 4);
         const EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, t };
-        int ao = 0, ori = 0;
+        int ao = 0, ao2 = 0, ori = 0;
         if (act_lane) {
-            ao = ((int)(hw & 255u) + SSD_VIEW) * S + 8 + (int)((hw >> 8) & 255u);
+            const int row = (int)(hw & 255u), col = (int)((hw >> 8) & 255u);
+            ao = (row + SSD_VIEW) * S + 8 + col;
+            ao2 = (col + SSD_VIEW) * S2 + 8 + row;
             ori = (int)((hw >> 16) & 3u);
         }
-        // ---- prefetch the next env (in flight while this one is processed)
-        if (env + env_stride < p.E) {
-            const uint8_t* nx = g_rec + g_rec_step;
-#pragma unroll
-            for (int k = 0; k < VPL; k++) if (lane + 32 * k < nvec) pref[k] = reinterpret_cast<const uint4*>(nx)[lane + 32 * k];
-            if (lane < 14) hw = reinterpret_cast<const uint32_t*>(nx + p.map_bytes)[lane];
-        }
         __syncwarp();
-        if (act_lane) tile[ao] |= OCC_BIT;            // spawn eligibility: "no agent there" (co-located lanes write the same value)
+        uint32_t old = 0;
+        if (act_lane) {                               // spawn eligibility: "no agent there" (co-located lanes write the same value)
+            old = tile[ao] & CODE_MASK;
+            tile[ao] = (uint8_t)(old | OCC_BIT);
+        }
         __syncwarp();
         // ---- spawn
         bool changed = false;
@@ -712,15 +685,22 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
             if (cleanup_spawn_active(tb, hcount)) {
                 if (lane == 0) bulk_wait_read<0>();   // the previous observation store has drained `stage` (= scratch)
                 __syncwarp();
-                const int before = hcount;
-                changed = cleanup_spawn<ROUNDS>(p, tb, lane, tile, scratch, g, t, hcount);
-                if (hcount != before && lane == 0)
-                    *reinterpret_cast<int*>(g_rec + p.map_bytes + RO_HCOUNT) = hcount;
+                changed = cleanup_spawn<MW>(p, tb, lane, tile, tile2, scratch, g, t, hcount, pr, am, wm);
             }
         } else {
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
-            changed = harvest_spawn<ROUNDS>(p, lane, tile, scratch, tb.apple, g, t);
+            changed = harvest_spawn<MW>(p, lane, tile, tile2, scratch, g, t, pr, am);
+        }
+        if (changed) {                                // the masks (and #waste) go back only when the spawn changed them
+            uint32_t* hot = reinterpret_cast<uint32_t*>(g_rec);
+#pragma unroll
+            for (int q = 0; q < MW; q++)
+                if (lane == q) {
+                    hot[RO_AMASK / 4 + q] = am[q];
+                    if (KIND == SSD_ENV_CLEANUP) hot[RO_WMASK / 4 + q] = wm[q];
+                }
+            if (KIND == SSD_ENV_CLEANUP && lane == 0) hot[RO_HCOUNT / 4] = (uint32_t)hcount;
         }
 #endif
         int total_close = 0;
@@ -730,32 +710,19 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
         }
         if (FEAT) {
             const int cleaned = (KIND == SSD_ENV_CLEANUP && act_lane) ? (int)(res_g[(size_t)env * SSD_MAXN + lane] & RS_CLEANED_MASK) : 0;
-            write_features<KIND>(p, tb, lane, tile, ao, ori, cleaned, total_close, hcount, io.feat + (size_t)env * n * p.F);
-        }
-        // ---- the map goes back only when the spawn changed it (paint / occupancy stripped)
-        if (changed) {
-#pragma unroll
-            for (int k = 0; k < VPL; k++) {
-                if (lane + 32 * k < nvec) {
-                    uint32_t w4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) w4[j] = tw[k][j] >= 0 ? (tw32[tw[k][j]] & CODE_MASK4) : TILE_FILL4;
-                    reinterpret_cast<uint4*>(g_rec)[lane + 32 * k] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                }
-            }
+            write_features<KIND, MW>(p, tb, lane, hw, am, wm, cleaned, total_close, hcount, io.feat + (size_t)env * n * p.F);
         }
         // ---- paint agents in agent order: the highest index wins a shared cell (map_env.py:257-261)
         const unsigned grp = __match_any_sync(FULL, act_lane ? (uint32_t)ao : (0x40000000u | (uint32_t)lane));
         __syncwarp();
-        if (act_lane && lane == 31 - __clz(grp)) tile[ao] = (uint8_t)PAINT_CODE(lane);
+        if (act_lane && lane == 31 - __clz(grp)) { tile[ao] = (uint8_t)PAINT_CODE(lane); tile2[ao2] = (uint8_t)PAINT_CODE(lane); }
         __syncwarp();
-#ifndef OBS_SKIP_TRANSPOSE
-        transpose_tile(p, lane, tile, tile2);
-#endif
         // gather_obs2 waits (lane 0) until the previous observation store has drained `stage`, then syncs the warp
 #ifndef OBS_SKIP_GATHER
         gather_obs2(p, lane, tile, stage, tb.pal, vdesc, ao, ori, g_obs);
 #endif
+        // the agents' cells back to their code (gather_obs2 ends behind a warp barrier after its last tile read)
+        if (act_lane) { tile[ao] = (uint8_t)old; tile2[ao2] = (uint8_t)old; }
         g_rec += g_rec_step; g_obs += g_obs_step;
         __syncwarp();
     }

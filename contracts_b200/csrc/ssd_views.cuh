@@ -27,13 +27,24 @@ __global__ void __launch_bounds__(VIEW_THREADS) global_view_kernel(const GridPar
     const int G = min(VIEW_GROUP, p.E - env0);
     const int nvec = p.map_bytes >> 4;
     if (threadIdx.x < 16) s_pal[threadIdx.x] = p.pal[threadIdx.x];
-    for (int i = threadIdx.x; i < G * nvec; i += VIEW_THREADS) {
+    for (int i = threadIdx.x; i < G * nvec; i += VIEW_THREADS) {            // the static map ...
         const int g = i / nvec, v = i - g * nvec;
-        reinterpret_cast<uint4*>(vsm)[i] = reinterpret_cast<const uint4*>(p.state + (size_t)(env0 + g) * p.rec_stride)[v];
+        reinterpret_cast<uint4*>(vsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.base_map) + v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * (p.n_apple + p.n_waste); i += VIEW_THREADS) {   // ... + the dynamic cells from the masks
+        const int g = i / (p.n_apple + p.n_waste), j = i - g * (p.n_apple + p.n_waste);
+        const uint8_t* hdr = p.state + (size_t)(env0 + g) * p.rec_stride;
+        if (j < p.n_apple) {
+            if ((reinterpret_cast<const uint32_t*>(hdr + RO_AMASK)[j >> 5] >> (j & 31)) & 1u) vsm[g * p.map_bytes + p.apple_c[j]] = (uint8_t)C_APPLE;
+        } else {
+            const int k = j - p.n_apple;
+            if ((reinterpret_cast<const uint32_t*>(hdr + RO_WMASK)[k >> 5] >> (k & 31)) & 1u) vsm[g * p.map_bytes + p.waste_c[k]] = (uint8_t)C_WASTE;
+        }
     }
     __syncthreads();
     if (threadIdx.x < G) {                                    // paint in agent order: the highest index wins a shared cell
-        const uint8_t* hdr = p.state + (size_t)(env0 + threadIdx.x) * p.rec_stride + p.map_bytes;
+        const uint8_t* hdr = p.state + (size_t)(env0 + threadIdx.x) * p.rec_stride;
         const uint32_t* ag = reinterpret_cast<const uint32_t*>(hdr + RO_AGENTS);
         // MapEnv.reset (map_env.py:306-342) never paints the agents into world_map_color: they appear from the first step on
         const int na = (full_map || *reinterpret_cast<const int*>(hdr + RO_T) > 0) ? p.n : 0;
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) policy_inputs_kernel(const GridP
         else dst[o] = q.v[0];
     }
     if (contract && threadIdx.x < n * 10) {
-        const double theta = *reinterpret_cast<const double*>(p.state + (size_t)env * p.rec_stride + p.map_bytes + RO_THETA);
+        const double theta = *reinterpret_cast<const double*>(p.state + (size_t)env * p.rec_stride + RO_THETA);
         contract[(size_t)env * n * 10 + threadIdx.x] = policy_cast<T>((threadIdx.x & 1) ? 0.0f : __double2float_rn(theta));
     }
 }

@@ -33,6 +33,11 @@ SCENARIOS = {
                            [.22, .22, .22, .22, .03, .03, .03, .03]),
     "cleanup_open_n6": ("cleanup", 6, 44, 11, OPEN_CLEANUP, 1000, 1, 300, 9, None),
     "cleanup_n8_nocontract": ("cleanup", 8, 3, 5, None, 1000, 1, 120, 9, None),
+    # the deep spawning regime of the stock map: a cleaning-heavy policy takes #waste from 56 down to ~40 (below the
+    # apple / waste spawn threshold of 47), so apples spawn at several different probabilities, get eaten, and waste
+    # respawns through the shuffled first-success scan for hundreds of steps (cleanup_new.py:322-368)
+    "cleanup_n8_deep": ("cleanup", 8, 71, 424242, None, 1000, 1, 700, 9,
+                        [.14, .14, .14, .14, .02, .04, .04, .32, .02]),
     # use_collective_reward / inequity_averse_reward (map_env.py:289-301); short horizons so that the episode
     # metrics (equality / sustainability over the shaped rewards) are produced
     "cleanup_n4_collective": ("cleanup", 4, 51, 21, None, 60, 2, 60, 9, None),
@@ -101,6 +106,7 @@ NEGOTIATE_SCENARIOS = {
     "negotiate_cleanup_n2": ("cleanup", 2, 21, 3, 30, 1000, 4, 9),
     "negotiate_cleanup_n5": ("cleanup", 5, 22, 40, 1000, 25, 4, 9),     # ends on the base env's own horizon
     "negotiate_harvest_n4": ("harvest", 4, 23, 7, 20, 1000, 4, 8),
+    "negotiate_cleanup_n8": ("cleanup", 8, 27, 91, 60, 1000, 5, 9),      # BASELINE configs[2]: n = 8, 2 sampled acceptors
 }
 
 

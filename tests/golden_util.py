@@ -92,6 +92,25 @@ def metrics_from_raw(kind, n, contract, raw):
     return m
 
 
+def check_episode_metrics(kind, n, contract, raw, want, ctx):
+    """env.metrics of the reference at the end of an episode (`want`: name -> value) against a backend's raw
+    accumulators, bit for bit, incl. equality / sustainability when the episode ended."""
+    raw = np.asarray(raw, dtype=np.float64)
+    assert raw[5] == 0, "backend error flags %r" % raw[5]
+    got = metrics_from_raw(kind, n, contract, raw)
+    for k, v in got.items():
+        assert_same("metric " + k, np.float64(v), np.float64(want[k]), ctx)
+    if "equality" in want:          # episode ended: cleanup_new.py:264-266, two_stage_train.py:97-99
+        totals, tsums = list(raw[24:24 + n]), list(raw[32:32 + n])
+        assert_same("equality", np.float64(equality(totals)), np.float64(want["equality"]), ctx)
+        assert_same("sustainability", np.float64(sustainability(totals, tsums)), np.float64(want["sustainability"]), ctx)
+        if "transfer_equality" in want:
+            totals, tsums = list(raw[40:40 + n]), list(raw[48:48 + n])
+            assert_same("transfer_equality", np.float64(equality(totals)), np.float64(want["transfer_equality"]), ctx)
+            assert_same("transfer_sustainability", np.float64(sustainability(totals, tsums)),
+                        np.float64(want["transfer_sustainability"]), ctx)
+
+
 def replay(backend, fx, check_features=True):
     kind, n = str(fx["kind"]), int(fx["n"])
     episodes, steps = fx["actions"].shape[:2]
@@ -122,22 +141,8 @@ def replay(backend, fx, check_features=True):
             assert_same("done", int(o["done"]), int(fx["done"][ep, t]), ctx)
             if check_features and o.get("feature_obs") is not None:
                 assert_same("feature_obs", o["feature_obs"], fx["feature_obs"][ep, t], ctx)
-        raw = np.asarray(backend.metrics_raw(), dtype=np.float64)
-        assert raw[5] == 0, "backend error flags %r" % raw[5]
-        got = metrics_from_raw(kind, n, bool(fx["contract"]), raw)
         want = dict(zip(keys, fx["metrics"][ep]))
-        for k, v in got.items():
-            assert_same("metric " + k, np.float64(v), np.float64(want[k]), "ep %d" % ep)
-        if "equality" in want:          # episode ended: cleanup_new.py:264-266, two_stage_train.py:97-99
-            totals, tsums = list(raw[24:24 + n]), list(raw[32:32 + n])
-            assert_same("equality", np.float64(equality(totals)), np.float64(want["equality"]), "ep %d" % ep)
-            assert_same("sustainability", np.float64(sustainability(totals, tsums)),
-                        np.float64(want["sustainability"]), "ep %d" % ep)
-            if "transfer_equality" in want:
-                totals, tsums = list(raw[40:40 + n]), list(raw[48:48 + n])
-                assert_same("transfer_equality", np.float64(equality(totals)), np.float64(want["transfer_equality"]), "ep %d" % ep)
-                assert_same("transfer_sustainability", np.float64(sustainability(totals, tsums)),
-                            np.float64(want["transfer_sustainability"]), "ep %d" % ep)
+        check_episode_metrics(kind, n, bool(fx["contract"]), backend.metrics_raw(), want, "ep %d" % ep)
 
 
 class OracleBackend:

@@ -16,12 +16,3 @@ def test_cuda_matches_reference_golden(name):
 def test_cuda_matches_golden_padded_obs(name):
     fx = gu.load(name)
     gu.replay(gu.CudaBackend(fx, num_envs=4, index=3, padded_obs=True), fx, check_features=False)
-
-
-@pytest.mark.parametrize("name", ["cleanup_n8", "harvest_n8_short_horizon", "cleanup_cramped_n8", "cleanup_cramped_n8_inequity",
-                                  "harvest_cramped_n6_collective_inequity"])
-def test_fused_fallback_kernel_matches_golden(name, monkeypatch):
-    """The fused warp-per-env kernel (ssd_grid.cuh), used for maps whose compact form exceeds 1 KB, forced here."""
-    monkeypatch.setenv("SSD_GRID_KERNEL", "v3")
-    fx = gu.load(name)
-    gu.replay(gu.CudaBackend(fx), fx, check_features=True)

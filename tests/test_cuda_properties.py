@@ -97,7 +97,7 @@ def test_step_host_equals_step():
 
 @pytest.mark.parametrize("kind,contract,E,n,theta", [("cleanup_new", "CleanupContract", 3000, 8, 0.15),
                                                      ("cleanup_new", "CleanupContract", 700, 5, 0.0),
-                                                     ("harvest_new", "HarvestFeaturemodLocalContract", 2000, 4, 3.0),
+                                                     ("harvest_new", "HarvestFeaturemodLocalContract", 2000, 4, 2.5),
                                                      ("cleanup_new", None, 500, 3, 0.0)])
 def test_step_host_async_equals_step(kind, contract, E, n, theta):
     """ssd_step_host_async / _wait (double-buffered slots, compact int8 + sparse float64 result block, predicted copy

@@ -1,0 +1,87 @@
+"""Container-only (needs /root/reference): the LIVE unmodified reference (oracle/ref_harness.RefGridEnv, reference code
+under RNG injection) against the C oracle (oracle/ssd_oracle.c) over whole 1000-step episodes + re-resets, deep inside
+the spawning regime that the short committed fixtures only touch: every output of every step by bit pattern — map,
+agent positions / orientations, uint8 observations, rewards before / after transfers, transfers, infos, feature_obs,
+theta at reset, and the episode metrics.  This is what pins the oracle (and through it the CUDA path, which the GPU
+suite compares with the oracle on long rollouts) to the REFERENCE at depth, not only to the fixtures.
+
+Default: 2 episodes of 1000 steps + a third reset per config (~10 s each).  SSD_DEEP_EPISODES=10 gives the >= 10^4
+steps per config of SURVEY.md §8(c)(i).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not os.path.isdir("/root/reference/environments"),
+                                 reason="reference tree not present (GPU box): container-only differential test")]
+
+EPISODES = int(os.environ.get("SSD_DEEP_EPISODES", "2"))
+
+# (kind, n, action ids, action probabilities): the cleaning-heavy cleanup policies drive #waste far below the spawn
+# threshold so that apples spawn, are eaten, and waste respawns for most of the episode
+CASES = [("cleanup", 8, 9, [.14, .14, .14, .14, .02, .04, .04, .32, .02]),
+         ("cleanup", 2, 9, [.12, .12, .12, .12, .02, .05, .05, .38, .02]),
+         ("cleanup", 8, 8, None),                                   # the benchmark's iid uniform policy
+         ("harvest", 4, 8, None),
+         ("harvest", 8, 7, None)]
+
+
+@pytest.mark.parametrize("kind,n,nact,probs", CASES, ids=["%s_n%d_a%d" % c[:3] for c in CASES])
+def test_reference_vs_oracle_full_episodes(oracle_lib, kind, n, nact, probs):
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefGridEnv
+    seed, env_id = 900 + n, 31000 + 17 * n
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    amap = CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP
+    ref = RefGridEnv(kind, n, seed, env_id, contract=True, horizon=1000)
+    orc = oracle_lib.GridOracle(kind, 1, n, amap, horizon=1000, contract=contract, seed=seed, first_env_id=env_id)
+    rng = np.random.RandomState(7 * n + len(kind))
+    min_waste, max_apples, eaten, paid = 10 ** 9, 0, 0, 0
+    for ep in range(EPISODES + 1):
+        ctx = "%s n=%d episode %d reset" % (kind, n, ep)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"], ctx)
+        st = orc.get_state()
+        gu.assert_same("reset map", st["map"][0], r0["map"], ctx)
+        gu.assert_same("reset pos", st["pos"][0], r0["pos"], ctx)
+        gu.assert_same("reset ori", st["ori"][0], r0["ori"], ctx)
+        gu.assert_same("reset theta", st["theta"][0], r0["theta"], ctx)
+        if ep == EPISODES:
+            break
+        for t in range(1000):
+            a = rng.choice(nact, size=n, p=probs).astype(np.int32)
+            want = ref.step(a)
+            got = orc.step(a[None], want_features=True)
+            ctx = "%s n=%d episode %d step %d" % (kind, n, ep, t + 1)
+            gu.assert_same("obs", got["obs"][0], want["obs"], ctx)
+            gu.assert_same("rew", got["rew"][0], want["rew"], ctx)
+            gu.assert_same("base_rew", got["base_rew"][0], want["base_rew"], ctx)
+            gu.assert_same("transfers", got["transfers"][0], want["transfers"], ctx)
+            gu.assert_same("eaten_apples", got["info"][0][:, 0], want["eaten_apples"], ctx)
+            gu.assert_same("info1", got["info"][0][:, 1],
+                           want["cleaned_squares"] if kind == "cleanup" else want["eaten_close_apples"], ctx)
+            gu.assert_same("feature_obs", got["feature_obs"][0], want["feature_obs"], ctx)
+            assert bool(got["done"][0]) == want["done"] == (t == 999), ctx
+            if t % 25 == 0 or t == 999:                      # full state (the observations already cover it every step)
+                st = orc.get_state()
+                gu.assert_same("map", st["map"][0], want["map"], ctx)
+                gu.assert_same("pos", st["pos"][0], want["pos"], ctx)
+                gu.assert_same("ori", st["ori"][0], want["ori"], ctx)
+                if kind == "cleanup":
+                    min_waste = min(min_waste, int((want["map"] == ord("H")).sum()))
+                max_apples = max(max_apples, int((want["map"] == ord("A")).sum()))
+            eaten += int(want["eaten_apples"].sum())
+            paid += int((want["transfers"] != 0).sum())
+        want_m = ref.metrics()
+        assert "equality" in want_m and "transfer_sustainability" in want_m          # the episode really ended
+        gu.check_episode_metrics(kind, n, True, orc.metrics_raw()[0], want_m, "%s n=%d episode %d end" % (kind, n, ep))
+    # the run really was deep: the regime the short fixtures do not reach
+    if kind == "cleanup" and probs is not None:
+        # (two agents cannot out-clean the waste respawn: they hover at the spawn threshold of 47 cells)
+        assert min_waste <= (42 if n == 8 else 47) and max_apples >= 10 and eaten > 0 and paid > 0, (min_waste, max_apples, eaten, paid)
+    if kind == "harvest":
+        assert eaten > 0
