@@ -17,7 +17,8 @@ episode boundary — reset + negotiation prologue + statistics — is inside eve
 reached by an untimed burn-in of one horizon with staggered resets.  Weak scaling: every rank owns E envs with global
 ids rank*E ..; no collective on the step path; the statistics vector is all-gathered (NCCL) on a side stream.
 
-A "step" = random actions + `ssd_step` + masked reset (+ masked negotiate) over the rank's E envs.
+A "step" = random actions + `ssd_step` with auto_reset (the finished envs are reset and negotiate inside the step; the
+feature / selfdrive envs: + a masked reset launch) over the rank's E envs.
   value   : device-resident (actions generated on device, outputs stay in HBM), CUDA-event timed, max over ranks
   e2e     : the same step through the host-buffer API: pinned host actions -> device, step, result block (rewards +
             dones) -> pinned host memory, every step; pipelined two deep (`ssd_step_host_async` / `_wait`)
@@ -304,11 +305,17 @@ class Runner:
         if self.cfg["negotiate"]:
             self.env.negotiate(self.prop, self.acc, mask=m, out=self.dec)
 
+    def neg(self):
+        return (self.prop, self.acc, self.dec) if self.cfg["negotiate"] else None
+
     def substep(self, step_index=None):
         """everything one env step enqueues on the device (capturable in a CUDA graph)"""
         self.gen_actions(step_index)
-        self.env.step(self.actions, extras=False)
-        self.after_step()
+        if self.fam == "grid":       # finished envs restart (and negotiate) inside the step: ssd_step_io.auto_reset
+            self.env.step(self.actions, extras=False, auto_reset=True, negotiation=self.neg())
+        else:
+            self.env.step(self.actions, extras=False)
+            self.after_step()
 
     def burn_in(self):
         """reach the steady state: one horizon with env i (re)started at step i mod horizon"""
@@ -487,6 +494,7 @@ def main():
     Kk = 200
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
     run.policy()
+    # (the event pair brackets the step kernels only: the finished envs are reset by a separate call here)
     for k in range(Kk):
         run.gen_actions()
         kev[k][0].record()
@@ -532,8 +540,7 @@ def main():
             for i in range(steps):
                 if i % 50 == 0:
                     run.policy()
-                tk = env.step_host_async(host_actions[i % 4], res[i & 1])
-                run.after_step()                                 # device-side masked reset + negotiation, stream-ordered
+                tk = env.step_host_async(host_actions[i % 4], res[i & 1], auto_reset=True, negotiation=run.neg())
                 if prev is not None:
                     env.step_host_wait(prev[0])
                     consumed += prev[1].count + int(prev[1].done[0])
@@ -582,9 +589,8 @@ def main():
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         o0.record()
         for i in range(Ko):
-            tk = env.step_host_async(host_actions[i % 4], res[i & 1])
+            tk = env.step_host_async(host_actions[i % 4], res[i & 1], auto_reset=True, negotiation=run.neg())
             host_obs.copy_(env._obs_buf, non_blocking=True)
-            run.after_step()
             env.step_host_wait(tk)
             main_stream.synchronize()
         o1.record()

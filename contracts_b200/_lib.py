@@ -41,6 +41,8 @@ class ssd_step_io(ctypes.Structure):
         ("actions_dev", ctypes.c_void_p), ("obs_dev", ctypes.c_void_p), ("obs_env_stride", ctypes.c_int64),
         ("rew_dev", ctypes.c_void_p), ("base_rew_dev", ctypes.c_void_p), ("transfers_dev", ctypes.c_void_p),
         ("info_dev", ctypes.c_void_p), ("feature_obs_dev", ctypes.c_void_p), ("done_dev", ctypes.c_void_p),
+        ("auto_reset", ctypes.c_int32), ("neg_proposals_dev", ctypes.c_void_p), ("neg_accept_dev", ctypes.c_void_p),
+        ("neg_decision_dev", ctypes.c_void_p),
     ]
 
 

@@ -184,10 +184,26 @@ class BatchedGridEnv:
         _lib.check(self._h, self.lib.ssd_reset(self._h, _ptr(mask), _ptr(self._obs_buf), self.obs_stride, self._stream()))
         return self.obs
 
-    def step(self, actions, want_features=False, extras=True):
+    def _auto_reset_io(self, io, auto_reset, negotiation):
+        """vectorised-sampler mode of a step: finished envs restart inside the step (+ negotiate, given the policy's
+        negotiation outputs (proposals [E], accept [E, n], decisions uint8 [E] or None) as float64 CUDA tensors)"""
+        io.auto_reset = 1 if auto_reset else 0
+        io.neg_proposals_dev = io.neg_accept_dev = io.neg_decision_dev = None
+        if auto_reset and negotiation is not None:
+            prop, acc, dec = negotiation
+            for x, shape in ((prop, (self.E,)), (acc, (self.E, self.n))):
+                if x.dtype != torch.float64 or x.device != self.device or tuple(x.shape) != shape or not x.is_contiguous():
+                    raise ValueError("negotiation tensors must be contiguous float64 CUDA tensors [E] and [E, n]")
+            io.neg_proposals_dev, io.neg_accept_dev = prop.data_ptr(), acc.data_ptr()
+            io.neg_decision_dev = dec.data_ptr() if dec is not None else None
+
+    def step(self, actions, want_features=False, extras=True, auto_reset=False, negotiation=None):
         """actions: uint8 CUDA tensor [E, n].  Returns (obs, rew, done, info) device tensors.
 
         The same output tensors are reused every step.  extras=False skips base_rew/transfers.
+        auto_reset=True: envs that finish in this step are reset by the step itself (their observation is the reset
+        observation; rewards / done / info are the final step's) and, with negotiation=(proposals, accept, decisions),
+        negotiate their next contract — what `reset(done)` + `negotiate(..., mask=done)` would do, without the launches.
         """
         if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -203,6 +219,7 @@ class BatchedGridEnv:
         io.info_dev = self.info.data_ptr()
         io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
         io.done_dev = self.done.data_ptr()
+        self._auto_reset_io(io, auto_reset, negotiation)
         _lib.check(self._h, self.lib.ssd_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
 
@@ -227,6 +244,7 @@ class BatchedGridEnv:
         io.info_dev = self.info.data_ptr()
         io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
         io.done_dev = self.done.data_ptr()
+        self._auto_reset_io(io, False, None)
         _lib.check(self._h, self.lib.ssd_step_host(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
                                                    ctypes.c_void_p(rew_host.data_ptr()),
                                                    ctypes.c_void_p(done_host.data_ptr()) if done_host is not None else None,
@@ -243,7 +261,7 @@ class BatchedGridEnv:
         """A pinned host block for step_host_async + numpy views of its fields (`HostResult`)."""
         return HostResult(self)
 
-    def step_host_async(self, actions_host, result, want_features=False, dense_rewards=False):
+    def step_host_async(self, actions_host, result, want_features=False, dense_rewards=False, auto_reset=False, negotiation=None):
         """Submit one step with HOST actions (pinned uint8 [E, n]); returns a ticket without synchronising.  The
         compact result block (int8 rewards + exact float64 records + dones) is copied into `result` (a HostResult)
         while the observe kernel runs; `step_host_wait(ticket)` makes it valid.  At most two steps in flight.
@@ -262,6 +280,7 @@ class BatchedGridEnv:
         io.info_dev = self.info.data_ptr()
         io.feature_obs_dev = self.feature_obs.data_ptr() if want_features else None
         io.done_dev = self.done.data_ptr()
+        self._auto_reset_io(io, auto_reset, negotiation)
         ticket = ctypes.c_int64(-1)
         _lib.check(self._h, self.lib.ssd_step_host_async(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
                                                          ctypes.c_void_p(result.block.data_ptr()), ctypes.byref(ticket), self._stream()))

@@ -199,16 +199,18 @@ static int setup_grid(ssd_handle* h)
 
     // parse the map like MapEnv.__init__ / CleanupEnv.__init__ / HarvestEnv.__init__.  Static part: walls, river, stream;
     // dynamic part: apple points ('B' cleanup, 'A' harvest) and waste points ('H' / 'R'), in row-major (canonical) order.
-    p.tile_r16 = round_up(p.TH * p.S, 16);
-    const int tile2_bytes = round_up((p.Wp + 2 * SSD_VIEW) * p.S2, 16);
+    p.tile_r16 = round_up(p.TH * p.S + 1, 16);                          // + a spare sink byte behind T and behind T2 (see below)
+    const int tile2_bytes = round_up((p.Wp + 2 * SSD_VIEW) * p.S2 + 1, 16);
     p.tile2_off = p.tile_r16;
     p.g2_stage = p.tile2_off + tile2_bytes;
     std::vector<uint16_t> spawn, apple_rc, waste_rc, apple_c, waste_c, cell_info(round_up(H * p.Wp, 8), 0);
-    std::vector<uint32_t> apple_pt(32 * MAX_POINT_ROUNDS, 0u), waste_pt(32 * MAX_POINT_ROUNDS, 0u);
+    // point slots beyond a list point at the spare bytes behind T / T2: rewriting "their" cell is harmless
+    const uint32_t sink = (uint32_t)(p.TH * p.S) | ((uint32_t)(p.tile2_off + (p.Wp + 2 * SSD_VIEW) * p.S2) << 16);
+    std::vector<uint32_t> apple_pt(32 * MAX_POINT_ROUNDS, sink), waste_pt(32 * MAX_POINT_ROUNDS, sink);
     std::vector<uint8_t> base_map(p.map_bytes, (uint8_t)C_OUTSIDE), tile0(p.g2_stage, (uint8_t)C_OUTSIDE);
     auto rc16 = [](int r, int col) { return (uint16_t)((r << 8) | col); };
     auto off = [&](int r, int col) { return (uint32_t)((r + SSD_VIEW) * p.S + 8 + col); };
-    auto off2 = [&](int r, int col) { return (uint32_t)((col + SSD_VIEW) * p.S2 + 8 + r); };
+    auto off2 = [&](int r, int col) { return (uint32_t)((col + SSD_VIEW) * p.S2 + 8 + r); };           // within T2
     int n_spawn_unique = 0, n_waste_start = 0, na = 0, nw = 0;
     for (int r = 0; r < H; r++)
         for (int col = 0; col < W; col++) {
@@ -223,7 +225,7 @@ static int setup_grid(ssd_handle* h)
             if (apple_point || waste_point) {
                 if ((apple_point ? na : nw) >= 32 * MAX_POINT_ROUNDS)
                     return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * MAX_POINT_ROUNDS);
-                const uint32_t packed = off(r, col) | (off2(r, col) << 16);
+                const uint32_t packed = off(r, col) | ((p.tile2_off + off2(r, col)) << 16);       // both relative to the T base
                 if (apple_point) {
                     if (!cleanup) p.reset_amask[na >> 5] |= 1u << (na & 31);       // harvest starts with every apple (harvest_new.py:143-156)
                     apple_pt[na] = packed; apple_rc.push_back(rc16(r, col)); apple_c.push_back((uint16_t)(r * p.Wp + col));
@@ -243,7 +245,7 @@ static int setup_grid(ssd_handle* h)
     // canonical spawn order is the sorted list (row-major offsets are already sorted; duplicates adjacent)
     if (n_spawn_unique < n) return fail(h, SSD_EINVAL, "map has %d spawn points for %d agents", n_spawn_unique, n);
     if ((int)spawn.size() > 128) return fail(h, SSD_EUNSUPPORTED, "more than 128 spawn-list entries");
-    if ((p.S2 * (p.Wp + 2 * SSD_VIEW)) > 0xFFFF || p.TH * p.S > 0xFFFF) return fail(h, SSD_EUNSUPPORTED, "tile offsets exceed 16 bits");
+    if (p.g2_stage > 0xFFFF) return fail(h, SSD_EUNSUPPORTED, "tile offsets exceed 16 bits");
     p.n_apple = na; p.n_waste = nw; p.n_spawn = (int)spawn.size();
     p.n_waste_start = n_waste_start;
     h->rounds4 = p.n_apple <= 128 && p.n_waste <= 128;
@@ -320,6 +322,13 @@ static int setup_grid(ssd_handle* h)
     if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d; logic smem %d B\n",
                                      OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks, h->logic_smem);
     if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
+    if ((rc = dev_zalloc(h, 2, &p.obs_ctr))) return rc;
+    {   // observe kernel schedule: ~5/8 of every warp's envs static, the tail dynamic (SSD_OBS_STATIC_PCT overrides, 100 = all static)
+        const int per_warp = p.E / (h->obs_blocks * OBS_WARPS);
+        int pct = 62;
+        if (const char* e = getenv("SSD_OBS_STATIC_PCT")) pct = std::max(0, std::min(100, atoi(e)));
+        p.obs_static_iters = pct >= 100 ? (p.E + h->obs_blocks * OBS_WARPS - 1) / (h->obs_blocks * OBS_WARPS) : per_warp * pct / 100;
+    }
     return SSD_OK;
 }
 
@@ -538,24 +547,7 @@ __global__ void negotiate_kernel(SolverParams p, const uint8_t* mask, const doub
     if (env >= p.E) return;
     if (mask && !mask[env]) return;
     const uint32_t episode = *reinterpret_cast<const uint32_t*>(p.episode + (size_t)env * p.episode_stride) & p.episode_mask;
-    const uint32_t env_id = p.first_env_id + (uint32_t)env;
-    const int n = p.n;
-    double prod = 1.0;
-    if (n > 3) {
-        // random.sample(range(1, n), 2): first two of the stateless shuffle of [1..n-1]
-        uint32_t k1 = 0, k2 = 0; int i1 = -1, i2 = -1;
-        for (int j = 0; j < n - 1; j++) {
-            uint32_t k = draw_u32(p.seed, env_id, episode, 0, SITE_NEGOTIATE, 0, (uint32_t)j);
-            if (i1 < 0 || k < k1) { k2 = k1; i2 = i1; k1 = k; i1 = j; }
-            else if (i2 < 0 || k < k2) { k2 = k; i2 = j; }
-        }
-        prod = __dmul_rn(prod, accept[(size_t)env * n + 1 + i1]);
-        prod = __dmul_rn(prod, accept[(size_t)env * n + 1 + i2]);
-    } else {
-        for (int i = 1; i < n; i++) prod = __dmul_rn(prod, accept[(size_t)env * n + i]);
-    }
-    double r = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0, SITE_NEGOTIATE, 1, 0), 1.0 / 4294967296.0);
-    bool dec = r < prod;
+    const bool dec = negotiate_agreement(p.seed, p.first_env_id + (uint32_t)env, episode, p.n, accept + (size_t)env * p.n);
     *reinterpret_cast<double*>(p.theta + (size_t)env * p.theta_stride) = dec ? proposals[env] : 0.0;
     if (decision) decision[env] = dec ? 1 : 0;
 }
@@ -697,9 +689,9 @@ int ssd_reset(ssd_handle* h, const uint8_t* mask_dev, uint8_t* obs_dev, int64_t 
     cudaStream_t s = (cudaStream_t)stream;
     if (p.beam) beam_clear_kernel<<<(p.E + 3) / 4, 128, 0, s>>>(p, mask_dev);                 // self.beam_pos = [] (map_env.py:316)
     if (p.kind == SSD_ENV_CLEANUP)
-        grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+        grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride, StepIO());
     else
-        grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride);
+        grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, mask_dev, obs_dev, stride, StepIO());
     return check_launch(h, "reset");
 }
 
@@ -716,6 +708,13 @@ static int make_step_io(ssd_handle* h, const ssd_step_io* io, StepIO& k, bool as
     k.rew = io->rew_dev; k.base_rew = io->base_rew_dev; k.transfers = io->transfers_dev;
     k.info = io->info_dev; k.feat = io->feature_obs_dev; k.done = io->done_dev;
     if (k.info && (reinterpret_cast<uintptr_t>(k.info) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
+    k.auto_reset = io->auto_reset != 0;
+    if (k.auto_reset) {
+        if ((io->neg_proposals_dev == nullptr) != (io->neg_accept_dev == nullptr))
+            return fail(h, SSD_EINVAL, "neg_proposals_dev and neg_accept_dev go together");
+        k.neg_prop = io->neg_proposals_dev; k.neg_acc = io->neg_accept_dev; k.neg_dec = io->neg_decision_dev;
+        if (!k.done) return fail(h, SSD_EINVAL, "auto_reset needs done_dev");
+    }
     return SSD_OK;
 }
 
@@ -770,6 +769,11 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (p.kind == SSD_ENV_HARVEST) {
         h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
+    }
+    if (k.auto_reset) {          // the envs that finished restart (and negotiate) behind the step: one masked launch
+        h->launches++;
+        if (p.kind == SSD_ENV_CLEANUP) grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
+        else grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
     }
     if (h->timing) cudaEventRecord(h->tev[2], s);
     return check_launch(h, "step");

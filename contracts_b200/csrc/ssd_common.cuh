@@ -76,6 +76,33 @@ __device__ __forceinline__ uint32_t draw_u32(uint32_t seed, uint32_t env_id, uin
     return pick(draw_block(seed, env_id, episode, t, site, call, idx >> 2), idx & 3);
 }
 
+// Agreement stage of SeparateContractNegotiateStage.step (two_stage_train.py:266-281) for one env: the acceptance
+// probabilities of 2 sampled agents of 1..n-1 (all of them when n <= 3) are multiplied and one uniform draw decides.
+// accept: the env's row double [n] (each agent's action[-1]).  Draws are addressed by the env's CURRENT episode at t = 0.
+__device__ __forceinline__ bool negotiate_agreement(uint32_t seed, uint32_t env_id, uint32_t episode, int n, const double* accept)
+{
+    double prod = 1.0;
+    if (n > 3) {
+        // random.sample(range(1, n), 2): first two of the stateless shuffle of [1..n-1] (keys = draws 0..n-2 of call 0:
+        // one Philox block, two when n - 1 > 4)
+        const Philox4 b0 = draw_block(seed, env_id, episode, 0, SITE_NEGOTIATE, 0, 0);
+        Philox4 b1 = b0;
+        if (n - 1 > 4) b1 = draw_block(seed, env_id, episode, 0, SITE_NEGOTIATE, 0, 1);
+        uint32_t k1 = 0, k2 = 0; int i1 = -1, i2 = -1;
+        for (int j = 0; j < n - 1; j++) {
+            const uint32_t k = pick(j < 4 ? b0 : b1, (uint32_t)j & 3u);
+            if (i1 < 0 || k < k1) { k2 = k1; i2 = i1; k1 = k; i1 = j; }
+            else if (i2 < 0 || k < k2) { k2 = k; i2 = j; }
+        }
+        prod = __dmul_rn(prod, accept[1 + i1]);
+        prod = __dmul_rn(prod, accept[1 + i2]);
+    } else {
+        for (int i = 1; i < n; i++) prod = __dmul_rn(prod, accept[i]);
+    }
+    const double r = __dmul_rn((double)draw_u32(seed, env_id, episode, 0, SITE_NEGOTIATE, 1, 0), 1.0 / 4294967296.0);
+    return r < prod;
+}
+
 // SSD_STEP_AUTO (ssd_random_actions & co.): counter[0] = step index, counter[1] = CTAs finished.  Every CTA reads
 // counter[0] before it arrives at counter[1]; the last one to arrive bumps the index for the next launch, so a captured
 // CUDA graph draws fresh actions at every replay without a separate one-thread kernel.

@@ -103,6 +103,8 @@ struct GridParams {
     uint8_t* state;
     uint8_t* beam;               // optional [E][map_bytes]: beam_pos of the last step as a char overlay (render only)
     double* stats;               // optional [8]: ssd_set_episode_stats accumulator (added to by the reset kernel)
+    uint32_t* obs_ctr;           // [2] observe kernel: next env of the dynamically scheduled tail, CTAs finished
+    int obs_static_iters;        // observe kernel: iterations every warp takes from the static grid-stride schedule
 };
 
 // use_collective_reward / inequity_averse_reward (map_env.py:289-301): the shaped reward of agent a from the
@@ -156,6 +158,10 @@ struct StepIO {
     // compact result block of ssd_step_host_async (all null otherwise): int8 rewards, dones, and records
     // { int32 env; int32 0; double rew[n] } for the envs whose rewards are not all integers in [-127, 127]
     int8_t* c_rew8; uint8_t* c_done; uint32_t* c_count; uint8_t* c_rec;
+    // auto_reset: envs that finish in this step (t == horizon) are reset by the step itself — their observation becomes
+    // the reset observation — and, when neg_prop / neg_acc are given, negotiate their next contract (two_stage_train.py:266-281)
+    int auto_reset;
+    const double* neg_prop; const double* neg_acc; uint8_t* neg_dec;
 };
 
 // is `r` exactly an integer in [-127, 127]?  (bit pattern compared: -0.0 is not)
@@ -341,7 +347,9 @@ __device__ __noinline__ uint32_t resolve_moves_slow(int lane, int n, uint32_t se
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-lane point registers: lane l owns points l, l + 32, ... of each list.  pt[q] = offset in T | offset in T2 << 16.
+// Per-lane point registers: lane l owns points l, l + 32, ... of each list.  pt[q] = offset in T | offset in T2 << 16,
+// both relative to the warp's tile base (T2 follows T).  Slots beyond a list point at spare sink bytes behind T / T2, so
+// the dynamic-cell rewrite needs no bounds tests.
 template <int MW>
 struct PointRegs { uint32_t a[MW], w[MW]; };
 template <int MW>
@@ -359,10 +367,10 @@ __device__ __forceinline__ uint32_t round_valid(int count, int q)
     return left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
 }
 // write a dynamic cell into T and (when kept) T2
-__device__ __forceinline__ void put_cell(uint8_t* tile, uint8_t* tile2, uint32_t pt, uint32_t code)
+__device__ __forceinline__ void put_cell(uint8_t* tile, bool has2, uint32_t pt, uint32_t code)
 {
     tile[pt & 0xFFFFu] = (uint8_t)code;
-    if (tile2) tile2[pt >> 16] = (uint8_t)code;
+    if (has2) tile[pt >> 16] = (uint8_t)code;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -374,7 +382,7 @@ __device__ __forceinline__ bool cleanup_spawn_active(const SharedTables& tb, int
     return tb.thr_apple[hcount] != 0 || tb.waste_on[hcount] != 0;
 }
 template <int MW>
-__device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile, uint8_t* tile2,
+__device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile, bool tile2,
                                               uint32_t* scratch, const EnvRng& g, uint32_t t, int& hcount,
                                               const PointRegs<MW>& pr, uint32_t (&am)[MW], uint32_t (&wm)[MW])
 {
@@ -482,7 +490,7 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
 // whatever the neighbour count is.  So the 3x3 neighbour counts (8 tile reads) are evaluated only for those ~5 % of the
 // eligible points, compacted into a list: one pass of the warp instead of one per 32 points.
 template <int MW>
-__device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, uint8_t* tile2, uint32_t* scratch,
+__device__ __forceinline__ bool harvest_spawn(const GridParams& p, int lane, uint8_t* tile, bool tile2, uint32_t* scratch,
                                               const EnvRng& g, uint32_t t, const PointRegs<MW>& pr, uint32_t (&am)[MW])
 {
     const int S = p.S;
@@ -742,25 +750,158 @@ __device__ __forceinline__ void init_warp_tiles(const GridParams& p, uint8_t* ti
     const uint4* src = reinterpret_cast<const uint4*>(p.tile0);
     for (int i = lane; i < (p.g2_stage >> 4); i += 32) reinterpret_cast<uint4*>(tile)[i] = __ldg(src + i);
 }
-// rewrite every dynamic cell of T (and T2) from the env's masks
-template <int MW>
-__device__ __forceinline__ void apply_masks(const GridParams& p, int lane, uint8_t* tile, uint8_t* tile2, const PointRegs<MW>& pr,
-                                            const uint32_t (&am)[MW], const uint32_t (&wm)[MW])
+// rewrite every dynamic cell of T (and T2) from the env's masks.  rot3 = (lane - 3) & 31, rot2 = (lane - 2) & 31: rotating a
+// mask word right by them puts this lane's bit where the cell code wants it (C_APPLE = 8 = bit 3; C_RIVER - C_WASTE = 4).
+template <int MW, bool HAS2>
+__device__ __forceinline__ void apply_masks(const GridParams& p, uint8_t* tile, const PointRegs<MW>& pr,
+                                            const uint32_t (&am)[MW], const uint32_t (&wm)[MW], uint32_t rot3, uint32_t rot2)
 {
+    static_assert(C_APPLE == 8 && C_EMPTY == 0 && C_RIVER == 16 && C_WASTE == 12, "cell codes are folded into bit tricks here");
 #pragma unroll
     for (int q = 0; q < MW; q++) {
-        if (q * 32 < p.n_apple && lane + 32 * q < p.n_apple) put_cell(tile, tile2, pr.a[q], ((am[q] >> lane) & 1u) ? C_APPLE : C_EMPTY);
-        if (q * 32 < p.n_waste && lane + 32 * q < p.n_waste) put_cell(tile, tile2, pr.w[q], ((wm[q] >> lane) & 1u) ? C_WASTE : C_RIVER);
+        if (q * 32 < p.n_apple) put_cell(tile, HAS2, pr.a[q], __funnelshift_r(am[q], am[q], rot3) & 8u);
+        if (q * 32 < p.n_waste) put_cell(tile, HAS2, pr.w[q], 16u - (__funnelshift_r(wm[q], wm[q], rot2) & 4u));
     }
 }
 
 // =============================================================================================
-// RESET: setup_agents + reset_map + custom_reset + reset-time spawn + contract sample + reset obs.  One warp per env;
-// the warp's envs are env0 + i * estride, their mask bytes are read 32 at a time (one round trip, one ballot), so a
-// sparse mask — a vectorised sampler in steady state resets ~E / horizon envs per step — costs a few loads per warp.
+// RESET of one env by one warp: setup_agents + reset_map + custom_reset + reset-time spawn + contract sample + reset obs
+// (+ the negotiation agreement when the policy's negotiation outputs are given).  `tile` is the warp's T with every agent
+// mark removed; it is left that way.
+// (Measured and dropped in round 2: doing this inside the observe kernel for the envs that finish in the step.  Inlined it
+// costs the hot loop registers (12 -> 68 B of spills), out of line it forces spills around the call, and a warp that
+// resets an env finishes ~10 us after the others of the one-wave persistent grid: observe kernel 0.204 -> 0.223 ms, more
+// than the launch it saves.  ssd_step_io.auto_reset therefore launches the masked reset kernel behind the step.)
+template <int KIND, int MW>
+__device__ __forceinline__ void reset_env(const GridParams& p, const SharedTables& tb, int lane, uint8_t* tile, uint8_t* stage, int4* vdesc,
+                                          const PointRegs<MW>& pr, int env, uint8_t* obs_dst, const double* neg_prop,
+                                          const double* neg_acc, uint8_t* neg_dec)
+{
+    const int n = p.n, S = p.S;
+    const bool act_lane = lane < n;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
+    uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
+    uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
+    uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
+    if (p.stats && (flags & 0x80000000u)) {       // a finished episode is replaced: hand its accumulators over
+        double tr = 0.0, raw = 0.0;
+        if (act_lane) {
+            tr = reinterpret_cast<const double*>(hdr + RO_SUM_TR)[lane];
+            raw = p.reward_mode ? reinterpret_cast<const double*>(hdr + RO_XSUM)[lane]
+                                : (double)reinterpret_cast<const int*>(hdr + RO_SUM_RAW)[lane];
+        }
+        for (int o = 16; o; o >>= 1) { tr += __shfl_xor_sync(FULL, tr, o); raw += __shfl_xor_sync(FULL, raw, o); }
+        if (lane == 0) {
+            atomicAdd(p.stats + 0, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_APPLES));
+            atomicAdd(p.stats + 1, p.reward_mode ? *reinterpret_cast<const double*>(hdr + RO_XRAW) : raw);
+            atomicAdd(p.stats + 2, *reinterpret_cast<const double*>(hdr + RO_TRANSFERS));
+            atomicAdd(p.stats + 3, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_DIRT));
+            atomicAdd(p.stats + 4, tr);
+            atomicAdd(p.stats + 5, raw);
+            atomicAdd(p.stats + 6, 1.0);
+            // non-negative doubles order like their bit patterns
+            atomicMax(reinterpret_cast<unsigned long long*>(p.stats + 7),
+                      (unsigned long long)__double_as_longlong((double)((flags >> RF_ERR_SHIFT) & 0xFFFFu)));
+        }
+    }
+    // the first reset of a record (flags bit 31 clear) is episode 0; later resets increment
+    episode = (flags & 0x80000000u) ? episode + 1u : 0u;
+    EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, 0u };
+
+    // ---- setup_agents (cleanup_new.py:302-320 / harvest_new.py:132-141; map_env.py:816-832)
+    // Lane l owns the canonical spawn-list entries 4 l .. 4 l + 3 (<= 128 entries), so ONE Philox block per agent gives
+    // the lane's four shuffle keys (draw idx j lives in block j >> 2, word j & 3); lane i draws agent i's rotation.
+    int ao = 0, ori = 0;
+    uint32_t cells[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cells[k] = 4 * lane + k < p.n_spawn ? (uint32_t)__ldg(p.spawn_pts + 4 * lane + k) : 0xFFFFFFFFu;
+    uint32_t rot = 0;
+    if (act_lane) rot = draw_u32(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_ROT, (uint32_t)lane, 0u) >> 30;
+    unsigned taken[4] = { 0, 0, 0, 0 };          // taken[k] bit l: entry 4 l + k is occupied (uniform)
+    for (int i = 0; i < n; i++) {
+        // shuffled list = canonical entries ordered by (key, idx); the LAST free entry wins (:822-825)
+        const Philox4 kq = draw_block(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_POINT, (uint32_t)i, (uint32_t)lane);
+        const uint32_t kk4[4] = { kq.x, kq.y, kq.z, kq.w };
+        uint32_t bk = 0; int bj = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int j = 4 * lane + k;
+            if (j < p.n_spawn && !((taken[k] >> lane) & 1u)) {
+                const uint32_t kk = kk4[k];
+                if (bj < 0 || kk > bk || (kk == bk && j > bj)) { bk = kk; bj = j; }
+            }
+        }
+        uint32_t kmax = __reduce_max_sync(FULL, bj >= 0 ? bk : 0u);
+        int jmax = (int)__reduce_max_sync(FULL, (bj >= 0 && bk == kmax) ? (uint32_t)(bj + 1) : 0u) - 1;
+        const uint32_t mine = (jmax & 3) == 0 ? cells[0] : ((jmax & 3) == 1 ? cells[1] : ((jmax & 3) == 2 ? cells[2] : cells[3]));
+        const int cell = (int)__shfl_sync(FULL, mine, jmax >> 2);
+        // every canonical entry on that cell becomes occupied (cleanup lists each point twice)
+#pragma unroll
+        for (int k = 0; k < 4; k++) taken[k] |= __ballot_sync(FULL, cells[k] == (uint32_t)cell);
+        const uint32_t rdraw = __shfl_sync(FULL, rot, i);
+        // list(ORIENTATIONS.keys()) = LEFT, RIGHT, UP, DOWN (map_env.py:22, :829-832)
+        int o = rdraw == 0 ? ORI_LEFT : (rdraw == 1 ? ORI_RIGHT : (rdraw == 2 ? ORI_UP : ORI_DOWN));
+        if (lane == i) { ao = cell; ori = o; }
+    }
+    // ---- reset_map + custom_reset: the initial dynamic state, occupancy, reset-time spawn (map_env.py:319-320)
+    uint32_t am[MW], wm[MW];
+#pragma unroll
+    for (int q = 0; q < MW; q++) { am[q] = p.reset_amask[q]; wm[q] = p.reset_wmask[q]; }
+    apply_masks<MW, false>(p, tile, pr, am, wm, (uint32_t)(lane - 3) & 31u, (uint32_t)(lane - 2) & 31u);
+    if (lane == 0) bulk_wait_read<0>();          // `stage` doubles as the spawn scratch
+    __syncwarp();
+    if (act_lane) tile[ao] |= OCC_BIT;           // co-located lanes write the same value
+    __syncwarp();
+    int hcount = p.n_waste_start;
+    if (KIND == SSD_ENV_CLEANUP) cleanup_spawn<MW>(p, tb, lane, tile, false, scratch, g, 0u, hcount, pr, am, wm);
+    else harvest_spawn<MW>(p, lane, tile, false, scratch, g, 0u, pr, am);
+    __syncwarp();
+    if (act_lane) tile[ao] &= CODE_MASK;              // MapEnv.reset never paints agents into the colour grid; the tile is clean again
+    __syncwarp();
+    if (obs_dst) gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, obs_dst);
+
+    // ---- SeparateContractSubgameStage.reset (two_stage_train.py:163-168)
+    double theta = 0.0;
+    if (p.contract != SSD_CONTRACT_NONE) {
+        Philox4 q = draw_block(g.seed, g.env_id, g.episode, 0, SITE_CONTRACT, 0, 0);
+        double u0 = __dmul_rn((double)q.x, 1.0 / 4294967296.0), u1 = __dmul_rn((double)q.y, 1.0 / 4294967296.0);
+        theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1))
+                                   : p.theta_low;
+    }
+    // ---- negotiation prologue of the new episode (SeparateContractNegotiateStage.step, two_stage_train.py:257-281)
+    if (neg_prop && lane == 0) {
+        const bool dec = negotiate_agreement(g.seed, g.env_id, episode, n, neg_acc + (size_t)env * n);
+        theta = dec ? neg_prop[env] : 0.0;
+        if (neg_dec) neg_dec[env] = dec ? 1 : 0;
+    }
+    // ---- record: zero everything, then the hot line
+    for (int i = lane; i < p.hdr_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(hdr)[i] = 0u;
+    __syncwarp();
+    if (act_lane) {
+        uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
+        reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
+    }
+#pragma unroll
+    for (int q = 0; q < MW; q++)
+        if (lane == q) {
+            reinterpret_cast<uint32_t*>(hdr + RO_AMASK)[q] = am[q];
+            reinterpret_cast<uint32_t*>(hdr + RO_WMASK)[q] = wm[q];
+        }
+    if (lane == 0) {
+        *reinterpret_cast<uint32_t*>(hdr + RO_EPISODE) = episode;
+        *reinterpret_cast<double*>(hdr + RO_THETA) = theta;
+        *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = 0x80000000u | (KIND == SSD_ENV_CLEANUP ? RF_STALE_EMPTY : 0u);
+        *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
+    }
+    __syncwarp();
+}
+
+// RESET kernel: one warp per env; the warp's envs are env0 + i * estride, their mask bytes are read 32 at a time (one round
+// trip, one ballot), so a sparse mask — a vectorised sampler in steady state resets ~E / horizon envs per step — costs a
+// few loads per warp.
 template <int KIND>
 __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridParams p, const uint8_t* mask,
-                                                                  uint8_t* obs, long long obs_stride)
+                                                                  uint8_t* obs, long long obs_stride, const StepIO io)
 {
     constexpr int MW = MAX_POINT_ROUNDS;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -775,123 +916,19 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     const SharedTables tb = load_shared_tables(p, smem, false);
     uint8_t* tile = smem + p.sm_warp0 + warp * p.g2_warp_bytes;
     uint8_t* stage = tile + p.g2_stage;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
     int4* vdesc = reinterpret_cast<int4*>(tile + p.g2_misc + MISC_VDESC);
     const PointRegs<MW> pr = load_point_regs<MW>(p, lane);
     init_warp_tiles(p, tile, lane);
     __syncthreads();
-    const int n = p.n, S = p.S;
-    const bool act_lane = lane < n;
-
     for (int i0 = 0; env0 + (long long)i0 * estride < p.E; i0 += 32) {
-      const long long el = env0 + (long long)(i0 + lane) * estride;
-      unsigned todo = __ballot_sync(FULL, el < p.E && (!mask || mask[el]));
-      while (todo) {
-        const int env = env0 + (i0 + __ffs(todo) - 1) * estride;
-        todo &= todo - 1;
-        uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
-        uint32_t flags = *reinterpret_cast<const uint32_t*>(hdr + RO_FLAGS);
-        uint32_t episode = *reinterpret_cast<const uint32_t*>(hdr + RO_EPISODE);
-        if (p.stats && (flags & 0x80000000u)) {       // a finished episode is replaced: hand its accumulators over
-            double tr = 0.0, raw = 0.0;
-            if (act_lane) {
-                tr = reinterpret_cast<const double*>(hdr + RO_SUM_TR)[lane];
-                raw = p.reward_mode ? reinterpret_cast<const double*>(hdr + RO_XSUM)[lane]
-                                    : (double)reinterpret_cast<const int*>(hdr + RO_SUM_RAW)[lane];
-            }
-            for (int o = 16; o; o >>= 1) { tr += __shfl_xor_sync(FULL, tr, o); raw += __shfl_xor_sync(FULL, raw, o); }
-            if (lane == 0) {
-                atomicAdd(p.stats + 0, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_APPLES));
-                atomicAdd(p.stats + 1, p.reward_mode ? *reinterpret_cast<const double*>(hdr + RO_XRAW) : raw);
-                atomicAdd(p.stats + 2, *reinterpret_cast<const double*>(hdr + RO_TRANSFERS));
-                atomicAdd(p.stats + 3, (double)*reinterpret_cast<const uint32_t*>(hdr + RO_DIRT));
-                atomicAdd(p.stats + 4, tr);
-                atomicAdd(p.stats + 5, raw);
-                atomicAdd(p.stats + 6, 1.0);
-                // non-negative doubles order like their bit patterns
-                atomicMax(reinterpret_cast<unsigned long long*>(p.stats + 7),
-                          (unsigned long long)__double_as_longlong((double)((flags >> RF_ERR_SHIFT) & 0xFFFFu)));
-            }
+        const long long el = env0 + (long long)(i0 + lane) * estride;
+        unsigned todo = __ballot_sync(FULL, el < p.E && (!mask || mask[el]));
+        while (todo) {
+            const int env = env0 + (i0 + __ffs(todo) - 1) * estride;
+            todo &= todo - 1;
+            reset_env<KIND, MW>(p, tb, lane, tile, stage, vdesc, pr, env, obs ? obs + (size_t)env * (size_t)obs_stride : nullptr,
+                                io.neg_prop, io.neg_acc, io.neg_dec);
         }
-        // the first reset of a record (flags bit 31 clear) is episode 0; later resets increment
-        episode = (flags & 0x80000000u) ? episode + 1u : 0u;
-        EnvRng g = { p.seed, p.first_env_id + (uint32_t)env, episode, 0u };
-
-        // ---- setup_agents (cleanup_new.py:302-320 / harvest_new.py:132-141; map_env.py:816-832)
-        int ao = 0, ori = 0;
-        unsigned taken[4] = { 0, 0, 0, 0 };          // bit per canonical spawn entry (<= 128), uniform
-        for (int i = 0; i < n; i++) {
-            // shuffled list = canonical entries ordered by (key, idx); the LAST free entry wins (:822-825)
-            uint32_t bk = 0; int bj = -1;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                int j = lane + 32 * q;
-                if (j < p.n_spawn && !((taken[q] >> lane) & 1u)) {
-                    uint32_t kk = draw_u32(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_POINT, (uint32_t)i, (uint32_t)j);
-                    if (bj < 0 || kk > bk || (kk == bk && j > bj)) { bk = kk; bj = j; }
-                }
-            }
-            uint32_t kmax = __reduce_max_sync(FULL, bj >= 0 ? bk : 0u);
-            int jmax = (int)__reduce_max_sync(FULL, (bj >= 0 && bk == kmax) ? (uint32_t)(bj + 1) : 0u) - 1;
-            int cell = (int)__ldg(p.spawn_pts + jmax);
-            // every canonical entry on that cell becomes occupied (cleanup lists each point twice)
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                int j = lane + 32 * q;
-                bool same = j < p.n_spawn && (int)__ldg(p.spawn_pts + j) == cell;
-                taken[q] |= __ballot_sync(FULL, same);
-            }
-            uint32_t rdraw = draw_u32(g.seed, g.env_id, g.episode, 0, SITE_SPAWN_ROT, (uint32_t)i, 0u) >> 30;
-            // list(ORIENTATIONS.keys()) = LEFT, RIGHT, UP, DOWN (map_env.py:22, :829-832)
-            int o = rdraw == 0 ? ORI_LEFT : (rdraw == 1 ? ORI_RIGHT : (rdraw == 2 ? ORI_UP : ORI_DOWN));
-            if (lane == i) { ao = cell; ori = o; }
-        }
-        // ---- reset_map + custom_reset: the initial dynamic state, occupancy, reset-time spawn (map_env.py:319-320)
-        uint32_t am[MW], wm[MW];
-#pragma unroll
-        for (int q = 0; q < MW; q++) { am[q] = p.reset_amask[q]; wm[q] = p.reset_wmask[q]; }
-        apply_masks<MW>(p, lane, tile, nullptr, pr, am, wm);
-        if (lane == 0) bulk_wait_read<0>();          // `stage` doubles as the spawn scratch
-        __syncwarp();
-        if (act_lane) tile[ao] |= OCC_BIT;           // co-located lanes write the same value
-        __syncwarp();
-        int hcount = p.n_waste_start;
-        if (KIND == SSD_ENV_CLEANUP) cleanup_spawn<MW>(p, tb, lane, tile, nullptr, scratch, g, 0u, hcount, pr, am, wm);
-        else harvest_spawn<MW>(p, lane, tile, nullptr, scratch, g, 0u, pr, am);
-        __syncwarp();
-        if (act_lane) tile[ao] &= CODE_MASK;              // MapEnv.reset never paints agents into the colour grid; the tile is clean again
-        __syncwarp();
-        if (obs) gather_obs<0>(p, lane, tile, stage, tb.pal, vdesc, ao, ori, obs + (size_t)env * (size_t)obs_stride);
-
-        // ---- SeparateContractSubgameStage.reset (two_stage_train.py:163-168)
-        double theta = 0.0;
-        if (p.contract != SSD_CONTRACT_NONE) {
-            Philox4 q = draw_block(g.seed, g.env_id, g.episode, 0, SITE_CONTRACT, 0, 0);
-            double u0 = __dmul_rn((double)q.x, 1.0 / 4294967296.0), u1 = __dmul_rn((double)q.y, 1.0 / 4294967296.0);
-            theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1))
-                                       : p.theta_low;
-        }
-        // ---- record: zero everything, then the hot line
-        for (int i = lane; i < p.hdr_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(hdr)[i] = 0u;
-        __syncwarp();
-        if (act_lane) {
-            uint32_t row = (uint32_t)(ao / S) - SSD_VIEW, col = (uint32_t)(ao % S) - 8u;
-            reinterpret_cast<uint32_t*>(hdr + RO_AGENTS)[lane] = row | (col << 8) | ((uint32_t)ori << 16);
-        }
-#pragma unroll
-        for (int q = 0; q < MW; q++)
-            if (lane == q) {
-                reinterpret_cast<uint32_t*>(hdr + RO_AMASK)[q] = am[q];
-                reinterpret_cast<uint32_t*>(hdr + RO_WMASK)[q] = wm[q];
-            }
-        if (lane == 0) {
-            *reinterpret_cast<uint32_t*>(hdr + RO_EPISODE) = episode;
-            *reinterpret_cast<double*>(hdr + RO_THETA) = theta;
-            *reinterpret_cast<uint32_t*>(hdr + RO_FLAGS) = 0x80000000u | (KIND == SSD_ENV_CLEANUP ? RF_STALE_EMPTY : 0u);
-            *reinterpret_cast<int*>(hdr + RO_HCOUNT) = hcount;
-        }
-        __syncwarp();
-      }
     }
     if (lane == 0) bulk_wait_read<0>();
 }

@@ -641,17 +641,34 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
     const int n = p.n, S = p.S, S2 = p.S2;
     const bool act_lane = lane < n;
     const int env_stride = gridDim.x * OBS_WARPS;
+    const uint32_t rot3 = (uint32_t)(lane - 3) & 31u, rot2 = (uint32_t)(lane - 2) & 31u;
 
-    int env = blockIdx.x * OBS_WARPS + warp;
-    uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
-    const size_t g_rec_step = (size_t)env_stride * p.rec_stride;
-    uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
-    const size_t g_obs_step = (size_t)env_stride * (size_t)io.obs_stride;
+    // Schedule.  An env costs 3-7 us depending on whether its spawn is active, and a one-wave persistent grid ends with its
+    // slowest warp (ncu, static schedule: 21 of 24 resident warps active on average).  So every warp takes its first
+    // obs_static_iters envs from the static grid-stride schedule and the rest, one at a time, from a global counter
+    // (requested two envs ahead, so the atomic's latency hides behind an env's work; the last CTA to finish rearms it).
+    const int nwarps = env_stride, wid = blockIdx.x * OBS_WARPS + warp;
+    const int dyn0 = p.obs_static_iters * nwarps;          // first env of the dynamic pool
+    int it = 0;
+    auto next_env = [&]() -> int {
+        int e;
+        if (it < p.obs_static_iters) e = wid + it * nwarps;
+        else {
+            e = 0;
+            if (lane == 0) e = dyn0 + (int)atomicAdd(p.obs_ctr, 1u);
+            e = __shfl_sync(FULL, e, 0);
+        }
+        it++;
+        return e;
+    };
+    int env = next_env(), env_n = next_env();
     uint32_t hw_next = 0;
-    if (env < p.E) hw_next = reinterpret_cast<const uint32_t*>(g_rec)[lane];
-    for (; env < p.E; env += env_stride) {
+    if (env < p.E) hw_next = reinterpret_cast<const uint32_t*>(p.state + (size_t)env * p.rec_stride)[lane];
+    for (; env < p.E; env = env_n, env_n = next_env()) {
+        uint8_t* g_rec = p.state + (size_t)env * p.rec_stride;
+        uint8_t* g_obs = io.obs + (size_t)env * (size_t)io.obs_stride;
         const uint32_t hw = hw_next;
-        if (env + env_stride < p.E) hw_next = reinterpret_cast<const uint32_t*>(g_rec + g_rec_step)[lane];
+        if (env_n < p.E) hw_next = reinterpret_cast<const uint32_t*>(p.state + (size_t)env_n * p.rec_stride)[lane];
         // ---- dynamic cells of T and T2 from the masks; header scalars
         uint32_t am[MW], wm[MW];
 #pragma unroll
@@ -659,7 +676,7 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
             am[q] = __shfl_sync(FULL, hw, RO_AMASK / 4 + q);
             wm[q] = KIND == SSD_ENV_CLEANUP ? __shfl_sync(FULL, hw, RO_WMASK / 4 + q) : 0u;
         }
-        apply_masks<MW>(p, lane, tile, tile2, pr, am, wm);
+        apply_masks<MW, true>(p, tile, pr, am, wm, rot3, rot2);
         const uint32_t t = __shfl_sync(FULL, hw, RO_T / 4);               // already incremented by the logic kernel
         const uint32_t episode = __shfl_sync(FULL, hw, RO_EPISODE / 4);
         int hcount = (int)__shfl_sync(FULL, hw, RO_HCOUNT / 4);
@@ -685,12 +702,12 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
             if (cleanup_spawn_active(tb, hcount)) {
                 if (lane == 0) bulk_wait_read<0>();   // the previous observation store has drained `stage` (= scratch)
                 __syncwarp();
-                changed = cleanup_spawn<MW>(p, tb, lane, tile, tile2, scratch, g, t, hcount, pr, am, wm);
+                changed = cleanup_spawn<MW>(p, tb, lane, tile, true, scratch, g, t, hcount, pr, am, wm);
             }
         } else {
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
-            changed = harvest_spawn<MW>(p, lane, tile, tile2, scratch, g, t, pr, am);
+            changed = harvest_spawn<MW>(p, lane, tile, true, scratch, g, t, pr, am);
         }
         if (changed) {                                // the masks (and #waste) go back only when the spawn changed them
             uint32_t* hot = reinterpret_cast<uint32_t*>(g_rec);
@@ -723,8 +740,12 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
 #endif
         // the agents' cells back to their code (gather_obs2 ends behind a warp barrier after its last tile read)
         if (act_lane) { tile[ao] = (uint8_t)old; tile2[ao2] = (uint8_t)old; }
-        g_rec += g_rec_step; g_obs += g_obs_step;
         __syncwarp();
     }
     if (lane == 0) bulk_wait_read<0>();      // smem must outlive the async bulk reads
+    __syncthreads();
+    if (threadIdx.x == 0) {                  // every warp of this CTA has taken its last env: rearm the counter behind the last CTA
+        __threadfence();
+        if (atomicAdd(p.obs_ctr + 1, 1u) == gridDim.x - 1) { p.obs_ctr[0] = 0u; p.obs_ctr[1] = 0u; }
+    }
 }

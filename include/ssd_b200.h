@@ -102,6 +102,17 @@ typedef struct ssd_step_io {
     uint8_t* info_dev;        /* [E][n][4]: eaten_apples, cleaned_squares|eaten_close_apples, total_close_apples, 0 */
     double* feature_obs_dev;  /* [E][n][F] infos['feature_obs'] (cleanup_new.py:243-251 F=12+n, harvest_new.py:215-222 F=10+2n) */
     uint8_t* done_dev;        /* [E] dones['__all__'] (cleanup_new.py:242) */
+    /* Vectorised-sampler mode (what RLlib's rollout worker does with a vector env, utils/ray_config_utils.py:140: reset
+     * an env as soon as it is done).  auto_reset != 0: every env that finishes in this step (t == horizon) is reset
+     * by the step itself, exactly as ssd_reset with mask = done would (same draws, same episode statistics hand-off):
+     * its rewards / dones / infos are those of the final step, its observation is the RESET observation of the next
+     * episode.  With neg_proposals_dev / neg_accept_dev (double [E] / [E][n], the policy's negotiation outputs for every
+     * env; only the rows of the resetting envs are read) the agreement stage of ssd_negotiate also runs for them
+     * (neg_decision_dev uint8 [E], nullable, receives their decisions).  Needs done_dev.  One masked launch behind the step. */
+    int32_t auto_reset;
+    const double* neg_proposals_dev;
+    const double* neg_accept_dev;
+    uint8_t* neg_decision_dev;
 } ssd_step_io;
 
 /* --- lifetime ------------------------------------------------------------------------------- */

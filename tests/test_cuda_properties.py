@@ -247,3 +247,53 @@ def test_handle_on_non_current_device():
         assert torch.equal(r1[0].cpu(), r0[0].cpu()) and torch.equal(r1[1].cpu(), r0[1].cpu())
     e1.close(); e0.close()
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("kind,contract,n,negotiate", [("cleanup_new", "CleanupContract", 8, True), ("cleanup_new", "CleanupContract", 3, False),
+                                                       ("harvest_new", "HarvestFeaturemodLocalContract", 4, True),
+                                                       ("cleanup_new", None, 5, False)])
+def test_auto_reset_equals_step_reset_negotiate(kind, contract, n, negotiate):
+    """ssd_step_io.auto_reset (finished envs restart — and negotiate — inside the step) leaves exactly the state, outputs
+    and episode statistics that step + reset(mask = done) + negotiate(mask = done) leave.  Horizons are staggered through
+    set_state(t) so that a few envs finish in every step, as in a vectorised sampler's steady state."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    E, H = 900, 23
+    a = BatchedGridEnv(kind, E, n, contract=contract, seed=31, first_env_id=5, horizon=H)
+    b = BatchedGridEnv(kind, E, n, contract=contract, seed=31, first_env_id=5, horizon=H)
+    sa, sb = (torch.zeros(8, dtype=torch.float64, device=a.device) for _ in range(2))
+    a.set_episode_stats(sa); b.set_episode_stats(sb)
+    a.reset(); b.reset()
+    t0 = (torch.arange(E, device=a.device) % H).to(torch.int32)
+    a.set_state(t=t0); b.set_state(t=t0)
+    gen = torch.Generator(device=a.device); gen.manual_seed(1)
+    nact = 9 if kind == "cleanup_new" else 8
+    dec_a = torch.zeros(E, dtype=torch.uint8, device=a.device); dec_b = torch.zeros_like(dec_a)
+    resets = 0
+    for t in range(3 * H):
+        prop = torch.rand(E, dtype=torch.float64, device=a.device, generator=gen) * 0.2
+        acc = torch.rand((E, n), dtype=torch.float64, device=a.device, generator=gen) * 0.5 + 0.5
+        act = a.random_actions(t, nact)
+        oa, ra, da, ia = a.step(act)
+        if bool(da.any()):
+            oa = a.reset(da)
+            if negotiate:
+                a.negotiate(prop, acc, mask=da, out=dec_a)
+        ob, rb, db, ib = b.step(act, auto_reset=True, negotiation=(prop, acc, dec_b) if negotiate else None)
+        resets += int(da.sum())
+        ctx = (kind, t)
+        assert torch.equal(da, db) and int(da.sum()) > 0, ctx
+        assert torch.equal(oa, ob), ctx
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ia, ib), ctx
+        assert torch.equal(a.base_rew.view(torch.int64), b.base_rew.view(torch.int64)), ctx
+        sta, stb = a.get_state(), b.get_state()
+        for k in sta:
+            assert torch.equal(sta[k], stb[k]), (k,) + ctx
+        if negotiate:
+            assert torch.equal(dec_a, dec_b), ctx
+    assert resets > 2 * E
+    assert torch.equal(a.metrics_raw(), b.metrics_raw())
+    got_a, got_b = sa.cpu().numpy(), sb.cpu().numpy()
+    assert got_a[6] == got_b[6] == resets
+    assert np.allclose(got_a, got_b, rtol=1e-12, atol=1e-9)          # float64 atomics: order-dependent in the last bits
+    assert np.array_equal(got_a[[0, 3, 6, 7]], got_b[[0, 3, 6, 7]])   # integer-valued statistics are exact
