@@ -289,6 +289,42 @@ class BatchedGridEnv:
     def step_host_wait(self, ticket):
         _lib.check(self._h, self.lib.ssd_step_host_wait(self._h, int(ticket)))
 
+    # ---- packed host snapshots (dict façade, vector adapter): ONE device -> host copy per call ----------------
+    def host_snapshot(self, index=None, features=False, extras=True, obs=True):
+        """Everything a dict API returns for env `index` (None: every env), gathered into one device byte buffer and
+        copied to the host with ONE transfer + ONE synchronisation.  Returns numpy views:
+        obs uint8 [.., n, 15, 15, 3], rew / base_rew / transfers float64 [.., n], info uint8 [.., n, 4], done uint8 [..],
+        feat float64 [.., n, F] (when `features`)."""
+        sel = slice(None) if index is None else slice(index, index + 1)
+        E = self.E if index is None else 1
+        parts = [("rew", self.rew[sel], np.float64, (E, self.n)), ("info", self.info[sel], np.uint8, (E, self.n, 4)),
+                 ("done", self.done[sel], np.uint8, (E,))]
+        if obs:
+            parts.append(("obs", self.obs[sel], np.uint8, (E, self.n, 15, 15, 3)))
+        if extras:
+            parts += [("base_rew", self.base_rew[sel], np.float64, (E, self.n)), ("transfers", self.transfers[sel], np.float64, (E, self.n))]
+        if features and self.feature_obs is not None:
+            parts.append(("feat", self.feature_obs[sel], np.float64, (E, self.n, self.F)))
+        # float64 fields first: every field starts 8-byte aligned in the packed buffer
+        parts.sort(key=lambda x: -np.dtype(x[2]).itemsize)
+        flat = [t.reshape(-1).view(torch.uint8) if t.dtype != torch.uint8 else t.reshape(-1) for _, t, _, _ in parts]
+        packed = torch.cat(flat)
+        key = int(packed.numel())
+        host = self._snap_host.get(key) if hasattr(self, "_snap_host") else None
+        if host is None:
+            if not hasattr(self, "_snap_host"):
+                self._snap_host = {}
+            host = self._snap_host[key] = torch.empty((key,), dtype=torch.uint8).pin_memory()
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        buf, out, off = host.numpy(), {}, 0
+        for (name, _, dt, shape), f in zip(parts, flat):
+            nb = int(f.numel())
+            a = buf[off:off + nb].view(dt).reshape(shape)
+            out[name] = a[0] if index is not None else a
+            off += nb
+        return out
+
     def random_actions(self, step_index, num_actions, out=None):
         """Uniform random actions; step_index=None uses the handle's device-side counter (CUDA-graph friendly)."""
         if step_index is None:

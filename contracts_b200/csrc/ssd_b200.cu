@@ -366,6 +366,9 @@ static int setup_features(ssd_handle* h)
     const int H = c.map_h, W = c.map_w, n = c.num_agents;
     const bool cleanup = c.env_kind == SSD_ENV_CLEANUP_FEATURES;
     if (H < 1 || W < 1 || H > 255 || W > 255) return fail(h, SSD_EINVAL, "map size %dx%d out of range", H, W);
+    // the closest-point search packs an L1 distance |dr| + |dc| into one key byte per agent (VABSDIFF4, ssd_features.cuh):
+    // it must stay below 255, also against the (127, 127) padding entries
+    if (H + W - 2 > 254) return fail(h, SSD_EUNSUPPORTED, "feature envs: map_h + map_w - 2 = %d exceeds 254 (distance keys are one byte)", H + W - 2);
     if (!c.ascii_map || (int)h->ascii.size() != H * W) return fail(h, SSD_EINVAL, "ascii_map must hold map_h*map_w chars");
     p.E = c.num_envs; p.n = n; p.kind = c.env_kind; p.H = H; p.W = W; p.horizon = c.horizon; p.contract = c.contract_kind;
     p.F = cleanup ? 12 + n : 10 + 2 * n;

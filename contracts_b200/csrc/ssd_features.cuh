@@ -497,6 +497,9 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kerne
         if (p.contract != SSD_CONTRACT_NONE && total != 0.0) red_add(p.metrics + (size_t)2 * p.E + env, total);
         if (n_eaten) red_add(p.metrics + (size_t)3 * p.E + env, (double)n_eaten);
         if (n_close) red_add(p.metrics + (size_t)4 * p.E + env, (double)n_close);
+        // birth stamps are 16 bits (list order = stamp order decides np.argmin ties): an episode with more than 65535
+        // spawns of one kind would wrap them — flag it instead of picking a wrong closest point silently
+        if ((next_apple | next_waste) > 0xFFFFu) p.metrics[(size_t)5 * p.E + env] = 1.0;
         if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
     }
     feat_write_obs(p, mine, env, s_tile + (threadIdx.x >> 5) * 32 * (FEAT_MAXF + 1), io.obs, pos, ca, cw, close5, cleaned,
@@ -509,7 +512,7 @@ __global__ void feat_get_metrics_kernel(const FeatParams p, double* out)
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     double* o = out + (size_t)env * 40;
-    for (int q = 0; q < 8; q++) o[q] = q < 5 ? p.metrics[(size_t)q * p.E + env] : 0.0;
+    for (int q = 0; q < 8; q++) o[q] = q < 6 ? p.metrics[(size_t)q * p.E + env] : 0.0;        // [5]: err_flags
     for (int a = 0; a < SSD_MAXN; a++) {
         const bool v = a < p.n;
         const size_t so = (size_t)a * p.E + env;

@@ -140,11 +140,11 @@ class _GridWorldEnv:
 
     def step(self, acts):
         b = self.batch
-        obs, rew, done, info = b.step(self._actions_tensor(acts), want_features=True)
+        b.step(self._actions_tensor(acts), want_features=True)
         self.timesteps += 1
-        self._last = {"obs": obs[0].cpu().numpy(), "rew": rew[0].cpu().numpy(), "base_rew": b.base_rew[0].cpu().numpy(),
-                      "transfers": b.transfers[0].cpu().numpy(), "info": info[0].cpu().numpy(),
-                      "feat": b.feature_obs[0].cpu().numpy(), "done": bool(done[0].item())}
+        snap = b.host_snapshot(index=0, features=True)             # one packed device -> host copy (was seven)
+        self._last = {k: np.array(v) for k, v in snap.items()}
+        self._last["done"] = bool(snap["done"])
         L = self._last
         infos = {}
         for i, k in enumerate(self.agent_ids):

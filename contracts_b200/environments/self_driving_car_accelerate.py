@@ -69,6 +69,14 @@ class SelfAcceleratingCarEnv:
         if self.agent_dones["__all__"]:
             raise RuntimeError("episode is over: call reset() (the reference raises AttributeError here, :160)")
         b = self.batch
+        # The acting set is the device's (cars that are done stop acting, as under RLlib): the dict must name exactly the
+        # live cars.  The reference would move only the cars that are named and crash on a finished one; a mismatch here is
+        # a caller error and is reported instead of being silently reinterpreted.
+        live = {k for k in self.agent_ids if not self.agent_dones.get(k, False)}
+        if set(acts.keys()) != live:
+            raise ValueError("selfdrive step: actions for %s given, live cars are %s" % (sorted(acts.keys()), sorted(live)))
+        # accelerations are float32 on the device — the reference's action space is a float32 Box, so RLlib hands float32
+        # values over; a float64 action that float32 cannot represent is rounded before the +-0.1 clamp
         a = np.zeros((self.num_envs, self.num_agents), dtype=np.float32)
         for k, v in acts.items():
             a[0, int(k[1:])] = np.float32(np.asarray(v).reshape(-1)[0])

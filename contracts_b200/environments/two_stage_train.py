@@ -160,7 +160,8 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
             dones = {"__all__": True}
             infos = {k: {} for k in self.agent_ids}
             if self.policy is None:
-                if not hasattr(self.base_env, "image_obs"):
+                from .gridworld import _GridWorldEnv
+                if not isinstance(self.base_env, _GridWorldEnv):       # the feature envs also carry `image_obs`
                     raise NotImplementedError("the random-action subgame rollout exists for the grid worlds; pass policy=...")
                 rews, infos = self._random_rollout(rews, infos)
             else:
@@ -194,16 +195,14 @@ class SeparateContractNegotiateStage(SeparateContractEnv):
         b = self.base_env.batch
         na = self.base_env.action_space.n
         total = torch.zeros_like(b.rew)
-        steps = 0
-        done = False
-        while not done and steps < self.horizon:
+        # the reference stops at env_dones['__all__'] (:286-333), i.e. when the base env reaches ITS horizon: the number
+        # of steps is known up front, so the loop needs no device -> host poll of the done flag
+        limit = min(int(self.horizon), max(int(self.base_env.horizon) - int(self.base_env.timesteps), 0))
+        for steps in range(limit):
             a = b.random_actions(steps, na)
             b.step(a, want_features=False)
             total += b.rew
-            steps += 1
             self.base_env.timesteps += 1
-            if steps % 64 == 0 or steps == self.horizon:
-                done = bool(b.done[0].item())
         tot = total[0].cpu().numpy()
         rews = {k: rews[k] + tot[i] for i, k in enumerate(self.agent_ids)}
         self.last_seen_obs = self.base_env._image_obs(b.obs[0].cpu().numpy()) if self.base_env.image_obs else self.last_seen_obs

@@ -1,0 +1,116 @@
+"""A vectorised, RLlib-`BaseEnv`-shaped adapter over a device batch: E environments behind ONE rollout worker.
+
+The reference hands RLlib one Python env per rollout worker (`utils/ray_config_utils.py:140` `num_workers`,
+`run_training.py:68`); RLlib's sampler talks to envs through `BaseEnv.poll()` / `send_actions()` / `try_reset()`
+(ray/rllib/env/base_env.py).  `SSDVectorEnv` exposes E device-resident envs through exactly those three calls, with
+the dict conventions of the reference's wrappers (`{env_id: {agent_id: ...}}`; observations as
+`SeparateContractEnv._with_contract` builds them, two_stage_train.py:104-121; `dones[env_id]['__all__']`), and
+  * ONE host -> device copy per `send_actions` (the action matrix) and ONE device -> host copy per `poll` (a packed
+    snapshot of observations, rewards, dones, infos of all E envs: `BatchedGridEnv.host_snapshot`);
+  * finished envs are reset by `try_reset(env_id)` (RLlib calls it after `dones['__all__']`), batched: the resets
+    requested between two polls run as one masked device reset.
+Arrays are also available without the dict building through `poll_arrays()` — for samplers that batch the policy
+forward themselves the dict layer is pure overhead (INTEGRATION.md §5 has the measured rates).
+"""
+import numpy as np
+import torch
+
+from .batched import BatchedGridEnv
+
+
+class SSDVectorEnv:
+    def __init__(self, kind, num_envs, num_agents, contract=None, horizon=1000, seed=73907, first_env_id=0, device=None,
+                 ascii_map=None, one_hot_id=False, **batch_kwargs):
+        self.batch = BatchedGridEnv(kind, num_envs, num_agents, ascii_map=ascii_map, horizon=horizon, contract=contract,
+                                    seed=seed, first_env_id=first_env_id, device=device, **batch_kwargs)
+        self.num_envs, self.num_agents, self.contract = int(num_envs), int(num_agents), contract
+        self.agent_ids = ["a%d" % i for i in range(self.num_agents)]
+        self.one_hot_id = one_hot_id
+        self._actions_host = torch.full((self.num_envs, self.num_agents), 4, dtype=torch.uint8).pin_memory()
+        self._actions_dev = torch.empty_like(self._actions_host, device=self.batch.device)
+        self._pending_reset = np.zeros(self.num_envs, dtype=np.uint8)
+        self._fresh = None            # envs whose next poll() returns a reset observation (no reward / done yet)
+        self._stepped = False
+        self.batch.reset()
+        self._theta = self.batch.get_state()["theta"].cpu().numpy() if contract else None
+        self._fresh = np.ones(self.num_envs, dtype=bool)
+
+    # ---- BaseEnv ---------------------------------------------------------------------------------------
+    def send_actions(self, action_dict):
+        """{env_id: {agent_id: action}}; agents that are absent stay put (action 4), as in the drop-in classes."""
+        a = self._actions_host.numpy()
+        a[:] = 4
+        for e, acts in action_dict.items():
+            for k, v in acts.items():
+                a[e, int(k[1:])] = int(v)
+        self.send_action_array(self._actions_host)
+
+    def send_action_array(self, actions_host):
+        """uint8 [E, n] pinned host tensor (or numpy array): one host -> device copy, then the step is enqueued."""
+        if not torch.is_tensor(actions_host):
+            self._actions_host.numpy()[:] = actions_host
+            actions_host = self._actions_host
+        self._flush_resets()
+        self._actions_dev.copy_(actions_host, non_blocking=True)
+        self.batch.step(self._actions_dev, extras=False)
+        self._stepped = True
+        self._fresh[:] = False
+
+    def try_reset(self, env_id):
+        """Queue env_id for reset; the observation arrives with the next poll() (RLlib accepts that: ASYNC_RESET_RETURN)."""
+        self._pending_reset[env_id] = 1
+        return None
+
+    def _flush_resets(self):
+        if self._pending_reset.any():
+            mask = torch.from_numpy(self._pending_reset).to(self.batch.device, non_blocking=False)
+            self.batch.reset(mask)
+            if self.contract:
+                self._theta = self.batch.get_state()["theta"].cpu().numpy()
+            self._fresh = self._pending_reset.astype(bool)
+            self._pending_reset[:] = 0
+            self._stepped = False
+
+    def poll_arrays(self):
+        """-> dict of numpy arrays for all E envs from ONE device -> host copy: obs uint8 [E, n, 15, 15, 3], rew float64
+        [E, n], done uint8 [E], info uint8 [E, n, 4] (+ `fresh` bool [E]: the env was just reset, rew / done are void)."""
+        self._flush_resets()
+        snap = self.batch.host_snapshot(index=None, extras=False)
+        snap["fresh"] = self._fresh.copy()
+        if not self._stepped:
+            snap["rew"] = np.zeros_like(snap["rew"]); snap["done"] = np.zeros_like(snap["done"])
+        return snap
+
+    def poll(self):
+        """-> (obs, rewards, dones, infos, off_policy_actions), each {env_id: {agent_id: value}} (BaseEnv.poll)."""
+        s = self.poll_arrays()
+        obs, rews, dones, infos = {}, {}, {}, {}
+        img = s["obs"].astype(np.float64) / 255                    # `curr_obs / 255` (cleanup_new.py:204,258)
+        cleanup = self.batch.kind == "cleanup_new"
+        for e in range(self.num_envs):
+            if not self._stepped and not s["fresh"][e]:            # nothing new for this env since the last poll
+                continue
+            o = {}
+            for i, k in enumerate(self.agent_ids):
+                d = {"image": img[e, i]}
+                if self.one_hot_id:
+                    v = np.zeros(self.num_agents); v[i] = 1; d["features"] = v
+                if self.contract:                                  # SeparateContractEnv._with_contract (two_stage_train.py:104-111)
+                    d["contract"] = np.array([self._theta[e], 0.0])
+                o[k] = d
+            obs[e] = o
+            if s["fresh"][e]:
+                continue
+            rews[e] = {k: np.float64(s["rew"][e, i]) for i, k in enumerate(self.agent_ids)}
+            dn = bool(s["done"][e])
+            dones[e] = {"__all__": dn, "a0": dn, "a1": dn}         # the keys the reference hard-codes (cleanup_new.py:242)
+            infos[e] = {k: ({"eaten_apples": int(s["info"][e, i, 0]), "cleaned_squares": int(s["info"][e, i, 1])} if cleanup else
+                            {"eaten_apples": int(s["info"][e, i, 0]), "eaten_close_apples": int(s["info"][e, i, 1])})
+                        for i, k in enumerate(self.agent_ids)}
+        return obs, rews, dones, infos, {}
+
+    def get_sub_environments(self):
+        return []
+
+    def stop(self):
+        self.batch.close()

@@ -305,7 +305,8 @@ int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream);
  * theta double [E], t int32 [E]; NULL pointers are skipped */
 int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev,
                        int32_t* t_dev, void* stream);
-/* double [E][40]: dirt_cleaned, raw_env_rewards, transfers, total_apples_eaten, low_density_apples_eaten, 0, 0, 0,
+/* double [E][40]: dirt_cleaned, raw_env_rewards, transfers, total_apples_eaten, low_density_apples_eaten,
+ * err_flags (1: more than 65535 spawns of one kind in an episode — the 16-bit birth stamps wrapped), 0, 0,
  * per agent: sum r [8], sum t*r [8], sum transferred r [8], sum t * transferred r [8] */
 int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream);
 
