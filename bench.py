@@ -313,9 +313,8 @@ class Runner:
         self.gen_actions(step_index)
         if self.fam == "grid":       # finished envs restart (and negotiate) inside the step: ssd_step_io.auto_reset
             self.env.step(self.actions, extras=False, auto_reset=True, negotiation=self.neg())
-        else:
-            self.env.step(self.actions, extras=False)
-            self.after_step()
+        else:                        # feature / selfdrive envs: next-step auto-reset inside the step kernel
+            self.env.step(self.actions, extras=False, auto_reset=True)
 
     def burn_in(self):
         """reach the steady state: one horizon with env i (re)started at step i mod horizon"""
@@ -495,12 +494,17 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
     run.policy()
     # (the event pair brackets the step kernels only: the finished envs are reset by a separate call here)
+    grid = cfg["family"] == "grid"
     for k in range(Kk):
         run.gen_actions()
         kev[k][0].record()
-        env.step(run.actions, extras=False)
+        if grid:
+            env.step(run.actions, extras=False)
+        else:
+            env.step(run.actions, extras=False, auto_reset=True)
         kev[k][1].record()
-        run.after_step()
+        if grid:
+            run.after_step()
     barrier()
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     kern_ms = None
@@ -557,10 +561,9 @@ def main():
         def e2e_run(steps):
             for i in range(steps):
                 run.actions.copy_(host_actions[i % 4], non_blocking=True)
-                env.step(run.actions, extras=False)
+                env.step(run.actions, extras=False, auto_reset=True)
                 host_rew.copy_(env.rew, non_blocking=True)
                 host_done.copy_(env.done, non_blocking=True)
-                run.after_step()
                 main_stream.synchronize()
         e2e_note = "Batched*Env.step with pinned host actions in, float64 rewards + dones out, synchronous every step"
     e2e_run(5)

@@ -77,12 +77,12 @@ def make_config(**kw):
 
 class ssd_selfdrive_io(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("actions_dev", "obs_dev", "rew_dev", "base_rew_dev", "transfers_dev",
-                                               "info_dev", "done_dev")]
+                                               "info_dev", "done_dev")] + [("auto_reset", ctypes.c_int32)]
 
 
 class ssd_feat_io(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("actions_dev", "obs_dev", "rew_dev", "base_rew_dev", "transfers_dev",
-                                               "info_dev", "done_dev")]
+                                               "info_dev", "done_dev")] + [("auto_reset", ctypes.c_int32)]
 
 
 EXPORTS = [

@@ -1163,7 +1163,7 @@ int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
     REQUIRE_FEAT(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
-    FeatIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev };
+    FeatIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
     feat_step_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, k);
     return check_launch(h, "feat_step");
 }
@@ -1203,7 +1203,7 @@ int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream)
     REQUIRE_CAR(h);
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 31)) return fail(h, SSD_EINVAL, "info_dev must be 32-byte aligned");
-    CarIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev };
+    CarIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
     car_step_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, k);
     return check_launch(h, "selfdrive_step");
 }

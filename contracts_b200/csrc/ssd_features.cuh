@@ -59,6 +59,7 @@ struct FeatIO {
     double* rew; double* base_rew; double* transfers;   // [E][n]
     uint8_t* info;              // [E][n][4]: cleanup (cleaned_squares,0,0,0); harvest (eaten_apples, eaten_close_apples,0,0)
     uint8_t* done;              // [E]
+    int auto_reset;             // next-step auto-reset (see feat_step_kernel)
 };
 
 struct FeatDraws {              // k-th random.random() of a step: Philox block cached
@@ -255,20 +256,13 @@ __device__ __forceinline__ int feat_popcount_mask(const uint32_t* m, int npts)
     return c;
 }
 
-__global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatParams p, const uint8_t* mask, double* obs)
+// reset of one env by its thread (cleanup_features.py:256-284 / harvest_features.py:289-336 + two_stage_train.py:159-187)
+__device__ __forceinline__ void feat_reset_env(const FeatParams& p, int env, uint32_t* am, uint32_t* wm, uint32_t (&pos)[SSD_MAXN],
+                                               uint32_t (&ca)[SSD_MAXN], uint32_t (&cw)[SSD_MAXN], int (&close5)[SSD_MAXN],
+                                               int& n_cur_apple, int& n_cur_waste)
 {
-    __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
-    __shared__ double s_tile[(FEAT_THREADS / 32) * 32 * (FEAT_MAXF + 1)];
-    const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
     const int n = p.n;
-    const bool mine = env < p.E && (!mask || mask[env]);
-    uint32_t* am = s_am + threadIdx.x; uint32_t* wm = s_wm + threadIdx.x;
-    uint32_t pos[SSD_MAXN], ca[SSD_MAXN], cw[SSD_MAXN];
-    int close5[SSD_MAXN], cleaned[SSD_MAXN];
-    int n_cur_apple = 0, n_cur_waste = 0;
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
-    if (mine) {
+    {
         const uint32_t c3 = p.counters[(size_t)3 * p.E + env];
         const uint32_t episode = (c3 & 0x80000000u) ? (c3 & 0x7fffffffu) + 1u : 0u;
         const uint32_t env_id = p.first_env_id + (uint32_t)env;
@@ -282,21 +276,29 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatPara
         } else {
             for (int i = 0; i < p.n_apple; i++) { mask_set(am, i); p.apple_stamp[(size_t)i * p.E + env] = (uint16_t)next_apple++; n_cur_apple++; }
         }
-        // initialize_players: agent a takes the spawn point with the (a+1)-th smallest (key, index)
+        // initialize_players: agent a takes the spawn point with the (a+1)-th smallest (key, index).  Every key is drawn
+        // once (one Philox block per four points) and inserted into a sorted list of the n smallest.
         {
-            uint32_t prev_key = 0u; int prev_idx = -1;
-            for (int a = 0; a < n; a++) {
-                uint32_t bk = 0xffffffffu; int bj = -1;
-                for (int j = 0; j < p.n_spawn; j++) {
-                    const uint32_t kk = draw_u32(p.seed, env_id, episode, 0u, SITE_FEAT_ORDER, 0u, (uint32_t)j);
-                    const bool after = prev_idx < 0 || kk > prev_key || (kk == prev_key && j > prev_idx);
-                    if (after && (bj < 0 || kk < bk)) { bk = kk; bj = j; }
-                }
-                prev_key = bk; prev_idx = bj;
-                const uint32_t rc = __ldg(p.spawn_rc + bj);
-                const uint32_t o = draw_u32(p.seed, env_id, episode, 0u, SITE_FEAT_ROT, (uint32_t)a, 0u) >> 30;
+            uint32_t bk[SSD_MAXN]; int bj[SSD_MAXN];
 #pragma unroll
-                for (int q = 0; q < SSD_MAXN; q++) if (q == a) pos[q] = (rc >> 8) | ((rc & 255u) << 8) | (o << 16);
+            for (int q = 0; q < SSD_MAXN; q++) { bk[q] = 0xffffffffu; bj[q] = 0x7fffffff; }
+            Philox4 blk = { 0, 0, 0, 0 };
+            for (int j = 0; j < p.n_spawn; j++) {
+                if ((j & 3) == 0) blk = draw_block(p.seed, env_id, episode, 0u, SITE_FEAT_ORDER, 0u, (uint32_t)(j >> 2));
+                uint32_t kk = pick(blk, (uint32_t)j & 3u); int jj = j;
+#pragma unroll
+                for (int q = 0; q < SSD_MAXN; q++) {                 // insertion: (kk, jj) sinks to its place, the rest shift down
+                    const bool less = kk < bk[q] || (kk == bk[q] && jj < bj[q]);
+                    const uint32_t tk = bk[q]; const int tj = bj[q];
+                    if (less) { bk[q] = kk; bj[q] = jj; kk = tk; jj = tj; }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < SSD_MAXN; a++) {
+                if (a >= n) continue;
+                const uint32_t rc = __ldg(p.spawn_rc + bj[a]);
+                const uint32_t o = draw_u32(p.seed, env_id, episode, 0u, SITE_FEAT_ROT, (uint32_t)a, 0u) >> 30;
+                pos[a] = (rc >> 8) | ((rc & 255u) << 8) | (o << 16);
             }
         }
         FeatDraws dr = { p.seed, env_id, episode, 0u, 0xffffffffu, { 0, 0, 0, 0 } };
@@ -328,6 +330,21 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatPara
         p.theta[env] = theta;
         for (int q = 0; q < 8; q++) p.metrics[(size_t)q * p.E + env] = 0.0;
     }
+}
+
+__global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatParams p, const uint8_t* mask, double* obs)
+{
+    __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
+    __shared__ double s_tile[(FEAT_THREADS / 32) * 32 * (FEAT_MAXF + 1)];
+    const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    const bool mine = env < p.E && (!mask || mask[env]);
+    uint32_t* am = s_am + threadIdx.x; uint32_t* wm = s_wm + threadIdx.x;
+    uint32_t pos[SSD_MAXN], ca[SSD_MAXN], cw[SSD_MAXN];
+    int close5[SSD_MAXN], cleaned[SSD_MAXN];
+    int n_cur_apple = 0, n_cur_waste = 0;
+#pragma unroll
+    for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
+    if (mine) feat_reset_env(p, env, am, wm, pos, ca, cw, close5, n_cur_apple, n_cur_waste);
     if (obs) feat_write_obs(p, mine, env, s_tile + (threadIdx.x >> 5) * 32 * (FEAT_MAXF + 1), obs, pos, ca, cw, close5, cleaned,
                             n_cur_apple, n_cur_waste);
 }
@@ -348,7 +365,20 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kerne
     int n_cur_apple = 0, n_cur_waste = 0;
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
-    if (mine) {
+    // next-step auto-reset (ssd_feat_io.auto_reset): an env that reached its horizon in the previous step starts its next
+    // episode in this one — reset observation, zero rewards, done cleared, the actions of this step ignored
+    const bool restart = mine && io.auto_reset && (int)p.counters[(size_t)2 * p.E + env] == p.horizon;
+    if (restart) {
+        feat_reset_env(p, env, am, wm, pos, ca, cw, close5, n_cur_apple, n_cur_waste);
+        for (int a = 0; a < n; a++) {
+            const size_t o = (size_t)env * n + a;
+            io.rew[o] = 0.0;
+            if (io.base_rew) io.base_rew[o] = 0.0;
+            if (io.transfers) io.transfers[o] = 0.0;
+            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = 0u;
+        }
+        if (io.done) io.done[env] = 0;
+    } else if (mine) {
         const uint32_t env_id = p.first_env_id + (uint32_t)env;
         uint32_t next_apple = p.counters[(size_t)0 * p.E + env], next_waste = p.counters[(size_t)1 * p.E + env];
         int t = (int)p.counters[(size_t)2 * p.E + env];

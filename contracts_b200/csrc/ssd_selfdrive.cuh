@@ -38,6 +38,7 @@ struct CarIO {
     double* rew; double* base_rew; double* transfers;   // [E][n]
     double* info;           // [E][n][4]: just_passed, active, ambulance_rank, ambulance_dist_to_front (row of the first acting agent)
     uint8_t* done;          // [E][n+1]
+    int auto_reset;         // next-step auto-reset (see car_step_kernel)
 };
 
 __device__ __forceinline__ double py_min(double x, double y) { return y < x ? y : x; }   // Python min([x, y])
@@ -80,14 +81,12 @@ __device__ __forceinline__ void car_write_obs(const CarParams& p, const double* 
     }
 }
 
-__global__ void __launch_bounds__(CAR_THREADS) car_reset_kernel(const CarParams p, const uint8_t* mask, double* obs)
+// reset of one env by its thread (self_driving_car_accelerate.py:49-79 + two_stage_train.py:159-187); leaves the new
+// positions / velocities in the thread's shared-memory columns for car_write_obs
+__device__ __forceinline__ void car_reset_env(const CarParams& p, int env, double* s_pos, double* s_vel)
 {
-    __shared__ double s_pos[SSD_MAXN * CAR_STRIDE], s_vel[SSD_MAXN * CAR_STRIDE];
-    const int env = blockIdx.x * CAR_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     const int n = p.n;
-    const bool mine = env < p.E && (!mask || mask[env]);
-    if (mine) {
+    {
         const uint32_t meta = p.meta[env];
         const uint32_t episode = (meta & 0x80000000u) ? p.episode[env] + 1u : 0u;
         const uint32_t env_id = p.first_env_id + (uint32_t)env;
@@ -112,6 +111,15 @@ __global__ void __launch_bounds__(CAR_THREADS) car_reset_kernel(const CarParams 
         p.theta[env] = theta; p.m_transfers[env] = 0.0; p.dist_front[env] = -1.0;
         p.crossed[env] = 0u; p.meta[env] = 0x80000000u; p.t[env] = 0; p.episode[env] = episode;
     }
+}
+
+__global__ void __launch_bounds__(CAR_THREADS) car_reset_kernel(const CarParams p, const uint8_t* mask, double* obs)
+{
+    __shared__ double s_pos[SSD_MAXN * CAR_STRIDE], s_vel[SSD_MAXN * CAR_STRIDE];
+    const int env = blockIdx.x * CAR_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool mine = env < p.E && (!mask || mask[env]);
+    if (mine) car_reset_env(p, env, s_pos, s_vel);
     const unsigned valid = __ballot_sync(0xffffffffu, mine);
     __syncwarp();
     if (obs) car_write_obs(p, s_pos, s_vel, obs, env - lane, lane, valid);
@@ -124,7 +132,21 @@ __global__ void __launch_bounds__(CAR_THREADS) car_step_kernel(const CarParams p
     const int lane = threadIdx.x & 31, tx = threadIdx.x;
     const int n = p.n;
     const bool mine = env < p.E;
-    if (mine) {
+    // next-step auto-reset (ssd_selfdrive_io.auto_reset): an env whose episode ended in the previous step starts its next
+    // episode in this one — reset observation, zero rewards, dones cleared, the actions of this step ignored
+    const bool restart = mine && io.auto_reset && ((p.meta[env] >> 16) & 1u);
+    if (restart) {
+        car_reset_env(p, env, s_pos, s_vel);
+        for (int k = 0; k < n; k++) {
+            const size_t o = (size_t)env * n + k;
+            io.rew[o] = 0.0;
+            if (io.base_rew) io.base_rew[o] = 0.0;
+            if (io.transfers) io.transfers[o] = 0.0;
+            if (io.info) reinterpret_cast<double4*>(io.info)[o] = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (io.done) io.done[(size_t)env * (n + 1) + k] = 0;
+        }
+        if (io.done) io.done[(size_t)env * (n + 1) + n] = 0;
+    } else if (mine) {
         uint32_t meta = p.meta[env];
         int n_crossed = (int)(meta & 0xFFu);
         uint32_t done_mask = (meta >> 8) & 0xFFu;

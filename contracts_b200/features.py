@@ -77,7 +77,7 @@ class BatchedFeatureEnv:
         _lib.check(self._h, self.lib.ssd_feat_reset(self._h, _ptr(mask), _ptr(self.obs), self._stream()))
         return self.obs
 
-    def step(self, actions, extras=True):
+    def step(self, actions, extras=True, auto_reset=False):
         """actions: uint8 CUDA tensor [E, n].  Returns (obs [E, n, F], rew, done [E], info [E, n, 4])."""
         if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -87,6 +87,7 @@ class BatchedFeatureEnv:
         io.transfers_dev = self.transfers.data_ptr() if extras else None
         io.info_dev = self.info.data_ptr()
         io.done_dev = self.done.data_ptr()
+        io.auto_reset = 1 if auto_reset else 0       # next-step auto-reset: finished envs restart in the following step
         _lib.check(self._h, self.lib.ssd_feat_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
 

@@ -68,7 +68,7 @@ class BatchedCarEnv:
         _lib.check(self._h, self.lib.ssd_selfdrive_reset(self._h, _ptr(mask), _ptr(self.obs), self._stream()))
         return self.obs
 
-    def step(self, actions, extras=True):
+    def step(self, actions, extras=True, auto_reset=False):
         """actions: float32 CUDA tensor [E, n].  Returns (obs, rew, done [E, n+1], info [E, n, 4])."""
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
@@ -78,6 +78,7 @@ class BatchedCarEnv:
         io.transfers_dev = self.transfers.data_ptr() if extras else None
         io.info_dev = self.info.data_ptr() if extras else None
         io.done_dev = self.done.data_ptr()
+        io.auto_reset = 1 if auto_reset else 0       # next-step auto-reset: finished envs restart in the following step
         _lib.check(self._h, self.lib.ssd_selfdrive_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
 

@@ -276,6 +276,9 @@ typedef struct ssd_selfdrive_io {
     double* info_dev;           /* [E][n][4] nullable: just_passed, acted, ambulance_rank, ambulance_dist_to_front
                                    (last two in the row of the first acting car, like infos[key_lst[0]]) */
     uint8_t* done_dev;          /* [E][n+1] nullable: per-car dones, then '__all__' */
+    int32_t auto_reset;         /* next-step auto-reset: an env whose episode ended ('__all__') in the previous step is reset
+                                   by this step instead of being stepped — reset observation, zero rewards, dones cleared,
+                                   its actions ignored (what ssd_selfdrive_reset with mask = done[:, n] would do, no launch) */
 } ssd_selfdrive_io;
 int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
 int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream);
@@ -298,6 +301,7 @@ typedef struct ssd_feat_io {
     double* transfers_dev;      /* [E][n] nullable */
     uint8_t* info_dev;          /* [E][n][4] nullable: cleanup (cleaned_squares,0,0,0); harvest (eaten_apples, eaten_close_apples,0,0) */
     uint8_t* done_dev;          /* [E] nullable: dones['__all__'] (timesteps == horizon) */
+    int32_t auto_reset;         /* next-step auto-reset, as in ssd_selfdrive_io */
 } ssd_feat_io;
 int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
 int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream);

@@ -194,3 +194,36 @@ def test_cuda_features_rollout_matches_oracle(oracle_lib, kind, n, E, nact):
     so, sc = orc.get_state(), env.get_state()
     for k in ("pos", "ori", "cells", "theta", "t"):
         gu.assert_same(k, sc[k].cpu().numpy(), so[k], "end")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,contract,n", [("cleanup", "CleanupContract", 8), ("harvest", "HarvestFeaturemodLocalContract", 4)])
+def test_feature_env_next_step_auto_reset(kind, contract, n):
+    """ssd_feat_io.auto_reset: an env that reached its horizon is reset by the NEXT step call (reset observation, zero
+    rewards, done cleared, actions ignored) — compared env by env with single-env handles driven by explicit reset()."""
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    E, H, nact = 12, 9, 8 if kind == "cleanup" else 7
+    batch = BatchedFeatureEnv(kind, E, n, horizon=H, contract=contract, seed=17, first_env_id=50)
+    singles = [BatchedFeatureEnv(kind, 1, n, horizon=H, contract=contract, seed=17, first_env_id=50 + e) for e in range(E)]
+    obs = batch.reset().cpu().numpy().copy()
+    for e, s in enumerate(singles):
+        assert np.array_equal(s.reset().cpu().numpy()[0], obs[e])
+    # stagger: env e takes e % 4 extra steps before the comparison starts, so that the resets do not coincide
+    rng = np.random.RandomState(5)
+    done_prev = np.zeros(E, dtype=bool)
+    for t in range(4 * H):
+        acts = rng.randint(0, nact, size=(E, n)).astype(np.uint8)
+        o, r, d, i = batch.step(torch.as_tensor(acts).cuda(), auto_reset=True)
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for e, s in enumerate(singles):
+            if done_prev[e]:
+                so = s.reset().cpu().numpy()[0]
+                assert np.array_equal(o[e], so) and not r[e].any() and d[e] == 0, (t, e)
+            else:
+                so, sr, sd, _ = s.step(torch.as_tensor(acts[e:e + 1]).cuda())
+                assert np.array_equal(o[e].view(np.uint64), so.cpu().numpy()[0].view(np.uint64)), (t, e)
+                assert np.array_equal(r[e].view(np.uint64), sr.cpu().numpy()[0].view(np.uint64)), (t, e)
+                assert d[e] == int(sd[0].item())
+        done_prev = d.astype(bool)
+    assert t > 3 * H

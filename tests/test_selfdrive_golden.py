@@ -158,3 +158,36 @@ def test_cuda_selfdrive_rollout_matches_oracle(oracle_lib, n, E, contract):
     so, sc = orc.get_state(), env.get_state()
     for k in ("pos", "vel", "theta", "transfers", "t"):
         gu.assert_same(k, sc[k].cpu().numpy(), so[k], "end")
+
+
+@pytest.mark.gpu
+def test_selfdrive_next_step_auto_reset():
+    """ssd_selfdrive_io.auto_reset: an env whose episode ended is reset by the NEXT step call — compared env by env with
+    single-env handles driven by explicit reset() (episodes end at different steps in different envs)."""
+    import torch
+    from contracts_b200.selfdrive import BatchedCarEnv
+    E, n = 10, 4
+    batch = BatchedCarEnv(E, n, contract="SelfdriveContractDistprop", seed=9, first_env_id=20)
+    singles = [BatchedCarEnv(1, n, contract="SelfdriveContractDistprop", seed=9, first_env_id=20 + e) for e in range(E)]
+    obs = batch.reset().cpu().numpy().copy()
+    for e, s in enumerate(singles):
+        assert np.array_equal(s.reset().cpu().numpy()[0], obs[e])
+    rng = np.random.RandomState(2)
+    done_prev = np.zeros(E, dtype=bool)
+    resets = 0
+    for t in range(500):
+        acts = (rng.uniform(-0.02, 0.1, size=(E, n))).astype(np.float32)
+        o, r, d, _ = batch.step(torch.as_tensor(acts).cuda(), auto_reset=True)
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for e, s in enumerate(singles):
+            if done_prev[e]:
+                so = s.reset().cpu().numpy()[0]
+                resets += 1
+                assert np.array_equal(o[e], so) and not r[e].any() and not d[e].any(), (t, e)
+            else:
+                so, sr, sd, _ = s.step(torch.as_tensor(acts[e:e + 1]).cuda())
+                assert np.array_equal(o[e].view(np.uint64), so.cpu().numpy()[0].view(np.uint64)), (t, e)
+                assert np.array_equal(r[e].view(np.uint64), sr.cpu().numpy()[0].view(np.uint64)), (t, e)
+                assert np.array_equal(d[e], sd.cpu().numpy()[0])
+        done_prev = d[:, n].astype(bool)
+    assert resets >= E
