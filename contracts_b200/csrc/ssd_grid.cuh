@@ -453,17 +453,18 @@ __device__ __forceinline__ bool cleanup_spawn(const GridParams& p, const SharedT
         if (succ) kstar = k0 + __ffs(succ) - 1;
     }
     if (kstar < 0) return apples;
-    // the (kstar+1)-th smallest (key, index) among the candidates
+    // the (kstar+1)-th smallest (key, index) among the candidates.  Each lane's <= MW candidate keys are read once; a
+    // taken candidate's key becomes +inf.  Ties between equal keys go to the smaller index (a lane's own candidates are
+    // scanned in index order, across lanes the second reduction decides).
+    uint32_t ck[MW];
+#pragma unroll
+    for (int q = 0; q < MW; q++) ck[q] = ((candm[q] >> lane) & 1u) ? keys[lane + 32 * q] : 0xFFFFFFFFu;
     int chosen = -1;
     for (int it = 0; it <= kstar; it++) {
         uint32_t bk = 0xFFFFFFFFu; int bj = 0x7FFFFFFF;
 #pragma unroll
-        for (int q = 0; q < MW; q++) {
-            if ((candm[q] >> lane) & 1u) {
-                int j = lane + 32 * q; uint32_t kk = keys[j];
-                if (kk < bk || (kk == bk && j < bj)) { bk = kk; bj = j; }
-            }
-        }
+        for (int q = 0; q < MW; q++)
+            if (((candm[q] >> lane) & 1u) && ck[q] < bk) { bk = ck[q]; bj = lane + 32 * q; }
         uint32_t kmin = __reduce_min_sync(FULL, bk);
         int jmin = (int)__reduce_min_sync(FULL, (bk == kmin) ? (uint32_t)bj : 0x7FFFFFFFu);
         chosen = jmin;
