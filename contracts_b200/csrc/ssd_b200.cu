@@ -33,6 +33,7 @@ struct ssd_handle {
     int grid_blocks;
     int obs_blocks;          // grid of the observe kernel (persistent: CTAs per SM x SMs, or fewer for small batches)
     int logic_smem;          // dynamic shared memory of the logic kernel (cell table + per-warp mask copies)
+    bool pdl;                // programmatic dependent launch of the observe / reset kernels behind the logic / observe kernels
     cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
@@ -323,6 +324,7 @@ static int setup_grid(ssd_handle* h)
                                      OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks, h->logic_smem);
     if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
     if ((rc = dev_zalloc(h, 2, &p.obs_ctr))) return rc;
+    h->pdl = !(getenv("SSD_NO_PDL") && atoi(getenv("SSD_NO_PDL")) != 0);
     {   // observe kernel schedule: ~5/8 of every warp's envs static, the tail dynamic (SSD_OBS_STATIC_PCT overrides, 100 = all static)
         const int per_warp = p.E / (h->obs_blocks * OBS_WARPS);
         int pct = 62;
@@ -577,6 +579,19 @@ __global__ void random_actions_kernel(GridParams p, uint32_t step_index, uint32_
     if (counter) counter_finish(counter, step_index);
 }
 
+// launch `kernel` behind the previous kernel of the stream with programmatic dependent launch (see pdl_wait in ssd_grid.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // =============================================================================================
 extern "C" {
 
@@ -768,14 +783,20 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (h->timing) cudaEventRecord(h->tev[1], s);
     if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
     if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
-    obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
+    // programmatic dependent launch: the observe CTAs become resident (tables, tiles) as the one-wave logic grid drains
+    if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr), dim3(h->obs_blocks), dim3(OBS_WARPS * 32),
+                                       (size_t)p.g2_smem_bytes, s, p, k, h->d_res));
+    else obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
     if (p.kind == SSD_ENV_HARVEST) {
         h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
     }
     if (k.auto_reset) {          // the envs that finished restart (and negotiate) behind the step: one masked launch
         h->launches++;
-        if (p.kind == SSD_ENV_CLEANUP) grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
+        if (p.kind == SSD_ENV_CLEANUP && h->pdl)
+            CUDA_TRY(h, launch_pdl(grid_reset_kernel<SSD_ENV_CLEANUP>, dim3(h->grid_blocks), dim3(GRID_THREADS), (size_t)p.g2_smem_bytes, s,
+                                   p, (const uint8_t*)k.done, k.obs, k.obs_stride, k));
+        else if (p.kind == SSD_ENV_CLEANUP) grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
         else grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
     }
     if (h->timing) cudaEventRecord(h->tev[2], s);

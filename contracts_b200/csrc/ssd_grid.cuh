@@ -236,6 +236,14 @@ __device__ __forceinline__ void bulk_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may become resident
+// while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and its writes are
+// visible, so everything before it (table loads, tile set-up) overlaps the predecessor's tail.  pdl_launch_dependents() in
+// the predecessor lets the dependent grid be scheduled as soon as every predecessor CTA has issued it (or exited).
+// Both are no-ops for a kernel that was launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // One out-of-line copy of the 10 Philox rounds for the step kernel (the inlined form is ~80
 // instructions per call site; the hot loop has to fit the instruction cache).
 __device__ __noinline__ uint4 draw_block_ool(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t,
@@ -908,6 +916,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_reset_kernel(const GridPara
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env0 = blockIdx.x * GRID_WARPS + warp, estride = gridDim.x * GRID_WARPS;
+    pdl_wait();                                       // the mask (dones) and the records come from the step's kernels
     // nothing to do for this CTA (steady state: most of them)?  Leave before the table / tile set-up.
     {
         bool any = false;

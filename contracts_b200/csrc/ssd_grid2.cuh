@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
 {
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     extern __shared__ __align__(16) uint8_t dsm[];
+    pdl_launch_dependents();                                      // the observe kernel's CTAs may take the SM slots this grid frees
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = p.n, H = p.H, W = p.W, Wp = p.Wp, mw = p.mw;
     const int ci_bytes = (H * Wp * 2 + 15) & ~15;
@@ -661,6 +662,8 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, cons
         it++;
         return e;
     };
+    pdl_launch_dependents();                                   // the masked reset behind the step (auto_reset) may set up early
+    pdl_wait();                                                // the hot lines are the logic kernel's output
     int env = next_env(), env_n = next_env();
     uint32_t hw_next = 0;
     if (env < p.E) hw_next = reinterpret_cast<const uint32_t*>(p.state + (size_t)env * p.rec_stride)[lane];
