@@ -34,6 +34,8 @@ struct ssd_handle {
     int obs_blocks;          // grid of the observe kernel (persistent: CTAs per SM x SMs, or fewer for small batches)
     int logic_smem;          // dynamic shared memory of the logic kernel (cell table + per-warp mask copies)
     bool pdl;                // programmatic dependent launch of the observe / reset kernels behind the logic / observe kernels
+    int obs_lay;             // observe kernel specialisation the handle qualifies for (obs_layout_id)
+    int logic_lay;           // logic kernel specialisation (logic_layout_id)
     cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
@@ -61,12 +63,39 @@ typedef void (*obs_kernel_t)(const GridParams, const StepIO, uint32_t*);
 template <int KIND>
 static obs_kernel_t obs_pick(bool rounds4, bool feat)
 {
-    if (rounds4) return feat ? grid_obs_kernel<KIND, 4, true> : grid_obs_kernel<KIND, 4, false>;
-    return feat ? grid_obs_kernel<KIND, MAX_POINT_ROUNDS, true> : grid_obs_kernel<KIND, MAX_POINT_ROUNDS, false>;
+    if (rounds4) return feat ? grid_obs_kernel<KIND, 4, true, 0> : grid_obs_kernel<KIND, 4, false, 0>;
+    return feat ? grid_obs_kernel<KIND, MAX_POINT_ROUNDS, true, 0> : grid_obs_kernel<KIND, MAX_POINT_ROUNDS, false, 0>;
 }
-static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat)
+// lay: 0, or 1 when the handle matches OBS_LAY_CLEANUP8 (stock cleanup map, 8 agents, dense observation tensor, no feature_obs)
+static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat, int lay = 0)
 {
+    if (lay == 1 && kind == SSD_ENV_CLEANUP && rounds4 && !feat) return grid_obs_kernel<SSD_ENV_CLEANUP, 4, false, 1>;
     return kind == SSD_ENV_CLEANUP ? obs_pick<SSD_ENV_CLEANUP>(rounds4, feat) : obs_pick<SSD_ENV_HARVEST>(rounds4, feat);
+}
+typedef void (*logic_kernel_t)(const GridParams, const StepIO, uint32_t*);
+static logic_kernel_t logic_kernel_fn(int kind, int lay)
+{
+    if (kind == SSD_ENV_CLEANUP) return lay == 1 ? grid_logic_kernel<SSD_ENV_CLEANUP, 1> : grid_logic_kernel<SSD_ENV_CLEANUP, 0>;
+    return grid_logic_kernel<SSD_ENV_HARVEST, 0>;
+}
+static int logic_layout_id(const GridParams& p)
+{
+    bool ok = p.kind == SSD_ENV_CLEANUP;
+#define LOGIC_CHECK(field, value) ok = ok && p.field == (value);
+    LOGIC_LAY_CLEANUP8(LOGIC_CHECK)
+#undef LOGIC_CHECK
+    if (const char* e = getenv("SSD_LOGIC_GENERIC")) if (atoi(e)) ok = false;
+    return ok ? 1 : 0;
+}
+// does the handle have the layout the specialised observe kernel assumes?
+static int obs_layout_id(const GridParams& p)
+{
+    bool ok = p.kind == SSD_ENV_CLEANUP && p.s_magic == 119304648u;
+#define OBS_CHECK(field, value) ok = ok && p.field == (value);
+    OBS_LAY_CLEANUP8(OBS_CHECK)
+#undef OBS_CHECK
+    if (const char* e = getenv("SSD_OBS_GENERIC")) if (atoi(e)) ok = false;
+    return ok ? 1 : 0;
 }
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
@@ -309,17 +338,21 @@ static int setup_grid(ssd_handle* h)
 
     // observe kernel: persistent grid at the achievable occupancy; logic kernel: cell table + per-warp mask copies
     int per_sm2 = 0;
+    h->obs_lay = obs_layout_id(p);
     for (int feat = 0; feat < 2; feat++)
         CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, feat != 0),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
+    if (h->obs_lay) CUDA_TRY(h, cudaFuncSetAttribute((const void*)obs_kernel_fn(c.env_kind, h->rounds4, false, h->obs_lay),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2_smem_bytes));
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void*)obs_kernel_fn(c.env_kind, h->rounds4, false),
                                                               OBS_WARPS * 32, p.g2_smem_bytes));
     if (per_sm2 < 1) return fail(h, SSD_EUNSUPPORTED, "observe kernel does not fit on an SM (smem %d B)", p.g2_smem_bytes);
     const int want_obs = (p.E + OBS_WARPS - 1) / OBS_WARPS;
     h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
     h->logic_smem = round_up(H * p.Wp * 2, 16) + LOGIC_WARPS * 2 * p.mw * 32 * 4;
-    const void* logic_k = cleanup ? (const void*)grid_logic_kernel<SSD_ENV_CLEANUP> : (const void*)grid_logic_kernel<SSD_ENV_HARVEST>;
-    CUDA_TRY(h, cudaFuncSetAttribute(logic_k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
+    h->logic_lay = logic_layout_id(p);
+    for (int lay = 0; lay <= h->logic_lay; lay++)
+        CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, lay), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
     if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d; logic smem %d B\n",
                                      OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks, h->logic_smem);
     if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
@@ -777,16 +810,16 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
     if (h->timing) cudaEventRecord(h->tev[0], s);
-    if (p.kind == SSD_ENV_CLEANUP) grid_logic_kernel<SSD_ENV_CLEANUP><<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
-    else grid_logic_kernel<SSD_ENV_HARVEST><<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
+    logic_kernel_fn(p.kind, h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
     h->launches++;
     if (h->timing) cudaEventRecord(h->tev[1], s);
     if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
     if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
     // programmatic dependent launch: the observe CTAs become resident (tables, tiles) as the one-wave logic grid drains
-    if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr), dim3(h->obs_blocks), dim3(OBS_WARPS * 32),
-                                       (size_t)p.g2_smem_bytes, s, p, k, h->d_res));
-    else obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr)<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
+    const int lay = (h->obs_lay == 1 && k.obs_stride == 5400 && !k.feat) ? 1 : 0;
+    const obs_kernel_t obs_k = obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, lay);
+    if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(obs_k, dim3(h->obs_blocks), dim3(OBS_WARPS * 32), (size_t)p.g2_smem_bytes, s, p, k, h->d_res));
+    else obs_k<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
     if (p.kind == SSD_ENV_HARVEST) {
         h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;

@@ -307,9 +307,21 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 // arrays for the places that index them dynamically (mask bits by point index, the warp-cooperative contested-move
 // resolution, the beam walk).
 // dynamic shared memory: [cell_info u16 H*Wp, padded to 16 B][per warp: apple mask [mw][32], waste mask [mw][32]]
-template <int KIND>
-__global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
+// LAY == 1: the handle is the stock cleanup map with 8 agents, CleanupContract, plain rewards (logic_layout_id in ssd_b200.cu):
+// the fields below become compile-time constants (the per-agent `a < n` tests fold away, strides become immediates).
+#define LOGIC_LAY_CLEANUP8(F) F(n, 8) F(H, 25) F(W, 18) F(Wp, 20) F(mw, 4) F(rec_stride, 512) F(map_bytes, 512) F(reward_mode, 0) \
+    F(contract, SSD_CONTRACT_CLEANUP)
+template <int KIND, int LAY>
+__global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_kernel(const GridParams p_in, const StepIO io, uint32_t* __restrict__ res_g)
 {
+    GridParams p_pin;
+    if (LAY == 1) {
+        p_pin = p_in;
+#define LOGIC_PIN(field, value) p_pin.field = (value);
+        LOGIC_LAY_CLEANUP8(LOGIC_PIN)
+#undef LOGIC_PIN
+    }
+    const GridParams& p = LAY == 1 ? p_pin : p_in;
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     extern __shared__ __align__(16) uint8_t dsm[];
     pdl_launch_dependents();                                      // the observe kernel's CTAs may take the SM slots this grid frees
@@ -625,9 +637,26 @@ __device__ __forceinline__ void gather_obs2(const GridParams& p, int lane, const
 // OBSERVE: one warp per env.  Spawn + observation windows.  Per warp: [T | T2 | stage (obs staging, aliased
 // by the spawn scratch) | misc].  Lane l prefetches word l of the NEXT env's hot line (one coalesced 128-byte load) while
 // the current env is processed: words 0-7 agents, 8 t, 9 episode, 12 flags, 13 #waste, 16.. apple mask, 24.. waste mask.
-template <int KIND, int MW, bool FEAT>
-__global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p, const StepIO io, uint32_t* __restrict__ res_g)
+// LAY: 0 = every layout value is read from the kernel parameters; 1 = the handle was checked (obs_layout_id in ssd_b200.cu) to be
+// the stock cleanup map with 8 agents, and the layout values below are compile-time constants for the optimiser (row
+// strides become shifts / immediates, the per-agent loops lose their bounds): same code, fewer instructions and registers.
+#define OBS_LAY_CLEANUP8(F) F(S, 36) F(S2, 44) F(tile2_off, 1408) F(g2_stage, 2912) F(g2_misc, 8336) F(g2_warp_bytes, 8464) \
+    F(sm_thr, 64) F(sm_won, 544) F(sm_apple_rc, 672) F(sm_waste_rc, 880) F(sm_warp0, 1120) F(n, 8) F(obs_items, 30) \
+    F(n_apple, 103) F(n_waste, 119) F(rec_stride, 512) F(H, 25) F(W, 18) F(Wp, 20)
+template <int KIND, int MW, bool FEAT, int LAY>
+__global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p_in, const StepIO io_in, uint32_t* __restrict__ res_g)
 {
+    GridParams p_pin; StepIO io_pin;                  // LAY == 1: a copy (scalar-replaced by the compiler) with the layout fields pinned
+    if (LAY == 1) {
+        p_pin = p_in; io_pin = io_in;
+#define OBS_PIN(field, value) p_pin.field = (value);
+        OBS_LAY_CLEANUP8(OBS_PIN)
+#undef OBS_PIN
+        p_pin.s_magic = 119304648u;
+        io_pin.obs_stride = 5400;
+    }
+    const GridParams& p = LAY == 1 ? p_pin : p_in;
+    const StepIO& io = LAY == 1 ? io_pin : io_in;
     extern __shared__ __align__(16) uint8_t smem[];
     const SharedTables tb = load_shared_tables(p, smem, FEAT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
