@@ -70,32 +70,39 @@ static obs_kernel_t obs_pick(bool rounds4, bool feat)
 static obs_kernel_t obs_kernel_fn(int kind, bool rounds4, bool feat, int lay = 0)
 {
     if (lay == 1 && kind == SSD_ENV_CLEANUP && rounds4 && !feat) return grid_obs_kernel<SSD_ENV_CLEANUP, 4, false, 1>;
+    if (lay == 2 && kind == SSD_ENV_HARVEST && !rounds4 && !feat) return grid_obs_kernel<SSD_ENV_HARVEST, MAX_POINT_ROUNDS, false, 2>;
     return kind == SSD_ENV_CLEANUP ? obs_pick<SSD_ENV_CLEANUP>(rounds4, feat) : obs_pick<SSD_ENV_HARVEST>(rounds4, feat);
 }
 typedef void (*logic_kernel_t)(const GridParams, const StepIO, uint32_t*);
 static logic_kernel_t logic_kernel_fn(int kind, int lay)
 {
     if (kind == SSD_ENV_CLEANUP) return lay == 1 ? grid_logic_kernel<SSD_ENV_CLEANUP, 1> : grid_logic_kernel<SSD_ENV_CLEANUP, 0>;
-    return grid_logic_kernel<SSD_ENV_HARVEST, 0>;
+    return lay == 2 ? grid_logic_kernel<SSD_ENV_HARVEST, 2> : grid_logic_kernel<SSD_ENV_HARVEST, 0>;
 }
 static int logic_layout_id(const GridParams& p)
 {
-    bool ok = p.kind == SSD_ENV_CLEANUP;
+    if (const char* e = getenv("SSD_LOGIC_GENERIC")) if (atoi(e)) return 0;
+    bool ok = p.kind == SSD_ENV_CLEANUP, ok2 = p.kind == SSD_ENV_HARVEST;
 #define LOGIC_CHECK(field, value) ok = ok && p.field == (value);
     LOGIC_LAY_CLEANUP8(LOGIC_CHECK)
 #undef LOGIC_CHECK
-    if (const char* e = getenv("SSD_LOGIC_GENERIC")) if (atoi(e)) ok = false;
-    return ok ? 1 : 0;
+#define LOGIC_CHECK(field, value) ok2 = ok2 && p.field == (value);
+    LOGIC_LAY_HARVEST4(LOGIC_CHECK)
+#undef LOGIC_CHECK
+    return ok ? 1 : (ok2 ? 2 : 0);
 }
 // does the handle have the layout the specialised observe kernel assumes?
 static int obs_layout_id(const GridParams& p)
 {
-    bool ok = p.kind == SSD_ENV_CLEANUP && p.s_magic == 119304648u;
+    if (const char* e = getenv("SSD_OBS_GENERIC")) if (atoi(e)) return 0;
+    bool ok = p.kind == SSD_ENV_CLEANUP && p.s_magic == 119304648u, ok2 = p.kind == SSD_ENV_HARVEST && p.s_magic == 76695845u;
 #define OBS_CHECK(field, value) ok = ok && p.field == (value);
     OBS_LAY_CLEANUP8(OBS_CHECK)
 #undef OBS_CHECK
-    if (const char* e = getenv("SSD_OBS_GENERIC")) if (atoi(e)) ok = false;
-    return ok ? 1 : 0;
+#define OBS_CHECK(field, value) ok2 = ok2 && p.field == (value);
+    OBS_LAY_HARVEST4(OBS_CHECK)
+#undef OBS_CHECK
+    return ok ? 1 : (ok2 ? 2 : 0);
 }
 
 static int fail(ssd_handle* h, int code, const char* fmt, ...)
@@ -351,8 +358,9 @@ static int setup_grid(ssd_handle* h)
     h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
     h->logic_smem = round_up(H * p.Wp * 2, 16) + LOGIC_WARPS * 2 * p.mw * 32 * 4;
     h->logic_lay = logic_layout_id(p);
-    for (int lay = 0; lay <= h->logic_lay; lay++)
-        CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, lay), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
+    CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
+    if (h->logic_lay)
+        CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, h->logic_lay), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
     if (getenv("SSD_DEBUG")) fprintf(stderr, "[ssd] observe kernel: %d warps/CTA, %d CTAs/SM, %d B smem/CTA, grid %d; logic smem %d B\n",
                                      OBS_WARPS, per_sm2, p.g2_smem_bytes, h->obs_blocks, h->logic_smem);
     if ((rc = dev_zalloc(h, (size_t)p.E * SSD_MAXN, &h->d_res))) return rc;
@@ -810,13 +818,13 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
     if (h->timing) cudaEventRecord(h->tev[0], s);
-    logic_kernel_fn(p.kind, h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
+    logic_kernel_fn(p.kind, p.beam ? 0 : h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
     h->launches++;
     if (h->timing) cudaEventRecord(h->tev[1], s);
     if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
     if (p.kind == SSD_ENV_CLEANUP) { int rc = copy_rewards(h, k, s, hc); if (rc) return rc; }
     // programmatic dependent launch: the observe CTAs become resident (tables, tiles) as the one-wave logic grid drains
-    const int lay = (h->obs_lay == 1 && k.obs_stride == 5400 && !k.feat) ? 1 : 0;
+    const int lay = (h->obs_lay != 0 && k.obs_stride == (long long)p.n * SSD_OBS_BYTES && !k.feat) ? h->obs_lay : 0;
     const obs_kernel_t obs_k = obs_kernel_fn(p.kind, h->rounds4, k.feat != nullptr, lay);
     if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(obs_k, dim3(h->obs_blocks), dim3(OBS_WARPS * 32), (size_t)p.g2_smem_bytes, s, p, k, h->d_res));
     else obs_k<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);

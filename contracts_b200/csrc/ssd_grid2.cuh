@@ -311,6 +311,8 @@ __device__ __forceinline__ void env_rewards(const GridParams& p, const StepIO& i
 // the fields below become compile-time constants (the per-agent `a < n` tests fold away, strides become immediates).
 #define LOGIC_LAY_CLEANUP8(F) F(n, 8) F(H, 25) F(W, 18) F(Wp, 20) F(mw, 4) F(rec_stride, 512) F(map_bytes, 512) F(reward_mode, 0) \
     F(contract, SSD_CONTRACT_CLEANUP)
+#define LOGIC_LAY_HARVEST4(F) F(n, 4) F(H, 16) F(W, 38) F(Wp, 40) F(mw, 8) F(rec_stride, 512) F(map_bytes, 640) F(reward_mode, 0) \
+    F(contract, SSD_CONTRACT_HARVEST_LOCAL)
 template <int KIND, int LAY>
 __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_kernel(const GridParams p_in, const StepIO io, uint32_t* __restrict__ res_g)
 {
@@ -320,8 +322,16 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
 #define LOGIC_PIN(field, value) p_pin.field = (value);
         LOGIC_LAY_CLEANUP8(LOGIC_PIN)
 #undef LOGIC_PIN
+        p_pin.beam = nullptr;                                     // the specialised variants are not launched while beams are recorded
     }
-    const GridParams& p = LAY == 1 ? p_pin : p_in;
+    if (LAY == 2) {
+        p_pin = p_in;
+#define LOGIC_PIN(field, value) p_pin.field = (value);
+        LOGIC_LAY_HARVEST4(LOGIC_PIN)
+#undef LOGIC_PIN
+        p_pin.beam = nullptr;
+    }
+    const GridParams& p = LAY != 0 ? p_pin : p_in;
     __shared__ uint32_t s_arr[LOGIC_WARPS][4][SSD_MAXN * 32];     // per warp: agents, results, move targets, beam keys
     extern __shared__ __align__(16) uint8_t dsm[];
     pdl_launch_dependents();                                      // the observe kernel's CTAs may take the SM slots this grid frees
@@ -643,6 +653,10 @@ __device__ __forceinline__ void gather_obs2(const GridParams& p, int lane, const
 #define OBS_LAY_CLEANUP8(F) F(S, 36) F(S2, 44) F(tile2_off, 1408) F(g2_stage, 2912) F(g2_misc, 8336) F(g2_warp_bytes, 8464) \
     F(sm_thr, 64) F(sm_won, 544) F(sm_apple_rc, 672) F(sm_waste_rc, 880) F(sm_warp0, 1120) F(n, 8) F(obs_items, 30) \
     F(n_apple, 103) F(n_waste, 119) F(rec_stride, 512) F(H, 25) F(W, 18) F(Wp, 20)
+// LAY == 2: the stock harvest map with 4 agents (BASELINE configs[1])
+#define OBS_LAY_HARVEST4(F) F(S, 56) F(S2, 32) F(tile2_off, 1696) F(g2_stage, 3440) F(g2_misc, 6512) F(g2_warp_bytes, 6640) \
+    F(sm_thr, 64) F(sm_won, 80) F(sm_apple_rc, 96) F(sm_waste_rc, 416) F(sm_warp0, 416) F(n, 4) F(obs_items, 15) \
+    F(n_apple, 155) F(n_waste, 0) F(rec_stride, 512) F(H, 16) F(W, 38) F(Wp, 40)
 template <int KIND, int MW, bool FEAT, int LAY>
 __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p_in, const StepIO io_in, uint32_t* __restrict__ res_g)
 {
@@ -655,8 +669,16 @@ __global__ void __maxnreg__(OBS_MAXREG) grid_obs_kernel(const GridParams p_in, c
         p_pin.s_magic = 119304648u;
         io_pin.obs_stride = 5400;
     }
-    const GridParams& p = LAY == 1 ? p_pin : p_in;
-    const StepIO& io = LAY == 1 ? io_pin : io_in;
+    if (LAY == 2) {
+        p_pin = p_in; io_pin = io_in;
+#define OBS_PIN(field, value) p_pin.field = (value);
+        OBS_LAY_HARVEST4(OBS_PIN)
+#undef OBS_PIN
+        p_pin.s_magic = 76695845u;
+        io_pin.obs_stride = 2700;
+    }
+    const GridParams& p = LAY != 0 ? p_pin : p_in;
+    const StepIO& io = LAY != 0 ? io_pin : io_in;
     extern __shared__ __align__(16) uint8_t smem[];
     const SharedTables tb = load_shared_tables(p, smem, FEAT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
