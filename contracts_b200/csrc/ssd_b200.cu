@@ -602,6 +602,7 @@ __global__ void negotiate_kernel(SolverParams p, const uint8_t* mask, const doub
 // counter_finish in ssd_common.cuh), so that a captured CUDA graph draws fresh actions at every replay
 __global__ void random_actions_kernel(GridParams p, uint32_t step_index, uint32_t* counter, int num_actions, uint8_t* actions)
 {
+    pdl_launch_dependents();                          // a step launched behind this kernel may load its tables meanwhile
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (counter) step_index = *reinterpret_cast<volatile uint32_t*>(counter);
     if (env < p.E) {
@@ -818,7 +819,9 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
     if (h->timing) cudaEventRecord(h->tev[0], s);
-    logic_kernel_fn(p.kind, p.beam ? 0 : h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
+    if (h->pdl && !h->timing && !p.beam)
+        CUDA_TRY(h, launch_pdl(logic_kernel_fn(p.kind, h->logic_lay), dim3(lb), dim3(LOGIC_THREADS), (size_t)h->logic_smem, s, p, k, h->d_res));
+    else logic_kernel_fn(p.kind, p.beam ? 0 : h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
     h->launches++;
     if (h->timing) cudaEventRecord(h->tev[1], s);
     if (hc && hc->slot >= 0) CUDA_TRY(h, cudaEventRecord(h->slot[hc->slot].ev_logic, s));   // the slot's actions were read
@@ -829,13 +832,20 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(obs_k, dim3(h->obs_blocks), dim3(OBS_WARPS * 32), (size_t)p.g2_smem_bytes, s, p, k, h->d_res));
     else obs_k<<<h->obs_blocks, OBS_WARPS * 32, p.g2_smem_bytes, s>>>(p, k, h->d_res);
     if (p.kind == SSD_ENV_HARVEST) {
-        h->launches++; grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
+        h->launches++;
+        if (h->pdl && !h->timing) CUDA_TRY(h, launch_pdl(grid_reward_kernel, dim3(lb), dim3(LOGIC_THREADS), (size_t)0, s, p, k, (const uint32_t*)h->d_res));
+        else grid_reward_kernel<<<lb, LOGIC_THREADS, 0, s>>>(p, k, h->d_res);
         int rc = copy_rewards(h, k, s, hc); if (rc) return rc;
     }
     if (k.auto_reset) {          // the envs that finished restart (and negotiate) behind the step: one masked launch
         h->launches++;
-        if (p.kind == SSD_ENV_CLEANUP && h->pdl)
+        // (the copy_rewards event record of the host paths sits between the harvest reward kernel and this launch: plain launch then)
+        const bool pdl_ok = h->pdl && !h->timing && (p.kind == SSD_ENV_CLEANUP || !hc);
+        if (p.kind == SSD_ENV_CLEANUP && pdl_ok)
             CUDA_TRY(h, launch_pdl(grid_reset_kernel<SSD_ENV_CLEANUP>, dim3(h->grid_blocks), dim3(GRID_THREADS), (size_t)p.g2_smem_bytes, s,
+                                   p, (const uint8_t*)k.done, k.obs, k.obs_stride, k));
+        else if (pdl_ok)
+            CUDA_TRY(h, launch_pdl(grid_reset_kernel<SSD_ENV_HARVEST>, dim3(h->grid_blocks), dim3(GRID_THREADS), (size_t)p.g2_smem_bytes, s,
                                    p, (const uint8_t*)k.done, k.obs, k.obs_stride, k));
         else if (p.kind == SSD_ENV_CLEANUP) grid_reset_kernel<SSD_ENV_CLEANUP><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);
         else grid_reset_kernel<SSD_ENV_HARVEST><<<h->grid_blocks, GRID_THREADS, p.g2_smem_bytes, s>>>(p, k.done, k.obs, k.obs_stride, k);

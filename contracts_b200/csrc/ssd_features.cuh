@@ -187,60 +187,80 @@ __device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32
             ac[a >> 2] = (ac[a >> 2] & ~(0xFFu << sh)) | (((pos[a] >> 8) & 255u) << sh);
         }
     }
+    // Software-pipelined over the live points: the position word and the birth stamp of the NEXT point are requested before
+    // the current one is evaluated, so the kernel's longest-latency loads (20 % of its stall samples when they sat in the
+    // chain) overlap the key updates.
     const int nw = (npts + 31) >> 5;
-    for (int w = 0; w < nw; w++) {
-        uint32_t m = mask[w * FEAT_THREADS];
-        while (m) {
+    int w = 0;
+    uint32_t m = nw > 0 ? mask[0] : 0u;
+    int i_nx = -1; uint32_t prc_nx = 0, st_nx = 0;
+    auto fetch_next = [&]() {
+        while (m == 0u && ++w < nw) m = mask[w * FEAT_THREADS];
+        if (m) {
             const int b = __ffs(m) - 1; m &= m - 1;
-            const int i = w * 32 + b;
-            const uint32_t prc = __ldg(rc + i);
-            const uint32_t base = ((uint32_t)stamp[(size_t)i * E + env] << 8) | (uint32_t)i;
-            const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
-            const uint32_t d[2] = { __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]), __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]) };
+            i_nx = w * 32 + b;
+            prc_nx = __ldg(rc + i_nx);
+            st_nx = stamp[(size_t)i_nx * E + env];
+        } else i_nx = -1;
+    };
+    fetch_next();
+    while (i_nx >= 0) {
+        const int i = i_nx; const uint32_t prc = prc_nx;
+        const uint32_t base = (st_nx << 8) | (uint32_t)i;
+        fetch_next();
+        const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
+        const uint32_t d[2] = { __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]), __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]) };
 #pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) {
-                if (a >= n) continue;
-                const uint32_t key = __byte_perm(d[a >> 2], 0u, 0x0444u | ((uint32_t)(a & 3) << 12)) | base;   // distance -> byte 3
-                best[a] = min(best[a], key);
-            }
+        for (int a = 0; a < SSD_MAXN; a++) {
+            if (a >= n) continue;
+            const uint32_t key = __byte_perm(d[a >> 2], 0u, 0x0444u | ((uint32_t)(a & 3) << 12)) | base;   // distance -> byte 3
+            best[a] = min(best[a], key);
         }
     }
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) out_rc[a] = (a < n && best[a] != 0xFFFFFFFFu) ? (uint32_t)__ldg(rc + (best[a] & 255u)) : 0u;   // sentinel [0, 0]
 }
 
-// feature rows of all agents -> global memory through the warp-private tile
-__device__ __forceinline__ void feat_write_obs(const FeatParams& p, bool mine, int env, double* tile /* [32][F+1] of this warp */,
-                                               double* obs, const uint32_t* pos, const uint32_t* ca, const uint32_t* cw,
-                                               const int* close5, const int* cleaned, int n_cur_apple, int n_cur_waste)
+// feature rows of all agents -> global memory.  Every thread stores its env's n rows itself (F float64 each, 16-byte
+// stores): a row is one contiguous 160 / 208-byte run, an env's n rows are contiguous, and the L2 merges the sectors a warp's
+// stores touch.  (Round 1 transposed the rows through a warp-private shared tile so that every store instruction wrote one
+// contiguous row: 32 x n predicated store iterations per warp — 16 % of the kernel's instructions.)
+__device__ __forceinline__ void feat_write_obs(const FeatParams& p, bool mine, int env, double* obs, const uint32_t* pos,
+                                               const uint32_t* ca, const uint32_t* cw, const int* close5, const int* cleaned,
+                                               int n_cur_apple, int n_cur_waste)
 {
-    const int n = p.n, F = p.F, lane = threadIdx.x & 31;
-    const unsigned valid = __ballot_sync(0xffffffffu, mine);
+    if (!mine) return;
+    const int n = p.n, F = p.F;
     const int cp0 = n > 1 ? 1 : 0;
+    const bool cleanup = p.kind == SSD_ENV_CLEANUP_FEATURES;
+    const bool even = (F & 1) == 0;                                   // rows are 16-byte aligned iff F is even
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) {
         if (a >= n) continue;
-        if (mine) {
-            double* o = tile + lane * (F + 1);
-            const uint32_t me = pos[a], other = pos[a == 0 ? cp0 : 0];      // compute_closest_pos quirk
-            o[0] = (double)(me & 255u); o[1] = (double)((me >> 8) & 255u); o[2] = (double)((me >> 16) & 3u);
-            o[3] = (double)(other & 255u); o[4] = (double)((other >> 8) & 255u); o[5] = (double)((other >> 16) & 3u);
-            o[6] = (double)(ca[a] >> 8); o[7] = (double)(ca[a] & 255u);
-            if (p.kind == SSD_ENV_CLEANUP_FEATURES) {
-                o[8] = (double)(cw[a] >> 8); o[9] = (double)(cw[a] & 255u); o[10] = (double)n_cur_apple; o[11] = (double)n_cur_waste;
+        double v[FEAT_MAXF];                                          // fully unrolled below: stays in registers
+        const uint32_t me = pos[a], other = pos[a == 0 ? cp0 : 0];    // compute_closest_pos quirk
+        v[0] = (double)(me & 255u); v[1] = (double)((me >> 8) & 255u); v[2] = (double)((me >> 16) & 3u);
+        v[3] = (double)(other & 255u); v[4] = (double)((other >> 8) & 255u); v[5] = (double)((other >> 16) & 3u);
+        v[6] = (double)(ca[a] >> 8); v[7] = (double)(ca[a] & 255u);
+        if (cleanup) {
+            v[8] = (double)(cw[a] >> 8); v[9] = (double)(cw[a] & 255u); v[10] = (double)n_cur_apple; v[11] = (double)n_cur_waste;
 #pragma unroll
-                for (int i = 0; i < SSD_MAXN; i++) if (i < n) o[12 + i] = (double)cleaned[i];
-            } else {
-                o[8] = (double)close5[a]; o[9] = (double)n_cur_apple;
-                for (int i = 0; i < 2 * n; i++) o[10 + i] = 0.0;
-            }
+            for (int i = 0; i < SSD_MAXN; i++) v[12 + i] = i < n ? (double)cleaned[i] : 0.0;
+#pragma unroll
+            for (int i = 20; i < FEAT_MAXF; i++) v[i] = 0.0;
+        } else {
+            v[8] = (double)close5[a]; v[9] = (double)n_cur_apple;
+#pragma unroll
+            for (int i = 10; i < FEAT_MAXF; i++) v[i] = 0.0;
         }
-        __syncwarp();
-        for (int el = 0; el < 32; el++) {
-            if (!((valid >> el) & 1u)) continue;
-            if (lane < F) obs[((size_t)(env - lane + el) * n + a) * F + lane] = tile[el * (F + 1) + lane];
+        double* o = obs + ((size_t)env * n + a) * F;
+        if (even) {
+#pragma unroll
+            for (int k = 0; k < FEAT_MAXF; k += 2) if (k < F) reinterpret_cast<double2*>(o)[k >> 1] = make_double2(v[k], v[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < FEAT_MAXF; k++) if (k < F) o[k] = v[k];
         }
-        __syncwarp();
     }
 }
 
@@ -335,7 +355,6 @@ __device__ __forceinline__ void feat_reset_env(const FeatParams& p, int env, uin
 __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatParams p, const uint8_t* mask, double* obs)
 {
     __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
-    __shared__ double s_tile[(FEAT_THREADS / 32) * 32 * (FEAT_MAXF + 1)];
     const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
     const bool mine = env < p.E && (!mask || mask[env]);
     uint32_t* am = s_am + threadIdx.x; uint32_t* wm = s_wm + threadIdx.x;
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatPara
 #pragma unroll
     for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
     if (mine) feat_reset_env(p, env, am, wm, pos, ca, cw, close5, n_cur_apple, n_cur_waste);
-    if (obs) feat_write_obs(p, mine, env, s_tile + (threadIdx.x >> 5) * 32 * (FEAT_MAXF + 1), obs, pos, ca, cw, close5, cleaned,
+    if (obs) feat_write_obs(p, mine, env, obs, pos, ca, cw, close5, cleaned,
                             n_cur_apple, n_cur_waste);
 }
 
@@ -355,7 +374,6 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatPara
 __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kernel(const FeatParams p, const FeatIO io)
 {
     __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
-    __shared__ double s_tile[(FEAT_THREADS / 32) * 32 * (FEAT_MAXF + 1)];
     const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
     const int n = p.n, W = p.W;
     const bool mine = env < p.E;
@@ -390,10 +408,16 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kerne
         n_cur_waste = feat_popcount_mask(wm, p.n_waste);
         int act[SSD_MAXN]; uint32_t claim[SSD_MAXN]; bool has[SSD_MAXN];
         int reward[SSD_MAXN], eaten[SSD_MAXN], eaten_close[SSD_MAXN];
+        uint2 apk = make_uint2(0x04040404u, 0x04040404u);
+        const bool packed_actions = n == 8 && (reinterpret_cast<uintptr_t>(io.actions) & 7u) == 0;
+        if (packed_actions) apk = *reinterpret_cast<const uint2*>(io.actions + (size_t)env * 8);      // one 8-byte load
 #pragma unroll
         for (int a = 0; a < SSD_MAXN; a++) {
             has[a] = false; claim[a] = 0u; reward[a] = eaten[a] = eaten_close[a] = 0; act[a] = 4;
-            if (a < n) { pos[a] = p.agents[(size_t)a * p.E + env]; act[a] = io.actions[(size_t)env * n + a]; }
+            if (a < n) {
+                pos[a] = p.agents[(size_t)a * p.E + env];
+                act[a] = packed_actions ? (int)(((a < 4 ? apk.x : apk.y) >> (8 * (a & 3))) & 255u) : (int)io.actions[(size_t)env * n + a];
+            }
         }
         const bool cleanup = p.kind == SSD_ENV_CLEANUP_FEATURES;
         // stay first: highest priority (cleanup: act == 4; harvest: every act > 3)
@@ -532,7 +556,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kerne
         if ((next_apple | next_waste) > 0xFFFFu) p.metrics[(size_t)5 * p.E + env] = 1.0;
         if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
     }
-    feat_write_obs(p, mine, env, s_tile + (threadIdx.x >> 5) * 32 * (FEAT_MAXF + 1), io.obs, pos, ca, cw, close5, cleaned,
+    feat_write_obs(p, mine, env, io.obs, pos, ca, cw, close5, cleaned,
                    n_cur_apple, n_cur_waste);
 }
 

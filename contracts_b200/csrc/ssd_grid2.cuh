@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
     const uint16_t* ci = reinterpret_cast<const uint16_t*>(dsm);
     for (int i = threadIdx.x; i < (ci_bytes >> 2); i += LOGIC_THREADS)
         reinterpret_cast<uint32_t*>(dsm)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.cell_info) + i);
+    pdl_wait();                                                   // the actions (and the records) come from the preceding kernels
     uint32_t* amk = reinterpret_cast<uint32_t*>(dsm + ci_bytes) + warp * 2 * mw * 32 + lane;
     uint32_t* wmk = amk + mw * 32;
     uint32_t* agA = s_arr[warp][0]; uint32_t* mvA = s_arr[warp][2];
@@ -568,6 +569,8 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
 // harvest: rewards after the observe kernel has added total_close_apples to the result words
 __global__ void __launch_bounds__(LOGIC_THREADS) grid_reward_kernel(const GridParams p, const StepIO io, const uint32_t* __restrict__ res_g)
 {
+    pdl_launch_dependents();                          // (auto_reset) the masked reset kernel may set up meanwhile
+    pdl_wait();                                       // total_close_apples come from the observe kernel
     const int env = blockIdx.x * LOGIC_THREADS + threadIdx.x;
     if (env >= p.E) return;
     uint8_t* hdr = p.state + (size_t)env * p.rec_stride;
