@@ -31,6 +31,7 @@ struct ssd_handle {
     CarParams cp;
     FeatParams fp;
     int grid_blocks;
+    int feat_smem;           // dynamic shared memory of the feature-env kernels
     int obs_blocks;          // grid of the observe kernel (persistent: CTAs per SM x SMs, or fewer for small batches)
     int logic_smem;          // dynamic shared memory of the logic kernel (cell table + per-warp mask copies)
     bool pdl;                // programmatic dependent launch of the observe / reset kernels behind the logic / observe kernels
@@ -435,47 +436,93 @@ static int setup_features(ssd_handle* h)
     if (apple_rc.size() > 32 * FEAT_MASK_WORDS || waste_rc.size() > 32 * FEAT_MASK_WORDS)
         return fail(h, SSD_EUNSUPPORTED, "more than %d apple or waste points", 32 * FEAT_MASK_WORDS);
     p.n_apple = (int)apple_rc.size(); p.n_waste = (int)waste_rc.size(); p.n_spawn = (int)spawn_rc.size(); p.potential = p.n_waste;
-    std::vector<int16_t> nbr(std::max<size_t>(apple_rc.size(), 1) * 8, -1);      // 3x3 neighbours (j*j + k*k <= APPLE_RADIUS = 2)
-    for (size_t i = 0; i < apple_rc.size(); i++) {
-        int q = 0;
+    p.nwa = (p.n_apple + 31) / 32; p.nww = (p.n_waste + 31) / 32;
+    p.LA = std::max(16, (p.n_apple + 15) / 16 * 16); p.LW = std::max(16, (p.n_waste + 15) / 16 * 16); p.LS = p.LA + p.LW;
+    p.sm_static = 2 * (p.LA + p.LW); p.oct_bytes = 256 + p.LA + p.LW;
+    const int nwa = std::max(p.nwa, 1), nww = std::max(p.nww, 1);
+    // 3x3 neighbours of an apple point (j*j + k*k <= APPLE_RADIUS = 2, harvest_features.py:139-151) as a mask over the points
+    std::vector<uint32_t> nbr_mask(std::max<size_t>(apple_rc.size(), 1) * nwa, 0u);
+    for (size_t i = 0; i < apple_rc.size(); i++)
         for (int j = -1; j <= 1; j++)
             for (int k = -1; k <= 1; k++) {
                 if (!j && !k) continue;
                 const int r = (apple_rc[i] >> 8) + j, col = (apple_rc[i] & 255) + k;
-                nbr[i * 8 + q++] = (r >= 0 && r < H && col >= 0 && col < W) ? apple_idx[r * W + col] : (int16_t)-1;
+                if (r < 0 || r >= H || col < 0 || col >= W || apple_idx[r * W + col] < 0) continue;
+                const int q = apple_idx[r * W + col];
+                nbr_mask[i * nwa + (q >> 5)] |= 1u << (q & 31);
             }
-    }
+    // count_apples_in_radius(5, cell) (harvest_features.py:128-137): the apple points with j*j + k*k <= 5 around a cell
+    std::vector<uint32_t> near5((size_t)H * W * nwa, 0u);
+    // cleaning beam fired from (cell, orientation) (cleanup_features.py:196-219): the waste points on its three rays — each ray
+    // starts on the agent's own row / column of cells, runs 6 cells, skips cells outside the map and stops at the first wall
+    std::vector<uint32_t> beam_tab((size_t)H * W * 4 * nww, 0u);
+    for (int r0 = 0; r0 < H; r0++)
+        for (int c0 = 0; c0 < W; c0++) {
+            for (int j = -2; j <= 2; j++)
+                for (int k = -2; k <= 2; k++) {
+                    if (j * j + k * k > 5) continue;
+                    const int r = r0 + j, col = c0 + k;
+                    if (r < 0 || r >= H || col < 0 || col >= W || apple_idx[r * W + col] < 0) continue;
+                    const int q = apple_idx[r * W + col];
+                    near5[(size_t)(r0 * W + c0) * nwa + (q >> 5)] |= 1u << (q & 31);
+                }
+            if (!cleanup) continue;
+            for (int o = 0; o < 4; o++) {
+                const int o1 = (o + 1) & 3;
+                const int dr = o == 0 ? -1 : (o == 2 ? 1 : 0), dc = o == 1 ? 1 : (o == 3 ? -1 : 0);
+                const int sr = o1 == 0 ? -1 : (o1 == 2 ? 1 : 0), sc = o1 == 1 ? 1 : (o1 == 3 ? -1 : 0);
+                uint32_t* row = &beam_tab[((size_t)(r0 * W + c0) * 4 + o) * nww];
+                for (int b = 0; b < 3; b++) {
+                    const int br = r0 + (b == 1 ? sr : (b == 2 ? -sr : 0)), bc = c0 + (b == 1 ? sc : (b == 2 ? -sc : 0));
+                    for (int j = 0; j < 6; j++) {
+                        const int r = br + j * dr, col = bc + j * dc;
+                        if (r < 0 || r >= H || col < 0 || col >= W) continue;
+                        if (wall[r * W + col]) break;
+                        const int wi = waste_idx[r * W + col];
+                        if (wi >= 0) row[wi >> 5] |= 1u << (wi & 31);
+                    }
+                }
+            }
+        }
+    std::vector<uint32_t> start_mask(FEAT_MASK_WORDS, 0u);
+    for (size_t i = 0; i < waste_start.size(); i++) if (waste_start[i]) start_mask[i >> 5] |= 1u << (i & 31);
     std::vector<uint32_t> thr_apple;
     std::vector<uint8_t> waste_on;
     cleanup_probability_table(p.potential, thr_apple, waste_on);
-    const double SPAWN_PROB[4] = { 0, 0.005, 0.02, 0.05 };           // harvest_features.py:36
+    const double SPAWN_PROB[4] = { 0, 0.005, 0.02, 0.05 };           // harvest_features.py:36 (increasing: the kernel ranks a draw against them)
     for (int i = 0; i < 4; i++) p.thr_harvest[i] = prob_threshold(SPAWN_PROB[i]);
     p.thr_waste = prob_threshold(0.5);
+    if (apple_rc.empty()) apple_rc.push_back(0);
+    if (waste_rc.empty()) waste_rc.push_back(0);
     int rc;
     if ((rc = upload(h, wall, &p.wall))) return rc;
     if ((rc = upload(h, apple_idx, &p.apple_idx))) return rc;
     if ((rc = upload(h, waste_idx, &p.waste_idx))) return rc;
     if ((rc = upload(h, apple_rc, &p.apple_rc))) return rc;
     if ((rc = upload(h, waste_rc, &p.waste_rc))) return rc;
-    if ((rc = upload(h, nbr, &p.apple_nbr))) return rc;
     if ((rc = upload(h, spawn_rc, &p.spawn_rc))) return rc;
-    if ((rc = upload(h, waste_start, &p.waste_start))) return rc;
+    if ((rc = upload(h, start_mask, &p.waste_start_mask))) return rc;
     if ((rc = upload(h, thr_apple, &p.thr_apple))) return rc;
     if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
+    if ((rc = upload(h, beam_tab, &p.beam_tab))) return rc;
+    if ((rc = upload(h, near5, &p.near5))) return rc;
+    if ((rc = upload(h, nbr_mask, &p.nbr_mask))) return rc;
     const size_t E = (size_t)p.E;
-    if ((rc = dev_zalloc(h, E * n, &p.agents))) return rc;
-    if ((rc = dev_zalloc(h, E * FEAT_MASK_WORDS, &p.apple_mask))) return rc;
-    if ((rc = dev_zalloc(h, E * FEAT_MASK_WORDS, &p.waste_mask))) return rc;
-    if ((rc = dev_zalloc(h, E * p.n_apple, &p.apple_stamp))) return rc;
-    if ((rc = dev_zalloc(h, E * p.n_waste, &p.waste_stamp))) return rc;
-    if ((rc = dev_zalloc(h, E * 4, &p.counters))) return rc;
-    if ((rc = dev_zalloc(h, E, &p.theta))) return rc;
+    if ((rc = dev_zalloc(h, E * FR_WORDS, &p.rec))) return rc;
+    if ((rc = dev_zalloc(h, E * p.LS, &p.lists))) return rc;
     if ((rc = dev_zalloc(h, E * 8, &p.metrics))) return rc;
     if ((rc = dev_zalloc(h, E * n, &p.sum_raw))) return rc;
     if ((rc = dev_zalloc(h, E * n, &p.tsum_raw))) return rc;
     if ((rc = dev_zalloc(h, E * n, &p.sum_tr))) return rc;
     if ((rc = dev_zalloc(h, E * n, &p.tsum_tr))) return rc;
-    h->grid_blocks = (p.E + FEAT_THREADS - 1) / FEAT_THREADS;
+    h->feat_smem = p.sm_static + FEAT_ENVS_PER_CTA * p.oct_bytes;
+    if (h->feat_smem > 200 * 1024) return fail(h, SSD_EUNSUPPORTED, "feature envs: %d bytes of shared memory per CTA", h->feat_smem);
+    for (int q = 0; q < 4; q++) {
+        const void* fn = q == 0 ? (const void*)feat_kernel<true, false> : q == 1 ? (const void*)feat_kernel<true, true>
+                       : q == 2 ? (const void*)feat_kernel<false, false> : (const void*)feat_kernel<false, true>;
+        CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->feat_smem));
+    }
+    h->grid_blocks = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
     return SSD_OK;
 }
 
@@ -1141,8 +1188,8 @@ static SolverParams solver_params(ssd_handle* h)
         s.episode = reinterpret_cast<const uint8_t*>(h->cp.episode); s.episode_stride = 4; s.episode_mask = 0xFFFFFFFFu;
         s.theta = reinterpret_cast<uint8_t*>(h->cp.theta); s.theta_stride = 8;
     } else if (IS_FEAT(h)) {
-        s.episode = reinterpret_cast<const uint8_t*>(h->fp.counters + (size_t)3 * h->fp.E); s.episode_stride = 4; s.episode_mask = 0x7FFFFFFFu;
-        s.theta = reinterpret_cast<uint8_t*>(h->fp.theta); s.theta_stride = 8;
+        s.episode = reinterpret_cast<const uint8_t*>(h->fp.rec + FR_EPISODE); s.episode_stride = 4 * FR_WORDS; s.episode_mask = 0x7FFFFFFFu;
+        s.theta = reinterpret_cast<uint8_t*>(h->fp.rec + FR_THETA); s.theta_stride = 4 * FR_WORDS;
     } else {
         const GridParams& p = h->gp;
         s.episode = p.state + RO_EPISODE; s.episode_stride = p.rec_stride; s.episode_mask = 0xFFFFFFFFu;
@@ -1224,7 +1271,10 @@ int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void
     if (!h) return SSD_EINVAL;
     ON_DEVICE(h);
     REQUIRE_FEAT(h);
-    feat_reset_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, mask_dev, obs_dev);
+    FeatIO k = {};
+    k.obs = obs_dev;
+    if (h->cfg.env_kind == SSD_ENV_CLEANUP_FEATURES) feat_kernel<true, true><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, mask_dev);
+    else feat_kernel<false, true><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, mask_dev);
     return check_launch(h, "feat_reset");
 }
 
@@ -1236,7 +1286,8 @@ int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
     FeatIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
-    feat_step_kernel<<<h->grid_blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(h->fp, k);
+    if (h->cfg.env_kind == SSD_ENV_CLEANUP_FEATURES) feat_kernel<true, false><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, nullptr);
+    else feat_kernel<false, false><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, nullptr);
     return check_launch(h, "feat_step");
 }
 
@@ -1334,7 +1385,7 @@ int ssd_feature_dim(const ssd_handle* h)
 int64_t ssd_state_bytes_per_env(const ssd_handle* h)
 {
     if (!h) return 0;
-    if (IS_FEAT(h)) return (int64_t)(2 * (h->fp.n_apple + h->fp.n_waste) + 64 * FEAT_MASK_WORDS / 8 + 36 * h->fp.n + 88);
+    if (IS_FEAT(h)) return (int64_t)(4 * FR_WORDS + h->fp.LS + 28 * h->fp.n + 64);
     return h->cfg.env_kind == SSD_ENV_SELFDRIVE ? (int64_t)(16 * h->cp.n + 44) : (int64_t)h->gp.rec_stride;
 }
 int64_t ssd_kernel_launches(const ssd_handle* h) { return h ? h->launches : 0; }

@@ -8,22 +8,47 @@
 //       count_apples_in_radius :128-137
 //   contract/contract_list.py :22-27, :45-54 ; environments/two_stage_train.py :62-121, :159-187
 //
-// Mapping: these envs are list manipulations on <= 155 apple / 119 waste points with data-dependent sequential scans
-// (HarvestFeatures' regrowth reads the list it is appending to), and the benchmark runs ~1M of them: one THREAD per
-// env.  The current apple / waste lists are a presence bitmask (shared memory while stepping) plus a birth stamp per
-// point (global memory, struct of arrays) — list order = stamp order, which decides np.argmin ties in
-// compute_closest_*.  Feature rows (12+n or 10+2n doubles per agent) are transposed through a warp-private shared
-// tile so that every global store instruction writes one contiguous row.
+// Mapping (round 2): EIGHT LANES PER ENV (an "octet"; lane = agent), four envs per warp.  Round 1 ran one thread per env:
+// 128 registers, 16 warps per SM, 15 of 32 lanes active on average and every thread a ~30 k-instruction dependency chain
+// (0.36 ms per step at 131072 envs = 12 % of HBM).  Here
+//   * the env's state is the reference's own data structure: current_apple_points / current_waste_points as byte lists of
+//     point indices IN LIST (= birth) ORDER — np.argmin ties in compute_closest_* fall to the lowest list position — plus
+//     presence bitmasks for the membership tests; a 128-byte hot record (agents, counters, contract parameter, masks) and
+//     the two lists are one coalesced load / store per octet;
+//   * movement claims are resolved with one ballot per mover, same-cell apple conflicts with one match.any;
+//   * a cleaning beam is a table row (cell, orientation) -> bitmask of the waste points its three rays reach (walls are
+//     static), so firing is an AND with the waste mask and an exclusive OR-scan over the agents for the attribution;
+//   * spawn draws: lane l computes Philox blocks l, l + 8, ... of the step's stream and compares its four draws in place;
+//     only the successes (a few per step) are mapped from draw rank back to points;
+//   * closest apple / waste: lane = list slot; the L1 distances of an entry to four agents come from two VABSDIFF4 + one
+//     add, a key (distance << 8 | list position) per agent is one PRMT + one min, and a three-step transpose-reduce leaves
+//     agent a's winner in lane a;
+//   * removals (eaten apples, cleaned waste) compact the list in place with a ballot-free octet prefix sum;
+//   * every lane stores its own agent's feature row (16-byte stores; an octet's rows are one contiguous run).
 #pragma once
 #include "ssd_common.cuh"
 
-#define FEAT_THREADS 128
-#define FEAT_MASK_WORDS 8               // up to 256 apple and 256 waste points
+#define FEAT_WARPS 8
+#define FEAT_THREADS (FEAT_WARPS * 32)
+#define FEAT_ENVS_PER_CTA (FEAT_WARPS * 4)
+#define FEAT_MASK_WORDS 8               // up to 256 apple and 256 waste points: mask word w is owned by lane w of the octet
 #define FEAT_MAXF 26                    // 10 + 2 * 8
+#define FULLMASK 0xffffffffu
+
+// hot record: uint32 [E][32]
+enum { FR_AGENT = 0,                    // [8] row | col << 8 | ori << 16
+       FR_NA = 8, FR_NW = 9,            // list lengths
+       FR_T = 10, FR_EPISODE = 11,      // episode | initialised << 31
+       FR_THETA = 12,                   // float64
+       FR_AM = 16, FR_WM = 24,          // presence masks
+       FR_WORDS = 32 };
 
 struct FeatParams {
     int E, n, kind, H, W, F, horizon, contract;
     int n_apple, n_waste, n_spawn, potential;
+    int nwa, nww;               // mask words in use
+    int LA, LW, LS;             // list capacities in bytes (multiples of 16), LS = LA + LW
+    int sm_static, oct_bytes;   // shared memory: static tables, bytes per octet
     uint32_t seed, first_env_id;
     double theta_low, theta_high, null_prob;
     uint32_t thr_harvest[4], thr_waste;
@@ -33,19 +58,16 @@ struct FeatParams {
     const int16_t* waste_idx;   // [H*W]
     const uint16_t* apple_rc;   // [n_apple] row << 8 | col
     const uint16_t* waste_rc;   // [n_waste]
-    const int16_t* apple_nbr;   // [n_apple][8] apple indices of the 3x3 neighbours or -1 (harvest regrowth)
     const uint16_t* spawn_rc;   // [n_spawn]
-    const uint8_t* waste_start; // [n_waste] 1 if the point starts as waste ('H')
+    const uint32_t* waste_start_mask; // [8] points that start as waste ('H')
     const uint32_t* thr_apple;  // [potential + 1] apple spawn threshold by #waste (cleanup)
     const uint8_t* waste_on;    // [potential + 1]
-    // state, struct of arrays
-    uint32_t* agents;           // [n][E] row | col << 8 | ori << 16
-    uint32_t* apple_mask;       // [FEAT_MASK_WORDS][E]
-    uint32_t* waste_mask;       // [FEAT_MASK_WORDS][E]
-    uint16_t* apple_stamp;      // [n_apple][E]
-    uint16_t* waste_stamp;      // [n_waste][E]
-    uint32_t* counters;         // [4][E] next apple stamp, next waste stamp, t, episode | initialised << 31
-    double* theta;              // [E]
+    const uint32_t* beam_tab;   // [H*W][4][nww] waste points reached by a cleaning beam fired from (cell, orientation)
+    const uint32_t* near5;      // [H*W][nwa] apple points with j*j + k*k <= 5 around the cell (count_apples_in_radius)
+    const uint32_t* nbr_mask;   // [n_apple][nwa] apple points in the 3x3 neighbourhood of a point (harvest regrowth)
+    // state
+    uint32_t* rec;              // [E][FR_WORDS]
+    uint8_t* lists;             // [E][LS]: apple list (LA bytes) then waste list
     double* metrics;            // [8][E] dirt, raw, transfers, apples, low_density
     uint32_t* sum_raw;          // [n][E]
     unsigned long long* tsum_raw; // [n][E]
@@ -59,202 +81,535 @@ struct FeatIO {
     double* rew; double* base_rew; double* transfers;   // [E][n]
     uint8_t* info;              // [E][n][4]: cleanup (cleaned_squares,0,0,0); harvest (eaten_apples, eaten_close_apples,0,0)
     uint8_t* done;              // [E]
-    int auto_reset;             // next-step auto-reset (see feat_step_kernel)
+    int auto_reset;             // next-step auto-reset (see feat_kernel)
 };
 
-struct FeatDraws {              // k-th random.random() of a step: Philox block cached
-    uint32_t seed, env_id, episode, t, blk;
-    Philox4 q;
-    __device__ __forceinline__ uint32_t get(uint32_t k)
-    {
-        if ((k >> 2) != blk) { blk = k >> 2; q = philox4x32_10(blk, SITE_FEAT_SPAWN, t, episode, seed, env_id); }
-        return pick(q, k & 3u);
-    }
-};
-
-// per-thread views of the presence masks in shared memory: word w of this thread = m[w * FEAT_THREADS]
-__device__ __forceinline__ bool mask_test(const uint32_t* m, int idx) { return (m[(idx >> 5) * FEAT_THREADS] >> (idx & 31)) & 1u; }
-__device__ __forceinline__ void mask_set(uint32_t* m, int idx) { m[(idx >> 5) * FEAT_THREADS] |= 1u << (idx & 31); }
-__device__ __forceinline__ void mask_clear(uint32_t* m, int idx) { m[(idx >> 5) * FEAT_THREADS] &= ~(1u << (idx & 31)); }
-
-// count_apples_in_radius(radius, loc): j*j + k*k <= radius (sic) over the live list
-__device__ __forceinline__ int feat_count_radius5(const FeatParams& p, const uint32_t* am, int r, int c)
+// ---- octet primitives (all 32 lanes execute them; an octet is lanes obase .. obase + 7) --------------------------------
+__device__ __forceinline__ int oct_scan_incl(int v, int a)
 {
-    int cnt = 0;
-    for (int j = -2; j <= 2; j++)
-        for (int k = -2; k <= 2; k++) {
-            if (j * j + k * k > 5) continue;
-            const int rr = r + j, cc = c + k;
-            if (rr < 0 || rr >= p.H || cc < 0 || cc >= p.W) continue;
-            const int i = __ldg(p.apple_idx + rr * p.W + cc);
-            if (i >= 0 && mask_test(am, i)) cnt++;
-        }
-    return cnt;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) { const int t = __shfl_up_sync(FULLMASK, v, d, 8); if (a >= d) v += t; }
+    return v;
 }
-
-// spawn_apples_and_waste (cleanup_features.py:111-125) / spawn_apples (harvest_features.py:139-151)
-__device__ __forceinline__ void feat_spawn(const FeatParams& p, int env, uint32_t* am, uint32_t* wm, const uint32_t* pos, FeatDraws& dr,
-                                           uint32_t& next_apple, uint32_t& next_waste, int& n_cur_apple, int& n_cur_waste)
+__device__ __forceinline__ int oct_sum(int v)
 {
-    const int n = p.n;
-    // apple points under an agent are not eligible
-    uint32_t occ[FEAT_MASK_WORDS];
+    v += __shfl_xor_sync(FULLMASK, v, 1); v += __shfl_xor_sync(FULLMASK, v, 2); v += __shfl_xor_sync(FULLMASK, v, 4);
+    return v;
+}
+__device__ __forceinline__ uint32_t oct_or(uint32_t v)
+{
+    v |= __shfl_xor_sync(FULLMASK, v, 1); v |= __shfl_xor_sync(FULLMASK, v, 2); v |= __shfl_xor_sync(FULLMASK, v, 4);
+    return v;
+}
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    const int lo = __shfl_sync(FULLMASK, __double2loint(v), src, 8), hi = __shfl_sync(FULLMASK, __double2hiint(v), src, 8);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ uint32_t feat_valid_word(int npts, int w)
+{
+    const int left = npts - 32 * w;
+    return left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+__device__ __forceinline__ int feat_cell(const FeatParams& p, uint32_t pos)
+{
+    const int r = min((int)(pos & 255u), p.H - 1), c = min((int)((pos >> 8) & 255u), p.W - 1);
+    return r * p.W + c;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// list.remove() of every entry whose point left the presence mask m[0..7], in place (order kept).  Lane a takes words a,
+// a + 8, ... of the list (4 entries each); a round's reads finish before its writes, and writes never pass the round's
+// own read positions.  Octets with need == false keep their list.  Returns the new length (octet-uniform).
+__device__ __forceinline__ int oct_compact(uint8_t* list, int L, bool need, const uint32_t* m, int a)
+{
+    const int Leff = need ? L : 0;
+    const int Lmax = __reduce_max_sync(FULLMASK, Leff);
+    int out = 0;
+    for (int w0 = 0; w0 * 4 < Lmax; w0 += 8) {
+        const int wi = w0 + a;
+        uint32_t e4 = 0u, keep = 0u;
+        if (wi * 4 < Leff) {
+            e4 = *reinterpret_cast<const uint32_t*>(list + 4 * wi);
 #pragma unroll
-    for (int w = 0; w < FEAT_MASK_WORDS; w++) occ[w] = 0u;
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) {
-        if (a >= n) continue;
-        const int i = __ldg(p.apple_idx + (int)(pos[a] & 255u) * p.W + (int)((pos[a] >> 8) & 255u));
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) if (i >= 0 && (i >> 5) == w) occ[w] |= 1u << (i & 31);
-    }
-    const int aw = (p.n_apple + 31) >> 5;
-    uint32_t k = 0;
-    if (p.kind == SSD_ENV_CLEANUP_FEATURES) {
-        const uint32_t thrA = __ldg(p.thr_apple + n_cur_waste);
-        const bool waste_on = __ldg(p.waste_on + n_cur_waste) != 0;
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) {
-            if (w >= aw) continue;
-            const uint32_t valid = (w == aw - 1 && (p.n_apple & 31)) ? ((1u << (p.n_apple & 31)) - 1u) : 0xffffffffu;
-            uint32_t elig = ~am[w * FEAT_THREADS] & ~occ[w] & valid;
-            if (thrA == 0u) { k += (uint32_t)__popc(elig); continue; }      // r < 0 never holds; the draws are still consumed
-            while (elig) {
-                const int b = __ffs(elig) - 1; elig &= elig - 1;
-                if (dr.get(k++) < thrA) {
-                    const int i = w * 32 + b;
-                    mask_set(am, i); p.apple_stamp[(size_t)i * p.E + env] = (uint16_t)next_apple++; n_cur_apple++;
-                }
+            for (int j = 0; j < 4; j++) {
+                const uint32_t idx = (e4 >> (8 * j)) & 255u;
+                if (4 * wi + j < Leff && ((m[idx >> 5] >> (idx & 31u)) & 1u)) keep |= 1u << j;
             }
         }
-        if (waste_on) {
-            const int ww = (p.n_waste + 31) >> 5;
-            bool spawned = false;
-            for (int w = 0; w < ww && !spawned; w++) {
-                const uint32_t valid = (w == ww - 1 && (p.n_waste & 31)) ? ((1u << (p.n_waste & 31)) - 1u) : 0xffffffffu;
-                uint32_t cand = ~wm[w * FEAT_THREADS] & valid;
-                while (cand) {
-                    const int b = __ffs(cand) - 1; cand &= cand - 1;
-                    if (dr.get(k++) < p.thr_waste) {
-                        const int i = w * 32 + b;
-                        mask_set(wm, i); p.waste_stamp[(size_t)i * p.E + env] = (uint16_t)next_waste++; n_cur_waste++;
-                        spawned = true;
-                        break;
+        const int kc = __popc(keep);
+        const int incl = oct_scan_incl(kc, a);
+        const int tot = __shfl_sync(FULLMASK, incl, 7, 8);
+        __syncwarp();
+        int o = out + incl - kc;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if ((keep >> j) & 1u) list[o++] = (uint8_t)((e4 >> (8 * j)) & 255u);
+        out += tot;
+        __syncwarp();
+    }
+    return need ? out : L;
+}
+
+// compute_closest_*: for agent a (left in lane a) the entry of the list with the smallest (L1 distance, list position);
+// returns its row << 8 | col, or 0 — the reference's [0, 0] sentinel — for an empty list.  ar / ac: the agents' rows /
+// columns packed one per byte (agents 0-3, 4-7); absent agents sit at (127, 127) so that no byte sum carries.
+__device__ __forceinline__ uint32_t oct_closest(const uint8_t* list, int L, const uint16_t* rc, const uint32_t (&ar)[2],
+                                                const uint32_t (&ac)[2], bool n_gt4, int a)
+{
+    const int Lmax = __reduce_max_sync(FULLMASK, L);
+    uint32_t best[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) best[g] = 0xFFFFu;
+    for (int w0 = 0; w0 * 4 < Lmax; w0 += 8) {
+        const int wi = w0 + a;
+        if (wi * 4 >= L) continue;                               // (no collectives inside the loop)
+        const uint32_t e4 = *reinterpret_cast<const uint32_t*>(list + 4 * wi);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t pos = (uint32_t)(4 * wi + j);
+            const uint32_t prc = rc[(e4 >> (8 * j)) & 255u];
+            const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
+            const bool live = (int)pos < L;
+            uint32_t d0 = __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]);
+            if (!live) d0 = 0xFFFFFFFFu;
+#pragma unroll
+            for (int g = 0; g < 4; g++) best[g] = min(best[g], __byte_perm(d0, pos, 0x5504u | ((uint32_t)g << 4)));   // d_g << 8 | pos
+            if (n_gt4) {
+                uint32_t d1 = __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]);
+                if (!live) d1 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int g = 0; g < 4; g++) best[4 + g] = min(best[4 + g], __byte_perm(d1, pos, 0x5504u | ((uint32_t)g << 4)));
+            }
+        }
+    }
+    // transpose-reduce: lane a ends with the minimum over the octet of best[a]
+    uint32_t b4[4], b2[2];
+    const bool h4 = (a & 4) != 0, h2 = (a & 2) != 0, h1 = (a & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t snd = h4 ? best[j] : best[4 + j], kp = h4 ? best[4 + j] : best[j];
+        b4[j] = min(kp, __shfl_xor_sync(FULLMASK, snd, 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t snd = h2 ? b4[j] : b4[2 + j], kp = h2 ? b4[2 + j] : b4[j];
+        b2[j] = min(kp, __shfl_xor_sync(FULLMASK, snd, 2));
+    }
+    const uint32_t snd = h1 ? b2[0] : b2[1], kp = h1 ? b2[1] : b2[0];
+    const uint32_t key = min(kp, __shfl_xor_sync(FULLMASK, snd, 1));
+    if ((key >> 8) >= 0xFFu) return 0u;                           // no live entry
+    return rc[list[key & 255u]];
+}
+
+#ifndef FEAT_MIN_BLOCKS
+#define FEAT_MIN_BLOCKS 4
+#endif
+
+// One launch = one step (or, RESET_ONLY, one masked reset) of every env.
+// Next-step auto-reset (ssd_feat_io.auto_reset): an env that reached its horizon in the previous step starts its next
+// episode in this one — reset observation, zero rewards, done cleared, the actions of this step ignored.
+template <bool CLEANUP, bool RESET_ONLY>
+__global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(const FeatParams p, const FeatIO io, const uint8_t* __restrict__ mask)
+{
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, a = lane & 7, obase = lane & 24;
+    const int n = p.n;
+    uint16_t* s_arc = reinterpret_cast<uint16_t*>(fsm);
+    uint16_t* s_wrc = s_arc + p.LA;
+    for (int i = threadIdx.x; i < p.n_apple; i += FEAT_THREADS) s_arc[i] = __ldg(p.apple_rc + i);
+    for (int i = threadIdx.x; i < p.n_waste; i += FEAT_THREADS) s_wrc[i] = __ldg(p.waste_rc + i);
+    __syncthreads();
+    const int env_raw = (blockIdx.x * FEAT_WARPS + warp) * 4 + (lane >> 3);
+    bool active = env_raw < p.E;
+    const int env = active ? env_raw : p.E - 1;
+    if (RESET_ONLY && mask) active = active && mask[env] != 0;
+    if (RESET_ONLY && !__any_sync(FULLMASK, active)) return;
+
+    uint8_t* ob = fsm + p.sm_static + (size_t)(warp * 4 + (lane >> 3)) * p.oct_bytes;
+    uint32_t* s_rec = reinterpret_cast<uint32_t*>(ob);
+    uint32_t* s_scr = s_rec + 32;                    // [0..7] eligibility, [8..15] / [16..23] success bits by draw rank
+    uint8_t* s_al = ob + 256;
+    uint8_t* s_wl = s_al + p.LA;
+    uint32_t* grec = p.rec + (size_t)env * FR_WORDS;
+    uint8_t* glist = p.lists + (size_t)env * p.LS;
+
+    // ---- state in: the hot record (16 bytes per lane), then the live parts of the two lists (asynchronous copies)
+    {
+        uint4 h4 = make_uint4(0u, 0u, 0u, 0u);
+        if (active) h4 = *reinterpret_cast<const uint4*>(grec + 4 * a);
+        *reinterpret_cast<uint4*>(s_rec + 4 * a) = h4;
+    }
+    __syncwarp();
+    const uint32_t c3 = s_rec[FR_EPISODE];
+    const bool doreset = RESET_ONLY ? active : (active && io.auto_reset && (int)s_rec[FR_T] == p.horizon);
+    const bool stepping = !RESET_ONLY && active && !doreset;
+    int nA = stepping ? (int)s_rec[FR_NA] : 0, nW = stepping ? (int)s_rec[FR_NW] : 0;
+    if (!RESET_ONLY) {
+        for (int j = a; j * 16 < p.LA; j += 8) if (j * 16 < nA) cp_async16(s_al + 16 * j, glist + 16 * j);
+        for (int j = a; j * 16 < p.LW; j += 8) if (j * 16 < nW) cp_async16(s_wl + 16 * j, glist + p.LA + 16 * j);
+    }
+    uint32_t episode = c3 & 0x7fffffffu;
+    const uint32_t env_id = p.first_env_id + (uint32_t)env;
+    double theta = __hiloint2double((int)s_rec[FR_THETA + 1], (int)s_rec[FR_THETA]);
+    uint32_t pos = a < n ? s_rec[FR_AGENT + a] : 0u;
+    bool a_chg = false, w_chg = false;               // lists to write back
+
+    // ---- reset (cleanup_features.py:256-284 / harvest_features.py:289-336 + two_stage_train.py:159-187)
+    if (__any_sync(FULLMASK, doreset)) {
+        uint32_t sm = (CLEANUP && doreset) ? __ldg(p.waste_start_mask + a) : 0u;
+        const int sc = __popc(sm);
+        const int sincl = oct_scan_incl(sc, a);
+        const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
+        if (doreset) {
+            episode = (c3 & 0x80000000u) ? (c3 & 0x7fffffffu) + 1u : 0u;
+            // initialize_arrays
+            if (CLEANUP) {
+                s_rec[FR_AM + a] = 0u; s_rec[FR_WM + a] = sm;
+                int o = sincl - sc;
+                while (sm) { const int b = __ffs(sm) - 1; sm &= sm - 1; s_wl[o++] = (uint8_t)(a * 32 + b); }
+                nA = 0; nW = stot;
+            } else {
+                s_rec[FR_AM + a] = feat_valid_word(p.n_apple, a); s_rec[FR_WM + a] = 0u;
+                for (int i = a; i < p.n_apple; i += 8) s_al[i] = (uint8_t)i;
+                nA = p.n_apple; nW = 0;
+            }
+            a_chg = w_chg = true;
+            // initialize_players: agent a takes the spawn point with the (a+1)-th smallest (key, index).  Every lane walks
+            // all keys (one Philox block per four points) keeping the n smallest in a sorted register list.
+            {
+                uint32_t bk[SSD_MAXN]; int bj[SSD_MAXN];
+#pragma unroll
+                for (int q = 0; q < SSD_MAXN; q++) { bk[q] = 0xffffffffu; bj[q] = 0x7fffffff; }
+                Philox4 blk = { 0, 0, 0, 0 };
+                for (int j = 0; j < p.n_spawn; j++) {
+                    if ((j & 3) == 0) blk = draw_block(p.seed, env_id, episode, 0u, SITE_FEAT_ORDER, 0u, (uint32_t)(j >> 2));
+                    uint32_t kk = pick(blk, (uint32_t)j & 3u); int jj = j;
+#pragma unroll
+                    for (int q = 0; q < SSD_MAXN; q++) {             // insertion: (kk, jj) sinks to its place, the rest shift down
+                        const bool less = kk < bk[q] || (kk == bk[q] && jj < bj[q]);
+                        const uint32_t tk = bk[q]; const int tj = bj[q];
+                        if (less) { bk[q] = kk; bj[q] = jj; kk = tk; jj = tj; }
                     }
                 }
+                int mine = bj[0];
+#pragma unroll
+                for (int q = 1; q < SSD_MAXN; q++) if (a == q) mine = bj[q];
+                if (a < n) {
+                    const uint32_t rc = __ldg(p.spawn_rc + mine);
+                    const uint32_t o = draw_u32(p.seed, env_id, episode, 0u, SITE_FEAT_ROT, (uint32_t)a, 0u) >> 30;
+                    pos = (rc >> 8) | ((rc & 255u) << 8) | (o << 16);
+                }
+            }
+            theta = 0.0;
+            if (p.contract != SSD_CONTRACT_NONE) {
+                const double u0 = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, SITE_CONTRACT, 0u, 0u), 1.0 / 4294967296.0);
+                const double u1 = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, SITE_CONTRACT, 0u, 1u), 1.0 / 4294967296.0);
+                theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1)) : p.theta_low;
+            }
+            if (a < n) {
+                const size_t so = (size_t)a * p.E + env;
+                p.sum_raw[so] = 0u; p.tsum_raw[so] = 0ull; p.sum_tr[so] = 0.0; p.tsum_tr[so] = 0.0;
+            }
+            p.metrics[(size_t)a * p.E + env] = 0.0;
+        }
+        __syncwarp();
+    }
+
+    int reward = 0, eaten = 0, eaten_close = 0, cleaned = 0, dirt = 0;
+    if (!RESET_ONLY) {
+        // ---- moves (cleanup_features.py:162-183): stays claim first, then the movers in agent order
+        int act = 255;
+        if (stepping && a < n) act = io.actions[(size_t)env * n + a];
+        const bool agent_ok = stepping && a < n;
+        const bool mover = agent_ok && act < 4;
+        bool has = agent_ok && (CLEANUP ? act == 4 : act > 3);
+        uint32_t claim = pos & 0xFFFFu, tgt = claim;
+        bool wallblk = false;
+        if (mover) {
+            const int r = (int)(pos & 255u), c = (int)((pos >> 8) & 255u);
+            const int tr = r + (act == 2 ? -1 : (act == 3 ? 1 : 0)), tc = c + (act == 0 ? -1 : (act == 1 ? 1 : 0));
+            tgt = (uint32_t)tr | ((uint32_t)tc << 8);
+            wallblk = (tr < 0 || tr >= p.H || tc < 0 || tc >= p.W) ? false : __ldg(p.wall + tr * p.W + tc) != 0;
+        }
+        const uint32_t mv_all = __ballot_sync(FULLMASK, mover);
+        const uint32_t mv_any = (mv_all | (mv_all >> 8) | (mv_all >> 16) | (mv_all >> 24)) & 0xFFu;
+        for (int m = 0; m < n; m++) {
+            if (!((mv_any >> m) & 1u)) continue;
+            const uint32_t tgt_m = __shfl_sync(FULLMASK, tgt, m, 8);
+            const uint32_t hit = (__ballot_sync(FULLMASK, has && claim == tgt_m) >> obase) & 0xFFu;
+            if (a == m && mover) { claim = (wallblk || hit) ? (pos & 0xFFFFu) : tgt; has = true; }
+        }
+        if (has) pos = (pos & 0xFFFF0000u) | claim;
+
+        // ---- consume in move_squares insertion order: stays (agent order), then movers (agent order)
+        cp_async_wait_all();
+        __syncwarp();
+        const int cell = feat_cell(p, pos);
+        int ai = -1;
+        if (has) ai = __ldg(p.apple_idx + cell);
+        bool cand = ai >= 0 && ((s_rec[FR_AM + (ai >> 5)] >> (ai & 31)) & 1u);
+        {   // two agents can share a cell: the first in insertion order eats
+            const uint32_t key = cand ? (((uint32_t)obase << 16) | (uint32_t)ai) : (0x80000000u | (uint32_t)lane);
+            const uint32_t grp = __match_any_sync(FULLMASK, key);
+            const uint32_t stays = grp & ~mv_all;
+            const int winner = stays ? __ffs(stays) - 1 : __ffs(grp) - 1;
+            cand = cand && winner == lane;
+        }
+        if (CLEANUP) {
+            if (cand) { reward = 1; atomicAnd(&s_rec[FR_AM + (ai >> 5)], ~(1u << (ai & 31))); }
+        } else {
+            // harvest_features.py:204-215: an eater also counts the apples within the radius of its square at the moment it
+            // eats (its own apple included, earlier eaters' apples gone), so the eaters go one at a time
+            uint32_t pend = __ballot_sync(FULLMASK, cand);
+            while (pend) {
+                const uint32_t pe = (pend >> obase) & 0xFFu, st = pe & ~(mv_all >> obase);
+                const int nxt = pe ? (st ? __ffs(st) - 1 : __ffs(pe) - 1) : -1;
+                const int cell_n = __shfl_sync(FULLMASK, cell, nxt < 0 ? 0 : nxt, 8);
+                int cnt = 0;
+                if (nxt >= 0 && a < p.nwa) cnt = __popc(s_rec[FR_AM + a] & __ldg(p.near5 + (size_t)cell_n * p.nwa + a));
+                cnt = oct_sum(cnt);
+                __syncwarp();
+                if (a == nxt) {
+                    reward = 1; eaten = 1; eaten_close = cnt < 4 ? 1 : 0; cand = false;
+                    s_rec[FR_AM + (ai >> 5)] &= ~(1u << (ai & 31));
+                }
+                __syncwarp();
+                pend = __ballot_sync(FULLMASK, cand);
             }
         }
-    } else {
+        const uint32_t ate = __ballot_sync(FULLMASK, reward != 0);
+        if (ate) {
+            __syncwarp();
+            const bool need = ((ate >> obase) & 0xFFu) != 0u;
+            nA = oct_compact(s_al, nA, need, s_rec + FR_AM, a);
+            a_chg = a_chg || need;
+        }
+        // ---- rotations
+        if (agent_ok) {
+            uint32_t o = (pos >> 16) & 3u;
+            if (act == 5) o = (o + 1u) & 3u;
+            if (act == 6) o = (o + 3u) & 3u;
+            pos = (pos & 0xFFFFu) | (o << 16);
+        }
+        // ---- cleaning beams (cleanup_features.py:196-219): 3 rays x 6 cells incl. the agent's own, stopped by walls only.
+        // Agents fire in index order, so a waste cell goes to the first firing agent whose beam reaches it.
+        if (CLEANUP) {
+            const bool fire = agent_ok && act == 7;
+            if (__any_sync(FULLMASK, fire)) {
+                const uint32_t* row = p.beam_tab + ((size_t)feat_cell(p, pos) * 4 + ((pos >> 16) & 3u)) * p.nww;
+                for (int w = 0; w < p.nww; w++) {
+                    const uint32_t wmw = s_rec[FR_WM + w];
+                    const uint32_t v = fire ? (__ldg(row + w) & wmw) : 0u;
+                    uint32_t incl = v;
 #pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) {
-            if (w >= aw) continue;
-            const uint32_t valid = (w == aw - 1 && (p.n_apple & 31)) ? ((1u << (p.n_apple & 31)) - 1u) : 0xffffffffu;
-            uint32_t elig = ~am[w * FEAT_THREADS] & ~occ[w] & valid;
-            while (elig) {
-                const int b = __ffs(elig) - 1; elig &= elig - 1;
-                const int i = w * 32 + b;
-                int num = 0;                                                // live list: sees this loop's earlier spawns
-                const int4 n0 = __ldg(reinterpret_cast<const int4*>(p.apple_nbr + i * 8));
-                const int nb[8] = { (short)(n0.x & 0xFFFF), (short)(n0.x >> 16), (short)(n0.y & 0xFFFF), (short)(n0.y >> 16),
-                                    (short)(n0.z & 0xFFFF), (short)(n0.z >> 16), (short)(n0.w & 0xFFFF), (short)(n0.w >> 16) };
-#pragma unroll
-                for (int q = 0; q < 8; q++) if (nb[q] >= 0 && mask_test(am, nb[q])) num++;
-                const uint32_t kk = k++;
-                if (num > 0 && dr.get(kk) < p.thr_harvest[num < 3 ? num : 3]) {
-                    mask_set(am, i); p.apple_stamp[(size_t)i * p.E + env] = (uint16_t)next_apple++; n_cur_apple++;
+                    for (int d = 1; d < 8; d <<= 1) { const uint32_t t = __shfl_up_sync(FULLMASK, incl, d, 8); if (a >= d) incl |= t; }
+                    uint32_t excl = __shfl_up_sync(FULLMASK, incl, 1, 8);
+                    if (a == 0) excl = 0u;
+                    cleaned += __popc(v & ~excl);
+                    const uint32_t all = __shfl_sync(FULLMASK, incl, 7, 8);
+                    dirt += __popc(all);
+                    __syncwarp();
+                    if (a == 0 && all) s_rec[FR_WM + w] = wmw & ~all;
+                }
+                __syncwarp();
+                if (__any_sync(FULLMASK, dirt != 0)) {
+                    nW = oct_compact(s_wl, nW, dirt != 0, s_rec + FR_WM, a);
+                    w_chg = w_chg || dirt != 0;
                 }
             }
         }
     }
-}
 
-// closest point of a list to each agent: smallest (L1 distance, birth stamp)  (np.argmin over the list in birth order).
-// One key per (point, agent): distance << 24 | birth stamp << 8 | point index, so the search is a running minimum —
-// no data-dependent stamp loads on ties (the stamp of every live point is read once, coalesced across the warp's
-// envs: stamp[i][env]).  The L1 distances of a point to four agents at a time come from two VABSDIFF4.U8 (rows, columns:
-// agents packed one per byte) and one add; distances are < 256, stamps 16 bits, indices < 256 (FEAT_MASK_WORDS * 32).
-__device__ __forceinline__ void feat_closest(int n, int E, int env, const uint32_t* mask, int npts, const uint16_t* rc,
-                                             const uint16_t* stamp, const uint32_t* pos, uint32_t* out_rc /* [MAXN] */)
-{
-    uint32_t best[SSD_MAXN];
-    uint32_t ar[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu }, ac[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu };     // absent agents: (127, 127), no byte carry
+    // ---- spawn_apples_and_waste (cleanup_features.py:111-125) / spawn_apples (harvest_features.py:139-151).
+    // The k-th random.random() of the step is draw k of the step's Philox stream (block k >> 2, word k & 3); an apple point
+    // that is neither in the list nor under an agent consumes one draw, in point order.
+    const uint32_t tdraw = doreset ? 0u : s_rec[FR_T] + 1u;
+    s_scr[a] = ~s_rec[FR_AM + a] & feat_valid_word(p.n_apple, a);
+    s_scr[8 + a] = 0u;
+    if (!CLEANUP) s_scr[16 + a] = 0u;
+    __syncwarp();
+    if (active && a < n) {
+        const int aj = __ldg(p.apple_idx + feat_cell(p, pos));
+        if (aj >= 0) atomicAnd(&s_scr[aj >> 5], ~(1u << (aj & 31)));
+    }
+    __syncwarp();
+    const uint32_t elig = active ? s_scr[a] : 0u;
+    const int ecnt = __popc(elig);
+    const int eincl = oct_scan_incl(ecnt, a);
+    const int eexcl = eincl - ecnt;
+    const int nelig = __shfl_sync(FULLMASK, eincl, 7, 8);
+    if (CLEANUP) {
+        const uint32_t thrA = active ? __ldg(p.thr_apple + nW) : 0u;       // compute_probabilities by the waste count
+        const bool won = active && __ldg(p.waste_on + nW) != 0;
+        const int nblk = thrA ? (nelig + 3) >> 2 : 0;                      // r < 0 never holds: the draws are consumed unseen
+        const int maxblk = __reduce_max_sync(FULLMASK, nblk);
+        for (int b0 = 0; b0 < maxblk; b0 += 8) {
+            const int b = b0 + a;
+            if (b < nblk) {
+                const Philox4 q = philox4x32_10((uint32_t)b, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
+                uint32_t bits = (q.x < thrA ? 1u : 0u) | (q.y < thrA ? 2u : 0u) | (q.z < thrA ? 4u : 0u) | (q.w < thrA ? 8u : 0u);
+                const int left = nelig - 4 * b;
+                if (left < 4) bits &= (1u << left) - 1u;
+                if (bits) atomicOr(&s_scr[8 + (b >> 3)], bits << ((b & 7) * 4));
+            }
+        }
+        __syncwarp();
+        {   // successes by draw rank -> points of this lane's mask word, appended in point order
+            uint32_t sb = 0u;
+            if (ecnt) {
+                const int w = eexcl >> 5;
+                const uint32_t lo = s_scr[8 + w], hi = w + 1 < 8 ? s_scr[8 + w + 1] : 0u;
+                sb = __funnelshift_r(lo, hi, (uint32_t)(eexcl & 31));
+                if (ecnt < 32) sb &= (1u << ecnt) - 1u;
+            }
+            const int scnt = __popc(sb);
+            const int sincl = oct_scan_incl(scnt, a);
+            const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
+            int lp = nA + sincl - scnt, seen = 0;
+            uint32_t x = elig;
+            while (sb) {
+                const int j = __ffs(sb) - 1; sb &= sb - 1;
+                while (seen < j) { x &= x - 1; seen++; }
+                const int bit = __ffs(x) - 1;
+                s_rec[FR_AM + a] |= 1u << bit;
+                s_al[lp++] = (uint8_t)(a * 32 + bit);
+            }
+            nA += stot;
+            a_chg = a_chg || stot != 0;
+        }
+        // at most one waste point: the first success over the points that are not waste, in point order
+        const uint32_t cwm = won ? (~s_rec[FR_WM + a] & feat_valid_word(p.n_waste, a)) : 0u;
+        const int ccnt = __popc(cwm);
+        const int cincl = oct_scan_incl(ccnt, a);
+        const int cexcl = cincl - ccnt;
+        const int ncand = __shfl_sync(FULLMASK, cincl, 7, 8);
+        const uint32_t k0 = (uint32_t)nelig;
+        int jstar = -1;
+        bool searching = won && ncand > 0;
+        for (int it = 0; __any_sync(FULLMASK, searching); it++) {
+            uint32_t bits = 0u;
+            if (searching) {
+                const Philox4 q = philox4x32_10((k0 >> 2) + 8u * (uint32_t)it + (uint32_t)a, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
+                bits = ((q.x < p.thr_waste ? 1u : 0u) | (q.y < p.thr_waste ? 2u : 0u) | (q.z < p.thr_waste ? 4u : 0u) | (q.w < p.thr_waste ? 8u : 0u)) << (4 * a);
+            }
+            bits = oct_or(bits);
+            const int rbase = 32 * it - (int)(k0 & 3u);                    // candidate rank of bit 0
+            if (searching) {
+                uint32_t ok = bits;
+                if (rbase < 0) ok &= 0xFFFFFFFFu << (-rbase);
+                const int lim = ncand - rbase;
+                if (lim < 32) ok &= (1u << lim) - 1u;
+                if (ok) { jstar = rbase + __ffs(ok) - 1; searching = false; }
+                else if (rbase + 32 >= ncand) searching = false;
+            }
+        }
+        if (jstar >= cexcl && jstar < cexcl + ccnt) {
+            uint32_t x = cwm;
+            for (int j = jstar - cexcl; j > 0; j--) x &= x - 1;
+            const int bit = __ffs(x) - 1;
+            s_rec[FR_WM + a] |= 1u << bit;
+            s_wl[nW] = (uint8_t)(a * 32 + bit);
+        }
+        if (jstar >= 0) { nW++; w_chg = true; }
+    } else {
+        // regrowth probability by the number of apples in the 3x3 neighbourhood, READ FROM THE LIST BEING APPENDED TO: a
+        // draw is ranked against the three thresholds (SPAWN_PROB is increasing: level 3 = below all of them) and the few
+        // ranked draws are then resolved in point order against the live mask by the lane that owns the point's word.
+        const int nblk = (nelig + 3) >> 2;
+        const int maxblk = __reduce_max_sync(FULLMASK, nblk);
+        for (int b0 = 0; b0 < maxblk; b0 += 8) {
+            const int b = b0 + a;
+            if (b < nblk) {
+                const Philox4 q = philox4x32_10((uint32_t)b, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
+                const uint32_t d[4] = { q.x, q.y, q.z, q.w };
+                uint32_t lo = 0u, hi = 0u;
 #pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) {
-        best[a] = 0xFFFFFFFFu;
-        if (a < n) {
-            const uint32_t sh = 8u * (a & 3);
-            ar[a >> 2] = (ar[a >> 2] & ~(0xFFu << sh)) | ((pos[a] & 255u) << sh);
-            ac[a >> 2] = (ac[a >> 2] & ~(0xFFu << sh)) | (((pos[a] >> 8) & 255u) << sh);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t lvl = (d[j] < p.thr_harvest[1] ? 1u : 0u) + (d[j] < p.thr_harvest[2] ? 1u : 0u) + (d[j] < p.thr_harvest[3] ? 1u : 0u);
+                    lo |= (lvl & 1u) << j; hi |= (lvl >> 1) << j;
+                }
+                const int left = nelig - 4 * b;
+                if (left < 4) { lo &= (1u << left) - 1u; hi &= (1u << left) - 1u; }
+                if (lo) atomicOr(&s_scr[8 + (b >> 3)], lo << ((b & 7) * 4));
+                if (hi) atomicOr(&s_scr[16 + (b >> 3)], hi << ((b & 7) * 4));
+            }
+        }
+        __syncwarp();
+        for (int w = 0; w < 8; w++) {
+            const uint32_t lo = s_scr[8 + w], hi = s_scr[16 + w];
+            uint32_t cwd = lo | hi;
+            while (__any_sync(FULLMASK, cwd != 0u)) {
+                bool spawned = false;
+                if (cwd) {
+                    const int kb = __ffs(cwd) - 1; cwd &= cwd - 1;
+                    const int k = w * 32 + kb;
+                    if (k >= eexcl && k < eexcl + ecnt) {
+                        uint32_t x = elig;
+                        for (int j = k - eexcl; j > 0; j--) x &= x - 1;
+                        const int bit = __ffs(x) - 1, i = a * 32 + bit;
+                        const int lvl = (int)((lo >> kb) & 1u) + 2 * (int)((hi >> kb) & 1u);
+                        int num = 0;
+                        for (int q = 0; q < p.nwa; q++) num += __popc(s_rec[FR_AM + q] & __ldg(p.nbr_mask + (size_t)i * p.nwa + q));
+                        if (min(num, 3) >= 4 - lvl) {
+                            s_rec[FR_AM + a] |= 1u << bit;
+                            s_al[nA] = (uint8_t)i;
+                            spawned = true;
+                        }
+                    }
+                }
+                if ((__ballot_sync(FULLMASK, spawned) >> obase) & 0xFFu) { nA++; a_chg = true; }
+                __syncwarp();
+            }
         }
     }
-    // Software-pipelined over the live points: the position word and the birth stamp of the NEXT point are requested before
-    // the current one is evaluated, so the kernel's longest-latency loads (20 % of its stall samples when they sat in the
-    // chain) overlap the key updates.
-    const int nw = (npts + 31) >> 5;
-    int w = 0;
-    uint32_t m = nw > 0 ? mask[0] : 0u;
-    int i_nx = -1; uint32_t prc_nx = 0, st_nx = 0;
-    auto fetch_next = [&]() {
-        while (m == 0u && ++w < nw) m = mask[w * FEAT_THREADS];
-        if (m) {
-            const int b = __ffs(m) - 1; m &= m - 1;
-            i_nx = w * 32 + b;
-            prc_nx = __ldg(rc + i_nx);
-            st_nx = stamp[(size_t)i_nx * E + env];
-        } else i_nx = -1;
-    };
-    fetch_next();
-    while (i_nx >= 0) {
-        const int i = i_nx; const uint32_t prc = prc_nx;
-        const uint32_t base = (st_nx << 8) | (uint32_t)i;
-        fetch_next();
-        const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
-        const uint32_t d[2] = { __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]), __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]) };
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a >= n) continue;
-            const uint32_t key = __byte_perm(d[a >> 2], 0u, 0x0444u | ((uint32_t)(a & 3) << 12)) | base;   // distance -> byte 3
-            best[a] = min(best[a], key);
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) out_rc[a] = (a < n && best[a] != 0xFFFFFFFFu) ? (uint32_t)__ldg(rc + (best[a] & 255u)) : 0u;   // sentinel [0, 0]
-}
+    __syncwarp();
 
-// feature rows of all agents -> global memory.  Every thread stores its env's n rows itself (F float64 each, 16-byte
-// stores): a row is one contiguous 160 / 208-byte run, an env's n rows are contiguous, and the L2 merges the sectors a warp's
-// stores touch.  (Round 1 transposed the rows through a warp-private shared tile so that every store instruction wrote one
-// contiguous row: 32 x n predicated store iterations per warp — 16 % of the kernel's instructions.)
-__device__ __forceinline__ void feat_write_obs(const FeatParams& p, bool mine, int env, double* obs, const uint32_t* pos,
-                                               const uint32_t* ca, const uint32_t* cw, const int* close5, const int* cleaned,
-                                               int n_cur_apple, int n_cur_waste)
-{
-    if (!mine) return;
-    const int n = p.n, F = p.F;
-    const int cp0 = n > 1 ? 1 : 0;
-    const bool cleanup = p.kind == SSD_ENV_CLEANUP_FEATURES;
-    const bool even = (F & 1) == 0;                                   // rows are 16-byte aligned iff F is even
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) {
-        if (a >= n) continue;
-        double v[FEAT_MAXF];                                          // fully unrolled below: stays in registers
-        const uint32_t me = pos[a], other = pos[a == 0 ? cp0 : 0];    // compute_closest_pos quirk
-        v[0] = (double)(me & 255u); v[1] = (double)((me >> 8) & 255u); v[2] = (double)((me >> 16) & 3u);
+    // ---- observations: closest apple / waste (cleanup), apples within the radius (harvest)
+    uint32_t ar[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu }, ac[2] = { 0x7F7F7F7Fu, 0x7F7F7F7Fu };
+    {
+        const uint32_t sh = 8u * (uint32_t)(a & 3);
+        const bool lo4 = a < 4, on = a < n;
+        const uint32_t rr = on ? (pos & 255u) : 0x7Fu, cc = on ? ((pos >> 8) & 255u) : 0x7Fu;
+        ar[0] = oct_or(lo4 ? rr << sh : 0u); ar[1] = oct_or(lo4 ? 0u : rr << sh);
+        ac[0] = oct_or(lo4 ? cc << sh : 0u); ac[1] = oct_or(lo4 ? 0u : cc << sh);
+    }
+    const uint32_t ca = oct_closest(s_al, nA, s_arc, ar, ac, n > 4, a);
+    uint32_t cw = 0u; int close5 = 0;
+    if (CLEANUP) cw = oct_closest(s_wl, nW, s_wrc, ar, ac, n > 4, a);
+    else {
+        const uint32_t* row = p.near5 + (size_t)feat_cell(p, pos) * p.nwa;
+        for (int q = 0; q < p.nwa; q++) close5 += __popc(s_rec[FR_AM + q] & __ldg(row + q));
+    }
+    const uint32_t other = __shfl_sync(FULLMASK, pos, a == 0 ? (n > 1 ? 1 : 0) : 0, 8);       // compute_closest_pos quirk
+    uint32_t cl_lo = 0u, cl_hi = 0u;                                       // cleaned_squares of every agent, one per byte
+    if (CLEANUP) {
+        cl_lo = oct_or(a < 4 ? (uint32_t)cleaned << (8 * a) : 0u);
+        cl_hi = oct_or(a < 4 ? 0u : (uint32_t)cleaned << (8 * (a - 4)));
+    }
+    if (io.obs && active && a < n) {
+        double v[FEAT_MAXF];
+        v[0] = (double)(pos & 255u); v[1] = (double)((pos >> 8) & 255u); v[2] = (double)((pos >> 16) & 3u);
         v[3] = (double)(other & 255u); v[4] = (double)((other >> 8) & 255u); v[5] = (double)((other >> 16) & 3u);
-        v[6] = (double)(ca[a] >> 8); v[7] = (double)(ca[a] & 255u);
-        if (cleanup) {
-            v[8] = (double)(cw[a] >> 8); v[9] = (double)(cw[a] & 255u); v[10] = (double)n_cur_apple; v[11] = (double)n_cur_waste;
+        v[6] = (double)(ca >> 8); v[7] = (double)(ca & 255u);
+        if (CLEANUP) {
+            v[8] = (double)(cw >> 8); v[9] = (double)(cw & 255u); v[10] = (double)nA; v[11] = (double)nW;
 #pragma unroll
-            for (int i = 0; i < SSD_MAXN; i++) v[12 + i] = i < n ? (double)cleaned[i] : 0.0;
+            for (int i = 0; i < SSD_MAXN; i++) v[12 + i] = (double)(((i < 4 ? cl_lo : cl_hi) >> (8 * (i & 3))) & 255u);
 #pragma unroll
             for (int i = 20; i < FEAT_MAXF; i++) v[i] = 0.0;
         } else {
-            v[8] = (double)close5[a]; v[9] = (double)n_cur_apple;
+            v[8] = (double)close5; v[9] = (double)nA;
 #pragma unroll
             for (int i = 10; i < FEAT_MAXF; i++) v[i] = 0.0;
         }
-        double* o = obs + ((size_t)env * n + a) * F;
-        if (even) {
+        const int F = p.F;
+        double* o = io.obs + ((size_t)env * n + a) * F;
+        if ((F & 1) == 0) {                                                // rows are 16-byte aligned iff F is even
 #pragma unroll
             for (int k = 0; k < FEAT_MAXF; k += 2) if (k < F) reinterpret_cast<double2*>(o)[k >> 1] = make_double2(v[k], v[k + 1]);
         } else {
@@ -262,302 +617,68 @@ __device__ __forceinline__ void feat_write_obs(const FeatParams& p, bool mine, i
             for (int k = 0; k < FEAT_MAXF; k++) if (k < F) o[k] = v[k];
         }
     }
-}
 
-struct FeatState {      // per-thread scalars
-    uint32_t next_apple, next_waste, episode;
-    int t, n_cur_apple, n_cur_waste;
-};
-
-__device__ __forceinline__ int feat_popcount_mask(const uint32_t* m, int npts)
-{
-    int c = 0;
-    for (int w = 0; w < ((npts + 31) >> 5); w++) c += __popc(m[w * FEAT_THREADS]);
-    return c;
-}
-
-// reset of one env by its thread (cleanup_features.py:256-284 / harvest_features.py:289-336 + two_stage_train.py:159-187)
-__device__ __forceinline__ void feat_reset_env(const FeatParams& p, int env, uint32_t* am, uint32_t* wm, uint32_t (&pos)[SSD_MAXN],
-                                               uint32_t (&ca)[SSD_MAXN], uint32_t (&cw)[SSD_MAXN], int (&close5)[SSD_MAXN],
-                                               int& n_cur_apple, int& n_cur_waste)
-{
-    const int n = p.n;
-    {
-        const uint32_t c3 = p.counters[(size_t)3 * p.E + env];
-        const uint32_t episode = (c3 & 0x80000000u) ? (c3 & 0x7fffffffu) + 1u : 0u;
-        const uint32_t env_id = p.first_env_id + (uint32_t)env;
-        // initialize_arrays
-        uint32_t next_apple = 1u, next_waste = 1u;
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) { am[w * FEAT_THREADS] = 0u; wm[w * FEAT_THREADS] = 0u; }
-        if (p.kind == SSD_ENV_CLEANUP_FEATURES) {
-            for (int i = 0; i < p.n_waste; i++)
-                if (__ldg(p.waste_start + i)) { mask_set(wm, i); p.waste_stamp[(size_t)i * p.E + env] = (uint16_t)next_waste++; n_cur_waste++; }
-        } else {
-            for (int i = 0; i < p.n_apple; i++) { mask_set(am, i); p.apple_stamp[(size_t)i * p.E + env] = (uint16_t)next_apple++; n_cur_apple++; }
+    // ---- rewards, contract transfers (contract_list.py:22-27,45-54), redistribution (two_stage_train.py:71-92)
+    const int t_new = doreset ? 0 : (int)s_rec[FR_T] + 1;
+    if (!RESET_ONLY) {
+        double rew = (double)reward, tr = 0.0, total = 0.0;
+        if (stepping && a < n) {
+            if (p.contract == SSD_CONTRACT_CLEANUP) tr = __dmul_rn(-theta, (double)cleaned);
+            else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr = (close5 < 4 && eaten_close > 0) ? theta : 0.0;
         }
-        // initialize_players: agent a takes the spawn point with the (a+1)-th smallest (key, index).  Every key is drawn
-        // once (one Philox block per four points) and inserted into a sorted list of the n smallest.
-        {
-            uint32_t bk[SSD_MAXN]; int bj[SSD_MAXN];
-#pragma unroll
-            for (int q = 0; q < SSD_MAXN; q++) { bk[q] = 0xffffffffu; bj[q] = 0x7fffffff; }
-            Philox4 blk = { 0, 0, 0, 0 };
-            for (int j = 0; j < p.n_spawn; j++) {
-                if ((j & 3) == 0) blk = draw_block(p.seed, env_id, episode, 0u, SITE_FEAT_ORDER, 0u, (uint32_t)(j >> 2));
-                uint32_t kk = pick(blk, (uint32_t)j & 3u); int jj = j;
-#pragma unroll
-                for (int q = 0; q < SSD_MAXN; q++) {                 // insertion: (kk, jj) sinks to its place, the rest shift down
-                    const bool less = kk < bk[q] || (kk == bk[q] && jj < bj[q]);
-                    const uint32_t tk = bk[q]; const int tj = bj[q];
-                    if (less) { bk[q] = kk; bj[q] = jj; kk = tk; jj = tj; }
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) {
-                if (a >= n) continue;
-                const uint32_t rc = __ldg(p.spawn_rc + bj[a]);
-                const uint32_t o = draw_u32(p.seed, env_id, episode, 0u, SITE_FEAT_ROT, (uint32_t)a, 0u) >> 30;
-                pos[a] = (rc >> 8) | ((rc & 255u) << 8) | (o << 16);
+        // (all transfers +-0: the loop below would leave every reward as it is — x - +-0 = x, x + +-0 / (n - 1) = x for x >= +0)
+        if (p.contract != SSD_CONTRACT_NONE && __any_sync(FULLMASK, tr != 0.0)) {
+            const double share = __ddiv_rn(tr, (double)(n - 1));
+            for (int i = 0; i < n; i++) {
+                const double tri = shfl_f64(tr, i), shi = shfl_f64(share, i);
+                total = __dadd_rn(total, tri);
+                rew = i == a ? __dsub_rn(rew, tri) : __dadd_rn(rew, shi);
             }
         }
-        FeatDraws dr = { p.seed, env_id, episode, 0u, 0xffffffffu, { 0, 0, 0, 0 } };
-        feat_spawn(p, env, am, wm, pos, dr, next_apple, next_waste, n_cur_apple, n_cur_waste);
-        feat_closest(n, p.E, env, am, p.n_apple, p.apple_rc, p.apple_stamp, pos, ca);
-        if (p.kind == SSD_ENV_CLEANUP_FEATURES) feat_closest(n, p.E, env, wm, p.n_waste, p.waste_rc, p.waste_stamp, pos, cw);
-        else {
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) if (a < n) close5[a] = feat_count_radius5(p, am, (int)(pos[a] & 255u), (int)((pos[a] >> 8) & 255u));
-        }
-        double theta = 0.0;
-        if (p.contract != SSD_CONTRACT_NONE) {
-            const double u0 = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, SITE_CONTRACT, 0u, 0u), 1.0 / 4294967296.0);
-            const double u1 = __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, SITE_CONTRACT, 0u, 1u), 1.0 / 4294967296.0);
-            theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1)) : p.theta_low;
-        }
-        // state out
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) { p.apple_mask[(size_t)w * p.E + env] = am[w * FEAT_THREADS]; p.waste_mask[(size_t)w * p.E + env] = wm[w * FEAT_THREADS]; }
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a >= n) continue;
-            p.agents[(size_t)a * p.E + env] = pos[a];
-            p.sum_raw[(size_t)a * p.E + env] = 0u; p.tsum_raw[(size_t)a * p.E + env] = 0ull;
-            p.sum_tr[(size_t)a * p.E + env] = 0.0; p.tsum_tr[(size_t)a * p.E + env] = 0.0;
-        }
-        p.counters[(size_t)0 * p.E + env] = next_apple; p.counters[(size_t)1 * p.E + env] = next_waste;
-        p.counters[(size_t)2 * p.E + env] = 0u; p.counters[(size_t)3 * p.E + env] = episode | 0x80000000u;
-        p.theta[env] = theta;
-        for (int q = 0; q < 8; q++) p.metrics[(size_t)q * p.E + env] = 0.0;
-    }
-}
-
-__global__ void __launch_bounds__(FEAT_THREADS) feat_reset_kernel(const FeatParams p, const uint8_t* mask, double* obs)
-{
-    __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
-    const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
-    const bool mine = env < p.E && (!mask || mask[env]);
-    uint32_t* am = s_am + threadIdx.x; uint32_t* wm = s_wm + threadIdx.x;
-    uint32_t pos[SSD_MAXN], ca[SSD_MAXN], cw[SSD_MAXN];
-    int close5[SSD_MAXN], cleaned[SSD_MAXN];
-    int n_cur_apple = 0, n_cur_waste = 0;
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
-    if (mine) feat_reset_env(p, env, am, wm, pos, ca, cw, close5, n_cur_apple, n_cur_waste);
-    if (obs) feat_write_obs(p, mine, env, obs, pos, ca, cw, close5, cleaned,
-                            n_cur_apple, n_cur_waste);
-}
-
-#ifndef FEAT_MIN_BLOCKS
-#define FEAT_MIN_BLOCKS 4          // 128 registers: 16 warps per SM (measured best of 3..6, tools/sweep_feat.sh)
-#endif
-__global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_step_kernel(const FeatParams p, const FeatIO io)
-{
-    __shared__ uint32_t s_am[FEAT_MASK_WORDS * FEAT_THREADS], s_wm[FEAT_MASK_WORDS * FEAT_THREADS];
-    const int env = blockIdx.x * FEAT_THREADS + threadIdx.x;
-    const int n = p.n, W = p.W;
-    const bool mine = env < p.E;
-    uint32_t* am = s_am + threadIdx.x; uint32_t* wm = s_wm + threadIdx.x;
-    uint32_t pos[SSD_MAXN], ca[SSD_MAXN], cw[SSD_MAXN];
-    int close5[SSD_MAXN], cleaned[SSD_MAXN];
-    int n_cur_apple = 0, n_cur_waste = 0;
-#pragma unroll
-    for (int a = 0; a < SSD_MAXN; a++) { pos[a] = 0u; ca[a] = cw[a] = 0u; close5[a] = 0; cleaned[a] = 0; }
-    // next-step auto-reset (ssd_feat_io.auto_reset): an env that reached its horizon in the previous step starts its next
-    // episode in this one — reset observation, zero rewards, done cleared, the actions of this step ignored
-    const bool restart = mine && io.auto_reset && (int)p.counters[(size_t)2 * p.E + env] == p.horizon;
-    if (restart) {
-        feat_reset_env(p, env, am, wm, pos, ca, cw, close5, n_cur_apple, n_cur_waste);
-        for (int a = 0; a < n; a++) {
-            const size_t o = (size_t)env * n + a;
-            io.rew[o] = 0.0;
-            if (io.base_rew) io.base_rew[o] = 0.0;
-            if (io.transfers) io.transfers[o] = 0.0;
-            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = 0u;
-        }
-        if (io.done) io.done[env] = 0;
-    } else if (mine) {
-        const uint32_t env_id = p.first_env_id + (uint32_t)env;
-        uint32_t next_apple = p.counters[(size_t)0 * p.E + env], next_waste = p.counters[(size_t)1 * p.E + env];
-        int t = (int)p.counters[(size_t)2 * p.E + env];
-        const uint32_t episode = p.counters[(size_t)3 * p.E + env] & 0x7fffffffu;
-        const double theta = p.theta[env];
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) { am[w * FEAT_THREADS] = p.apple_mask[(size_t)w * p.E + env]; wm[w * FEAT_THREADS] = p.waste_mask[(size_t)w * p.E + env]; }
-        n_cur_apple = feat_popcount_mask(am, p.n_apple);
-        n_cur_waste = feat_popcount_mask(wm, p.n_waste);
-        int act[SSD_MAXN]; uint32_t claim[SSD_MAXN]; bool has[SSD_MAXN];
-        int reward[SSD_MAXN], eaten[SSD_MAXN], eaten_close[SSD_MAXN];
-        uint2 apk = make_uint2(0x04040404u, 0x04040404u);
-        const bool packed_actions = n == 8 && (reinterpret_cast<uintptr_t>(io.actions) & 7u) == 0;
-        if (packed_actions) apk = *reinterpret_cast<const uint2*>(io.actions + (size_t)env * 8);      // one 8-byte load
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            has[a] = false; claim[a] = 0u; reward[a] = eaten[a] = eaten_close[a] = 0; act[a] = 4;
-            if (a < n) {
-                pos[a] = p.agents[(size_t)a * p.E + env];
-                act[a] = packed_actions ? (int)(((a < 4 ? apk.x : apk.y) >> (8 * (a & 3))) & 255u) : (int)io.actions[(size_t)env * n + a];
-            }
-        }
-        const bool cleanup = p.kind == SSD_ENV_CLEANUP_FEATURES;
-        // stay first: highest priority (cleanup: act == 4; harvest: every act > 3)
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) if (a < n && (cleanup ? act[a] == 4 : act[a] > 3)) { claim[a] = pos[a] & 0xFFFFu; has[a] = true; }
-        // movers, in agent order: blocked by walls and by squares already claimed
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a >= n || act[a] > 3) continue;
-            int r = (int)(pos[a] & 255u), c = (int)((pos[a] >> 8) & 255u);
-            const int tr = r + (act[a] == 2 ? -1 : (act[a] == 3 ? 1 : 0)), tc = c + (act[a] == 0 ? -1 : (act[a] == 1 ? 1 : 0));
-            const uint32_t tgt = (uint32_t)tr | ((uint32_t)tc << 8);
-            bool blocked = tr < 0 || tr >= p.H || tc < 0 || tc >= W ? false : __ldg(p.wall + tr * W + tc) != 0;
-#pragma unroll
-            for (int b = 0; b < SSD_MAXN; b++) if (b < n && has[b] && claim[b] == tgt) blocked = true;
-            claim[a] = blocked ? (pos[a] & 0xFFFFu) : tgt;
-            has[a] = true;
-        }
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) if (a < n && has[a]) pos[a] = (pos[a] & 0xFFFF0000u) | claim[a];
-        // consume in move_squares insertion order: stays (agent order), then movers (agent order)
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) {
-                if (a >= n || !has[a]) continue;
-                const bool mover = act[a] <= 3;
-                if ((pass == 1) != mover) continue;
-                const int r = (int)(pos[a] & 255u), c = (int)((pos[a] >> 8) & 255u);
-                const int i = __ldg(p.apple_idx + r * W + c);
-                if (i < 0 || !mask_test(am, i)) continue;
-                reward[a] += 1;
-                if (!cleanup) {
-                    eaten[a] += 1;
-                    if (feat_count_radius5(p, am, r, c) < 4) eaten_close[a] += 1;
-                }
-                mask_clear(am, i); n_cur_apple--;
-            }
-        }
-        // rotations
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a >= n) continue;
-            uint32_t o = (pos[a] >> 16) & 3u;
-            if (act[a] == 5) o = (o + 1u) & 3u;
-            if (act[a] == 6) o = (o + 3u) & 3u;
-            pos[a] = (pos[a] & 0xFFFFu) | (o << 16);
-        }
-        // cleaning beams (cleanup_features.py:196-219): 3 rays x 6 cells incl. the agent's own, stopped by walls only
-        int dirt = 0;
-        if (cleanup) {
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) {
-                if (a >= n || (act[a] != 7 && act[a] != 8)) continue;
-                const int o = (int)((pos[a] >> 16) & 3u), o1 = (o + 1) & 3;
-                const int dr = o == 0 ? -1 : (o == 2 ? 1 : 0), dc = o == 1 ? 1 : (o == 3 ? -1 : 0);
-                const int sr = o1 == 0 ? -1 : (o1 == 2 ? 1 : 0), sc = o1 == 1 ? 1 : (o1 == 3 ? -1 : 0);
-                const int r0 = (int)(pos[a] & 255u), c0 = (int)((pos[a] >> 8) & 255u);
-                for (int b = 0; b < 3; b++) {
-                    const int br = r0 + (b == 1 ? sr : (b == 2 ? -sr : 0)), bc = c0 + (b == 1 ? sc : (b == 2 ? -sc : 0));
-                    for (int j = 0; j < 6; j++) {
-                        const int r = br + j * dr, c = bc + j * dc;
-                        if (r < 0 || r >= p.H || c < 0 || c >= W) continue;
-                        if (__ldg(p.wall + r * W + c)) break;
-                        if (act[a] == 7) {
-                            const int wi = __ldg(p.waste_idx + r * W + c);
-                            if (wi >= 0 && mask_test(wm, wi)) { mask_clear(wm, wi); n_cur_waste--; cleaned[a]++; dirt++; }
-                        }
-                    }
-                }
-            }
-        }
-        FeatDraws dr = { p.seed, env_id, episode, (uint32_t)t + 1u, 0xffffffffu, { 0, 0, 0, 0 } };
-        feat_spawn(p, env, am, wm, pos, dr, next_apple, next_waste, n_cur_apple, n_cur_waste);
-        feat_closest(n, p.E, env, am, p.n_apple, p.apple_rc, p.apple_stamp, pos, ca);
-        if (cleanup) feat_closest(n, p.E, env, wm, p.n_waste, p.waste_rc, p.waste_stamp, pos, cw);
-        else {
-#pragma unroll
-            for (int a = 0; a < SSD_MAXN; a++) if (a < n) close5[a] = feat_count_radius5(p, am, (int)(pos[a] & 255u), (int)((pos[a] >> 8) & 255u));
-        }
-        t += 1;
-        // rewards, contract transfers (contract_list.py:22-27,45-54), redistribution (two_stage_train.py:71-92)
-        double r[SSD_MAXN], tr[SSD_MAXN], total = 0.0, raw = 0.0;
-        int n_eaten = 0, n_close = 0;
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            r[a] = (double)reward[a]; tr[a] = 0.0;
-            if (a >= n) continue;
-            raw = __dadd_rn(raw, r[a]);
-            n_eaten += eaten[a]; n_close += eaten_close[a];
-            if (p.contract == SSD_CONTRACT_CLEANUP) tr[a] = __dmul_rn(-theta, (double)cleaned[a]);
-            else if (p.contract == SSD_CONTRACT_HARVEST_LOCAL) tr[a] = (close5[a] < 4 && eaten_close[a] > 0) ? theta : 0.0;
-        }
-        if (p.contract != SSD_CONTRACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < SSD_MAXN; i++) {
-                if (i >= n) continue;
-                r[i] = __dsub_rn(r[i], tr[i]); total = __dadd_rn(total, tr[i]);
-                const double share = __ddiv_rn(tr[i], (double)(n - 1));
-#pragma unroll
-                for (int j = 0; j < SSD_MAXN; j++) if (j < n && j != i) r[j] = __dadd_rn(r[j], share);
-            }
-        }
-        // outputs + state
-#pragma unroll
-        for (int a = 0; a < SSD_MAXN; a++) {
-            if (a >= n) continue;
+        const int raw = oct_sum(reward), n_eaten = oct_sum(eaten), n_close = oct_sum(eaten_close);
+        if (active && a < n) {
             const size_t o = (size_t)env * n + a, so = (size_t)a * p.E + env;
-            io.rew[o] = r[a];
-            if (io.base_rew) io.base_rew[o] = (double)reward[a];
-            if (io.transfers) io.transfers[o] = tr[a];
-            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = cleanup ? (uint32_t)cleaned[a] : ((uint32_t)eaten[a] | ((uint32_t)eaten_close[a] << 8));
-            p.agents[so] = pos[a];
+            io.rew[o] = rew;
+            if (io.base_rew) io.base_rew[o] = (double)reward;
+            if (io.transfers) io.transfers[o] = tr;
+            if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = CLEANUP ? (uint32_t)cleaned : ((uint32_t)eaten | ((uint32_t)eaten_close << 8));
             // episode accumulators as fire-and-forget reductions (one add per address and step: a float64 RED rounds
-            // exactly like `x = x + y`), so no load round trip sits in the thread's dependency chain
-            if (reward[a]) {
-                red_add(p.sum_raw + so, (uint32_t)reward[a]);
-                red_add(reinterpret_cast<long long*>(p.tsum_raw + so), (long long)((unsigned long long)(t - 1) * (unsigned long long)reward[a]));
+            // exactly like `x = x + y`)
+            if (reward) {
+                red_add(p.sum_raw + so, (uint32_t)reward);
+                red_add(reinterpret_cast<long long*>(p.tsum_raw + so), (long long)((unsigned long long)(t_new - 1) * (unsigned long long)reward));
             }
-            if (r[a] != 0.0) {
-                red_add(p.sum_tr + so, r[a]);
-                red_add(p.tsum_tr + so, __dmul_rn((double)(t - 1), r[a]));
+            if (rew != 0.0) {
+                red_add(p.sum_tr + so, rew);
+                red_add(p.tsum_tr + so, __dmul_rn((double)(t_new - 1), rew));
             }
         }
-#pragma unroll
-        for (int w = 0; w < FEAT_MASK_WORDS; w++) { p.apple_mask[(size_t)w * p.E + env] = am[w * FEAT_THREADS]; p.waste_mask[(size_t)w * p.E + env] = wm[w * FEAT_THREADS]; }
-        p.counters[(size_t)0 * p.E + env] = next_apple; p.counters[(size_t)1 * p.E + env] = next_waste;
-        p.counters[(size_t)2 * p.E + env] = (uint32_t)t;
-        if (dirt) red_add(p.metrics + (size_t)0 * p.E + env, (double)dirt);
-        if (raw != 0.0) red_add(p.metrics + (size_t)1 * p.E + env, raw);
-        if (p.contract != SSD_CONTRACT_NONE && total != 0.0) red_add(p.metrics + (size_t)2 * p.E + env, total);
-        if (n_eaten) red_add(p.metrics + (size_t)3 * p.E + env, (double)n_eaten);
-        if (n_close) red_add(p.metrics + (size_t)4 * p.E + env, (double)n_close);
-        // birth stamps are 16 bits (list order = stamp order decides np.argmin ties): an episode with more than 65535
-        // spawns of one kind would wrap them — flag it instead of picking a wrong closest point silently
-        if ((next_apple | next_waste) > 0xFFFFu) p.metrics[(size_t)5 * p.E + env] = 1.0;
-        if (io.done) io.done[env] = t == p.horizon ? 1 : 0;
+        if (stepping && a == 0) {
+            if (dirt) red_add(p.metrics + (size_t)0 * p.E + env, (double)dirt);
+            if (raw) red_add(p.metrics + (size_t)1 * p.E + env, (double)raw);
+            if (total != 0.0) red_add(p.metrics + (size_t)2 * p.E + env, total);
+            if (n_eaten) red_add(p.metrics + (size_t)3 * p.E + env, (double)n_eaten);
+            if (n_close) red_add(p.metrics + (size_t)4 * p.E + env, (double)n_close);
+        }
+        if (active && a == 0 && io.done) io.done[env] = (stepping && t_new == p.horizon) ? 1 : 0;
     }
-    feat_write_obs(p, mine, env, io.obs, pos, ca, cw, close5, cleaned,
-                   n_cur_apple, n_cur_waste);
+
+    // ---- state out
+    __syncwarp();
+    if (active) {
+        if (a < n) s_rec[FR_AGENT + a] = pos;
+        if (a == 0) {
+            s_rec[FR_NA] = (uint32_t)nA; s_rec[FR_NW] = (uint32_t)nW; s_rec[FR_T] = (uint32_t)t_new;
+            s_rec[FR_EPISODE] = episode | 0x80000000u;
+            s_rec[FR_THETA] = (uint32_t)__double2loint(theta); s_rec[FR_THETA + 1] = (uint32_t)__double2hiint(theta);
+        }
+    }
+    __syncwarp();
+    if (active) {
+        *reinterpret_cast<uint4*>(grec + 4 * a) = *reinterpret_cast<const uint4*>(s_rec + 4 * a);
+        if (a_chg) for (int j = a; j * 16 < nA; j += 8) *reinterpret_cast<uint4*>(glist + 16 * j) = *reinterpret_cast<const uint4*>(s_al + 16 * j);
+        if (w_chg) for (int j = a; j * 16 < nW; j += 8) *reinterpret_cast<uint4*>(glist + p.LA + 16 * j) = *reinterpret_cast<const uint4*>(s_wl + 16 * j);
+    }
 }
 
 // metrics [E][40]: dirt, raw, transfers, apples, low_density, 0, 0, 0, sum_raw[8], tsum_raw[8], sum_tr[8], tsum_tr[8]
@@ -566,7 +687,7 @@ __global__ void feat_get_metrics_kernel(const FeatParams p, double* out)
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     double* o = out + (size_t)env * 40;
-    for (int q = 0; q < 8; q++) o[q] = q < 6 ? p.metrics[(size_t)q * p.E + env] : 0.0;        // [5]: err_flags
+    for (int q = 0; q < 8; q++) o[q] = q < 6 ? p.metrics[(size_t)q * p.E + env] : 0.0;        // [5]: err_flags (unused: no wrapping stamps any more)
     for (int a = 0; a < SSD_MAXN; a++) {
         const bool v = a < p.n;
         const size_t so = (size_t)a * p.E + env;
@@ -579,26 +700,27 @@ __global__ void feat_get_state_kernel(const FeatParams p, int32_t* pos, int32_t*
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
+    const uint32_t* rec = p.rec + (size_t)env * FR_WORDS;
     for (int a = 0; a < p.n; a++) {
-        const uint32_t v = p.agents[(size_t)a * p.E + env];
+        const uint32_t v = rec[FR_AGENT + a];
         if (pos) { pos[((size_t)env * p.n + a) * 2] = (int)(v & 255u); pos[((size_t)env * p.n + a) * 2 + 1] = (int)((v >> 8) & 255u); }
         if (ori) ori[(size_t)env * p.n + a] = (int)((v >> 16) & 3u);
     }
     if (cells) {
         uint8_t* c = cells + (size_t)env * p.H * p.W;
         for (int i = 0; i < p.H * p.W; i++) c[i] = 0;
-        for (int i = 0; i < p.n_apple; i++)
-            if ((p.apple_mask[(size_t)(i >> 5) * p.E + env] >> (i & 31)) & 1u) { const uint32_t rc = p.apple_rc[i]; c[(rc >> 8) * p.W + (rc & 255u)] = 1; }
-        for (int i = 0; i < p.n_waste; i++)
-            if ((p.waste_mask[(size_t)(i >> 5) * p.E + env] >> (i & 31)) & 1u) { const uint32_t rc = p.waste_rc[i]; c[(rc >> 8) * p.W + (rc & 255u)] = 2; }
+        // the lists are the state of record (the masks mirror them)
+        const uint8_t* al = p.lists + (size_t)env * p.LS; const uint8_t* wl = al + p.LA;
+        for (int i = 0; i < (int)rec[FR_NA]; i++) { const uint32_t rc = p.apple_rc[al[i]]; c[(rc >> 8) * p.W + (rc & 255u)] = 1; }
+        for (int i = 0; i < (int)rec[FR_NW]; i++) { const uint32_t rc = p.waste_rc[wl[i]]; c[(rc >> 8) * p.W + (rc & 255u)] = 2; }
     }
-    if (theta) theta[env] = p.theta[env];
-    if (t) t[env] = (int)p.counters[(size_t)2 * p.E + env];
+    if (theta) theta[env] = *reinterpret_cast<const double*>(rec + FR_THETA);
+    if (t) t[env] = (int)rec[FR_T];
 }
 __global__ void feat_set_theta_kernel(const FeatParams p, const double* theta)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env < p.E) p.theta[env] = theta[env];
+    if (env < p.E) *reinterpret_cast<double*>(p.rec + (size_t)env * FR_WORDS + FR_THETA) = theta[env];
 }
 __global__ void feat_random_actions_kernel(const FeatParams p, uint32_t step_index, uint32_t* counter, int num_actions, uint8_t* actions)
 {

@@ -1,0 +1,114 @@
+"""CleanupFeatures / HarvestFeatures (cleanup_features.py:156-284, harvest_features.py:173-336) on the CUDA path vs the C
+oracle on seeded random rollouts: every output and the full state, bit by bit, over whole episodes, with masked resets and
+the next-step auto-reset, for agent counts that fill an octet (8) and that do not (2, 4, 5), batches that do not fill
+their last warp, and short horizons that force many episode boundaries."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _maps(kind):
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    return CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP
+
+
+def _contract(kind):
+    return "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+
+
+def _compare_state(env, orc, ctx):
+    st, so = env.get_state(), orc.get_state()
+    for k in ("pos", "ori", "cells", "theta", "t"):
+        gu.assert_same(k, st[k].cpu().numpy(), so[k], ctx)
+
+
+def _compare_step(env, o, ctx):
+    gu.assert_same("obs", env.obs.cpu().numpy(), o["obs"], ctx)
+    gu.assert_same("rew", env.rew.cpu().numpy(), o["rew"], ctx)
+    gu.assert_same("base_rew", env.base_rew.cpu().numpy(), o["base_rew"], ctx)
+    gu.assert_same("transfers", env.transfers.cpu().numpy(), o["transfers"], ctx)
+    gu.assert_same("info", env.info.cpu().numpy()[..., :2].astype(np.int32), o["info"][..., :2], ctx)
+    gu.assert_same("done", env.done.cpu().numpy(), o["done"], ctx)
+
+
+@pytest.mark.parametrize("kind,n,E,steps,horizon,contract", [
+    ("cleanup", 8, 203, 260, 1000, True),
+    ("cleanup", 5, 67, 200, 1000, True),
+    ("cleanup", 2, 64, 200, 1000, False),
+    ("harvest", 8, 203, 260, 1000, True),
+    ("harvest", 4, 130, 200, 1000, True),
+    ("harvest", 2, 33, 150, 1000, False),
+])
+def test_feature_rollout_matches_oracle(oracle_lib, kind, n, E, steps, horizon, contract):
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    c = _contract(kind) if contract else None
+    env = BatchedFeatureEnv(kind, E, n, horizon=horizon, contract=c, seed=4242, first_env_id=1000)
+    orc = oracle_lib.FeatOracle(kind, E, n, _maps(kind), horizon=horizon, contract=c, seed=4242, first_env_id=1000)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    _compare_state(env, orc, "reset")
+    rng = np.random.default_rng(7)
+    nact = 9 if kind == "cleanup" else 8
+    for t in range(steps):
+        a = rng.integers(0, nact, size=(E, n))
+        if t % 3 == 0:                               # bursts of cleaning / eating so that list removals are frequent
+            a[rng.random((E, n)) < 0.4] = 7 if kind == "cleanup" else rng.integers(0, 4)
+        o = orc.step(a)
+        env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        ctx = "%s n=%d step %d" % (kind, n, t)
+        _compare_step(env, o, ctx)
+        if t % 10 == 0 or t == steps - 1:
+            _compare_state(env, orc, ctx)
+        if t % 50 == 49:                             # masked reset of a third of the envs mid-episode
+            m = (rng.random(E) < 0.33).astype(np.uint8)
+            want = orc.reset(m)
+            got = env.reset(torch.as_tensor(m).cuda()).cpu().numpy()
+            sel = m.astype(bool)
+            gu.assert_same("masked reset obs", got[sel], want[sel], ctx)
+            _compare_state(env, orc, ctx + " after masked reset")
+    gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
+
+
+@pytest.mark.parametrize("kind,n", [("cleanup", 8), ("harvest", 8), ("cleanup", 4)])
+def test_feature_auto_reset_matches_oracle(oracle_lib, kind, n):
+    """Short horizon + ssd_feat_io.auto_reset: an env that finished is reset by the next step call (its actions ignored,
+    zero rewards, done cleared).  One single-env oracle per env: a finished one is reset instead of stepped."""
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    E, horizon = 41, 23
+    c = _contract(kind)
+    env = BatchedFeatureEnv(kind, E, n, horizon=horizon, contract=c, seed=99, first_env_id=5)
+    orcs = [oracle_lib.FeatOracle(kind, 1, n, _maps(kind), horizon=horizon, contract=c, seed=99, first_env_id=5 + i) for i in range(E)]
+    env.reset()
+    for o in orcs:
+        o.reset()
+    rng = np.random.default_rng(3)
+    nact = 9 if kind == "cleanup" else 8
+    done_prev = np.zeros(E, bool)
+    for t in range(100):
+        a = rng.integers(0, nact, size=(E, n))
+        if t == 7:                                   # stagger the episodes
+            m = (np.arange(E) % 3 == 0).astype(np.uint8)
+            for i in np.nonzero(m)[0]:
+                orcs[i].reset()
+            env.reset(torch.as_tensor(m).cuda())
+            done_prev[m.astype(bool)] = False
+        env.step(torch.as_tensor(a.astype(np.uint8)).cuda(), auto_reset=True)
+        got = {k: getattr(env, k).cpu().numpy() for k in ("obs", "rew", "base_rew", "transfers", "done")}
+        st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+        for i in range(E):
+            ctx = "%s auto-reset step %d env %d" % (kind, t, i)
+            if done_prev[i]:
+                gu.assert_same("restart obs", got["obs"][i], orcs[i].reset()[0], ctx)
+                assert not got["rew"][i].any() and not got["base_rew"][i].any() and not got["transfers"][i].any() and got["done"][i] == 0, ctx
+            else:
+                o = orcs[i].step(a[i][None])
+                for k in ("obs", "rew", "base_rew", "transfers", "done"):
+                    gu.assert_same(k, got[k][i], o[k][0], ctx)
+            so = orcs[i].get_state()
+            for k in ("pos", "ori", "cells", "theta", "t"):
+                gu.assert_same(k, st[k][i], so[k][0], ctx)
+        done_prev = got["done"].astype(bool)
