@@ -522,7 +522,16 @@ static int setup_features(ssd_handle* h)
                        : q == 2 ? (const void*)feat_kernel<false, false> : (const void*)feat_kernel<false, true>;
         CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->feat_smem));
     }
-    h->grid_blocks = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
+    // persistent CTAs: as many as are resident at once (a warp takes four envs per round)
+    {
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(h, cudaGetDevice(&dev));
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const void* fn = cleanup ? (const void*)feat_kernel<true, false> : (const void*)feat_kernel<false, false>;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FEAT_THREADS, (size_t)h->feat_smem));
+        const int groups = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
+        h->grid_blocks = std::max(1, std::min(groups, sms * std::max(per_sm, 1)));
+    }
     return SSD_OK;
 }
 

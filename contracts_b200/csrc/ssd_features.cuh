@@ -125,8 +125,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // list.remove() of every entry whose point left the presence mask m[0..7], in place (order kept).  Lane a takes words a,
 // a + 8, ... of the list (4 entries each); a round's reads finish before its writes, and writes never pass the round's
-// own read positions.  Octets with need == false keep their list.  Returns the new length (octet-uniform).
-__device__ __forceinline__ int oct_compact(uint8_t* list, int L, bool need, const uint32_t* m, int a)
+// own read positions.  Octets with need == false keep their list.  Returns the new length (octet-uniform).  (Not inlined: see oct_closest.)
+__device__ __noinline__ int oct_compact(uint8_t* list, int L, bool need, const uint32_t* m, int a)
 {
     const int Leff = need ? L : 0;
     const int Lmax = __reduce_max_sync(FULLMASK, Leff);
@@ -158,13 +158,14 @@ __device__ __forceinline__ int oct_compact(uint8_t* list, int L, bool need, cons
 // compute_closest_*: for agent a (left in lane a) the entry of the list with the smallest (L1 distance, list position);
 // returns its row << 8 | col, or 0 — the reference's [0, 0] sentinel — for an empty list.  ar / ac: the agents' rows /
 // columns packed one per byte (agents 0-3, 4-7); absent agents sit at (127, 127) so that no byte sum carries.
-__device__ __forceinline__ uint32_t oct_closest(const uint8_t* list, int L, const uint16_t* rc, const uint32_t (&ar)[2],
-                                                const uint32_t (&ac)[2], bool n_gt4, int a)
+// A key is 16 bits (distance << 8 | list position), two agents share a register: one PRMT builds a pair of keys and one
+// VIMNMX.U16x2 takes both minima.  (Not inlined: the cleanup kernel calls it for both lists and its hot path should stay
+// inside the instruction cache.)
+__device__ __noinline__ uint32_t oct_closest(const uint8_t* list, int L, const uint16_t* rc, uint32_t ar0, uint32_t ar1,
+                                             uint32_t ac0, uint32_t ac1, bool n_gt4, int a)
 {
     const int Lmax = __reduce_max_sync(FULLMASK, L);
-    uint32_t best[8];
-#pragma unroll
-    for (int g = 0; g < 8; g++) best[g] = 0xFFFFu;
+    uint32_t b01 = 0xFFFFFFFFu, b23 = 0xFFFFFFFFu, b45 = 0xFFFFFFFFu, b67 = 0xFFFFFFFFu;
     for (int w0 = 0; w0 * 4 < Lmax; w0 += 8) {
         const int wi = w0 + a;
         if (wi * 4 >= L) continue;                               // (no collectives inside the loop)
@@ -175,39 +176,34 @@ __device__ __forceinline__ uint32_t oct_closest(const uint8_t* list, int L, cons
             const uint32_t prc = rc[(e4 >> (8 * j)) & 255u];
             const uint32_t pr4 = __byte_perm(prc, 0u, 0x1111), pc4 = __byte_perm(prc, 0u, 0x0000);   // row / col in every byte
             const bool live = (int)pos < L;
-            uint32_t d0 = __vabsdiffu4(pr4, ar[0]) + __vabsdiffu4(pc4, ac[0]);
+            uint32_t d0 = __vabsdiffu4(pr4, ar0) + __vabsdiffu4(pc4, ac0);
             if (!live) d0 = 0xFFFFFFFFu;
-#pragma unroll
-            for (int g = 0; g < 4; g++) best[g] = min(best[g], __byte_perm(d0, pos, 0x5504u | ((uint32_t)g << 4)));   // d_g << 8 | pos
+            b01 = __vminu2(b01, __byte_perm(d0, pos, 0x1404));   // (d_0 << 8 | pos) | (d_1 << 8 | pos) << 16
+            b23 = __vminu2(b23, __byte_perm(d0, pos, 0x3424));
             if (n_gt4) {
-                uint32_t d1 = __vabsdiffu4(pr4, ar[1]) + __vabsdiffu4(pc4, ac[1]);
+                uint32_t d1 = __vabsdiffu4(pr4, ar1) + __vabsdiffu4(pc4, ac1);
                 if (!live) d1 = 0xFFFFFFFFu;
-#pragma unroll
-                for (int g = 0; g < 4; g++) best[4 + g] = min(best[4 + g], __byte_perm(d1, pos, 0x5504u | ((uint32_t)g << 4)));
+                b45 = __vminu2(b45, __byte_perm(d1, pos, 0x1404));
+                b67 = __vminu2(b67, __byte_perm(d1, pos, 0x3424));
             }
         }
     }
-    // transpose-reduce: lane a ends with the minimum over the octet of best[a]
-    uint32_t b4[4], b2[2];
-    const bool h4 = (a & 4) != 0, h2 = (a & 2) != 0, h1 = (a & 1) != 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t snd = h4 ? best[j] : best[4 + j], kp = h4 ? best[4 + j] : best[j];
-        b4[j] = min(kp, __shfl_xor_sync(FULLMASK, snd, 4));
-    }
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const uint32_t snd = h2 ? b4[j] : b4[2 + j], kp = h2 ? b4[2 + j] : b4[j];
-        b2[j] = min(kp, __shfl_xor_sync(FULLMASK, snd, 2));
-    }
-    const uint32_t snd = h1 ? b2[0] : b2[1], kp = h1 ? b2[1] : b2[0];
-    const uint32_t key = min(kp, __shfl_xor_sync(FULLMASK, snd, 1));
+    // transpose-reduce: lane a ends with the minimum over the octet of agent a's key
+    const bool h4 = (a & 4) != 0, h2 = (a & 2) != 0;
+    uint32_t k0 = __vminu2(h4 ? b45 : b01, __shfl_xor_sync(FULLMASK, h4 ? b01 : b45, 4));
+    uint32_t k1 = __vminu2(h4 ? b67 : b23, __shfl_xor_sync(FULLMASK, h4 ? b23 : b67, 4));
+    uint32_t k = __vminu2(h2 ? k1 : k0, __shfl_xor_sync(FULLMASK, h2 ? k0 : k1, 2));
+    k = __vminu2(k, __shfl_xor_sync(FULLMASK, k, 1));
+    const uint32_t key = (a & 1) ? k >> 16 : k & 0xFFFFu;
     if ((key >> 8) >= 0xFFu) return 0u;                           // no live entry
     return rc[list[key & 255u]];
 }
 
 #ifndef FEAT_MIN_BLOCKS
 #define FEAT_MIN_BLOCKS 4
+#endif
+#ifndef FEAT_WASTE_DRAWS
+#define FEAT_WASTE_DRAWS 8               // waste draws evaluated together with the apple draws (more only when all of them fail)
 #endif
 
 // One launch = one step (or, RESET_ONLY, one masked reset) of every env.
@@ -224,11 +220,14 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     for (int i = threadIdx.x; i < p.n_apple; i += FEAT_THREADS) s_arc[i] = __ldg(p.apple_rc + i);
     for (int i = threadIdx.x; i < p.n_waste; i += FEAT_THREADS) s_wrc[i] = __ldg(p.waste_rc + i);
     __syncthreads();
-    const int env_raw = (blockIdx.x * FEAT_WARPS + warp) * 4 + (lane >> 3);
+    // persistent CTAs: a warp takes four envs per round
+    const int ngroups = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int env_raw = (grp * FEAT_WARPS + warp) * 4 + (lane >> 3);
     bool active = env_raw < p.E;
     const int env = active ? env_raw : p.E - 1;
     if (RESET_ONLY && mask) active = active && mask[env] != 0;
-    if (RESET_ONLY && !__any_sync(FULLMASK, active)) return;
+    if (RESET_ONLY && !__any_sync(FULLMASK, active)) continue;
 
     uint8_t* ob = fsm + p.sm_static + (size_t)(warp * 4 + (lane >> 3)) * p.oct_bytes;
     uint32_t* s_rec = reinterpret_cast<uint32_t*>(ob);
@@ -337,12 +336,22 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             wallblk = (tr < 0 || tr >= p.H || tc < 0 || tc >= p.W) ? false : __ldg(p.wall + tr * p.W + tc) != 0;
         }
         const uint32_t mv_all = __ballot_sync(FULLMASK, mover);
-        const uint32_t mv_any = (mv_all | (mv_all >> 8) | (mv_all >> 16) | (mv_all >> 24)) & 0xFFu;
-        for (int m = 0; m < n; m++) {
-            if (!((mv_any >> m) & 1u)) continue;
-            const uint32_t tgt_m = __shfl_sync(FULLMASK, tgt, m, 8);
-            const uint32_t hit = (__ballot_sync(FULLMASK, has && claim == tgt_m) >> obase) & 0xFFu;
-            if (a == m && mover) { claim = (wallblk || hit) ? (pos & 0xFFFFu) : tgt; has = true; }
+        {
+            // A mover is blocked by a wall or by a square claimed before it.  If the squares the agents WOULD claim — their
+            // own for stays and for movers facing a wall, the target for the other movers — are all distinct, nobody can be
+            // blocked by a claim; only otherwise the movers are taken one at a time.
+            const uint32_t want = (mover && !wallblk) ? tgt : (pos & 0xFFFFu);
+            const uint32_t key = (has || mover) ? (((uint32_t)obase << 16) | (want & 0xFFFFu)) : (0x80000000u | (uint32_t)lane);
+            const bool clash = __popc(__match_any_sync(FULLMASK, key)) > 1;
+            if (__any_sync(FULLMASK, clash)) {
+                const uint32_t mv_any = (mv_all | (mv_all >> 8) | (mv_all >> 16) | (mv_all >> 24)) & 0xFFu;
+                for (int m = 0; m < n; m++) {
+                    if (!((mv_any >> m) & 1u)) continue;
+                    const uint32_t tgt_m = __shfl_sync(FULLMASK, tgt, m, 8);
+                    const uint32_t hit = (__ballot_sync(FULLMASK, has && claim == tgt_m) >> obase) & 0xFFu;
+                    if (a == m && mover) { claim = (wallblk || hit) ? (pos & 0xFFFFu) : tgt; has = true; }
+                }
+            } else if (mover) { claim = want; has = true; }
         }
         if (has) pos = (pos & 0xFFFF0000u) | claim;
 
@@ -446,20 +455,42 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     if (CLEANUP) {
         const uint32_t thrA = active ? __ldg(p.thr_apple + nW) : 0u;       // compute_probabilities by the waste count
         const bool won = active && __ldg(p.waste_on + nW) != 0;
-        const int nblk = thrA ? (nelig + 3) >> 2 : 0;                      // r < 0 never holds: the draws are consumed unseen
-        const int maxblk = __reduce_max_sync(FULLMASK, nblk);
-        for (int b0 = 0; b0 < maxblk; b0 += 8) {
-            const int b = b0 + a;
-            if (b < nblk) {
+        // at most one waste point: the first success over the points that are not waste, in point order; its draws
+        // follow the apple draws in the step's stream (candidate rank j <-> draw nelig + j)
+        const uint32_t cwm = won ? (~s_rec[FR_WM + a] & feat_valid_word(p.n_waste, a)) : 0u;
+        const int ccnt = __popc(cwm);
+        const int cincl = oct_scan_incl(ccnt, a);
+        const int cexcl = cincl - ccnt;
+        const int ncand = __shfl_sync(FULLMASK, cincl, 7, 8);
+        const int k0 = nelig;
+        // ONE pass over the Philox blocks: the apple blocks (when the apple probability is not 0 — otherwise r < 0 never
+        // holds and the draws are consumed unseen) and, with them, the blocks of the first FEAT_WASTE_DRAWS waste draws
+        const int nblk_a = thrA ? (nelig + 3) >> 2 : 0;
+        const bool wsearch = won && ncand > 0;
+        const int bw0 = k0 >> 2;                                           // block of the first waste draw
+        const int bw1 = wsearch ? ((k0 + min(ncand, FEAT_WASTE_DRAWS) + 3) >> 2) : 0;   // end of the first waste blocks
+        const int bstart = thrA ? 0 : bw0, bend = max(nblk_a, bw1);
+        const int maxcnt = __reduce_max_sync(FULLMASK, max(bend - bstart, 0));
+        uint32_t wbits = 0u;                                               // waste successes by candidate rank (< 32)
+        for (int b0 = 0; b0 < maxcnt; b0 += 8) {
+            const int b = bstart + b0 + a;
+            if (b < bend) {
                 const Philox4 q = philox4x32_10((uint32_t)b, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
-                uint32_t bits = (q.x < thrA ? 1u : 0u) | (q.y < thrA ? 2u : 0u) | (q.z < thrA ? 4u : 0u) | (q.w < thrA ? 8u : 0u);
-                const int left = nelig - 4 * b;
-                if (left < 4) bits &= (1u << left) - 1u;
-                if (bits) atomicOr(&s_scr[8 + (b >> 3)], bits << ((b & 7) * 4));
+                if (b < nblk_a) {
+                    uint32_t bits = (q.x < thrA ? 1u : 0u) | (q.y < thrA ? 2u : 0u) | (q.z < thrA ? 4u : 0u) | (q.w < thrA ? 8u : 0u);
+                    const int left = nelig - 4 * b;
+                    if (left < 4) bits &= (1u << left) - 1u;
+                    if (bits) atomicOr(&s_scr[8 + (b >> 3)], bits << ((b & 7) * 4));
+                }
+                if (wsearch && b >= bw0) {
+                    const uint32_t bits = (q.x < p.thr_waste ? 1u : 0u) | (q.y < p.thr_waste ? 2u : 0u) | (q.z < p.thr_waste ? 4u : 0u) | (q.w < p.thr_waste ? 8u : 0u);
+                    const int r0 = 4 * b - k0;                             // candidate rank of the block's first draw (>= -3)
+                    wbits |= r0 >= 0 ? (r0 < 32 ? bits << r0 : 0u) : bits >> (-r0);
+                }
             }
         }
         __syncwarp();
-        {   // successes by draw rank -> points of this lane's mask word, appended in point order
+        {   // apple successes by draw rank -> points of this lane's mask word, appended in point order
             uint32_t sb = 0u;
             if (ecnt) {
                 const int w = eexcl >> 5;
@@ -482,30 +513,29 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             nA += stot;
             a_chg = a_chg || stot != 0;
         }
-        // at most one waste point: the first success over the points that are not waste, in point order
-        const uint32_t cwm = won ? (~s_rec[FR_WM + a] & feat_valid_word(p.n_waste, a)) : 0u;
-        const int ccnt = __popc(cwm);
-        const int cincl = oct_scan_incl(ccnt, a);
-        const int cexcl = cincl - ccnt;
-        const int ncand = __shfl_sync(FULLMASK, cincl, 7, 8);
-        const uint32_t k0 = (uint32_t)nelig;
-        int jstar = -1;
-        bool searching = won && ncand > 0;
-        for (int it = 0; __any_sync(FULLMASK, searching); it++) {
+        wbits = oct_or(wbits);
+        int covered = wsearch ? min(4 * bw1 - k0, 32) : 0;                 // candidate ranks looked at so far
+        if (covered > ncand) covered = ncand;
+        if (covered < 32) wbits &= (1u << max(covered, 0)) - 1u;
+        int jstar = wbits ? __ffs(wbits) - 1 : -1;
+        bool searching = wsearch && jstar < 0 && covered < ncand;          // (1 / 2^FEAT_WASTE_DRAWS of the steps at p = 0.5)
+        while (__any_sync(FULLMASK, searching)) {
+            // eight more blocks: draws k0 + covered - ((k0 + covered) & 3) ...
+            const int d0 = k0 + covered, bb = (d0 >> 2) + a;
             uint32_t bits = 0u;
             if (searching) {
-                const Philox4 q = philox4x32_10((k0 >> 2) + 8u * (uint32_t)it + (uint32_t)a, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
+                const Philox4 q = philox4x32_10((uint32_t)bb, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
                 bits = ((q.x < p.thr_waste ? 1u : 0u) | (q.y < p.thr_waste ? 2u : 0u) | (q.z < p.thr_waste ? 4u : 0u) | (q.w < p.thr_waste ? 8u : 0u)) << (4 * a);
             }
             bits = oct_or(bits);
-            const int rbase = 32 * it - (int)(k0 & 3u);                    // candidate rank of bit 0
             if (searching) {
-                uint32_t ok = bits;
-                if (rbase < 0) ok &= 0xFFFFFFFFu << (-rbase);
+                const int skip = d0 & 3;                                   // draws of the first block that were looked at already
+                const int rbase = covered - skip;                          // candidate rank of bit 0
+                uint32_t ok = bits & (0xFFFFFFFFu << skip);
                 const int lim = ncand - rbase;
                 if (lim < 32) ok &= (1u << lim) - 1u;
                 if (ok) { jstar = rbase + __ffs(ok) - 1; searching = false; }
-                else if (rbase + 32 >= ncand) searching = false;
+                else { covered = rbase + 32; if (covered >= ncand) searching = false; }
             }
         }
         if (jstar >= cexcl && jstar < cexcl + ccnt) {
@@ -578,9 +608,9 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         ar[0] = oct_or(lo4 ? rr << sh : 0u); ar[1] = oct_or(lo4 ? 0u : rr << sh);
         ac[0] = oct_or(lo4 ? cc << sh : 0u); ac[1] = oct_or(lo4 ? 0u : cc << sh);
     }
-    const uint32_t ca = oct_closest(s_al, nA, s_arc, ar, ac, n > 4, a);
+    const uint32_t ca = oct_closest(s_al, nA, s_arc, ar[0], ar[1], ac[0], ac[1], n > 4, a);
     uint32_t cw = 0u; int close5 = 0;
-    if (CLEANUP) cw = oct_closest(s_wl, nW, s_wrc, ar, ac, n > 4, a);
+    if (CLEANUP) cw = oct_closest(s_wl, nW, s_wrc, ar[0], ar[1], ac[0], ac[1], n > 4, a);
     else {
         const uint32_t* row = p.near5 + (size_t)feat_cell(p, pos) * p.nwa;
         for (int q = 0; q < p.nwa; q++) close5 += __popc(s_rec[FR_AM + q] & __ldg(row + q));
@@ -678,6 +708,8 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         *reinterpret_cast<uint4*>(grec + 4 * a) = *reinterpret_cast<const uint4*>(s_rec + 4 * a);
         if (a_chg) for (int j = a; j * 16 < nA; j += 8) *reinterpret_cast<uint4*>(glist + 16 * j) = *reinterpret_cast<const uint4*>(s_al + 16 * j);
         if (w_chg) for (int j = a; j * 16 < nW; j += 8) *reinterpret_cast<uint4*>(glist + p.LA + 16 * j) = *reinterpret_cast<const uint4*>(s_wl + 16 * j);
+    }
+    __syncwarp();                                    // the octet's shared state is rewritten by the next round
     }
 }
 
