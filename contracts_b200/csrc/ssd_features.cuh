@@ -131,6 +131,7 @@ __device__ __noinline__ int oct_compact(uint8_t* list, int L, bool need, const u
     const int Leff = need ? L : 0;
     const int Lmax = __reduce_max_sync(FULLMASK, Leff);
     int out = 0;
+#pragma unroll 1
     for (int w0 = 0; w0 * 4 < Lmax; w0 += 8) {
         const int wi = w0 + a;
         uint32_t e4 = 0u, keep = 0u;
@@ -166,6 +167,7 @@ __device__ __noinline__ uint32_t oct_closest(const uint8_t* list, int L, const u
 {
     const int Lmax = __reduce_max_sync(FULLMASK, L);
     uint32_t b01 = 0xFFFFFFFFu, b23 = 0xFFFFFFFFu, b45 = 0xFFFFFFFFu, b67 = 0xFFFFFFFFu;
+#pragma unroll 1
     for (int w0 = 0; w0 * 4 < Lmax; w0 += 8) {
         const int wi = w0 + a;
         if (wi * 4 >= L) continue;                               // (no collectives inside the loop)
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     __syncthreads();
     // persistent CTAs: a warp takes four envs per round
     const int ngroups = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
+#pragma unroll 1
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int env_raw = (grp * FEAT_WARPS + warp) * 4 + (lane >> 3);
     bool active = env_raw < p.E;
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             if (CLEANUP) {
                 s_rec[FR_AM + a] = 0u; s_rec[FR_WM + a] = sm;
                 int o = sincl - sc;
+#pragma unroll 1
                 while (sm) { const int b = __ffs(sm) - 1; sm &= sm - 1; s_wl[o++] = (uint8_t)(a * 32 + b); }
                 nA = 0; nW = stot;
             } else {
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
 #pragma unroll
                 for (int q = 0; q < SSD_MAXN; q++) { bk[q] = 0xffffffffu; bj[q] = 0x7fffffff; }
                 Philox4 blk = { 0, 0, 0, 0 };
+#pragma unroll 1
                 for (int j = 0; j < p.n_spawn; j++) {
                     if ((j & 3) == 0) blk = draw_block(p.seed, env_id, episode, 0u, SITE_FEAT_ORDER, 0u, (uint32_t)(j >> 2));
                     uint32_t kk = pick(blk, (uint32_t)j & 3u); int jj = j;
@@ -345,6 +350,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             const bool clash = __popc(__match_any_sync(FULLMASK, key)) > 1;
             if (__any_sync(FULLMASK, clash)) {
                 const uint32_t mv_any = (mv_all | (mv_all >> 8) | (mv_all >> 16) | (mv_all >> 24)) & 0xFFu;
+#pragma unroll 1
                 for (int m = 0; m < n; m++) {
                     if (!((mv_any >> m) & 1u)) continue;
                     const uint32_t tgt_m = __shfl_sync(FULLMASK, tgt, m, 8);
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             // harvest_features.py:204-215: an eater also counts the apples within the radius of its square at the moment it
             // eats (its own apple included, earlier eaters' apples gone), so the eaters go one at a time
             uint32_t pend = __ballot_sync(FULLMASK, cand);
+#pragma unroll 1
             while (pend) {
                 const uint32_t pe = (pend >> obase) & 0xFFu, st = pe & ~(mv_all >> obase);
                 const int nxt = pe ? (st ? __ffs(st) - 1 : __ffs(pe) - 1) : -1;
@@ -411,6 +418,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             const bool fire = agent_ok && act == 7;
             if (__any_sync(FULLMASK, fire)) {
                 const uint32_t* row = p.beam_tab + ((size_t)feat_cell(p, pos) * 4 + ((pos >> 16) & 3u)) * p.nww;
+#pragma unroll 1
                 for (int w = 0; w < p.nww; w++) {
                     const uint32_t wmw = s_rec[FR_WM + w];
                     const uint32_t v = fire ? (__ldg(row + w) & wmw) : 0u;
@@ -472,6 +480,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         const int bstart = thrA ? 0 : bw0, bend = max(nblk_a, bw1);
         const int maxcnt = __reduce_max_sync(FULLMASK, max(bend - bstart, 0));
         uint32_t wbits = 0u;                                               // waste successes by candidate rank (< 32)
+#pragma unroll 1
         for (int b0 = 0; b0 < maxcnt; b0 += 8) {
             const int b = bstart + b0 + a;
             if (b < bend) {
@@ -503,8 +512,10 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
             int lp = nA + sincl - scnt, seen = 0;
             uint32_t x = elig;
+#pragma unroll 1
             while (sb) {
                 const int j = __ffs(sb) - 1; sb &= sb - 1;
+#pragma unroll 1
                 while (seen < j) { x &= x - 1; seen++; }
                 const int bit = __ffs(x) - 1;
                 s_rec[FR_AM + a] |= 1u << bit;
@@ -519,6 +530,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         if (covered < 32) wbits &= (1u << max(covered, 0)) - 1u;
         int jstar = wbits ? __ffs(wbits) - 1 : -1;
         bool searching = wsearch && jstar < 0 && covered < ncand;          // (1 / 2^FEAT_WASTE_DRAWS of the steps at p = 0.5)
+#pragma unroll 1
         while (__any_sync(FULLMASK, searching)) {
             // eight more blocks: draws k0 + covered - ((k0 + covered) & 3) ...
             const int d0 = k0 + covered, bb = (d0 >> 2) + a;
@@ -552,6 +564,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         // ranked draws are then resolved in point order against the live mask by the lane that owns the point's word.
         const int nblk = (nelig + 3) >> 2;
         const int maxblk = __reduce_max_sync(FULLMASK, nblk);
+#pragma unroll 1
         for (int b0 = 0; b0 < maxblk; b0 += 8) {
             const int b = b0 + a;
             if (b < nblk) {
@@ -570,9 +583,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             }
         }
         __syncwarp();
+#pragma unroll 1
         for (int w = 0; w < 8; w++) {
             const uint32_t lo = s_scr[8 + w], hi = s_scr[16 + w];
             uint32_t cwd = lo | hi;
+#pragma unroll 1
             while (__any_sync(FULLMASK, cwd != 0u)) {
                 bool spawned = false;
                 if (cwd) {
@@ -659,6 +674,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         // (all transfers +-0: the loop below would leave every reward as it is — x - +-0 = x, x + +-0 / (n - 1) = x for x >= +0)
         if (p.contract != SSD_CONTRACT_NONE && __any_sync(FULLMASK, tr != 0.0)) {
             const double share = __ddiv_rn(tr, (double)(n - 1));
+#pragma unroll 1
             for (int i = 0; i < n; i++) {
                 const double tri = shfl_f64(tr, i), shi = shfl_f64(share, i);
                 total = __dadd_rn(total, tri);

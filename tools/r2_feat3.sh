@@ -9,4 +9,4 @@ for v in base "$@"; do
   done
 done
 unset SSD_LIB_PATH
-bash tools/r2_prof_feat.sh ${tag}
+if [ -n "$PROF" ]; then bash tools/r2_prof_feat.sh ${tag}; fi
