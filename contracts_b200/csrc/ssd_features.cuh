@@ -116,6 +116,17 @@ __device__ __forceinline__ int feat_cell(const FeatParams& p, uint32_t pos)
     const int r = min((int)(pos & 255u), p.H - 1), c = min((int)((pos >> 8) & 255u), p.W - 1);
     return r * p.W + c;
 }
+// position of the j-th (0-based) set bit of x (x has more than j set bits)
+__device__ __forceinline__ int select_bit(uint32_t x, int j)
+{
+    int pos = 0, c;
+    c = __popc(x & 0xFFFFu); if (j >= c) { j -= c; pos += 16; x >>= 16; }
+    c = __popc(x & 0xFFu);   if (j >= c) { j -= c; pos += 8;  x >>= 8; }
+    c = __popc(x & 0xFu);    if (j >= c) { j -= c; pos += 4;  x >>= 4; }
+    c = __popc(x & 0x3u);    if (j >= c) { j -= c; pos += 2;  x >>= 2; }
+    if (j >= (int)(x & 1u)) pos += 1;
+    return pos;
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -510,14 +521,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             const int scnt = __popc(sb);
             const int sincl = oct_scan_incl(scnt, a);
             const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
-            int lp = nA + sincl - scnt, seen = 0;
-            uint32_t x = elig;
+            int lp = nA + sincl - scnt;
 #pragma unroll 1
             while (sb) {
                 const int j = __ffs(sb) - 1; sb &= sb - 1;
-#pragma unroll 1
-                while (seen < j) { x &= x - 1; seen++; }
-                const int bit = __ffs(x) - 1;
+                const int bit = select_bit(elig, j);
                 s_rec[FR_AM + a] |= 1u << bit;
                 s_al[lp++] = (uint8_t)(a * 32 + bit);
             }
@@ -551,9 +559,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             }
         }
         if (jstar >= cexcl && jstar < cexcl + ccnt) {
-            uint32_t x = cwm;
-            for (int j = jstar - cexcl; j > 0; j--) x &= x - 1;
-            const int bit = __ffs(x) - 1;
+            const int bit = select_bit(cwm, jstar - cexcl);
             s_rec[FR_WM + a] |= 1u << bit;
             s_wl[nW] = (uint8_t)(a * 32 + bit);
         }
@@ -569,47 +575,72 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             const int b = b0 + a;
             if (b < nblk) {
                 const Philox4 q = philox4x32_10((uint32_t)b, SITE_FEAT_SPAWN, tdraw, episode, p.seed, env_id);
-                const uint32_t d[4] = { q.x, q.y, q.z, q.w };
-                uint32_t lo = 0u, hi = 0u;
+                if (min(min(q.x, q.y), min(q.z, q.w)) < p.thr_harvest[3]) {        // (one block in five)
+                    const uint32_t d[4] = { q.x, q.y, q.z, q.w };
+                    uint32_t lo = 0u, hi = 0u;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t lvl = (d[j] < p.thr_harvest[1] ? 1u : 0u) + (d[j] < p.thr_harvest[2] ? 1u : 0u) + (d[j] < p.thr_harvest[3] ? 1u : 0u);
-                    lo |= (lvl & 1u) << j; hi |= (lvl >> 1) << j;
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t lvl = (d[j] < p.thr_harvest[1] ? 1u : 0u) + (d[j] < p.thr_harvest[2] ? 1u : 0u) + (d[j] < p.thr_harvest[3] ? 1u : 0u);
+                        lo |= (lvl & 1u) << j; hi |= (lvl >> 1) << j;
+                    }
+                    const int left = nelig - 4 * b;
+                    if (left < 4) { lo &= (1u << left) - 1u; hi &= (1u << left) - 1u; }
+                    if (lo) atomicOr(&s_scr[8 + (b >> 3)], lo << ((b & 7) * 4));
+                    if (hi) atomicOr(&s_scr[16 + (b >> 3)], hi << ((b & 7) * 4));
                 }
-                const int left = nelig - 4 * b;
-                if (left < 4) { lo &= (1u << left) - 1u; hi &= (1u << left) - 1u; }
-                if (lo) atomicOr(&s_scr[8 + (b >> 3)], lo << ((b & 7) * 4));
-                if (hi) atomicOr(&s_scr[16 + (b >> 3)], hi << ((b & 7) * 4));
             }
         }
         __syncwarp();
+        // The ranked draws (a few per step) are resolved by the lane that owns the point's mask word, all lanes at once.
+        // A point sees the apples of the list plus this step's spawns BELOW it (the reference appends while it iterates in
+        // point order), so the lanes iterate to the fixed point: every round only adds points the sequential loop adds too
+        // (the thresholds grow with the count), and the lowest missing point of the sequential result passes in the next one.
+        uint32_t lo_r = 0u, hi_r = 0u;                  // level bits of this lane's eligible points (bit j <-> j-th eligible point)
+        if (ecnt) {
+            const int w = eexcl >> 5;
+            const uint32_t sh = (uint32_t)(eexcl & 31);
+            lo_r = __funnelshift_r(s_scr[8 + w], w + 1 < 8 ? s_scr[8 + w + 1] : 0u, sh);
+            hi_r = __funnelshift_r(s_scr[16 + w], w + 1 < 8 ? s_scr[16 + w + 1] : 0u, sh);
+            if (ecnt < 32) { const uint32_t mk = (1u << ecnt) - 1u; lo_r &= mk; hi_r &= mk; }
+        }
+        uint32_t pending = lo_r | hi_r, mynew = 0u;
+        s_scr[a] = 0u;                                  // points spawned in this step, by mask word (elig lives in a register)
+        __syncwarp();
+        bool go = __any_sync(FULLMASK, pending != 0u);
 #pragma unroll 1
-        for (int w = 0; w < 8; w++) {
-            const uint32_t lo = s_scr[8 + w], hi = s_scr[16 + w];
-            uint32_t cwd = lo | hi;
+        while (go) {
+            bool changed = false;
+            uint32_t tmp = pending;
 #pragma unroll 1
-            while (__any_sync(FULLMASK, cwd != 0u)) {
-                bool spawned = false;
-                if (cwd) {
-                    const int kb = __ffs(cwd) - 1; cwd &= cwd - 1;
-                    const int k = w * 32 + kb;
-                    if (k >= eexcl && k < eexcl + ecnt) {
-                        uint32_t x = elig;
-                        for (int j = k - eexcl; j > 0; j--) x &= x - 1;
-                        const int bit = __ffs(x) - 1, i = a * 32 + bit;
-                        const int lvl = (int)((lo >> kb) & 1u) + 2 * (int)((hi >> kb) & 1u);
-                        int num = 0;
-                        for (int q = 0; q < p.nwa; q++) num += __popc(s_rec[FR_AM + q] & __ldg(p.nbr_mask + (size_t)i * p.nwa + q));
-                        if (min(num, 3) >= 4 - lvl) {
-                            s_rec[FR_AM + a] |= 1u << bit;
-                            s_al[nA] = (uint8_t)i;
-                            spawned = true;
-                        }
-                    }
+            while (tmp) {
+                const int j = __ffs(tmp) - 1; tmp &= tmp - 1;
+                const int bit = select_bit(elig, j), i = a * 32 + bit;
+                const int lvl = (int)((lo_r >> j) & 1u) + 2 * (int)((hi_r >> j) & 1u);
+                const uint32_t* nb = p.nbr_mask + (size_t)i * p.nwa;
+                int num = 0;
+#pragma unroll 1
+                for (int q = 0; q < p.nwa; q++) {
+                    const uint32_t below = q < a ? 0xFFFFFFFFu : (q == a ? (1u << bit) - 1u : 0u);
+                    num += __popc(__ldg(nb + q) & (s_rec[FR_AM + q] | (s_scr[q] & below)));
                 }
-                if ((__ballot_sync(FULLMASK, spawned) >> obase) & 0xFFu) { nA++; a_chg = true; }
-                __syncwarp();
+                if (min(num, 3) >= 4 - lvl) { pending &= ~(1u << j); mynew |= 1u << bit; changed = true; }
             }
+            __syncwarp();
+            if (changed) s_scr[a] = mynew;
+            __syncwarp();
+            go = __any_sync(FULLMASK, changed);
+        }
+        {   // the new apples join the list in point order
+            const int scnt = __popc(mynew);
+            const int sincl = oct_scan_incl(scnt, a);
+            const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
+            int lp = nA + sincl - scnt;
+            uint32_t m = mynew;
+#pragma unroll 1
+            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; s_al[lp++] = (uint8_t)(a * 32 + bit); }
+            s_rec[FR_AM + a] |= mynew;
+            nA += stot;
+            a_chg = a_chg || stot != 0;
         }
     }
     __syncwarp();
