@@ -32,6 +32,7 @@ struct ssd_handle {
     FeatParams fp;
     int grid_blocks;
     int feat_smem;           // dynamic shared memory of the feature-env kernels
+    int car_smem;            // dynamic shared memory of the selfdrive kernels
     int obs_blocks;          // grid of the observe kernel (persistent: CTAs per SM x SMs, or fewer for small batches)
     int logic_smem;          // dynamic shared memory of the logic kernel (cell table + per-warp mask copies)
     bool pdl;                // programmatic dependent launch of the observe / reset kernels behind the logic / observe kernels
@@ -398,7 +399,11 @@ static int setup_selfdrive(ssd_handle* h)
     if ((rc = dev_zalloc(h, E, &p.meta))) return rc;
     if ((rc = dev_zalloc(h, E, &p.t))) return rc;
     if ((rc = dev_zalloc(h, E, &p.episode))) return rc;
-    h->grid_blocks = (p.E + CAR_THREADS - 1) / CAR_THREADS;
+    p.warp_doubles = (4 * p.n * p.D + 1) / 2 * 2 + 4 * CAR_OCT_DOUBLES;
+    h->car_smem = CAR_WARPS * p.warp_doubles * (int)sizeof(double);
+    CUDA_TRY(h, cudaFuncSetAttribute((const void*)car_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->car_smem));
+    CUDA_TRY(h, cudaFuncSetAttribute((const void*)car_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->car_smem));
+    h->grid_blocks = (p.E + CAR_ENVS_PER_CTA - 1) / CAR_ENVS_PER_CTA;
     return SSD_OK;
 }
 
@@ -1324,7 +1329,9 @@ int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev,
     if (!h) return SSD_EINVAL;
     ON_DEVICE(h);
     REQUIRE_CAR(h);
-    car_reset_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, mask_dev, obs_dev);
+    CarIO k = {};
+    k.obs = obs_dev;
+    car_kernel<true><<<h->grid_blocks, CAR_THREADS, h->car_smem, (cudaStream_t)stream>>>(h->cp, k, mask_dev);
     return check_launch(h, "selfdrive_reset");
 }
 
@@ -1336,7 +1343,7 @@ int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream)
     if (!io->actions_dev || !io->obs_dev || !io->rew_dev) return fail(h, SSD_EINVAL, "actions_dev, obs_dev and rew_dev are required");
     if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 31)) return fail(h, SSD_EINVAL, "info_dev must be 32-byte aligned");
     CarIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
-    car_step_kernel<<<h->grid_blocks, CAR_THREADS, 0, (cudaStream_t)stream>>>(h->cp, k);
+    car_kernel<false><<<h->grid_blocks, CAR_THREADS, h->car_smem, (cudaStream_t)stream>>>(h->cp, k, nullptr);
     return check_launch(h, "selfdrive_step");
 }
 

@@ -5,19 +5,26 @@
 //       update_infos :127-149, make_new_pos_consistent :92-108 (collision_on=False)
 //   contract/contract_list.py :66-102 ; environments/two_stage_train.py :62-121, :159-187
 //
-// Mapping: the kinematics are <= 8 cars of serial float64 arithmetic per env, the output is a 2n+5-double
-// observation row per car that is a pure function of the 2n positions / velocities.  So: one THREAD per env for the
-// step logic (state is struct-of-arrays: coalesced), positions / velocities are parked in shared memory, and each warp
-// then expands the observation rows of its 32 envs with lanes = row elements, which makes the dominant HBM write
-// (n * (2n+5) * 8 B per env) contiguous.  Everything is float64 and rounds like the reference (-fmad=false).
+// Mapping (round 2): EIGHT LANES PER ENV (lane = car), four envs per warp.  The kinematics are a handful of float64
+// operations per car; the dominant cost is the 2n+5-double observation row per car (n (2n+5) 8 B per env), a pure function
+// of the 2n positions / velocities.  Round 1 ran one thread per env and expanded the rows of a warp's 32 envs with lanes =
+// row elements: 513 warp-instructions per env, most of them the flat-index bookkeeping of that expansion (0.155 ms per
+// step at 131072 envs = 23 % of HBM).  Here every lane builds its own car's row in a warp-private staging area and the
+// warp copies the four envs' rows out as one contiguous run of 16-byte stores; the cross-car parts of the step — crossing
+// order, dist_to_front, make_new_pos_consistent, the contract's redistribution — happen on a few percent of the steps and
+// run as plain scalar code on the octet's positions in shared memory.  State stays struct-of-arrays ([car][env]: a warp's
+// loads touch whole 32-byte sectors).  Everything is float64 and rounds like the reference (-fmad=false).
 #pragma once
 #include "ssd_common.cuh"
 
-#define CAR_THREADS 128
-#define CAR_STRIDE 129                  // doubles per car row in shared memory (odd: conflict-free column walks)
+#define CAR_WARPS 8
+#define CAR_THREADS (CAR_WARPS * 32)
+#define CAR_ENVS_PER_CTA (CAR_WARPS * 4)
+#define CAR_OCT_DOUBLES 24              // per octet: old positions [8], new positions [8], velocities [8]
 
 struct CarParams {
     int E, n, D, contract;
+    int warp_doubles;       // shared memory per warp: 4 n D staged observation doubles (rounded up to even) + 4 octets' scratch
     double low_bound, high_bound, start_vel, start_vel_amb, theta_low, theta_high, null_prob;
     uint32_t seed, first_env_id;
     // state, struct of arrays
@@ -48,51 +55,124 @@ __device__ __forceinline__ double car_u01(const CarParams& p, uint32_t env_id, u
     return __dmul_rn((double)draw_u32(p.seed, env_id, episode, 0u, site, 0u, idx), 1.0 / 4294967296.0);
 }
 
-// each warp writes the observation rows of its 32 envs (:244-249).  The n * D doubles of an env and the envs of a warp
-// are contiguous in `obs`, so the warp walks the 32 * n * D block with flat, fully coalesced 256-byte stores; a lane
-// tracks (env, car, element) of its flat index incrementally.
-__device__ __forceinline__ void car_write_obs(const CarParams& p, const double* s_pos, const double* s_vel, double* obs,
-                                              int env0, int lane, unsigned valid_mask)
+#define CAR_FULL 0xffffffffu
+
+// update_infos (:127-149) for the cars that crossed in this step, in index order: dist_to_front of the LAST of them stays
+// in the env; the ambulance's own crossing also sets the infos of the step.  Scalar code, identical in the octet's lanes.
+__device__ __noinline__ void car_update_infos(const CarParams& p, const double* o_new, uint32_t justm, uint32_t active_m,
+                                              uint32_t crossed, int n_crossed, double& dist, double& info2, double& info3)
 {
-    const int n = p.n, D = p.D, total = 32 * n * D;
-    double* base = obs + (size_t)env0 * n * D;
-    const int col0 = threadIdx.x & ~31;
-    int el = 0, k = 0, j = lane;                        // flat index f = (el * n + k) * D + j
-    while (j >= D) { j -= D; k++; }
-    while (k >= n) { k -= n; el++; }
-    for (int f = lane; f < total; f += 32) {
-        if ((valid_mask >> el) & 1u) {
-            const int col = col0 + el;
-            const double pk = s_pos[k * CAR_STRIDE + col];
-            double v;
-            if (j < 2) v = j == 0 ? pk : s_vel[k * CAR_STRIDE + col];
-            else if (j < 2 + 2 * n) {
-                const int q = j - 2;
-                const double x = (q < n ? s_pos : s_vel)[(q < n ? q : q - n) * CAR_STRIDE + col];
-                v = q < n ? __dsub_rn(x, pk) : x;
-            } else if (j == 2 + 2 * n) v = s_pos[col] > 0 ? 1.0 : 0.0;
-            else if (j == 3 + 2 * n) v = pk > 0 ? 1.0 : 0.0;
-            else v = 0.0;
-            base[f] = v;
+    const int n = p.n;
+    for (int k = 0; k < n; k++) {
+        if (!((justm >> k) & 1u)) continue;
+        const double nk = o_new[k];
+        double d = 0.0;
+        for (int i = 0; i < n; i++) {
+            if (i == k) continue;
+            const bool act_i = (active_m >> i) & 1u;
+            const double ni = o_new[i];
+            if (!act_i) { if (__dsub_rn(p.high_bound, nk) > d) d = __dsub_rn(__dadd_rn(p.high_bound, 1.0), nk); }
+            else if (ni > nk) { if (__dsub_rn(ni, nk) > d) d = __dsub_rn(ni, ni); }      // sic (:143)
         }
-        j += 32;
-        while (j >= D) { j -= D; k++; }
-        while (k >= n) { k -= n; el++; }
+        dist = d;
+        if (k == 0) {
+            int c0 = 0;
+            for (int i = 0; i < n_crossed; i++) if (((crossed >> (4 * i)) & 15u) == 0u) c0 = i;
+            info2 = (double)(c0 + 1); info3 = d;
+        }
     }
 }
 
-// reset of one env by its thread (self_driving_car_accelerate.py:49-79 + two_stage_train.py:159-187); leaves the new
-// positions / velocities in the thread's shared-memory columns for car_write_obs
-__device__ __forceinline__ void car_reset_env(const CarParams& p, int env, double* s_pos, double* s_vel)
+// make_new_pos_consistent (:92-108), run by ONE lane on the octet's shared positions when a crossed car stands behind the
+// car that crossed after it: the later car is put 0.01 behind, cars pushed back below 0 leave the crossing order.
+__device__ __noinline__ void car_make_consistent(const double* o_pos, double* o_new, uint32_t active_m, uint32_t& crossed, int& n_crossed)
+{
+    uint32_t pre = 0u;
+    for (int i = 0; i + 1 < n_crossed; i++) {
+        const int f = (int)((crossed >> (4 * i)) & 15u), b = (int)((crossed >> (4 * i + 4)) & 15u);
+        const bool af = (active_m >> f) & 1u, ab = (active_m >> b) & 1u;
+        const double pf = af ? o_new[f] : o_pos[f];
+        const double pb = ab ? o_new[b] : o_pos[b];
+        if (pf < pb && af && ab) {
+            const double nb = __dsub_rn(pf, 0.01);
+            o_new[b] = nb;
+            if (nb < 0) pre |= 1u << b;
+        }
+    }
+    if (pre) {
+        uint32_t kept = 0u; int m = 0;
+        for (int i = 0; i < n_crossed; i++) {
+            const uint32_t a = (crossed >> (4 * i)) & 15u;
+            if (!((pre >> a) & 1u)) { kept |= a << (4 * m); m++; }
+        }
+        crossed = kept; n_crossed = m;
+    }
+}
+
+// SelfdriveContractDistprop (contract_list.py:66-102) + redistribution (two_stage_train.py:71-92) on the step the ambulance
+// crosses: scalar code over the octet's final positions, every lane keeps its own car's reward / transfer.
+__device__ __noinline__ void car_contract(const CarParams& p, const double* o_pos, uint32_t active_m, double theta, int k,
+                                          double& rew, double& tr, double& total)
 {
     const int n = p.n;
-    {
-        const uint32_t meta = p.meta[env];
-        const uint32_t episode = (meta & 0x80000000u) ? p.episode[env] + 1u : 0u;
+    const double x0 = o_pos[0];
+    uint32_t behind = 0u;
+    double sum = 0.0, rew0 = rew;                       // rew0: car 0's running reward (meaningful in lane 0)
+    for (int i = 1; i < n; i++) {
+        const double rel = __dsub_rn(o_pos[i], x0);
+        if (rel < 0) { behind |= 1u << i; sum = __dadd_rn(sum, -rel); }
+    }
+    total = 0.0;
+    if (behind) {
+        const double v0 = __dmul_rn(theta, sum);
+        if (k == 0) tr = v0;
+        rew0 = __dsub_rn(rew0, v0); total = __dadd_rn(total, v0);
+        if (k > 0 && k < n && ((behind >> k) & 1u) && ((active_m >> k) & 1u)) {
+            const double dj = -__dsub_rn(o_pos[k], x0);
+            rew = __dadd_rn(rew, __dmul_rn(v0, __ddiv_rn(dj, sum)));
+        }
+    }
+    for (int i = 1; i < n; i++) {
+        if (!((active_m >> i) & 1u) || ((behind >> i) & 1u)) continue;
+        const double vi = __dmul_rn(theta, __dsub_rn(o_pos[i], x0));
+        if (i == k) { tr = vi; rew = __dsub_rn(rew, vi); }
+        total = __dadd_rn(total, vi);
+        rew0 = __dadd_rn(rew0, vi);
+    }
+    if (k == 0) rew = rew0;
+}
+
+// One launch = one step (or, RESET_ONLY, one masked reset) of every env.
+// Next-step auto-reset (ssd_selfdrive_io.auto_reset): an env whose episode ended in the previous step starts its next
+// episode in this one — reset observation, zero rewards, dones cleared, the actions of this step ignored.
+template <bool RESET_ONLY>
+__global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, const CarIO io, const uint8_t* __restrict__ mask)
+{
+    extern __shared__ __align__(16) double csm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, k = lane & 7, oct = lane >> 3, obase = lane & 24;
+    const int n = p.n, D = p.D, nD = n * D;
+    double* w_stage = csm + (size_t)warp * p.warp_doubles;
+    double* o_pos = w_stage + (p.warp_doubles - 4 * CAR_OCT_DOUBLES) + oct * CAR_OCT_DOUBLES;
+    double* o_new = o_pos + 8;
+    double* o_vel = o_pos + 16;
+    const int env_raw = (blockIdx.x * CAR_WARPS + warp) * 4 + oct;
+    bool live = env_raw < p.E;
+    const int env = live ? env_raw : p.E - 1;
+    if (RESET_ONLY && mask) live = live && mask[env] != 0;
+    if (RESET_ONLY && !__any_sync(CAR_FULL, live)) return;
+    const bool kv = k < n;
+    const size_t so = (size_t)k * p.E + env;
+    const uint32_t meta0 = live ? p.meta[env] : 0u;
+    const bool doreset = RESET_ONLY ? live : (live && io.auto_reset && ((meta0 >> 16) & 1u));
+    const bool stepping = !RESET_ONLY && live && !doreset;
+    double x = 0.0, v = 0.0;                            // this car's position / velocity after the step (or the reset)
+
+    if (doreset) {
+        // self_driving_car_accelerate.py:49-79 + two_stage_train.py:159-187
+        const uint32_t episode = (meta0 & 0x80000000u) ? p.episode[env] + 1u : 0u;
         const uint32_t env_id = p.first_env_id + (uint32_t)env;
-        for (int k = 0; k < n; k++) {
+        if (kv) {
             const double u = car_u01(p, env_id, episode, SITE_SELFDRIVE_RESET, (uint32_t)k);
-            double x, v;
             if (k == 0) {        // random.random() * low / 2 + low / 2  (:53)
                 x = __dadd_rn(__ddiv_rn(__dmul_rn(u, p.low_bound), 2.0), __ddiv_rn(p.low_bound, 2.0));
                 v = p.start_vel_amb;
@@ -100,200 +180,146 @@ __device__ __forceinline__ void car_reset_env(const CarParams& p, int env, doubl
                 x = __dadd_rn(__ddiv_rn(__dmul_rn(u, p.low_bound), 16.0), __ddiv_rn(__dmul_rn(p.low_bound, 3.0), 16.0));
                 v = p.start_vel;
             }
-            p.pos[(size_t)k * p.E + env] = x; p.vel[(size_t)k * p.E + env] = v;
-            s_pos[k * CAR_STRIDE + threadIdx.x] = x; s_vel[k * CAR_STRIDE + threadIdx.x] = v;
+            p.pos[so] = x; p.vel[so] = v;
         }
-        double theta = 0.0;
-        if (p.contract != SSD_CONTRACT_NONE) {       // two_stage_train.py:163-166
-            const double u0 = car_u01(p, env_id, episode, SITE_CONTRACT, 0u), u1 = car_u01(p, env_id, episode, SITE_CONTRACT, 1u);
-            theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1)) : p.theta_low;
-        }
-        p.theta[env] = theta; p.m_transfers[env] = 0.0; p.dist_front[env] = -1.0;
-        p.crossed[env] = 0u; p.meta[env] = 0x80000000u; p.t[env] = 0; p.episode[env] = episode;
-    }
-}
-
-__global__ void __launch_bounds__(CAR_THREADS) car_reset_kernel(const CarParams p, const uint8_t* mask, double* obs)
-{
-    __shared__ double s_pos[SSD_MAXN * CAR_STRIDE], s_vel[SSD_MAXN * CAR_STRIDE];
-    const int env = blockIdx.x * CAR_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool mine = env < p.E && (!mask || mask[env]);
-    if (mine) car_reset_env(p, env, s_pos, s_vel);
-    const unsigned valid = __ballot_sync(0xffffffffu, mine);
-    __syncwarp();
-    if (obs) car_write_obs(p, s_pos, s_vel, obs, env - lane, lane, valid);
-}
-
-__global__ void __launch_bounds__(CAR_THREADS) car_step_kernel(const CarParams p, const CarIO io)
-{
-    __shared__ double s_pos[SSD_MAXN * CAR_STRIDE], s_vel[SSD_MAXN * CAR_STRIDE], s_new[SSD_MAXN * CAR_STRIDE];
-    const int env = blockIdx.x * CAR_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31, tx = threadIdx.x;
-    const int n = p.n;
-    const bool mine = env < p.E;
-    // next-step auto-reset (ssd_selfdrive_io.auto_reset): an env whose episode ended in the previous step starts its next
-    // episode in this one — reset observation, zero rewards, dones cleared, the actions of this step ignored
-    const bool restart = mine && io.auto_reset && ((p.meta[env] >> 16) & 1u);
-    if (restart) {
-        car_reset_env(p, env, s_pos, s_vel);
-        for (int k = 0; k < n; k++) {
-            const size_t o = (size_t)env * n + k;
-            io.rew[o] = 0.0;
-            if (io.base_rew) io.base_rew[o] = 0.0;
-            if (io.transfers) io.transfers[o] = 0.0;
-            if (io.info) reinterpret_cast<double4*>(io.info)[o] = make_double4(0.0, 0.0, 0.0, 0.0);
-            if (io.done) io.done[(size_t)env * (n + 1) + k] = 0;
-        }
-        if (io.done) io.done[(size_t)env * (n + 1) + n] = 0;
-    } else if (mine) {
-        uint32_t meta = p.meta[env];
-        int n_crossed = (int)(meta & 0xFFu);
-        uint32_t done_mask = (meta >> 8) & 0xFFu;
-        bool all_done = (meta >> 16) & 1u;
-        uint32_t crossed = p.crossed[env];
-        const double theta = p.theta[env];
-        for (int k = 0; k < n; k++) { s_pos[k * CAR_STRIDE + tx] = p.pos[(size_t)k * p.E + env]; s_vel[k * CAR_STRIDE + tx] = p.vel[(size_t)k * p.E + env]; }
-        const uint32_t active = all_done ? 0u : (~done_mask & ((1u << n) - 1u));   // done agents stop acting (RLlib)
-        double rew[SSD_MAXN], tr[SSD_MAXN];
-        double info2 = 0.0, info3 = 0.0;
-        uint32_t just = 0u;
-#pragma unroll
-        for (int k = 0; k < SSD_MAXN; k++) { rew[k] = 0.0; tr[k] = 0.0; }
-        const int first = active ? __ffs(active) - 1 : -1;
-        if (active) {
-            p.t[env] += 1;
-            for (int k = 0; k < n; k++) {
-                double x = s_pos[k * CAR_STRIDE + tx];
-                if ((active >> k) & 1u) {
-                    const double a = (double)io.actions[(size_t)env * n + k];
-                    const double v = py_max(py_min(__dadd_rn(py_max(py_min(a, 0.1), -0.1), s_vel[k * CAR_STRIDE + tx]),
-                                                   k == 0 ? 1.0 : 0.25), 0.0);          // :172-174
-                    s_vel[k * CAR_STRIDE + tx] = v;
-                    x = __dadd_rn(v, x);                                                 // :180
-                }
-                s_new[k * CAR_STRIDE + tx] = x;
+        if (k == 0) {
+            double theta = 0.0;
+            if (p.contract != SSD_CONTRACT_NONE) {       // two_stage_train.py:163-166
+                const double u0 = car_u01(p, env_id, episode, SITE_CONTRACT, 0u), u1 = car_u01(p, env_id, episode, SITE_CONTRACT, 1u);
+                theta = (u0 > p.null_prob) ? __dadd_rn(p.theta_low, __dmul_rn(__dsub_rn(p.theta_high, p.theta_low), u1)) : p.theta_low;
             }
+            p.theta[env] = theta; p.m_transfers[env] = 0.0; p.dist_front[env] = -1.0;
+            p.crossed[env] = 0u; p.meta[env] = 0x80000000u; p.t[env] = 0; p.episode[env] = episode;
+        }
+    }
+
+    if (!RESET_ONLY) {
+        int n_crossed = (int)(meta0 & 0xFFu);
+        uint32_t done_mask = (meta0 >> 8) & 0xFFu;
+        bool all_done = (meta0 >> 16) & 1u;
+        uint32_t crossed = stepping ? p.crossed[env] : 0u;
+        const double theta = stepping ? p.theta[env] : 0.0;
+        const double pos0 = (stepping && kv) ? p.pos[so] : 0.0, vel0 = (stepping && kv) ? p.vel[so] : 0.0;
+        const uint32_t active_m = (!stepping || all_done) ? 0u : (~done_mask & ((1u << n) - 1u));   // done agents stop acting (RLlib)
+        const bool on = active_m != 0u, act = (active_m >> k) & 1u;
+        const int first = active_m ? __ffs(active_m) - 1 : -1;
+        double rew = 0.0, tr = 0.0, info2 = 0.0, info3 = 0.0;
+        double newx = pos0;
+        if (stepping) { x = pos0; v = vel0; }
+        if (act) {
+            const double a = (double)io.actions[(size_t)env * n + k];
+            v = py_max(py_min(__dadd_rn(py_max(py_min(a, 0.1), -0.1), vel0), k == 0 ? 1.0 : 0.25), 0.0);      // :172-174
+            newx = __dadd_rn(v, pos0);                                                                         // :180
+        }
+        const bool just = act && pos0 < 0.0 && newx > 0.0;
+        const uint32_t justm = (__ballot_sync(CAR_FULL, just) >> obase) & 0xFFu;
+        if (on) {
+            if (k == 0) p.t[env] += 1;
             // infos defaults (:183-189)
             int ci = -1;
             for (int i = 0; i < n_crossed; i++) if (((crossed >> (4 * i)) & 15u) == 0u) ci = i;
             info2 = ci >= 0 ? (double)(ci + 1) : (double)n;
             { const double d0 = n == 1 ? p.dist_front[env] : -1.0; info3 = d0 > -1.0 ? d0 : __dsub_rn(p.high_bound, p.low_bound); }
             // update_rel_rank (:110-125): crossers appended in index order
-            for (int k = 0; k < n; k++) {
-                if (((active >> k) & 1u) && s_pos[k * CAR_STRIDE + tx] < 0.0 && s_new[k * CAR_STRIDE + tx] > 0.0) {
-                    just |= 1u << k;
-                    crossed |= (uint32_t)k << (4 * n_crossed);
-                    n_crossed++;
-                }
+            for (uint32_t jm = justm; jm; jm &= jm - 1) { crossed |= (uint32_t)(__ffs(jm) - 1) << (4 * n_crossed); n_crossed++; }
+        }
+        o_pos[k] = pos0; o_new[k] = newx;
+        __syncwarp();
+        if (__any_sync(CAR_FULL, justm != 0u)) {                           // a few percent of the steps
+            if (justm) {
+                double dist = 0.0;
+                car_update_infos(p, o_new, justm, active_m, crossed, n_crossed, dist, info2, info3);
+                if (k == 0) p.dist_front[env] = dist;
             }
-            // update_infos (:127-149)
-            for (int k = 0; k < n; k++) {
-                if (!((just >> k) & 1u)) continue;
-                const double nk = s_new[k * CAR_STRIDE + tx];
-                double d = 0.0;
-                for (int i = 0; i < n; i++) {
-                    if (i == k) continue;
-                    const bool act_i = (active >> i) & 1u;
-                    const double ni = s_new[i * CAR_STRIDE + tx];
-                    if (!act_i) { if (__dsub_rn(p.high_bound, nk) > d) d = __dsub_rn(__dadd_rn(p.high_bound, 1.0), nk); }
-                    else if (ni > nk) { if (__dsub_rn(ni, nk) > d) d = __dsub_rn(ni, ni); }      // sic (:143)
-                }
-                p.dist_front[env] = d;
-                if (k == 0) {
-                    int c0 = 0;
-                    for (int i = 0; i < n_crossed; i++) if (((crossed >> (4 * i)) & 15u) == 0u) c0 = i;
-                    info2 = (double)(c0 + 1); info3 = d;
-                }
+        }
+        {   // make_new_pos_consistent changes something only if a crossed car stands behind its successor in the order
+            bool viol = false;
+            if (on && k + 1 < n_crossed) {
+                const int f = (int)((crossed >> (4 * k)) & 15u), b = (int)((crossed >> (4 * k + 4)) & 15u);
+                const bool af = (active_m >> f) & 1u, ab = (active_m >> b) & 1u;
+                viol = af && ab && (af ? o_new[f] : o_pos[f]) < (ab ? o_new[b] : o_pos[b]);
             }
-            // make_new_pos_consistent (:92-108)
-            uint32_t pre = 0u;
-            for (int i = 0; i + 1 < n_crossed; i++) {
-                const int f = (int)((crossed >> (4 * i)) & 15u), b = (int)((crossed >> (4 * i + 4)) & 15u);
-                const bool af = (active >> f) & 1u, ab = (active >> b) & 1u;
-                const double pf = af ? s_new[f * CAR_STRIDE + tx] : s_pos[f * CAR_STRIDE + tx];
-                const double pb = ab ? s_new[b * CAR_STRIDE + tx] : s_pos[b * CAR_STRIDE + tx];
-                if (pf < pb && af && ab) {
-                    const double nb = __dsub_rn(pf, 0.01);
-                    s_new[b * CAR_STRIDE + tx] = nb;
-                    if (nb < 0) pre |= 1u << b;
+            const uint32_t vm = __ballot_sync(CAR_FULL, viol);
+            if (vm) {
+                if ((vm >> obase) & 0xFFu) {
+                    if (k == 0) car_make_consistent(o_pos, o_new, active_m, crossed, n_crossed);
                 }
+                __syncwarp();
+                crossed = __shfl_sync(CAR_FULL, crossed, 0, 8);
+                n_crossed = __shfl_sync(CAR_FULL, n_crossed, 0, 8);
+                newx = o_new[k];
             }
-            if (pre) {
-                uint32_t kept = 0u; int m = 0;
-                for (int i = 0; i < n_crossed; i++) {
-                    const uint32_t a = (crossed >> (4 * i)) & 15u;
-                    if (!((pre >> a) & 1u)) { kept |= a << (4 * m); m++; }
-                }
-                crossed = kept; n_crossed = m;
-            }
+        }
+        if (on) {
             // new positions, rewards, dones (:216-238)
-#pragma unroll
-            for (int k = 0; k < SSD_MAXN; k++) {
-                if (k >= n) continue;
-                double x = ((active >> k) & 1u) ? s_new[k * CAR_STRIDE + tx] : s_pos[k * CAR_STRIDE + tx];
-                if ((active >> k) & 1u) rew[k] = k == 0 ? __dsub_rn(-1.0, 99.0) : -1.0;
-                if (x > p.high_bound) { x = __dadd_rn(p.high_bound, 1.0); done_mask |= 1u << k; }
-                s_pos[k * CAR_STRIDE + tx] = x;
-                p.pos[(size_t)k * p.E + env] = x; p.vel[(size_t)k * p.E + env] = s_vel[k * CAR_STRIDE + tx];
-            }
-            all_done = (active & ~done_mask) == 0u;
+            x = act ? newx : pos0;
+            if (act) rew = k == 0 ? __dsub_rn(-1.0, 99.0) : -1.0;
         }
-        double base[SSD_MAXN];
-#pragma unroll
-        for (int k = 0; k < SSD_MAXN; k++) base[k] = rew[k];
-        // SelfdriveContractDistprop (contract_list.py:66-102) + redistribution (two_stage_train.py:71-92)
-        if (p.contract == SSD_CONTRACT_SELFDRIVE_DISTPROP && (active & 1u) && (just & 1u)) {
-            const double x0 = s_pos[tx];
-            uint32_t behind = 0u;
-            double sum = 0.0;
-            for (int i = 1; i < n; i++) {
-                const double rel = __dsub_rn(s_pos[i * CAR_STRIDE + tx], x0);
-                if (rel < 0) { behind |= 1u << i; sum = __dadd_rn(sum, -rel); }
-            }
-            double total = 0.0;
-            if (behind) {
-                const double v0 = __dmul_rn(theta, sum);
-                tr[0] = v0;
-                rew[0] = __dsub_rn(rew[0], v0); total = __dadd_rn(total, v0);
-#pragma unroll
-                for (int j = 1; j < SSD_MAXN; j++)
-                    if (j < n && ((behind >> j) & 1u) && ((active >> j) & 1u)) {
-                        const double dj = -__dsub_rn(s_pos[j * CAR_STRIDE + tx], x0);
-                        rew[j] = __dadd_rn(rew[j], __dmul_rn(v0, __ddiv_rn(dj, sum)));
-                    }
-            }
-#pragma unroll
-            for (int i = 1; i < SSD_MAXN; i++) {
-                if (i >= n || !((active >> i) & 1u) || ((behind >> i) & 1u)) continue;
-                const double vi = __dmul_rn(theta, __dsub_rn(s_pos[i * CAR_STRIDE + tx], x0));
-                tr[i] = vi;
-                rew[i] = __dsub_rn(rew[i], vi); total = __dadd_rn(total, vi);
-                rew[0] = __dadd_rn(rew[0], vi);
-            }
-            p.m_transfers[env] = __dadd_rn(p.m_transfers[env], total);
+        const bool over = on && kv && x > p.high_bound;
+        if (over) x = __dadd_rn(p.high_bound, 1.0);
+        done_mask |= (__ballot_sync(CAR_FULL, over) >> obase) & 0xFFu;
+        if (on) {
+            all_done = (active_m & ~done_mask) == 0u;
+            if (kv) { p.pos[so] = x; p.vel[so] = v; }
         }
-        p.crossed[env] = crossed;
-        p.meta[env] = 0x80000000u | (uint32_t)n_crossed | (done_mask << 8) | ((all_done ? 1u : 0u) << 16);
-#pragma unroll
-        for (int k = 0; k < SSD_MAXN; k++) {
-            if (k >= n) continue;
+        const double base = rew;
+        __syncwarp();
+        o_pos[k] = x;                                                      // final positions (contract, observation rows)
+        __syncwarp();
+        const bool deal = stepping && p.contract == SSD_CONTRACT_SELFDRIVE_DISTPROP && (active_m & 1u) && (justm & 1u);
+        if (__any_sync(CAR_FULL, deal)) {
+            if (deal) {
+                double total = 0.0;
+                car_contract(p, o_pos, active_m, theta, k, rew, tr, total);
+                if (k == 0) p.m_transfers[env] = __dadd_rn(p.m_transfers[env], total);
+            }
+        }
+        if (stepping && k == 0) {
+            p.crossed[env] = crossed;
+            p.meta[env] = 0x80000000u | (uint32_t)n_crossed | (done_mask << 8) | ((all_done ? 1u : 0u) << 16);
+        }
+        if (live && kv) {                                                  // (a restarting env: zeros)
             const size_t o = (size_t)env * n + k;
-            io.rew[o] = rew[k];
-            if (io.base_rew) io.base_rew[o] = base[k];
-            if (io.transfers) io.transfers[o] = tr[k];
-            if (io.info) {
-                double4 r = make_double4(((just >> k) & 1u) ? 1.0 : 0.0, ((active >> k) & 1u) ? 1.0 : 0.0,
-                                         k == first ? info2 : 0.0, k == first ? info3 : 0.0);
-                reinterpret_cast<double4*>(io.info)[o] = r;
-            }
-            if (io.done) io.done[(size_t)env * (n + 1) + k] = (uint8_t)((done_mask >> k) & 1u);
+            io.rew[o] = rew;
+            if (io.base_rew) io.base_rew[o] = base;
+            if (io.transfers) io.transfers[o] = tr;
+            if (io.info)
+                reinterpret_cast<double4*>(io.info)[o] = stepping ? make_double4(just ? 1.0 : 0.0, act ? 1.0 : 0.0, k == first ? info2 : 0.0, k == first ? info3 : 0.0)
+                                                                  : make_double4(0.0, 0.0, 0.0, 0.0);
+            if (io.done) io.done[(size_t)env * (n + 1) + k] = stepping ? (uint8_t)((done_mask >> k) & 1u) : (uint8_t)0;
         }
-        if (io.done) io.done[(size_t)env * (n + 1) + n] = all_done ? 1 : 0;
+        if (live && k == 0 && io.done) io.done[(size_t)env * (n + 1) + n] = (stepping && all_done) ? 1 : 0;
+    } else {
+        o_pos[k] = x;
     }
-    const unsigned valid = __ballot_sync(0xffffffffu, mine);
+    o_vel[k] = v;
     __syncwarp();
-    car_write_obs(p, s_pos, s_vel, io.obs, env - lane, lane, valid);
+
+    // ---- observation rows (:244-249): [pos, vel, pos_q - pos (q < n), vel_q (q < n), pos_0 > 0, pos > 0, 0], built by the
+    // car's lane in the staging area, then copied out as one contiguous run per env
+    if (io.obs) {
+        if (kv) {
+            double* row = w_stage + (size_t)(oct * n + k) * D;
+            row[0] = x; row[1] = v;
+            for (int q = 0; q < n; q++) { row[2 + q] = __dsub_rn(o_pos[q], x); row[2 + n + q] = o_vel[q]; }
+            row[2 + 2 * n] = o_pos[0] > 0 ? 1.0 : 0.0;
+            row[3 + 2 * n] = x > 0 ? 1.0 : 0.0;
+            row[4 + 2 * n] = 0.0;
+        }
+        __syncwarp();
+        const uint32_t lv = __ballot_sync(CAR_FULL, live);
+        for (int q = 0; q < 4; q++) {
+            if (!((lv >> (8 * q)) & 1u)) continue;                        // (uniform)
+            const int e = (blockIdx.x * CAR_WARPS + warp) * 4 + q;
+            double* dst = io.obs + (size_t)e * nD;
+            const double* src = w_stage + (size_t)q * nD;
+            if ((nD & 1) == 0) {                                           // 16-byte aligned runs
+                for (int f = lane; 2 * f < nD; f += 32) reinterpret_cast<double2*>(dst)[f] = reinterpret_cast<const double2*>(src)[f];
+            } else {
+                for (int f = lane; f < nD; f += 32) dst[f] = src[f];
+            }
+        }
+    }
 }
 
 __global__ void car_random_actions_kernel(const CarParams p, uint32_t step_index, uint32_t* counter, float lo, float hi,
