@@ -17,7 +17,12 @@
 #pragma once
 #include "ssd_common.cuh"
 
+#ifndef CAR_WARPS
 #define CAR_WARPS 8
+#endif
+#ifndef CAR_MIN_BLOCKS
+#define CAR_MIN_BLOCKS 4
+#endif
 #define CAR_THREADS (CAR_WARPS * 32)
 #define CAR_ENVS_PER_CTA (CAR_WARPS * 4)
 #define CAR_OCT_DOUBLES 24              // per octet: old positions [8], new positions [8], velocities [8]
@@ -83,19 +88,22 @@ __device__ __noinline__ void car_update_infos(const CarParams& p, const double* 
     }
 }
 
-// make_new_pos_consistent (:92-108), run by ONE lane on the octet's shared positions when a crossed car stands behind the
-// car that crossed after it: the later car is put 0.01 behind, cars pushed back below 0 leave the crossing order.
-__device__ __noinline__ void car_make_consistent(const double* o_pos, double* o_new, uint32_t active_m, uint32_t& crossed, int& n_crossed)
+// make_new_pos_consistent (:92-108), run by ONE lane on the octet's effective positions (new for the acting cars, old for
+// the others) when a crossed car stands behind the car that crossed after it: the later car is put 0.01 behind, cars
+// pushed back below 0 leave the crossing order.  vmask: the pairs (i, i + 1) of the order that are inconsistent before any
+// change — a pair needs a look only if it is one of them or its front car has just been moved.
+__device__ __noinline__ void car_make_consistent(double* o_eff, uint32_t active_m, uint32_t vmask, uint32_t& crossed, int& n_crossed)
 {
     uint32_t pre = 0u;
-    for (int i = 0; i + 1 < n_crossed; i++) {
+    bool moved = false;
+    for (int i = __ffs(vmask) - 1; i + 1 < n_crossed; i++) {
+        if (!moved && !((vmask >> i) & 1u)) continue;
         const int f = (int)((crossed >> (4 * i)) & 15u), b = (int)((crossed >> (4 * i + 4)) & 15u);
-        const bool af = (active_m >> f) & 1u, ab = (active_m >> b) & 1u;
-        const double pf = af ? o_new[f] : o_pos[f];
-        const double pb = ab ? o_new[b] : o_pos[b];
-        if (pf < pb && af && ab) {
+        const double pf = o_eff[f], pb = o_eff[b];
+        moved = pf < pb && ((active_m >> f) & (active_m >> b) & 1u);
+        if (moved) {
             const double nb = __dsub_rn(pf, 0.01);
-            o_new[b] = nb;
+            o_eff[b] = nb;
             if (nb < 0) pre |= 1u << b;
         }
     }
@@ -146,7 +154,7 @@ __device__ __noinline__ void car_contract(const CarParams& p, const double* o_po
 // Next-step auto-reset (ssd_selfdrive_io.auto_reset): an env whose episode ended in the previous step starts its next
 // episode in this one — reset observation, zero rewards, dones cleared, the actions of this step ignored.
 template <bool RESET_ONLY>
-__global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, const CarIO io, const uint8_t* __restrict__ mask)
+__global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const CarParams p, const CarIO io, const uint8_t* __restrict__ mask)
 {
     extern __shared__ __align__(16) double csm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, k = lane & 7, oct = lane >> 3, obase = lane & 24;
@@ -162,7 +170,15 @@ __global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, con
     if (RESET_ONLY && !__any_sync(CAR_FULL, live)) return;
     const bool kv = k < n;
     const size_t so = (size_t)k * p.E + env;
+    // every input of the step is requested before the first of them is looked at (one memory round trip, not two)
     const uint32_t meta0 = live ? p.meta[env] : 0u;
+    uint32_t crossed_in = 0u; double theta_in = 0.0, pos_in = 0.0, vel_in = 0.0, dist_in = -1.0; float act_in = 0.0f; int t_in = 0;
+    if (!RESET_ONLY && live) {
+        crossed_in = p.crossed[env]; theta_in = p.theta[env];
+        if (kv) { pos_in = p.pos[so]; vel_in = p.vel[so]; act_in = io.actions[(size_t)env * n + k]; }
+        if (k == 0) t_in = p.t[env];
+        if (n == 1) dist_in = p.dist_front[env];
+    }
     const bool doreset = RESET_ONLY ? live : (live && io.auto_reset && ((meta0 >> 16) & 1u));
     const bool stepping = !RESET_ONLY && live && !doreset;
     double x = 0.0, v = 0.0;                            // this car's position / velocity after the step (or the reset)
@@ -197,9 +213,9 @@ __global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, con
         int n_crossed = (int)(meta0 & 0xFFu);
         uint32_t done_mask = (meta0 >> 8) & 0xFFu;
         bool all_done = (meta0 >> 16) & 1u;
-        uint32_t crossed = stepping ? p.crossed[env] : 0u;
-        const double theta = stepping ? p.theta[env] : 0.0;
-        const double pos0 = (stepping && kv) ? p.pos[so] : 0.0, vel0 = (stepping && kv) ? p.vel[so] : 0.0;
+        uint32_t crossed = stepping ? crossed_in : 0u;
+        const double theta = theta_in;
+        const double pos0 = stepping ? pos_in : 0.0, vel0 = stepping ? vel_in : 0.0;
         const uint32_t active_m = (!stepping || all_done) ? 0u : (~done_mask & ((1u << n) - 1u));   // done agents stop acting (RLlib)
         const bool on = active_m != 0u, act = (active_m >> k) & 1u;
         const int first = active_m ? __ffs(active_m) - 1 : -1;
@@ -207,23 +223,27 @@ __global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, con
         double newx = pos0;
         if (stepping) { x = pos0; v = vel0; }
         if (act) {
-            const double a = (double)io.actions[(size_t)env * n + k];
+            const double a = (double)act_in;
             v = py_max(py_min(__dadd_rn(py_max(py_min(a, 0.1), -0.1), vel0), k == 0 ? 1.0 : 0.25), 0.0);      // :172-174
             newx = __dadd_rn(v, pos0);                                                                         // :180
         }
         const bool just = act && pos0 < 0.0 && newx > 0.0;
         const uint32_t justm = (__ballot_sync(CAR_FULL, just) >> obase) & 0xFFu;
         if (on) {
-            if (k == 0) p.t[env] += 1;
+            if (k == 0) p.t[env] = t_in + 1;
             // infos defaults (:183-189)
-            int ci = -1;
-            for (int i = 0; i < n_crossed; i++) if (((crossed >> (4 * i)) & 15u) == 0u) ci = i;
+            int ci = -1;                                                  // the ambulance's place in the crossing order
+            {   // lowest zero nibble of the order (a car appears once; the lowest flag of the zero-in-word test is exact)
+                const uint32_t z = (crossed - 0x11111111u) & ~crossed & 0x88888888u;
+                const int i0 = z ? (__ffs(z) - 1) >> 2 : 8;
+                if (i0 < n_crossed) ci = i0;
+            }
             info2 = ci >= 0 ? (double)(ci + 1) : (double)n;
-            { const double d0 = n == 1 ? p.dist_front[env] : -1.0; info3 = d0 > -1.0 ? d0 : __dsub_rn(p.high_bound, p.low_bound); }
+            { const double d0 = dist_in; info3 = d0 > -1.0 ? d0 : __dsub_rn(p.high_bound, p.low_bound); }
             // update_rel_rank (:110-125): crossers appended in index order
             for (uint32_t jm = justm; jm; jm &= jm - 1) { crossed |= (uint32_t)(__ffs(jm) - 1) << (4 * n_crossed); n_crossed++; }
         }
-        o_pos[k] = pos0; o_new[k] = newx;
+        o_new[k] = newx;
         __syncwarp();
         if (__any_sync(CAR_FULL, justm != 0u)) {                           // a few percent of the steps
             if (justm) {
@@ -233,17 +253,15 @@ __global__ void __launch_bounds__(CAR_THREADS) car_kernel(const CarParams p, con
             }
         }
         {   // make_new_pos_consistent changes something only if a crossed car stands behind its successor in the order
-            bool viol = false;
+            bool viol = false;                                             // (o_new: new positions of the acting cars, old ones of the others)
             if (on && k + 1 < n_crossed) {
                 const int f = (int)((crossed >> (4 * k)) & 15u), b = (int)((crossed >> (4 * k + 4)) & 15u);
-                const bool af = (active_m >> f) & 1u, ab = (active_m >> b) & 1u;
-                viol = af && ab && (af ? o_new[f] : o_pos[f]) < (ab ? o_new[b] : o_pos[b]);
+                viol = ((active_m >> f) & (active_m >> b) & 1u) && o_new[f] < o_new[b];
             }
             const uint32_t vm = __ballot_sync(CAR_FULL, viol);
             if (vm) {
-                if ((vm >> obase) & 0xFFu) {
-                    if (k == 0) car_make_consistent(o_pos, o_new, active_m, crossed, n_crossed);
-                }
+                const uint32_t vo = (vm >> obase) & 0xFFu;
+                if (vo && k == 0) car_make_consistent(o_new, active_m, vo, crossed, n_crossed);
                 __syncwarp();
                 crossed = __shfl_sync(CAR_FULL, crossed, 0, 8);
                 n_crossed = __shfl_sync(CAR_FULL, n_crossed, 0, 8);
