@@ -533,10 +533,9 @@ def main():
     else:
         host_actions = [torch.randint(0, nact, (E, n), dtype=torch.uint8).pin_memory() for _ in range(4)]
     consumed = 0
-    if cfg["family"] == "grid":
-        res = [env.new_host_result(), env.new_host_result()]
-        lay = res[0].lay
-
+    res = [env.new_host_result(), env.new_host_result()]
+    lay = res[0].lay
+    if True:
         def e2e_run(steps):
             """pipelined two deep: submit step i + 1, then wait for (and read) the result block of step i"""
             nonlocal consumed
@@ -544,28 +543,20 @@ def main():
             for i in range(steps):
                 if i % 50 == 0:
                     run.policy()
-                tk = env.step_host_async(host_actions[i % 4], res[i & 1], auto_reset=True, negotiation=run.neg())
+                if cfg["family"] == "grid":
+                    tk = env.step_host_async(host_actions[i % 4], res[i & 1], auto_reset=True, negotiation=run.neg())
+                else:
+                    tk = env.step_host_async(host_actions[i % 4], res[i & 1], auto_reset=True)
                 if prev is not None:
                     env.step_host_wait(prev[0])
-                    consumed += prev[1].count + int(prev[1].done[0])
+                    consumed += prev[1].count + int(prev[1].done.flat[0])
                 prev = (tk, res[i & 1])
             env.step_host_wait(prev[0])
             consumed += prev[1].count
-        e2e_note = ("ssd_step_host_async/_wait, two steps in flight: pinned uint8 actions up on a copy-in stream, ONE lossless "
+        e2e_note = ("ssd_step_host_async/_wait, two steps in flight: pinned %s actions up on a copy-in stream, ONE lossless "
                     "result block down per step (int8 rewards + exact float64 records of the envs that paid a transfer + dones) "
-                    "while the observe kernel runs; observations stay in the device batch tensor")
-    else:
-        host_rew = torch.empty(tuple(env.rew.shape), dtype=torch.float64).pin_memory()
-        host_done = torch.empty(tuple(env.done.shape), dtype=torch.uint8).pin_memory()
-
-        def e2e_run(steps):
-            for i in range(steps):
-                run.actions.copy_(host_actions[i % 4], non_blocking=True)
-                env.step(run.actions, extras=False, auto_reset=True)
-                host_rew.copy_(env.rew, non_blocking=True)
-                host_done.copy_(env.done, non_blocking=True)
-                main_stream.synchronize()
-        e2e_note = "Batched*Env.step with pinned host actions in, float64 rewards + dones out, synchronous every step"
+                    "while the %s runs; observations stay in the device batch tensor"
+                    % ("float32" if cfg["family"] == "car" else "uint8", "observe kernel" if cfg["family"] == "grid" else "next step"))
     e2e_run(5)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -577,12 +568,9 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * E * n * Ke / (float(e2e_ms.item()) * 1e-3)
-    if cfg["family"] == "grid":
-        rec_mean = float(np.mean([r.count for r in res]))
-        d2h = int(lay.records_offset + min(lay.record_capacity, 2 * rec_mean + 1024) * lay.record_bytes)
-        h2d = E * n
-    else:
-        d2h, h2d = host_rew.numel() * 8 + host_done.numel(), E * n * host_actions[0].element_size()
+    rec_mean = float(np.mean([r.count for r in res]))
+    d2h = int(lay.records_offset + min(lay.record_capacity, 2 * rec_mean + 1024) * lay.record_bytes)
+    h2d = E * n * host_actions[0].element_size()
     # informational: also ship the observations to the host (PCIe-bound by construction)
     obs_to_host = None
     if rank == 0 and cfg["family"] == "grid":

@@ -93,6 +93,7 @@ EXPORTS = [
     "ssd_selfdrive_random_actions", "ssd_feat_reset", "ssd_feat_step", "ssd_feat_get_state", "ssd_feat_get_metrics",
     "ssd_global_view", "ssd_concat_obs", "ssd_solver_sample", "ssd_solver_choose", "ssd_policy_inputs", "ssd_record_beams", "ssd_render", "ssd_step_host",
     "ssd_step_host_async", "ssd_step_host_wait", "ssd_host_result_layout", "ssd_host_result_expand", "ssd_set_episode_stats",
+    "ssd_feat_step_host_async", "ssd_selfdrive_step_host_async",
 ]
 
 _LIB = None
@@ -120,6 +121,8 @@ def load():
     L.ssd_negotiate.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ssd_step_host_async.argtypes = [vp, ctypes.POINTER(ssd_step_io), vp, vp, ctypes.POINTER(i64), vp]
     L.ssd_step_host_wait.argtypes = [vp, i64]
+    L.ssd_feat_step_host_async.argtypes = [vp, ctypes.POINTER(ssd_feat_io), vp, vp, ctypes.POINTER(i64), vp]
+    L.ssd_selfdrive_step_host_async.argtypes = [vp, ctypes.POINTER(ssd_selfdrive_io), vp, vp, ctypes.POINTER(i64), vp]
     L.ssd_host_result_layout.argtypes = [vp, ctypes.POINTER(ssd_host_layout)]
     L.ssd_host_result_expand.argtypes = [vp, vp, vp]
     L.ssd_set_episode_stats.argtypes = [vp, vp]

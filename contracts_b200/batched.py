@@ -72,7 +72,8 @@ def solver_choose(batch, params, vals, rule="majority"):
 
 class HostResult:
     """One pinned result block of `ssd_step_host_async` with numpy views of its fields (valid after step_host_wait):
-    count (records in use), done uint8 [E], rew_i8 int8 [E, n], rec_env int32 [E], rec_rew float64 [E, n]."""
+    count (records in use), done uint8 [E] ([E, n + 1] for selfdrive), rew_i8 int8 [E, n], rec_env int32 [E],
+    rec_rew float64 [E, n].  `batch` is any of the batched envs (grid, feature, selfdrive)."""
 
     def __init__(self, batch):
         lay = batch.host_result_layout()
@@ -81,7 +82,8 @@ class HostResult:
         b = self.block.numpy()
         E, n = batch.E, batch.n
         self._count = b[lay.count_offset:lay.count_offset + 4].view(np.uint32)
-        self.done = b[lay.done_offset:lay.done_offset + E]
+        dshape = getattr(batch, "host_done_shape", (E,))          # selfdrive: [E, n + 1] (per-car dones, then '__all__')
+        self.done = b[lay.done_offset:lay.done_offset + int(np.prod(dshape))].reshape(dshape)
         self.rew_i8 = b[lay.rew_i8_offset:lay.rew_i8_offset + E * n].view(np.int8).reshape(E, n)
         rec = b[lay.records_offset:lay.records_offset + E * lay.record_bytes].reshape(E, lay.record_bytes)
         self.rec_env = rec[:, 0:4].view(np.int32).reshape(E)
@@ -100,7 +102,24 @@ class HostResult:
         return out
 
 
-class BatchedGridEnv:
+class HostResultMixin:
+    """host_result_layout / new_host_result / step_host_wait shared by the batched envs (ssd_host_result_layout,
+    ssd_step_host_wait serve every env kind)."""
+
+    def host_result_layout(self):
+        lay = _lib.ssd_host_layout()
+        _lib.check(self._h, self.lib.ssd_host_result_layout(self._h, ctypes.byref(lay)))
+        return lay
+
+    def new_host_result(self):
+        """A pinned host block for step_host_async + numpy views of its fields (`HostResult`)."""
+        return HostResult(self)
+
+    def step_host_wait(self, ticket):
+        _lib.check(self._h, self.lib.ssd_step_host_wait(self._h, int(ticket)))
+
+
+class BatchedGridEnv(HostResultMixin):
     """E environments of one kind on one device.
 
     kind: 'cleanup_new' | 'harvest_new' (the reference's `environment` strings,
@@ -252,15 +271,6 @@ class BatchedGridEnv:
         return self.obs, rew_host, done_host
 
     # ---- pipelined host-buffer step (RLlib BaseEnv send_actions / poll shape) ---------------------------------
-    def host_result_layout(self):
-        lay = _lib.ssd_host_layout()
-        _lib.check(self._h, self.lib.ssd_host_result_layout(self._h, ctypes.byref(lay)))
-        return lay
-
-    def new_host_result(self):
-        """A pinned host block for step_host_async + numpy views of its fields (`HostResult`)."""
-        return HostResult(self)
-
     def step_host_async(self, actions_host, result, want_features=False, dense_rewards=False, auto_reset=False, negotiation=None):
         """Submit one step with HOST actions (pinned uint8 [E, n]); returns a ticket without synchronising.  The
         compact result block (int8 rewards + exact float64 records + dones) is copied into `result` (a HostResult)
@@ -285,9 +295,6 @@ class BatchedGridEnv:
         _lib.check(self._h, self.lib.ssd_step_host_async(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
                                                          ctypes.c_void_p(result.block.data_ptr()), ctypes.byref(ticket), self._stream()))
         return ticket.value
-
-    def step_host_wait(self, ticket):
-        _lib.check(self._h, self.lib.ssd_step_host_wait(self._h, int(ticket)))
 
     # ---- packed host snapshots (dict façade, vector adapter): ONE device -> host copy per call ----------------
     def host_snapshot(self, index=None, features=False, extras=True, obs=True):

@@ -956,12 +956,15 @@ int ssd_step_host(ssd_handle* h, const ssd_step_io* io, const void* actions_host
 }
 
 // ---- pipelined host-buffer step (see include/ssd_b200.h) --------------------------------------------------------
+// bytes of one env's actions / done flags on the host paths: uint8 [n] / 1 (gridworlds, feature envs), float32 [n] / n + 1 (selfdrive)
+static int64_t host_action_bytes(const ssd_handle* h) { return (int64_t)h->cfg.num_agents * (h->cfg.env_kind == SSD_ENV_SELFDRIVE ? 4 : 1); }
+static int64_t host_done_bytes(const ssd_handle* h) { return h->cfg.env_kind == SSD_ENV_SELFDRIVE ? h->cfg.num_agents + 1 : 1; }
 static void host_layout(const ssd_handle* h, ssd_host_layout* l)
 {
-    const int64_t E = h->gp.E, n = h->gp.n;
+    const int64_t E = h->cfg.num_envs, n = h->cfg.num_agents;
     l->count_offset = 0;
     l->done_offset = 64;
-    l->rew_i8_offset = l->done_offset + (E + 63) / 64 * 64;
+    l->rew_i8_offset = l->done_offset + (E * host_done_bytes(h) + 63) / 64 * 64;
     l->records_offset = l->rew_i8_offset + (E * n + 63) / 64 * 64;
     l->record_bytes = (int32_t)(8 + 8 * n);
     l->record_capacity = (int32_t)E;
@@ -971,7 +974,6 @@ static void host_layout(const ssd_handle* h, ssd_host_layout* l)
 int ssd_host_result_layout(const ssd_handle* h, ssd_host_layout* out)
 {
     if (!h || !out) return SSD_EINVAL;
-    if (h->cfg.env_kind != SSD_ENV_CLEANUP && h->cfg.env_kind != SSD_ENV_HARVEST) return SSD_EINVAL;
     host_layout(h, out);
     return SSD_OK;
 }
@@ -982,7 +984,7 @@ static int async_setup(ssd_handle* h)
     host_layout(h, &h->lay);
     for (int i = 0; i < 2; i++) {
         int rc;
-        if ((rc = dev_zalloc(h, (size_t)h->gp.E * h->gp.n, &h->slot[i].d_actions))) return rc;
+        if ((rc = dev_zalloc(h, (size_t)h->cfg.num_envs * (size_t)host_action_bytes(h), &h->slot[i].d_actions))) return rc;
         if ((rc = dev_zalloc(h, (size_t)h->lay.total_bytes, &h->slot[i].d_block))) return rc;
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_up, cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot[i].ev_rew, cudaEventDisableTiming));
@@ -1036,11 +1038,43 @@ int ssd_step_host_async(ssd_handle* h, const ssd_step_io* io, const void* action
     return SSD_OK;
 }
 
+// Front / back halves of the feature-env and selfdrive submissions (one kernel per step): upload the actions into the
+// slot on the copy-in stream, order `s` behind the upload and behind the slot's previous copy-out; afterwards mark the
+// actions as read, send the result block down on the copy-out stream and hand out the ticket.
+static int async_begin(ssd_handle* h, const void* actions_host, void* result_host, cudaStream_t s, int* slot_out)
+{
+    int rc = async_setup(h);
+    if (rc) return rc;
+    const int si = (int)(h->next_ticket & 1);
+    ssd_handle::Slot& sl = h->slot[si];
+    if (sl.busy) return fail(h, SSD_EINVAL, "step_host_async: ticket %lld of this slot has not been waited for", (long long)sl.ticket);
+    if (sl.ticket >= 0) CUDA_TRY(h, cudaStreamWaitEvent(h->s_in, sl.ev_logic, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(sl.d_actions, actions_host, (size_t)h->cfg.num_envs * (size_t)host_action_bytes(h), cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaEventRecord(sl.ev_up, h->s_in));
+    CUDA_TRY(h, cudaStreamWaitEvent(s, sl.ev_up, 0));
+    if (sl.ticket >= 0) CUDA_TRY(h, cudaStreamWaitEvent(s, sl.ev_copied, 0));
+    sl.host_block = result_host;
+    *slot_out = si;
+    return SSD_OK;
+}
+static int async_end(ssd_handle* h, int si, cudaStream_t s, int64_t* ticket_out)
+{
+    ssd_handle::Slot& sl = h->slot[si];
+    CUDA_TRY(h, cudaEventRecord(sl.ev_logic, s));                       // the slot's actions were read
+    const HostCopy hc = { nullptr, nullptr, si };
+    const StepIO unused = {};
+    int rc = copy_rewards(h, unused, s, &hc);
+    if (rc) return rc;
+    sl.ticket = h->next_ticket++;
+    sl.busy = true;
+    *ticket_out = sl.ticket;
+    return SSD_OK;
+}
+
 int ssd_step_host_wait(ssd_handle* h, int64_t ticket)
 {
     if (!h) return SSD_EINVAL;
     ON_DEVICE(h);
-    REQUIRE_GRID(h);
     if (!h->s_out || ticket < 0) return fail(h, SSD_EINVAL, "step_host_wait: unknown ticket %lld", (long long)ticket);
     ssd_handle::Slot& sl = h->slot[ticket & 1];
     if (!sl.busy || sl.ticket != ticket) return fail(h, SSD_EINVAL, "step_host_wait: ticket %lld is not in flight", (long long)ticket);
@@ -1061,11 +1095,10 @@ int ssd_step_host_wait(ssd_handle* h, int64_t ticket)
 int ssd_host_result_expand(const ssd_handle* h, const void* result_host, double* rew_out)
 {
     if (!h || !result_host || !rew_out) return SSD_EINVAL;
-    if (h->cfg.env_kind != SSD_ENV_CLEANUP && h->cfg.env_kind != SSD_ENV_HARVEST) return SSD_EINVAL;
     ssd_host_layout l;
     host_layout(h, &l);
     const uint8_t* b = (const uint8_t*)result_host;
-    const int64_t E = h->gp.E, n = h->gp.n;
+    const int64_t E = h->cfg.num_envs, n = h->cfg.num_agents;
     const int8_t* r8 = reinterpret_cast<const int8_t*>(b + l.rew_i8_offset);
     for (int64_t i = 0; i < E * n; i++) rew_out[i] = (double)r8[i];
     const uint32_t count = *reinterpret_cast<const uint32_t*>(b + l.count_offset);
@@ -1305,6 +1338,28 @@ int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream)
     return check_launch(h, "feat_step");
 }
 
+int ssd_feat_step_host_async(ssd_handle* h, const ssd_feat_io* io, const void* actions_host, void* result_host, int64_t* ticket_out,
+                             void* stream)
+{
+    if (!h || !io || !actions_host || !result_host || !ticket_out || !io->obs_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
+    REQUIRE_FEAT(h);
+    if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 3)) return fail(h, SSD_EINVAL, "info_dev must be 4-byte aligned");
+    int si = 0;
+    int rc = async_begin(h, actions_host, result_host, (cudaStream_t)stream, &si);
+    if (rc) return rc;
+    ssd_handle::Slot& sl = h->slot[si];
+    FeatIO k = { sl.d_actions, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
+    k.c_count = reinterpret_cast<uint32_t*>(sl.d_block + h->lay.count_offset);
+    k.c_done = sl.d_block + h->lay.done_offset;
+    k.c_rew8 = reinterpret_cast<int8_t*>(sl.d_block + h->lay.rew_i8_offset);
+    k.c_rec = sl.d_block + h->lay.records_offset;
+    if (h->cfg.env_kind == SSD_ENV_CLEANUP_FEATURES) feat_kernel<true, false><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, nullptr);
+    else feat_kernel<false, false><<<h->grid_blocks, FEAT_THREADS, h->feat_smem, (cudaStream_t)stream>>>(h->fp, k, nullptr);
+    if ((rc = check_launch(h, "feat_step_host_async"))) return rc;
+    return async_end(h, si, (cudaStream_t)stream, ticket_out);
+}
+
 int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev, int32_t* t_dev, void* stream)
 {
     if (!h) return SSD_EINVAL;
@@ -1345,6 +1400,28 @@ int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream)
     CarIO k = { io->actions_dev, io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev, io->auto_reset };
     car_kernel<false><<<h->grid_blocks, CAR_THREADS, h->car_smem, (cudaStream_t)stream>>>(h->cp, k, nullptr);
     return check_launch(h, "selfdrive_step");
+}
+
+int ssd_selfdrive_step_host_async(ssd_handle* h, const ssd_selfdrive_io* io, const void* actions_host, void* result_host,
+                                  int64_t* ticket_out, void* stream)
+{
+    if (!h || !io || !actions_host || !result_host || !ticket_out || !io->obs_dev) return SSD_EINVAL;
+    ON_DEVICE(h);
+    if (h->cfg.env_kind != SSD_ENV_SELFDRIVE) return fail(h, SSD_EINVAL, "selfdrive_step_host_async: handle is not a selfdrive env");
+    if (io->info_dev && (reinterpret_cast<uintptr_t>(io->info_dev) & 31)) return fail(h, SSD_EINVAL, "info_dev must be 32-byte aligned");
+    int si = 0;
+    int rc = async_begin(h, actions_host, result_host, (cudaStream_t)stream, &si);
+    if (rc) return rc;
+    ssd_handle::Slot& sl = h->slot[si];
+    CarIO k = { reinterpret_cast<const float*>(sl.d_actions), io->obs_dev, io->rew_dev, io->base_rew_dev, io->transfers_dev, io->info_dev, io->done_dev,
+                io->auto_reset };
+    k.c_count = reinterpret_cast<uint32_t*>(sl.d_block + h->lay.count_offset);
+    k.c_done = sl.d_block + h->lay.done_offset;
+    k.c_rew8 = reinterpret_cast<int8_t*>(sl.d_block + h->lay.rew_i8_offset);
+    k.c_rec = sl.d_block + h->lay.records_offset;
+    car_kernel<false><<<h->grid_blocks, CAR_THREADS, h->car_smem, (cudaStream_t)stream>>>(h->cp, k, nullptr);
+    if ((rc = check_launch(h, "selfdrive_step_host_async"))) return rc;
+    return async_end(h, si, (cudaStream_t)stream, ticket_out);
 }
 
 int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, double* theta_dev, double* transfers_dev,

@@ -82,6 +82,9 @@ struct FeatIO {
     uint8_t* info;              // [E][n][4]: cleanup (cleaned_squares,0,0,0); harvest (eaten_apples, eaten_close_apples,0,0)
     uint8_t* done;              // [E]
     int auto_reset;             // next-step auto-reset (see feat_kernel)
+    // compact result block of ssd_feat_step_host_async (all null otherwise): int8 rewards, dones, and records
+    // { int32 env; int32 0; double rew[n] } for the envs whose rewards are not all integers in [-127, 127]
+    int8_t* c_rew8; uint8_t* c_done; uint32_t* c_count; uint8_t* c_rec;
 };
 
 // ---- octet primitives (all 32 lanes execute them; an octet is lanes obase .. obase + 7) --------------------------------
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
         const int raw = oct_sum(reward), n_eaten = oct_sum(eaten), n_close = oct_sum(eaten_close);
         if (active && a < n) {
             const size_t o = (size_t)env * n + a, so = (size_t)a * p.E + env;
-            io.rew[o] = rew;
+            if (io.rew) io.rew[o] = rew;
             if (io.base_rew) io.base_rew[o] = (double)reward;
             if (io.transfers) io.transfers[o] = tr;
             if (io.info) reinterpret_cast<uint32_t*>(io.info)[o] = CLEANUP ? (uint32_t)cleaned : ((uint32_t)eaten | ((uint32_t)eaten_close << 8));
@@ -738,6 +741,26 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
             if (n_close) red_add(p.metrics + (size_t)4 * p.E + env, (double)n_close);
         }
         if (active && a == 0 && io.done) io.done[env] = (stepping && t_new == p.horizon) ? 1 : 0;
+        if (io.c_rew8) {                                                   // the pipelined host path's lossless result block
+            int vi = 0;
+            const bool mine = active && a < n, fits = reward_fits_i8(rew, vi);
+            if (mine) io.c_rew8[(size_t)env * n + a] = fits ? (int8_t)vi : (int8_t)0;
+            if (active && a == 0) io.c_done[env] = (stepping && t_new == p.horizon) ? 1 : 0;
+            const uint32_t badm = __ballot_sync(FULLMASK, mine && !fits);
+            if (badm) {                                                    // one record per env with such a reward, one atomic per warp
+                const bool need = ((badm >> obase) & 0xFFu) != 0u;
+                const uint32_t needm = __ballot_sync(FULLMASK, need && a == 0);
+                const int leader = __ffs(needm) - 1;
+                uint32_t base = 0u;
+                if (lane == leader) base = atomicAdd(io.c_count, (uint32_t)__popc(needm));
+                base = __shfl_sync(FULLMASK, base, leader);
+                if (need) {
+                    uint8_t* rec = io.c_rec + (size_t)(base + (uint32_t)__popc(needm & ((1u << obase) - 1u))) * (size_t)(8 + 8 * n);
+                    if (a == 0) { reinterpret_cast<int32_t*>(rec)[0] = env; reinterpret_cast<int32_t*>(rec)[1] = 0; }
+                    if (a < n) reinterpret_cast<double*>(rec + 8)[a] = rew;
+                }
+            }
+        }
     }
 
     // ---- state out

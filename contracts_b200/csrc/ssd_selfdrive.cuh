@@ -50,7 +50,10 @@ struct CarIO {
     double* rew; double* base_rew; double* transfers;   // [E][n]
     double* info;           // [E][n][4]: just_passed, active, ambulance_rank, ambulance_dist_to_front (row of the first acting agent)
     uint8_t* done;          // [E][n+1]
-    int auto_reset;         // next-step auto-reset (see car_step_kernel)
+    int auto_reset;         // next-step auto-reset (see car_kernel)
+    // compact result block of ssd_selfdrive_step_host_async (all null otherwise): int8 rewards, dones [E][n+1], and records
+    // { int32 env; int32 0; double rew[n] } for the envs whose rewards are not all integers in [-127, 127]
+    int8_t* c_rew8; uint8_t* c_done; uint32_t* c_count; uint8_t* c_rec;
 };
 
 __device__ __forceinline__ double py_min(double x, double y) { return y < x ? y : x; }   // Python min([x, y])
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
             all_done = (active_m & ~done_mask) == 0u;
             if (kv) { p.pos[so] = x; p.vel[so] = v; }
         }
-        const double base = rew;
+        const double base_rew = rew;
         __syncwarp();
         o_pos[k] = x;                                                      // final positions (contract, observation rows)
         __syncwarp();
@@ -298,8 +301,8 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
         }
         if (live && kv) {                                                  // (a restarting env: zeros)
             const size_t o = (size_t)env * n + k;
-            io.rew[o] = rew;
-            if (io.base_rew) io.base_rew[o] = base;
+            if (io.rew) io.rew[o] = rew;
+            if (io.base_rew) io.base_rew[o] = base_rew;
             if (io.transfers) io.transfers[o] = tr;
             if (io.info)
                 reinterpret_cast<double4*>(io.info)[o] = stepping ? make_double4(just ? 1.0 : 0.0, act ? 1.0 : 0.0, k == first ? info2 : 0.0, k == first ? info3 : 0.0)
@@ -307,6 +310,29 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
             if (io.done) io.done[(size_t)env * (n + 1) + k] = stepping ? (uint8_t)((done_mask >> k) & 1u) : (uint8_t)0;
         }
         if (live && k == 0 && io.done) io.done[(size_t)env * (n + 1) + n] = (stepping && all_done) ? 1 : 0;
+        if (io.c_rew8) {                                                   // the pipelined host path's lossless result block
+            int vi = 0;
+            const bool mine = live && kv, fits = reward_fits_i8(rew, vi);
+            if (mine) {
+                io.c_rew8[(size_t)env * n + k] = fits ? (int8_t)vi : (int8_t)0;
+                io.c_done[(size_t)env * (n + 1) + k] = stepping ? (uint8_t)((done_mask >> k) & 1u) : (uint8_t)0;
+            }
+            if (live && k == 0) io.c_done[(size_t)env * (n + 1) + n] = (stepping && all_done) ? 1 : 0;
+            const uint32_t badm = __ballot_sync(CAR_FULL, mine && !fits);
+            if (badm) {                                                    // one record per env with such a reward, one atomic per warp
+                const bool need = ((badm >> obase) & 0xFFu) != 0u;
+                const uint32_t needm = __ballot_sync(CAR_FULL, need && k == 0);
+                const int leader = __ffs(needm) - 1;
+                uint32_t base = 0u;
+                if (lane == leader) base = atomicAdd(io.c_count, (uint32_t)__popc(needm));
+                base = __shfl_sync(CAR_FULL, base, leader);
+                if (need) {
+                    uint8_t* rec = io.c_rec + (size_t)(base + (uint32_t)__popc(needm & ((1u << obase) - 1u))) * (size_t)(8 + 8 * n);
+                    if (k == 0) { reinterpret_cast<int32_t*>(rec)[0] = env; reinterpret_cast<int32_t*>(rec)[1] = 0; }
+                    if (kv) reinterpret_cast<double*>(rec + 8)[k] = rew;
+                }
+            }
+        }
     } else {
         o_pos[k] = x;
     }

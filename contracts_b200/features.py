@@ -1,7 +1,7 @@
 """Batched device-resident CleanupFeatures / HarvestFeatures (+ fused subgame contract wrapper).
 
 Reference: environments/cleanup_features.py:48-336, environments/harvest_features.py:60-364,
-contract/contract_list.py:7-54, environments/two_stage_train.py:62-121,159-187.  One thread per env, one launch per
+contract/contract_list.py:7-54, environments/two_stage_train.py:62-121,159-187.  Eight lanes per env, one launch per
 step; observations are float64 feature vectors [E, n, F].
 """
 import ctypes
@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .batched import HostResultMixin
 from .maps import CLEANUP_MAP, HARVEST_MAP
 
 _DEFAULT_HIGH = {"CleanupContract": 0.2, "HarvestFeaturemodLocalContract": 10.0}
@@ -19,7 +20,7 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-class BatchedFeatureEnv:
+class BatchedFeatureEnv(HostResultMixin):
     """kind: 'cleanup' | 'harvest' (the reference's `environment` strings for the feature envs)."""
 
     def __init__(self, kind, num_envs, num_agents, ascii_map=None, horizon=1000, contract=None, theta_low=0.0,
@@ -90,6 +91,24 @@ class BatchedFeatureEnv:
         io.auto_reset = 1 if auto_reset else 0       # next-step auto-reset: finished envs restart in the following step
         _lib.check(self._h, self.lib.ssd_feat_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
+
+    def step_host_async(self, actions_host, result, dense_rewards=False, auto_reset=False):
+        """Submit one step with HOST actions (pinned uint8 [E, n]); returns a ticket without synchronising.  The compact
+        result block (int8 rewards + exact float64 records + dones) lands in `result` (a HostResult from new_host_result());
+        `step_host_wait(ticket)` makes it valid.  At most two steps in flight; observations stay in self.obs."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous():
+            raise ValueError("step_host_async needs a contiguous CPU uint8 tensor [E, n] (pinned for an asynchronous copy)")
+        io = self._io
+        io.actions_dev, io.obs_dev = None, self.obs.data_ptr()
+        io.rew_dev = self.rew.data_ptr() if dense_rewards else None
+        io.base_rew_dev = io.transfers_dev = None
+        io.info_dev = self.info.data_ptr()
+        io.done_dev = self.done.data_ptr()
+        io.auto_reset = 1 if auto_reset else 0
+        ticket = ctypes.c_int64(-1)
+        _lib.check(self._h, self.lib.ssd_feat_step_host_async(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                              ctypes.c_void_p(result.block.data_ptr()), ctypes.byref(ticket), self._stream()))
+        return ticket.value
 
     def random_actions(self, step_index, num_actions, out=None):
         if step_index is None:

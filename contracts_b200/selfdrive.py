@@ -9,13 +9,14 @@ import numpy as np
 import torch
 
 from . import _lib
+from .batched import HostResultMixin
 
 
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-class BatchedCarEnv:
+class BatchedCarEnv(HostResultMixin):
     def __init__(self, num_envs, num_agents, contract=None, low_bound=-10.0, high_bound=10.0, start_vel=0.2,
                  start_vel_ambulance=0.8, theta_low=0.0, theta_high=100.0, null_prob=0.0, seed=73907, first_env_id=0,
                  device=None):
@@ -81,6 +82,27 @@ class BatchedCarEnv:
         io.auto_reset = 1 if auto_reset else 0       # next-step auto-reset: finished envs restart in the following step
         _lib.check(self._h, self.lib.ssd_selfdrive_step(self._h, ctypes.byref(io), self._stream()))
         return self.obs, self.rew, self.done, self.info
+
+    @property
+    def host_done_shape(self):
+        return (self.E, self.n + 1)
+
+    def step_host_async(self, actions_host, result, dense_rewards=False, auto_reset=False):
+        """Submit one step with HOST actions (pinned float32 [E, n]); returns a ticket without synchronising.  The compact
+        result block (int8 rewards + exact float64 records + dones [E, n+1]) lands in `result` (a HostResult from
+        new_host_result()); `step_host_wait(ticket)` makes it valid.  At most two steps in flight."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.float32 or not actions_host.is_contiguous():
+            raise ValueError("step_host_async needs a contiguous CPU float32 tensor [E, n] (pinned for an asynchronous copy)")
+        io = self._io
+        io.actions_dev, io.obs_dev = None, self.obs.data_ptr()
+        io.rew_dev = self.rew.data_ptr() if dense_rewards else None
+        io.base_rew_dev = io.transfers_dev = io.info_dev = None
+        io.done_dev = self.done.data_ptr()
+        io.auto_reset = 1 if auto_reset else 0
+        ticket = ctypes.c_int64(-1)
+        _lib.check(self._h, self.lib.ssd_selfdrive_step_host_async(self._h, ctypes.byref(io), ctypes.c_void_p(actions_host.data_ptr()),
+                                                                   ctypes.c_void_p(result.block.data_ptr()), ctypes.byref(ticket), self._stream()))
+        return ticket.value
 
     def random_actions(self, step_index, lo=-0.1, hi=0.1, out=None):
         if step_index is None:

@@ -186,6 +186,10 @@ int ssd_host_result_layout(const ssd_handle* h, ssd_host_layout* out);
 int ssd_step_host_async(ssd_handle* h, const ssd_step_io* io, const void* actions_host, void* result_host,
                         int64_t* ticket_out, void* stream);
 int ssd_step_host_wait(ssd_handle* h, int64_t ticket);
+/* The same pipelined form for the feature envs and selfdrive (declared with their io structs below): one kernel per step,
+ * io->actions_dev ignored, io->rew_dev may be NULL.  ssd_host_result_layout / ssd_step_host_wait / ssd_host_result_expand
+ * serve every env kind; the block's `done` field is uint8 [E] for the gridworlds and the feature envs and uint8 [E][n+1]
+ * (per-car dones, then '__all__') for selfdrive, whose actions_host is float32 [E][n]. */
 /* host code only: rew_out double [E][n] from a valid result block */
 int ssd_host_result_expand(const ssd_handle* h, const void* result_host, double* rew_out);
 
@@ -282,6 +286,9 @@ typedef struct ssd_selfdrive_io {
 } ssd_selfdrive_io;
 int ssd_selfdrive_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
 int ssd_selfdrive_step(ssd_handle* h, const ssd_selfdrive_io* io, void* stream);
+/* host actions in (float32 [E][n], pinned), compact result block out: see ssd_step_host_async */
+int ssd_selfdrive_step_host_async(ssd_handle* h, const ssd_selfdrive_io* io, const void* actions_host, void* result_host,
+                                  int64_t* ticket_out, void* stream);
 /* pos/vel double [E][n], theta / transfers metric double [E], t int32 [E]; NULL pointers are skipped */
 int ssd_selfdrive_get_state(ssd_handle* h, double* pos_dev, double* vel_dev, double* theta_dev, double* transfers_dev,
                             int32_t* t_dev, void* stream);
@@ -305,12 +312,15 @@ typedef struct ssd_feat_io {
 } ssd_feat_io;
 int ssd_feat_reset(ssd_handle* h, const uint8_t* mask_dev, double* obs_dev, void* stream);
 int ssd_feat_step(ssd_handle* h, const ssd_feat_io* io, void* stream);
+/* host actions in (uint8 [E][n], pinned), compact result block out: see ssd_step_host_async */
+int ssd_feat_step_host_async(ssd_handle* h, const ssd_feat_io* io, const void* actions_host, void* result_host,
+                             int64_t* ticket_out, void* stream);
 /* pos int32 [E][n][2], ori int32 [E][n], cells uint8 [E][H][W] (1 = apple, 2 = waste in the current lists),
  * theta double [E], t int32 [E]; NULL pointers are skipped */
 int ssd_feat_get_state(ssd_handle* h, int32_t* pos_dev, int32_t* ori_dev, uint8_t* cells_dev, double* theta_dev,
                        int32_t* t_dev, void* stream);
 /* double [E][40]: dirt_cleaned, raw_env_rewards, transfers, total_apples_eaten, low_density_apples_eaten,
- * err_flags (1: more than 65535 spawns of one kind in an episode — the 16-bit birth stamps wrapped), 0, 0,
+ * err_flags (always 0 since the lists are kept in birth order; was: 16-bit birth stamps wrapped), 0, 0,
  * per agent: sum r [8], sum t*r [8], sum transferred r [8], sum t * transferred r [8] */
 int ssd_feat_get_metrics(ssd_handle* h, double* out_dev, void* stream);
 

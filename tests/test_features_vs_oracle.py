@@ -112,3 +112,58 @@ def test_feature_auto_reset_matches_oracle(oracle_lib, kind, n):
             for k in ("pos", "ori", "cells", "theta", "t"):
                 gu.assert_same(k, st[k][i], so[k][0], ctx)
         done_prev = got["done"].astype(bool)
+
+
+def _fits_i8(w):
+    return (w == np.round(w)) & (np.abs(w) <= 127) & ~(np.signbit(w) & (w == 0))
+
+
+@pytest.mark.parametrize("kind,n,E,theta", [("cleanup", 8, 1500, 0.15), ("harvest", 8, 900, 2.5), ("cleanup", 5, 301, 0.0)])
+def test_feature_step_host_async_equals_step(kind, n, E, theta):
+    """ssd_feat_step_host_async / ssd_step_host_wait (two slots, compact int8 + sparse float64 result block) delivers bit
+    for bit what ssd_feat_step produces: observations (device), dones, and — after ssd_host_result_expand — the float64
+    rewards; with the next-step auto-reset on a short horizon."""
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    c = _contract(kind)
+    a = BatchedFeatureEnv(kind, E, n, horizon=17, contract=c, seed=5, first_env_id=11)
+    b = BatchedFeatureEnv(kind, E, n, horizon=17, contract=c, seed=5, first_env_id=11)
+    a.reset(); b.reset()
+    a.set_contract_params(theta); b.set_contract_params(theta)
+    rng = np.random.RandomState(1)
+    nact = 9 if kind == "cleanup" else 8
+    T = 60
+    acts = [torch.as_tensor(rng.randint(0, nact, size=(E, n)).astype(np.uint8)).pin_memory() for _ in range(T)]
+    res = [b.new_host_result(), b.new_host_result()]
+    want = []
+    for t in range(T):
+        obs_a, rew_a, done_a, _ = a.step(acts[t].cuda(), auto_reset=True)
+        want.append((rew_a.cpu().numpy().copy(), done_a.cpu().numpy().copy(), obs_a.cpu().numpy().copy() if t % 7 == 0 else None))
+        if t % 17 == 16:                                # (auto-reset draws a new theta: pin it again on both sides)
+            pass
+    tickets, sparse_total = [], 0
+
+    def check(t):
+        nonlocal sparse_total
+        b.step_host_wait(tickets[t])
+        r = res[t & 1]
+        assert np.array_equal(r.rewards().view(np.uint64), want[t][0].view(np.uint64)), (kind, t)
+        assert np.array_equal(r.done, want[t][1]), (kind, t)
+        envs = r.rec_env[:r.count]
+        assert len(np.unique(envs)) == r.count
+        sparse_env = np.nonzero(~_fits_i8(want[t][0]).all(1))[0]
+        assert np.array_equal(np.sort(envs), sparse_env), (kind, t)
+        sparse_total += r.count
+    for t in range(T):
+        tickets.append(b.step_host_async(acts[t], res[t & 1], auto_reset=True))
+        if want[t][2] is not None:
+            assert np.array_equal(b.obs.cpu().numpy().view(np.uint64), want[t][2].view(np.uint64)), (kind, t)
+        if t >= 1:
+            check(t - 1)
+    check(T - 1)
+    assert sparse_total > 0                             # transfers were paid (theta is redrawn at the auto-reset): records exercised
+    from contracts_b200 import _lib
+    t0 = b.step_host_async(acts[0], res[0]); t1 = b.step_host_async(acts[1], res[1])
+    with pytest.raises(_lib.SsdError):
+        b.step_host_async(acts[2], res[0])
+    b.step_host_wait(t0); b.step_host_wait(t1)

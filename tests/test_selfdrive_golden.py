@@ -191,3 +191,46 @@ def test_selfdrive_next_step_auto_reset():
                 assert np.array_equal(d[e], sd.cpu().numpy()[0])
         done_prev = d[:, n].astype(bool)
     assert resets >= E
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,E,contract", [(8, 2050, True), (3, 333, True), (5, 64, False)])
+def test_selfdrive_step_host_async_equals_step(n, E, contract):
+    """ssd_selfdrive_step_host_async / ssd_step_host_wait: float32 host actions in, the compact result block out (int8
+    rewards + exact float64 records + dones [E, n+1]) — bit for bit what ssd_selfdrive_step produces, auto-reset on."""
+    import torch
+    from contracts_b200.selfdrive import BatchedCarEnv
+    c = "SelfdriveContractDistprop" if contract else None
+    a = BatchedCarEnv(E, n, contract=c, seed=5, first_env_id=3)
+    b = BatchedCarEnv(E, n, contract=c, seed=5, first_env_id=3)
+    a.reset(); b.reset()
+    rng = np.random.RandomState(4)
+    T = 200
+    acts = [torch.as_tensor((rng.uniform(-0.7, 1.0, size=(E, n)) * 0.15).astype(np.float32)).pin_memory() for _ in range(T)]
+    res = [b.new_host_result(), b.new_host_result()]
+    want = []
+    for t in range(T):
+        obs_a, rew_a, done_a, _ = a.step(acts[t].cuda(), auto_reset=True)
+        want.append((rew_a.cpu().numpy().copy(), done_a.cpu().numpy().copy(), obs_a.cpu().numpy().copy() if t % 19 == 0 else None))
+    tickets, sparse_total, finished = [], 0, 0
+
+    def check(t):
+        nonlocal sparse_total, finished
+        b.step_host_wait(tickets[t])
+        r = res[t & 1]
+        assert np.array_equal(r.rewards().view(np.uint64), want[t][0].view(np.uint64)), t
+        assert np.array_equal(r.done, want[t][1]), t
+        w = want[t][0]
+        fits = (w == np.round(w)) & (np.abs(w) <= 127) & ~(np.signbit(w) & (w == 0))
+        assert np.array_equal(np.sort(r.rec_env[:r.count]), np.nonzero(~fits.all(1))[0]), t
+        sparse_total += r.count
+        finished += int(want[t][1][:, n].sum())
+    for t in range(T):
+        tickets.append(b.step_host_async(acts[t], res[t & 1], auto_reset=True))
+        if want[t][2] is not None:
+            assert np.array_equal(b.obs.cpu().numpy().view(np.uint64), want[t][2].view(np.uint64)), t
+        if t >= 1:
+            check(t - 1)
+    check(T - 1)
+    assert finished > 0
+    assert (sparse_total > 0) == bool(contract)
