@@ -85,3 +85,109 @@ def test_reference_vs_oracle_full_episodes(oracle_lib, kind, n, nact, probs):
         assert min_waste <= (42 if n == 8 else 47) and max_apples >= 10 and eaten > 0 and paid > 0, (min_waste, max_apples, eaten, paid)
     if kind == "harvest":
         assert eaten > 0
+
+
+# ---- feature envs and selfdrive: the same differential, live reference vs C oracle ----------------------------------
+# (default: one episode + re-reset per case to keep the CPU suite short; SSD_DEEP_EPISODES scales it up)
+FEAT_EPISODES = max(1, EPISODES // 2)
+FEAT_CASES = [("cleanup", 8, 9, None), ("cleanup", 3, 8, [.12, .12, .12, .12, .06, .06, .06, .34]), ("harvest", 8, 8, None),
+              ("harvest", 4, 7, None)]
+
+
+@pytest.mark.parametrize("kind,n,nact,probs", FEAT_CASES, ids=["feat_%s_n%d_a%d" % c[:3] for c in FEAT_CASES])
+def test_reference_vs_oracle_feature_envs_full_episodes(oracle_lib, kind, n, nact, probs):
+    """CleanupFeatures / HarvestFeatures (cleanup_features.py:156-284, harvest_features.py:173-336) + subgame wrapper:
+    whole 1000-step episodes + re-resets of the LIVE reference against features_oracle.c — observations, positions,
+    orientations, the apple / waste cells, rewards before / after transfers, transfers, infos, theta, done, metrics."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefFeatEnv
+    seed, env_id = 700 + n, 41000 + 13 * n
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    amap = CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP
+    ref = RefFeatEnv(kind, n, seed, env_id, contract=True, horizon=1000)
+    orc = oracle_lib.FeatOracle(kind, 1, n, amap, horizon=1000, contract=contract, seed=seed, first_env_id=env_id)
+    rng = np.random.RandomState(11 * n + len(kind) + nact)
+    paid, eaten = 0, 0
+    for ep in range(FEAT_EPISODES + 1):
+        ctx = "features %s n=%d episode %d reset" % (kind, n, ep)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"][:, :orc.F], ctx)
+        st = orc.get_state()
+        for k in ("pos", "ori", "cells"):
+            gu.assert_same("reset " + k, st[k][0], r0[k], ctx)
+        gu.assert_same("reset theta", st["theta"][0], r0["theta"], ctx)
+        if ep == FEAT_EPISODES:
+            break
+        for t in range(1000):
+            a = rng.choice(nact, size=n, p=probs).astype(np.int32)
+            want = ref.step(a)
+            got = orc.step(a[None])
+            ctx = "features %s n=%d episode %d step %d" % (kind, n, ep, t + 1)
+            gu.assert_same("obs", got["obs"][0], want["obs"][:, :orc.F], ctx)
+            gu.assert_same("rew", got["rew"][0], want["rew"], ctx)
+            gu.assert_same("base_rew", got["base_rew"][0], want["base_rew"], ctx)
+            gu.assert_same("transfers", got["transfers"][0], want["transfers"], ctx)
+            gu.assert_same("info0", got["info"][0][:, 0], want["info0"], ctx)
+            gu.assert_same("info1", got["info"][0][:, 1], want["info1"], ctx)
+            gu.assert_same("done", bool(got["done"][0]), bool(want["done"]), ctx)
+            paid += int(np.count_nonzero(want["transfers"])); eaten += int(want["base_rew"].sum())
+            if t % 25 == 0 or t == 999:
+                st = orc.get_state()
+                for k in ("pos", "ori", "cells"):
+                    gu.assert_same(k, st[k][0], want[k], ctx)
+        raw = orc.metrics_raw()[0]
+        m = ref.metrics()
+        gu.assert_same("metric raw_env_rewards", np.float64(raw[1]), np.float64(m["raw_env_rewards"]), "episode %d" % ep)
+        gu.assert_same("metric transfers", np.float64(raw[2]), np.float64(m["transfers"]), "episode %d" % ep)
+    assert paid > 0 and eaten > 0          # the contract paid and apples were eaten: the interesting paths ran
+
+
+CAR_CASES = [(8, True), (4, True), (2, False)]
+
+
+@pytest.mark.parametrize("n,contract", CAR_CASES, ids=["car_n%d_%s" % (n, "contract" if c else "plain") for n, c in CAR_CASES])
+def test_reference_vs_oracle_selfdrive_many_episodes(oracle_lib, n, contract):
+    """SelfAcceleratingCarEnv (+ SelfdriveContractDistprop; self_driving_car_accelerate.py:49-250, contract_list.py:66-102):
+    many whole episodes of the LIVE reference against selfdrive_oracle.c, every output by bit pattern."""
+    from oracle.ref_harness import RefCarEnv
+    seed, env_id = 800 + n, 51000 + 7 * n
+    ref = RefCarEnv(n, seed, env_id, contract=contract)
+    orc = oracle_lib.CarOracle(1, n, contract=contract, seed=seed, first_env_id=env_id)
+    rng = np.random.RandomState(3 * n + 1)
+    D = orc.D
+    steps_total, paid, overtakes = 0, 0, 0
+    for ep in range(10 * EPISODES):
+        ctx = "selfdrive n=%d episode %d reset" % (n, ep)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"][:, :D], ctx)
+        if contract:
+            gu.assert_same("reset theta", orc.get_state()["theta"][0], r0["theta"], ctx)
+        scale = [0.15, 0.05, 0.3][ep % 3]
+        for t in range(2000):
+            a = (rng.uniform(-0.7, 1.0, size=n) * scale).astype(np.float32)
+            want = ref.step(a)
+            got = orc.step(a[None])
+            ctx = "selfdrive n=%d episode %d step %d" % (n, ep, t + 1)
+            act = want["active"].astype(bool)
+            gu.assert_same("obs", got["obs"][0][act], want["obs"][act][:, :D], ctx)
+            gu.assert_same("rew", got["rew"][0], want["rew"], ctx)
+            gu.assert_same("done", got["done"][0], want["done"], ctx)
+            gu.assert_same("just_passed", got["info"][0][:, 0].astype(np.uint8), want["just_passed"], ctx)
+            first = int(np.argmax(act))
+            gu.assert_same("ambulance_rank", np.float64(got["info"][0][first, 2]), want["ambulance_rank"], ctx)
+            gu.assert_same("ambulance_dist_to_front", np.float64(got["info"][0][first, 3]), want["ambulance_dist_to_front"], ctx)
+            st = orc.get_state()
+            gu.assert_same("pos", st["pos"][0], want["pos"], ctx)
+            gu.assert_same("vel", st["vel"][0], want["vel"], ctx)
+            gu.assert_same("metric transfers", np.float64(st["transfers"][0]), want["metric_transfers"], ctx)
+            if contract:
+                gu.assert_same("base_rew", got["base_rew"][0], want["base_rew"], ctx)
+                gu.assert_same("transfers", got["transfers"][0], want["transfers"], ctx)
+                paid += int(np.count_nonzero(want["transfers"]))
+            steps_total += 1
+            if want["done"][-1]:
+                break
+        else:
+            raise AssertionError("episode did not end")
+    assert steps_total > 500
+    assert (paid > 0) == bool(contract)
