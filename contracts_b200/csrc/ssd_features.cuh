@@ -266,8 +266,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     const bool stepping = !RESET_ONLY && active && !doreset;
     int nA = stepping ? (int)s_rec[FR_NA] : 0, nW = stepping ? (int)s_rec[FR_NW] : 0;
     if (!RESET_ONLY) {
-        for (int j = a; j * 16 < p.LA; j += 8) if (j * 16 < nA) cp_async16(s_al + 16 * j, glist + 16 * j);
-        for (int j = a; j * 16 < p.LW; j += 8) if (j * 16 < nW) cp_async16(s_wl + 16 * j, glist + p.LA + 16 * j);
+        // (LA, LW <= 256: at most two 16-byte chunks per lane and list)
+        if (a * 16 < nA) cp_async16(s_al + 16 * a, glist + 16 * a);
+        if ((a + 8) * 16 < nA) cp_async16(s_al + 16 * (a + 8), glist + 16 * (a + 8));
+        if (a * 16 < nW) cp_async16(s_wl + 16 * a, glist + p.LA + 16 * a);
+        if ((a + 8) * 16 < nW) cp_async16(s_wl + 16 * (a + 8), glist + p.LA + 16 * (a + 8));
     }
     uint32_t episode = c3 & 0x7fffffffu;
     const uint32_t env_id = p.first_env_id + (uint32_t)env;
@@ -471,19 +474,18 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     __syncwarp();
     const uint32_t elig = active ? s_scr[a] : 0u;
     const int ecnt = __popc(elig);
-    const int eincl = oct_scan_incl(ecnt, a);
-    const int eexcl = eincl - ecnt;
-    const int nelig = __shfl_sync(FULLMASK, eincl, 7, 8);
+    // (cleanup: the waste candidates are counted in the same scan, in the upper half of the word)
+    const uint32_t thrA = (CLEANUP && active) ? __ldg(p.thr_apple + nW) : 0u;       // compute_probabilities by the waste count
+    const bool won = CLEANUP && active && __ldg(p.waste_on + nW) != 0;
+    // at most one waste point: the first success over the points that are not waste, in point order; its draws
+    // follow the apple draws in the step's stream (candidate rank j <-> draw nelig + j)
+    const uint32_t cwm = won ? (~s_rec[FR_WM + a] & feat_valid_word(p.n_waste, a)) : 0u;
+    const int ccnt = __popc(cwm);
+    const int pincl = oct_scan_incl(ecnt | (ccnt << 16), a);
+    const int ptot = __shfl_sync(FULLMASK, pincl, 7, 8);
+    const int eexcl = (pincl & 0xFFFF) - ecnt, nelig = ptot & 0xFFFF;
     if (CLEANUP) {
-        const uint32_t thrA = active ? __ldg(p.thr_apple + nW) : 0u;       // compute_probabilities by the waste count
-        const bool won = active && __ldg(p.waste_on + nW) != 0;
-        // at most one waste point: the first success over the points that are not waste, in point order; its draws
-        // follow the apple draws in the step's stream (candidate rank j <-> draw nelig + j)
-        const uint32_t cwm = won ? (~s_rec[FR_WM + a] & feat_valid_word(p.n_waste, a)) : 0u;
-        const int ccnt = __popc(cwm);
-        const int cincl = oct_scan_incl(ccnt, a);
-        const int cexcl = cincl - ccnt;
-        const int ncand = __shfl_sync(FULLMASK, cincl, 7, 8);
+        const int cexcl = (pincl >> 16) - ccnt, ncand = ptot >> 16;
         const int k0 = nelig;
         // ONE pass over the Philox blocks: the apple blocks (when the apple probability is not 0 — otherwise r < 0 never
         // holds and the draws are consumed unseen) and, with them, the blocks of the first FEAT_WASTE_DRAWS waste draws
@@ -521,19 +523,21 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
                 sb = __funnelshift_r(lo, hi, (uint32_t)(eexcl & 31));
                 if (ecnt < 32) sb &= (1u << ecnt) - 1u;
             }
-            const int scnt = __popc(sb);
-            const int sincl = oct_scan_incl(scnt, a);
-            const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
-            int lp = nA + sincl - scnt;
+            if (__any_sync(FULLMASK, sb != 0u)) {
+                const int scnt = __popc(sb);
+                const int sincl = oct_scan_incl(scnt, a);
+                const int stot = __shfl_sync(FULLMASK, sincl, 7, 8);
+                int lp = nA + sincl - scnt;
 #pragma unroll 1
-            while (sb) {
-                const int j = __ffs(sb) - 1; sb &= sb - 1;
-                const int bit = select_bit(elig, j);
-                s_rec[FR_AM + a] |= 1u << bit;
-                s_al[lp++] = (uint8_t)(a * 32 + bit);
+                while (sb) {
+                    const int j = __ffs(sb) - 1; sb &= sb - 1;
+                    const int bit = select_bit(elig, j);
+                    s_rec[FR_AM + a] |= 1u << bit;
+                    s_al[lp++] = (uint8_t)(a * 32 + bit);
+                }
+                nA += stot;
+                a_chg = a_chg || stot != 0;
             }
-            nA += stot;
-            a_chg = a_chg || stot != 0;
         }
         wbits = oct_or(wbits);
         int covered = wsearch ? min(4 * bw1 - k0, 32) : 0;                 // candidate ranks looked at so far
@@ -776,8 +780,14 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     __syncwarp();
     if (active) {
         *reinterpret_cast<uint4*>(grec + 4 * a) = *reinterpret_cast<const uint4*>(s_rec + 4 * a);
-        if (a_chg) for (int j = a; j * 16 < nA; j += 8) *reinterpret_cast<uint4*>(glist + 16 * j) = *reinterpret_cast<const uint4*>(s_al + 16 * j);
-        if (w_chg) for (int j = a; j * 16 < nW; j += 8) *reinterpret_cast<uint4*>(glist + p.LA + 16 * j) = *reinterpret_cast<const uint4*>(s_wl + 16 * j);
+        if (a_chg) {
+            if (a * 16 < nA) *reinterpret_cast<uint4*>(glist + 16 * a) = *reinterpret_cast<const uint4*>(s_al + 16 * a);
+            if ((a + 8) * 16 < nA) *reinterpret_cast<uint4*>(glist + 16 * (a + 8)) = *reinterpret_cast<const uint4*>(s_al + 16 * (a + 8));
+        }
+        if (w_chg) {
+            if (a * 16 < nW) *reinterpret_cast<uint4*>(glist + p.LA + 16 * a) = *reinterpret_cast<const uint4*>(s_wl + 16 * a);
+            if ((a + 8) * 16 < nW) *reinterpret_cast<uint4*>(glist + p.LA + 16 * (a + 8)) = *reinterpret_cast<const uint4*>(s_wl + 16 * (a + 8));
+        }
     }
     __syncwarp();                                    // the octet's shared state is rewritten by the next round
     }
