@@ -313,6 +313,36 @@ static int setup_grid(ssd_handle* h)
     if ((rc = upload(h, waste_on, &p.waste_on))) return rc;
     if ((rc = upload(h, tile0, &p.tile0))) return rc;
     if ((rc = upload(h, cell_info, &p.cell_info))) return rc;
+    {   // the static part of a beam fired from (cell, orientation): update_map_fire (map_env.py:721-814) walks three rays —
+        // centre: along 1..5; right / left: beside the shooter, along 0..4 — and a ray stops at a wall or outside the map
+        std::vector<uint4> beam_tab((size_t)H * p.Wp * 4 * 2, make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+        const int RAYPOS[3] = { 0, 9, 16 };                               // RAY_L, RAY_C, RAY_R (ssd_grid2.cuh)
+        for (int r = 0; r < H; r++)
+            for (int col = 0; col < W; col++)
+                for (int o = 0; o < 4; o++) {
+                    const int dr = o == ORI_UP ? -1 : (o == ORI_DOWN ? 1 : 0), dc = o == ORI_RIGHT ? 1 : (o == ORI_LEFT ? -1 : 0);
+                    const int o1 = (o + 1) & 3;                           // right = clockwise of the firing direction
+                    const int rr = o1 == ORI_UP ? -1 : (o1 == ORI_DOWN ? 1 : 0), rcl = o1 == ORI_RIGHT ? 1 : (o1 == ORI_LEFT ? -1 : 0);
+                    uint32_t wall = 0;
+                    uint8_t widx[16];
+                    memset(widx, 0xFF, sizeof(widx));
+                    for (int b = 0; b < 3; b++)                           // left, centre, right
+                        for (int i = 0; i < 5; i++) {
+                            const int along = b == 1 ? i + 1 : i, across = b == 0 ? -1 : (b == 1 ? 0 : 1);
+                            const int cr = r + along * dr + across * rr, cc = col + along * dc + across * rcl;
+                            uint16_t info = CI_WALL;
+                            if (cr >= 0 && cr < H && cc >= 0 && cc < W) info = cell_info[cr * p.Wp + cc];
+                            if (info & CI_WALL) wall |= 1u << (RAYPOS[b] + i);
+                            if (info & CI_WASTE) widx[5 * b + i] = (uint8_t)(info & CI_IDX);
+                        }
+                    uint32_t w4[4];
+                    memcpy(w4, widx, 16);
+                    uint4* e = &beam_tab[((size_t)(r * p.Wp + col) * 4 + o) * 2];
+                    e[0] = make_uint4(wall, w4[0], w4[1], w4[2]);
+                    e[1] = make_uint4(w4[3], 0u, 0u, 0u);
+                }
+        if ((rc = upload(h, beam_tab, &p.beam_tab))) return rc;
+    }
     if ((rc = upload(h, base_map, &p.base_map))) return rc;
 
     // shared memory of the observe / reset kernels: CTA tables, then per warp [T | T2 | stage | misc]

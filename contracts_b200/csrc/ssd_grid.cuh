@@ -95,6 +95,9 @@ struct GridParams {
     const uint8_t* waste_on;     // [n_waste + 1]
     const uint8_t* tile0;        // [tile_r16 + tile2 bytes]: static T | T2 with every dynamic cell OFF (apple point empty, waste point river)
     const uint16_t* cell_info;   // [H * Wp] CI_* words (logic kernel)
+    const uint4* beam_tab;       // [H * Wp][4 orientations][2]: a beam's static part — .x of the first word: wall mask of the 15 ray
+                                 // cells (RAY_* bit layout, cells outside the map are walls); bytes 4..18: the cells' waste-point
+                                 // indices (0xFF: not a waste point), order left ray 0-4, centre 0-4, right 0-4
     const uint8_t* base_map;     // [map_bytes] compact static codes, dynamic cells OFF (views, get / set state)
     const uint16_t* apple_c;     // compact offsets (row * Wp + col) of the points (views, get / set state)
     const uint16_t* waste_c;

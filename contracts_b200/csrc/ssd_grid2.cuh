@@ -100,28 +100,25 @@ __device__ __noinline__ void g2_hit(const uint32_t* ags /* lane-strided */, int 
     if (victim >= 0) res[victim * 32] -= 50u << RS_REWARD_SHIFT;            // Agent.hit(b"F"): -50 (Agent.py:224-226)
 }
 
-__device__ __forceinline__ int g2_fire(const uint16_t* ci, uint32_t* wmk, uint8_t* beam, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN],
-                                       const uint32_t* ags, int n, uint32_t* res, bool clean, int H, int W, int Wp)
+__device__ __forceinline__ int g2_fire(const uint4* btab, int mwords, uint32_t* wmk, uint8_t* beam, uint32_t shooter, const uint32_t (&agc)[SSD_MAXN],
+                                       const uint32_t* ags, int n, uint32_t* res, bool clean, int Wp)
 {
     const int row = (int)(shooter & 255u), col = (int)((shooter >> 8) & 255u), ori = (int)((shooter >> 16) & 3u);
-    const int dr = ori_dr(ori), dc = ori_dc(ori);
-    const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);       // right = clockwise of dir
-    // cells of the map in front of the shooter; the side rays start on the shooter's own row / column
-    const int ahead = ori == ORI_UP ? row : (ori == ORI_DOWN ? H - 1 - row : (ori == ORI_LEFT ? col : W - 1 - col));
-    const int n0 = min(ahead, 5), ns = min(ahead + 1, 5);
-    const bool okr = (unsigned)(row + rr) < (unsigned)H && (unsigned)(col + rcl) < (unsigned)W;
-    const bool okl = (unsigned)(row - rr) < (unsigned)H && (unsigned)(col - rcl) < (unsigned)W;
-    const int step = dr * Wp + dc, side = rr * Wp + rcl, base = row * Wp + col;
-    const int nr = okr ? ns : 0, nl = okl ? ns : 0;
-    uint32_t wall = 0, waste = 0;
+    // the static part of the beam (which ray cells are walls or outside the map, which are waste points) is a table row
+    const uint4* trow = btab + ((size_t)(row * Wp + col) * 4 + ori) * 2;
+    const uint4 t0 = __ldg(trow);
+    const uint32_t wall = t0.x;
+    uint32_t waste = 0;
+    uint32_t widx[4] = { t0.y, t0.z, t0.w, 0u };
+    if (clean) {
+        widx[3] = __ldg(trow + 1).x;
+        const uint32_t imask = (uint32_t)(mwords * 32 - 1);
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const uint32_t cc = i < n0 ? (uint32_t)ci[base + (i + 1) * step] : CI_WALL;
-        const uint32_t cr = i < nr ? (uint32_t)ci[base + side + i * step] : CI_WALL;
-        const uint32_t cl = i < nl ? (uint32_t)ci[base - side + i * step] : CI_WALL;
-        wall |= ((cl >> 13) & 1u) << (RAY_L + i) | ((cc >> 13) & 1u) << (RAY_C + i) | ((cr >> 13) & 1u) << (RAY_R + i);
-        if (clean)
-            waste |= cell_has(wmk, cl, 15) << (RAY_L + i) | cell_has(wmk, cc, 15) << (RAY_C + i) | cell_has(wmk, cr, 15) << (RAY_R + i);
+        for (int k = 0; k < 15; k++) {
+            const uint32_t idx = (widx[k >> 2] >> (8 * (k & 3))) & 255u;
+            const int pos = (k < 5 ? RAY_L : (k < 10 ? RAY_C - 5 : RAY_R - 10)) + k;
+            waste |= (idx != 255u ? mask_bit(wmk, idx & imask) : 0u) << pos;
+        }
     }
     // agents on the rays
     const uint32_t sel = ori == ORI_UP ? 0x3214u : (ori == ORI_DOWN ? 0x3250u : (ori == ORI_RIGHT ? 0x3201u : 0x3245u));
@@ -143,15 +140,19 @@ __device__ __forceinline__ int g2_fire(const uint16_t* ci, uint32_t* wmk, uint8_
         const uint32_t s5 = (stop >> sh) & 31u;
         const uint32_t f = (s5 & (0u - s5)) << sh;                            // the ray's first stopping cell (0: none)
         if (beam) {                                                            // firing_points -> beam_pos (map_env.py:789,812)
+            const int dr = ori_dr(ori), dc = ori_dc(ori);
+            const int rr = ori_dr((ori + 1) & 3), rcl = ori_dc((ori + 1) & 3);  // right = clockwise of dir
+            const int step = dr * Wp + dc, side = rr * Wp + rcl, base = row * Wp + col;
             const int cnt = f ? __ffs(f) - 1 - sh + ((f & ~wall) ? 1 : 0) : 5; // cells up to and including a non-wall stop
             for (int i = 0; i < cnt; i++)
                 beam[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step] = clean ? (uint8_t)'C' : (uint8_t)'F';
         }
         if (f & ~wall) {
             if (f & waste) {                                                   // CLEAN: H -> R (cleanup_new.py:285-290)
-                const int i = __ffs(f) - 1 - sh;
-                const uint32_t c = ci[base + (b == 0 ? -side : (b == 1 ? step : side)) + i * step];
-                wmk[((c & CI_IDX) >> 5) * 32] &= ~(1u << (c & 31u));
+                const int k = 5 * b + __ffs(f) - 1 - sh;                       // the cell's place in the table row
+                const uint32_t wk = k < 8 ? (k < 4 ? widx[0] : widx[1]) : (k < 12 ? widx[2] : widx[3]);   // (no dynamic register index)
+                const uint32_t c = (wk >> (8 * (k & 3))) & 255u;
+                wmk[(c >> 5) * 32] &= ~(1u << (c & 31u));
                 nup++;
             }
             if (!clean && (f & occ)) g2_hit(ags, n, res, cs, sel, (uint32_t)(__ffs(f) - 1));
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, LOGIC_MIN_BLOCKS) grid_logic_ke
             }
             rem &= ~(1u << s);
             const bool clean = (cleanm >> s) & 1u;
-            const int nup = g2_fire(ci, wmk, p.beam ? p.beam + (size_t)env * p.map_bytes : nullptr, ags[s * 32], agc, ags, n, res, clean, H, W, Wp);
+            const int nup = g2_fire(p.beam_tab, mw, wmk, p.beam ? p.beam + (size_t)env * p.map_bytes : nullptr, ags[s * 32], agc, ags, n, res, clean, Wp);
             if (clean) { res[s * 32] |= (uint32_t)nup; ncleaned += nup; }
             else res[s * 32] -= 1u << RS_REWARD_SHIFT;                    // fire cost (Agent.py:217-219)
         }
