@@ -18,6 +18,7 @@
 #include "../../include/ssd_b200.h"
 #include "ssd_grid.cuh"
 #include "ssd_grid2.cuh"
+#include "ssd_grid3.cuh"
 #include "ssd_views.cuh"
 #include "ssd_selfdrive.cuh"
 #include "ssd_features.cuh"
@@ -38,6 +39,8 @@ struct ssd_handle {
     bool pdl;                // programmatic dependent launch of the observe / reset kernels behind the logic / observe kernels
     int obs_lay;             // observe kernel specialisation the handle qualifies for (obs_layout_id)
     int logic_lay;           // logic kernel specialisation (logic_layout_id)
+    bool logic8;             // the eight-lanes-per-env logic kernel (ssd_grid3.cuh): small batches; SSD_LOGIC8=0 / 1 forces the choice
+    int logic8_smem, logic8_blocks;
     cudaEvent_t tev[3];      // ssd_enable_timing: before the logic kernel / between / after the observe (+ reward) kernel
     bool timing;
     uint32_t* d_res;         // u32 [E][8] per-agent result words passed between the step's kernels
@@ -390,6 +393,21 @@ static int setup_grid(ssd_handle* h)
     h->obs_blocks = want_obs < sms * per_sm2 ? want_obs : sms * per_sm2;
     h->logic_smem = round_up(H * p.Wp * 2, 16) + LOGIC_WARPS * 2 * p.mw * 32 * 4;
     h->logic_lay = logic_layout_id(p);
+    {   // eight lanes per env: persistent CTAs, as many as are resident at once
+        // Measured (1 x B200): at E = 16384 (n = 4) the octet kernel takes 13.6 us against 15.8 us for the thread-per-env kernel, whose
+        // time there is the latency of one warp's chain; at E = 131072 (n = 8) 75 us against 45 us — it executes ~3 x the warp-
+        // instructions per env (sequential beams four envs per warp-iteration instead of 32) and loses once the GPU is full.
+        const char* e8 = getenv("SSD_LOGIC8");
+        h->logic8 = e8 ? e8[0] != '0' : p.E <= 24576;
+        h->logic8_smem = round_up(H * p.Wp * 2, 16) + L8_ENVS_PER_CTA * L8_OCT_WORDS * 4;
+        const void* fn8 = cleanup ? (const void*)grid_logic8_kernel<SSD_ENV_CLEANUP> : (const void*)grid_logic8_kernel<SSD_ENV_HARVEST>;
+        CUDA_TRY(h, cudaFuncSetAttribute(fn8, cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic8_smem));
+        int dev8 = 0, sms8 = 0, per_sm8 = 0;
+        CUDA_TRY(h, cudaGetDevice(&dev8));
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms8, cudaDevAttrMultiProcessorCount, dev8));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, fn8, L8_THREADS, (size_t)h->logic8_smem));
+        h->logic8_blocks = std::max(1, std::min((p.E + L8_ENVS_PER_CTA - 1) / L8_ENVS_PER_CTA, sms8 * std::max(per_sm8, 1)));
+    }
     CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
     if (h->logic_lay)
         CUDA_TRY(h, cudaFuncSetAttribute((const void*)logic_kernel_fn(c.env_kind, h->logic_lay), cudaFuncAttributeMaxDynamicSharedMemorySize, h->logic_smem));
@@ -910,7 +928,12 @@ static int launch_step(ssd_handle* h, const StepIO& k, cudaStream_t s, const Hos
     if (p.beam) CUDA_TRY(h, cudaMemsetAsync(p.beam, 0, (size_t)p.E * p.map_bytes, s));       // self.beam_pos = [] (map_env.py:231)
     const int lb = (p.E + LOGIC_THREADS - 1) / LOGIC_THREADS;
     if (h->timing) cudaEventRecord(h->tev[0], s);
-    if (h->pdl && !h->timing && !p.beam)
+    if (h->logic8) {
+        const logic_kernel_t fn8 = p.kind == SSD_ENV_CLEANUP ? grid_logic8_kernel<SSD_ENV_CLEANUP> : grid_logic8_kernel<SSD_ENV_HARVEST>;
+        if (h->pdl && !h->timing && !p.beam)
+            CUDA_TRY(h, launch_pdl(fn8, dim3(h->logic8_blocks), dim3(L8_THREADS), (size_t)h->logic8_smem, s, p, k, h->d_res));
+        else fn8<<<h->logic8_blocks, L8_THREADS, h->logic8_smem, s>>>(p, k, h->d_res);
+    } else if (h->pdl && !h->timing && !p.beam)
         CUDA_TRY(h, launch_pdl(logic_kernel_fn(p.kind, h->logic_lay), dim3(lb), dim3(LOGIC_THREADS), (size_t)h->logic_smem, s, p, k, h->d_res));
     else logic_kernel_fn(p.kind, p.beam ? 0 : h->logic_lay)<<<lb, LOGIC_THREADS, h->logic_smem, s>>>(p, k, h->d_res);
     h->launches++;

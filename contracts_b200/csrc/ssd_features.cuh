@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     const int pincl = oct_scan_incl(ecnt | (ccnt << 16), a);
     const int ptot = __shfl_sync(FULLMASK, pincl, 7, 8);
     const int eexcl = (pincl & 0xFFFF) - ecnt, nelig = ptot & 0xFFFF;
-    if (CLEANUP) {
+    if constexpr (CLEANUP) {
         const int cexcl = (pincl >> 16) - ccnt, ncand = ptot >> 16;
         const int k0 = nelig;
         // ONE pass over the Philox blocks: the apple blocks (when the apple probability is not 0 — otherwise r < 0 never
