@@ -3,7 +3,7 @@ import pytest
 
 import golden_util as gu
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("logic_variant")]
 
 
 @pytest.mark.parametrize("name", gu.fixture_names())

@@ -72,7 +72,7 @@ def test_full_size_rollout_properties(oracle_lib, kind, E, n, nact, contract):
         assert torch.equal(st[k], st2[k]), k
 
 
-def test_step_host_equals_step():
+def test_step_host_equals_step(logic_variant):
     """ssd_step_host (host buffers, overlapped D2H copy) produces exactly what ssd_step + explicit copies produce."""
     import torch
     from contracts_b200.batched import BatchedGridEnv
@@ -99,7 +99,7 @@ def test_step_host_equals_step():
                                                      ("cleanup_new", "CleanupContract", 700, 5, 0.0),
                                                      ("harvest_new", "HarvestFeaturemodLocalContract", 2000, 4, 2.5),
                                                      ("cleanup_new", None, 500, 3, 0.0)])
-def test_step_host_async_equals_step(kind, contract, E, n, theta):
+def test_step_host_async_equals_step(logic_variant, kind, contract, E, n, theta):
     """ssd_step_host_async / _wait (double-buffered slots, compact int8 + sparse float64 result block, predicted copy
     size) delivers bit for bit what ssd_step produces: observations, dones, and — after ssd_host_result_expand — the
     float64 rewards.  Two steps are kept in flight, as the pipelined caller does."""
@@ -252,7 +252,7 @@ def test_handle_on_non_current_device():
 @pytest.mark.parametrize("kind,contract,n,negotiate", [("cleanup_new", "CleanupContract", 8, True), ("cleanup_new", "CleanupContract", 3, False),
                                                        ("harvest_new", "HarvestFeaturemodLocalContract", 4, True),
                                                        ("cleanup_new", None, 5, False)])
-def test_auto_reset_equals_step_reset_negotiate(kind, contract, n, negotiate):
+def test_auto_reset_equals_step_reset_negotiate(logic_variant, kind, contract, n, negotiate):
     """ssd_step_io.auto_reset (finished envs restart — and negotiate — inside the step) leaves exactly the state, outputs
     and episode statistics that step + reset(mask = done) + negotiate(mask = done) leave.  Horizons are staggered through
     set_state(t) so that a few envs finish in every step, as in a vectorised sampler's steady state."""
