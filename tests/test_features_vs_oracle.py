@@ -167,3 +167,42 @@ def test_feature_step_host_async_equals_step(kind, n, E, theta):
     with pytest.raises(_lib.SsdError):
         b.step_host_async(acts[2], res[0])
     b.step_host_wait(t0); b.step_host_wait(t1)
+
+
+# custom maps: cramped ones (agents block each other, share squares, fire into walls at point-blank range), a cleanup map
+# without waste points and one whose point lists need all eight mask words
+_CRAMPED_CLEANUP = ["@@@@@@", "@PPPP@", "@PPPP@", "@HBBR@", "@PPPP@", "@@@@@@"]
+_CRAMPED_HARVEST = ["@@@@@@", "@PPPP@", "@PAAP@", "@PAAP@", "@PPPP@", "@@@@@@"]
+_NO_WASTE_CLEANUP = ["@@@@@@@", "@PPBBP@", "@PBBBP@", "@PPSSP@", "@@@@@@@"]
+_BIG_CLEANUP = ["@" * 34] + ["@" + "P" * 4 + "B" * 12 + "R" * 8 + "H" * 8 + "@"] * 15 + ["@" * 34]      # 180 apple, 240 waste points
+_BIG_HARVEST = ["@" * 30] + ["@" + "P" * 4 + "A" * 24 + "@"] * 10 + ["@" * 30]                         # 240 apple points
+
+
+@pytest.mark.parametrize("kind,amap,n,nact", [
+    ("cleanup", _CRAMPED_CLEANUP, 8, 9), ("cleanup", _CRAMPED_CLEANUP, 3, 9), ("harvest", _CRAMPED_HARVEST, 8, 8),
+    ("harvest", _CRAMPED_HARVEST, 1, 8), ("cleanup", _NO_WASTE_CLEANUP, 4, 9), ("cleanup", _BIG_CLEANUP, 8, 9),
+    ("harvest", _BIG_HARVEST, 7, 8)], ids=["cramped_cleanup_n8", "cramped_cleanup_n3", "cramped_harvest_n8", "cramped_harvest_n1",
+                                          "cleanup_no_waste_n4", "big_cleanup_n8", "big_harvest_n7"])
+def test_feature_rollout_custom_maps(oracle_lib, kind, amap, n, nact):
+    import torch
+    from contracts_b200.features import BatchedFeatureEnv
+    E, steps = 50, 150
+    c = _contract(kind) if n > 1 else None
+    env = BatchedFeatureEnv(kind, E, n, ascii_map=amap, horizon=60, contract=c, seed=11, first_env_id=77)
+    orc = oracle_lib.FeatOracle(kind, E, n, amap, horizon=60, contract=c, seed=11, first_env_id=77)
+    gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "reset")
+    _compare_state(env, orc, "reset")
+    rng = np.random.default_rng(n)
+    for t in range(steps):
+        a = rng.integers(0, nact, size=(E, n))
+        o = orc.step(a)
+        env.step(torch.as_tensor(a.astype(np.uint8)).cuda())
+        ctx = "%s custom map n=%d step %d" % (kind, n, t)
+        _compare_step(env, o, ctx)
+        _compare_state(env, orc, ctx)
+        if o["done"].any():
+            m = o["done"].astype(np.uint8)
+            want = orc.reset(m)
+            got = env.reset(torch.as_tensor(m).cuda()).cpu().numpy()
+            gu.assert_same("reset obs", got[m.astype(bool)], want[m.astype(bool)], ctx)
+    gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
