@@ -491,7 +491,7 @@ static int setup_features(ssd_handle* h)
     p.n_apple = (int)apple_rc.size(); p.n_waste = (int)waste_rc.size(); p.n_spawn = (int)spawn_rc.size(); p.potential = p.n_waste;
     p.nwa = (p.n_apple + 31) / 32; p.nww = (p.n_waste + 31) / 32;
     p.LA = std::max(16, (p.n_apple + 15) / 16 * 16); p.LW = std::max(16, (p.n_waste + 15) / 16 * 16); p.LS = p.LA + p.LW;
-    p.sm_static = 2 * (p.LA + p.LW); p.oct_bytes = 256 + p.LA + p.LW;
+    p.sm_static = 2 * 2 * 32 * FEAT_MASK_WORDS; p.oct_bytes = 256 + p.LA + p.LW;     // two 256-entry uint16 point tables
     const int nwa = std::max(p.nwa, 1), nww = std::max(p.nww, 1);
     // 3x3 neighbours of an apple point (j*j + k*k <= APPLE_RADIUS = 2, harvest_features.py:139-151) as a mask over the points
     std::vector<uint32_t> nbr_mask(std::max<size_t>(apple_rc.size(), 1) * nwa, 0u);

@@ -234,10 +234,14 @@ __global__ void __launch_bounds__(FEAT_THREADS, FEAT_MIN_BLOCKS) feat_kernel(con
     extern __shared__ __align__(16) uint8_t fsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, a = lane & 7, obase = lane & 24;
     const int n = p.n;
+    // row << 8 | col of every point, 256 entries per table: the closest search also looks up the (ignored) bytes behind a
+    // list's end in its last word, which may hold anything
     uint16_t* s_arc = reinterpret_cast<uint16_t*>(fsm);
-    uint16_t* s_wrc = s_arc + p.LA;
-    for (int i = threadIdx.x; i < p.n_apple; i += FEAT_THREADS) s_arc[i] = __ldg(p.apple_rc + i);
-    for (int i = threadIdx.x; i < p.n_waste; i += FEAT_THREADS) s_wrc[i] = __ldg(p.waste_rc + i);
+    uint16_t* s_wrc = s_arc + 32 * FEAT_MASK_WORDS;
+    for (int i = threadIdx.x; i < 32 * FEAT_MASK_WORDS; i += FEAT_THREADS) {
+        s_arc[i] = i < p.n_apple ? __ldg(p.apple_rc + i) : (uint16_t)0;
+        s_wrc[i] = i < p.n_waste ? __ldg(p.waste_rc + i) : (uint16_t)0;
+    }
     __syncthreads();
     // persistent CTAs: a warp takes four envs per round
     const int ngroups = (p.E + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
