@@ -116,8 +116,11 @@ class GridOracle:
             raise ValueError("inequity_averse_reward needs more than one agent (map_env.py:294)")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().oracle_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:        # (module globals are gone at interpreter shutdown)
+            try:
+                lib().oracle_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, mask=None):
@@ -252,8 +255,11 @@ class CarOracle:
         self.episode = np.full(self.E, -1, dtype=np.int64)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().car_oracle_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:        # (module globals are gone at interpreter shutdown)
+            try:
+                lib().car_oracle_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, mask=None):
@@ -306,8 +312,11 @@ class FeatOracle:
         self.episode = np.full(self.E, -1, dtype=np.int64)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().feat_oracle_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:        # (module globals are gone at interpreter shutdown)
+            try:
+                lib().feat_oracle_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, mask=None):
