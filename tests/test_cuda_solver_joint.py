@@ -192,7 +192,7 @@ def test_policy_inputs_match_vision_net_preprocessing(kind, n, E, padded):
 
 
 @pytest.mark.parametrize("name", gu.fixture_names("render_"))
-def test_render_with_beams_matches_reference(name):
+def test_render_with_beams_matches_reference(logic_variant, name):
     """full_map_to_colors incl. the beams of the last step (map_env.py:354-375,389-392): batched path and dict API."""
     import torch
     from contracts_b200.batched import BatchedGridEnv
@@ -220,7 +220,7 @@ def test_render_with_beams_matches_reference(name):
             gu.assert_same("frame (dict API)", dropin.full_map_to_colors(), fx["obs"][ep, t], "ep %d step %d" % (ep, t))
 
 
-def test_render_matches_oracle_masked_reset(oracle_lib):
+def test_render_matches_oracle_masked_reset(logic_variant, oracle_lib):
     """Beam overlays across a larger batch, cleared per env by masked resets."""
     import torch
     from contracts_b200.batched import BatchedGridEnv
