@@ -451,7 +451,13 @@ static int setup_selfdrive(ssd_handle* h)
     h->car_smem = CAR_WARPS * p.warp_doubles * (int)sizeof(double);
     CUDA_TRY(h, cudaFuncSetAttribute((const void*)car_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->car_smem));
     CUDA_TRY(h, cudaFuncSetAttribute((const void*)car_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->car_smem));
-    h->grid_blocks = (p.E + CAR_ENVS_PER_CTA - 1) / CAR_ENVS_PER_CTA;
+    {   // persistent CTAs: as many as are resident at once
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(h, cudaGetDevice(&dev));
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)car_kernel<false>, CAR_THREADS, (size_t)h->car_smem));
+        h->grid_blocks = std::max(1, std::min((p.E + CAR_ENVS_PER_CTA - 1) / CAR_ENVS_PER_CTA, sms * std::max(per_sm, 1)));
+    }
     return SSD_OK;
 }
 

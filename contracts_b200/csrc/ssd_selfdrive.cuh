@@ -13,7 +13,8 @@
 // warp copies the four envs' rows out as one contiguous run of 16-byte stores; the cross-car parts of the step — crossing
 // order, dist_to_front, make_new_pos_consistent, the contract's redistribution — happen on a few percent of the steps and
 // run as plain scalar code on the octet's positions in shared memory.  State stays struct-of-arrays ([car][env]: a warp's
-// loads touch whole 32-byte sectors).  Everything is float64 and rounds like the reference (-fmad=false).
+// loads touch whole 32-byte sectors).  CTAs are persistent and request a warp's next four envs' inputs before they process the
+// current four (+4 %).  Everything is float64 and rounds like the reference (-fmad=false).
 #pragma once
 #include "ssd_common.cuh"
 
@@ -166,22 +167,43 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
     double* o_pos = w_stage + (p.warp_doubles - 4 * CAR_OCT_DOUBLES) + oct * CAR_OCT_DOUBLES;
     double* o_new = o_pos + 8;
     double* o_vel = o_pos + 16;
-    const int env_raw = (blockIdx.x * CAR_WARPS + warp) * 4 + oct;
-    bool live = env_raw < p.E;
-    const int env = live ? env_raw : p.E - 1;
-    if (RESET_ONLY && mask) live = live && mask[env] != 0;
-    if (RESET_ONLY && !__any_sync(CAR_FULL, live)) return;
     const bool kv = k < n;
+    // Persistent CTAs; the inputs of a warp's NEXT four envs are requested before the current four are processed, so the
+    // one round of global loads a step needs (its only long-latency wait) overlaps a whole round of work.
+    struct In { uint32_t meta, crossed; double theta, pos, vel, dist; float act; int t; int env; bool live; };
+    auto fetch = [&](int g) {
+        In in = { 0u, 0u, 0.0, 0.0, 0.0, -1.0, 0.0f, 0, p.E - 1, false };
+        const int e_raw = (g * CAR_WARPS + warp) * 4 + oct;
+        in.live = e_raw < p.E;
+        in.env = in.live ? e_raw : p.E - 1;
+        if (RESET_ONLY && mask) in.live = in.live && mask[in.env] != 0;
+        if (in.live) {
+            in.meta = p.meta[in.env];
+            if (!RESET_ONLY) {
+                in.crossed = p.crossed[in.env]; in.theta = p.theta[in.env];
+                if (kv) {
+                    const size_t so_ = (size_t)k * p.E + in.env;
+                    in.pos = p.pos[so_]; in.vel = p.vel[so_]; in.act = io.actions[(size_t)in.env * n + k];
+                }
+                if (k == 0) in.t = p.t[in.env];
+                if (n == 1) in.dist = p.dist_front[in.env];
+            }
+        }
+        return in;
+    };
+    const int ngroups = (p.E + CAR_ENVS_PER_CTA - 1) / CAR_ENVS_PER_CTA;
+    In cur = fetch(blockIdx.x < ngroups ? (int)blockIdx.x : 0);
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int grp_next = grp + (int)gridDim.x;
+    const In nxt = fetch(grp_next < ngroups ? grp_next : grp);
+    const bool live = cur.live;
+    const int env = cur.env;
     const size_t so = (size_t)k * p.E + env;
-    // every input of the step is requested before the first of them is looked at (one memory round trip, not two)
-    const uint32_t meta0 = live ? p.meta[env] : 0u;
-    uint32_t crossed_in = 0u; double theta_in = 0.0, pos_in = 0.0, vel_in = 0.0, dist_in = -1.0; float act_in = 0.0f; int t_in = 0;
-    if (!RESET_ONLY && live) {
-        crossed_in = p.crossed[env]; theta_in = p.theta[env];
-        if (kv) { pos_in = p.pos[so]; vel_in = p.vel[so]; act_in = io.actions[(size_t)env * n + k]; }
-        if (k == 0) t_in = p.t[env];
-        if (n == 1) dist_in = p.dist_front[env];
-    }
+    const uint32_t meta0 = cur.meta;
+    const uint32_t crossed_in = cur.crossed; const double theta_in = cur.theta, pos_in = cur.pos, vel_in = cur.vel, dist_in = cur.dist;
+    const float act_in = cur.act; const int t_in = cur.t;
+    if (!RESET_ONLY || __any_sync(CAR_FULL, live)) {
     const bool doreset = RESET_ONLY ? live : (live && io.auto_reset && ((meta0 >> 16) & 1u));
     const bool stepping = !RESET_ONLY && live && !doreset;
     double x = 0.0, v = 0.0;                            // this car's position / velocity after the step (or the reset)
@@ -354,7 +376,7 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
         const uint32_t lv = __ballot_sync(CAR_FULL, live);
         for (int q = 0; q < 4; q++) {
             if (!((lv >> (8 * q)) & 1u)) continue;                        // (uniform)
-            const int e = (blockIdx.x * CAR_WARPS + warp) * 4 + q;
+            const int e = (grp * CAR_WARPS + warp) * 4 + q;
             double* dst = io.obs + (size_t)e * nD;
             const double* src = w_stage + (size_t)q * nD;
             if ((nD & 1) == 0) {                                           // 16-byte aligned runs
@@ -363,6 +385,10 @@ __global__ void __launch_bounds__(CAR_THREADS, CAR_MIN_BLOCKS) car_kernel(const 
                 for (int f = lane; f < nD; f += 32) dst[f] = src[f];
             }
         }
+    }
+    }
+    cur = nxt;
+    __syncwarp();                                       // the warp's staging area is rewritten by the next round
     }
 }
 
