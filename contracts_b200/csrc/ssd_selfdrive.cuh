@@ -99,16 +99,18 @@ __device__ __noinline__ void car_update_infos(const CarParams& p, const double* 
 __device__ __noinline__ void car_make_consistent(double* o_eff, uint32_t active_m, uint32_t vmask, uint32_t& crossed, int& n_crossed)
 {
     uint32_t pre = 0u;
-    bool moved = false;
-    for (int i = __ffs(vmask) - 1; i + 1 < n_crossed; i++) {
-        if (!moved && !((vmask >> i) & 1u)) continue;
+    int i = __ffs(vmask) - 1;
+    while (i >= 0 && i + 1 < n_crossed) {
         const int f = (int)((crossed >> (4 * i)) & 15u), b = (int)((crossed >> (4 * i + 4)) & 15u);
         const double pf = o_eff[f], pb = o_eff[b];
-        moved = pf < pb && ((active_m >> f) & (active_m >> b) & 1u);
-        if (moved) {
+        if (pf < pb && ((active_m >> f) & (active_m >> b) & 1u)) {
             const double nb = __dsub_rn(pf, 0.01);
             o_eff[b] = nb;
             if (nb < 0) pre |= 1u << b;
+            i++;                                                           // its front car has moved: the next pair needs a look
+        } else {
+            vmask &= ~((2u << i) - 1u);                                    // on to the next pair that was inconsistent to begin with
+            i = __ffs(vmask) - 1;
         }
     }
     if (pre) {
