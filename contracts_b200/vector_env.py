@@ -114,3 +114,116 @@ class SSDVectorEnv:
 
     def stop(self):
         self.batch.close()
+
+
+class _ArrayVectorEnv:
+    """poll_arrays() / send_action_array() / try_reset() over a feature-env or selfdrive batch (same contract as
+    `SSDVectorEnv`: one host -> device copy per send, one packed device -> host copy per poll, resets requested between two
+    polls run as one masked device reset and show up as `fresh` envs in the next poll)."""
+
+    def _setup(self, batch, action_dtype, idle_action):
+        self.batch = batch
+        self.num_envs, self.num_agents = batch.E, batch.n
+        self.agent_ids = ["a%d" % i for i in range(self.num_agents)]
+        self._idle = idle_action
+        self._actions_host = torch.full((self.num_envs, self.num_agents), idle_action, dtype=action_dtype).pin_memory()
+        self._actions_dev = torch.empty_like(self._actions_host, device=batch.device)
+        self._pending_reset = np.zeros(self.num_envs, dtype=np.uint8)
+        self._stepped = False
+        batch.reset()
+        self._fresh = np.ones(self.num_envs, dtype=bool)
+        self._fields = [("obs", batch.obs), ("rew", batch.rew), ("done", batch.done)]
+        self._packed = torch.empty((sum(t.numel() * t.element_size() for _, t in self._fields) + 8 * self.num_envs,),
+                                   dtype=torch.uint8).pin_memory()
+
+    def send_action_array(self, actions_host):
+        if not torch.is_tensor(actions_host):
+            self._actions_host.numpy()[:] = actions_host
+            actions_host = self._actions_host
+        self._flush_resets()
+        self._actions_dev.copy_(actions_host, non_blocking=True)
+        self.batch.step(self._actions_dev, extras=False)
+        self._stepped = True
+        self._fresh[:] = False
+
+    def try_reset(self, env_id):
+        self._pending_reset[env_id] = 1
+        return None
+
+    def _flush_resets(self):
+        if self._pending_reset.any():
+            self.batch.reset(torch.from_numpy(self._pending_reset).to(self.batch.device))
+            self._fresh = self._pending_reset.astype(bool)
+            self._pending_reset[:] = 0
+            self._stepped = False
+
+    def poll_arrays(self):
+        """-> numpy arrays of all E envs from ONE device -> host copy: obs float64 [E, n, F], rew float64 [E, n], done uint8
+        (features: [E]; selfdrive: [E, n + 1]), theta float64 [E], fresh bool [E] (just reset: rew / done are void)."""
+        self._flush_resets()
+        theta = self.batch.get_state()["theta"]
+        parts = [t.reshape(-1).view(torch.uint8) for _, t in self._fields] + [theta.reshape(-1).view(torch.uint8)]
+        self._packed.copy_(torch.cat(parts), non_blocking=False)
+        buf, off, out = self._packed.numpy(), 0, {}
+        for name, t in self._fields + [("theta", theta)]:
+            nbytes = t.numel() * t.element_size()
+            dt = {torch.float64: np.float64, torch.uint8: np.uint8}[t.dtype]
+            out[name] = buf[off:off + nbytes].view(dt).reshape(tuple(t.shape)).copy()
+            off += nbytes
+        out["fresh"] = self._fresh.copy()
+        if not self._stepped:
+            out["rew"] = np.zeros_like(out["rew"]); out["done"] = np.zeros_like(out["done"])
+        return out
+
+    def get_sub_environments(self):
+        return []
+
+    def stop(self):
+        self.batch.close()
+
+
+class SSDFeatureVectorEnv(_ArrayVectorEnv):
+    """E CleanupFeatures / HarvestFeatures envs ('cleanup' / 'harvest') behind one rollout worker; `poll()` returns the flat
+    observations of the non-convolutional wrapper, features ++ [theta, 0] (two_stage_train.py:104-121)."""
+
+    def __init__(self, kind, num_envs, num_agents, contract=None, horizon=1000, seed=73907, first_env_id=0, device=None,
+                 ascii_map=None):
+        from .features import BatchedFeatureEnv
+        self.contract = contract
+        self._setup(BatchedFeatureEnv(kind, num_envs, num_agents, ascii_map=ascii_map, horizon=horizon, contract=contract,
+                                      seed=seed, first_env_id=first_env_id, device=device), torch.uint8, 4)
+
+    def send_actions(self, action_dict):
+        a = self._actions_host.numpy()
+        a[:] = self._idle
+        for e, acts in action_dict.items():
+            for k, v in acts.items():
+                a[e, int(k[1:])] = int(v)
+        self.send_action_array(self._actions_host)
+
+    def poll(self):
+        s = self.poll_arrays()
+        obs, rews, dones, infos = {}, {}, {}, {}
+        for e in range(self.num_envs):
+            if not self._stepped and not s["fresh"][e]:
+                continue
+            tail = np.array([s["theta"][e], 0.0])
+            obs[e] = {k: (np.concatenate((s["obs"][e, i], tail)) if self.contract else s["obs"][e, i].copy()) for i, k in enumerate(self.agent_ids)}
+            if s["fresh"][e]:
+                continue
+            rews[e] = {k: np.float64(s["rew"][e, i]) for i, k in enumerate(self.agent_ids)}
+            dn = bool(s["done"][e])
+            dones[e] = {"__all__": dn, "a0": dn, "a1": dn}
+            infos[e] = {k: {} for k in self.agent_ids}
+        return obs, rews, dones, infos, {}
+
+
+class SSDCarVectorEnv(_ArrayVectorEnv):
+    """E SelfAcceleratingCarEnv envs behind one rollout worker (arrays only: float32 accelerations [E, n] in; cars that are
+    done are flagged in done[:, k] and their actions are ignored)."""
+
+    def __init__(self, num_envs, num_agents, contract=None, seed=73907, first_env_id=0, device=None, **batch_kwargs):
+        from .selfdrive import BatchedCarEnv
+        self.contract = contract
+        self._setup(BatchedCarEnv(num_envs, num_agents, contract=contract, seed=seed, first_env_id=first_env_id, device=device,
+                                  **batch_kwargs), torch.float32, 0.0)
