@@ -569,7 +569,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * E * n * Ke / (float(e2e_ms.item()) * 1e-3)
     rec_mean = float(np.mean([r.count for r in res]))
-    d2h = int(lay.records_offset + min(lay.record_capacity, 2 * rec_mean + 1024) * lay.record_bytes)
+    d2h = int(lay.records_offset + min(lay.record_capacity, 1.25 * rec_mean + 1024) * lay.record_bytes)      # the prefix ssd_step_host_async sends
     h2d = E * n * host_actions[0].element_size()
     # informational: also ship the observations to the host (PCIe-bound by construction)
     obs_to_host = None

@@ -901,8 +901,10 @@ static int copy_rewards(ssd_handle* h, const StepIO& k, cudaStream_t s, const Ho
     if (!hc) return SSD_OK;
     if (hc->slot >= 0) {
         ssd_handle::Slot& sl = h->slot[hc->slot];
-        // the record prefix that travels: twice the recent maximum (+ slack); ssd_step_host_wait fetches a remainder
-        uint32_t want = 2u * std::max(h->recent_count[0], h->recent_count[1]) + 1024u;
+        // the record prefix that travels: the recent maximum + 25 % + 1024 (the count of a large batch is a sum of many
+        // independent envs: tens of standard deviations); ssd_step_host_wait fetches a remainder on a miss
+        const uint32_t recent = std::max(h->recent_count[0], h->recent_count[1]);
+        uint32_t want = recent + recent / 4u + 1024u;
         if (want > (uint32_t)h->lay.record_capacity) want = (uint32_t)h->lay.record_capacity;
         sl.copied_records = want;
         CUDA_TRY(h, cudaEventRecord(sl.ev_rew, s));
