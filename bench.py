@@ -211,30 +211,42 @@ def run_reference(config, steps, warmup):
     return {"value": rate, "unit": "agent-steps/s", "cores": procs, "kind": "reference", "ms_per_env_step": ms, "sample": sample}
 
 
-def cpu_arms(config, cfg, ref_steps=150, port_steps=150):
-    ref = run_reference(config, ref_steps, 5)
+def cpu_arms(config, cfg, ref_steps=150, port_steps=150, ref_warmup=5):
+    ref = run_reference(config, ref_steps, ref_warmup)
     port = run_port(cfg, 64, port_steps, 20)
     return ref, port
 
 
+REF_ENV_STEPS_PER_STEP = 8
+
+
 def reference_arm(args):
+    """`--impl reference`: EXACTLY --steps K timed steps after --warmup W untimed ones.  One step of this arm is a bounded
+    sample of the workload: every one of the P one-env processes advances its env by R env steps (R = 8; fewer for a very
+    large K so that the run stays within minutes at ~1-2 ms per reference env step)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cfg = CONFIGS[args.config]
-    steps = min(max(args.steps, 100), 300)                  # bounded: ~2 ms per env step per process
-    warm = min(max(args.warmup, 3), 20)
-    ref, port = cpu_arms(args.config, cfg, steps, min(max(args.steps, 20), 300))
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    R = max(1, min(REF_ENV_STEPS_PER_STEP, 40000 // steps))
+    ref = run_reference(args.config, steps * R, warm * R)
+    # the C restatement: reported beside the reference on a bounded sample; the timed arm itself (exactly K steps) only
+    # where no reference tree was staged
+    port = run_port(cfg, 64, min(max(steps, 20), 300), 20) if ref is not None else run_port(cfg, 64, steps, warm)
     main_arm = ref or port
     if main_arm is None:
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref (staged reference) nor a C port for this config"}))
         return
     line = {
         "impl": "reference", "metric": "agent-steps/sec", "value": main_arm["value"], "unit": "agent-steps/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": main_arm.get("ms_per_env_step", main_arm.get("ms_per_step")),
+        "steps": steps, "warmup": warm,
+        "ms_per_step": main_arm["ms_per_env_step"] * R if main_arm is ref else main_arm["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if cfg["family"] == "grid" else "f64",
         "data": "synthetic",
         "config": config_dict(args.config, cfg, args.envs or cfg["envs"], int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": main_arm,
+        "step_definition": "%d env steps in each of the %d one-env processes" % (R, main_arm["cores"]) if main_arm is ref
+                           else "one step of the C restatement's env batch",
         "e2e": {"value": main_arm["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "kind=reference: the unmodified Python reference (staged into oracle/_ref by __graft_entry__.build()), one "
