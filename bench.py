@@ -208,7 +208,11 @@ def run_reference(config, steps, warmup):
     if ref_bench.available() is None:
         return None
     rate, procs, ms, sample = ref_bench.run(config, steps=steps, warmup=warmup)
-    return {"value": rate, "unit": "agent-steps/s", "cores": procs, "kind": "reference", "ms_per_env_step": ms, "sample": sample}
+    out = {"value": rate, "unit": "agent-steps/s", "cores": procs, "kind": "reference", "ms_per_env_step": ms, "sample": sample}
+    if procs > 1:                                            # the one-process figure beside the P-process one
+        r1, _, ms1, _ = ref_bench.run(config, steps=min(steps, 100), warmup=min(warmup, 5), procs=1)
+        out["one_process"] = {"value": r1, "unit": "agent-steps/s", "ms_per_env_step": ms1, "steps": min(steps, 100)}
+    return out
 
 
 def cpu_arms(config, cfg, ref_steps=150, port_steps=150, ref_warmup=5):

@@ -10,12 +10,27 @@ the dict conventions of the reference's wrappers (`{env_id: {agent_id: ...}}`; o
   * finished envs are reset by `try_reset(env_id)` (RLlib calls it after `dones['__all__']`), batched: the resets
     requested between two polls run as one masked device reset.
 Arrays are also available without the dict building through `poll_arrays()` — for samplers that batch the policy
-forward themselves the dict layer is pure overhead (INTEGRATION.md §5 has the measured rates).
+forward themselves the dict layer is pure overhead (INTEGRATION.md §2b has the measured rates).
 """
 import numpy as np
 import torch
 
 from .batched import BatchedGridEnv
+
+
+def _upload(v, actions_host):
+    """one asynchronous host -> device copy of the action matrix; an event marks when the pinned staging buffer may be
+    rewritten (two sends without a poll between them must not race with the copy still reading it)"""
+    v._actions_dev.copy_(actions_host, non_blocking=True)
+    if actions_host is v._actions_host:
+        if v._uploaded is None:
+            v._uploaded = torch.cuda.Event()
+        v._uploaded.record(torch.cuda.current_stream(v.batch.device))
+
+
+def _staging_free(v):
+    if v._uploaded is not None:
+        v._uploaded.synchronize()
 
 
 class SSDVectorEnv:
@@ -28,6 +43,7 @@ class SSDVectorEnv:
         self.one_hot_id = one_hot_id
         self._actions_host = torch.full((self.num_envs, self.num_agents), 4, dtype=torch.uint8).pin_memory()
         self._actions_dev = torch.empty_like(self._actions_host, device=self.batch.device)
+        self._uploaded = None         # event behind the last asynchronous upload out of _actions_host
         self._pending_reset = np.zeros(self.num_envs, dtype=np.uint8)
         self._fresh = None            # envs whose next poll() returns a reset observation (no reward / done yet)
         self._stepped = False
@@ -38,6 +54,7 @@ class SSDVectorEnv:
     # ---- BaseEnv ---------------------------------------------------------------------------------------
     def send_actions(self, action_dict):
         """{env_id: {agent_id: action}}; agents that are absent stay put (action 4), as in the drop-in classes."""
+        _staging_free(self)
         a = self._actions_host.numpy()
         a[:] = 4
         for e, acts in action_dict.items():
@@ -48,10 +65,11 @@ class SSDVectorEnv:
     def send_action_array(self, actions_host):
         """uint8 [E, n] pinned host tensor (or numpy array): one host -> device copy, then the step is enqueued."""
         if not torch.is_tensor(actions_host):
+            _staging_free(self)
             self._actions_host.numpy()[:] = actions_host
             actions_host = self._actions_host
         self._flush_resets()
-        self._actions_dev.copy_(actions_host, non_blocking=True)
+        _upload(self, actions_host)
         self.batch.step(self._actions_dev, extras=False)
         self._stepped = True
         self._fresh[:] = False
@@ -128,6 +146,7 @@ class _ArrayVectorEnv:
         self._idle = idle_action
         self._actions_host = torch.full((self.num_envs, self.num_agents), idle_action, dtype=action_dtype).pin_memory()
         self._actions_dev = torch.empty_like(self._actions_host, device=batch.device)
+        self._uploaded = None
         self._pending_reset = np.zeros(self.num_envs, dtype=np.uint8)
         self._stepped = False
         batch.reset()
@@ -138,10 +157,11 @@ class _ArrayVectorEnv:
 
     def send_action_array(self, actions_host):
         if not torch.is_tensor(actions_host):
+            _staging_free(self)
             self._actions_host.numpy()[:] = actions_host
             actions_host = self._actions_host
         self._flush_resets()
-        self._actions_dev.copy_(actions_host, non_blocking=True)
+        _upload(self, actions_host)
         self.batch.step(self._actions_dev, extras=False)
         self._stepped = True
         self._fresh[:] = False
@@ -194,6 +214,7 @@ class SSDFeatureVectorEnv(_ArrayVectorEnv):
                                       seed=seed, first_env_id=first_env_id, device=device), torch.uint8, 4)
 
     def send_actions(self, action_dict):
+        _staging_free(self)
         a = self._actions_host.numpy()
         a[:] = self._idle
         for e, acts in action_dict.items():
