@@ -197,3 +197,18 @@ class CudaBackend:
 
     def metrics_raw(self):
         return self.env.metrics_raw()[self.i].cpu().numpy()
+
+
+def random_map(rng, kind, n):
+    """A walled H x W map with random interior content: at least n spawn points and one cell of every dynamic kind;
+    inner walls, dead ends and agents packed next to each other make contested moves and blocked beams frequent."""
+    H, W = int(rng.randint(6, 15)), int(rng.randint(6, 15))
+    g = np.full((H, W), "@", dtype="<U1")
+    inner = [(r, c) for r in range(1, H - 1) for c in range(1, W - 1)]
+    rng.shuffle(inner)
+    chars = {"cleanup": (["P", "H", "R", "S", "B", " ", "@"], [.22, .16, .08, .06, .2, .2, .08]),
+             "harvest": (["P", "A", " ", "@"], [.25, .35, .3, .1])}[kind]
+    must = ["P"] * n + (["H", "R", "S", "B"] if kind == "cleanup" else ["A"])
+    for i, (r, c) in enumerate(inner):
+        g[r, c] = must[i] if i < len(must) else rng.choice(chars[0], p=chars[1])
+    return ["".join(row) for row in g]

@@ -162,3 +162,42 @@ def test_soak_many_envs_matches_oracle(oracle_lib, kind, amap_name, n, nact):
             for k in ("map", "pos", "ori"):
                 gu.assert_same(k, sc[k].cpu().numpy(), so[k], ctx)
     gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "end")
+
+
+@pytest.mark.parametrize("kind", ["cleanup", "harvest"])
+def test_random_maps_match_oracle(oracle_lib, kind):
+    """Maps nobody drew by hand (golden_util.random_map: 6..14 x 6..14, inner walls, 2..8 agents, at least one cell of every
+    dynamic kind — the same generator pins the oracle to the live reference in test_deep_differential.py): odd row pitches,
+    one-entry point lists, windows that are mostly outside the map, corridors."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    rng = np.random.RandomState(40 + len(kind))
+    nact = 9 if kind == "cleanup" else 8
+    for m in range(10):
+        n = int(rng.randint(2, 9))
+        amap = gu.random_map(rng, kind, n)
+        E, seed, first = 48, 500 + m, 1000 * m
+        orc = oracle_lib.GridOracle(kind, E, n, amap, horizon=40, contract=contract, seed=seed, first_env_id=first)
+        env = BatchedGridEnv(kind + "_new", E, n, amap, horizon=40, contract=contract, seed=seed, first_env_id=first)
+        gu.assert_same("reset obs", env.reset().cpu().numpy(), orc.reset(), "map %d %r reset" % (m, amap))
+        for t in range(60):
+            a = rng.randint(0, nact, size=(E, n))
+            feat = t % 4 == 0
+            o = orc.step(a, want_features=feat)
+            obs, rew, done, info = env.step(torch.as_tensor(a.astype(np.uint8)).cuda(), want_features=feat)
+            ctx = "map %d %r step %d" % (m, amap, t)
+            gu.assert_same("obs", obs.cpu().numpy(), o["obs"], ctx)
+            gu.assert_same("rew", rew.cpu().numpy(), o["rew"], ctx)
+            gu.assert_same("info", info.cpu().numpy()[..., :3], o["info"][..., :3], ctx)
+            gu.assert_same("done", done.cpu().numpy(), o["done"], ctx)
+            if feat:
+                gu.assert_same("feature_obs", env.feature_obs.cpu().numpy(), o["feature_obs"], ctx)
+            if o["done"].any():
+                mask = o["done"].astype(bool)
+                gu.assert_same("reset obs", env.reset(torch.as_tensor(o["done"]).cuda()).cpu().numpy()[mask], orc.reset(o["done"])[mask], ctx)
+        so, sc = orc.get_state(), env.get_state()
+        for k in ("map", "pos", "ori", "t"):
+            gu.assert_same(k, sc[k].cpu().numpy(), so[k], "map %d end" % m)
+        gu.assert_same("metrics", env.metrics_raw().cpu().numpy(), orc.metrics_raw(), "map %d end" % m)
+        env.close()

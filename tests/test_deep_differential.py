@@ -191,3 +191,50 @@ def test_reference_vs_oracle_selfdrive_many_episodes(oracle_lib, n, contract):
             raise AssertionError("episode did not end")
     assert steps_total > 500
     assert (paid > 0) == bool(contract)
+
+
+# ---- random maps: the live reference against the C oracle away from the two stock layouts -----------------------------
+@pytest.mark.parametrize("kind", ["cleanup", "harvest"])
+def test_reference_vs_oracle_random_maps(oracle_lib, kind):
+    """MapEnv on maps it never shipped with (map_env.py:61-170 parses any ascii map): per map the reset, 150 steps and the
+    step-151 state of the LIVE reference against the oracle — map parsing, point-list order, spawn probabilities
+    (cleanup_new.py:351-372 for any waste area), view windows at the border, contested moves in corridors."""
+    from oracle.ref_harness import RefGridEnv
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    maps = int(os.environ.get("SSD_DEEP_MAPS", "6")) * max(1, EPISODES // 2)
+    rng = np.random.RandomState(20 + len(kind))
+    eaten = fired = 0
+    for m in range(maps):
+        n = int(rng.randint(2, 9))
+        amap = gu.random_map(rng, kind, n)
+        seed, env_id = 300 + m, 52000 + 7 * m
+        ref = RefGridEnv(kind, n, seed, env_id, contract=True, ascii_map=amap, horizon=100)
+        orc = oracle_lib.GridOracle(kind, 1, n, amap, horizon=100, contract=contract, seed=seed, first_env_id=env_id)
+        ctx = "%s map %d %r reset" % (kind, m, amap)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"], ctx)
+        st = orc.get_state()
+        for k in ("map", "pos", "ori", "theta"):
+            gu.assert_same("reset " + k, st[k][0], r0[k], ctx)
+        nact = 9 if kind == "cleanup" else 8
+        for t in range(150):
+            if t == 100:                                        # the episode ended at the horizon: second episode
+                r0 = ref.reset()
+                gu.assert_same("re-reset obs", orc.reset()[0], r0["obs"], ctx)
+            a = rng.randint(0, nact, size=n).astype(np.int32)
+            want = ref.step(a)
+            got = orc.step(a[None], want_features=True)
+            ctx = "%s map %d %r step %d" % (kind, m, amap, t + 1)
+            for k in ("obs", "rew", "base_rew", "transfers", "feature_obs"):
+                gu.assert_same(k, got[k][0], want[k], ctx)
+            gu.assert_same("eaten_apples", got["info"][0][:, 0], want["eaten_apples"], ctx)
+            gu.assert_same("info1", got["info"][0][:, 1],
+                           want["cleaned_squares"] if kind == "cleanup" else want["eaten_close_apples"], ctx)
+            assert bool(got["done"][0]) == want["done"], ctx
+            if t % 10 == 0 or t == 149:
+                st = orc.get_state()
+                for k in ("map", "pos", "ori"):
+                    gu.assert_same(k, st[k][0], want[k], ctx)
+            eaten += int(want["eaten_apples"].sum())
+            fired += int((a >= 7).sum())
+    assert fired > 0 and (kind == "cleanup" or eaten > 0)
