@@ -372,7 +372,7 @@ void feat_oracle_step(void* h, const int32_t* acts, double* obs, double* rew, do
 {
     fbatch* b = (fbatch*)h;
     int n = b->n;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (b->E > 1)   /* a one-env batch (the live differential tests) stays on the calling thread */
     for (int i = 0; i < b->E; i++)
         env_step(&b->envs[i], acts + (size_t)i * n, obs + (size_t)i * n * b->F, rew + (size_t)i * n, base_rew + (size_t)i * n,
                  transfers + (size_t)i * n, info + (size_t)i * n * 4, done + i);

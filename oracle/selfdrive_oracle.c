@@ -245,7 +245,7 @@ void car_oracle_step(void* h, const float* acts, double* obs, double* rew, doubl
 {
     car_batch* b = (car_batch*)h;
     int n = b->n, D = obs_dim(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (b->E > 1)   /* a one-env batch (the live differential tests) stays on the calling thread */
     for (int i = 0; i < b->E; i++)
         env_step(&b->envs[i], acts + (size_t)i * n, obs + (size_t)i * n * D, rew + (size_t)i * n, base_rew + (size_t)i * n,
                  transfers + (size_t)i * n, info + (size_t)i * n * 4, done + (size_t)i * (n + 1));

@@ -824,7 +824,7 @@ void oracle_reset(void* h, const uint8_t* mask, const uint32_t* episode, uint8_t
 {
     batch_t* b = (batch_t*)h;
     size_t ob = (size_t)b->n * OBSW * OBSW * 3;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (b->E > 1)   /* a one-env batch (the live differential tests) stays on the calling thread */
     for (int i = 0; i < b->E; i++) {
         if (mask && !mask[i]) continue;
         env_t* e = &b->envs[i];
@@ -839,7 +839,7 @@ void oracle_step(void* h, const int32_t* actions, uint8_t* obs, double* rew, dou
     batch_t* b = (batch_t*)h;
     int n = b->n;
     size_t ob = (size_t)n * OBSW * OBSW * 3;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (b->E > 1)   /* a one-env batch (the live differential tests) stays on the calling thread */
     for (int i = 0; i < b->E; i++) {
         step_out o;
         o.obs = obs + i * ob; o.rew = rew + (size_t)i * n; o.base_rew = base_rew + (size_t)i * n;
