@@ -1,4 +1,6 @@
 """GPU: CUDA path vs the C oracle on seeded random rollouts (many envs, every output, bit-exact)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -174,7 +176,7 @@ def test_random_maps_match_oracle(oracle_lib, kind):
     contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
     rng = np.random.RandomState(40 + len(kind))
     nact = 9 if kind == "cleanup" else 8
-    for m in range(10):
+    for m in range(int(os.environ.get("SSD_GPU_MAPS", "10"))):
         n = int(rng.randint(2, 9))
         amap = gu.random_map(rng, kind, n)
         E, seed, first = 48, 500 + m, 1000 * m
