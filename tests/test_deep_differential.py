@@ -238,3 +238,44 @@ def test_reference_vs_oracle_random_maps(oracle_lib, kind):
             eaten += int(want["eaten_apples"].sum())
             fired += int((a >= 7).sum())
     assert fired > 0 and (kind == "cleanup" or eaten > 0)
+
+
+# ---- negotiation stage: many live agreement draws ----------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [("cleanup", 2), ("cleanup", 3), ("cleanup", 4), ("cleanup", 8), ("harvest", 4), ("harvest", 5)])
+def test_reference_vs_oracle_negotiation_many_episodes(oracle_lib, kind, n):
+    """SeparateContractNegotiateStage (two_stage_train.py:257-358) of the LIVE reference against the oracle over many
+    episodes with accept probabilities across [0, 1]: the agreement (all agents for n <= 3, two sampled ones of a1.. for
+    n > 3, product of their accept values against one uniform, :266-281), the contract every agent then observes, the summed
+    rewards of the short frozen-policy rollout and the final observation."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefNegotiateEnv
+    episodes = 12 * max(1, EPISODES // 2)
+    horizon, base_horizon = 4, 1000
+    rng = np.random.RandomState(5 * n + len(kind))
+    table = rng.randint(0, 9 if kind == "cleanup" else 8, size=(horizon, n))
+    seed, env_id = 60 + n, 7000 + n
+    ref = RefNegotiateEnv(kind, n, seed, env_id, horizon, base_horizon, table)
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=base_horizon,
+                                contract=contract, seed=seed, first_env_id=env_id)
+    high = 0.2 if kind == "cleanup" else 10.0
+    outcomes = set()
+    for ep in range(episodes):
+        ctx = "%s n=%d episode %d" % (kind, n, ep)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"], ctx)
+        acts = np.stack([rng.uniform(0, high, size=n), rng.uniform(0.3, 1.0, size=n) ** (1.0 / max(1, min(n - 1, 2)))], axis=1)
+        s2 = ref.step(acts)
+        s3 = ref.step(acts)
+        assert not s2["done"] and s3["done"], ctx
+        dec = orc.negotiate(acts[0, 0], acts[:, 1])
+        gu.assert_same("accepted", dec[0], s3["accepted"], ctx)
+        gu.assert_same("theta", orc.get_state()["theta"][0], s3["contract_obs"][0, 0], ctx)
+        total = np.zeros(n)
+        for t in range(horizon):
+            r = orc.step(table[t][None], want_features=False)
+            total = total + r["rew"][0]
+        gu.assert_same("summed rewards", total, s3["rew"], ctx)
+        gu.assert_same("final obs", r["obs"][0], s3["obs"], ctx)
+        outcomes.add(int(s3["accepted"]))
+    assert outcomes == {0, 1}, "both outcomes must occur: %r" % (outcomes,)
