@@ -279,3 +279,41 @@ def test_reference_vs_oracle_negotiation_many_episodes(oracle_lib, kind, n):
         gu.assert_same("final obs", r["obs"][0], s3["obs"], ctx)
         outcomes.add(int(s3["accepted"]))
     assert outcomes == {0, 1}, "both outcomes must occur: %r" % (outcomes,)
+
+
+# ---- NegotiationSolver: many live candidate draws and decisions -----------------------------------------------------
+@pytest.mark.parametrize("kind,n,S,rule", [("cleanup", 2, 5, "max"), ("cleanup", 4, 20, "majority"), ("cleanup", 8, 50, "majority"),
+                                           ("harvest", 4, 20, "max"), ("harvest", 8, 7, "majority")])
+def test_reference_vs_oracle_solver_many_episodes(oracle_lib, kind, n, S, rule):
+    """NegotiationSolver.negotiate / compute_best_param (two_stage_train.py:705-776) of the LIVE reference (scripted value
+    function, oracle/scripted.py) against the oracle's restatement: the 1 + S candidate contracts of every episode, the
+    chosen contract under the configured rule, and three contract-wrapped steps."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefSolverEnv
+    episodes = 10 * max(1, EPISODES // 2)
+    seed, env_id = 80 + n + S, 9000 + 3 * n
+    ref = RefSolverEnv(kind, n, seed, env_id, S, rule, horizon=50)
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=50, contract=contract,
+                                seed=seed, first_env_id=env_id)
+    high = float(np.float32(0.2)) if kind == "cleanup" else float(np.float32(10.0))
+    rng = np.random.RandomState(n + S)
+    chosen = set()
+    for ep in range(episodes):
+        ctx = "%s n=%d S=%d %s episode %d" % (kind, n, S, rule, ep)
+        r0 = ref.reset()
+        gu.assert_same("reset obs", orc.reset()[0], r0["obs"], ctx)
+        params = oracle_lib.solver_candidates(seed, env_id, ep, 0.0, high, S)
+        gu.assert_same("candidates", params, r0["params"], ctx)
+        theta, idx = oracle_lib.solver_choose(params, r0["vals"], rule)
+        gu.assert_same("theta", theta, r0["theta"], ctx)
+        chosen.add(int(idx))
+        orc.set_theta(theta)
+        for t in range(3):
+            a = rng.randint(0, 9 if kind == "cleanup" else 8, size=n).astype(np.int32)
+            want = ref.step(a)
+            got = orc.step(a[None], want_features=False)
+            gu.assert_same("obs", got["obs"][0], want["obs"], ctx)
+            gu.assert_same("rew", got["rew"][0], want["rew"], ctx)
+            gu.assert_same("contract obs", np.array([theta, 0.0]), want["contract_obs"][0], ctx)
+    assert len(chosen) > 1, "the decision never varied: %r" % (chosen,)
