@@ -317,3 +317,64 @@ def test_reference_vs_oracle_solver_many_episodes(oracle_lib, kind, n, S, rule):
             gu.assert_same("rew", got["rew"][0], want["rew"], ctx)
             gu.assert_same("contract obs", np.array([theta, 0.0]), want["contract_obs"][0], ctx)
     assert len(chosen) > 1, "the decision never varied: %r" % (chosen,)
+
+
+# ---- JointEnv layouts and rendered frames, live -------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,mode", [("cleanup", 2, "global"), ("cleanup", 8, "concatenated"), ("harvest", 4, "global"),
+                                         ("harvest", 5, "concatenated")])
+def test_reference_vs_oracle_joint_env_episodes(oracle_lib, kind, n, mode):
+    """JointEnv (two_stage_train.py:476-617) of the LIVE reference against the oracle: the global map / the channel-
+    concatenated windows, the summed reward, done, and the infos summed key by key, over whole short episodes + re-resets."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefJointEnv
+    horizon = 120
+    seed, env_id = 40 + n, 3000 + n
+    ref = RefJointEnv(kind, n, seed, env_id, mode, horizon=horizon)
+    orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=horizon, contract=None,
+                                seed=seed, first_env_id=env_id)
+    rng = np.random.RandomState(3 * n + len(mode))
+    view = (lambda obs: orc.global_view()[0]) if mode == "global" else (lambda obs: oracle_lib.concatenated_obs(obs)[0])
+    for ep in range(max(2, EPISODES)):
+        gu.assert_same("reset obs", view(orc.reset()), ref.reset(), "%s %s episode %d reset" % (kind, mode, ep))
+        for t in range(horizon):
+            ctx = "%s n=%d %s episode %d step %d" % (kind, n, mode, ep, t + 1)
+            a = rng.randint(0, 9 if kind == "cleanup" else 8, size=n).astype(np.int32)
+            want = ref.step(a)
+            o = orc.step(a[None], want_features=True)
+            gu.assert_same("obs", view(o["obs"]), want["obs"], ctx)
+            rew = 0
+            for r in o["rew"][0]:                                  # sum(env_rews.values()) in agent order (:592)
+                rew = rew + r
+            gu.assert_same("rew", np.float64(rew), want["rew"], ctx)
+            assert bool(o["done"][0]) == want["done"] == (t == horizon - 1), ctx
+            gu.assert_same("eaten_apples", int(o["info"][0, :, 0].sum()), want["eaten_apples"], ctx)
+            gu.assert_same("info1", int(o["info"][0, :, 1].sum()), want["info1"], ctx)
+            feat = 0
+            for i in range(n):
+                feat = feat + o["feature_obs"][0, i]
+            gu.assert_same("feature_obs", feat, want["feature_obs"], ctx)
+
+
+@pytest.mark.parametrize("kind,n", [("cleanup", 8), ("harvest", 6)])
+def test_reference_vs_oracle_rendered_frames(oracle_lib, kind, n):
+    """render(mode='rgb_array') = full_map_to_colors with the beams of the last step (map_env.py:354-392,460-475), every
+    frame of a firing-heavy rollout on the stock map."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefGridEnv
+    seed, env_id = 90 + n, 6100 + n
+    probs = [.1, .1, .1, .1, .05, .1, .1, .2, .15] if kind == "cleanup" else [.12, .12, .12, .12, .06, .1, .1, .26]
+    ref = RefGridEnv(kind, n, seed, env_id, contract=False, horizon=1000, disable_firing=False)
+    orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=1000, seed=seed,
+                                first_env_id=env_id)
+    rng = np.random.RandomState(n)
+    ref.reset(); orc.reset()
+    gu.assert_same("reset frame", orc.render()[0], np.asarray(ref.base.render(mode="rgb_array"), dtype=np.uint8), "reset")
+    beams = 0
+    for t in range(150 * max(1, EPISODES // 2)):
+        a = rng.choice(len(probs), size=n, p=probs).astype(np.int32)
+        ref.step(a)
+        orc.step(a[None], want_features=False)
+        want = np.asarray(ref.base.render(mode="rgb_array"), dtype=np.uint8)
+        gu.assert_same("frame", orc.render()[0], want, "%s n=%d step %d" % (kind, n, t + 1))
+        beams += int(((want == (255, 255, 0)).all(-1) | (want == (100, 255, 255)).all(-1)).sum())
+    assert beams > 100
