@@ -378,3 +378,43 @@ def test_reference_vs_oracle_rendered_frames(oracle_lib, kind, n):
         gu.assert_same("frame", orc.render()[0], want, "%s n=%d step %d" % (kind, n, t + 1))
         beams += int(((want == (255, 255, 0)).all(-1) | (want == (100, 255, 255)).all(-1)).sum())
     assert beams > 100
+
+
+# ---- reward shaping over whole episodes ------------------------------------------------------------------------------
+SHAPED = [("cleanup", 8, dict(use_collective_reward=True)),
+          ("cleanup", 5, dict(inequity_averse_reward=True, alpha=5.0, beta=0.05)),
+          ("harvest", 4, dict(use_collective_reward=True, inequity_averse_reward=True, alpha=-0.7, beta=0.9)),
+          ("harvest", 8, dict(inequity_averse_reward=True, alpha=0.3, beta=-1.1))]
+
+
+@pytest.mark.parametrize("kind,n,shaping", SHAPED, ids=["%s_n%d_%s" % (k, n, "+".join(sorted(s)[:2])) for k, n, s in SHAPED])
+def test_reference_vs_oracle_shaped_rewards_full_episodes(oracle_lib, kind, n, shaping):
+    """use_collective_reward / inequity_averse_reward (map_env.py:289-301) with the contract wrapper on top, whole 400-step
+    episodes + re-reset: the float64 shaped rewards, the transfers computed from them, and the episode metrics."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle.ref_harness import RefGridEnv
+    horizon = 400
+    seed, env_id = 120 + n, 8800 + n
+    contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+    ref = RefGridEnv(kind, n, seed, env_id, contract=True, horizon=horizon, **shaping)
+    orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=horizon, contract=contract,
+                                seed=seed, first_env_id=env_id, **shaping)
+    rng = np.random.RandomState(n)
+    probs = [.12, .12, .12, .12, .02, .05, .05, .38, .02] if kind == "cleanup" else None
+    nact = 9 if kind == "cleanup" else 8
+    nonint = 0
+    for ep in range(max(2, EPISODES)):
+        gu.assert_same("reset obs", orc.reset()[0], ref.reset()["obs"], "%s n=%d episode %d reset" % (kind, n, ep))
+        for t in range(horizon):
+            a = rng.choice(nact, size=n, p=probs).astype(np.int32)
+            want = ref.step(a)
+            got = orc.step(a[None], want_features=False)
+            ctx = "%s n=%d %r episode %d step %d" % (kind, n, shaping, ep, t + 1)
+            for k in ("obs", "rew", "base_rew", "transfers"):
+                gu.assert_same(k, got[k][0], want[k], ctx)
+            assert bool(got["done"][0]) == want["done"], ctx
+            nonint += int((want["base_rew"] != np.rint(want["base_rew"])).sum())
+        gu.check_episode_metrics(kind, n, True, orc.metrics_raw()[0], ref.metrics(), "%s n=%d episode %d end" % (kind, n, ep))
+    if shaping.get("inequity_averse_reward") and not shaping.get("use_collective_reward"):
+        # (after the collective reward every agent holds the same sum, so the inequity terms vanish, map_env.py:289-301)
+        assert nonint > 0, "the shaping never produced a fractional reward"
