@@ -418,3 +418,50 @@ def test_reference_vs_oracle_shaped_rewards_full_episodes(oracle_lib, kind, n, s
     if shaping.get("inequity_averse_reward") and not shaping.get("use_collective_reward"):
         # (after the collective reward every agent holds the same sum, so the inequity terms vanish, map_env.py:289-301)
         assert nonint > 0, "the shaping never produced a fractional reward"
+
+
+# ---- null contracts ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family,kind,n", [("grid", "cleanup", 4), ("grid", "harvest", 3), ("feat", "cleanup", 5), ("feat", "harvest", 4),
+                                           ("car", None, 6)])
+def test_reference_vs_oracle_null_contract_probability(oracle_lib, family, kind, n):
+    """SeparateContractSubgameStage.reset with null_prob > 0 (two_stage_train.py:159-166): `rand() > null_prob` decides
+    between a uniform contract parameter and the null contract (contract_low); many resets, both branches, and a few
+    steps under each drawn parameter."""
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    from oracle import ref_harness as rh
+    null_prob, seed, env_id = 0.45, 140 + n, 7700 + n
+    if family == "grid":
+        contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+        ref = rh.RefGridEnv(kind, n, seed, env_id, contract=True, null_prob=null_prob, horizon=1000)
+        orc = oracle_lib.GridOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=1000, contract=contract,
+                                    null_prob=null_prob, seed=seed, first_env_id=env_id)
+        theta_of = lambda: orc.get_state()["theta"][0]                       # noqa: E731
+        act = lambda rng: rng.randint(0, 9 if kind == "cleanup" else 8, size=n).astype(np.int32)   # noqa: E731
+    elif family == "feat":
+        contract = "CleanupContract" if kind == "cleanup" else "HarvestFeaturemodLocalContract"
+        ref = rh.RefFeatEnv(kind, n, seed, env_id, contract=True, null_prob=null_prob, horizon=1000)
+        orc = oracle_lib.FeatOracle(kind, 1, n, CLEANUP_MAP if kind == "cleanup" else HARVEST_MAP, horizon=1000, contract=contract,
+                                    null_prob=null_prob, seed=seed, first_env_id=env_id)
+        theta_of = lambda: orc.get_state()["theta"][0]                       # noqa: E731
+        act = lambda rng: rng.randint(0, 8 if kind == "cleanup" else 7, size=n).astype(np.int32)   # noqa: E731
+    else:
+        ref = rh.RefCarEnv(n, seed, env_id, contract=True, null_prob=null_prob)
+        orc = oracle_lib.CarOracle(1, n, contract="SelfdriveContractDistprop", null_prob=null_prob, seed=seed, first_env_id=env_id)
+        theta_of = lambda: orc.get_state()["theta"][0]                       # noqa: E731
+        act = lambda rng: rng.uniform(-0.1, 0.1, size=n).astype(np.float32)  # noqa: E731
+    rng = np.random.RandomState(n)
+    nulls = drawn = 0
+    for ep in range(30 * max(1, EPISODES // 2)):
+        ctx = "%s %s n=%d episode %d" % (family, kind, n, ep)
+        r0 = ref.reset()
+        orc.reset()
+        gu.assert_same("theta", theta_of(), r0["theta"], ctx)
+        nulls += int(r0["theta"] == 0.0)
+        drawn += int(r0["theta"] != 0.0)
+        for t in range(4):
+            a = act(rng)
+            want = ref.step(a)
+            got = orc.step(a[None]) if family != "grid" else orc.step(a[None], want_features=False)
+            gu.assert_same("rew", got["rew"][0], want["rew"], ctx + " step %d" % t)
+            gu.assert_same("transfers", got["transfers"][0], want["transfers"], ctx + " step %d" % t)
+    assert nulls > 3 and drawn > 3, (nulls, drawn)
