@@ -297,3 +297,34 @@ def test_auto_reset_equals_step_reset_negotiate(logic_variant, kind, contract, n
     assert got_a[6] == got_b[6] == resets
     assert np.allclose(got_a, got_b, rtol=1e-12, atol=1e-9)          # float64 atomics: order-dependent in the last bits
     assert np.array_equal(got_a[[0, 3, 6, 7]], got_b[[0, 3, 6, 7]])   # integer-valued statistics are exact
+
+
+@pytest.mark.gpu
+def test_null_contract_probability_matches_oracle(oracle_lib):
+    """null_prob > 0 (SeparateContractSubgameStage.reset, two_stage_train.py:159-166): the null / drawn contract parameter of
+    every env and episode, grid worlds, feature envs and selfdrive, against the oracle (pinned to the live reference by
+    test_deep_differential.py::test_reference_vs_oracle_null_contract_probability)."""
+    import torch
+    from contracts_b200.batched import BatchedGridEnv
+    from contracts_b200.features import BatchedFeatureEnv
+    from contracts_b200.selfdrive import BatchedCarEnv
+    from contracts_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    E, null_prob = 300, 0.45
+    pairs = [
+        (BatchedGridEnv("cleanup_new", E, 4, contract="CleanupContract", null_prob=null_prob, seed=3, first_env_id=9),
+         oracle_lib.GridOracle("cleanup", E, 4, CLEANUP_MAP, contract="CleanupContract", null_prob=null_prob, seed=3, first_env_id=9)),
+        (BatchedFeatureEnv("harvest", E, 5, contract="HarvestFeaturemodLocalContract", null_prob=null_prob, seed=4, first_env_id=2),
+         oracle_lib.FeatOracle("harvest", E, 5, HARVEST_MAP, contract="HarvestFeaturemodLocalContract", null_prob=null_prob, seed=4,
+                               first_env_id=2)),
+        (BatchedCarEnv(E, 6, contract="SelfdriveContractDistprop", null_prob=null_prob, seed=5, first_env_id=1),
+         oracle_lib.CarOracle(E, 6, contract="SelfdriveContractDistprop", null_prob=null_prob, seed=5, first_env_id=1)),
+    ]
+    for env, orc in pairs:
+        for ep in range(3):
+            env.reset(); orc.reset()
+            got, want = env.get_state()["theta"].cpu().numpy(), orc.get_state()["theta"]
+            assert np.array_equal(got.view(np.uint64), np.asarray(want, dtype=np.float64).view(np.uint64)), \
+                "%s episode %d: theta differs from the oracle" % (type(env).__name__, ep)
+            nulls = int((want == 0).sum())
+            assert 0.3 * E < nulls < 0.6 * E, nulls
+        env.close()
