@@ -547,7 +547,8 @@ class RefCarEnv:
     injection.  Done agents stop acting (what RLlib does once a done flag was returned); actions are passed as
     Python floats so that the arithmetic stays float64 under NumPy >= 2 scalar promotion."""
 
-    def __init__(self, num_agents, seed, env_id, contract=True, null_prob=0.0):
+    def __init__(self, num_agents, seed, env_id, contract=True, null_prob=0.0, **env_kwargs):
+        """env_kwargs: low_bound, high_bound, start_vel, start_vel_ambulance (self_driving_car_accelerate.py:19)"""
         install()
         from utils.env_creator_functions import env_creator
         import contract.contract_list as cl
@@ -555,7 +556,7 @@ class RefCarEnv:
         self.ctx = DrawContext(seed, env_id)
         self.episode = -1
         self.keys = ["a%d" % i for i in range(num_agents)]
-        self.base = env_creator("SelfDrive", dict(num_agents=num_agents))
+        self.base = env_creator("SelfDrive", dict(num_agents=num_agents, **env_kwargs))
         self.wrapped = bool(contract)
         if contract:
             c = cl.SelfdriveContractDistprop(num_agents)
