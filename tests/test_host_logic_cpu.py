@@ -169,3 +169,85 @@ def test_random_rollout_negotiate_stage(oracle_device):
     assert all(np.asarray(info[k]["contract_param"]).tolist() == [0.1] for k in obs)
     with pytest.raises(RuntimeError):
         env.step(acts)
+
+
+# ---- feature envs and selfdrive: the same idea over FeatOracle / CarOracle ------------------------------------------------
+class _FlatOracleBatch:
+    """step() -> (obs, rew, done, info) CPU tensors + persistent base_rew / transfers, like BatchedFeatureEnv / BatchedCarEnv"""
+
+    def _finish_init(self, action_dtype):
+        self.device = torch.device("cpu")
+        self._action_dtype = action_dtype
+        self.base_rew = torch.zeros((self.E, self.n), dtype=torch.float64)
+        self.transfers = torch.zeros((self.E, self.n), dtype=torch.float64)
+
+    def reset(self, mask=None):
+        return torch.from_numpy(self.o.reset(None if mask is None else mask.numpy()))
+
+    def step(self, actions, extras=True, auto_reset=False):
+        r = self.o.step(actions.numpy().astype(self._action_dtype))
+        self.base_rew.copy_(torch.from_numpy(r["base_rew"]))
+        self.transfers.copy_(torch.from_numpy(r["transfers"]))
+        return torch.from_numpy(r["obs"]), torch.from_numpy(r["rew"]), torch.from_numpy(r["done"]), torch.from_numpy(np.asarray(r["info"]))
+
+    def get_state(self):
+        return {k: torch.from_numpy(np.asarray(v)) for k, v in self.o.get_state().items()}
+
+    def metrics_raw(self):
+        return torch.from_numpy(self.o.metrics_raw())
+
+    def close(self):
+        pass
+
+
+class OracleFeatBatch(_FlatOracleBatch):
+    def __init__(self, kind, num_envs, num_agents, ascii_map=None, horizon=1000, contract=None, theta_low=0.0, theta_high=None,
+                 null_prob=0.0, seed=73907, first_env_id=0, device=None):
+        from oracle import oracle
+        self.E, self.n = int(num_envs), int(num_agents)
+        self.o = oracle.FeatOracle(kind, self.E, self.n, list(ascii_map), horizon=horizon, contract=contract, theta_low=theta_low,
+                                   theta_high=theta_high, null_prob=null_prob, seed=seed, first_env_id=first_env_id)
+        self._finish_init(np.int32)
+
+
+class OracleCarBatch(_FlatOracleBatch):
+    def __init__(self, num_envs, num_agents, contract=None, low_bound=-10.0, high_bound=10.0, start_vel=0.2, start_vel_ambulance=0.8,
+                 theta_low=0.0, theta_high=100.0, null_prob=0.0, seed=73907, first_env_id=0, device=None):
+        from oracle import oracle
+        self.E, self.n = int(num_envs), int(num_agents)
+        self.o = oracle.CarOracle(self.E, self.n, contract=bool(contract), low_bound=low_bound, high_bound=high_bound,
+                                  start_vel=start_vel, start_vel_ambulance=start_vel_ambulance, theta_low=theta_low,
+                                  theta_high=theta_high, null_prob=null_prob, seed=seed, first_env_id=first_env_id)
+        self._finish_init(np.float32)
+
+
+@pytest.fixture
+def oracle_flat_devices(monkeypatch, oracle_lib):
+    from contracts_b200.environments import feature_envs, self_driving_car_accelerate
+    monkeypatch.setattr(feature_envs, "BatchedFeatureEnv", OracleFeatBatch)
+    monkeypatch.setattr(self_driving_car_accelerate, "BatchedCarEnv", OracleCarBatch)
+
+
+@pytest.mark.parametrize("name", [n for n in gu.fixture_names("features_") if "nocontract" not in n])
+def test_feature_env_dict_api_host_logic(oracle_flat_devices, name):
+    import test_features_golden as T
+    T.test_dropin_feature_env_dict_api(name)
+
+
+@pytest.mark.parametrize("name", [n for n in gu.fixture_names("selfdrive_") if "nocontract" not in n and n != "selfdrive_n1"])
+def test_selfdrive_dict_api_host_logic(oracle_flat_devices, name):
+    import test_selfdrive_golden as T
+    T.test_dropin_selfdrive_dict_api(name)
+
+
+def test_selfdrive_dict_api_rejects_wrong_acting_set(oracle_flat_devices):
+    """the dict must name exactly the live cars (the reference would move only the named ones / crash on a finished one)"""
+    from contracts_b200.utils.env_creator_functions import env_creator
+    env = env_creator("SelfDrive", dict(num_agents=3, seed=1, env_id=2))
+    obs = env.reset()
+    assert sorted(obs) == ["a0", "a1", "a2"]
+    with pytest.raises(ValueError):
+        env.step({"a0": [0.05], "a1": [0.05]})
+    obs, rew, done, info = env.step({k: [0.05] for k in obs})
+    assert set(done) == {"a0", "a1", "a2", "__all__"} and set(info["a0"]) == {"just_passed", "is_crashed", "ambulance_rank",
+                                                                               "ambulance_dist_to_front"}
